@@ -1,0 +1,112 @@
+/* skdist_b200.h -- C-ABI of libskdist_b200.so (hand-written sm_100a CUDA, no torch types).
+ *
+ * This is the drop-in boundary for the hot path of Ibotta/sk-dist (reference v0.1.9):
+ * the per-task fits that skdist.distribute fans out over Spark executors.  The
+ * reference has no FFI (it is pure Python); each entry point below names the Python
+ * call site whose work it replaces ("ref:" = path under the reference tree, "SK/" =
+ * site-packages/sklearn 1.9.0, the third-party code that executes the arithmetic).
+ * INTEGRATION.md shows the ctypes stub a maintainer would add on the reference side.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error; the message is
+ * available from skd_last_error(ctx) (ctx may be NULL for creation failures).  All
+ * pointers are HOST pointers owned by the caller unless the name says `_device`.
+ * A context is bound to one GPU and must be used from one host thread at a time.
+ */
+#ifndef SKDIST_B200_H
+#define SKDIST_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct skd_ctx skd_ctx;
+
+/* Library version (major*10000 + minor*100 + patch). */
+int skd_version(void);
+
+/* Create / destroy a context on CUDA device `device`.
+ * ref: replaces the SparkContext `sc` argument of every Dist* estimator
+ * (skdist/distribute/search.py:309-313). */
+int skd_ctx_create(int device, skd_ctx** out);
+int skd_ctx_destroy(skd_ctx* ctx);
+const char* skd_last_error(skd_ctx* ctx);
+
+/* Number of CUDA devices visible (0 if none / driver missing). */
+int skd_device_count(void);
+
+/* Stage the design matrix once in HBM (fp32, row-major, n rows, d features, leading
+ * dimension ldx >= d in elements).
+ * ref: replaces shipping X in the task closure / sc.broadcast
+ * (skdist/distribute/search.py:414-421, multiclass.py:35-50). */
+int skd_stage_x(skd_ctx* ctx, const float* X, int64_t n, int64_t d, int64_t ldx);
+/* Same, from a DEVICE pointer on ctx's device (e.g. the buffer an NCCL broadcast filled). */
+int skd_stage_x_device(skd_ctx* ctx, const float* dX, int64_t n, int64_t d, int64_t ldx);
+
+/* Stage integer class ids (0..K-1), one per row.  Column j of a batch treats rows with
+ * y_class == col_pos[j] as positive, the rest as negative.
+ * ref: y in the closure (search.py:416-421); LabelBinarizer columns (multiclass.py:289-317). */
+int skd_stage_labels(skd_ctx* ctx, const int32_t* y_class, int64_t n);
+
+/* Stage real-valued targets (regression; Ridge).  ref: same as above. */
+int skd_stage_targets(skd_ctx* ctx, const float* y, int64_t n);
+
+/* Stage the cross-validation layout as one int8 fold id per row (0..n_folds-1; test fold
+ * of the row).  Replaces the per-task (train_idx, test_idx) index arrays and the
+ * X[train]/X[test] copies.  ref: search.py:378-383 (fit_sets), utils.py:171-209 (_safe_split). */
+int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_folds);
+
+/* Batched binary L2 logistic regression (lbfgs), B independent columns sharing X.
+ * Column j: positives = rows with y_class == col_pos[j]; training rows = rows whose fold id
+ * != col_fold[j] (col_fold[j] < 0: all rows); l2 strength = 1 / (C[j] * n_train_j).
+ * Outputs: coef_out[j*(d+1) + k] (k<d weights, k==d intercept, 0 if !fit_intercept),
+ * n_iter_out[j] = min(nit, max_iter), status_out[j] (1,2 converged; 3 max_iter; 4 abnormal
+ * line search; 5 non-finite), loss_out[j] final objective, n_evals_out[j] number of
+ * loss+gradient evaluations, gpu_seconds_out (CUDA-event time of the whole call; may be NULL).
+ * ref: replaces B invocations of search.py:180-288 (_fit_and_score -> estimator.fit,
+ * line 230) / multiclass.py:109-152 (_fit_binary) for LogisticRegression(solver="lbfgs",
+ * penalty="l2"): SK/linear_model/_logistic.py:219-717, SK/linear_model/_linear_loss.py:291-379,
+ * scipy L-BFGS-B with maxiter=max_iter, maxls=50, gtol=tol, ftol=64*eps. */
+int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t* col_fold,
+                         const int32_t* col_pos, int32_t fit_intercept, double tol,
+                         int32_t max_iter, float* coef_out, int32_t* n_iter_out,
+                         int32_t* status_out, double* loss_out, int32_t* n_evals_out,
+                         double* gpu_seconds_out);
+
+/* Accuracy counts of B linear binary classifiers on their held-out rows.
+ * Column j is scored on rows whose fold id == col_fold[j] (col_fold[j] == -2: all rows;
+ * col_fold[j] == -3-f: rows NOT in fold f, i.e. the training rows, for return_train_score);
+ * prediction = (x.w + b > 0) compared with (y_class == col_pos[j]).
+ * ref: replaces search.py:264 (_score -> ClassifierMixin.score -> accuracy_score). */
+int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_t* col_fold,
+                           const int32_t* col_pos, int64_t* correct_out, int64_t* count_out);
+
+/* Decision values out[i*B + j] = X[i,:].coef_j + intercept_j for the staged X (all rows).
+ * ref: estimator.decision_function / predict inside scorers (utils.py:45-72) and
+ * skdist/distribute/predict.py:160-179 (model.predict over row batches). */
+int skd_linear_decision(skd_ctx* ctx, int32_t B, const float* coef, float* out);
+
+/* Which evaluation kernel skd_logreg_fit_batch uses: 0 = auto, 1 = SIMT fp32, 2 = tcgen05
+ * (fp16x2-split, fp32 accumulate).  Returns the previous value. */
+int skd_set_kernel(skd_ctx* ctx, int32_t which);
+
+/* Counters since context creation: kernels launched by this library, bytes H2D, bytes D2H. */
+int skd_get_counters(skd_ctx* ctx, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* Host-side optimiser object exposing the same L-BFGS-B core the device kernels run
+ * (csrc/lbfgs_core.h); used by the CPU tests that pin it against scipy's setulb.
+ * ref: scipy/optimize/_lbfgsb_py.py:393-437 reverse-communication loop. */
+typedef struct skd_lbfgs skd_lbfgs;
+skd_lbfgs* skd_lbfgs_create(int32_t n, int32_t m, int32_t maxiter, int32_t maxls, double pgtol,
+                            double ftol);
+double* skd_lbfgs_x(skd_lbfgs* h);
+double* skd_lbfgs_g(skd_lbfgs* h);
+int skd_lbfgs_advance(skd_lbfgs* h, double f); /* returns status (0 = evaluate at x again) */
+int skd_lbfgs_nit(skd_lbfgs* h);
+int skd_lbfgs_nfev(skd_lbfgs* h);
+void skd_lbfgs_free(skd_lbfgs* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKDIST_B200_H */

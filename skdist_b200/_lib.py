@@ -1,0 +1,92 @@
+"""ctypes binding of libskdist_b200.so (the C-ABI in include/skdist_b200.h).
+
+There is NO CPU fallback: if the library is missing or no B200 is visible the
+calls raise.  The library is built in-tree by ``skdist_b200._build`` /
+``__graft_entry__.build()``.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _build
+
+_c = ctypes
+_LIB = None
+
+
+class SkdError(RuntimeError):
+    pass
+
+
+def _p(dtype):
+    return np.ctypeslib.ndpointer(dtype=dtype, flags="C_CONTIGUOUS")
+
+
+SYMBOLS = {
+    # name: (restype, argtypes)
+    "skd_version": (_c.c_int, []),
+    "skd_device_count": (_c.c_int, []),
+    "skd_ctx_create": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_void_p)]),
+    "skd_ctx_destroy": (_c.c_int, [_c.c_void_p]),
+    "skd_last_error": (_c.c_char_p, [_c.c_void_p]),
+    "skd_stage_x": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int64]),
+    "skd_stage_x_device": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int64]),
+    "skd_stage_labels": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64]),
+    "skd_stage_targets": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64]),
+    "skd_stage_folds": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32]),
+    "skd_logreg_fit_batch": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                        _c.c_int32, _c.c_double, _c.c_int32, _c.c_void_p, _c.c_void_p,
+                                        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_double)]),
+    "skd_linear_score_batch": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                          _c.c_void_p, _c.c_void_p]),
+    "skd_linear_decision": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p]),
+    "skd_set_kernel": (_c.c_int, [_c.c_void_p, _c.c_int32]),
+    "skd_get_counters": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64),
+                                    _c.POINTER(_c.c_int64)]),
+    "skd_lbfgs_create": (_c.c_void_p, [_c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_double,
+                                       _c.c_double]),
+    "skd_lbfgs_x": (_c.POINTER(_c.c_double), [_c.c_void_p]),
+    "skd_lbfgs_g": (_c.POINTER(_c.c_double), [_c.c_void_p]),
+    "skd_lbfgs_advance": (_c.c_int, [_c.c_void_p, _c.c_double]),
+    "skd_lbfgs_nit": (_c.c_int, [_c.c_void_p]),
+    "skd_lbfgs_nfev": (_c.c_int, [_c.c_void_p]),
+    "skd_lbfgs_free": (None, [_c.c_void_p]),
+}
+
+
+def lib_path():
+    return _build.LIBPATH
+
+
+def load(build_if_missing=True):
+    """Load the shared library (building it first if the source is newer)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as e:  # no nvcc on the box: use the prebuilt file if any
+            if not os.path.exists(path):
+                raise SkdError("libskdist_b200.so is missing and could not be built: %s" % e)
+    if not os.path.exists(path):
+        raise SkdError("libskdist_b200.so not found at %s (run __graft_entry__.build())" % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc, ctx=None):
+    if rc != 0:
+        msg = load().skd_last_error(ctx)
+        raise SkdError(msg.decode() if msg else "libskdist_b200 call failed (rc=%d)" % rc)
+
+
+def ptr(a):
+    return a.ctypes.data_as(_c.c_void_p)

@@ -1,0 +1,383 @@
+// api.cu -- the C-ABI declared in include/skdist_b200.h.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "../../include/skdist_b200.h"
+#include "skd_internal.h"
+
+namespace skd {
+static std::mutex g_err_mu;
+static std::string g_err;
+void set_global_error(const std::string& s) {
+  std::lock_guard<std::mutex> l(g_err_mu);
+  g_err = s;
+}
+}  // namespace skd
+
+using namespace skd;
+
+struct skd_ctx {
+  Ctx c;
+};
+
+struct skd_lbfgs {
+  LbfgsScalars s;
+  LbfgsVectors v;
+  std::vector<double> buf;
+};
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+extern "C" {
+
+int skd_version(void) { return 100; }
+
+int skd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* skd_last_error(skd_ctx* ctx) {
+  if (ctx) return ctx->c.err.c_str();
+  std::lock_guard<std::mutex> l(g_err_mu);
+  static thread_local std::string copy;
+  copy = g_err;
+  return copy.c_str();
+}
+
+int skd_ctx_create(int device, skd_ctx** out) {
+  if (!out) return fail(nullptr, "skd_ctx_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, std::string("skd_ctx_create: no CUDA device available (") +
+                             cudaGetErrorString(e) + "); this library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(nullptr, "skd_ctx_create: bad device index");
+  SKD_CUDA(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SKD_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    char b[256];
+    snprintf(b, sizeof(b), "skd_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+             device, prop.major, prop.minor);
+    return fail(nullptr, b);
+  }
+  skd_ctx* h = new skd_ctx();
+  h->c.device = device;
+  h->c.sm_count = prop.multiProcessorCount;
+  SKD_CUDA(nullptr, cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+  *out = h;
+  return 0;
+}
+
+static void free_staged(Ctx& c) {
+  if (c.X) cudaFree(c.X);
+  if (c.ycls) cudaFree(c.ycls);
+  if (c.yreal) cudaFree(c.yreal);
+  if (c.fold) cudaFree(c.fold);
+  c.X = nullptr; c.ycls = nullptr; c.yreal = nullptr; c.fold = nullptr;
+}
+
+int skd_ctx_destroy(skd_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  free_staged(ctx->c);
+  cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+  return 0;
+}
+
+static int stage_x_common(Ctx* c, const float* src, int64_t n, int64_t d, int64_t ldx_src,
+                          cudaMemcpyKind kind) {
+  if (!src || n <= 0 || d <= 0 || ldx_src < d) return fail(c, "skd_stage_x: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  if (c->X) { cudaFree(c->X); c->X = nullptr; }
+  int64_t ldx = round_up(d, 16);
+  SKD_CUDA(c, cudaMalloc((void**)&c->X, (size_t)n * ldx * sizeof(float)));
+  if (ldx != d) SKD_CUDA(c, cudaMemsetAsync(c->X, 0, (size_t)n * ldx * sizeof(float), c->stream));
+  SKD_CUDA(c, cudaMemcpy2DAsync(c->X, ldx * sizeof(float), src, ldx_src * sizeof(float),
+                                d * sizeof(float), n, kind, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n = n; c->d = d; c->ldx = ldx;
+  if (kind == cudaMemcpyHostToDevice) c->h2d += (int64_t)n * d * sizeof(float);
+  return 0;
+}
+
+int skd_stage_x(skd_ctx* ctx, const float* X, int64_t n, int64_t d, int64_t ldx) {
+  if (!ctx) return fail(nullptr, "skd_stage_x: ctx is NULL");
+  return stage_x_common(&ctx->c, X, n, d, ldx, cudaMemcpyHostToDevice);
+}
+
+int skd_stage_x_device(skd_ctx* ctx, const float* dX, int64_t n, int64_t d, int64_t ldx) {
+  if (!ctx) return fail(nullptr, "skd_stage_x_device: ctx is NULL");
+  return stage_x_common(&ctx->c, dX, n, d, ldx, cudaMemcpyDeviceToDevice);
+}
+
+int skd_stage_labels(skd_ctx* ctx, const int32_t* y, int64_t n) {
+  if (!ctx) return fail(nullptr, "skd_stage_labels: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!y || n != c->n) return fail(c, "skd_stage_labels: n does not match the staged X");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  if (c->ycls) { cudaFree(c->ycls); c->ycls = nullptr; }
+  SKD_CUDA(c, cudaMalloc((void**)&c->ycls, (size_t)n * sizeof(int32_t)));
+  SKD_CUDA(c, cudaMemcpyAsync(c->ycls, y, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->h2d += n * (int64_t)sizeof(int32_t);
+  return 0;
+}
+
+int skd_stage_targets(skd_ctx* ctx, const float* y, int64_t n) {
+  if (!ctx) return fail(nullptr, "skd_stage_targets: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!y || n != c->n) return fail(c, "skd_stage_targets: n does not match the staged X");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  if (c->yreal) { cudaFree(c->yreal); c->yreal = nullptr; }
+  SKD_CUDA(c, cudaMalloc((void**)&c->yreal, (size_t)n * sizeof(float)));
+  SKD_CUDA(c, cudaMemcpyAsync(c->yreal, y, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->h2d += n * (int64_t)sizeof(float);
+  return 0;
+}
+
+int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_folds) {
+  if (!ctx) return fail(nullptr, "skd_stage_folds: ctx is NULL");
+  Ctx* c = &ctx->c;
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  if (c->fold) { cudaFree(c->fold); c->fold = nullptr; }
+  c->n_folds = 0;
+  c->fold_count.clear();
+  if (!fold_id) return 0;  // cleared
+  if (n != c->n || n_folds <= 0 || n_folds > 127) return fail(c, "skd_stage_folds: bad arguments");
+  c->fold_count.assign(n_folds, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    int f = fold_id[i];
+    if (f < 0 || f >= n_folds) return fail(c, "skd_stage_folds: fold id out of range");
+    c->fold_count[f] += 1;
+  }
+  SKD_CUDA(c, cudaMalloc((void**)&c->fold, (size_t)n));
+  SKD_CUDA(c, cudaMemcpyAsync(c->fold, fold_id, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_folds = n_folds;
+  c->h2d += n;
+  return 0;
+}
+
+int skd_set_kernel(skd_ctx* ctx, int32_t which) {
+  if (!ctx) return -1;
+  int prev = ctx->c.kernel_choice;
+  ctx->c.kernel_choice = which;
+  return prev;
+}
+
+int skd_get_counters(skd_ctx* ctx, int64_t* launches, int64_t* h2d, int64_t* d2h) {
+  if (!ctx) return fail(nullptr, "skd_get_counters: ctx is NULL");
+  if (launches) *launches = ctx->c.launches;
+  if (h2d) *h2d = ctx->c.h2d;
+  if (d2h) *d2h = ctx->c.d2h;
+  return 0;
+}
+
+int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t* col_fold,
+                         const int32_t* col_pos, int32_t fit_intercept, double tol,
+                         int32_t max_iter, float* coef_out, int32_t* n_iter_out,
+                         int32_t* status_out, double* loss_out, int32_t* n_evals_out,
+                         double* gpu_seconds_out) {
+  if (!ctx) return fail(nullptr, "skd_logreg_fit_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || !c->ycls) return fail(c, "skd_logreg_fit_batch: stage X and labels first");
+  if (B <= 0 || !C || !col_fold || !col_pos || !coef_out || !n_iter_out || !status_out)
+    return fail(c, "skd_logreg_fit_batch: bad arguments");
+  if (max_iter < 1) return fail(c, "skd_logreg_fit_batch: max_iter must be >= 1");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  const int64_t n = c->n, d = c->d, ldx = c->ldx;
+  const int dp = (int)d + 1, m = 10;
+
+  // host-side per-column constants
+  std::vector<double> l2(B), inv_n(B);
+  for (int j = 0; j < B; ++j) {
+    int f = col_fold[j];
+    int64_t ntrain = n;
+    if (f >= 0) {
+      if (!c->fold || f >= c->n_folds) return fail(c, "skd_logreg_fit_batch: col_fold refers to an unstaged fold");
+      ntrain = n - c->fold_count[f];
+    }
+    if (ntrain <= 0) return fail(c, "skd_logreg_fit_batch: empty training set");
+    if (!(C[j] > 0.0)) return fail(c, "skd_logreg_fit_batch: C must be positive");
+    l2[j] = 1.0 / (C[j] * (double)ntrain);  // SK/linear_model/_logistic.py:580
+    inv_n[j] = 1.0 / (double)ntrain;
+  }
+
+  Scratch sx(c);
+  LogregWork w;
+  w.B = B; w.dp = dp;
+  w.vec_stride = (size_t)(5 + 2 * m) * dp + 2 * m;
+  w.ldg = (int)round_up(B, 64);
+  w.nz = 1024;
+  w.cap_sc = (int64_t)4 * c->sm_count * 64 + B + 64;
+  SKD_CUDA(c, sx.alloc(&w.sc, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.vec, (size_t)B * w.vec_stride));
+  SKD_CUDA(c, sx.alloc(&w.l2, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.inv_n, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.col_fold, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.col_pos, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.n_evals, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.slot, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.Wact, (size_t)B * ldx + B));
+  if ((double)n * w.ldg * 4.0 > 120e9)
+    return fail(c, "skd_logreg_fit_batch: batch too large for one call (n * B * 4 bytes > 120 GB); split the batch");
+  SKD_CUDA(c, sx.alloc(&w.G, (size_t)n * w.ldg));
+  SKD_CUDA(c, sx.alloc(&w.lossp, (size_t)w.cap_sc));
+  SKD_CUDA(c, sx.alloc(&w.gsump, (size_t)w.cap_sc));
+  SKD_CUDA(c, sx.alloc(&w.gradp, (size_t)w.cap_sc * ldx));
+  SKD_CUDA(c, sx.alloc(&w.n_act, 1));
+  float* dcoef; int32_t *dniter, *dstatus; double* dloss;
+  SKD_CUDA(c, sx.alloc(&dcoef, (size_t)B * dp));
+  SKD_CUDA(c, sx.alloc(&dniter, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&dstatus, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&dloss, (size_t)B));
+
+  cudaEvent_t e0, e1;
+  SKD_CUDA(c, cudaEventCreate(&e0));
+  SKD_CUDA(c, cudaEventCreate(&e1));
+  SKD_CUDA(c, cudaEventRecord(e0, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(w.l2, l2.data(), B * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(w.inv_n, inv_n.data(), B * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(w.col_fold, col_fold, B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(w.col_pos, col_pos, B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  c->h2d += (int64_t)B * 24;
+
+  if (lbfgs_dev_init(c, w, fit_intercept, tol, max_iter)) return 1;
+  int n_act = B;
+  const long max_rounds = (long)max_iter * 52 + 16;
+  long rounds = 0;
+  while (n_act > 0) {
+    int nz_used = 0;
+    if (simt_eval(c, w, n_act, &nz_used)) return 1;
+    int n_next = 0;
+    if (lbfgs_dev_step(c, w, n_act, nz_used, fit_intercept, &n_next)) return 1;
+    n_act = n_next;
+    if (++rounds > max_rounds) return fail(c, "skd_logreg_fit_batch: round limit exceeded (internal error)");
+  }
+  if (lbfgs_dev_finish(c, w, dcoef, dniter, dstatus, dloss)) return 1;
+  SKD_CUDA(c, cudaMemcpyAsync(coef_out, dcoef, (size_t)B * dp * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(n_iter_out, dniter, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(status_out, dstatus, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (loss_out)
+    SKD_CUDA(c, cudaMemcpyAsync(loss_out, dloss, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (n_evals_out)
+    SKD_CUDA(c, cudaMemcpyAsync(n_evals_out, w.n_evals, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaEventRecord(e1, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->d2h += (int64_t)B * (dp * 4 + 20);
+  float ms = 0.f;
+  SKD_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
+  return 0;
+}
+
+// Pack caller coefficients [B x (d+1)] into the kernel layout: weights [B x ldx] + bias [B].
+static int pack_coef(Ctx* c, Scratch& sx, int B, const float* coef, float** dW) {
+  const int64_t d = c->d, ldx = c->ldx;
+  std::vector<float> h((size_t)B * ldx + B, 0.f);
+  for (int j = 0; j < B; ++j) {
+    memcpy(&h[(size_t)j * ldx], coef + (size_t)j * (d + 1), d * sizeof(float));
+    h[(size_t)B * ldx + j] = coef[(size_t)j * (d + 1) + d];
+  }
+  SKD_CUDA(c, sx.alloc(dW, h.size()));
+  SKD_CUDA(c, cudaMemcpyAsync(*dW, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->h2d += (int64_t)h.size() * 4;
+  return 0;
+}
+
+int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_t* col_fold,
+                           const int32_t* col_pos, int64_t* correct_out, int64_t* count_out) {
+  if (!ctx) return fail(nullptr, "skd_linear_score_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || !c->ycls) return fail(c, "skd_linear_score_batch: stage X and labels first");
+  if (B <= 0 || !coef || !col_fold || !col_pos || !correct_out || !count_out)
+    return fail(c, "skd_linear_score_batch: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  Scratch sx(c);
+  float* dW;
+  if (pack_coef(c, sx, B, coef, &dW)) return 1;
+  std::vector<SlotMeta> hs(B);
+  for (int j = 0; j < B; ++j) {
+    int f = col_fold[j] >= 0 ? col_fold[j] : (col_fold[j] <= -3 ? -3 - col_fold[j] : -1);
+    if (col_fold[j] == -1) return fail(c, "skd_linear_score_batch: col_fold -1 is not a scoring code");
+    if (f >= 0 && (!c->fold || f >= c->n_folds))
+      return fail(c, "skd_linear_score_batch: col_fold refers to an unstaged fold");
+    hs[j].col = j; hs[j].fold = col_fold[j]; hs[j].pos = col_pos[j]; hs[j].pad = 0;
+  }
+  SlotMeta* dslot; int64_t *dcorrect, *dcount;
+  SKD_CUDA(c, sx.alloc(&dslot, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&dcorrect, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&dcount, (size_t)B));
+  SKD_CUDA(c, cudaMemcpyAsync(dslot, hs.data(), B * sizeof(SlotMeta), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemsetAsync(dcorrect, 0, B * sizeof(int64_t), c->stream));
+  SKD_CUDA(c, cudaMemsetAsync(dcount, 0, B * sizeof(int64_t), c->stream));
+  if (simt_score(c, B, dW, dslot, dcorrect, dcount)) return 1;
+  SKD_CUDA(c, cudaMemcpyAsync(correct_out, dcorrect, B * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(count_out, dcount, B * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->d2h += (int64_t)B * 16;
+  return 0;
+}
+
+int skd_linear_decision(skd_ctx* ctx, int32_t B, const float* coef, float* out) {
+  if (!ctx) return fail(nullptr, "skd_linear_decision: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X) return fail(c, "skd_linear_decision: stage X first");
+  if (B <= 0 || !coef || !out) return fail(c, "skd_linear_decision: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  Scratch sx(c);
+  float *dW, *dout;
+  if (pack_coef(c, sx, B, coef, &dW)) return 1;
+  SKD_CUDA(c, sx.alloc(&dout, (size_t)c->n * B));
+  if (simt_decision(c, B, dW, dout)) return 1;
+  SKD_CUDA(c, cudaMemcpyAsync(out, dout, (size_t)c->n * B * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->d2h += (int64_t)c->n * B * 4;
+  return 0;
+}
+
+// ---- host-side L-BFGS object (tests) ----------------------------------------------------
+skd_lbfgs* skd_lbfgs_create(int32_t n, int32_t m, int32_t maxiter, int32_t maxls, double pgtol,
+                            double ftol) {
+  skd_lbfgs* h = new skd_lbfgs();
+  lbfgs_init(h->s, n, m, maxiter, maxls, pgtol, ftol);
+  h->buf.assign((size_t)5 * n + 2 * (size_t)m * n + 2 * m, 0.0);
+  double* p = h->buf.data();
+  h->v.x = p; p += n;
+  h->v.g = p; p += n;
+  h->v.t = p; p += n;
+  h->v.r = p; p += n;
+  h->v.d = p; p += n;
+  h->v.S = p; p += (size_t)m * n;
+  h->v.Y = p; p += (size_t)m * n;
+  h->v.rho = p; p += m;
+  h->v.alpha = p;
+  return h;
+}
+double* skd_lbfgs_x(skd_lbfgs* h) { return h->v.x; }
+double* skd_lbfgs_g(skd_lbfgs* h) { return h->v.g; }
+int skd_lbfgs_advance(skd_lbfgs* h, double f) {
+  SeqPar P;
+  lbfgs_advance(P, h->s, h->v, f);
+  return h->s.status;
+}
+int skd_lbfgs_nit(skd_lbfgs* h) { return h->s.nit; }
+int skd_lbfgs_nfev(skd_lbfgs* h) { return h->s.nfev; }
+void skd_lbfgs_free(skd_lbfgs* h) { delete h; }
+
+}  // extern "C"

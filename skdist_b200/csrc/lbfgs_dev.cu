@@ -1,0 +1,241 @@
+// lbfgs_dev.cu -- device-resident batched L-BFGS-B driver: one CTA per active column.
+//
+// Replaces the host loop scipy/optimize/_lbfgsb_py.py:406-437 (setulb reverse communication)
+// that each of the reference's tasks runs inside estimator.fit (ref search.py:230); the
+// optimiser arithmetic is csrc/lbfgs_core.h.  Per round:
+//   lb_step_kernel    : gather the slot's partial sums -> f, g (float64, adds the L2 term as
+//                       SK/linear_model/_linear_loss.py:350,356-361), advance the state machine
+//   lb_compact_kernel : rebuild the list of still-running columns (stable order)
+//   lb_export_kernel  : cast the new trial points to fp32 (SK/_linear_loss.py:216-217) into the
+//                       active-slot weight matrix for the next evaluation
+#include "skd_internal.h"
+
+namespace skd {
+
+constexpr int LB_THREADS = 128;
+
+struct CtaPar {
+  double* red;  // shared, >= 4 doubles
+  __device__ __forceinline__ int tid() const { return threadIdx.x; }
+  __device__ __forceinline__ int nthr() const { return LB_THREADS; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+  __device__ __forceinline__ double block_sum(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();  // protect red from the previous reduction's readers
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return (red[0] + red[1]) + (red[2] + red[3]);
+  }
+  __device__ __forceinline__ double dot(const double* a, const double* b, int n) const {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += LB_THREADS) acc += a[i] * b[i];
+    return block_sum(acc);
+  }
+  __device__ __forceinline__ double amax(const double* a, int n) const {
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += LB_THREADS) m = fmax(m, fabs(a[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    return fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+  }
+};
+
+__device__ __forceinline__ LbfgsVectors col_vectors(double* base, int n, int m) {
+  LbfgsVectors v;
+  double* p = base;
+  v.x = p; p += n;
+  v.g = p; p += n;
+  v.t = p; p += n;
+  v.r = p; p += n;
+  v.d = p; p += n;
+  v.S = p; p += (size_t)m * n;
+  v.Y = p; p += (size_t)m * n;
+  v.rho = p; p += m;
+  v.alpha = p;
+  return v;
+}
+
+__global__ void lb_init_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, int B, int n,
+                               int m, int maxiter, int maxls, double pgtol, double ftol,
+                               SlotMeta* slot, const int32_t* col_fold, const int32_t* col_pos,
+                               int32_t* n_evals, int32_t* n_act) {
+  int col = blockIdx.x;
+  if (col >= B) return;
+  double* base = vec + (size_t)col * vec_stride;
+  for (size_t i = threadIdx.x; i < vec_stride; i += blockDim.x) base[i] = 0.0;
+  if (threadIdx.x == 0) {
+    LbfgsScalars s;
+    lbfgs_init(s, n, m, maxiter, maxls, pgtol, ftol);
+    sc[col] = s;
+    SlotMeta sm;
+    sm.col = col; sm.fold = col_fold[col]; sm.pos = col_pos[col]; sm.pad = 0;
+    slot[col] = sm;
+    n_evals[col] = 0;
+    if (col == 0) *n_act = B;
+  }
+}
+
+__global__ void __launch_bounds__(LB_THREADS)
+lb_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta* slot, int n_act,
+               int nz_used, int d, int ldx, int fit_intercept, const double* __restrict__ lossp,
+               const double* __restrict__ gsump, const float* __restrict__ gradp,
+               const double* __restrict__ l2v, const double* __restrict__ inv_nv,
+               int32_t* n_evals) {
+  __shared__ double red[8];
+  const int s = blockIdx.x;
+  if (s >= n_act) return;
+  const int col = slot[s].col;
+  LbfgsScalars st = sc[col];
+  const int n = st.n, m = st.m;
+  LbfgsVectors v = col_vectors(vec + (size_t)col * vec_stride, n, m);
+  CtaPar P{red};
+  const double l2 = l2v[col], inv_n = inv_nv[col];
+  // gather f and g
+  double lsum = 0.0, gsum = 0.0;
+  for (int z = 0; z < nz_used; ++z) {
+    lsum += lossp[(size_t)z * n_act + s];
+    gsum += gsump[(size_t)z * n_act + s];
+  }
+  double wsq = 0.0;
+  for (int k = threadIdx.x; k < d; k += LB_THREADS) {
+    double acc = 0.0;
+    for (int z = 0; z < nz_used; ++z) acc += (double)gradp[((size_t)z * n_act + s) * ldx + k];
+    double xk = v.x[k];
+    v.g[k] = acc * inv_n + l2 * xk;
+    wsq += xk * xk;
+  }
+  if (threadIdx.x == 0) v.g[d] = fit_intercept ? gsum * inv_n : 0.0;
+  wsq = P.block_sum(wsq);
+  double f = lsum * inv_n + 0.5 * l2 * wsq;
+  __syncthreads();
+  lbfgs_advance(P, st, v, f);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sc[col] = st;
+    n_evals[col] += 1;
+  }
+}
+
+// Stable in-place compaction of the active slot list (single CTA).
+__global__ void lb_compact_kernel(const LbfgsScalars* sc, SlotMeta* slot, int n_act_in,
+                                  int32_t* n_act_out, int32_t* n_act_host) {
+  __shared__ int wsum[32];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  for (int start = 0; start < n_act_in; start += blockDim.x) {
+    int i = start + tid;
+    SlotMeta sm;
+    int keep = 0;
+    if (i < n_act_in) {
+      sm = slot[i];
+      keep = sc[sm.col].status == LB_RUNNING ? 1 : 0;
+    }
+    // block exclusive scan of keep
+    int x = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int w = (lane < (int)(blockDim.x >> 5)) ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      wsum[lane] = w;  // inclusive
+    }
+    __syncthreads();
+    int prefix = x - keep + (wid > 0 ? wsum[wid - 1] : 0);
+    int total = wsum[(blockDim.x >> 5) - 1];
+    int base = base_s;
+    __syncthreads();
+    if (keep) slot[base + prefix] = sm;
+    if (tid == 0) base_s = base + total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *n_act_out = base_s;
+    if (n_act_host) *n_act_host = base_s;
+  }
+}
+
+__global__ void lb_export_kernel(const LbfgsScalars* sc, const double* vec, size_t vec_stride,
+                                 const SlotMeta* slot, const int32_t* n_act, int d, int ldx,
+                                 int Bcap, float* Wact) {
+  const int s = blockIdx.x;
+  if (s >= *n_act) return;
+  const int col = slot[s].col;
+  const double* x = vec + (size_t)col * vec_stride;
+  for (int k = threadIdx.x; k < ldx; k += blockDim.x)
+    Wact[(size_t)s * ldx + k] = k < d ? (float)x[k] : 0.f;
+  if (threadIdx.x == 0) Wact[(size_t)Bcap * ldx + s] = (float)x[d];
+}
+
+__global__ void lb_finish_kernel(const LbfgsScalars* sc, const double* vec, size_t vec_stride,
+                                 int B, int d, float* coef, int32_t* niter, int32_t* status,
+                                 double* loss) {
+  const int col = blockIdx.x;
+  if (col >= B) return;
+  const double* x = vec + (size_t)col * vec_stride;
+  for (int k = threadIdx.x; k <= d; k += blockDim.x) coef[(size_t)col * (d + 1) + k] = (float)x[k];
+  if (threadIdx.x == 0) {
+    const LbfgsScalars& s = sc[col];
+    niter[col] = s.nit < s.maxiter ? s.nit : s.maxiter;
+    status[col] = s.status;
+    loss[col] = s.f;
+  }
+}
+
+int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max_iter) {
+  (void)fit_intercept;
+  const int m = 10, maxls = 50;
+  const double ftol = 64.0 * 2.220446049250313e-16;
+  lb_init_kernel<<<w.B, 128, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.B, w.dp, m, max_iter,
+                                             maxls, tol, ftol, w.slot, w.col_fold, w.col_pos,
+                                             w.n_evals, w.n_act);
+  // initial iterate is w0 = 0 (SK/linear_model/_logistic.py:443): export zeros
+  SKD_CUDA(c, cudaMemsetAsync(w.Wact, 0, ((size_t)w.B * c->ldx + w.B) * sizeof(float), c->stream));
+  c->launches += 1;
+  SKD_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_intercept,
+                   int* n_act_out) {
+  const int d = (int)c->d, ldx = (int)c->ldx;
+  lb_step_kernel<<<n_act_in, LB_THREADS, 0, c->stream>>>(
+      w.sc, w.vec, w.vec_stride, w.slot, n_act_in, nz_used, d, ldx, fit_intercept, w.lossp,
+      w.gsump, w.gradp, w.l2, w.inv_n, w.n_evals);
+  lb_compact_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, nullptr);
+  lb_export_kernel<<<n_act_in, 128, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.slot, w.n_act, d,
+                                                    ldx, w.B, w.Wact);
+  c->launches += 3;
+  SKD_CUDA(c, cudaGetLastError());
+  int32_t na = 0;
+  SKD_CUDA(c, cudaMemcpyAsync(&na, w.n_act, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->d2h += sizeof(int32_t);
+  *n_act_out = na;
+  return 0;
+}
+
+int lbfgs_dev_finish(Ctx* c, LogregWork& w, float* dcoef, int32_t* dniter, int32_t* dstatus,
+                     double* dloss) {
+  lb_finish_kernel<<<w.B, 128, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.B, (int)c->d, dcoef,
+                                               dniter, dstatus, dloss);
+  c->launches += 1;
+  SKD_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+}  // namespace skd

@@ -1,0 +1,124 @@
+// skd_internal.h -- context object and helpers shared by the .cu translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "lbfgs_core.h"
+
+namespace skd {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int sm_count = 148;
+  int kernel_choice = 0;  // 0 auto, 1 simt, 2 tcgen05
+  // staged data
+  float* X = nullptr;       // [n x ldx] fp32 row-major
+  int64_t n = 0, d = 0, ldx = 0;
+  int32_t* ycls = nullptr;  // [n]
+  float* yreal = nullptr;   // [n]
+  int8_t* fold = nullptr;   // [n]
+  int32_t n_folds = 0;
+  std::vector<int64_t> fold_count;  // rows per fold id
+  // counters
+  int64_t launches = 0, h2d = 0, d2h = 0;
+  // scratch arena (grown on demand, reused across calls)
+  std::vector<DevBuf> arena;
+};
+
+// error plumbing ---------------------------------------------------------------------
+void set_global_error(const std::string& s);
+inline int fail(Ctx* c, const std::string& s) {
+  if (c) c->err = s;
+  set_global_error(s);
+  return 1;
+}
+
+#define SKD_CUDA(ctx, call)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      char _b[512];                                                                      \
+      snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,             \
+               cudaGetErrorString(_e));                                                  \
+      return skd::fail(ctx, _b);                                                         \
+    }                                                                                    \
+  } while (0)
+
+// Simple RAII device allocation tied to a stream-ordered free at scope exit.
+struct Scratch {
+  Ctx* ctx;
+  std::vector<void*> ptrs;
+  explicit Scratch(Ctx* c) : ctx(c) {}
+  ~Scratch() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <class T>
+  cudaError_t alloc(T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T) + 256);
+    if (e == cudaSuccess) { ptrs.push_back(p); *out = (T*)p; }
+    return e;
+  }
+};
+
+// ---- logistic-regression batch solver pieces (logreg_simt.cu / lbfgs_dev.cu) -----------
+
+// Per-slot metadata of the active evaluation batch.
+struct SlotMeta {
+  int32_t col;     // column id in the caller's batch
+  int32_t fold;    // held-out fold id (-1: none)
+  int32_t pos;     // positive class id
+  int32_t pad;
+};
+
+// Workspace of one skd_logreg_fit_batch call (device pointers).
+struct LogregWork {
+  int32_t B = 0;        // columns in the batch
+  int32_t dp = 0;       // d + 1 (intercept slot always present; pinned to 0 if !fit_intercept)
+  int32_t nz = 0;       // max row chunks per evaluation (partials per slot)
+  int64_t cap_sc = 0;   // capacity of the partial buffers in (chunk, slot) pairs
+  int32_t ldg = 0;      // leading dimension of G (columns, padded)
+  // per column (indexed by col)
+  LbfgsScalars* sc = nullptr;
+  double* vec = nullptr;       // per column block of (5 + 2m) * dp + 2m doubles
+  size_t vec_stride = 0;
+  double* l2 = nullptr;        // [B] l2 strength
+  double* inv_n = nullptr;     // [B] 1 / n_train
+  int32_t* col_fold = nullptr; // [B]
+  int32_t* col_pos = nullptr;  // [B]
+  int32_t* n_evals = nullptr;  // [B]
+  // per slot (active batch)
+  SlotMeta* slot = nullptr;    // [B]
+  float* Wact = nullptr;       // [B x ldx] fp32 weights of the active slots, then bias[B]
+  float* G = nullptr;          // [n x ldg] pointwise gradients (SIMT path)
+  double* lossp = nullptr;     // [cap_sc]        indexed z * n_act + slot
+  double* gsump = nullptr;     // [cap_sc]
+  float* gradp = nullptr;      // [cap_sc x ldx]
+  int32_t* n_act = nullptr;    // device scalar
+};
+
+// forward (Z = X W^T, pointwise loss / gradient on training rows) + backward (G^T X)
+int simt_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used);
+// scoring / decision kernels
+int simt_score(Ctx* c, int B, const float* dW, const SlotMeta* dslot, int64_t* dcorrect,
+               int64_t* dcount);
+int simt_decision(Ctx* c, int B, const float* dW, float* dout);
+
+// device L-BFGS (lbfgs_dev.cu)
+int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max_iter);
+int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_intercept,
+                   int* n_act_out);  // advance + compact + export (synchronises)
+int lbfgs_dev_finish(Ctx* c, LogregWork& w, float* dcoef, int32_t* dniter, int32_t* dstatus,
+                     double* dloss);
+
+}  // namespace skd

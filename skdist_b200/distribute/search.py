@@ -1,0 +1,415 @@
+"""Distributed hyper-parameter search meta-estimators on B200s.
+
+Drop-in for /root/reference/skdist/distribute/search.py (class names, constructor
+signatures incl. positional order, fitted attributes).  The reference fans
+``_fit_and_score`` (search.py:180-288) out over Spark executors, one task per
+(candidate, fold) (search.py:378-437); here every (candidate, fold) pair is one *column*
+of a batched solve on the GPU(s):
+
+  reference                                    this module
+  ---------                                    -----------
+  cv.split -> (train_idx, test_idx) per task   one int8 fold id per row      (_fold_ids)
+  _safe_split copies X[train], X[test]         none: rows are masked by fold id in-kernel
+  estimator.fit per task                       Engine.logreg_fit_batch / ridge_cv (all columns)
+  scorer(estimator, X_test, y_test)            Engine.linear_score_batch (accuracy counts) / r2
+  sc.parallelize(...).map(...).collect()       round-robin column shards over ranks + all_gather
+  cv_results_ assembly, best_*, refit          same arithmetic as search.py:461-550 (host)
+
+Base estimators with a device path: ``LogisticRegression`` (binary y, penalty l2, solver
+lbfgs) and ``Ridge`` (dense, single target).  Anything else raises NotImplementedError: by
+design there is no CPU fallback (the reference's joblib branch, search.py:388-409, is what
+the CPU baseline in bench.py times).
+"""
+import numbers
+import time
+from collections import defaultdict
+from functools import partial
+
+import numpy as np
+from numpy.ma import MaskedArray
+from scipy.stats import rankdata
+from sklearn.base import BaseEstimator, is_classifier
+from sklearn.linear_model import LogisticRegression, Ridge
+from sklearn.model_selection import (GridSearchCV, ParameterGrid, ParameterSampler,
+                                     RandomizedSearchCV, check_cv)
+from sklearn.utils.validation import indexable
+
+from .. import parallel
+from ..engine import get_engine
+from .base import _clone, _parse_partitions, _ScParamMixin
+from .utils import _check_multimetric_scoring, _num_samples
+from .validation import _check_estimator
+
+__all__ = ["DistGridSearchCV", "DistRandomizedSearchCV"]
+
+
+# ----------------------------------------------------------------------------------------
+# cross-validation layout
+# ----------------------------------------------------------------------------------------
+def _fold_ids(cv_splitted, n_samples):
+    """Turn the list of (train, test) index arrays (ref search.py:379) into one fold id per
+    row.  Requires what KFold / StratifiedKFold / GroupKFold / LeaveOneGroupOut produce: test
+    sets partition the rows and each train set is the complement of its test set."""
+    if len(cv_splitted) > 127:
+        raise NotImplementedError("more than 127 cv splits are not supported on the device path")
+    fold = np.full(n_samples, -1, dtype=np.int8)
+    for k, (train, test) in enumerate(cv_splitted):
+        test = np.asarray(test)
+        if np.any(fold[test] != -1):
+            raise NotImplementedError(
+                "cv splits with overlapping test sets (e.g. ShuffleSplit, RepeatedKFold) are not "
+                "supported on the device path")
+        fold[test] = k
+        if len(train) + len(test) != n_samples:
+            raise NotImplementedError(
+                "cv splits whose train set is not the complement of the test set are not "
+                "supported on the device path")
+    if np.any(fold < 0):
+        raise NotImplementedError("cv splits must cover every row exactly once on the device path")
+    for k, (train, test) in enumerate(cv_splitted):
+        if np.any(fold[np.asarray(train)] == k):
+            raise NotImplementedError("cv train/test sets overlap")
+    return fold
+
+
+# ----------------------------------------------------------------------------------------
+# estimator families with a device path
+# ----------------------------------------------------------------------------------------
+_LOGREG_SEARCHABLE = {"C", "tol", "max_iter", "fit_intercept"}
+
+
+def _resolve(estimator, params):
+    est = _clone(estimator)
+    if params:
+        est.set_params(**params)
+    return est
+
+
+def _check_logreg(est):
+    """Raise unless `est` is a configuration the batched lbfgs kernel path reproduces
+    (SK/linear_model/_logistic.py:1355-1593)."""
+    p = est.get_params(deep=False)
+    bad = []
+    if p.get("solver", "lbfgs") != "lbfgs":
+        bad.append("solver=%r (only 'lbfgs')" % p["solver"])
+    pen = p.get("penalty", "deprecated")
+    if pen not in ("l2", "deprecated"):
+        bad.append("penalty=%r (only 'l2')" % (pen,))
+    if p.get("l1_ratio", 0.0) not in (None, 0, 0.0):
+        bad.append("l1_ratio=%r" % (p["l1_ratio"],))
+    if p.get("class_weight", None) is not None:
+        bad.append("class_weight")
+    if p.get("dual", False):
+        bad.append("dual=True")
+    if p.get("warm_start", False):
+        bad.append("warm_start=True")
+    if bad:
+        raise NotImplementedError(
+            "LogisticRegression configuration without a device path: " + ", ".join(bad))
+    return p
+
+
+class _LogRegFamily:
+    """(candidate x fold) columns of binary L2 logistic regression."""
+
+    name = "logreg"
+
+    def __init__(self, estimator, candidate_params, X, y, scorers):
+        self.estimator = estimator
+        self.cands = [_check_logreg(_resolve(estimator, p)) for p in candidate_params]
+        for p in candidate_params:
+            extra = set(p) - _LOGREG_SEARCHABLE
+            if extra:
+                raise NotImplementedError(
+                    "searching LogisticRegression over %s has no device path (searchable: %s)"
+                    % (sorted(extra), sorted(_LOGREG_SEARCHABLE)))
+        self.classes_ = np.unique(y)
+        if len(self.classes_) != 2:
+            raise NotImplementedError(
+                "LogisticRegression device path is binary (got %d classes); wrap the estimator "
+                "in DistOneVsRestClassifier for multiclass" % len(self.classes_))
+        self.y_class = np.searchsorted(self.classes_, y).astype(np.int32)
+        scorer = scorers["score"]
+        # scoring=None -> _PassthroughScorer -> estimator.score == accuracy (ref utils.py:75-143)
+        sname = type(scorer).__name__
+        ok = sname == "_PassthroughScorer"
+        if not ok:
+            f = getattr(scorer, "_score_func", None)
+            ok = getattr(f, "__name__", "") == "accuracy_score" and getattr(scorer, "_sign", 1) == 1 \
+                and not getattr(scorer, "_kwargs", {})
+        if not ok:
+            raise NotImplementedError(
+                "only scoring=None / 'accuracy' is scored on the device for classifiers (got %r)" % (scorer,))
+
+    def stage(self, eng, X, fold, n_splits):
+        eng.stage_x(X)
+        eng.stage_labels(self.y_class)
+        eng.stage_folds(fold, n_splits)
+
+    def run_columns(self, eng, cols, n_splits, return_train_score):
+        """Fit + score the given global column ids (col = cand * n_splits + fold).
+        Returns dict of per-column arrays aligned with `cols`."""
+        cols = np.asarray(cols, dtype=np.int64)
+        out = {
+            "test_score": np.zeros(len(cols)), "n_test": np.zeros(len(cols), dtype=np.int64),
+            "fit_time": np.zeros(len(cols)), "score_time": np.zeros(len(cols)),
+            "n_iter": np.zeros(len(cols), dtype=np.int32), "status": np.zeros(len(cols), dtype=np.int32),
+        }
+        if return_train_score:
+            out["train_score"] = np.zeros(len(cols))
+        cand = cols // n_splits
+        fold = (cols % n_splits).astype(np.int32)
+        groups = defaultdict(list)
+        for i, c in enumerate(cand):
+            p = self.cands[c]
+            groups[(bool(p["fit_intercept"]), float(p["tol"]), int(p["max_iter"]))].append(i)
+        for (fi, tol, mi), idx in groups.items():
+            idx = np.asarray(idx)
+            C = np.array([self.cands[c]["C"] for c in cand[idx]], dtype=np.float64)
+            pos = np.ones(len(idx), dtype=np.int32)
+            t0 = time.time()
+            res = eng.logreg_fit_batch(C, fold[idx], pos, fit_intercept=fi, tol=tol, max_iter=mi)
+            t1 = time.time()
+            correct, count = eng.linear_score_batch(res["coef"], fold[idx], pos)
+            t2 = time.time()
+            out["test_score"][idx] = correct / np.maximum(count, 1)
+            out["n_test"][idx] = count
+            out["fit_time"][idx] = (t1 - t0) / len(idx)
+            out["score_time"][idx] = (t2 - t1) / len(idx)
+            out["n_iter"][idx] = res["n_iter"]
+            out["status"][idx] = res["status"]
+            if return_train_score:
+                c2, n2 = eng.linear_score_batch(res["coef"], (-3 - fold[idx]).astype(np.int32), pos)
+                out["train_score"][idx] = c2 / np.maximum(n2, 1)
+        return out
+
+    def refit(self, eng, params, X_dtype, n_features):
+        p = _check_logreg(_resolve(self.estimator, params))
+        res = eng.logreg_fit_batch(np.array([p["C"]]), np.array([-1], dtype=np.int32),
+                                   np.array([1], dtype=np.int32), fit_intercept=p["fit_intercept"],
+                                   tol=p["tol"], max_iter=p["max_iter"])
+        return self.make_estimator(params, res["coef"][0], res["n_iter"][0], X_dtype, n_features)
+
+    def make_estimator(self, params, coef_row, n_iter, X_dtype, n_features):
+        """A genuine fitted sklearn LogisticRegression (attributes as set by
+        SK/linear_model/_logistic.py:1561-1593) so inherited predict* work."""
+        est = _resolve(self.estimator, params)
+        dt = np.float64 if X_dtype == np.float64 else np.float32
+        est.coef_ = coef_row[None, :n_features].astype(dt)
+        if est.fit_intercept:
+            est.intercept_ = coef_row[n_features:n_features + 1].astype(dt)
+        else:
+            est.intercept_ = np.zeros(1, dtype=dt)
+        est.classes_ = self.classes_
+        est.n_iter_ = np.array([n_iter], dtype=np.int32)
+        est.n_features_in_ = n_features
+        return est
+
+    def fold_proba(self, eng, params, fold, n_splits):
+        """preds_ support (ref search.py:551-560): per-fold refit of the best params,
+        predict_proba on the held-out rows, stacked in fold order."""
+        p = _check_logreg(_resolve(self.estimator, params))
+        f = np.arange(n_splits, dtype=np.int32)
+        res = eng.logreg_fit_batch(np.full(n_splits, p["C"]), f, np.ones(n_splits, dtype=np.int32),
+                                   fit_intercept=p["fit_intercept"], tol=p["tol"], max_iter=p["max_iter"])
+        dec = eng.linear_decision(res["coef"])
+        preds = []
+        for k in range(n_splits):
+            z = dec[fold == k, k].astype(np.float64)
+            p1 = 1.0 / (1.0 + np.exp(-z))
+            preds.append(np.column_stack([1.0 - p1, p1]))
+        return np.vstack(preds)
+
+
+def _pick_family(estimator, candidate_params, X, y, scorers):
+    if type(estimator) is LogisticRegression:
+        return _LogRegFamily(estimator, candidate_params, X, y, scorers)
+    if type(estimator) is Ridge:
+        from .ridge_family import _RidgeFamily
+        return _RidgeFamily(estimator, candidate_params, X, y, scorers)
+    raise NotImplementedError(
+        "%s has no device path; supported base estimators: LogisticRegression(solver='lbfgs'), "
+        "Ridge.  (No CPU fallback by design.)" % type(estimator).__name__)
+
+
+# ----------------------------------------------------------------------------------------
+# the meta-estimators
+# ----------------------------------------------------------------------------------------
+class DistBaseSearchCV(_ScParamMixin):
+    """Same role as the reference's DistBaseSearchCV (search.py:291-581)."""
+
+    def fit(self, X, y=None, groups=None, **fit_params):
+        """Run fit with all sets of parameters (ref search.py:315-571)."""
+        if fit_params:
+            raise NotImplementedError("fit_params are not supported on the device path")
+        _check_estimator(self, verbose=self.verbose)
+        estimator = self.estimator
+        cv = check_cv(self.cv, y, classifier=is_classifier(estimator))
+        scorers, self.multimetric_ = _check_multimetric_scoring(self.estimator, scoring=self.scoring)
+        if self.multimetric_:
+            raise NotImplementedError("multi-metric scoring is not supported on the device path")
+        refit_metric = "score"
+
+        X, y, groups = indexable(X, y, groups)
+        n_splits = cv.get_n_splits(X, y, groups)
+        candidate_params = list(self._get_param_iterator())
+        n_candidates = len(candidate_params)
+        if self.verbose > 0:
+            print("Fitting {0} folds for each of {1} candidates, totalling {2} fits".format(
+                n_splits, n_candidates, n_candidates * n_splits))
+        _parse_partitions(self.partitions, n_candidates * n_splits)
+
+        X_arr = np.asarray(X)
+        if X_arr.ndim != 2:
+            raise ValueError("X must be a 2-d array")
+        y_arr = np.asarray(y)
+        n_samples, n_features = X_arr.shape
+        cv_splitted = list(cv.split(X, y, groups))
+        fold = _fold_ids(cv_splitted, n_samples)
+        family = _pick_family(estimator, candidate_params, X_arr, y_arr, scorers)
+
+        rank, world, _ = parallel.dist_info()
+        eng = get_engine()
+        family.stage(eng, X_arr, fold, n_splits)
+
+        # task order: candidate-major, fold-minor (ref search.py:378-383); column j -> rank j % world
+        n_cols = n_candidates * n_splits
+        my_cols = parallel.shard_indices(n_cols, rank, world)
+        loc = family.run_columns(eng, my_cols, n_splits, bool(self.return_train_score))
+        keys = ["test_score", "n_test", "fit_time", "score_time"]
+        if self.return_train_score:
+            keys.append("train_score")
+        res = {k: parallel.all_gather_columns(loc[k], n_cols, rank, world) for k in keys}
+
+        error_score = self.error_score
+        bad = ~np.isfinite(res["test_score"])
+        if np.any(bad):
+            # ref search.py:226-259 semantics for a failed fit
+            if isinstance(error_score, numbers.Number):
+                res["test_score"][bad] = error_score
+            else:
+                raise ValueError("a fit produced a non-finite score and error_score=%r" % (error_score,))
+
+        results = {}
+
+        def _store(key_name, array, weights=None, splits=False, rank=False):
+            """ref search.py:463-484"""
+            array = np.array(array, dtype=np.float64).reshape(n_candidates, n_splits)
+            if splits:
+                for split_i in range(n_splits):
+                    results["split%d_%s" % (split_i, key_name)] = array[:, split_i]
+            array_means = np.average(array, axis=1, weights=weights)
+            results["mean_%s" % key_name] = array_means
+            array_stds = np.sqrt(np.average((array - array_means[:, np.newaxis]) ** 2, axis=1,
+                                            weights=weights))
+            results["std_%s" % key_name] = array_stds
+            if rank:
+                results["rank_%s" % key_name] = np.asarray(rankdata(-array_means, method="min"),
+                                                           dtype=np.int32)
+
+        _store("fit_time", res["fit_time"])
+        _store("score_time", res["score_time"])
+        param_results = defaultdict(partial(MaskedArray, np.empty(n_candidates,), mask=True, dtype=object))
+        for cand_i, params in enumerate(candidate_params):
+            for name, value in params.items():
+                param_results["param_%s" % name][cand_i] = value
+        results.update(param_results)
+        results["params"] = candidate_params
+
+        # ref search.py:510-519: weights = test-fold sizes when `iid` is truthy ("warn" default)
+        test_sample_counts = np.array(res["n_test"][:n_splits], dtype=int)
+        _store("test_score", res["test_score"], splits=True, rank=True,
+               weights=test_sample_counts if self.iid else None)
+        if self.return_train_score:
+            _store("train_score", res["train_score"], splits=True)
+
+        # ref search.py:538-541
+        self.best_index_ = results["rank_test_%s" % refit_metric].argmin()
+        self.best_params_ = candidate_params[self.best_index_]
+        self.best_score_ = results["mean_test_%s" % refit_metric][self.best_index_]
+
+        if self.refit:
+            # ref search.py:543-550 (one more full-data fit, here on the device)
+            t0 = time.time()
+            self.best_estimator_ = family.refit(eng, self.best_params_, X_arr.dtype, n_features)
+            self.refit_time_ = time.time() - t0
+            if self.preds:
+                self.preds_ = family.fold_proba(eng, self.best_params_, fold, n_splits)
+
+        self.scorer_ = scorers["score"]
+        self.cv_results_ = results
+        self.n_splits_ = n_splits
+
+        # ref search.py:568-570
+        del self.sc
+        if hasattr(self.estimator, "sc"):
+            del self.estimator.sc
+        return self
+
+    def get_preds(self):
+        """Get CV predictions (ref search.py:573-576)."""
+        if hasattr(self, "preds_"):
+            return self.preds_
+
+    def drop_preds(self):
+        """Remove preds_ attribute (ref search.py:578-581)."""
+        if hasattr(self, "preds_"):
+            del self.preds_
+
+
+class DistGridSearchCV(DistBaseSearchCV, GridSearchCV):
+    """Same as sklearn `GridSearchCV` but with the fits batched on B200s.
+    Constructor mirrors ref search.py:608-641 (``sc`` is the 3rd positional argument)."""
+
+    def __init__(self, estimator, param_grid, sc=None, partitions="auto", preds=False,
+                 scoring=None, n_jobs=None, iid="warn", refit=True, cv=5, verbose=0,
+                 pre_dispatch="2*n_jobs", error_score="raise-deprecating",
+                 return_train_score=False):
+        self.estimator = estimator
+        self.param_grid = param_grid
+        self.sc = sc
+        self.partitions = partitions
+        self.preds = preds
+        self.scoring = scoring
+        self.n_jobs = n_jobs
+        self.iid = iid
+        self.refit = refit
+        self.cv = cv
+        self.verbose = verbose
+        self.pre_dispatch = pre_dispatch
+        self.error_score = error_score
+        self.return_train_score = return_train_score
+
+    def _get_param_iterator(self):
+        """ref search.py:643-645"""
+        return ParameterGrid(self.param_grid)
+
+
+class DistRandomizedSearchCV(DistBaseSearchCV, RandomizedSearchCV):
+    """Same as sklearn `RandomizedSearchCV` but with the fits batched on B200s.
+    Constructor mirrors ref search.py:671-708."""
+
+    def __init__(self, estimator, param_distributions, sc=None, partitions="auto", preds=False,
+                 n_iter=10, scoring=None, n_jobs=None, iid="warn", refit=True, cv=5, verbose=0,
+                 pre_dispatch="2*n_jobs", random_state=None, error_score="raise-deprecating",
+                 return_train_score=False):
+        self.estimator = estimator
+        self.param_distributions = param_distributions
+        self.sc = sc
+        self.partitions = partitions
+        self.preds = preds
+        self.n_iter = n_iter
+        self.scoring = scoring
+        self.n_jobs = n_jobs
+        self.iid = iid
+        self.refit = refit
+        self.cv = cv
+        self.verbose = verbose
+        self.pre_dispatch = pre_dispatch
+        self.random_state = random_state
+        self.error_score = error_score
+        self.return_train_score = return_train_score
+
+    def _get_param_iterator(self):
+        """ref search.py:710-714"""
+        return ParameterSampler(self.param_distributions, self.n_iter, random_state=self.random_state)

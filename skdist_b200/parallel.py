@@ -1,0 +1,75 @@
+"""One-process-per-GPU plumbing over torch.distributed (NCCL on GPUs, gloo in CPU tests).
+
+The reference's communication backend is PySpark (sc.broadcast / parallelize / map /
+collect: skdist/distribute/search.py:411-436).  Here: X and y are replicated on every
+rank (one broadcast from rank 0 over NVLink when only rank 0 holds the data), the
+independent (candidate x fold) columns / labels / trees are dealt round-robin to ranks
+(no data-path collective), and fixed-size per-column results are all-gathered at the end.
+"""
+import os
+
+import numpy as np
+
+
+def dist_info():
+    """(rank, world_size, local_rank); (0, 1, 0) when torch.distributed is not initialised."""
+    try:
+        import torch.distributed as dist
+    except Exception:  # pragma: no cover
+        return 0, 1, 0
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size(), int(os.environ.get("LOCAL_RANK", 0))
+    return 0, 1, 0
+
+
+def shard_indices(n_items, rank, world):
+    """Round-robin deal: item j -> rank j % world.  Candidate-major task
+    order means every rank receives a mix of hyper-parameter values, which balances the
+    per-column iteration counts."""
+    return np.arange(rank, n_items, world, dtype=np.int64)
+
+
+def all_gather_columns(local, n_items, rank, world):
+    """Inverse of shard_indices for per-item result rows.
+
+    local: array [len(shard_indices(n_items, rank, world)), ...].  Returns the full
+    [n_items, ...] array on every rank."""
+    local = np.ascontiguousarray(local)
+    if world == 1:
+        return local
+    import torch
+    import torch.distributed as dist
+
+    per = (n_items + world - 1) // world
+    tail = local.shape[1:]
+    pad = np.zeros((per,) + tail, dtype=local.dtype)
+    pad[: local.shape[0]] = local
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.from_numpy(pad).to(dev)
+    outs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(outs, t)
+    full = np.zeros((n_items,) + tail, dtype=local.dtype)
+    for r in range(world):
+        idx = shard_indices(n_items, r, world)
+        full[idx] = outs[r].cpu().numpy()[: len(idx)]
+    return full
+
+
+def broadcast_array(arr, shape, dtype, src=0):
+    """Replicate a host array held by rank `src` on every rank (NCCL broadcast through
+    device memory on GPUs).  Ranks other than src pass arr=None."""
+    rank, world, _ = dist_info()
+    if world == 1:
+        return arr
+    import torch
+    import torch.distributed as dist
+
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    if rank == src:
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=dtype)).to(dev)
+    else:
+        t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), device=dev)
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy()

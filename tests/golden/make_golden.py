@@ -1,0 +1,83 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference per-task functions
+(/root/reference/skdist/distribute/search.py:_fit_and_score) under oracle/refshim.py.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py
+The fixtures pin (i) the oracle restatement oracle/search_oracle.py against the reference
+and (ii) the CUDA path against both (tests/test_gpu_parity.py).  Inputs are regenerated
+from seeds by skdist_b200.datasets, so only outputs are stored.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from sklearn.datasets import load_digits  # noqa: E402
+from sklearn.linear_model import LogisticRegression  # noqa: E402
+from sklearn.model_selection import ParameterGrid  # noqa: E402
+
+from oracle import refshim, search_oracle  # noqa: E402
+from skdist_b200.datasets import make_g1_classification  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def reference_task(ref_search):
+    def task(estimator, X, y, scorer, train, test, params):
+        # exactly the call DistBaseSearchCV.fit makes (ref search.py:391-406)
+        return ref_search._fit_and_score(
+            estimator, X, y, {"score": scorer}, train, test, 0, params, fit_params={},
+            return_train_score=False, return_n_test_samples=True, return_times=True,
+            return_parameters=False, error_score="raise")
+    return task
+
+
+def run_case(name, X, y, grid, cv, ref_search):
+    est = LogisticRegression()
+    cands = list(ParameterGrid(grid))
+    ref = search_oracle.search_cv(est, cands, X, y, cv=cv, iid=True, task_fn=reference_task(ref_search))
+    ora = search_oracle.search_cv(est, cands, X, y, cv=cv, iid=True)
+    n_splits = ref["n_splits_"]
+    keys = ["split%d_test_score" % i for i in range(n_splits)] + ["mean_test_score", "std_test_score",
+                                                                  "rank_test_score"]
+    for k in keys:
+        assert np.array_equal(ref["cv_results_"][k], ora["cv_results_"][k]), (name, k)
+    assert ref["best_index_"] == ora["best_index_"]
+    # per-(candidate, fold) coefficients from the same sklearn fit the task runs
+    from sklearn.model_selection import check_cv
+    splits = list(check_cv(cv, y, classifier=True).split(X, y))
+    d = X.shape[1]
+    coef = np.zeros((len(cands), n_splits, d + 1), np.float32)
+    n_iter = np.zeros((len(cands), n_splits), np.int32)
+    for ci, p in enumerate(cands):
+        for fi, (tr, te) in enumerate(splits):
+            m = LogisticRegression(**p).fit(X[tr], y[tr])
+            coef[ci, fi, :d] = m.coef_[0]
+            coef[ci, fi, d] = m.intercept_[0]
+            n_iter[ci, fi] = m.n_iter_[0]
+    out = {k: ref["cv_results_"][k] for k in keys}
+    out.update(best_index=ref["best_index_"], coef=coef, n_iter=n_iter,
+               refit_coef=np.r_[ref["best_estimator_"].coef_[0], ref["best_estimator_"].intercept_],
+               C=np.array([p["C"] for p in cands]))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "mean_test_score", ref["cv_results_"]["mean_test_score"], "n_iter", n_iter.ravel())
+
+
+def main():
+    ref_search, _, _ = refshim.load()
+    X, y = make_g1_classification(4000, 16, seed=3)
+    run_case("search_logreg_g1_4000x16", X, y, {"C": [1e-3, 1e-2, 1e-1, 1.0, 10.0, 100.0]}, 3, ref_search)
+    X, y = make_g1_classification(20000, 64, seed=4)
+    run_case("search_logreg_g1_20000x64", X, y, {"C": [1e-4, 1e-2, 1.0, 100.0]}, 5, ref_search)
+    # config 1 of BASELINE.json, binarised (digit 3 vs rest), float32 as the device path computes
+    dg = load_digits()
+    Xd = dg.data.astype(np.float32)
+    yd = (dg.target == 3).astype(np.int64)
+    run_case("search_logreg_digits3", Xd, yd, {"C": [0.01, 0.1, 1.0, 10.0]}, 3, ref_search)
+
+
+if __name__ == "__main__":
+    main()

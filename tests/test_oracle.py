@@ -1,0 +1,69 @@
+"""The oracle against (a) the committed golden fixtures produced by the reference's own
+_fit_and_score (tests/golden/make_golden.py) and (b) installed scikit-learn."""
+import os
+
+import numpy as np
+import pytest
+from sklearn.datasets import load_digits
+from sklearn.linear_model import LogisticRegression
+from sklearn.model_selection import ParameterGrid
+
+from oracle import logreg_oracle as lo
+from oracle import refshim, search_oracle
+from skdist_b200.datasets import make_g1_classification
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _case(name):
+    if name == "search_logreg_g1_4000x16":
+        X, y = make_g1_classification(4000, 16, seed=3)
+        return X, y, 3
+    if name == "search_logreg_digits3":
+        dg = load_digits()
+        return dg.data.astype(np.float32), (dg.target == 3).astype(np.int64), 3
+    X, y = make_g1_classification(20000, 64, seed=4)
+    return X, y, 5
+
+
+@pytest.mark.parametrize("name", ["search_logreg_g1_4000x16", "search_logreg_digits3"])
+@pytest.mark.filterwarnings("ignore")
+def test_search_oracle_matches_golden(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    X, y, cv = _case(name)
+    cands = [{"C": float(c)} for c in g["C"]]
+    ora = search_oracle.search_cv(LogisticRegression(), cands, X, y, cv=cv, iid=True)
+    for i in range(cv):
+        k = "split%d_test_score" % i
+        np.testing.assert_array_equal(ora["cv_results_"][k], g[k])
+    np.testing.assert_array_equal(ora["cv_results_"]["mean_test_score"], g["mean_test_score"])
+    np.testing.assert_array_equal(ora["cv_results_"]["rank_test_score"], g["rank_test_score"])
+    assert ora["best_index_"] == int(g["best_index"])
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_logreg_restatement_is_bit_identical_to_sklearn():
+    X, y = make_g1_classification(5000, 20, seed=7)
+    yf = y.astype(np.float32)
+    for C in [0.01, 1.0, 100.0]:
+        for fi in [True, False]:
+            coef, b, it = lo.fit_binary_lbfgs(X, yf, C=C, fit_intercept=fi)
+            m = LogisticRegression(C=C, fit_intercept=fi).fit(X, y)
+            assert np.array_equal(coef, m.coef_[0]) and it == m.n_iter_[0]
+            if fi:
+                assert b == m.intercept_[0]
+            assert lo.accuracy(X, yf, coef, b) == m.score(X, y)
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+@pytest.mark.filterwarnings("ignore")
+def test_oracle_task_equals_reference_task():
+    """Live pin: reference _fit_and_score (search.py:180-288) vs oracle.fit_and_score."""
+    from tests.golden.make_golden import reference_task
+    ref_search, _, _ = refshim.load()
+    X, y = make_g1_classification(1500, 8, seed=5)
+    cands = list(ParameterGrid({"C": [0.1, 10.0]}))
+    a = search_oracle.search_cv(LogisticRegression(), cands, X, y, cv=3, task_fn=reference_task(ref_search))
+    b = search_oracle.search_cv(LogisticRegression(), cands, X, y, cv=3)
+    np.testing.assert_array_equal(a["cv_results_"]["mean_test_score"], b["cv_results_"]["mean_test_score"])
+    assert a["best_params_"] == b["best_params_"]

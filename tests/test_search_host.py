@@ -1,0 +1,61 @@
+"""Host-side logic of DistGridSearchCV / DistRandomizedSearchCV (no GPU): cv_results_
+assembly, best selection and refit must equal the oracle restatement of the reference's
+driver loop (oracle/search_oracle.py <- ref search.py:315-571)."""
+import pickle
+
+import numpy as np
+import pytest
+from sklearn.linear_model import LogisticRegression
+from sklearn.model_selection import ParameterGrid
+
+from oracle import search_oracle
+from skdist.distribute.search import DistGridSearchCV, DistRandomizedSearchCV
+from skdist_b200.datasets import make_g1_classification
+
+
+def test_grid_matches_oracle(fake_engine):
+    X, y = make_g1_classification(3000, 12, seed=1)
+    grid = {"C": [0.01, 0.1, 1.0, 10.0]}
+    gs = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, return_train_score=True)
+    gs.fit(X, y)
+    ora = search_oracle.search_cv(LogisticRegression(), ParameterGrid(grid), X, y, cv=3,
+                                  iid=True, return_train_score=True)
+    for k in ["split0_test_score", "split1_test_score", "split2_test_score", "mean_test_score",
+              "std_test_score", "rank_test_score", "mean_train_score"]:
+        np.testing.assert_array_equal(gs.cv_results_[k], ora["cv_results_"][k], err_msg=k)
+    assert gs.best_index_ == ora["best_index_"]
+    assert gs.best_params_ == ora["best_params_"]
+    assert gs.best_score_ == ora["best_score_"]
+    assert gs.n_splits_ == 3
+    np.testing.assert_array_equal(gs.best_estimator_.coef_, ora["best_estimator_"].coef_)
+    np.testing.assert_array_equal(gs.predict(X[:50]), ora["best_estimator_"].predict(X[:50]))
+    assert list(gs.cv_results_["params"]) == list(ParameterGrid(grid))
+    assert not hasattr(gs, "sc")              # ref search.py:568
+    pickle.loads(pickle.dumps(gs))            # fitted object pickles (examples/search/basic_usage.py:113)
+    assert gs.get_params()["sc"] is None
+
+
+def test_reference_toy_case(fake_engine):
+    """ref skdist/distribute/tests/test_search.py:37-56 (same data, lbfgs instead of liblinear)."""
+    X = np.array([[1, 1, 1], [0, 0, 0], [-1, -1, -1]] * 100)
+    y = np.array([0, 0, 1] * 100)
+    gs = DistGridSearchCV(LogisticRegression(), {"C": [0.1, 1.0]}, cv=3)
+    gs.fit(X, y)
+    assert np.allclose(gs.predict(X[:3]), np.array([0, 0, 1]))
+    rs = DistRandomizedSearchCV(LogisticRegression(), {"C": [0.1, 1.0]}, cv=3, n_iter=2)
+    rs.fit(X, y)
+    assert np.allclose(rs.predict(X[:3]), np.array([0, 0, 1]))
+
+
+def test_preds_and_unsupported(fake_engine):
+    X, y = make_g1_classification(600, 5, seed=2)
+    gs = DistGridSearchCV(LogisticRegression(), {"C": [1.0]}, cv=3, preds=True).fit(X, y)
+    assert gs.get_preds().shape == (600, 2)
+    np.testing.assert_allclose(gs.get_preds().sum(1), 1.0)
+    gs.drop_preds()
+    assert gs.get_preds() is None
+    from sklearn.naive_bayes import GaussianNB
+    with pytest.raises(NotImplementedError):
+        DistGridSearchCV(GaussianNB(), {"var_smoothing": [1e-9]}, cv=3).fit(X, y)
+    with pytest.raises(NotImplementedError):
+        DistGridSearchCV(LogisticRegression(solver="liblinear"), {"C": [1.0]}, cv=3).fit(X, y)
