@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- candidate-fits/sec of DistGridSearchCV(LogisticRegression) on synthetic
+1M x 256 fp32, 512-point C grid x 5 folds (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path
+
+A "step" is one complete pass of the hot path: every (candidate, fold) column fitted with
+the batched L-BFGS solver and scored on its held-out rows.  `value` is measured with
+(X, y, folds) already resident in HBM; `e2e` goes through the public drop-in API
+(DistGridSearchCV.fit on HOST numpy arrays: H2D staging, fits, scoring, D2H of results; refit
+excluded as SURVEY.md section 8d defines the metric).  Under torchrun (N > 1) columns are dealt
+round-robin to ranks ("weak": the per-rank batch shrinks, total work is fixed -> "strong").
+One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "candidate-fits/sec (params x folds) DistGridSearchCV LogReg 1Mx256"
+UNIT = "fits/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=2)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--n", type=int, default=1_000_000)
+    p.add_argument("--d", type=int, default=256)
+    p.add_argument("--candidates", type=int, default=512)
+    p.add_argument("--folds", type=int, default=5)
+    p.add_argument("--cpu-sample", type=int, default=2, help="fits timed for cpu_baseline (0 = skip)")
+    p.add_argument("--kernel", type=int, default=0, help="0 auto, 1 SIMT fp32, 2 tcgen05")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        j = json.load(open(path))
+        return {"bf16_burst": j["bf16_tflops"], "bf16_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                "hbm": j["hbm_gbs"], "src": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_fits_per_sec(X, y, fold, Cs, n_fits, n_jobs=1):
+    """The reference's sc=None branch (search.py:388-409): the same per-task function
+    (oracle.search_oracle.fit_and_score <- search.py:180-288) on the host cores, on a bounded
+    sample of (candidate, fold) tasks of the same workload."""
+    from joblib import Parallel, delayed
+    from sklearn.linear_model import LogisticRegression
+    from sklearn.metrics import check_scoring
+    from oracle.search_oracle import fit_and_score
+    est = LogisticRegression()
+    scorer = check_scoring(est)
+    n_folds = int(fold.max()) + 1
+    # stratified sample over the C grid, fold cycling
+    idx = np.linspace(0, len(Cs) - 1, n_fits).round().astype(int)
+    tasks = []
+    for t, ci in enumerate(idx):
+        f = t % n_folds
+        tasks.append(({"C": float(Cs[ci])}, np.flatnonzero(fold != f), np.flatnonzero(fold == f)))
+    t0 = time.time()
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = Parallel(n_jobs=n_jobs)(delayed(fit_and_score)(est, X, y, scorer, tr, te, p) for p, tr, te in tasks)
+    dt = time.time() - t0
+    return len(tasks) / dt, dt, [o[0]["score"] for o in out]
+
+
+def fold_ids(y, n_folds):
+    from sklearn.model_selection import StratifiedKFold
+    fold = np.zeros(len(y), np.int8)
+    for k, (_, te) in enumerate(StratifiedKFold(n_folds).split(np.zeros((len(y), 1)), y)):
+        fold[te] = k
+    return fold
+
+
+def workload_name(a):
+    return "DistGridSearchCV(LogisticRegression) %d-point C grid x %d folds, synthetic G1 %dx%d fp32" % (
+        a.candidates, a.folds, a.n, a.d)
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from skdist_b200.datasets import make_g1_classification
+    X, y = make_g1_classification(a.n, a.d, seed=0)
+    fold = fold_ids(y, a.folds)
+    Cs = np.logspace(-4, 4, a.candidates)
+    cores = os.cpu_count() or 1
+    per_step = max(1, a.cpu_sample)
+    vals = []
+    for s in range(a.warmup + a.steps):
+        # warm-up steps of a CPU arm only need to page the data in: one short fit
+        if s < a.warmup:
+            cpu_fits_per_sec(X[: max(1000, a.n // 50)], y[: max(1000, a.n // 50)],
+                             fold[: max(1000, a.n // 50)], Cs, 1)
+            continue
+        v, dt, _ = cpu_fits_per_sec(X, y, fold, Cs, per_step, n_jobs=1)
+        vals.append((v, dt))
+    tot_fits = per_step * len(vals)
+    tot_t = sum(dt for _, dt in vals)
+    value = tot_fits / tot_t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(vals)),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(a), "inputs": "exceed L2"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d (candidate, fold) fits per step, C spread over the grid, BLAS threads=%d "
+                                   "(reference sc=None branch: joblib n_jobs=1 x threaded BLAS)" % (per_step, cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from sklearn.linear_model import LogisticRegression
+    from skdist.distribute.search import DistGridSearchCV
+    from skdist_b200 import parallel
+    from skdist_b200.datasets import make_g1_classification
+    from skdist_b200.engine import get_engine
+
+    X, y = make_g1_classification(a.n, a.d, seed=0)   # every rank builds the same seeded inputs
+    Cs = np.logspace(-4, 4, a.candidates)
+    fold = fold_ids(y, a.folds)
+    eng = get_engine()
+    if a.kernel:
+        eng.set_kernel(a.kernel)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: inputs staged once, each step = fit + score of this rank's columns
+    eng.stage_x(X)
+    eng.stage_labels(y.astype(np.int32))
+    eng.stage_folds(fold, a.folds)
+    n_cols = a.candidates * a.folds
+    my = parallel.shard_indices(n_cols, rank, world)
+    C_cols = np.repeat(Cs, a.folds)[my]
+    f_cols = np.tile(np.arange(a.folds, dtype=np.int32), a.candidates)[my]
+    pos = np.ones(len(my), np.int32)
+
+    def step():
+        res = eng.logreg_fit_batch(C_cols, f_cols, pos)
+        correct, count = eng.linear_score_batch(res["coef"], f_cols, pos)
+        return res, correct, count
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile(1)
+    c0 = eng.counters()
+    # CUDA events on the stream the kernels are launched on (the library's own stream;
+    # torch.cuda.Event would only see torch's current stream)
+    eng.timer_start()
+    for _ in range(a.steps):
+        res, correct, count = step()
+    wall = eng.timer_stop()
+    barrier()
+    prof = eng.profile(0)
+    c1 = eng.counters()
+    clocks = sampler.stop() if rank == 0 else None
+    # device time between the two events, max over ranks
+    tt = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_steps = float(tt.item())
+    value = n_cols * a.steps / t_steps
+
+    # ---- end-to-end arm: public API on host arrays (H2D + fits + scoring + D2H), refit excluded
+    gs_times = []
+    h2d = d2h = 0
+    for i in range(1 + 1):   # one warm-up, one timed
+        barrier()
+        cc0 = eng.counters()
+        t0 = time.perf_counter()
+        gs = DistGridSearchCV(LogisticRegression(), {"C": list(Cs)}, None, cv=a.folds, refit=False)
+        gs.fit(X, y)
+        barrier()
+        gs_times.append(time.perf_counter() - t0)
+        cc1 = eng.counters()
+        h2d, d2h = cc1["h2d_bytes"] - cc0["h2d_bytes"], cc1["d2h_bytes"] - cc0["d2h_bytes"]
+    te = torch.tensor([gs_times[-1]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_cols / float(te.item())
+
+    if rank == 0:
+        pk = peaks()
+        achieved = prof["eval_flops"] / (prof["eval_ms"] * 1e-3) / 1e12 if prof["eval_ms"] > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * t_steps / a.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "inputs": "exceed L2 (X is %.2f GB)" % (X.nbytes / 1e9),
+                       "parallelism": "columns round-robin over %d rank(s), X replicated" % world,
+                       "kernel": {0: "auto", 1: "simt-fp32", 2: "tcgen05"}[a.kernel],
+                       "mean_test_score_best": float(np.max(gs.cv_results_["mean_test_score"])),
+                       "best_C": float(gs.best_params_["C"]),
+                       "rounds_per_step": prof["rounds"] / max(1, a.steps)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "seconds": float(te.item())},
+            "gpu_launches": int(c1["launches"] - c0["launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
+                         "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                         "peak_source": pk["src"] + " bf16 dense (sustained)",
+                         "kernel": "logistic loss+gradient evaluation (rank 0)",
+                         "launches": prof["eval_launches"], "avg_launch_ms": prof["eval_ms"] / max(1, prof["eval_launches"]),
+                         "algorithmic_flops": "4 * n_train * d per active column per launch"},
+        }
+        if world == 1 and a.cpu_sample > 0:
+            cores = os.cpu_count() or 1
+            v, dt, _ = cpu_fits_per_sec(X, y, fold, Cs, a.cpu_sample, n_jobs=1)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d (candidate, fold) fits of the same workload in %.1f s, C spread over the grid, "
+                          "joblib n_jobs=1 x %d BLAS threads (reference sc=None branch, search.py:388-409)"
+                          % (a.cpu_sample, dt, cores)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,14 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
                          int32_t* status_out, double* loss_out, int32_t* n_evals_out,
                          double* gpu_seconds_out);
 
+/* Objective and gradient of B columns at caller-supplied points w_in[j*(d+1)+k] (float64;
+ * cast to fp32 for the products as sklearn does).  loss_out[j], grad_out[j*(d+1)+k] follow
+ * SK/linear_model/_linear_loss.py:291-379 exactly (mean loss + 0.5*l2*|w|^2, intercept last).
+ * Diagnostic / test entry: it runs the same evaluation kernels as skd_logreg_fit_batch. */
+int skd_logreg_loss_grad(skd_ctx* ctx, int32_t B, const double* w_in, const double* C,
+                         const int32_t* col_fold, const int32_t* col_pos, int32_t fit_intercept,
+                         double* loss_out, double* grad_out);
+
 /* Accuracy counts of B linear binary classifiers on their held-out rows.
  * Column j is scored on rows whose fold id == col_fold[j] (col_fold[j] == -2: all rows;
  * col_fold[j] == -3-f: rows NOT in fold f, i.e. the training rows, for return_train_score);
@@ -92,6 +100,19 @@ int skd_set_kernel(skd_ctx* ctx, int32_t which);
 
 /* Counters since context creation: kernels launched by this library, bytes H2D, bytes D2H. */
 int skd_get_counters(skd_ctx* ctx, int64_t* launches, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* Per-evaluation timing for the roofline report: reads the accumulators (summed CUDA-event
+ * time of the evaluation launches of skd_logreg_fit_batch, their algorithmic FLOPs
+ * (4 * n_train * d per active column per launch), launch and round counts) and then, if
+ * enable >= 0, resets them and switches collection on (1) or off (0).  enable < 0: read only. */
+int skd_profile(skd_ctx* ctx, int32_t enable, double* eval_ms, double* eval_flops,
+                int64_t* eval_launches, int64_t* rounds);
+
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of this library is
+ * launched on): start records an event, stop records a second one, waits for it and returns
+ * the elapsed device time in milliseconds.  Used by bench.py to time K steps on the device. */
+int skd_timer_start(skd_ctx* ctx);
+int skd_timer_stop(skd_ctx* ctx, double* ms_out);
 
 /* Host-side optimiser object exposing the same L-BFGS-B core the device kernels run
  * (csrc/lbfgs_core.h); used by the CPU tests that pin it against scipy's setulb.

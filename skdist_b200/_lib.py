@@ -38,10 +38,16 @@ SYMBOLS = {
     "skd_logreg_fit_batch": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                         _c.c_int32, _c.c_double, _c.c_int32, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_double)]),
+    "skd_logreg_loss_grad": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                        _c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p]),
     "skd_linear_score_batch": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                           _c.c_void_p, _c.c_void_p]),
     "skd_linear_decision": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p]),
     "skd_set_kernel": (_c.c_int, [_c.c_void_p, _c.c_int32]),
+    "skd_profile": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double),
+                               _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64)]),
+    "skd_timer_start": (_c.c_int, [_c.c_void_p]),
+    "skd_timer_stop": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_double)]),
     "skd_get_counters": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_int64), _c.POINTER(_c.c_int64),
                                     _c.POINTER(_c.c_int64)]),
     "skd_lbfgs_create": (_c.c_void_p, [_c.c_int32, _c.c_int32, _c.c_int32, _c.c_int32, _c.c_double,

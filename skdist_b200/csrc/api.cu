@@ -31,6 +31,11 @@ struct skd_lbfgs {
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
+// Which evaluation kernel serves this batch (SIMT fp32 now; tcgen05 once it lands).
+static int eval_dispatch(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
+  return simt_eval(c, w, n_act, nz_used);
+}
+
 extern "C" {
 
 int skd_version(void) { return 100; }
@@ -177,6 +182,46 @@ int skd_set_kernel(skd_ctx* ctx, int32_t which) {
   return prev;
 }
 
+int skd_profile(skd_ctx* ctx, int32_t enable, double* eval_ms, double* eval_flops,
+                int64_t* eval_launches, int64_t* rounds) {
+  if (!ctx) return fail(nullptr, "skd_profile: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (eval_ms) *eval_ms = c->prof_eval_ms;
+  if (eval_flops) *eval_flops = c->prof_eval_flops;
+  if (eval_launches) *eval_launches = c->prof_eval_launches;
+  if (rounds) *rounds = c->prof_rounds;
+  if (enable >= 0) {
+    c->prof = enable != 0;
+    c->prof_eval_ms = 0.0; c->prof_eval_flops = 0.0; c->prof_eval_launches = 0; c->prof_rounds = 0;
+  }
+  return 0;
+}
+
+int skd_timer_start(skd_ctx* ctx) {
+  if (!ctx) return fail(nullptr, "skd_timer_start: ctx is NULL");
+  Ctx* c = &ctx->c;
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  if (!c->timer[0]) {
+    SKD_CUDA(c, cudaEventCreate(&c->timer[0]));
+    SKD_CUDA(c, cudaEventCreate(&c->timer[1]));
+  }
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  SKD_CUDA(c, cudaEventRecord(c->timer[0], c->stream));
+  return 0;
+}
+
+int skd_timer_stop(skd_ctx* ctx, double* ms_out) {
+  if (!ctx) return fail(nullptr, "skd_timer_stop: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->timer[0] || !ms_out) return fail(c, "skd_timer_stop: timer not started");
+  SKD_CUDA(c, cudaEventRecord(c->timer[1], c->stream));
+  SKD_CUDA(c, cudaEventSynchronize(c->timer[1]));
+  float ms = 0.f;
+  SKD_CUDA(c, cudaEventElapsedTime(&ms, c->timer[0], c->timer[1]));
+  *ms_out = ms;
+  return 0;
+}
+
 int skd_get_counters(skd_ctx* ctx, int64_t* launches, int64_t* h2d, int64_t* d2h) {
   if (!ctx) return fail(nullptr, "skd_get_counters: ctx is NULL");
   if (launches) *launches = ctx->c.launches;
@@ -202,6 +247,7 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
 
   // host-side per-column constants
   std::vector<double> l2(B), inv_n(B);
+  double mean_ntrain = 0.0;
   for (int j = 0; j < B; ++j) {
     int f = col_fold[j];
     int64_t ntrain = n;
@@ -213,6 +259,7 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
     if (!(C[j] > 0.0)) return fail(c, "skd_logreg_fit_batch: C must be positive");
     l2[j] = 1.0 / (C[j] * (double)ntrain);  // SK/linear_model/_logistic.py:580
     inv_n[j] = 1.0 / (double)ntrain;
+    mean_ntrain += (double)ntrain / B;
   }
 
   Scratch sx(c);
@@ -258,13 +305,43 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   int n_act = B;
   const long max_rounds = (long)max_iter * 52 + 16;
   long rounds = 0;
+  std::vector<double> round_flops;
+  size_t ev_used = 0;
   while (n_act > 0) {
     int nz_used = 0;
-    if (simt_eval(c, w, n_act, &nz_used)) return 1;
+    if (c->prof) {
+      if (c->prof_events.size() < ev_used + 2) {
+        cudaEvent_t a, b;
+        SKD_CUDA(c, cudaEventCreate(&a));
+        SKD_CUDA(c, cudaEventCreate(&b));
+        c->prof_events.push_back(a);
+        c->prof_events.push_back(b);
+      }
+      SKD_CUDA(c, cudaEventRecord(c->prof_events[ev_used], c->stream));
+    }
+    if (eval_dispatch(c, w, n_act, &nz_used)) return 1;
+    if (c->prof) {
+      SKD_CUDA(c, cudaEventRecord(c->prof_events[ev_used + 1], c->stream));
+      ev_used += 2;
+      // algorithmic work of this launch: 4 * n_train * d per active column; the active set is
+      // only known on the device, so use the mean training fraction of the batch
+      round_flops.push_back(4.0 * (double)d * (double)n_act * mean_ntrain);
+    }
     int n_next = 0;
     if (lbfgs_dev_step(c, w, n_act, nz_used, fit_intercept, &n_next)) return 1;
     n_act = n_next;
     if (++rounds > max_rounds) return fail(c, "skd_logreg_fit_batch: round limit exceeded (internal error)");
+  }
+  if (c->prof) {
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i + 1 < ev_used; i += 2) {
+      float ms = 0.f;
+      SKD_CUDA(c, cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+      c->prof_eval_ms += ms;
+      c->prof_eval_flops += round_flops[i / 2];
+      c->prof_eval_launches += 1;
+    }
+    c->prof_rounds += rounds;
   }
   if (lbfgs_dev_finish(c, w, dcoef, dniter, dstatus, dloss)) return 1;
   SKD_CUDA(c, cudaMemcpyAsync(coef_out, dcoef, (size_t)B * dp * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -282,6 +359,63 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
+  return 0;
+}
+
+int skd_logreg_loss_grad(skd_ctx* ctx, int32_t B, const double* w_in, const double* C,
+                         const int32_t* col_fold, const int32_t* col_pos, int32_t fit_intercept,
+                         double* loss_out, double* grad_out) {
+  if (!ctx) return fail(nullptr, "skd_logreg_loss_grad: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || !c->ycls) return fail(c, "skd_logreg_loss_grad: stage X and labels first");
+  if (B <= 0 || !w_in || !C || !col_fold || !col_pos || !loss_out || !grad_out)
+    return fail(c, "skd_logreg_loss_grad: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  const int64_t n = c->n, d = c->d, ldx = c->ldx;
+  const int dp = (int)d + 1;
+  std::vector<double> l2(B), inv_n(B);
+  std::vector<SlotMeta> hs(B);
+  std::vector<float> hw((size_t)B * ldx + B, 0.f);
+  for (int j = 0; j < B; ++j) {
+    int f = col_fold[j];
+    int64_t ntrain = n;
+    if (f >= 0) {
+      if (!c->fold || f >= c->n_folds) return fail(c, "skd_logreg_loss_grad: unstaged fold");
+      ntrain = n - c->fold_count[f];
+    }
+    l2[j] = 1.0 / (C[j] * (double)ntrain);
+    inv_n[j] = 1.0 / (double)ntrain;
+    hs[j].col = j; hs[j].fold = f; hs[j].pos = col_pos[j]; hs[j].pad = 0;
+    for (int k = 0; k < d; ++k) hw[(size_t)j * ldx + k] = (float)w_in[(size_t)j * dp + k];
+    hw[(size_t)B * ldx + j] = fit_intercept ? (float)w_in[(size_t)j * dp + d] : 0.f;
+  }
+  Scratch sx(c);
+  LogregWork w;
+  w.B = B; w.dp = dp; w.ldg = (int)round_up(B, 64); w.nz = 1024;
+  w.cap_sc = (int64_t)4 * c->sm_count * 64 + B + 64;
+  SKD_CUDA(c, sx.alloc(&w.l2, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.inv_n, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.slot, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.Wact, (size_t)B * ldx + B));
+  SKD_CUDA(c, sx.alloc(&w.G, (size_t)n * w.ldg));
+  SKD_CUDA(c, sx.alloc(&w.lossp, (size_t)w.cap_sc));
+  SKD_CUDA(c, sx.alloc(&w.gsump, (size_t)w.cap_sc));
+  SKD_CUDA(c, sx.alloc(&w.gradp, (size_t)w.cap_sc * ldx));
+  double *dx, *df, *dg;
+  SKD_CUDA(c, sx.alloc(&dx, (size_t)B * dp));
+  SKD_CUDA(c, sx.alloc(&df, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&dg, (size_t)B * dp));
+  SKD_CUDA(c, cudaMemcpyAsync(w.l2, l2.data(), B * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(w.inv_n, inv_n.data(), B * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(w.slot, hs.data(), B * sizeof(SlotMeta), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(w.Wact, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(dx, w_in, (size_t)B * dp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int nz_used = 0;
+  if (eval_dispatch(c, w, B, &nz_used)) return 1;
+  if (lbfgs_dev_gather(c, w, B, nz_used, fit_intercept, dx, df, dg)) return 1;
+  SKD_CUDA(c, cudaMemcpyAsync(loss_out, df, B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(grad_out, dg, (size_t)B * dp * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -59,6 +59,49 @@ __device__ __forceinline__ LbfgsVectors col_vectors(double* base, int n, int m) 
   return v;
 }
 
+
+// f, g of slot s from the evaluation partials, with the L2 term added in float64 exactly as
+// SK/linear_model/_linear_loss.py:349-361 does (penalty on the weights only).
+__device__ __forceinline__ double gather_fg(const CtaPar& P, int s, int n_act, int nz_used, int d,
+                                            int ldx, int fit_intercept,
+                                            const double* __restrict__ lossp,
+                                            const double* __restrict__ gsump,
+                                            const float* __restrict__ gradp, double l2,
+                                            double inv_n, const double* x, double* g) {
+  double lsum = 0.0, gsum = 0.0;
+  for (int z = 0; z < nz_used; ++z) {
+    lsum += lossp[(size_t)z * n_act + s];
+    gsum += gsump[(size_t)z * n_act + s];
+  }
+  double wsq = 0.0;
+  for (int k = threadIdx.x; k < d; k += LB_THREADS) {
+    double acc = 0.0;
+    for (int z = 0; z < nz_used; ++z) acc += (double)gradp[((size_t)z * n_act + s) * ldx + k];
+    double xk = x[k];
+    g[k] = acc * inv_n + l2 * xk;
+    wsq += xk * xk;
+  }
+  if (threadIdx.x == 0) g[d] = fit_intercept ? gsum * inv_n : 0.0;
+  wsq = P.block_sum(wsq);
+  return lsum * inv_n + 0.5 * l2 * wsq;
+}
+
+// Diagnostic / test entry: objective and gradient of every slot at caller-supplied points.
+__global__ void __launch_bounds__(LB_THREADS)
+lb_gather_kernel(int n_act, int nz_used, int d, int ldx, int fit_intercept,
+                 const double* __restrict__ lossp, const double* __restrict__ gsump,
+                 const float* __restrict__ gradp, const double* __restrict__ l2v,
+                 const double* __restrict__ inv_nv, const double* __restrict__ xin,
+                 double* __restrict__ fout, double* __restrict__ gout) {
+  __shared__ double red[8];
+  const int s = blockIdx.x;
+  if (s >= n_act) return;
+  CtaPar P{red};
+  double f = gather_fg(P, s, n_act, nz_used, d, ldx, fit_intercept, lossp, gsump, gradp, l2v[s],
+                       inv_nv[s], xin + (size_t)s * (d + 1), gout + (size_t)s * (d + 1));
+  if (threadIdx.x == 0) fout[s] = f;
+}
+
 __global__ void lb_init_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, int B, int n,
                                int m, int maxiter, int maxls, double pgtol, double ftol,
                                SlotMeta* slot, const int32_t* col_fold, const int32_t* col_pos,
@@ -94,23 +137,8 @@ lb_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta*
   LbfgsVectors v = col_vectors(vec + (size_t)col * vec_stride, n, m);
   CtaPar P{red};
   const double l2 = l2v[col], inv_n = inv_nv[col];
-  // gather f and g
-  double lsum = 0.0, gsum = 0.0;
-  for (int z = 0; z < nz_used; ++z) {
-    lsum += lossp[(size_t)z * n_act + s];
-    gsum += gsump[(size_t)z * n_act + s];
-  }
-  double wsq = 0.0;
-  for (int k = threadIdx.x; k < d; k += LB_THREADS) {
-    double acc = 0.0;
-    for (int z = 0; z < nz_used; ++z) acc += (double)gradp[((size_t)z * n_act + s) * ldx + k];
-    double xk = v.x[k];
-    v.g[k] = acc * inv_n + l2 * xk;
-    wsq += xk * xk;
-  }
-  if (threadIdx.x == 0) v.g[d] = fit_intercept ? gsum * inv_n : 0.0;
-  wsq = P.block_sum(wsq);
-  double f = lsum * inv_n + 0.5 * l2 * wsq;
+  double f = gather_fg(P, s, n_act, nz_used, d, ldx, fit_intercept, lossp, gsump, gradp, l2, inv_n,
+                       v.x, v.g);
   __syncthreads();
   lbfgs_advance(P, st, v, f);
   __syncthreads();
@@ -226,6 +254,16 @@ int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_int
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->d2h += sizeof(int32_t);
   *n_act_out = na;
+  return 0;
+}
+
+int lbfgs_dev_gather(Ctx* c, LogregWork& w, int n_act, int nz_used, int fit_intercept,
+                     const double* dx, double* df, double* dg) {
+  lb_gather_kernel<<<n_act, LB_THREADS, 0, c->stream>>>(n_act, nz_used, (int)c->d, (int)c->ldx,
+                                                        fit_intercept, w.lossp, w.gsump, w.gradp,
+                                                        w.l2, w.inv_n, dx, df, dg);
+  c->launches += 1;
+  SKD_CUDA(c, cudaGetLastError());
   return 0;
 }
 

@@ -31,8 +31,15 @@ struct Ctx {
   std::vector<int64_t> fold_count;  // rows per fold id
   // counters
   int64_t launches = 0, h2d = 0, d2h = 0;
-  // scratch arena (grown on demand, reused across calls)
-  std::vector<DevBuf> arena;
+  // optional per-evaluation timing (bench.py roofline): CUDA events on `stream` around every
+  // evaluation launch of skd_logreg_fit_batch
+  bool prof = false;
+  double prof_eval_ms = 0.0;      // summed device time of the evaluation kernels
+  double prof_eval_flops = 0.0;   // algorithmic FLOPs of those launches (4 * n_train * d per column)
+  int64_t prof_eval_launches = 0; // evaluation launches (one per L-BFGS round)
+  int64_t prof_rounds = 0;
+  std::vector<cudaEvent_t> prof_events;
+  cudaEvent_t timer[2] = {nullptr, nullptr};
 };
 
 // error plumbing ---------------------------------------------------------------------
@@ -118,6 +125,8 @@ int simt_decision(Ctx* c, int B, const float* dW, float* dout);
 int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max_iter);
 int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_intercept,
                    int* n_act_out);  // advance + compact + export (synchronises)
+int lbfgs_dev_gather(Ctx* c, LogregWork& w, int n_act, int nz_used, int fit_intercept,
+                     const double* dx, double* df, double* dg);
 int lbfgs_dev_finish(Ctx* c, LogregWork& w, float* dcoef, int32_t* dniter, int32_t* dstatus,
                      double* dloss);
 

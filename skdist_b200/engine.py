@@ -72,6 +72,24 @@ class Engine:
         check(self._lib.skd_get_counters(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), self._h)
         return {"launches": a.value, "h2d_bytes": b.value, "d2h_bytes": c.value}
 
+    def profile(self, enable=-1):
+        """Read (and with enable in {0,1} reset + switch) the evaluation-kernel timers."""
+        ms, fl = ctypes.c_double(), ctypes.c_double()
+        nl, nr = ctypes.c_int64(), ctypes.c_int64()
+        check(self._lib.skd_profile(self._h, int(enable), ctypes.byref(ms), ctypes.byref(fl),
+                                    ctypes.byref(nl), ctypes.byref(nr)), self._h)
+        return {"eval_ms": ms.value, "eval_flops": fl.value, "eval_launches": nl.value,
+                "rounds": nr.value}
+
+    def timer_start(self):
+        check(self._lib.skd_timer_start(self._h), self._h)
+
+    def timer_stop(self):
+        """Elapsed device time (seconds) on the library's stream since timer_start()."""
+        ms = ctypes.c_double()
+        check(self._lib.skd_timer_stop(self._h, ctypes.byref(ms)), self._h)
+        return ms.value * 1e-3
+
     # -- solvers ------------------------------------------------------------------
     def logreg_fit_batch(self, C, col_fold, col_pos, fit_intercept=True, tol=1e-4, max_iter=100):
         C = np.ascontiguousarray(C, dtype=np.float64)
@@ -91,6 +109,19 @@ class Engine:
             ctypes.byref(secs)), self._h)
         return {"coef": coef, "n_iter": n_iter, "status": status, "loss": loss,
                 "n_evals": n_evals, "gpu_seconds": secs.value}
+
+    def logreg_loss_grad(self, w, C, col_fold, col_pos, fit_intercept=True):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        B = w.shape[0]
+        assert w.shape[1] == self.d + 1
+        C = np.ascontiguousarray(C, dtype=np.float64)
+        col_fold = np.ascontiguousarray(col_fold, dtype=np.int32)
+        col_pos = np.ascontiguousarray(col_pos, dtype=np.int32)
+        loss = np.empty(B, dtype=np.float64)
+        grad = np.empty((B, self.d + 1), dtype=np.float64)
+        check(self._lib.skd_logreg_loss_grad(self._h, B, ptr(w), ptr(C), ptr(col_fold), ptr(col_pos),
+                                             int(bool(fit_intercept)), ptr(loss), ptr(grad)), self._h)
+        return loss, grad
 
     def linear_score_batch(self, coef, col_fold, col_pos):
         coef = np.ascontiguousarray(coef, dtype=np.float32)
