@@ -1,5 +1,6 @@
 // api.cu -- the C-ABI declared in include/skdist_b200.h.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -33,7 +34,44 @@ static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * 
 
 // Which evaluation kernel serves this batch (SIMT fp32 now; tcgen05 once it lands).
 static int eval_dispatch(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
+  if (w.use_tc) return tc_eval(c, w, n_act, nz_used);
   return simt_eval(c, w, n_act, nz_used);
+}
+
+// Decide the evaluation path for a batch and allocate its evaluation buffers.
+static int alloc_eval_buffers(Ctx* c, Scratch& sx, LogregWork& w, int B) {
+  const int64_t n = c->n, ldx = c->ldx;
+  const int choice = c->kernel_choice;
+  if (choice == 2 && !tc_supported(c))
+    return fail(c, "tcgen05 path requested but the staged shape is unsupported (needs d <= 256)");
+  w.use_tc = (choice == 2) || (choice == 0 && tc_supported(c) && getenv("SKDIST_B200_AUTO_TC"));
+  w.cap_sc = (int64_t)4 * c->sm_count * 64 + B + 64;
+  w.nz = 1024;
+  SKD_CUDA(c, sx.alloc(&w.lossp, (size_t)w.cap_sc));
+  SKD_CUDA(c, sx.alloc(&w.gsump, (size_t)w.cap_sc));
+  if (w.use_tc) {
+    if (tc_prepare(c)) return 1;
+    w.ldw = c->tc.dpad;
+    w.gscale = c->tc.gscale;
+    w.slots_pad_cap = (int)round_up(B, 128);
+    size_t wbytes = (size_t)w.slots_pad_cap * c->tc.dpad * 2;
+    SKD_CUDA(c, sx.alloc((uint8_t**)&w.Wh, wbytes));
+    SKD_CUDA(c, sx.alloc((uint8_t**)&w.Wl, wbytes));
+    SKD_CUDA(c, sx.alloc((uint8_t**)&w.sp, (size_t)w.slots_pad_cap * tc_slot_param_bytes()));
+    SKD_CUDA(c, cudaMemsetAsync(w.Wh, 0, wbytes, c->stream));
+    SKD_CUDA(c, cudaMemsetAsync(w.Wl, 0, wbytes, c->stream));
+    SKD_CUDA(c, sx.alloc(&w.gradp, (size_t)w.cap_sc * w.ldw));
+  } else {
+    w.ldw = (int)ldx;
+    w.gscale = nullptr;
+    w.ldg = (int)round_up(B, 64);
+    if ((double)n * w.ldg * 4.0 > 120e9)
+      return fail(c, "skd_logreg_fit_batch: batch too large for one SIMT call (n * B * 4 bytes > 120 GB); split the batch");
+    SKD_CUDA(c, sx.alloc(&w.Wact, (size_t)B * ldx + B));
+    SKD_CUDA(c, sx.alloc(&w.G, (size_t)n * w.ldg));
+    SKD_CUDA(c, sx.alloc(&w.gradp, (size_t)w.cap_sc * ldx));
+  }
+  return 0;
 }
 
 extern "C" {
@@ -95,6 +133,7 @@ int skd_ctx_destroy(skd_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   free_staged(ctx->c);
+  tc_free(&ctx->c);
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;
   return 0;
@@ -112,6 +151,7 @@ static int stage_x_common(Ctx* c, const float* src, int64_t n, int64_t d, int64_
                                 d * sizeof(float), n, kind, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->n = n; c->d = d; c->ldx = ldx;
+  c->tc.x_valid = false;
   if (kind == cudaMemcpyHostToDevice) c->h2d += (int64_t)n * d * sizeof(float);
   return 0;
 }
@@ -136,6 +176,7 @@ int skd_stage_labels(skd_ctx* ctx, const int32_t* y, int64_t n) {
   SKD_CUDA(c, cudaMemcpyAsync(c->ycls, y, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->h2d += n * (int64_t)sizeof(int32_t);
+  c->tc.meta_valid = false;
   return 0;
 }
 
@@ -157,6 +198,7 @@ int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_fo
   Ctx* c = &ctx->c;
   SKD_CUDA(c, cudaSetDevice(c->device));
   if (c->fold) { cudaFree(c->fold); c->fold = nullptr; }
+  c->tc.meta_valid = false;
   c->n_folds = 0;
   c->fold_count.clear();
   if (!fold_id) return 0;  // cleared
@@ -266,9 +308,7 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   LogregWork w;
   w.B = B; w.dp = dp;
   w.vec_stride = (size_t)(5 + 2 * m) * dp + 2 * m;
-  w.ldg = (int)round_up(B, 64);
-  w.nz = 1024;
-  w.cap_sc = (int64_t)4 * c->sm_count * 64 + B + 64;
+  if (alloc_eval_buffers(c, sx, w, B)) return 1;
   SKD_CUDA(c, sx.alloc(&w.sc, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.vec, (size_t)B * w.vec_stride));
   SKD_CUDA(c, sx.alloc(&w.l2, (size_t)B));
@@ -277,13 +317,6 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   SKD_CUDA(c, sx.alloc(&w.col_pos, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.n_evals, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.slot, (size_t)B));
-  SKD_CUDA(c, sx.alloc(&w.Wact, (size_t)B * ldx + B));
-  if ((double)n * w.ldg * 4.0 > 120e9)
-    return fail(c, "skd_logreg_fit_batch: batch too large for one call (n * B * 4 bytes > 120 GB); split the batch");
-  SKD_CUDA(c, sx.alloc(&w.G, (size_t)n * w.ldg));
-  SKD_CUDA(c, sx.alloc(&w.lossp, (size_t)w.cap_sc));
-  SKD_CUDA(c, sx.alloc(&w.gsump, (size_t)w.cap_sc));
-  SKD_CUDA(c, sx.alloc(&w.gradp, (size_t)w.cap_sc * ldx));
   SKD_CUDA(c, sx.alloc(&w.n_act, 1));
   float* dcoef; int32_t *dniter, *dstatus; double* dloss;
   SKD_CUDA(c, sx.alloc(&dcoef, (size_t)B * dp));
@@ -391,16 +424,12 @@ int skd_logreg_loss_grad(skd_ctx* ctx, int32_t B, const double* w_in, const doub
   }
   Scratch sx(c);
   LogregWork w;
-  w.B = B; w.dp = dp; w.ldg = (int)round_up(B, 64); w.nz = 1024;
-  w.cap_sc = (int64_t)4 * c->sm_count * 64 + B + 64;
+  w.B = B; w.dp = dp;
+  if (alloc_eval_buffers(c, sx, w, B)) return 1;
   SKD_CUDA(c, sx.alloc(&w.l2, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.inv_n, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.slot, (size_t)B));
-  SKD_CUDA(c, sx.alloc(&w.Wact, (size_t)B * ldx + B));
-  SKD_CUDA(c, sx.alloc(&w.G, (size_t)n * w.ldg));
-  SKD_CUDA(c, sx.alloc(&w.lossp, (size_t)w.cap_sc));
-  SKD_CUDA(c, sx.alloc(&w.gsump, (size_t)w.cap_sc));
-  SKD_CUDA(c, sx.alloc(&w.gradp, (size_t)w.cap_sc * ldx));
+  SKD_CUDA(c, sx.alloc(&w.n_act, 1));
   double *dx, *df, *dg;
   SKD_CUDA(c, sx.alloc(&dx, (size_t)B * dp));
   SKD_CUDA(c, sx.alloc(&df, (size_t)B));
@@ -408,8 +437,14 @@ int skd_logreg_loss_grad(skd_ctx* ctx, int32_t B, const double* w_in, const doub
   SKD_CUDA(c, cudaMemcpyAsync(w.l2, l2.data(), B * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaMemcpyAsync(w.inv_n, inv_n.data(), B * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaMemcpyAsync(w.slot, hs.data(), B * sizeof(SlotMeta), cudaMemcpyHostToDevice, c->stream));
-  SKD_CUDA(c, cudaMemcpyAsync(w.Wact, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaMemcpyAsync(dx, w_in, (size_t)B * dp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (w.use_tc) {
+    int32_t nb = B;
+    SKD_CUDA(c, cudaMemcpyAsync(w.n_act, &nb, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (tc_export(c, w, B, dx, fit_intercept)) return 1;
+  } else {
+    SKD_CUDA(c, cudaMemcpyAsync(w.Wact, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
   int nz_used = 0;
   if (eval_dispatch(c, w, B, &nz_used)) return 1;
   if (lbfgs_dev_gather(c, w, B, nz_used, fit_intercept, dx, df, dg)) return 1;

@@ -66,7 +66,8 @@ __device__ __forceinline__ double gather_fg(const CtaPar& P, int s, int n_act, i
                                             int ldx, int fit_intercept,
                                             const double* __restrict__ lossp,
                                             const double* __restrict__ gsump,
-                                            const float* __restrict__ gradp, double l2,
+                                            const float* __restrict__ gradp,
+                                            const double* __restrict__ gscale, double l2,
                                             double inv_n, const double* x, double* g) {
   double lsum = 0.0, gsum = 0.0;
   for (int z = 0; z < nz_used; ++z) {
@@ -78,6 +79,7 @@ __device__ __forceinline__ double gather_fg(const CtaPar& P, int s, int n_act, i
     double acc = 0.0;
     for (int z = 0; z < nz_used; ++z) acc += (double)gradp[((size_t)z * n_act + s) * ldx + k];
     double xk = x[k];
+    if (gscale) acc *= gscale[k];
     g[k] = acc * inv_n + l2 * xk;
     wsq += xk * xk;
   }
@@ -90,15 +92,16 @@ __device__ __forceinline__ double gather_fg(const CtaPar& P, int s, int n_act, i
 __global__ void __launch_bounds__(LB_THREADS)
 lb_gather_kernel(int n_act, int nz_used, int d, int ldx, int fit_intercept,
                  const double* __restrict__ lossp, const double* __restrict__ gsump,
-                 const float* __restrict__ gradp, const double* __restrict__ l2v,
+                 const float* __restrict__ gradp, const double* __restrict__ gscale,
+                 const double* __restrict__ l2v,
                  const double* __restrict__ inv_nv, const double* __restrict__ xin,
                  double* __restrict__ fout, double* __restrict__ gout) {
   __shared__ double red[8];
   const int s = blockIdx.x;
   if (s >= n_act) return;
   CtaPar P{red};
-  double f = gather_fg(P, s, n_act, nz_used, d, ldx, fit_intercept, lossp, gsump, gradp, l2v[s],
-                       inv_nv[s], xin + (size_t)s * (d + 1), gout + (size_t)s * (d + 1));
+  double f = gather_fg(P, s, n_act, nz_used, d, ldx, fit_intercept, lossp, gsump, gradp, gscale,
+                       l2v[s], inv_nv[s], xin + (size_t)s * (d + 1), gout + (size_t)s * (d + 1));
   if (threadIdx.x == 0) fout[s] = f;
 }
 
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(LB_THREADS)
 lb_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta* slot, int n_act,
                int nz_used, int d, int ldx, int fit_intercept, const double* __restrict__ lossp,
                const double* __restrict__ gsump, const float* __restrict__ gradp,
+               const double* __restrict__ gscale,
                const double* __restrict__ l2v, const double* __restrict__ inv_nv,
                int32_t* n_evals) {
   __shared__ double red[8];
@@ -137,8 +141,8 @@ lb_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta*
   LbfgsVectors v = col_vectors(vec + (size_t)col * vec_stride, n, m);
   CtaPar P{red};
   const double l2 = l2v[col], inv_n = inv_nv[col];
-  double f = gather_fg(P, s, n_act, nz_used, d, ldx, fit_intercept, lossp, gsump, gradp, l2, inv_n,
-                       v.x, v.g);
+  double f = gather_fg(P, s, n_act, nz_used, d, ldx, fit_intercept, lossp, gsump, gradp, gscale, l2,
+                       inv_n, v.x, v.g);
   __syncthreads();
   lbfgs_advance(P, st, v, f);
   __syncthreads();
@@ -232,8 +236,12 @@ int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max
                                              maxls, tol, ftol, w.slot, w.col_fold, w.col_pos,
                                              w.n_evals, w.n_act);
   // initial iterate is w0 = 0 (SK/linear_model/_logistic.py:443): export zeros
-  SKD_CUDA(c, cudaMemsetAsync(w.Wact, 0, ((size_t)w.B * c->ldx + w.B) * sizeof(float), c->stream));
   c->launches += 1;
+  if (w.use_tc) {
+    if (tc_export(c, w, w.B, nullptr, fit_intercept)) return 1;
+  } else {
+    SKD_CUDA(c, cudaMemsetAsync(w.Wact, 0, ((size_t)w.B * c->ldx + w.B) * sizeof(float), c->stream));
+  }
   SKD_CUDA(c, cudaGetLastError());
   return 0;
 }
@@ -242,12 +250,17 @@ int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_int
                    int* n_act_out) {
   const int d = (int)c->d, ldx = (int)c->ldx;
   lb_step_kernel<<<n_act_in, LB_THREADS, 0, c->stream>>>(
-      w.sc, w.vec, w.vec_stride, w.slot, n_act_in, nz_used, d, ldx, fit_intercept, w.lossp,
-      w.gsump, w.gradp, w.l2, w.inv_n, w.n_evals);
+      w.sc, w.vec, w.vec_stride, w.slot, n_act_in, nz_used, d, w.ldw, fit_intercept, w.lossp,
+      w.gsump, w.gradp, w.gscale, w.l2, w.inv_n, w.n_evals);
   lb_compact_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, nullptr);
-  lb_export_kernel<<<n_act_in, 128, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.slot, w.n_act, d,
-                                                    ldx, w.B, w.Wact);
-  c->launches += 3;
+  c->launches += 2;
+  if (w.use_tc) {
+    if (tc_export(c, w, n_act_in, nullptr, fit_intercept)) return 1;
+  } else {
+    lb_export_kernel<<<n_act_in, 128, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.slot, w.n_act, d,
+                                                      ldx, w.B, w.Wact);
+    c->launches += 1;
+  }
   SKD_CUDA(c, cudaGetLastError());
   int32_t na = 0;
   SKD_CUDA(c, cudaMemcpyAsync(&na, w.n_act, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -259,9 +272,9 @@ int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_int
 
 int lbfgs_dev_gather(Ctx* c, LogregWork& w, int n_act, int nz_used, int fit_intercept,
                      const double* dx, double* df, double* dg) {
-  lb_gather_kernel<<<n_act, LB_THREADS, 0, c->stream>>>(n_act, nz_used, (int)c->d, (int)c->ldx,
+  lb_gather_kernel<<<n_act, LB_THREADS, 0, c->stream>>>(n_act, nz_used, (int)c->d, w.ldw,
                                                         fit_intercept, w.lossp, w.gsump, w.gradp,
-                                                        w.l2, w.inv_n, dx, df, dg);
+                                                        w.gscale, w.l2, w.inv_n, dx, df, dg);
   c->launches += 1;
   SKD_CUDA(c, cudaGetLastError());
   return 0;

@@ -1,0 +1,753 @@
+// logreg_tc.cu -- fused batched logistic loss + gradient on the 5th-gen tensor cores (sm_100a).
+//
+// One launch evaluates f, g of every active (candidate x fold) column, i.e. replaces, for all
+// columns at once, the two fp32 sgemv passes + pointwise loop that each reference task runs per
+// L-BFGS evaluation (SK/linear_model/_linear_loss.py:291-379; ref search.py:230):
+//
+//     Z  = W  X^T     (slots x rows)   GEMM1   tcgen05.mma, accumulators in TMEM
+//     G  = dloss(Z, y) masked by fold  epilogue (CUDA cores): tcgen05.ld -> math -> tcgen05.st
+//     dW = G  X       (slots x d)      GEMM2   tcgen05.mma, A operand = G straight from TMEM
+//
+// X is read ONCE per tile by TMA into 128B-swizzled shared memory and used by both GEMMs: as
+// the K-major B operand of GEMM1 (K = features) and, through a second descriptor over the same
+// bytes, as the MN-major B operand of GEMM2 (K = rows).
+//
+// fp32 fidelity on tensor cores (there is no fp32 MMA): every operand is split into two fp16
+// numbers, v = hi + lo (22+ mantissa bits after exact power-of-two pre-scaling per feature /
+// per column), and each product is three MMAs hi*hi + hi*lo + lo*hi accumulated in fp32.
+//
+// Work decomposition: a group = 128 slots (MMA M, the TMEM lanes); its rows are cut into P parts;
+// one persistent CTA per (group, part) item.  Per CTA: W_hi stationary in shared memory, W_lo
+// stationary in TMEM, gradient accumulators (128 x d fp32) stationary in TMEM, X streamed in
+// tiles of 64 rows through a ring of 5 half-tile (hi or lo) slots.
+//   warp 0      : TMA producer        warp 1 : MMA issuer (+ TMEM allocation)
+//   warps 2..5  : epilogue, one TMEM lane quadrant each (lane = slot)
+// TMEM columns : [0,256) grad accumulator | [256,384) W_lo (packed fp16 pairs) |
+//                [384,448) Z/G buffer 0 | [448,512) Z/G buffer 1
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "skd_internal.h"
+
+namespace skd {
+
+constexpr int TC_BC = 128;       // slots per group
+constexpr int TC_R = 64;         // rows per tile
+constexpr int TC_NS = 5;         // ring slots (half tiles)
+constexpr int TC_THREADS = 192;
+constexpr uint32_t TM_GRAD = 0, TM_WLO = 256, TM_Z0 = 384;
+constexpr float XSCALE_TARGET_EXP = 13.f;   // column max scaled into [2^13, 2^14)
+constexpr float GSCALE = 16384.f;           // 2^14
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must trap (error reported to the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  printf("skdist_b200 tc kernel: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag,
+         blockIdx.x, threadIdx.x, parity);
+  __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int x, int y,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
+      "%3}], [%4];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc,
+                                       uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::
+          "r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// pack two floats to f16x2: low half = lo_elem (even k), high half = hi_elem (odd k)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  __half2 h = *reinterpret_cast<__half2*>(&v);
+  return __half22float2(h);
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, cute/arch/mma_sm100_desc.hpp):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64) (2 = 128B swizzle)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1<<4), a/b format F16 (0),
+// a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// data preparation kernels
+// ---------------------------------------------------------------------------------------------
+// per-feature max |x|
+__global__ void tc_colmax_kernel(const float* __restrict__ X, int64_t n, int ldx, int d,
+                                 unsigned int* __restrict__ colmax_bits) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d) return;
+  int64_t r0 = (int64_t)blockIdx.y * 4096;
+  int64_t r1 = r0 + 4096 < n ? r0 + 4096 : n;
+  float m = 0.f;
+  for (int64_t r = r0; r < r1; ++r) m = fmaxf(m, fabsf(X[r * ldx + k]));
+  atomicMax(&colmax_bits[k], __float_as_uint(m));  // non-negative floats order as uints
+}
+
+// scale[k] = 2^(13 - floor(log2(colmax))) ; gscale[k] = 1 / (scale[k] * 2^14)
+__global__ void tc_scale_kernel(const unsigned int* __restrict__ colmax_bits, int d, int dpad,
+                                float* __restrict__ xscale, double* __restrict__ gscale) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= dpad) return;
+  float s = 1.f;
+  if (k < d) {
+    float m = __uint_as_float(colmax_bits[k]);
+    if (m > 0.f && isfinite(m)) {
+      int e;
+      frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)  -> floor(log2 m) = e - 1
+      s = ldexpf(1.f, (int)XSCALE_TARGET_EXP - (e - 1));
+    }
+  }
+  xscale[k] = s;
+  gscale[k] = 1.0 / ((double)s * (double)GSCALE);
+}
+
+// Xh, Xl [npad x dpad] fp16 (zero padded), rowmeta[npad] = (fold << 24) | class id (0xFF fold: pad)
+__global__ void tc_split_kernel(const float* __restrict__ X, int64_t n, int64_t npad, int ldx, int d,
+                                int dpad, const float* __restrict__ xscale,
+                                __half* __restrict__ Xh, __half* __restrict__ Xl) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = npad * dpad;
+  if (idx >= total) return;
+  int64_t r = idx / dpad;
+  int k = (int)(idx - r * dpad);
+  float v = 0.f;
+  if (r < n && k < d) v = X[r * ldx + k] * xscale[k];
+  __half h = __float2half_rn(v);
+  __half l = __float2half_rn(v - __half2float(h));
+  Xh[idx] = h;
+  Xl[idx] = l;
+}
+
+__global__ void tc_rowmeta_kernel(const int32_t* __restrict__ ycls, const int8_t* __restrict__ fold,
+                                  int64_t n, int64_t npad, uint32_t* __restrict__ rowmeta) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= npad) return;
+  uint32_t m = 0xFF000000u;
+  if (r < n) {
+    uint32_t f = fold ? (uint32_t)(uint8_t)fold[r] : 0u;
+    m = (f << 24) | ((uint32_t)ycls[r] & 0x00FFFFFFu);
+  }
+  rowmeta[r] = m;
+}
+
+// Export of the active slots' iterates in tensor-core form (replaces lb_export_kernel):
+// w32 = (float)x (SK/_linear_loss.py:216), W' = w32 / xscale * t, t = 2^(13 - floor(log2 max|w32/xscale|)),
+// Wh/Wl [slots_pad x dpad] fp16, wmeta[slot] = {1/t, bias, fold, pos}
+struct TcSlotParam {
+  float inv_t;
+  float bias;
+  int32_t fold;
+  int32_t pos;
+};
+
+__global__ void __launch_bounds__(128)
+tc_export_kernel(const double* __restrict__ vec, size_t vec_stride, const SlotMeta* __restrict__ slot,
+                 const int32_t* __restrict__ n_act, int d, int dpad, const float* __restrict__ xscale,
+                 __half* __restrict__ Wh, __half* __restrict__ Wl, TcSlotParam* __restrict__ sp,
+                 const double* __restrict__ xin /* optional: explicit points [slots x (d+1)] */,
+                 int fit_intercept) {
+  __shared__ float red[4];
+  const int s = blockIdx.x;
+  if (s >= *n_act) return;
+  const SlotMeta sm = slot[s];
+  const double* x = xin ? xin + (size_t)s * (d + 1) : vec + (size_t)sm.col * vec_stride;
+  float m = 0.f;
+  for (int k = threadIdx.x; k < d; k += 128) m = fmaxf(m, fabsf((float)x[k] / xscale[k]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  float t = 1.f;
+  if (m > 0.f && isfinite(m)) {
+    int e;
+    frexpf(m, &e);
+    t = ldexpf(1.f, (int)XSCALE_TARGET_EXP - (e - 1));
+  }
+  for (int k = threadIdx.x; k < dpad; k += 128) {
+    float v = 0.f;
+    if (k < d) v = ((float)x[k] / xscale[k]) * t;   // power-of-two scalings: exact
+    __half h = __float2half_rn(v);
+    __half l = __float2half_rn(v - __half2float(h));
+    Wh[(size_t)s * dpad + k] = h;
+    Wl[(size_t)s * dpad + k] = l;
+  }
+  if (threadIdx.x == 0) {
+    TcSlotParam p;
+    p.inv_t = 1.f / t;
+    p.bias = fit_intercept ? (float)x[d] : 0.f;
+    p.fold = sm.fold;
+    p.pos = sm.pos;
+    sp[s] = p;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------------
+struct TcParams {
+  const __half* Wl;          // [slots_pad x dpad]
+  const TcSlotParam* sp;     // [slots]
+  const uint32_t* rowmeta;   // [npad]
+  double* lossp;             // [P x n_act]
+  double* gsump;             // [P x n_act]
+  float* gradp;              // [P x n_act x ldw]
+  int n_act;
+  int groups;
+  int parts;                 // P
+  int n_tiles;               // npad / 64
+  int nchunk;                // dpad / 64
+  int ldw;                   // leading dimension of gradp (== dpad)
+};
+
+struct __align__(8) TcBarriers {
+  uint64_t full[TC_NS];
+  uint64_t empty[TC_NS];
+  uint64_t z_full[2];
+  uint64_t g_full[2];
+  uint64_t w_full;
+  uint64_t wl_full;
+  uint64_t acc_done;
+  uint64_t acc_free;
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+               const __grid_constant__ CUtensorMap map_wh, const TcParams prm) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = prm.nchunk;
+  // carve shared memory (1024-byte aligned for the 128B swizzle atoms)
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const uint32_t wh_chunk_bytes = TC_BC * 128;     // [128 slots x 64 fp16]
+  const uint32_t x_chunk_bytes = TC_R * 128;       // [64 rows x 64 fp16]
+  const uint32_t slot_bytes = nchunk * x_chunk_bytes;
+  uint8_t* s_wh = base;
+  uint8_t* s_ring = s_wh + nchunk * wh_chunk_bytes;
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(s_ring + TC_NS * slot_bytes);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_NS; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->z_full[i], 1); mbar_init(&bars->g_full[i], 128); }
+    mbar_init(&bars->w_full, 1);
+    mbar_init(&bars->wl_full, 128);
+    mbar_init(&bars->acc_done, 1);
+    mbar_init(&bars->acc_free, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&bars->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  const int total_items = prm.groups * prm.parts;
+  const int tiles_per_part = (prm.n_tiles + prm.parts - 1) / prm.parts;
+
+  if (warp == 0) {
+    // ================================ TMA producer ==========================================
+    if (lane == 0) {
+      uint32_t h = 0;  // running half-tile counter (ring position), persists across items
+      int it_local = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it_local) {
+        const int g = item / prm.parts, p = item % prm.parts;
+        const int t0 = p * tiles_per_part;
+        const int t1 = min(prm.n_tiles, t0 + tiles_per_part);
+        // W_hi of this group: wait until the previous item's MMAs are done with the buffer
+        if (it_local > 0) mbar_wait(&bars->acc_done, (it_local - 1) & 1, 100);
+        mbar_expect_tx(&bars->w_full, nchunk * wh_chunk_bytes);
+        for (int c = 0; c < nchunk; ++c)
+          tma_load_2d(s_wh + c * wh_chunk_bytes, &map_wh, c * 64, g * TC_BC, &bars->w_full);
+        for (int t = t0; t < t1; ++t) {
+          for (int half = 0; half < 2; ++half, ++h) {
+            const uint32_t sl = h % TC_NS, ph = (h / TC_NS) & 1;
+            mbar_wait(&bars->empty[sl], ph ^ 1, 101);
+            mbar_expect_tx(&bars->full[sl], slot_bytes);
+            const CUtensorMap* mp = half == 0 ? &map_xh : &map_xl;
+            for (int c = 0; c < nchunk; ++c)
+              tma_load_2d(s_ring + sl * slot_bytes + c * x_chunk_bytes, mp, c * 64, t * TC_R,
+                          &bars->full[sl]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ============================================
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc(TC_BC, TC_R, 0);              // GEMM1: N = 64 rows
+      const uint32_t idesc2 = make_idesc(TC_BC, nchunk * 64, 1);       // GEMM2: N = dpad, B MN-major
+      const int ksteps1 = nchunk * 4;                                  // K = dpad, 16 per MMA
+      uint32_t h = 0;       // half-tile counter, mirrors the producer
+      uint32_t tcount = 0;  // tile counter (Z buffer = tcount & 1)
+      int it_local = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it_local) {
+        const int p = item % prm.parts;
+        const int t0 = p * tiles_per_part;
+        const int t1 = min(prm.n_tiles, t0 + tiles_per_part);
+        const int nt = t1 - t0;
+        mbar_wait(&bars->w_full, it_local & 1, 200);
+        mbar_wait(&bars->wl_full, it_local & 1, 201);
+        if (it_local > 0) mbar_wait(&bars->acc_free, (it_local - 1) & 1, 202);
+        tc_fence_after();
+        const uint32_t wh_addr = smem_u32(s_wh);
+
+        auto issue_g1 = [&](uint32_t hh, uint32_t tc) {
+          const uint32_t zcol = tmem + TM_Z0 + (tc & 1) * 64;
+          // X_hi half tile
+          {
+            const uint32_t sl = hh % TC_NS, ph = (hh / TC_NS) & 1;
+            mbar_wait(&bars->full[sl], ph, 210);
+            tc_fence_after();
+            const uint32_t xb = smem_u32(s_ring + sl * slot_bytes);
+            for (int ks = 0; ks < ksteps1; ++ks) {
+              const int c = ks >> 2, kk = ks & 3;
+              const uint64_t bdesc = make_desc(xb + c * x_chunk_bytes + kk * 32, 16, 1024);
+              const uint64_t adesc = make_desc(wh_addr + c * wh_chunk_bytes + kk * 32, 16, 1024);
+              mma_ss(zcol, adesc, bdesc, idesc1, ks > 0 ? 1u : 0u);          // W_hi * X_hi
+              mma_ts(zcol, tmem + TM_WLO + ks * 8, bdesc, idesc1, 1u);       // W_lo * X_hi
+            }
+          }
+          // X_lo half tile
+          {
+            const uint32_t sl = (hh + 1) % TC_NS, ph = ((hh + 1) / TC_NS) & 1;
+            mbar_wait(&bars->full[sl], ph, 211);
+            tc_fence_after();
+            const uint32_t xb = smem_u32(s_ring + sl * slot_bytes);
+            for (int ks = 0; ks < ksteps1; ++ks) {
+              const int c = ks >> 2, kk = ks & 3;
+              const uint64_t bdesc = make_desc(xb + c * x_chunk_bytes + kk * 32, 16, 1024);
+              const uint64_t adesc = make_desc(wh_addr + c * wh_chunk_bytes + kk * 32, 16, 1024);
+              mma_ss(zcol, adesc, bdesc, idesc1, 1u);                        // W_hi * X_lo
+            }
+          }
+          tc_commit(&bars->z_full[tc & 1]);
+        };
+        auto issue_g2 = [&](uint32_t hh, uint32_t tc, bool first_tile) {
+          const uint32_t gcol = tmem + TM_Z0 + (tc & 1) * 64;
+          mbar_wait(&bars->g_full[tc & 1], (tc >> 1) & 1, 220);
+          tc_fence_after();
+          const uint32_t sl_h = hh % TC_NS, sl_l = (hh + 1) % TC_NS;
+          const uint32_t xh = smem_u32(s_ring + sl_h * slot_bytes);
+          const uint32_t xl = smem_u32(s_ring + sl_l * slot_bytes);
+          // B operand MN-major: N (features) contiguous within a chunk, chunks LBO apart;
+          // K (rows) in groups of 8 rows SBO = 1024 B apart; one MMA covers 16 rows = 2048 B
+          for (int ks = 0; ks < TC_R / 16; ++ks) {
+            const uint64_t bh = make_desc(xh + ks * 2048, x_chunk_bytes, 1024);
+            mma_ts(tmem + TM_GRAD, gcol + ks * 16, bh, idesc2, (first_tile && ks == 0) ? 0u : 1u);  // G_hi * X_hi
+            mma_ts(tmem + TM_GRAD, gcol + ks * 16 + 8, bh, idesc2, 1u);                             // G_lo * X_hi
+          }
+          tc_commit(&bars->empty[sl_h]);
+          for (int ks = 0; ks < TC_R / 16; ++ks) {
+            const uint64_t bl = make_desc(xl + ks * 2048, x_chunk_bytes, 1024);
+            mma_ts(tmem + TM_GRAD, gcol + ks * 16, bl, idesc2, 1u);                                 // G_hi * X_lo
+          }
+          tc_commit(&bars->empty[sl_l]);
+        };
+
+        if (nt > 0) issue_g1(h, tcount);
+        for (int i = 0; i < nt; ++i) {
+          if (i + 1 < nt) issue_g1(h + 2 * (i + 1), tcount + i + 1);
+          issue_g2(h + 2 * i, tcount + i, i == 0);
+        }
+        h += 2 * nt;
+        tcount += nt;
+        tc_commit(&bars->acc_done);
+      }
+    }
+  } else {
+    // ================================ epilogue warps ========================================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int lane_in_group = q * 32 + lane;      // slot within the group == TMEM lane
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t tcount = 0;
+    int it_local = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it_local) {
+      const int g = item / prm.parts, p = item % prm.parts;
+      const int t0 = p * tiles_per_part;
+      const int t1 = min(prm.n_tiles, t0 + tiles_per_part);
+      const int nt = t1 - t0;
+      const int slot = g * TC_BC + lane_in_group;
+      const bool valid = slot < prm.n_act;
+      TcSlotParam sp;
+      sp.inv_t = 1.f; sp.bias = 0.f; sp.fold = -1; sp.pos = -1;
+      if (valid) sp = prm.sp[slot];
+      // previous item's accumulators must have been flushed by all epilogue threads (same threads)
+      // and its MMAs finished reading W_lo: guaranteed by the acc_done wait at the end of the item.
+      {  // W_lo row of this slot -> TMEM (packed fp16 pairs), 16 columns (32 values) at a time
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.Wl + (size_t)slot * (nchunk * 64));
+        for (int c16 = 0; c16 < nchunk * 2; ++c16) {
+          uint32_t r[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = valid ? __ldg(src + c16 * 16 + j) : 0u;
+          tmem_st16(tl + TM_WLO + c16 * 16, r);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars->wl_full);
+      }
+      double lsum = 0.0, gsum = 0.0;
+      for (int i = 0; i < nt; ++i, ++tcount) {
+        const int t = t0 + i;
+        const uint32_t zb = tl + TM_Z0 + (tcount & 1) * 64;
+        mbar_wait(&bars->z_full[tcount & 1], (tcount >> 1) & 1, 300);
+        tc_fence_after();
+        float lt = 0.f, gt = 0.f;
+#pragma unroll 1
+        for (int ch = 0; ch < TC_R / 16; ++ch) {
+          uint32_t zr[16];
+          tmem_ld16(zb + ch * 16, zr);
+          const uint4* rm4 = reinterpret_cast<const uint4*>(prm.rowmeta + (size_t)t * TC_R + ch * 16);
+          uint32_t rm[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v = __ldg(rm4 + j);
+            rm[4 * j] = v.x; rm[4 * j + 1] = v.y; rm[4 * j + 2] = v.z; rm[4 * j + 3] = v.w;
+          }
+          tmem_wait_ld();
+          float gv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float z = fmaf(__uint_as_float(zr[j]), sp.inv_t, sp.bias);
+            const int fr = (int)(rm[j] >> 24);
+            const bool yb = (int)(rm[j] & 0x00FFFFFFu) == sp.pos;
+            const bool train = (fr != 0xFF) && (fr != sp.fold);
+            const float u = yb ? -z : z;
+            const float e = ex2_approx(-fabsf(u) * 1.4426950408889634f);
+            const float s1 = 1.f + e;
+            const float loss = fmaxf(u, 0.f) + lg2_approx(s1) * 0.6931471805599453f;
+            const float r = rcp_approx(s1);
+            const float sig = (u >= 0.f) ? r : e * r;
+            const float gg = yb ? -sig : sig;
+            gv[j] = train ? gg : 0.f;
+            lt += train ? loss : 0.f;
+            gt += gv[j];
+          }
+          uint32_t out[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float a = gv[2 * j] * GSCALE, b = gv[2 * j + 1] * GSCALE;
+            const uint32_t hi = pack_f16x2(a, b);
+            const float2 hf = unpack_f16x2(hi);
+            out[j] = hi;
+            out[8 + j] = pack_f16x2(a - hf.x, b - hf.y);
+          }
+          tmem_st16(zb + ch * 16, out);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bars->g_full[tcount & 1]);
+        lsum += (double)lt;
+        gsum += (double)gt;
+      }
+      // flush the gradient accumulators of this item
+      mbar_wait(&bars->acc_done, it_local & 1, 310);
+      tc_fence_after();
+      {
+        float* dst = prm.gradp + ((size_t)p * prm.n_act + slot) * prm.ldw;
+        for (int c16 = 0; c16 < nchunk * 4; ++c16) {
+          uint32_t r[16];
+          tmem_ld16(tl + TM_GRAD + c16 * 16, r);
+          tmem_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(dst + c16 * 16 + 4 * j) =
+                  make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          }
+        }
+        if (valid) {
+          prm.lossp[(size_t)p * prm.n_act + slot] = lsum;
+          prm.gsump[(size_t)p * prm.n_act + slot] = gsum;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&bars->acc_free);
+    }
+  }
+
+  // teardown
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp16 row-major [rows x cols] tensor, box = [box_rows x 64 cols], 128B swizzle
+static int make_map(Ctx* c, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols,
+                    uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(c, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * sizeof(__half)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char b[128];
+    snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return fail(c, b);
+  }
+  return 0;
+}
+
+bool tc_supported(const Ctx* c) { return c->d >= 1 && c->d <= 256; }
+
+void tc_free(Ctx* c) {
+  TcData& t = c->tc;
+  if (t.Xh) cudaFree(t.Xh);
+  if (t.Xl) cudaFree(t.Xl);
+  if (t.rowmeta) cudaFree(t.rowmeta);
+  if (t.xscale) cudaFree(t.xscale);
+  if (t.gscale) cudaFree(t.gscale);
+  t = TcData();
+}
+
+// Build (or refresh) the fp16-split copy of X and the per-row metadata.
+int tc_prepare(Ctx* c) {
+  TcData& t = c->tc;
+  const int64_t n = c->n;
+  const int d = (int)c->d, ldx = (int)c->ldx;
+  const int dpad = (d + 63) / 64 * 64;
+  const int64_t npad = (n + TC_R - 1) / TC_R * TC_R;
+  if (!t.x_valid) {
+    tc_free(c);
+    t.dpad = dpad;
+    t.npad = npad;
+    SKD_CUDA(c, cudaMalloc((void**)&t.Xh, (size_t)npad * dpad * sizeof(__half)));
+    SKD_CUDA(c, cudaMalloc((void**)&t.Xl, (size_t)npad * dpad * sizeof(__half)));
+    SKD_CUDA(c, cudaMalloc((void**)&t.rowmeta, (size_t)npad * sizeof(uint32_t)));
+    SKD_CUDA(c, cudaMalloc((void**)&t.xscale, (size_t)dpad * sizeof(float)));
+    SKD_CUDA(c, cudaMalloc((void**)&t.gscale, (size_t)dpad * sizeof(double)));
+    unsigned int* colmax;
+    SKD_CUDA(c, cudaMalloc((void**)&colmax, (size_t)dpad * sizeof(unsigned int)));
+    SKD_CUDA(c, cudaMemsetAsync(colmax, 0, (size_t)dpad * sizeof(unsigned int), c->stream));
+    dim3 g1((d + 127) / 128, (unsigned)((n + 4095) / 4096));
+    tc_colmax_kernel<<<g1, 128, 0, c->stream>>>(c->X, n, ldx, d, colmax);
+    tc_scale_kernel<<<(dpad + 127) / 128, 128, 0, c->stream>>>(colmax, d, dpad, t.xscale, t.gscale);
+    int64_t total = npad * dpad;
+    tc_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(
+        c->X, n, npad, ldx, d, dpad, t.xscale, (__half*)t.Xh, (__half*)t.Xl);
+    c->launches += 3;
+    SKD_CUDA(c, cudaGetLastError());
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(colmax);
+    if (make_map(c, &t.map_xh, t.Xh, (uint64_t)npad, (uint64_t)dpad, TC_R)) return 1;
+    if (make_map(c, &t.map_xl, t.Xl, (uint64_t)npad, (uint64_t)dpad, TC_R)) return 1;
+    t.x_valid = true;
+    t.meta_valid = false;
+  }
+  if (!t.meta_valid) {
+    if (!c->ycls) return fail(c, "tc_prepare: labels not staged");
+    tc_rowmeta_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(c->ycls, c->fold, n, npad,
+                                                                            t.rowmeta);
+    c->launches += 1;
+    SKD_CUDA(c, cudaGetLastError());
+    t.meta_valid = true;
+  }
+  return 0;
+}
+
+int tc_export(Ctx* c, LogregWork& w, int n_act_upper, const double* xin, int fit_intercept) {
+  TcData& t = c->tc;
+  tc_export_kernel<<<n_act_upper, 128, 0, c->stream>>>(w.vec, w.vec_stride, w.slot, w.n_act, (int)c->d,
+                                                       t.dpad, t.xscale, (__half*)w.Wh, (__half*)w.Wl,
+                                                       (TcSlotParam*)w.sp, xin, fit_intercept);
+  c->launches += 1;
+  SKD_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+size_t tc_slot_param_bytes() { return sizeof(TcSlotParam); }
+
+int tc_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
+  TcData& t = c->tc;
+  *nz_used = 0;
+  if (n_act <= 0) return 0;
+  const int nchunk = t.dpad / 64;
+  const int groups = (n_act + TC_BC - 1) / TC_BC;
+  const int n_tiles = (int)(t.npad / TC_R);
+  int parts = c->sm_count / groups;
+  if (parts < 1) parts = 1;
+  if (parts > n_tiles) parts = n_tiles;
+  if ((int64_t)parts * n_act > w.cap_sc) parts = (int)(w.cap_sc / n_act);
+  if (parts < 1) return fail(c, "tc_eval: partial buffer too small");
+  const int tiles_per_part = (n_tiles + parts - 1) / parts;
+  parts = (n_tiles + tiles_per_part - 1) / tiles_per_part;   // drop empty parts
+  CUtensorMap map_wh;
+  const int slots_pad = groups * TC_BC;
+  if (make_map(c, &map_wh, w.Wh, (uint64_t)w.slots_pad_cap, (uint64_t)t.dpad, TC_BC)) return 1;
+  (void)slots_pad;
+  TcParams prm;
+  prm.Wl = (const __half*)w.Wl;
+  prm.sp = (const TcSlotParam*)w.sp;
+  prm.rowmeta = t.rowmeta;
+  prm.lossp = w.lossp;
+  prm.gsump = w.gsump;
+  prm.gradp = w.gradp;
+  prm.n_act = n_act;
+  prm.groups = groups;
+  prm.parts = parts;
+  prm.n_tiles = n_tiles;
+  prm.nchunk = nchunk;
+  prm.ldw = w.ldw;
+  const size_t smem = 1024 + (size_t)nchunk * (TC_BC * 128) + (size_t)TC_NS * nchunk * (TC_R * 128) +
+                      sizeof(TcBarriers) + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SKD_CUDA(c, cudaFuncSetAttribute(tc_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    attr_set = true;
+  }
+  int grid = groups * parts;
+  if (grid > c->sm_count) grid = c->sm_count;
+  tc_eval_kernel<<<grid, TC_THREADS, smem, c->stream>>>(t.map_xh, t.map_xl, map_wh, prm);
+  c->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, std::string("tc_eval launch: ") + cudaGetErrorString(e));
+  *nz_used = parts;
+  return 0;
+}
+
+}  // namespace skd

@@ -1,5 +1,6 @@
 // skd_internal.h -- context object and helpers shared by the .cu translation units.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -13,6 +14,19 @@ namespace skd {
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+};
+
+// fp16-split copy of the staged X for the tensor-core path (logreg_tc.cu)
+struct TcData {
+  void* Xh = nullptr;          // [npad x dpad] fp16, X * xscale rounded to fp16
+  void* Xl = nullptr;          // [npad x dpad] fp16, remainder
+  uint32_t* rowmeta = nullptr; // [npad] (fold << 24) | class id ; fold 0xFF = padding row
+  float* xscale = nullptr;     // [dpad] power-of-two per-feature scale
+  double* gscale = nullptr;    // [dpad] 1 / (xscale * 2^14): un-scales the gradient partials
+  int dpad = 0;
+  int64_t npad = 0;
+  bool x_valid = false, meta_valid = false;
+  CUtensorMap map_xh, map_xl;
 };
 
 struct Ctx {
@@ -29,6 +43,7 @@ struct Ctx {
   int8_t* fold = nullptr;   // [n]
   int32_t n_folds = 0;
   std::vector<int64_t> fold_count;  // rows per fold id
+  TcData tc;
   // counters
   int64_t launches = 0, h2d = 0, d2h = 0;
   // optional per-evaluation timing (bench.py roofline): CUDA events on `stream` around every
@@ -112,6 +127,14 @@ struct LogregWork {
   double* gsump = nullptr;     // [cap_sc]
   float* gradp = nullptr;      // [cap_sc x ldx]
   int32_t* n_act = nullptr;    // device scalar
+  // tensor-core path (logreg_tc.cu)
+  bool use_tc = false;
+  int32_t ldw = 0;             // leading dimension of gradp rows (ldx for SIMT, dpad for TC)
+  const double* gscale = nullptr;  // per-feature un-scaling of gradp (TC) or nullptr
+  void* Wh = nullptr;          // [slots_pad_cap x dpad] fp16
+  void* Wl = nullptr;          // [slots_pad_cap x dpad] fp16
+  void* sp = nullptr;          // [slots_pad_cap] TcSlotParam
+  int32_t slots_pad_cap = 0;
 };
 
 // forward (Z = X W^T, pointwise loss / gradient on training rows) + backward (G^T X)
@@ -120,6 +143,14 @@ int simt_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used);
 int simt_score(Ctx* c, int B, const float* dW, const SlotMeta* dslot, int64_t* dcorrect,
                int64_t* dcount);
 int simt_decision(Ctx* c, int B, const float* dW, float* dout);
+
+// tensor-core evaluation (logreg_tc.cu)
+bool tc_supported(const Ctx* c);
+void tc_free(Ctx* c);
+int tc_prepare(Ctx* c);
+int tc_export(Ctx* c, LogregWork& w, int n_act_upper, const double* xin, int fit_intercept);
+int tc_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used);
+size_t tc_slot_param_bytes();
 
 // device L-BFGS (lbfgs_dev.cu)
 int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max_iter);
