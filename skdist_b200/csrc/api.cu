@@ -38,13 +38,19 @@ static int eval_dispatch(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
   return simt_eval(c, w, n_act, nz_used);
 }
 
+// 0 = auto: tensor cores whenever the staged shape is supported (d <= 256), else SIMT fp32.
+static bool want_tc(const Ctx* c) {
+  if (c->kernel_choice == 1) return false;
+  if (c->kernel_choice == 2) return true;
+  return tc_supported(c) && !getenv("SKDIST_B200_FORCE_SIMT");
+}
+
 // Decide the evaluation path for a batch and allocate its evaluation buffers.
 static int alloc_eval_buffers(Ctx* c, Scratch& sx, LogregWork& w, int B) {
   const int64_t n = c->n, ldx = c->ldx;
-  const int choice = c->kernel_choice;
-  if (choice == 2 && !tc_supported(c))
+  if (c->kernel_choice == 2 && !tc_supported(c))
     return fail(c, "tcgen05 path requested but the staged shape is unsupported (needs d <= 256)");
-  w.use_tc = (choice == 2) || (choice == 0 && tc_supported(c) && getenv("SKDIST_B200_AUTO_TC"));
+  w.use_tc = want_tc(c);
   w.cap_sc = (int64_t)4 * c->sm_count * 64 + B + 64;
   w.nz = 1024;
   SKD_CUDA(c, sx.alloc(&w.lossp, (size_t)w.cap_sc));
@@ -478,8 +484,6 @@ int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int
     return fail(c, "skd_linear_score_batch: bad arguments");
   SKD_CUDA(c, cudaSetDevice(c->device));
   Scratch sx(c);
-  float* dW;
-  if (pack_coef(c, sx, B, coef, &dW)) return 1;
   std::vector<SlotMeta> hs(B);
   for (int j = 0; j < B; ++j) {
     int f = col_fold[j] >= 0 ? col_fold[j] : (col_fold[j] <= -3 ? -3 - col_fold[j] : -1);
@@ -495,7 +499,38 @@ int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int
   SKD_CUDA(c, cudaMemcpyAsync(dslot, hs.data(), B * sizeof(SlotMeta), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaMemsetAsync(dcorrect, 0, B * sizeof(int64_t), c->stream));
   SKD_CUDA(c, cudaMemsetAsync(dcount, 0, B * sizeof(int64_t), c->stream));
-  if (simt_score(c, B, dW, dslot, dcorrect, dcount)) return 1;
+  if (c->kernel_choice == 2 && !tc_supported(c))
+    return fail(c, "tcgen05 path requested but the staged shape is unsupported (needs d <= 256)");
+  if (want_tc(c)) {
+    // tensor-core GEMM1-only pass with a counting epilogue (logreg_tc.cu, TC_SCORE)
+    if (tc_prepare(c)) return 1;
+    LogregWork w;
+    w.B = B; w.dp = (int)c->d + 1; w.use_tc = true; w.ldw = c->tc.dpad;
+    w.slot = dslot;
+    w.slots_pad_cap = (int)round_up(B, 128);
+    size_t wbytes = (size_t)w.slots_pad_cap * c->tc.dpad * 2;
+    SKD_CUDA(c, sx.alloc((uint8_t**)&w.Wh, wbytes));
+    SKD_CUDA(c, sx.alloc((uint8_t**)&w.Wl, wbytes));
+    SKD_CUDA(c, sx.alloc((uint8_t**)&w.sp, (size_t)w.slots_pad_cap * tc_slot_param_bytes()));
+    SKD_CUDA(c, sx.alloc(&w.n_act, 1));
+    SKD_CUDA(c, cudaMemsetAsync(w.Wh, 0, wbytes, c->stream));
+    SKD_CUDA(c, cudaMemsetAsync(w.Wl, 0, wbytes, c->stream));
+    std::vector<double> hx((size_t)B * w.dp);
+    for (size_t i = 0; i < hx.size(); ++i) hx[i] = (double)coef[i];
+    double* dx;
+    SKD_CUDA(c, sx.alloc(&dx, hx.size()));
+    int32_t nb = B;
+    SKD_CUDA(c, cudaMemcpyAsync(dx, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(w.n_act, &nb, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h2d += (int64_t)hx.size() * 8;
+    if (tc_export(c, w, B, dx, 1)) return 1;
+    if (tc_score(c, w, B, dcorrect, dcount)) return 1;
+  } else {
+    float* dW;
+    if (pack_coef(c, sx, B, coef, &dW)) return 1;
+    if (simt_score(c, B, dW, dslot, dcorrect, dcount)) return 1;
+  }
   SKD_CUDA(c, cudaMemcpyAsync(correct_out, dcorrect, B * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
   SKD_CUDA(c, cudaMemcpyAsync(count_out, dcount, B * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -21,11 +21,13 @@
 // stationary in TMEM, gradient accumulators (128 x d fp32) stationary in TMEM, X streamed in
 // tiles of 64 rows through a ring of 5 half-tile (hi or lo) slots.
 //   warp 0      : TMA producer        warp 1 : MMA issuer (+ TMEM allocation)
-//   warps 2..5  : epilogue, one TMEM lane quadrant each (lane = slot)
+//   warps 2..9  : epilogue, two warps per TMEM lane quadrant (lane = slot), 32 rows of the tile each
 // TMEM columns : [0,256) grad accumulator | [256,384) W_lo (packed fp16 pairs) |
 //                [384,448) Z/G buffer 0 | [448,512) Z/G buffer 1
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "skd_internal.h"
 
@@ -34,7 +36,9 @@ namespace skd {
 constexpr int TC_BC = 128;       // slots per group
 constexpr int TC_R = 64;         // rows per tile
 constexpr int TC_NS = 5;         // ring slots (half tiles)
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;     // two per TMEM lane quadrant
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
 constexpr uint32_t TM_GRAD = 0, TM_WLO = 256, TM_Z0 = 384;
 constexpr float XSCALE_TARGET_EXP = 13.f;   // column max scaled into [2^13, 2^14)
 constexpr float GSCALE = 16384.f;           // 2^14
@@ -110,6 +114,42 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
+// Warp-uniform issue forms: every lane executes the statement with identical operands (so the
+// descriptor arithmetic stays in the uniform datapath) and only the elected lane issues.
+__device__ __forceinline__ void mma_ss_u(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo,
+                                         uint32_t bhi, uint32_t idesc, uint32_t accumulate,
+                                         uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_u(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi,
+                                         uint32_t idesc, uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_u(uint64_t* bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
+          smem_u32(bar)),
+      "r"(leader)
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
@@ -300,15 +340,17 @@ struct TcParams {
   const __half* Wl;          // [slots_pad x dpad]
   const TcSlotParam* sp;     // [slots]
   const uint32_t* rowmeta;   // [npad]
-  double* lossp;             // [P x n_act]
-  double* gsump;             // [P x n_act]
-  float* gradp;              // [P x n_act x ldw]
+  double* lossp;             // [nz x n_act]        (fit)
+  double* gsump;             // [nz x n_act]        (fit)
+  float* gradp;              // [nz x n_act x ldw]  (fit)
+  unsigned long long* correct;  // [n_act]          (score)
+  unsigned long long* count;    // [n_act]          (score)
   int n_act;
   int groups;
-  int parts;                 // P
   int n_tiles;               // npad / 64
-  int nchunk;                // dpad / 64
   int ldw;                   // leading dimension of gradp (== dpad)
+  int parts;                 // > 0: aligned split (CTA = (group, part), same row ranges for every group)
+                             // 0  : balanced split (groups * n_tiles units cut into gridDim.x ranges)
 };
 
 struct __align__(8) TcBarriers {
@@ -324,28 +366,48 @@ struct __align__(8) TcBarriers {
   uint32_t pad;
 };
 
+// Work split: the (group, tile) pairs form one list of groups * n_tiles units, cut into
+// gridDim.x equal contiguous ranges, one per CTA, so every SM gets the same number of tiles.
+// A CTA's range touches one or two groups ("items"); the partial results of item (g, cta)
+// go to partial index z = cta - first_cta(g).
+struct TcRange {
+  long long u0, u1;
+};
+__device__ __forceinline__ long long tc_unit_begin(long long cta, long long units, long long grid) {
+  return cta * units / grid;
+}
+__device__ __forceinline__ int tc_first_cta(int g, int n_tiles, long long units, int grid) {
+  long long u = (long long)g * n_tiles;
+  long long c = u * grid / units;
+  while (c + 1 < grid && tc_unit_begin(c + 1, units, grid) <= u) ++c;
+  while (c > 0 && tc_unit_begin(c, units, grid) > u) --c;
+  return (int)c;
+}
+
+enum { TC_FIT = 0, TC_SCORE = 1 };
+
+template <int NCHUNK, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                const __grid_constant__ CUtensorMap map_wh, const TcParams prm) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nchunk = prm.nchunk;
   // carve shared memory (1024-byte aligned for the 128B swizzle atoms)
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const uint32_t wh_chunk_bytes = TC_BC * 128;     // [128 slots x 64 fp16]
-  const uint32_t x_chunk_bytes = TC_R * 128;       // [64 rows x 64 fp16]
-  const uint32_t slot_bytes = nchunk * x_chunk_bytes;
+  constexpr uint32_t WH_CHUNK = TC_BC * 128;     // [128 slots x 64 fp16]
+  constexpr uint32_t X_CHUNK = TC_R * 128;       // [64 rows x 64 fp16]
+  constexpr uint32_t SLOT_BYTES = NCHUNK * X_CHUNK;
   uint8_t* s_wh = base;
-  uint8_t* s_ring = s_wh + nchunk * wh_chunk_bytes;
-  TcBarriers* bars = reinterpret_cast<TcBarriers*>(s_ring + TC_NS * slot_bytes);
+  uint8_t* s_ring = s_wh + NCHUNK * WH_CHUNK;
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(s_ring + TC_NS * SLOT_BYTES);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_NS; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->z_full[i], 1); mbar_init(&bars->g_full[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->z_full[i], 1); mbar_init(&bars->g_full[i], TC_EPI_THREADS); }
     mbar_init(&bars->w_full, 1);
-    mbar_init(&bars->wl_full, 128);
+    mbar_init(&bars->wl_full, TC_EPI_THREADS);
     mbar_init(&bars->acc_done, 1);
-    mbar_init(&bars->acc_free, 128);
+    mbar_init(&bars->acc_free, TC_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -360,229 +422,315 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  const int total_items = prm.groups * prm.parts;
-  const int tiles_per_part = (prm.n_tiles + prm.parts - 1) / prm.parts;
+  const long long units = (long long)prm.groups * prm.n_tiles;
+  long long u_begin, u_end;
+  if (prm.parts > 0) {
+    // aligned: all groups stream the same rows at the same time -> X is fetched from HBM once
+    // and the other groups hit L2
+    const int gg = blockIdx.x / prm.parts, pp = blockIdx.x % prm.parts;
+    u_begin = (long long)gg * prm.n_tiles + (long long)pp * prm.n_tiles / prm.parts;
+    u_end = (long long)gg * prm.n_tiles + (long long)(pp + 1) * prm.n_tiles / prm.parts;
+  } else {
+    u_begin = tc_unit_begin(blockIdx.x, units, gridDim.x);
+    u_end = tc_unit_begin(blockIdx.x + 1, units, gridDim.x);
+  }
+  const int g_first = (int)(u_begin / prm.n_tiles);
+  const int g_last = u_end > u_begin ? (int)((u_end - 1) / prm.n_tiles) : g_first - 1;
+  // item (group g) of this CTA covers tiles [t0, t1)
+#define TC_ITEM_RANGE(g, t0, t1)                                                     \
+  const long long _gb = (long long)(g) * prm.n_tiles;                                \
+  const int t0 = (int)((u_begin > _gb ? u_begin : _gb) - _gb);                       \
+  const int t1 = (int)((u_end < _gb + prm.n_tiles ? u_end : _gb + prm.n_tiles) - _gb);
 
   if (warp == 0) {
     // ================================ TMA producer ==========================================
     if (lane == 0) {
       uint32_t h = 0;  // running half-tile counter (ring position), persists across items
       int it_local = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it_local) {
-        const int g = item / prm.parts, p = item % prm.parts;
-        const int t0 = p * tiles_per_part;
-        const int t1 = min(prm.n_tiles, t0 + tiles_per_part);
+      for (int g = g_first; g <= g_last; ++g, ++it_local) {
+        TC_ITEM_RANGE(g, t0, t1)
         // W_hi of this group: wait until the previous item's MMAs are done with the buffer
         if (it_local > 0) mbar_wait(&bars->acc_done, (it_local - 1) & 1, 100);
-        mbar_expect_tx(&bars->w_full, nchunk * wh_chunk_bytes);
-        for (int c = 0; c < nchunk; ++c)
-          tma_load_2d(s_wh + c * wh_chunk_bytes, &map_wh, c * 64, g * TC_BC, &bars->w_full);
+        mbar_expect_tx(&bars->w_full, NCHUNK * WH_CHUNK);
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c)
+          tma_load_2d(s_wh + c * WH_CHUNK, &map_wh, c * 64, g * TC_BC, &bars->w_full);
         for (int t = t0; t < t1; ++t) {
+#pragma unroll
           for (int half = 0; half < 2; ++half, ++h) {
             const uint32_t sl = h % TC_NS, ph = (h / TC_NS) & 1;
             mbar_wait(&bars->empty[sl], ph ^ 1, 101);
-            mbar_expect_tx(&bars->full[sl], slot_bytes);
+            mbar_expect_tx(&bars->full[sl], SLOT_BYTES);
             const CUtensorMap* mp = half == 0 ? &map_xh : &map_xl;
-            for (int c = 0; c < nchunk; ++c)
-              tma_load_2d(s_ring + sl * slot_bytes + c * x_chunk_bytes, mp, c * 64, t * TC_R,
-                          &bars->full[sl]);
+#pragma unroll
+            for (int c = 0; c < NCHUNK; ++c)
+              tma_load_2d(s_ring + sl * SLOT_BYTES + c * X_CHUNK, mp, c * 64, t * TC_R, &bars->full[sl]);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ============================================
-    if (lane == 0) {
-      const uint32_t idesc1 = make_idesc(TC_BC, TC_R, 0);              // GEMM1: N = 64 rows
-      const uint32_t idesc2 = make_idesc(TC_BC, nchunk * 64, 1);       // GEMM2: N = dpad, B MN-major
-      const int ksteps1 = nchunk * 4;                                  // K = dpad, 16 per MMA
+    // The whole warp runs the control flow (waits, counters) with warp-uniform values; the MMAs of
+    // a tile are issued inside one `elect.sync` branch, which lets ptxas keep the descriptor
+    // arithmetic in the uniform datapath (one UIADD3 per MMA instead of an elect/broadcast loop).
+    {
+      constexpr uint32_t idesc1 = make_idesc(TC_BC, TC_R, 0);            // GEMM1: N = 64 rows
+      constexpr uint32_t idesc2 = make_idesc(TC_BC, NCHUNK * 64, 1);     // GEMM2: N = dpad, B MN-major
+      constexpr int KS1 = NCHUNK * 4;                                    // K = dpad, 16 per MMA
+      // descriptors: only the start-address field (low word, >>4 units) changes between MMAs
+      const uint64_t a_base = make_desc(smem_u32(s_wh), 16, 1024);
+      const uint64_t bk_base = make_desc(smem_u32(s_ring), 16, 1024);          // K-major view
+      const uint64_t bmn_base = make_desc(smem_u32(s_ring), X_CHUNK, 1024);    // MN-major view
       uint32_t h = 0;       // half-tile counter, mirrors the producer
       uint32_t tcount = 0;  // tile counter (Z buffer = tcount & 1)
       int it_local = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it_local) {
-        const int p = item % prm.parts;
-        const int t0 = p * tiles_per_part;
-        const int t1 = min(prm.n_tiles, t0 + tiles_per_part);
+      for (int g = g_first; g <= g_last; ++g, ++it_local) {
+        TC_ITEM_RANGE(g, t0, t1)
         const int nt = t1 - t0;
         mbar_wait(&bars->w_full, it_local & 1, 200);
         mbar_wait(&bars->wl_full, it_local & 1, 201);
         if (it_local > 0) mbar_wait(&bars->acc_free, (it_local - 1) & 1, 202);
         tc_fence_after();
-        const uint32_t wh_addr = smem_u32(s_wh);
 
         auto issue_g1 = [&](uint32_t hh, uint32_t tc) {
           const uint32_t zcol = tmem + TM_Z0 + (tc & 1) * 64;
-          // X_hi half tile
-          {
+          {  // X_hi half tile: W_hi * X_hi + W_lo * X_hi
             const uint32_t sl = hh % TC_NS, ph = (hh / TC_NS) & 1;
             mbar_wait(&bars->full[sl], ph, 210);
             tc_fence_after();
-            const uint32_t xb = smem_u32(s_ring + sl * slot_bytes);
-            for (int ks = 0; ks < ksteps1; ++ks) {
-              const int c = ks >> 2, kk = ks & 3;
-              const uint64_t bdesc = make_desc(xb + c * x_chunk_bytes + kk * 32, 16, 1024);
-              const uint64_t adesc = make_desc(wh_addr + c * wh_chunk_bytes + kk * 32, 16, 1024);
-              mma_ss(zcol, adesc, bdesc, idesc1, ks > 0 ? 1u : 0u);          // W_hi * X_hi
-              mma_ts(zcol, tmem + TM_WLO + ks * 8, bdesc, idesc1, 1u);       // W_lo * X_hi
+            const uint64_t bb = bk_base + (uint64_t)((sl * SLOT_BYTES) >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < KS1; ++ks) {
+                const uint32_t aoff = ((ks >> 2) * WH_CHUNK + (ks & 3) * 32) >> 4;
+                const uint32_t boff = ((ks >> 2) * X_CHUNK + (ks & 3) * 32) >> 4;
+                mma_ss(zcol, a_base + aoff, bb + boff, idesc1, ks > 0 ? 1u : 0u);
+                mma_ts(zcol, tmem + TM_WLO + ks * 8, bb + boff, idesc1, 1u);
+              }
             }
+            __syncwarp();
           }
-          // X_lo half tile
-          {
+          {  // X_lo half tile: W_hi * X_lo
             const uint32_t sl = (hh + 1) % TC_NS, ph = ((hh + 1) / TC_NS) & 1;
             mbar_wait(&bars->full[sl], ph, 211);
             tc_fence_after();
-            const uint32_t xb = smem_u32(s_ring + sl * slot_bytes);
-            for (int ks = 0; ks < ksteps1; ++ks) {
-              const int c = ks >> 2, kk = ks & 3;
-              const uint64_t bdesc = make_desc(xb + c * x_chunk_bytes + kk * 32, 16, 1024);
-              const uint64_t adesc = make_desc(wh_addr + c * wh_chunk_bytes + kk * 32, 16, 1024);
-              mma_ss(zcol, adesc, bdesc, idesc1, 1u);                        // W_hi * X_lo
+            const uint64_t bb = bk_base + (uint64_t)((sl * SLOT_BYTES) >> 4);
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < KS1; ++ks) {
+                const uint32_t aoff = ((ks >> 2) * WH_CHUNK + (ks & 3) * 32) >> 4;
+                const uint32_t boff = ((ks >> 2) * X_CHUNK + (ks & 3) * 32) >> 4;
+                mma_ss(zcol, a_base + aoff, bb + boff, idesc1, 1u);
+              }
+              tc_commit(&bars->z_full[tc & 1]);
+              if (MODE == TC_SCORE) {  // no GEMM2: the ring slots are free once GEMM1 has read them
+                tc_commit(&bars->empty[hh % TC_NS]);
+                tc_commit(&bars->empty[(hh + 1) % TC_NS]);
+              }
             }
+            __syncwarp();
           }
-          tc_commit(&bars->z_full[tc & 1]);
         };
         auto issue_g2 = [&](uint32_t hh, uint32_t tc, bool first_tile) {
           const uint32_t gcol = tmem + TM_Z0 + (tc & 1) * 64;
           mbar_wait(&bars->g_full[tc & 1], (tc >> 1) & 1, 220);
           tc_fence_after();
           const uint32_t sl_h = hh % TC_NS, sl_l = (hh + 1) % TC_NS;
-          const uint32_t xh = smem_u32(s_ring + sl_h * slot_bytes);
-          const uint32_t xl = smem_u32(s_ring + sl_l * slot_bytes);
           // B operand MN-major: N (features) contiguous within a chunk, chunks LBO apart;
           // K (rows) in groups of 8 rows SBO = 1024 B apart; one MMA covers 16 rows = 2048 B
-          for (int ks = 0; ks < TC_R / 16; ++ks) {
-            const uint64_t bh = make_desc(xh + ks * 2048, x_chunk_bytes, 1024);
-            mma_ts(tmem + TM_GRAD, gcol + ks * 16, bh, idesc2, (first_tile && ks == 0) ? 0u : 1u);  // G_hi * X_hi
-            mma_ts(tmem + TM_GRAD, gcol + ks * 16 + 8, bh, idesc2, 1u);                             // G_lo * X_hi
+          const uint64_t bh = bmn_base + (uint64_t)((sl_h * SLOT_BYTES) >> 4);
+          const uint64_t bl = bmn_base + (uint64_t)((sl_l * SLOT_BYTES) >> 4);
+          if (elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < TC_R / 16; ++ks) {
+              mma_ts(tmem + TM_GRAD, gcol + ks * 16, bh + ks * 128, idesc2, (first_tile && ks == 0) ? 0u : 1u);
+              mma_ts(tmem + TM_GRAD, gcol + ks * 16 + 8, bh + ks * 128, idesc2, 1u);
+            }
+            tc_commit(&bars->empty[sl_h]);
+#pragma unroll
+            for (int ks = 0; ks < TC_R / 16; ++ks)
+              mma_ts(tmem + TM_GRAD, gcol + ks * 16, bl + ks * 128, idesc2, 1u);
+            tc_commit(&bars->empty[sl_l]);
           }
-          tc_commit(&bars->empty[sl_h]);
-          for (int ks = 0; ks < TC_R / 16; ++ks) {
-            const uint64_t bl = make_desc(xl + ks * 2048, x_chunk_bytes, 1024);
-            mma_ts(tmem + TM_GRAD, gcol + ks * 16, bl, idesc2, 1u);                                 // G_hi * X_lo
-          }
-          tc_commit(&bars->empty[sl_l]);
+          __syncwarp();
         };
 
-        if (nt > 0) issue_g1(h, tcount);
-        for (int i = 0; i < nt; ++i) {
-          if (i + 1 < nt) issue_g1(h + 2 * (i + 1), tcount + i + 1);
-          issue_g2(h + 2 * i, tcount + i, i == 0);
+        if (MODE == TC_FIT) {
+          if (nt > 0) issue_g1(h, tcount);
+          for (int i = 0; i < nt; ++i) {
+            if (i + 1 < nt) issue_g1(h + 2 * (i + 1), tcount + i + 1);
+            issue_g2(h + 2 * i, tcount + i, i == 0);
+          }
+        } else {
+          // score: GEMM1 only; Z buffer b may be overwritten once the epilogue has consumed it
+          for (int i = 0; i < nt; ++i) {
+            const uint32_t tc = tcount + i;
+            if (tc >= 2) { mbar_wait(&bars->g_full[tc & 1], ((tc >> 1) - 1) & 1, 230); tc_fence_after(); }
+            issue_g1(h + 2 * i, tc);
+          }
         }
         h += 2 * nt;
         tcount += nt;
-        tc_commit(&bars->acc_done);
+        if (elect_one()) tc_commit(&bars->acc_done);
+        __syncwarp();
       }
+      __syncwarp();
     }
   } else {
     // ================================ epilogue warps ========================================
+    // 8 warps: warps w and w+4 share TMEM lane quadrant q = w & 3 and split the tile's four
+    // 16-row chunks between them (hf = 0: chunks 0,1; hf = 1: chunks 2,3).
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int hf = (warp - 2) >> 2;
     const int lane_in_group = q * 32 + lane;      // slot within the group == TMEM lane
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     uint32_t tcount = 0;
     int it_local = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it_local) {
-      const int g = item / prm.parts, p = item % prm.parts;
-      const int t0 = p * tiles_per_part;
-      const int t1 = min(prm.n_tiles, t0 + tiles_per_part);
+    for (int g = g_first; g <= g_last; ++g, ++it_local) {
+      TC_ITEM_RANGE(g, t0, t1)
       const int nt = t1 - t0;
+      const int z_part = prm.parts > 0 ? (int)blockIdx.x % prm.parts
+                                       : (int)blockIdx.x - tc_first_cta(g, prm.n_tiles, units, gridDim.x);
       const int slot = g * TC_BC + lane_in_group;
       const bool valid = slot < prm.n_act;
       TcSlotParam sp;
       sp.inv_t = 1.f; sp.bias = 0.f; sp.fold = -1; sp.pos = -1;
       if (valid) sp = prm.sp[slot];
-      // previous item's accumulators must have been flushed by all epilogue threads (same threads)
-      // and its MMAs finished reading W_lo: guaranteed by the acc_done wait at the end of the item.
-      {  // W_lo row of this slot -> TMEM (packed fp16 pairs), 16 columns (32 values) at a time
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.Wl + (size_t)slot * (nchunk * 64));
-        for (int c16 = 0; c16 < nchunk * 2; ++c16) {
+      {  // W_lo row of this slot -> TMEM (packed fp16 pairs), 16 columns (32 values) at a time.
+         // The previous item's MMAs are done with W_lo: its acc_done was waited for below.
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.Wl + (size_t)slot * (NCHUNK * 64));
+#pragma unroll 1
+        for (int c16 = hf * NCHUNK; c16 < (hf + 1) * NCHUNK; ++c16) {
           uint32_t r[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = valid ? __ldg(src + c16 * 16 + j) : 0u;
+          for (int j = 0; j < 4; ++j) {
+            uint4 v = valid ? __ldg(reinterpret_cast<const uint4*>(src + c16 * 16) + j) : make_uint4(0, 0, 0, 0);
+            r[4 * j] = v.x; r[4 * j + 1] = v.y; r[4 * j + 2] = v.z; r[4 * j + 3] = v.w;
+          }
           tmem_st16(tl + TM_WLO + c16 * 16, r);
         }
         tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bars->wl_full);
       }
-      double lsum = 0.0, gsum = 0.0;
+      // per-item sums as compensated fp32 pairs (TwoSum): the fp64 pipe is slow enough that two
+      // DADDs per tile showed up as 16 % of the epilogue's stall samples
+      float ls_hi = 0.f, ls_lo = 0.f, gs_hi = 0.f, gs_lo = 0.f;
+      unsigned long long n_ok = 0, n_all = 0;
       for (int i = 0; i < nt; ++i, ++tcount) {
         const int t = t0 + i;
         const uint32_t zb = tl + TM_Z0 + (tcount & 1) * 64;
-        mbar_wait(&bars->z_full[tcount & 1], (tcount >> 1) & 1, 300);
-        tc_fence_after();
-        float lt = 0.f, gt = 0.f;
-#pragma unroll 1
-        for (int ch = 0; ch < TC_R / 16; ++ch) {
-          uint32_t zr[16];
-          tmem_ld16(zb + ch * 16, zr);
-          const uint4* rm4 = reinterpret_cast<const uint4*>(prm.rowmeta + (size_t)t * TC_R + ch * 16);
-          uint32_t rm[16];
+        // row metadata of this warp's 32 rows: issue the loads before waiting for the MMA so
+        // their latency is hidden behind the wait
+        uint32_t rm[32];
+        {
+          const uint4* rm4 = reinterpret_cast<const uint4*>(prm.rowmeta + (size_t)t * TC_R + hf * 32);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < 8; ++j) {
             uint4 v = __ldg(rm4 + j);
             rm[4 * j] = v.x; rm[4 * j + 1] = v.y; rm[4 * j + 2] = v.z; rm[4 * j + 3] = v.w;
           }
-          tmem_wait_ld();
-          float gv[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float z = fmaf(__uint_as_float(zr[j]), sp.inv_t, sp.bias);
-            const int fr = (int)(rm[j] >> 24);
-            const bool yb = (int)(rm[j] & 0x00FFFFFFu) == sp.pos;
-            const bool train = (fr != 0xFF) && (fr != sp.fold);
-            const float u = yb ? -z : z;
-            const float e = ex2_approx(-fabsf(u) * 1.4426950408889634f);
-            const float s1 = 1.f + e;
-            const float loss = fmaxf(u, 0.f) + lg2_approx(s1) * 0.6931471805599453f;
-            const float r = rcp_approx(s1);
-            const float sig = (u >= 0.f) ? r : e * r;
-            const float gg = yb ? -sig : sig;
-            gv[j] = train ? gg : 0.f;
-            lt += train ? loss : 0.f;
-            gt += gv[j];
-          }
-          uint32_t out[16];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float a = gv[2 * j] * GSCALE, b = gv[2 * j + 1] * GSCALE;
-            const uint32_t hi = pack_f16x2(a, b);
-            const float2 hf = unpack_f16x2(hi);
-            out[j] = hi;
-            out[8 + j] = pack_f16x2(a - hf.x, b - hf.y);
-          }
-          tmem_st16(zb + ch * 16, out);
         }
-        tmem_wait_st();
+        mbar_wait(&bars->z_full[tcount & 1], (tcount >> 1) & 1, 300);
+        tc_fence_after();
+        float lt = 0.f, gt = 0.f;
+        int ok_t = 0, all_t = 0;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int ch = hf * 2 + cc;
+          uint32_t zr[16];
+          tmem_ld16(zb + ch * 16, zr);
+          tmem_wait_ld();
+          if (MODE == TC_FIT) {
+            float gv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t m = rm[cc * 16 + j];
+              const float z = fmaf(__uint_as_float(zr[j]), sp.inv_t, sp.bias);
+              const int fr = (int)(m >> 24);
+              const bool yb = (int)(m & 0x00FFFFFFu) == sp.pos;
+              const bool train = (fr != 0xFF) && (fr != sp.fold);
+              const float u = yb ? -z : z;
+              const float e = ex2_approx(-fabsf(u) * 1.4426950408889634f);
+              const float s1 = 1.f + e;
+              const float loss = fmaxf(u, 0.f) + lg2_approx(s1) * 0.6931471805599453f;
+              const float r = rcp_approx(s1);
+              const float sig = (u >= 0.f) ? r : e * r;
+              const float gg = yb ? -sig : sig;
+              gv[j] = train ? gg : 0.f;
+              lt += train ? loss : 0.f;
+              gt += gv[j];
+            }
+            uint32_t out[16];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a = gv[2 * j] * GSCALE, b = gv[2 * j + 1] * GSCALE;
+              const uint32_t hi = pack_f16x2(a, b);
+              const float2 hf2 = unpack_f16x2(hi);
+              out[j] = hi;
+              out[8 + j] = pack_f16x2(a - hf2.x, b - hf2.y);
+            }
+            tmem_st16(zb + ch * 16, out);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t m = rm[cc * 16 + j];
+              const float z = fmaf(__uint_as_float(zr[j]), sp.inv_t, sp.bias);
+              const int fr = (int)(m >> 24);
+              const bool yb = (int)(m & 0x00FFFFFFu) == sp.pos;
+              // fold code: f >= 0 rows of fold f; -2 all rows; -3-f rows NOT in fold f
+              const bool in = (fr != 0xFF) && (sp.fold == -2 || (sp.fold >= 0 && fr == sp.fold) ||
+                                               (sp.fold <= -3 && fr != (-3 - sp.fold)));
+              ok_t += (in && ((z > 0.f) == yb)) ? 1 : 0;
+              all_t += in ? 1 : 0;
+            }
+          }
+        }
+        if (MODE == TC_FIT) tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bars->g_full[tcount & 1]);
-        lsum += (double)lt;
-        gsum += (double)gt;
+        {
+          float sl = ls_hi + lt, bb = sl - ls_hi;
+          ls_lo += (ls_hi - (sl - bb)) + (lt - bb);
+          ls_hi = sl;
+          float sg = gs_hi + gt, cc = sg - gs_hi;
+          gs_lo += (gs_hi - (sg - cc)) + (gt - cc);
+          gs_hi = sg;
+        }
+        n_ok += ok_t;
+        n_all += all_t;
       }
-      // flush the gradient accumulators of this item
+      // end of item: all MMAs done -> flush
       mbar_wait(&bars->acc_done, it_local & 1, 310);
       tc_fence_after();
-      {
-        float* dst = prm.gradp + ((size_t)p * prm.n_act + slot) * prm.ldw;
-        for (int c16 = 0; c16 < nchunk * 4; ++c16) {
+      if (MODE == TC_FIT) {
+        float* dst = prm.gradp + ((size_t)z_part * prm.n_act + slot) * prm.ldw;
+#pragma unroll 1
+        for (int c16 = hf * NCHUNK * 2; c16 < (hf + 1) * NCHUNK * 2; ++c16) {
           uint32_t r[16];
           tmem_ld16(tl + TM_GRAD + c16 * 16, r);
           tmem_wait_ld();
-          if (valid) {
+          if (valid && nt > 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               *reinterpret_cast<uint4*>(dst + c16 * 16 + 4 * j) =
                   make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           }
         }
-        if (valid) {
-          prm.lossp[(size_t)p * prm.n_act + slot] = lsum;
-          prm.gsump[(size_t)p * prm.n_act + slot] = gsum;
+        if (valid && nt > 0) {   // the two half-warps of a slot add into the zeroed partial (a + b == b + a)
+          atomicAdd(prm.lossp + (size_t)z_part * prm.n_act + slot, (double)ls_hi + (double)ls_lo);
+          atomicAdd(prm.gsump + (size_t)z_part * prm.n_act + slot, (double)gs_hi + (double)gs_lo);
         }
+      } else if (valid && n_all > 0) {
+        atomicAdd(prm.correct + slot, n_ok);
+        atomicAdd(prm.count + slot, n_all);
       }
       tc_fence_before();
       mbar_arrive(&bars->acc_free);
     }
   }
+#undef TC_ITEM_RANGE
 
   // teardown
   tc_fence_before();
@@ -702,24 +850,81 @@ int tc_export(Ctx* c, LogregWork& w, int n_act_upper, const double* xin, int fit
 
 size_t tc_slot_param_bytes() { return sizeof(TcSlotParam); }
 
-int tc_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
+// host mirror of the in-kernel work split
+static long long h_unit_begin(long long cta, long long units, long long grid) { return cta * units / grid; }
+static int h_cta_of_unit(long long u, long long units, int grid) {
+  long long c = u * grid / units;
+  while (c + 1 < grid && h_unit_begin(c + 1, units, grid) <= u) ++c;
+  while (c > 0 && h_unit_begin(c, units, grid) > u) --c;
+  return (int)c;
+}
+
+template <int MODE>
+static cudaError_t tc_launch(int nchunk, int grid, size_t smem, cudaStream_t st, const CUtensorMap& xh,
+                             const CUtensorMap& xl, const CUtensorMap& wh, const TcParams& prm) {
+  switch (nchunk) {
+#define TC_CASE(N)                                                                                   \
+  case N: {                                                                                          \
+    static bool attr = false;                                                                        \
+    if (!attr) {                                                                                     \
+      cudaError_t e = cudaFuncSetAttribute(tc_eval_kernel<N, MODE>,                                  \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);     \
+      if (e != cudaSuccess) return e;                                                                \
+      attr = true;                                                                                   \
+    }                                                                                                \
+    tc_eval_kernel<N, MODE><<<grid, TC_THREADS, smem, st>>>(xh, xl, wh, prm);                        \
+    break;                                                                                           \
+  }
+    TC_CASE(1) TC_CASE(2) TC_CASE(3) TC_CASE(4)
+#undef TC_CASE
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsigned long long* dcorrect,
+                  unsigned long long* dcount) {
   TcData& t = c->tc;
-  *nz_used = 0;
+  if (nz_used) *nz_used = 0;
   if (n_act <= 0) return 0;
   const int nchunk = t.dpad / 64;
   const int groups = (n_act + TC_BC - 1) / TC_BC;
   const int n_tiles = (int)(t.npad / TC_R);
-  int parts = c->sm_count / groups;
-  if (parts < 1) parts = 1;
-  if (parts > n_tiles) parts = n_tiles;
-  if ((int64_t)parts * n_act > w.cap_sc) parts = (int)(w.cap_sc / n_act);
-  if (parts < 1) return fail(c, "tc_eval: partial buffer too small");
-  const int tiles_per_part = (n_tiles + parts - 1) / parts;
-  parts = (n_tiles + tiles_per_part - 1) / tiles_per_part;   // drop empty parts
+  const long long units = (long long)groups * n_tiles;
+  int grid = c->sm_count;
+  if ((long long)grid > units) grid = (int)units;
+  // Work split.  "aligned" (default when it keeps >= 90 % of the SMs busy): parts = SMs / groups
+  // CTAs per group, every group cut at the same rows.  Otherwise "balanced" contiguous ranges.
+  int parts = 0;
+  {
+    const char* env = getenv("SKDIST_B200_TC_SPLIT");
+    int p_al = groups <= c->sm_count ? c->sm_count / groups : 0;
+    if (p_al > n_tiles) p_al = n_tiles;
+    bool want_aligned = p_al > 0 && (double)(groups * p_al) >= 0.90 * c->sm_count;
+    if (env && !strcmp(env, "balanced")) want_aligned = false;
+    if (env && !strcmp(env, "aligned") && p_al > 0) want_aligned = true;
+    if (want_aligned) parts = p_al;
+  }
+  int nz = 1;
+  if (parts > 0) {
+    grid = groups * parts;
+    nz = parts;
+  } else {
+    // partial slots needed: the largest number of CTAs that share one group
+    for (int g = 0; g < groups; ++g) {
+      int c0 = h_cta_of_unit((long long)g * n_tiles, units, grid);
+      int c1 = h_cta_of_unit((long long)(g + 1) * n_tiles - 1, units, grid);
+      if (c1 - c0 + 1 > nz) nz = c1 - c0 + 1;
+    }
+  }
+  if (mode == TC_FIT) {
+    if ((int64_t)nz * n_act > w.cap_sc) return fail(c, "tc_eval: partial buffer too small");
+    SKD_CUDA(c, cudaMemsetAsync(w.lossp, 0, (size_t)nz * n_act * sizeof(double), c->stream));
+    SKD_CUDA(c, cudaMemsetAsync(w.gsump, 0, (size_t)nz * n_act * sizeof(double), c->stream));
+    SKD_CUDA(c, cudaMemsetAsync(w.gradp, 0, (size_t)nz * n_act * w.ldw * sizeof(float), c->stream));
+  }
   CUtensorMap map_wh;
-  const int slots_pad = groups * TC_BC;
   if (make_map(c, &map_wh, w.Wh, (uint64_t)w.slots_pad_cap, (uint64_t)t.dpad, TC_BC)) return 1;
-  (void)slots_pad;
   TcParams prm;
   prm.Wl = (const __half*)w.Wl;
   prm.sp = (const TcSlotParam*)w.sp;
@@ -727,27 +932,30 @@ int tc_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
   prm.lossp = w.lossp;
   prm.gsump = w.gsump;
   prm.gradp = w.gradp;
+  prm.correct = dcorrect;
+  prm.count = dcount;
   prm.n_act = n_act;
   prm.groups = groups;
-  prm.parts = parts;
   prm.n_tiles = n_tiles;
-  prm.nchunk = nchunk;
   prm.ldw = w.ldw;
+  prm.parts = parts;
   const size_t smem = 1024 + (size_t)nchunk * (TC_BC * 128) + (size_t)TC_NS * nchunk * (TC_R * 128) +
                       sizeof(TcBarriers) + 64;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SKD_CUDA(c, cudaFuncSetAttribute(tc_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    attr_set = true;
-  }
-  int grid = groups * parts;
-  if (grid > c->sm_count) grid = c->sm_count;
-  tc_eval_kernel<<<grid, TC_THREADS, smem, c->stream>>>(t.map_xh, t.map_xl, map_wh, prm);
+  cudaError_t e = mode == TC_FIT ? tc_launch<TC_FIT>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm)
+                                 : tc_launch<TC_SCORE>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm);
   c->launches += 1;
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(c, std::string("tc_eval launch: ") + cudaGetErrorString(e));
-  *nz_used = parts;
+  if (nz_used) *nz_used = nz;
   return 0;
+}
+
+int tc_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
+  return tc_run(c, w, n_act, TC_FIT, nz_used, nullptr, nullptr);
+}
+
+// Accuracy counts of n_act slots whose weights were exported with tc_export (sp.fold = scoring code).
+int tc_score(Ctx* c, LogregWork& w, int n_act, int64_t* dcorrect, int64_t* dcount) {
+  return tc_run(c, w, n_act, TC_SCORE, nullptr, (unsigned long long*)dcorrect, (unsigned long long*)dcount);
 }
 
 }  // namespace skd

@@ -150,6 +150,7 @@ void tc_free(Ctx* c);
 int tc_prepare(Ctx* c);
 int tc_export(Ctx* c, LogregWork& w, int n_act_upper, const double* xin, int fit_intercept);
 int tc_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used);
+int tc_score(Ctx* c, LogregWork& w, int n_act, int64_t* dcorrect, int64_t* dcount);
 size_t tc_slot_param_bytes();
 
 // device L-BFGS (lbfgs_dev.cu)

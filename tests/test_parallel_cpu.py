@@ -1,0 +1,73 @@
+"""N > 1 path on CPU: world_size-2 gloo processes, columns dealt round-robin, results
+all-gathered; every rank must end with the single-process cv_results_."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sklearn.linear_model import LogisticRegression
+    from skdist.distribute.search import DistGridSearchCV
+    from skdist_b200 import engine, parallel
+    from skdist_b200.datasets import make_g1_classification
+    from tests.fake_engine import FakeEngine
+    engine.set_engine_factory(FakeEngine)
+    X, y = make_g1_classification(1500, 8, seed=9)
+    gs = DistGridSearchCV(LogisticRegression(), {"C": [0.01, 0.1, 1.0, 10.0, 100.0]}, cv=3).fit(X, y)
+    eng = engine.get_engine()
+    n_fit = sum(b for kind, b in eng.calls if kind == "fit")
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), mean=gs.cv_results_["mean_test_score"],
+             s0=gs.cv_results_["split0_test_score"], best=gs.best_index_, coef=gs.best_estimator_.coef_,
+             n_fit=n_fit, shard=parallel.shard_indices(15, rank, world))
+    # gather helper on a ragged split (7 items over 2 ranks)
+    idx = parallel.shard_indices(7, rank, world)
+    full = parallel.all_gather_columns(np.stack([idx * 10.0, idx * 1.0], 1), 7, rank, world)
+    assert np.array_equal(full[:, 0], np.arange(7) * 10.0)
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_grid_search_matches_single_process(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(tmp_path / "rank0.npz")
+    r1 = np.load(tmp_path / "rank1.npz")
+    for k in ("mean", "s0", "coef"):
+        np.testing.assert_array_equal(r0[k], r1[k])
+    assert int(r0["best"]) == int(r1["best"])
+    # each rank fitted only its own shard of the 15 columns (+ 1 refit)
+    assert int(r0["n_fit"]) == 8 + 1 and int(r1["n_fit"]) == 7 + 1
+    assert np.array_equal(r0["shard"], np.arange(0, 15, 2)) and np.array_equal(r1["shard"], np.arange(1, 15, 2))
+    # single-process reference through the same host code
+    from sklearn.linear_model import LogisticRegression
+    from skdist.distribute.search import DistGridSearchCV
+    from skdist_b200 import engine
+    from skdist_b200.datasets import make_g1_classification
+    from tests.fake_engine import FakeEngine
+    engine.set_engine_factory(FakeEngine)
+    try:
+        X, y = make_g1_classification(1500, 8, seed=9)
+        gs = DistGridSearchCV(LogisticRegression(), {"C": [0.01, 0.1, 1.0, 10.0, 100.0]}, cv=3).fit(X, y)
+    finally:
+        engine.set_engine_factory(None)
+    np.testing.assert_array_equal(gs.cv_results_["mean_test_score"], r0["mean"])
+    np.testing.assert_array_equal(gs.best_estimator_.coef_, r0["coef"])
