@@ -89,6 +89,44 @@ int skd_logreg_loss_grad(skd_ctx* ctx, int32_t B, const double* w_in, const doub
 int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_t* col_fold,
                            const int32_t* col_pos, int64_t* correct_out, int64_t* count_out);
 
+/* Batched Ridge: B independent (alpha, fold) columns from one pass over the staged X and the
+ * staged real targets.  Column j trains on rows whose fold id != col_fold[j] (col_fold[j] < 0: all
+ * rows).  coef_out[j*(d+1)+k] (k<d weights, k==d intercept); status_out[j] 1 = ok, 4 = matrix not
+ * positive definite.
+ * ref: replaces B invocations of search.py:180-288 with estimator = Ridge (dense, solver
+ * auto->cholesky): SK/linear_model/_base.py:113-220 (centring), SK/linear_model/_ridge.py:215-234
+ * (_solve_cholesky: X^T X, X^T y, LAPACK posv). */
+int skd_ridge_fit_batch(skd_ctx* ctx, int32_t B, const double* alpha, const int32_t* col_fold,
+                        int32_t fit_intercept, float* coef_out, int32_t* status_out,
+                        double* gpu_seconds_out);
+
+/* Exact-order column-batched SGD: B one-vs-rest label columns (positives of column j = rows with
+ * y_class == col_pos[j]) trained with the SAME shuffled sample order, one warp per column.
+ * loss: 0 hinge, 1 log_loss; penalty l2; lr_type: 0 optimal, 1 constant, 2 invscaling; `seed` and
+ * `optimal_init` are computed by the host exactly as scikit-learn does.  coef_out [B x d] float32
+ * (after reset_wscale), intercept_out [B] float64, n_iter_out epochs run, t_out = 1 + n_iter * n,
+ * status_out 1 = converged (n_iter_no_change), 3 = max_iter reached, 5 = non-finite.
+ * ref: replaces B invocations of multiclass.py:109-152 (_fit_binary -> SGDClassifier.fit):
+ * SK/linear_model/_stochastic_gradient.py:387-515, SK/linear_model/_sgd_fast.pyx.tp:274-640. */
+int skd_sgd_fit_batch(skd_ctx* ctx, int32_t B, const int32_t* col_pos, int32_t loss, double alpha,
+                      int32_t fit_intercept, int32_t max_iter, double tol, int32_t shuffle,
+                      uint32_t seed, int32_t lr_type, double eta0, double power_t, double optimal_init,
+                      int32_t n_iter_no_change, float* coef_out, double* intercept_out,
+                      int32_t* n_iter_out, double* t_out, int32_t* status_out, double* gpu_seconds_out);
+
+/* Sum of squared residuals and row counts of B linear regressors on the rows selected by the
+ * same fold codes as skd_linear_score_batch; the host forms r2 = 1 - sse / sst.
+ * ref: replaces search.py:264 (_score -> RegressorMixin.score -> r2_score). */
+int skd_linear_r2_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_t* col_fold,
+                        double* sse_out, int64_t* count_out);
+
+/* Streaming batched inference on NEW host rows: out[i*B + j] = Xnew[i,:].coef_j + intercept_j.
+ * Rows are moved in <= 1 GiB chunks, double buffered (H2D of chunk i+1 overlaps the kernel and
+ * D2H of chunk i).  gpu_seconds_out: device time of the whole call.
+ * ref: replaces skdist/distribute/predict.py:160-179 (pandas_udf around model.predict). */
+int skd_predict_linear(skd_ctx* ctx, const float* Xnew, int64_t m, int64_t d, int64_t ld, int32_t B,
+                       const float* coef, float* out, double* gpu_seconds_out);
+
 /* Decision values out[i*B + j] = X[i,:].coef_j + intercept_j for the staged X (all rows).
  * ref: estimator.decision_function / predict inside scorers (utils.py:45-72) and
  * skdist/distribute/predict.py:160-179 (model.predict over row batches). */

@@ -196,6 +196,7 @@ int skd_stage_targets(skd_ctx* ctx, const float* y, int64_t n) {
   SKD_CUDA(c, cudaMemcpyAsync(c->yreal, y, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->h2d += n * (int64_t)sizeof(float);
+  c->tc.meta_valid = false;
   return 0;
 }
 
@@ -538,6 +539,195 @@ int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int
   return 0;
 }
 
+int skd_ridge_fit_batch(skd_ctx* ctx, int32_t B, const double* alpha, const int32_t* col_fold,
+                        int32_t fit_intercept, float* coef_out, int32_t* status_out,
+                        double* gpu_seconds_out) {
+  if (!ctx) return fail(nullptr, "skd_ridge_fit_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || !c->yreal) return fail(c, "skd_ridge_fit_batch: stage X and targets first");
+  if (B <= 0 || !alpha || !col_fold || !coef_out || !status_out) return fail(c, "skd_ridge_fit_batch: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  const int n_folds = c->fold ? c->n_folds : 1;
+  std::vector<int32_t> hold(B);
+  for (int j = 0; j < B; ++j) {
+    if (!(alpha[j] >= 0.0)) return fail(c, "skd_ridge_fit_batch: alpha must be non-negative");
+    if (col_fold[j] >= 0) {
+      if (!c->fold || col_fold[j] >= c->n_folds) return fail(c, "skd_ridge_fit_batch: col_fold refers to an unstaged fold");
+      hold[j] = col_fold[j];
+    } else {
+      hold[j] = n_folds;   // hold out nothing
+    }
+  }
+  cudaEvent_t e0, e1;
+  SKD_CUDA(c, cudaEventCreate(&e0));
+  SKD_CUDA(c, cudaEventCreate(&e1));
+  SKD_CUDA(c, cudaEventRecord(e0, c->stream));
+  int rc = ridge_fit_batch(c, B, alpha, hold.data(), fit_intercept, coef_out, status_out);
+  float ms = 0.f;
+  if (!rc) {
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
+  return rc;
+}
+
+int skd_linear_r2_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_t* col_fold,
+                        double* sse_out, int64_t* count_out) {
+  if (!ctx) return fail(nullptr, "skd_linear_r2_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || !c->yreal) return fail(c, "skd_linear_r2_batch: stage X and targets first");
+  if (B <= 0 || !coef || !col_fold || !sse_out || !count_out) return fail(c, "skd_linear_r2_batch: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  Scratch sx(c);
+  std::vector<SlotMeta> hs(B);
+  for (int j = 0; j < B; ++j) {
+    int f = col_fold[j] >= 0 ? col_fold[j] : (col_fold[j] <= -3 ? -3 - col_fold[j] : -1);
+    if (col_fold[j] == -1) return fail(c, "skd_linear_r2_batch: col_fold -1 is not a scoring code");
+    if (f >= 0 && (!c->fold || f >= c->n_folds)) return fail(c, "skd_linear_r2_batch: col_fold refers to an unstaged fold");
+    hs[j].col = j; hs[j].fold = col_fold[j]; hs[j].pos = 0; hs[j].pad = 0;
+  }
+  SlotMeta* dslot; double* dsse; int64_t* dcount;
+  SKD_CUDA(c, sx.alloc(&dslot, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&dsse, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&dcount, (size_t)B));
+  SKD_CUDA(c, cudaMemcpyAsync(dslot, hs.data(), B * sizeof(SlotMeta), cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemsetAsync(dsse, 0, B * sizeof(double), c->stream));
+  SKD_CUDA(c, cudaMemsetAsync(dcount, 0, B * sizeof(int64_t), c->stream));
+  if (c->kernel_choice == 2 && !tc_supported(c))
+    return fail(c, "tcgen05 path requested but the staged shape is unsupported (needs d <= 256)");
+  if (want_tc(c)) {
+    if (tc_prepare(c)) return 1;
+    LogregWork w;
+    w.B = B; w.dp = (int)c->d + 1; w.use_tc = true; w.ldw = c->tc.dpad;
+    w.slot = dslot;
+    w.slots_pad_cap = (int)round_up(B, 128);
+    size_t wbytes = (size_t)w.slots_pad_cap * c->tc.dpad * 2;
+    SKD_CUDA(c, sx.alloc((uint8_t**)&w.Wh, wbytes));
+    SKD_CUDA(c, sx.alloc((uint8_t**)&w.Wl, wbytes));
+    SKD_CUDA(c, sx.alloc((uint8_t**)&w.sp, (size_t)w.slots_pad_cap * tc_slot_param_bytes()));
+    SKD_CUDA(c, sx.alloc(&w.n_act, 1));
+    SKD_CUDA(c, cudaMemsetAsync(w.Wh, 0, wbytes, c->stream));
+    SKD_CUDA(c, cudaMemsetAsync(w.Wl, 0, wbytes, c->stream));
+    std::vector<double> hx((size_t)B * w.dp);
+    for (size_t i = 0; i < hx.size(); ++i) hx[i] = (double)coef[i];
+    double* dx;
+    SKD_CUDA(c, sx.alloc(&dx, hx.size()));
+    int32_t nb = B;
+    SKD_CUDA(c, cudaMemcpyAsync(dx, hx.data(), hx.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(w.n_act, &nb, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h2d += (int64_t)hx.size() * 8;
+    if (tc_export(c, w, B, dx, 1)) return 1;
+    if (tc_r2(c, w, B, dsse, dcount)) return 1;
+  } else {
+    float* dW;
+    if (pack_coef(c, sx, B, coef, &dW)) return 1;
+    if (simt_r2(c, B, dW, dslot, dsse, dcount)) return 1;
+  }
+  SKD_CUDA(c, cudaMemcpyAsync(sse_out, dsse, B * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(count_out, dcount, B * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->d2h += (int64_t)B * 16;
+  return 0;
+}
+
+int skd_sgd_fit_batch(skd_ctx* ctx, int32_t B, const int32_t* col_pos, int32_t loss, double alpha,
+                      int32_t fit_intercept, int32_t max_iter, double tol, int32_t shuffle,
+                      uint32_t seed, int32_t lr_type, double eta0, double power_t, double optimal_init,
+                      int32_t n_iter_no_change, float* coef_out, double* intercept_out,
+                      int32_t* n_iter_out, double* t_out, int32_t* status_out, double* gpu_seconds_out) {
+  if (!ctx) return fail(nullptr, "skd_sgd_fit_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || !c->ycls) return fail(c, "skd_sgd_fit_batch: stage X and labels first");
+  if (B <= 0 || !col_pos || !coef_out || !intercept_out || !n_iter_out || !t_out || !status_out)
+    return fail(c, "skd_sgd_fit_batch: bad arguments");
+  if (loss < 0 || loss > 1 || lr_type < 0 || lr_type > 2 || !(alpha > 0.0) || max_iter < 1)
+    return fail(c, "skd_sgd_fit_batch: unsupported loss / learning rate / alpha / max_iter");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  cudaEvent_t e0, e1;
+  SKD_CUDA(c, cudaEventCreate(&e0));
+  SKD_CUDA(c, cudaEventCreate(&e1));
+  SKD_CUDA(c, cudaEventRecord(e0, c->stream));
+  int rc = sgd_fit_batch(c, B, col_pos, loss, alpha, fit_intercept, max_iter, tol, shuffle, seed, lr_type, eta0,
+                         power_t, optimal_init, n_iter_no_change, coef_out, intercept_out, n_iter_out, t_out,
+                         status_out);
+  float ms = 0.f;
+  if (!rc) {
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
+  return rc;
+}
+
+int skd_predict_linear(skd_ctx* ctx, const float* Xnew, int64_t m, int64_t d, int64_t ld, int32_t B,
+                       const float* coef, float* out, double* gpu_seconds_out) {
+  if (!ctx) return fail(nullptr, "skd_predict_linear: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!Xnew || m <= 0 || d <= 0 || ld < d || B <= 0 || !coef || !out) return fail(c, "skd_predict_linear: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  const int64_t ldx = round_up(d, 4);
+  Scratch sx(c);
+  // weights [B x ldx] + bias[B]
+  std::vector<float> hw((size_t)B * ldx + B, 0.f);
+  for (int j = 0; j < B; ++j) {
+    memcpy(&hw[(size_t)j * ldx], coef + (size_t)j * (d + 1), d * sizeof(float));
+    hw[(size_t)B * ldx + j] = coef[(size_t)j * (d + 1) + d];
+  }
+  float* dW;
+  SKD_CUDA(c, sx.alloc(&dW, hw.size()));
+  SKD_CUDA(c, cudaMemcpyAsync(dW, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  // row chunks of <= 1 GiB, double buffered on two streams so H2D of chunk i+1 overlaps chunk i
+  int64_t rows_per_chunk = std::max<int64_t>(1, ((int64_t)1 << 30) / (ldx * 4));
+  if (rows_per_chunk > m) rows_per_chunk = m;
+  float* dX[2]; float* dO[2];
+  cudaStream_t st[2]; cudaEvent_t ev[2];
+  for (int i = 0; i < 2; ++i) {
+    SKD_CUDA(c, sx.alloc(&dX[i], (size_t)rows_per_chunk * ldx));
+    SKD_CUDA(c, sx.alloc(&dO[i], (size_t)rows_per_chunk * B));
+    SKD_CUDA(c, cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    SKD_CUDA(c, cudaEventCreate(&ev[i]));
+    if (ldx != d) SKD_CUDA(c, cudaMemsetAsync(dX[i], 0, (size_t)rows_per_chunk * ldx * 4, c->stream));
+  }
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaEvent_t t0, t1;
+  SKD_CUDA(c, cudaEventCreate(&t0));
+  SKD_CUDA(c, cudaEventCreate(&t1));
+  SKD_CUDA(c, cudaEventRecord(t0, st[0]));
+  cudaStream_t keep = c->stream;
+  int rc = 0;
+  int k = 0;
+  for (int64_t r0 = 0; r0 < m && !rc; r0 += rows_per_chunk, k ^= 1) {
+    int64_t mr = std::min(rows_per_chunk, m - r0);
+    cudaError_t e = cudaMemcpy2DAsync(dX[k], ldx * 4, Xnew + r0 * ld, ld * 4, d * 4, mr, cudaMemcpyHostToDevice, st[k]);
+    if (e != cudaSuccess) { rc = fail(c, cudaGetErrorString(e)); break; }
+    c->stream = st[k];
+    rc = predict_device(c, dX[k], mr, (int)ldx, (int)d, B, dW, dO[k]);
+    c->stream = keep;
+    if (rc) break;
+    e = cudaMemcpyAsync(out + r0 * B, dO[k], (size_t)mr * B * 4, cudaMemcpyDeviceToHost, st[k]);
+    if (e != cudaSuccess) { rc = fail(c, cudaGetErrorString(e)); break; }
+    c->h2d += mr * d * 4;
+    c->d2h += mr * (int64_t)B * 4;
+  }
+  for (int i = 0; i < 2; ++i) cudaStreamSynchronize(st[i]);
+  cudaEventRecord(t1, st[0]);
+  cudaEventSynchronize(t1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, t0, t1);
+  if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
+  for (int i = 0; i < 2; ++i) { cudaStreamDestroy(st[i]); cudaEventDestroy(ev[i]); }
+  cudaEventDestroy(t0); cudaEventDestroy(t1);
+  return rc;
+}
+
 int skd_linear_decision(skd_ctx* ctx, int32_t B, const float* coef, float* out) {
   if (!ctx) return fail(nullptr, "skd_linear_decision: ctx is NULL");
   Ctx* c = &ctx->c;
@@ -548,7 +738,9 @@ int skd_linear_decision(skd_ctx* ctx, int32_t B, const float* coef, float* out) 
   float *dW, *dout;
   if (pack_coef(c, sx, B, coef, &dW)) return 1;
   SKD_CUDA(c, sx.alloc(&dout, (size_t)c->n * B));
-  if (simt_decision(c, B, dW, dout)) return 1;
+  if (B <= 16 && c->ldx * 4 * 8 <= 48 * 1024) {
+    if (predict_device(c, c->X, c->n, (int)c->ldx, (int)c->d, B, dW, dout)) return 1;
+  } else if (simt_decision(c, B, dW, dout)) return 1;
   SKD_CUDA(c, cudaMemcpyAsync(out, dout, (size_t)c->n * B * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->d2h += (int64_t)c->n * B * 4;

@@ -21,7 +21,7 @@ constexpr int TM = 64;   // rows per tile
 constexpr int TN = 64;   // slots per tile
 constexpr int TK = 16;
 
-enum { MODE_FIT = 0, MODE_SCORE = 1, MODE_DECISION = 2 };
+enum { MODE_FIT = 0, MODE_SCORE = 1, MODE_DECISION = 2, MODE_R2 = 3 };
 
 // sklearn's closs_grad_half_binomial (SK/_loss/_loss.pyx.tp:728-751), evaluated in double.
 __device__ __forceinline__ void loss_grad_half_binomial(double y, double raw, double& loss,
@@ -52,7 +52,7 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
            const int32_t* __restrict__ ycls, const int8_t* __restrict__ fold,
            int64_t rows_per_chunk, float* __restrict__ G, int ldg, double* __restrict__ lossp,
            double* __restrict__ gsump, int64_t* __restrict__ correct, int64_t* __restrict__ count,
-           float* __restrict__ dec, int ldd) {
+           float* __restrict__ dec, int ldd, const float* __restrict__ yreal) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   __shared__ double red[16][TN + 1];
@@ -120,8 +120,10 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
       int64_t gr = r0 + ty * 4 + i;
       bool rvalid = gr < row_end;
       int yc = -1, fd = -1;
+      float yr = 0.f;
       if (MODE != MODE_DECISION && rvalid) {
-        yc = ycls[gr];
+        if (MODE == MODE_R2) yr = yreal[gr];
+        else yc = ycls[gr];
         if (fold) fd = (int)fold[gr];
       }
       float gout[4];
@@ -151,6 +153,15 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
             acc_c[j] += (pred == y) ? 1 : 0;
             acc_n[j] += 1;
           }
+        } else if (MODE == MODE_R2) {
+          bool test = rvalid && sfold[j] != -100 &&
+                      (sfold[j] == -2 || (sfold[j] >= 0 && fd == sfold[j]) ||
+                       (sfold[j] <= -3 && fd != (-3 - sfold[j])));
+          if (test) {
+            double r = (double)yr - (double)raw;
+            acc_loss[j] += r * r;
+            acc_n[j] += 1;
+          }
         } else {
           gout[j] = raw;
         }
@@ -175,6 +186,7 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
     for (int j = 0; j < 4; ++j) {
       double v;
       if (MODE == MODE_FIT) v = pass == 0 ? acc_loss[j] : acc_g[j];
+      else if (MODE == MODE_R2) v = pass == 0 ? acc_loss[j] : (double)acc_n[j];
       else v = pass == 0 ? (double)acc_c[j] : (double)acc_n[j];
       red[ty][tx * 4 + j] = v;
     }
@@ -188,6 +200,9 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
         if (MODE == MODE_FIT) {
           if (pass == 0) lossp[(int64_t)z * n_act + s] = sum;
           else gsump[(int64_t)z * n_act + s] = sum;
+        } else if (MODE == MODE_R2) {
+          if (pass == 0) atomicAdd(&lossp[s], sum);      // sum of squared residuals per slot
+          else atomicAdd((unsigned long long*)&count[s], (unsigned long long)(sum + 0.5));
         } else {
           if (pass == 0) atomicAdd((unsigned long long*)&correct[s], (unsigned long long)(sum + 0.5));
           else atomicAdd((unsigned long long*)&count[s], (unsigned long long)(sum + 0.5));
@@ -280,7 +295,7 @@ int simt_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
   dim3 gf((n_act + TN - 1) / TN, nz);
   fwd_kernel<MODE_FIT><<<gf, 256, 0, c->stream>>>(
       c->X, c->n, ldx, w.Wact, w.Wact + (size_t)w.B * ldx /*bias block*/, w.slot, n_act, c->ycls,
-      c->fold, rpc, w.G, w.ldg, w.lossp, w.gsump, nullptr, nullptr, nullptr, 0);
+      c->fold, rpc, w.G, w.ldg, w.lossp, w.gsump, nullptr, nullptr, nullptr, 0, nullptr);
   dim3 gb((ldx + 63) / 64, (n_act + TN - 1) / TN, nz);
   bwd_kernel<<<gb, 256, 0, c->stream>>>(c->X, c->n, ldx, w.G, w.ldg, n_act, rpc, w.gradp);
   c->launches += 2;
@@ -299,10 +314,26 @@ int simt_score(Ctx* c, int B, const float* dW, const SlotMeta* dslot, int64_t* d
   dim3 g((B + TN - 1) / TN, nz);
   fwd_kernel<MODE_SCORE><<<g, 256, 0, c->stream>>>(
       c->X, c->n, ldx, dW, dW + (size_t)B * ldx, dslot, B, c->ycls, c->fold, rpc, nullptr, 0,
-      nullptr, nullptr, dcorrect, dcount, nullptr, 0);
+      nullptr, nullptr, dcorrect, dcount, nullptr, 0, nullptr);
   c->launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(c, std::string("simt_score launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+// sum of squared residuals and row counts per slot (regression scoring; fold codes as simt_score)
+int simt_r2(Ctx* c, int B, const float* dW, const SlotMeta* dslot, double* dsse, int64_t* dcount) {
+  int nz;
+  int64_t rpc;
+  pick_chunks(c, c->n, B, 4096, &nz, &rpc);
+  const int ldx = (int)c->ldx;
+  dim3 g((B + TN - 1) / TN, nz);
+  fwd_kernel<MODE_R2><<<g, 256, 0, c->stream>>>(
+      c->X, c->n, ldx, dW, dW + (size_t)B * ldx, dslot, B, nullptr, c->fold, rpc, nullptr, 0, dsse,
+      nullptr, nullptr, dcount, nullptr, 0, c->yreal);
+  c->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, std::string("simt_r2 launch: ") + cudaGetErrorString(e));
   return 0;
 }
 
@@ -315,7 +346,7 @@ int simt_decision(Ctx* c, int B, const float* dW, float* dout) {
   // slot metadata is unused in decision mode except for bounds; pass a dummy pointer-safe array
   fwd_kernel<MODE_DECISION><<<g, 256, 0, c->stream>>>(
       c->X, c->n, ldx, dW, dW + (size_t)B * ldx, nullptr, B, c->ycls, c->fold, rpc, nullptr, 0,
-      nullptr, nullptr, nullptr, nullptr, dout, B);
+      nullptr, nullptr, nullptr, nullptr, dout, B, nullptr);
   c->launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(c, std::string("simt_decision launch: ") + cudaGetErrorString(e));

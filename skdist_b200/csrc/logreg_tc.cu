@@ -277,7 +277,7 @@ __global__ void tc_rowmeta_kernel(const int32_t* __restrict__ ycls, const int8_t
   uint32_t m = 0xFF000000u;
   if (r < n) {
     uint32_t f = fold ? (uint32_t)(uint8_t)fold[r] : 0u;
-    m = (f << 24) | ((uint32_t)ycls[r] & 0x00FFFFFFu);
+    m = (f << 24) | (ycls ? ((uint32_t)ycls[r] & 0x00FFFFFFu) : 0u);
   }
   rowmeta[r] = m;
 }
@@ -340,6 +340,7 @@ struct TcParams {
   const __half* Wl;          // [slots_pad x dpad]
   const TcSlotParam* sp;     // [slots]
   const uint32_t* rowmeta;   // [npad]
+  const float* yreal;        // [npad] regression targets (TC_R2)
   double* lossp;             // [nz x n_act]        (fit)
   double* gsump;             // [nz x n_act]        (fit)
   float* gradp;              // [nz x n_act x ldw]  (fit)
@@ -384,7 +385,7 @@ __device__ __forceinline__ int tc_first_cta(int g, int n_tiles, long long units,
   return (int)c;
 }
 
-enum { TC_FIT = 0, TC_SCORE = 1 };
+enum { TC_FIT = 0, TC_SCORE = 1, TC_R2 = 2 };
 
 template <int NCHUNK, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -524,7 +525,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                 mma_ss(zcol, a_base + aoff, bb + boff, idesc1, 1u);
               }
               tc_commit(&bars->z_full[tc & 1]);
-              if (MODE == TC_SCORE) {  // no GEMM2: the ring slots are free once GEMM1 has read them
+              if (MODE != TC_FIT) {  // no GEMM2: the ring slots are free once GEMM1 has read them
                 tc_commit(&bars->empty[hh % TC_NS]);
                 tc_commit(&bars->empty[(hh + 1) % TC_NS]);
               }
@@ -632,6 +633,15 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             rm[4 * j] = v.x; rm[4 * j + 1] = v.y; rm[4 * j + 2] = v.z; rm[4 * j + 3] = v.w;
           }
         }
+        float yv[32];
+        if (MODE == TC_R2) {
+          const float4* y4 = reinterpret_cast<const float4*>(prm.yreal + (size_t)t * TC_R + hf * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v = __ldg(y4 + j);
+            yv[4 * j] = v.x; yv[4 * j + 1] = v.y; yv[4 * j + 2] = v.z; yv[4 * j + 3] = v.w;
+          }
+        }
         mbar_wait(&bars->z_full[tcount & 1], (tcount >> 1) & 1, 300);
         tc_fence_after();
         float lt = 0.f, gt = 0.f;
@@ -672,6 +682,18 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
               out[8 + j] = pack_f16x2(a - hf2.x, b - hf2.y);
             }
             tmem_st16(zb + ch * 16, out);
+          } else if (MODE == TC_R2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const uint32_t m = rm[cc * 16 + j];
+              const float z = fmaf(__uint_as_float(zr[j]), sp.inv_t, sp.bias);
+              const int fr = (int)(m >> 24);
+              const bool in = (fr != 0xFF) && (sp.fold == -2 || (sp.fold >= 0 && fr == sp.fold) ||
+                                               (sp.fold <= -3 && fr != (-3 - sp.fold)));
+              const float r = yv[cc * 16 + j] - z;
+              lt += in ? r * r : 0.f;
+              all_t += in ? 1 : 0;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -721,6 +743,11 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
         if (valid && nt > 0) {   // the two half-warps of a slot add into the zeroed partial (a + b == b + a)
           atomicAdd(prm.lossp + (size_t)z_part * prm.n_act + slot, (double)ls_hi + (double)ls_lo);
           atomicAdd(prm.gsump + (size_t)z_part * prm.n_act + slot, (double)gs_hi + (double)gs_lo);
+        }
+      } else if (MODE == TC_R2) {
+        if (valid && n_all > 0) {
+          atomicAdd(prm.lossp + slot, (double)ls_hi + (double)ls_lo);   // sum of squared residuals
+          atomicAdd(prm.count + slot, n_all);
         }
       } else if (valid && n_all > 0) {
         atomicAdd(prm.correct + slot, n_ok);
@@ -788,6 +815,7 @@ void tc_free(Ctx* c) {
   if (t.Xh) cudaFree(t.Xh);
   if (t.Xl) cudaFree(t.Xl);
   if (t.rowmeta) cudaFree(t.rowmeta);
+  if (t.yreal_pad) cudaFree(t.yreal_pad);
   if (t.xscale) cudaFree(t.xscale);
   if (t.gscale) cudaFree(t.gscale);
   t = TcData();
@@ -828,10 +856,15 @@ int tc_prepare(Ctx* c) {
     t.meta_valid = false;
   }
   if (!t.meta_valid) {
-    if (!c->ycls) return fail(c, "tc_prepare: labels not staged");
+    if (!c->ycls && !c->yreal) return fail(c, "tc_prepare: neither labels nor targets staged");
     tc_rowmeta_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(c->ycls, c->fold, n, npad,
                                                                             t.rowmeta);
     c->launches += 1;
+    if (c->yreal) {
+      if (!t.yreal_pad) SKD_CUDA(c, cudaMalloc((void**)&t.yreal_pad, (size_t)npad * sizeof(float)));
+      SKD_CUDA(c, cudaMemsetAsync(t.yreal_pad, 0, (size_t)npad * sizeof(float), c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(t.yreal_pad, c->yreal, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    }
     SKD_CUDA(c, cudaGetLastError());
     t.meta_valid = true;
   }
@@ -929,6 +962,7 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   prm.Wl = (const __half*)w.Wl;
   prm.sp = (const TcSlotParam*)w.sp;
   prm.rowmeta = t.rowmeta;
+  prm.yreal = t.yreal_pad;
   prm.lossp = w.lossp;
   prm.gsump = w.gsump;
   prm.gradp = w.gradp;
@@ -941,8 +975,10 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   prm.parts = parts;
   const size_t smem = 1024 + (size_t)nchunk * (TC_BC * 128) + (size_t)TC_NS * nchunk * (TC_R * 128) +
                       sizeof(TcBarriers) + 64;
+  if (mode == TC_R2 && !t.yreal_pad) return fail(c, "tc_r2: targets not staged");
   cudaError_t e = mode == TC_FIT ? tc_launch<TC_FIT>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm)
-                                 : tc_launch<TC_SCORE>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm);
+                  : mode == TC_SCORE ? tc_launch<TC_SCORE>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm)
+                                     : tc_launch<TC_R2>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm);
   c->launches += 1;
   if (e != cudaSuccess) return fail(c, std::string("tc_eval launch: ") + cudaGetErrorString(e));
   if (nz_used) *nz_used = nz;
@@ -956,6 +992,15 @@ int tc_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
 // Accuracy counts of n_act slots whose weights were exported with tc_export (sp.fold = scoring code).
 int tc_score(Ctx* c, LogregWork& w, int n_act, int64_t* dcorrect, int64_t* dcount) {
   return tc_run(c, w, n_act, TC_SCORE, nullptr, (unsigned long long*)dcorrect, (unsigned long long*)dcount);
+}
+
+// Sum of squared residuals / row counts of n_act regression slots (sp.fold = scoring code).
+int tc_r2(Ctx* c, LogregWork& w, int n_act, double* dsse, int64_t* dcount) {
+  double* keep = w.lossp;
+  w.lossp = dsse;
+  int rc = tc_run(c, w, n_act, TC_R2, nullptr, nullptr, (unsigned long long*)dcount);
+  w.lossp = keep;
+  return rc;
 }
 
 }  // namespace skd

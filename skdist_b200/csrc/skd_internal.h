@@ -21,6 +21,7 @@ struct TcData {
   void* Xh = nullptr;          // [npad x dpad] fp16, X * xscale rounded to fp16
   void* Xl = nullptr;          // [npad x dpad] fp16, remainder
   uint32_t* rowmeta = nullptr; // [npad] (fold << 24) | class id ; fold 0xFF = padding row
+  float* yreal_pad = nullptr;  // [npad] regression targets (zero padded), when staged
   float* xscale = nullptr;     // [dpad] power-of-two per-feature scale
   double* gscale = nullptr;    // [dpad] 1 / (xscale * 2^14): un-scales the gradient partials
   int dpad = 0;
@@ -143,6 +144,14 @@ int simt_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used);
 int simt_score(Ctx* c, int B, const float* dW, const SlotMeta* dslot, int64_t* dcorrect,
                int64_t* dcount);
 int simt_decision(Ctx* c, int B, const float* dW, float* dout);
+int simt_r2(Ctx* c, int B, const float* dW, const SlotMeta* dslot, double* dsse, int64_t* dcount);
+int sgd_fit_batch(Ctx* c, int B, const int32_t* col_pos, int loss, double alpha, int fit_intercept,
+                  int max_iter, double tol, int shuffle, uint32_t seed, int lr_type, double eta0,
+                  double power_t, double optimal_init, int n_iter_no_change, float* coef_out,
+                  double* intercept_out, int32_t* n_iter_out, double* t_out, int32_t* status_out);
+int predict_device(Ctx* c, const float* dX, int64_t m, int ldx, int d, int B, const float* dW, float* dout);
+int ridge_fit_batch(Ctx* c, int B, const double* alpha, const int32_t* hold, int fit_intercept,
+                    float* coef_out, int32_t* status_out);
 
 // tensor-core evaluation (logreg_tc.cu)
 bool tc_supported(const Ctx* c);
@@ -151,6 +160,7 @@ int tc_prepare(Ctx* c);
 int tc_export(Ctx* c, LogregWork& w, int n_act_upper, const double* xin, int fit_intercept);
 int tc_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used);
 int tc_score(Ctx* c, LogregWork& w, int n_act, int64_t* dcorrect, int64_t* dcount);
+int tc_r2(Ctx* c, LogregWork& w, int n_act, double* dsse, int64_t* dcount);
 size_t tc_slot_param_bytes();
 
 // device L-BFGS (lbfgs_dev.cu)

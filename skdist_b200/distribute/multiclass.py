@@ -1,0 +1,162 @@
+"""Distributed multiclass strategies on B200s.
+
+Drop-in for /root/reference/skdist/distribute/multiclass.py (class names, constructor
+signatures, fitted attributes).  The reference ships one dense 0/1 label vector per class to a
+Spark task that runs a full binary fit (`_fit_binary`, multiclass.py:109-152, fan-out
+:296-331).  Here the K label columns are K *columns* of one batched solve that shares X: rows
+carry an integer class id, column k treats `class id == k` as positive.
+
+  base estimator                         device path
+  --------------                         -----------
+  LogisticRegression(solver="lbfgs")     Engine.logreg_fit_batch (same kernels as the search path)
+  SGDClassifier(loss="hinge"|"log_loss") Engine.sgd_fit_batch (exact-order column-batched SGD)
+  anything else                          NotImplementedError (no CPU fallback by design)
+"""
+import warnings
+
+import numpy as np
+from sklearn.base import BaseEstimator
+from sklearn.linear_model import LogisticRegression, SGDClassifier
+from sklearn.multiclass import OneVsRestClassifier
+from sklearn.preprocessing import LabelBinarizer, normalize
+from sklearn.utils.validation import check_is_fitted
+
+from .. import parallel
+from ..engine import get_engine
+from .base import _clone, _parse_partitions, _ScParamMixin
+from .validation import _check_estimator
+
+__all__ = ["DistOneVsRestClassifier"]
+
+
+class _ConstantPredictor(BaseEstimator):
+    """Predicts the single label seen in training (ref multiclass.py:175-192)."""
+
+    def fit(self, X, y):
+        self.y_ = y
+        return self
+
+    def predict(self, X):
+        check_is_fitted(self, "y_")
+        return np.repeat(self.y_, X.shape[0])
+
+    def decision_function(self, X):
+        check_is_fitted(self, "y_")
+        return np.repeat(self.y_, X.shape[0])
+
+    def predict_proba(self, X):
+        check_is_fitted(self, "y_")
+        return np.repeat([np.hstack([1 - self.y_, self.y_])], X.shape[0], axis=0)
+
+
+def _binary_estimator(template, coef_row, n_features, X_dtype, **extra):
+    """A genuine fitted sklearn binary classifier (classes_ = [0, 1]) as `_fit_binary` returns
+    (ref multiclass.py:141-152) so the inherited predict / decision_function work."""
+    est = _clone(template)
+    dt = np.float64 if X_dtype == np.float64 else np.float32
+    est.coef_ = coef_row[None, :n_features].astype(dt)
+    b = coef_row[n_features:n_features + 1]
+    # LogisticRegression keeps the intercept in X's dtype, SGDClassifier in float64
+    bdt = dt if isinstance(est, LogisticRegression) else np.float64
+    est.intercept_ = b.astype(bdt) if est.fit_intercept else np.zeros(1, bdt)
+    est.classes_ = np.array([0, 1])
+    est.n_features_in_ = n_features
+    for k, v in extra.items():
+        setattr(est, k, v)
+    return est
+
+
+class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
+    """One-vs-the-rest with all label columns fitted as one batched GPU solve.
+    Constructor mirrors ref multiclass.py:230-253 (``sc`` is the 2nd positional argument)."""
+
+    def __init__(self, estimator, sc=None, norm=None, partitions="auto", max_negatives=None,
+                 random_state=None, method="ratio", n_splits=1, mlb_override=False, verbose=False,
+                 n_jobs=None):
+        self.estimator = estimator
+        self.sc = sc
+        self.norm = norm
+        self.partitions = partitions
+        self.max_negatives = max_negatives
+        self.random_state = random_state
+        self.method = method
+        self.n_splits = n_splits
+        self.mlb_override = mlb_override
+        self.verbose = verbose
+        self.n_jobs = n_jobs
+
+    def fit(self, X, y, **fit_params):
+        """Fit the K binary estimators (ref multiclass.py:255-335)."""
+        if fit_params:
+            raise NotImplementedError("fit_params are not supported on the device path")
+        _check_estimator(self, verbose=self.verbose)
+        if self.max_negatives is not None:
+            raise NotImplementedError("max_negatives down-sampling has no device path yet")
+        X_arr = np.asarray(X)
+        y_arr = np.asarray(y)
+        if y_arr.ndim != 1:
+            raise NotImplementedError("multilabel targets have no device path yet (1-d class labels only)")
+        self.label_binarizer_ = LabelBinarizer(sparse_output=True)      # ref :279-281
+        self.label_binarizer_.fit(y_arr)
+        self.classes_ = self.label_binarizer_.classes_
+        K = len(self.classes_)
+        n, d = X_arr.shape
+        _parse_partitions(self.partitions, K)
+        ycls = np.searchsorted(self.classes_, y_arr).astype(np.int32)
+        counts = np.bincount(ycls, minlength=K)
+
+        rank, world, _ = parallel.dist_info()
+        eng = get_engine()
+        eng.stage_x(X_arr)
+        eng.stage_labels(ycls)
+        eng.stage_folds(None, 0)
+        base = self.estimator
+        # constant columns (a label present in every / no row) -> _ConstantPredictor (ref :121-139)
+        const = (counts == 0) | (counts == n) if K > 2 else np.zeros(K, bool)
+        if K == 2:
+            # LabelBinarizer gives ONE column for binary problems (positive = classes_[1])
+            col_ids = np.array([1])
+        else:
+            col_ids = np.flatnonzero(~const)
+        mine = col_ids[parallel.shard_indices(len(col_ids), rank, world)]
+        if type(base) is LogisticRegression:
+            from .search import _check_logreg
+            p = _check_logreg(_clone(base))
+            res = eng.logreg_fit_batch(np.full(len(mine), p["C"]), np.full(len(mine), -1, np.int32),
+                                       mine.astype(np.int32), fit_intercept=p["fit_intercept"],
+                                       tol=p["tol"], max_iter=p["max_iter"])
+            packed = np.concatenate([res["coef"], res["n_iter"][:, None].astype(np.float32)], axis=1)
+            extra_of = lambda row: {"n_iter_": np.array([int(row[-1])], dtype=np.int32)}
+        elif type(base) is SGDClassifier:
+            res = eng.sgd_fit_batch(base, mine.astype(np.int32))
+            packed = np.concatenate([res["coef"], res["n_iter"][:, None].astype(np.float64),
+                                     res["t"][:, None]], axis=1)
+            extra_of = lambda row: {"n_iter_": int(row[-2]), "t_": float(row[-1])}
+        else:
+            raise NotImplementedError(
+                "%s has no device path; supported base estimators: LogisticRegression(solver='lbfgs'), "
+                "SGDClassifier.  (No CPU fallback by design.)" % type(base).__name__)
+        full = parallel.all_gather_columns(packed, len(col_ids), rank, world)
+        by_col = {int(c): full[i] for i, c in enumerate(col_ids)}
+        ests = []
+        cols = [1] if K == 2 else range(K)
+        for k in cols:
+            if k in by_col:
+                row = by_col[k]
+                ests.append(_binary_estimator(base, row[:d + 1], d, X_arr.dtype, **extra_of(row)))
+            else:
+                warnings.warn("Label %s is present in all training examples." % str(self.classes_[k]))
+                ests.append(_ConstantPredictor().fit(X_arr, np.array([1 if counts[k] == n else 0])))
+        self.estimators_ = ests
+        self.n_features_in_ = d
+        del self.sc                                                     # ref :283
+        if hasattr(self.estimator, "sc"):
+            del self.estimator.sc
+        return self
+
+    def predict_proba(self, X):
+        """Per-class probabilities with optional normalisation (ref multiclass.py:337-362)."""
+        probs = np.column_stack([e.predict_proba(X)[:, 1] for e in self.estimators_])
+        if self.norm:
+            return normalize(probs, norm=self.norm)
+        return probs

@@ -1,0 +1,134 @@
+"""(candidate x fold) columns of dense Ridge regression on the device.
+
+Replaces, for `DistGridSearchCV/DistRandomizedSearchCV(Ridge(), ...)`, the per-task
+`Ridge.fit` + r2 scoring that the reference fans out (ref search.py:180-288): one pass over X
+gives every fold's Gram block; each (alpha, fold) is then a 256x256 Cholesky solve
+(csrc/ridge.cu) and one r2 epilogue pass scores all columns (csrc/logreg_tc.cu TC_R2)."""
+import time
+from collections import defaultdict
+
+import numpy as np
+
+from .base import _clone
+
+_RIDGE_SEARCHABLE = {"alpha", "fit_intercept"}
+
+
+def _resolve(estimator, params):
+    est = _clone(estimator)
+    if params:
+        est.set_params(**params)
+    return est
+
+
+def _check_ridge(est):
+    p = est.get_params(deep=False)
+    bad = []
+    if p.get("solver", "auto") not in ("auto", "cholesky"):
+        bad.append("solver=%r (only 'auto'/'cholesky')" % p["solver"])
+    if p.get("positive", False):
+        bad.append("positive=True")
+    if np.ndim(p.get("alpha", 1.0)) != 0:
+        bad.append("per-target alpha")
+    if bad:
+        raise NotImplementedError("Ridge configuration without a device path: " + ", ".join(bad))
+    return p
+
+
+class _RidgeFamily:
+    name = "ridge"
+
+    def __init__(self, estimator, candidate_params, X, y, scorers):
+        self.estimator = estimator
+        for p in candidate_params:
+            extra = set(p) - _RIDGE_SEARCHABLE
+            if extra:
+                raise NotImplementedError(
+                    "searching Ridge over %s has no device path (searchable: %s)"
+                    % (sorted(extra), sorted(_RIDGE_SEARCHABLE)))
+        self.cands = [_check_ridge(_resolve(estimator, p)) for p in candidate_params]
+        if np.ndim(y) != 1:
+            raise NotImplementedError("multi-target Ridge has no device path")
+        self.y = np.asarray(y, dtype=np.float32)
+        scorer = scorers["score"]
+        ok = type(scorer).__name__ == "_PassthroughScorer"
+        if not ok:
+            f = getattr(scorer, "_score_func", None)
+            ok = getattr(f, "__name__", "") == "r2_score" and getattr(scorer, "_sign", 1) == 1 \
+                and not getattr(scorer, "_kwargs", {})
+        if not ok:
+            raise NotImplementedError("only scoring=None / 'r2' is scored on the device for regressors")
+
+    def stage(self, eng, X, fold, n_splits):
+        eng.stage_x(X)
+        eng.stage_targets(self.y)
+        eng.stage_folds(fold, n_splits)
+        self.fold = fold
+        y64 = self.y.astype(np.float64)
+        self.sst_test = np.zeros(n_splits)
+        self.sst_train = np.zeros(n_splits)
+        for k in range(n_splits):
+            t = y64[fold == k]
+            self.sst_test[k] = np.sum((t - t.mean()) ** 2)
+            t = y64[fold != k]
+            self.sst_train[k] = np.sum((t - t.mean()) ** 2)
+
+    def run_columns(self, eng, cols, n_splits, return_train_score):
+        cols = np.asarray(cols, dtype=np.int64)
+        out = {
+            "test_score": np.zeros(len(cols)), "n_test": np.zeros(len(cols), dtype=np.int64),
+            "fit_time": np.zeros(len(cols)), "score_time": np.zeros(len(cols)),
+            "n_iter": np.zeros(len(cols), dtype=np.int32), "status": np.zeros(len(cols), dtype=np.int32),
+        }
+        if return_train_score:
+            out["train_score"] = np.zeros(len(cols))
+        cand = cols // n_splits
+        fold = (cols % n_splits).astype(np.int32)
+        groups = defaultdict(list)
+        for i, c in enumerate(cand):
+            groups[bool(self.cands[c]["fit_intercept"])].append(i)
+        for fi, idx in groups.items():
+            idx = np.asarray(idx)
+            alpha = np.array([self.cands[c]["alpha"] for c in cand[idx]], dtype=np.float64)
+            t0 = time.time()
+            res = eng.ridge_fit_batch(alpha, fold[idx], fit_intercept=fi)
+            t1 = time.time()
+            sse, count = eng.linear_r2_batch(res["coef"], fold[idx])
+            t2 = time.time()
+            score = 1.0 - sse / self.sst_test[fold[idx]]
+            score[res["status"] != 1] = np.nan
+            out["test_score"][idx] = score
+            out["n_test"][idx] = count
+            out["fit_time"][idx] = (t1 - t0) / len(idx)
+            out["score_time"][idx] = (t2 - t1) / len(idx)
+            out["status"][idx] = res["status"]
+            if return_train_score:
+                sse2, _ = eng.linear_r2_batch(res["coef"], (-3 - fold[idx]).astype(np.int32))
+                out["train_score"][idx] = 1.0 - sse2 / self.sst_train[fold[idx]]
+        return out
+
+    def refit(self, eng, params, X_dtype, n_features):
+        p = _check_ridge(_resolve(self.estimator, params))
+        res = eng.ridge_fit_batch(np.array([p["alpha"]]), np.array([-1], dtype=np.int32),
+                                  fit_intercept=p["fit_intercept"])
+        return self.make_estimator(params, res["coef"][0], X_dtype, n_features)
+
+    def make_estimator(self, params, coef_row, X_dtype, n_features):
+        """A genuine fitted sklearn Ridge (attributes as SK/linear_model/_ridge.py:1016-1020 leaves
+        them) so inherited predict/score work."""
+        est = _resolve(self.estimator, params)
+        dt = np.float64 if X_dtype == np.float64 else np.float32
+        est.coef_ = coef_row[:n_features].astype(dt)
+        est.intercept_ = dt(coef_row[n_features]) if est.fit_intercept else 0.0
+        est.n_iter_ = None
+        est.solver_ = "cholesky"
+        est.n_features_in_ = n_features
+        return est
+
+    def fold_proba(self, eng, params, fold, n_splits):
+        """preds_ (ref search.py:551-560): regressors have no predict_proba -> predict."""
+        p = _check_ridge(_resolve(self.estimator, params))
+        f = np.arange(n_splits, dtype=np.int32)
+        res = eng.ridge_fit_batch(np.full(n_splits, p["alpha"]), f, fit_intercept=p["fit_intercept"])
+        dec = eng.linear_decision(res["coef"])
+        return np.vstack([dec[fold == k, k][:, None] for k in range(n_splits)])

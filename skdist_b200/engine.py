@@ -135,6 +135,92 @@ class Engine:
                                                ptr(correct), ptr(count)), self._h)
         return correct, count
 
+    def sgd_fit_batch(self, est, col_pos):
+        """Fit one binary SGDClassifier per entry of col_pos (one-vs-rest label columns).
+        `est` is the template SGDClassifier; host-side constants are derived exactly as
+        SK/linear_model/_stochastic_gradient.py:455-473 and _sgd_fast.pyx.tp:447-452 do."""
+        p = est.get_params(deep=False)
+        bad = []
+        loss = {"hinge": 0, "log_loss": 1}.get(p["loss"])
+        if loss is None:
+            bad.append("loss=%r" % p["loss"])
+        if p["penalty"] != "l2":
+            bad.append("penalty=%r" % (p["penalty"],))
+        lr = {"optimal": 0, "constant": 1, "invscaling": 2}.get(p["learning_rate"])
+        if lr is None:
+            bad.append("learning_rate=%r" % p["learning_rate"])
+        for k in ("average", "early_stopping", "warm_start"):
+            if p.get(k):
+                bad.append("%s=%r" % (k, p[k]))
+        if p.get("class_weight") is not None:
+            bad.append("class_weight")
+        if bad:
+            raise NotImplementedError("SGDClassifier configuration without a device path: " + ", ".join(bad))
+        from sklearn.utils import check_random_state
+        max_int = np.iinfo(np.int32).max
+        rs = check_random_state(p["random_state"])
+        rs.randint(1, max_int)                 # make_dataset() draws the dataset seed first
+        seed = int(rs.randint(max_int))
+        alpha = float(p["alpha"])
+        typw = np.sqrt(1.0 / np.sqrt(alpha))
+        if loss == 0:
+            g0 = -1.0 if -typw <= 1.0 else 0.0      # Hinge.cy_gradient(1.0, -typw)
+        else:
+            z = -typw
+            g0 = -1.0 / (np.exp(z) + 1.0) if -18.0 <= z <= 18.0 else (-1.0 if z < -18.0 else -np.exp(-z))
+        optimal_init = 1.0 / ((typw / max(1.0, g0)) * alpha)
+        col_pos = np.ascontiguousarray(col_pos, dtype=np.int32)
+        B = col_pos.shape[0]
+        coef = np.empty((B, self.d), dtype=np.float32)
+        intercept = np.empty(B, dtype=np.float64)
+        n_iter = np.empty(B, dtype=np.int32)
+        t = np.empty(B, dtype=np.float64)
+        status = np.empty(B, dtype=np.int32)
+        secs = ctypes.c_double(0.0)
+        tol = -np.inf if p["tol"] is None else float(p["tol"])
+        check(self._lib.skd_sgd_fit_batch(
+            self._h, B, ptr(col_pos), loss, alpha, int(bool(p["fit_intercept"])), int(p["max_iter"]), tol,
+            int(bool(p["shuffle"])), seed, lr, float(p["eta0"]), float(p["power_t"]), float(optimal_init),
+            int(p["n_iter_no_change"]), ptr(coef), ptr(intercept), ptr(n_iter), ptr(t), ptr(status),
+            ctypes.byref(secs)), self._h)
+        return {"coef": np.concatenate([coef.astype(np.float64), intercept[:, None]], axis=1),
+                "coef32": coef, "intercept": intercept, "n_iter": n_iter, "t": t, "status": status,
+                "gpu_seconds": secs.value}
+
+    def ridge_fit_batch(self, alpha, col_fold, fit_intercept=True):
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        B = alpha.shape[0]
+        col_fold = np.ascontiguousarray(col_fold, dtype=np.int32)
+        coef = np.empty((B, self.d + 1), dtype=np.float32)
+        status = np.empty(B, dtype=np.int32)
+        secs = ctypes.c_double(0.0)
+        check(self._lib.skd_ridge_fit_batch(self._h, B, ptr(alpha), ptr(col_fold), int(bool(fit_intercept)),
+                                            ptr(coef), ptr(status), ctypes.byref(secs)), self._h)
+        return {"coef": coef, "status": status, "gpu_seconds": secs.value}
+
+    def linear_r2_batch(self, coef, col_fold):
+        coef = np.ascontiguousarray(coef, dtype=np.float32)
+        B = coef.shape[0]
+        col_fold = np.ascontiguousarray(col_fold, dtype=np.int32)
+        sse = np.empty(B, dtype=np.float64)
+        count = np.empty(B, dtype=np.int64)
+        check(self._lib.skd_linear_r2_batch(self._h, B, ptr(coef), ptr(col_fold), ptr(sse), ptr(count)), self._h)
+        return sse, count
+
+    def predict_linear(self, Xnew, coef):
+        """out[m, B] for NEW host rows (streamed); coef [B, d+1] with the intercept last."""
+        Xnew = np.ascontiguousarray(Xnew, dtype=np.float32)
+        coef = np.ascontiguousarray(coef, dtype=np.float32)
+        m, d = Xnew.shape
+        B = coef.shape[0]
+        assert coef.shape[1] == d + 1
+        out = np.empty((m, B), dtype=np.float32)
+        secs = ctypes.c_double(0.0)
+        check(self._lib.skd_predict_linear(self._h, ptr(Xnew), m, d, d, B, ptr(coef), ptr(out),
+                                           ctypes.byref(secs)), self._h)
+        self.last_predict_seconds = secs.value
+        return out
+
     def linear_decision(self, coef):
         coef = np.ascontiguousarray(coef, dtype=np.float32)
         B = coef.shape[0]

@@ -6,6 +6,8 @@ package; tests install it through engine.set_engine_factory()."""
 import numpy as np
 
 from oracle import logreg_oracle as lo
+from oracle import ridge_oracle as ro
+from oracle import sgd_oracle as so
 
 
 class FakeEngine:
@@ -65,6 +67,46 @@ class FakeEngine:
             correct[j] = np.sum((z > 0) == (self.y[m] == col_pos[j]))
             count[j] = m.sum()
         return correct, count
+
+    def sgd_fit_batch(self, est, col_pos):
+        p = est.get_params(deep=False)
+        B = len(col_pos)
+        coef = np.zeros((B, self.d + 1))
+        n_iter = np.zeros(B, np.int32)
+        t = np.zeros(B)
+        for j in range(B):
+            ypm = np.where(self.y == col_pos[j], 1, -1)
+            w, b, it, tt = so.fit_binary_sgd(self.X, ypm, loss=p["loss"], alpha=p["alpha"],
+                                             fit_intercept=p["fit_intercept"], max_iter=p["max_iter"],
+                                             tol=-np.inf if p["tol"] is None else p["tol"], shuffle=p["shuffle"],
+                                             random_state=p["random_state"], n_iter_no_change=p["n_iter_no_change"])
+            coef[j, :self.d] = w
+            coef[j, self.d] = b
+            n_iter[j] = it
+            t[j] = tt
+        return {"coef": coef, "n_iter": n_iter, "t": t, "status": np.ones(B, np.int32), "gpu_seconds": 0.0}
+
+    def ridge_fit_batch(self, alpha, col_fold, fit_intercept=True):
+        B = len(alpha)
+        self.calls.append(("ridge", B))
+        coef = np.zeros((B, self.d + 1), np.float32)
+        for j in range(B):
+            m = self._train_mask(int(col_fold[j]))
+            w, b = ro.fit_ridge(self.X[m], self.yr[m], float(alpha[j]), fit_intercept)
+            coef[j, :self.d] = w
+            coef[j, self.d] = b
+        return {"coef": coef, "status": np.ones(B, np.int32), "gpu_seconds": 0.0}
+
+    def linear_r2_batch(self, coef, col_fold):
+        B = coef.shape[0]
+        sse = np.zeros(B)
+        count = np.zeros(B, np.int64)
+        for j in range(B):
+            m = self._rows(int(col_fold[j]))
+            pred = self.X[m] @ coef[j, :self.d] + coef[j, self.d]
+            sse[j] = np.sum((self.yr[m].astype(np.float64) - pred.astype(np.float64)) ** 2)
+            count[j] = m.sum()
+        return sse, count
 
     def linear_decision(self, coef):
         return (self.X @ coef[:, :self.d].T + coef[:, self.d][None, :]).astype(np.float32)

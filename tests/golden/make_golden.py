@@ -88,8 +88,37 @@ def run_case(name, X, y, grid, cv, ref_search):
     print(name, "mean_test_score", ref["cv_results_"]["mean_test_score"], "n_iter", n_iter.ravel())
 
 
+def run_ridge_case(name, X, y, alphas, cv, ref_search):
+    from sklearn.linear_model import Ridge
+    from sklearn.model_selection import KFold
+    est = Ridge()
+    cands = [{"alpha": float(a)} for a in alphas]
+    ref = search_oracle.search_cv(est, cands, X, y, cv=cv, iid=True, task_fn=reference_task(ref_search))
+    ora = search_oracle.search_cv(est, cands, X, y, cv=cv, iid=True)
+    keys = ["split%d_test_score" % i for i in range(cv)] + ["mean_test_score", "rank_test_score"]
+    for k in keys:
+        assert np.array_equal(ref["cv_results_"][k], ora["cv_results_"][k]), (name, k)
+    d = X.shape[1]
+    coef = np.zeros((len(cands), cv, d + 1), np.float32)
+    for ci, p in enumerate(cands):
+        for fi, (tr, te) in enumerate(KFold(cv).split(X)):
+            m = Ridge(**p).fit(X[tr], y[tr])
+            coef[ci, fi, :d] = m.coef_
+            coef[ci, fi, d] = m.intercept_
+    out = {k: ref["cv_results_"][k] for k in keys}
+    out.update(best_index=ref["best_index_"], coef=coef, alpha=np.asarray(alphas, float),
+               refit_coef=np.r_[ref["best_estimator_"].coef_, ref["best_estimator_"].intercept_])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "mean_test_score", ref["cv_results_"]["mean_test_score"])
+
+
 def main():
     ref_search, _, _ = refshim.load()
+    if "--ridge-only" in sys.argv:
+        from skdist_b200.datasets import make_g1_regression
+        X, y = make_g1_regression(6000, 40, seed=5)
+        run_ridge_case("search_ridge_g1_6000x40", X, y, [1e-3, 1e-1, 1.0, 10.0, 1e3], 4, ref_search)
+        return
     X, y = make_g1_classification(4000, 16, seed=3)
     run_case("search_logreg_g1_4000x16", X, y, {"C": [1e-3, 1e-2, 1e-1, 1.0, 10.0, 100.0]}, 3, ref_search)
     X, y = make_g1_classification(20000, 64, seed=4)

@@ -157,3 +157,117 @@ def test_dist_grid_search_end_to_end(eng):
                                atol=2e-3 * np.abs(ora["best_estimator_"].coef_).max())
     assert np.mean(gs.predict(X) == ora["best_estimator_"].predict(X)) > 0.9995
     assert gs.best_estimator_.coef_.dtype == np.float32
+
+
+def test_ridge_batch_vs_golden(eng):
+    """Deterministic linear solver: r2 per split within 1e-5 relative of the reference's
+    _fit_and_score(Ridge) (north-star tolerance), coefficients within fp32 Cholesky accuracy,
+    identical best candidate."""
+    from skdist_b200.datasets import make_g1_regression
+    g = np.load(os.path.join(GOLD, "search_ridge_g1_6000x40.npz"))
+    X, y = make_g1_regression(6000, 40, seed=5)
+    cv = 4
+    fold = np.repeat(np.arange(cv), 1500).astype(np.int8)     # KFold(4), unshuffled
+    eng.stage_x(X); eng.stage_targets(y); eng.stage_folds(fold, cv)
+    alphas = g["alpha"]
+    A = np.repeat(alphas, cv)
+    cf = np.tile(np.arange(cv, dtype=np.int32), len(alphas))
+    res = eng.ridge_fit_batch(A, cf)
+    assert np.all(res["status"] == 1)
+    gc = g["coef"].reshape(len(A), -1)
+    np.testing.assert_allclose(res["coef"], gc, rtol=0, atol=2e-5 * np.abs(gc).max())
+    sse, count = eng.linear_r2_batch(res["coef"], cf)
+    assert np.all(count == 1500)
+    y64 = y.astype(np.float64)
+    sst = np.array([np.sum((y64[fold == k] - y64[fold == k].mean()) ** 2) for k in range(cv)])
+    r2 = 1.0 - sse / sst[cf]
+    gold = np.stack([g["split%d_test_score" % i] for i in range(cv)], 1).ravel()
+    np.testing.assert_allclose(r2, gold, rtol=1e-5)
+    assert r2.reshape(len(alphas), cv).mean(1).argmax() == int(g["best_index"])
+    # refit on all rows
+    ref = eng.ridge_fit_batch(np.array([alphas[int(g["best_index"])]]), np.array([-1], np.int32))
+    np.testing.assert_allclose(ref["coef"][0], g["refit_coef"], rtol=0, atol=2e-5 * np.abs(g["refit_coef"]).max())
+
+
+def test_ridge_uncentred_features_and_no_intercept(eng):
+    """Large feature means (the reference centres before the Gram product) and fit_intercept=False."""
+    from oracle import ridge_oracle as ro
+    from skdist_b200.datasets import make_g1_regression
+    X, y = make_g1_regression(4000, 17, seed=8)
+    X = (X + 25.0).astype(np.float32)
+    eng.stage_x(X); eng.stage_targets(y); eng.stage_folds(None, 0)
+    for fi in (True, False):
+        res = eng.ridge_fit_batch(np.array([0.5, 50.0]), np.array([-1, -1], np.int32), fit_intercept=fi)
+        for j, a in enumerate([0.5, 50.0]):
+            w, b = ro.fit_ridge(X.astype(np.float64), y.astype(np.float64), a, fi)    # float64 truth
+            scale = np.abs(w).max()
+            np.testing.assert_allclose(res["coef"][j, :17], w, rtol=0, atol=3e-4 * scale)
+            assert abs(res["coef"][j, 17] - b) <= 3e-3 * max(1.0, abs(b))
+
+
+def test_predict_linear_streaming(eng):
+    from skdist_b200.datasets import make_g1_regression
+    X, _ = make_g1_regression(30000, 50, seed=9)
+    rng = np.random.default_rng(0)
+    coef = rng.standard_normal((3, 51)).astype(np.float32)
+    out = eng.predict_linear(X, coef)
+    want = X.astype(np.float64) @ coef[:, :50].T.astype(np.float64) + coef[:, 50]
+    np.testing.assert_allclose(out, want, rtol=0, atol=2e-5 * np.abs(want).max())
+    eng.stage_x(X)
+    np.testing.assert_allclose(eng.linear_decision(coef), want, rtol=0, atol=2e-5 * np.abs(want).max())
+
+
+def test_dist_randomized_search_ridge_end_to_end(eng):
+    from scipy.stats import loguniform
+    from sklearn.linear_model import Ridge
+    from sklearn.model_selection import ParameterSampler
+    from oracle import search_oracle
+    from skdist.distribute.search import DistRandomizedSearchCV
+    from skdist_b200.datasets import make_g1_regression
+    X, y = make_g1_regression(9000, 64, seed=10)
+    dist = {"alpha": loguniform(1e-3, 1e3)}
+    rs = DistRandomizedSearchCV(Ridge(), dist, None, n_iter=12, cv=5, random_state=0).fit(X, y)
+    ora = search_oracle.search_cv(Ridge(), list(ParameterSampler(dist, 12, random_state=0)), X, y, cv=5)
+    np.testing.assert_allclose(rs.cv_results_["mean_test_score"], ora["cv_results_"]["mean_test_score"], rtol=1e-5)
+    assert rs.best_params_ == ora["best_params_"]
+    np.testing.assert_allclose(rs.predict(X[:100]), ora["best_estimator_"].predict(X[:100]), rtol=0, atol=1e-3)
+
+
+def test_ovr_logreg_on_device(eng):
+    from sklearn.multiclass import OneVsRestClassifier
+    from skdist.distribute.multiclass import DistOneVsRestClassifier
+    from skdist_b200.datasets import make_multiclass
+    X, y = make_multiclass(6000, 24, 6, seed=11)
+    ovr = DistOneVsRestClassifier(LogisticRegression(C=0.05), None).fit(X, y)
+    ref = OneVsRestClassifier(LogisticRegression(C=0.05)).fit(X, y)
+    for a, b in zip(ovr.estimators_, ref.estimators_):
+        np.testing.assert_allclose(a.coef_, b.coef_, rtol=0, atol=1e-3 * np.abs(b.coef_).max())
+        assert abs(int(a.n_iter_[0]) - int(b.n_iter_[0])) <= 1
+    assert np.mean(ovr.predict(X) == ref.predict(X)) > 0.999
+
+
+def test_ovr_sgd_exact_order_on_device(eng):
+    """Hinge-loss SGD has no transcendental functions: the warp-per-column kernel reproduces
+    scikit-learn's float32/float64 arithmetic and shuffle order bit for bit."""
+    from sklearn.linear_model import SGDClassifier
+    from sklearn.multiclass import OneVsRestClassifier
+    from skdist.distribute.multiclass import DistOneVsRestClassifier
+    from skdist_b200.datasets import make_multiclass
+    import warnings
+    X, y = make_multiclass(3000, 40, 7, seed=12)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ovr = DistOneVsRestClassifier(SGDClassifier(random_state=0), None).fit(X, y)
+        ref = OneVsRestClassifier(SGDClassifier(random_state=0)).fit(X, y)
+    for a, b in zip(ovr.estimators_, ref.estimators_):
+        assert a.n_iter_ == b.n_iter_ and a.t_ == b.t_
+        np.testing.assert_array_equal(a.coef_, b.coef_)
+        np.testing.assert_array_equal(a.intercept_, b.intercept_)
+    np.testing.assert_array_equal(ovr.predict(X), ref.predict(X))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ovr = DistOneVsRestClassifier(SGDClassifier(loss="log_loss", random_state=1, shuffle=False), None).fit(X, y)
+        ref = OneVsRestClassifier(SGDClassifier(loss="log_loss", random_state=1, shuffle=False)).fit(X, y)
+    for a, b in zip(ovr.estimators_, ref.estimators_):
+        assert a.n_iter_ == b.n_iter_
+        np.testing.assert_allclose(a.coef_, b.coef_, rtol=0, atol=1e-5 * np.abs(b.coef_).max())

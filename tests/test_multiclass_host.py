@@ -1,0 +1,78 @@
+"""DistOneVsRestClassifier host logic (no GPU) against scikit-learn's OneVsRestClassifier, which the
+reference's DistOneVsRestClassifier equals bit for bit when run unmodified with sc=None
+(live check in test_reference_ovr_equals_sklearn)."""
+import pickle
+import warnings
+
+import numpy as np
+import pytest
+from sklearn.linear_model import LogisticRegression, SGDClassifier
+from sklearn.multiclass import OneVsRestClassifier
+
+from oracle import refshim, sgd_oracle
+from skdist.distribute.multiclass import DistOneVsRestClassifier
+from skdist_b200.datasets import make_multiclass
+
+
+def test_ovr_logreg_matches_sklearn(fake_engine):
+    X, y = make_multiclass(1200, 10, 5, seed=4)
+    ovr = DistOneVsRestClassifier(LogisticRegression(C=0.5), None).fit(X, y)
+    ref = OneVsRestClassifier(LogisticRegression(C=0.5)).fit(X, y)
+    assert list(ovr.classes_) == list(ref.classes_) and len(ovr.estimators_) == 5
+    for a, b in zip(ovr.estimators_, ref.estimators_):
+        np.testing.assert_array_equal(a.coef_, b.coef_)
+        np.testing.assert_array_equal(a.intercept_, b.intercept_)
+        assert a.coef_.dtype == b.coef_.dtype and list(a.classes_) == list(b.classes_)
+    np.testing.assert_array_equal(ovr.predict(X), ref.predict(X))
+    np.testing.assert_allclose(ovr.predict_proba(X[:20]).sum(1) > 0, True)
+    assert not hasattr(ovr, "sc")
+    pickle.loads(pickle.dumps(ovr))
+
+
+def test_reference_toy_case(fake_engine):
+    """ref skdist/distribute/tests/test_multiclass.py:23-38 (lbfgs instead of liblinear)."""
+    X = np.array([[0, 0, 1, 1], [1, 1, 0, 0], [-1, -1, -1, -1]] * 100)
+    y = np.array([0, 1, 2] * 100)
+    ovr = DistOneVsRestClassifier(LogisticRegression()).fit(X, y)
+    assert np.allclose(ovr.predict(X[:3]), np.array([0, 1, 2]))
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_sgd_oracle_is_bit_identical_to_sklearn():
+    X, y = make_multiclass(400, 7, 3, seed=6)
+    for loss in ("hinge", "log_loss"):
+        for shuffle in (True, False):
+            yk = (y == 1).astype(int)
+            m = SGDClassifier(loss=loss, random_state=3, shuffle=shuffle).fit(X, yk)
+            w, b, it, t = sgd_oracle.fit_binary_sgd(X, np.where(yk == 1, 1, -1), loss=loss, shuffle=shuffle,
+                                                    random_state=3)
+            if loss == "hinge":      # no transcendental functions: bit-exact
+                assert np.array_equal(w, m.coef_[0]) and b == m.intercept_[0]
+            else:                    # numpy's exp/log differ from libm's in the last ulp
+                np.testing.assert_allclose(w, m.coef_[0], rtol=0, atol=1e-5 * np.abs(w).max())
+            assert it == m.n_iter_ and t == m.t_
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_ovr_sgd_matches_sklearn(fake_engine):
+    X, y = make_multiclass(300, 6, 3, seed=7)
+    ovr = DistOneVsRestClassifier(SGDClassifier(random_state=0)).fit(X, y)
+    ref = OneVsRestClassifier(SGDClassifier(random_state=0)).fit(X, y)
+    for a, b in zip(ovr.estimators_, ref.estimators_):
+        np.testing.assert_array_equal(a.coef_, b.coef_)
+        np.testing.assert_array_equal(a.intercept_, b.intercept_)
+        assert a.n_iter_ == b.n_iter_ and a.t_ == b.t_
+    np.testing.assert_array_equal(ovr.predict(X), ref.predict(X))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+@pytest.mark.filterwarnings("ignore")
+def test_reference_ovr_equals_sklearn():
+    """Live pin of the oracle choice: the UNMODIFIED reference DistOneVsRestClassifier (sc=None)
+    equals sklearn's OneVsRestClassifier coefficient for coefficient."""
+    _, ref_multiclass, _ = refshim.load()
+    X, y = make_multiclass(500, 6, 4, seed=8)
+    r = ref_multiclass.DistOneVsRestClassifier(SGDClassifier(random_state=0)).fit(X, y)
+    s = OneVsRestClassifier(SGDClassifier(random_state=0)).fit(X, y)
+    for a, b in zip(r.estimators_, s.estimators_):
+        np.testing.assert_array_equal(a.coef_, b.coef_)

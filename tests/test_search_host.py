@@ -59,3 +59,26 @@ def test_preds_and_unsupported(fake_engine):
         DistGridSearchCV(GaussianNB(), {"var_smoothing": [1e-9]}, cv=3).fit(X, y)
     with pytest.raises(NotImplementedError):
         DistGridSearchCV(LogisticRegression(solver="liblinear"), {"C": [1.0]}, cv=3).fit(X, y)
+
+
+def test_ridge_randomized_matches_oracle(fake_engine):
+    """Config 5 shape in miniature: DistRandomizedSearchCV(Ridge) over loguniform alpha."""
+    from scipy.stats import loguniform
+    from sklearn.linear_model import Ridge
+    from sklearn.model_selection import ParameterSampler
+    from skdist_b200.datasets import make_g1_regression
+    X, y = make_g1_regression(2000, 10, seed=3)
+    dist = {"alpha": loguniform(1e-3, 1e3)}
+    rs = DistRandomizedSearchCV(Ridge(), dist, None, n_iter=6, cv=4, random_state=0,
+                                return_train_score=True).fit(X, y)
+    cands = list(ParameterSampler(dist, 6, random_state=0))
+    ora = search_oracle.search_cv(Ridge(), cands, X, y, cv=4, iid=True, return_train_score=True)
+    assert rs.cv_results_["params"] == cands
+    np.testing.assert_allclose(rs.cv_results_["mean_test_score"], ora["cv_results_"]["mean_test_score"],
+                               rtol=1e-6)
+    np.testing.assert_allclose(rs.cv_results_["mean_train_score"], ora["cv_results_"]["mean_train_score"],
+                               rtol=1e-6)
+    assert rs.best_index_ == ora["best_index_"]
+    np.testing.assert_allclose(rs.best_estimator_.coef_, ora["best_estimator_"].coef_, rtol=1e-5)
+    np.testing.assert_allclose(rs.predict(X[:20]), ora["best_estimator_"].predict(X[:20]), rtol=1e-5)
+    pickle.loads(pickle.dumps(rs))
