@@ -140,6 +140,7 @@ int skd_ctx_destroy(skd_ctx* ctx) {
   cudaStreamSynchronize(ctx->c.stream);
   free_staged(ctx->c);
   tc_free(&ctx->c);
+  forest_free(&ctx->c);
   cudaStreamDestroy(ctx->c.stream);
   delete ctx;
   return 0;
@@ -158,6 +159,7 @@ static int stage_x_common(Ctx* c, const float* src, int64_t n, int64_t d, int64_
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->n = n; c->d = d; c->ldx = ldx;
   c->tc.x_valid = false;
+  c->forest.valid = false;
   if (kind == cudaMemcpyHostToDevice) c->h2d += (int64_t)n * d * sizeof(float);
   return 0;
 }
@@ -666,6 +668,90 @@ int skd_sgd_fit_batch(skd_ctx* ctx, int32_t B, const int32_t* col_pos, int32_t l
   if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
   return rc;
 }
+
+struct skd_forest {
+  struct Tree {
+    int32_t max_depth = 0, n_classes = 0;
+    std::vector<int32_t> left, right, feature, nsamp;
+    std::vector<uint8_t> mgl;
+    std::vector<double> thr, imp, wn, val;
+  };
+  std::vector<Tree> trees;
+};
+
+static void forest_sink(void* arg, int t, const SkdTreeView* v) {
+  skd_forest* f = (skd_forest*)arg;
+  skd_forest::Tree& tr = f->trees[t];
+  const int m = v->node_count;
+  tr.max_depth = v->max_depth; tr.n_classes = v->n_classes;
+  tr.left.assign(v->left, v->left + m); tr.right.assign(v->right, v->right + m);
+  tr.feature.assign(v->feature, v->feature + m); tr.nsamp.assign(v->n_node_samples, v->n_node_samples + m);
+  tr.mgl.assign(v->missing_go_to_left, v->missing_go_to_left + m);
+  tr.thr.assign(v->threshold, v->threshold + m); tr.imp.assign(v->impurity, v->impurity + m);
+  tr.wn.assign(v->weighted_n_node_samples, v->weighted_n_node_samples + m);
+  tr.val.assign(v->value, v->value + (size_t)m * v->n_classes);
+}
+
+int skd_forest_fit(skd_ctx* ctx, int32_t n_trees, const uint8_t* sample_counts, const uint32_t* rand_states,
+                   int32_t n_classes, int32_t max_features, int32_t max_depth, int32_t min_samples_split,
+                   int32_t min_samples_leaf, double min_weight_leaf, double min_impurity_decrease,
+                   skd_forest** out, double* gpu_seconds_out) {
+  if (!ctx) return fail(nullptr, "skd_forest_fit: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!out) return fail(c, "skd_forest_fit: out is NULL");
+  *out = nullptr;
+  if (!c->X || !c->ycls) return fail(c, "skd_forest_fit: stage X and labels first");
+  if (n_trees <= 0 || !sample_counts || !rand_states || max_features < 1 || min_samples_split < 2 || min_samples_leaf < 1)
+    return fail(c, "skd_forest_fit: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  skd_forest* f = new skd_forest();
+  f->trees.resize(n_trees);
+  cudaEvent_t e0, e1;
+  SKD_CUDA(c, cudaEventCreate(&e0));
+  SKD_CUDA(c, cudaEventCreate(&e1));
+  SKD_CUDA(c, cudaEventRecord(e0, c->stream));
+  int rc = forest_fit(c, n_trees, sample_counts, rand_states, n_classes, max_features, max_depth, min_samples_split,
+                      min_samples_leaf, min_weight_leaf, min_impurity_decrease, forest_sink, f);
+  float ms = 0.f;
+  if (!rc) {
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
+  if (rc) { delete f; return rc; }
+  *out = f;
+  return 0;
+}
+
+int skd_forest_tree_size(skd_forest* f, int32_t tree, int32_t* node_count, int32_t* max_depth) {
+  if (!f || tree < 0 || tree >= (int)f->trees.size()) return fail(nullptr, "skd_forest_tree_size: bad arguments");
+  if (node_count) *node_count = (int32_t)f->trees[tree].left.size();
+  if (max_depth) *max_depth = f->trees[tree].max_depth;
+  return 0;
+}
+
+int skd_forest_tree_copy(skd_forest* f, int32_t tree, int32_t* left, int32_t* right, int32_t* feature,
+                         double* threshold, double* impurity, int32_t* n_node_samples,
+                         double* weighted_n_node_samples, uint8_t* missing_go_to_left, double* value) {
+  if (!f || tree < 0 || tree >= (int)f->trees.size()) return fail(nullptr, "skd_forest_tree_copy: bad arguments");
+  const skd_forest::Tree& t = f->trees[tree];
+  const size_t m = t.left.size();
+  if (left) memcpy(left, t.left.data(), m * 4);
+  if (right) memcpy(right, t.right.data(), m * 4);
+  if (feature) memcpy(feature, t.feature.data(), m * 4);
+  if (threshold) memcpy(threshold, t.thr.data(), m * 8);
+  if (impurity) memcpy(impurity, t.imp.data(), m * 8);
+  if (n_node_samples) memcpy(n_node_samples, t.nsamp.data(), m * 4);
+  if (weighted_n_node_samples) memcpy(weighted_n_node_samples, t.wn.data(), m * 8);
+  if (missing_go_to_left) memcpy(missing_go_to_left, t.mgl.data(), m);
+  if (value) memcpy(value, t.val.data(), t.val.size() * 8);
+  return 0;
+}
+
+void skd_forest_free(skd_forest* f) { delete f; }
 
 int skd_predict_linear(skd_ctx* ctx, const float* Xnew, int64_t m, int64_t d, int64_t ld, int32_t B,
                        const float* coef, float* out, double* gpu_seconds_out) {

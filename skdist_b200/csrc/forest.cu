@@ -1,0 +1,575 @@
+// forest.cu -- DistRandomForestClassifier: one persistent CTA per tree, exact depth-first builder.
+//
+// Replaces the reference's per-tree task `_build_trees` (ref ensemble.py:68-109: bootstrap counts
+// as sample_weight, then DecisionTreeClassifier.fit) for the default forest configuration:
+//   SK/tree/_tree.pyx:139-337      DepthFirstTreeBuilder.build  (stack order: push right, push left)
+//   SK/tree/_splitter.pyx:262-504  node_split_best  (Fisher-Yates feature draws from ONE xorshift
+//                                  stream, constant-feature bookkeeping, strict '>' on the proxy)
+//   SK/tree/_partitioner.pyx       DensePartitioner (sort node samples by feature value, scan the
+//                                  boundaries between values more than 1e-7 apart)
+//   SK/tree/_criterion.pyx:605-680 Gini (float64, same operation order; all class sums are integers,
+//                                  hence exact and independent of the summation order)
+// The sort-and-scan of a node is replaced by a shared-memory histogram over the feature's distinct
+// values (<= 256 per feature, precomputed bin codes, feature-major uint8): present bins visited in
+// ascending order ARE the sorted distinct values, so every candidate split, its class counts and
+// the threshold (v[p-1]/2 + v[p]/2) equal what the sort-based scan sees.  The tree topology, the
+// RNG consumption and therefore every later draw are bit-identical to scikit-learn's.
+// No tensor cores: the work is integer histogramming, bound by gather bandwidth / latency.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "skd_internal.h"
+
+namespace skd {
+
+constexpr int FO_THREADS = 256;
+constexpr int FO_MAXC = 16;      // classes
+constexpr int FO_BINS = 256;
+constexpr float FEATURE_THRESHOLD = 1e-7f;
+constexpr double FO_EPSILON = 2.220446049250313e-16;   // np.finfo('double').eps (SK/tree/_tree.pyx EPSILON)
+
+struct FoRecord {          // builder stack record (SK/tree/_tree.pyx StackRecord) + the node's class sums
+  int32_t start, end, depth, parent, is_left, n_const;
+  double impurity;
+  unsigned long long sums[FO_MAXC];
+};
+
+struct FoParams {
+  const uint8_t* xbin;        // [d][n] bin codes, feature-major
+  const float* binval;        // [d][256] distinct values ascending
+  const int32_t* ycls;        // [n]
+  int64_t n;
+  int d, n_classes;
+  int max_features, max_depth, min_samples_split, min_samples_leaf;
+  double min_weight_leaf, min_impurity_decrease;
+  // per tree (wave-local index = blockIdx.x)
+  const uint8_t* counts;      // [trees_in_wave][n] bootstrap multiplicities (sample_weight)
+  const uint32_t* rand_state; // [trees_in_wave]
+  int n_trees;
+  // per slot work + output buffers
+  uint2* samp;                // [slots][n]   (sample index, (weight << 8) | class)
+  uint2* samp_tmp;            // [slots][n]
+  FoRecord* stack;            // [slots][stack_cap]
+  int stack_cap;
+  int64_t node_cap;
+  int32_t* o_left; int32_t* o_right; int32_t* o_feature; int32_t* o_nsamp; uint8_t* o_mgl;
+  double* o_thr; double* o_imp; double* o_wn; double* o_val;   // o_val [node_cap][n_classes]
+  int32_t* o_count;           // [slots] node_count
+  int32_t* o_maxdepth;        // [slots]
+  int32_t* o_status;          // [slots] 0 ok, 1 node capacity, 2 stack capacity
+};
+
+__device__ __forceinline__ uint32_t fo_rand_r(uint32_t* seed) {   // SK/utils/_random.pxd:20-34
+  if (*seed == 0) *seed = 1;
+  *seed ^= (uint32_t)(*seed << 13);
+  *seed ^= (uint32_t)(*seed >> 17);
+  *seed ^= (uint32_t)(*seed << 5);
+  return *seed % ((uint32_t)2147483647 + 1);
+}
+__device__ __forceinline__ int fo_rand_int(int low, int high, uint32_t* seed) {
+  return low + (int)(fo_rand_r(seed) % (uint32_t)(high - low));
+}
+
+// Gini children impurity, float64 with scikit-learn's operation order (no FMA contraction)
+__device__ __forceinline__ void fo_children_impurity(const unsigned long long* sl, const unsigned long long* st,
+                                                     int C, double wl, double wr, double* il, double* ir) {
+  double sql = 0.0, sqr = 0.0;
+  for (int c = 0; c < C; ++c) {
+    const double a = (double)sl[c], b = (double)(st[c] - sl[c]);
+    sql = __dadd_rn(sql, __dmul_rn(a, a));
+    sqr = __dadd_rn(sqr, __dmul_rn(b, b));
+  }
+  *il = __dsub_rn(1.0, __ddiv_rn(sql, __dmul_rn(wl, wl)));
+  *ir = __dsub_rn(1.0, __ddiv_rn(sqr, __dmul_rn(wr, wr)));
+}
+
+__global__ void __launch_bounds__(FO_THREADS)
+forest_build_kernel(const FoParams P) {
+  const int slot = blockIdx.x;
+  if (slot >= P.n_trees) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int C = P.n_classes, d = P.d;
+  const int64_t n = P.n;
+  uint2* samp = P.samp + (size_t)slot * n;
+  uint2* tmp = P.samp_tmp + (size_t)slot * n;
+  FoRecord* stack = P.stack + (size_t)slot * P.stack_cap;
+  const uint8_t* cnt = P.counts + (size_t)slot * n;
+  const int64_t nb = (int64_t)slot * P.node_cap;
+
+  extern __shared__ int fo_sm[];
+  int* features = fo_sm;                     // [d]
+  int* constant_features = fo_sm + d;        // [d]
+  __shared__ unsigned int hist[FO_BINS * (FO_MAXC + 1)];   // [bin][C] class weights, then [bin] sample counts at offset C*256.. (layout below)
+  __shared__ unsigned int present[FO_BINS / 32];
+  __shared__ int wsum[FO_THREADS / 32][2];
+  __shared__ int s_ctrl[8];
+  __shared__ double s_dbl[4];
+  __shared__ FoRecord rec;
+  __shared__ unsigned long long best_sl[FO_MAXC];
+  unsigned int* hcls = hist;                 // hcls[c * 256 + bin]
+  unsigned int* hcnt = hist + FO_MAXC * FO_BINS;
+
+  // ---- initialise the tree: samples with non-zero weight in ascending order (Splitter.init) ----
+  __shared__ int base_s;
+  if (tid == 0) base_s = 0;
+  for (int i = tid; i < d; i += FO_THREADS) features[i] = i;
+  __syncthreads();
+  unsigned long long my_sums[FO_MAXC];
+  for (int c = 0; c < FO_MAXC; ++c) my_sums[c] = 0;
+  for (int64_t i0 = 0; i0 < n; i0 += FO_THREADS) {
+    const int64_t i = i0 + tid;
+    unsigned int w = 0, yc = 0;
+    if (i < n) { w = cnt[i]; yc = (unsigned)P.ycls[i]; }
+    const int keep = w != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[wid][0] = __popc(bal);
+    __syncthreads();
+    int off = 0, tot = 0;
+    for (int k = 0; k < FO_THREADS / 32; ++k) { if (k < wid) off += wsum[k][0]; tot += wsum[k][0]; }
+    const int b = base_s;
+    if (keep) {
+      samp[b + off + __popc(bal & ((1u << lane) - 1))] = make_uint2((unsigned)i, (w << 8) | yc);
+      for (int c = 0; c < C; ++c) if ((int)yc == c) my_sums[c] += w;
+    }
+    __syncthreads();
+    if (tid == 0) base_s = b + tot;
+    __syncthreads();
+  }
+  const int n_nz = base_s;
+  // reduce the class sums over the block (integers: exact)
+  __shared__ unsigned long long red[FO_MAXC];
+  if (tid < FO_MAXC) red[tid] = 0;
+  __syncthreads();
+  for (int c = 0; c < C; ++c) {
+    unsigned long long v = my_sums[c];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) atomicAdd(&red[c], v);
+  }
+  __syncthreads();
+  double w_samples = 0.0;
+  for (int c = 0; c < C; ++c) w_samples += (double)red[c];     // weighted_n_samples (integer valued)
+
+  uint32_t rstate = P.rand_state[slot];
+  int sp = 0;           // stack pointer
+  int node_count = 0, max_depth_seen = -1, status = 0;
+  if (tid == 0) {
+    FoRecord r;
+    r.start = 0; r.end = n_nz; r.depth = 0; r.parent = -1; r.is_left = 0; r.n_const = 0;
+    r.impurity = INFINITY;
+    for (int c = 0; c < FO_MAXC; ++c) r.sums[c] = c < C ? red[c] : 0;
+    stack[0] = r;
+  }
+  sp = 1;
+  bool first = true;
+  __syncthreads();
+
+  while (sp > 0 && status == 0) {
+    --sp;
+    if (tid == 0) rec = stack[sp];
+    __syncthreads();
+    const int start = rec.start, end = rec.end, depth = rec.depth;
+    const int n_node = end - start;
+    double w_node = 0.0;
+    for (int c = 0; c < C; ++c) w_node += (double)rec.sums[c];
+    double impurity = rec.impurity;
+    bool is_leaf = depth >= P.max_depth || n_node < P.min_samples_split || n_node < 2 * P.min_samples_leaf ||
+                   w_node < 2.0 * P.min_weight_leaf;
+    if (first) {   // root: node_impurity()  (SK/tree/_criterion.pyx:620-640)
+      double sq = 0.0;
+      for (int c = 0; c < C; ++c) { const double a = (double)rec.sums[c]; sq = __dadd_rn(sq, __dmul_rn(a, a)); }
+      impurity = __dsub_rn(1.0, __ddiv_rn(sq, __dmul_rn(w_node, w_node)));
+      first = false;
+    }
+    is_leaf = is_leaf || impurity <= FO_EPSILON;
+
+    // ------------------------------- node_split_best -------------------------------------
+    int best_feature = 0, best_pos = end, best_bin = -1, n_total_constants = rec.n_const;
+    double best_thr = 0.0, best_il = 0.0, best_ir = 0.0, best_improvement = 0.0;
+    int best_mgl = 0;
+    if (!is_leaf) {
+      const int n_known = rec.n_const;
+      int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0;
+      n_total_constants = n_known;
+      double best_proxy = -INFINITY;
+      for (;;) {
+        // --- thread 0: draw the next feature to evaluate (or stop) ---
+        if (tid == 0) {
+          int go = 0, fj = -1;
+          while (f_i > n_total_constants &&
+                 (n_visited < P.max_features || n_visited <= n_found + n_drawn)) {
+            n_visited += 1;
+            fj = fo_rand_int(n_drawn, f_i - n_found, &rstate);
+            if (fj < n_known) {   // a known constant: move it to the drawn-constants prefix
+              const int t = features[n_drawn]; features[n_drawn] = features[fj]; features[fj] = t;
+              n_drawn += 1;
+              continue;
+            }
+            fj += n_found;
+            go = 1;
+            break;
+          }
+          s_ctrl[0] = go; s_ctrl[1] = fj;
+        }
+        __syncthreads();
+        if (!s_ctrl[0]) break;
+        const int fj = s_ctrl[1];
+        const int f = features[fj];
+        // --- histogram of the node's samples over the feature's bins ---
+        for (int i = tid; i < FO_BINS * (FO_MAXC + 1); i += FO_THREADS) hist[i] = 0;
+        __syncthreads();
+        const uint8_t* xb = P.xbin + (size_t)f * n;
+        for (int i = start + tid; i < end; i += FO_THREADS) {
+          const uint2 sv = samp[i];
+          const unsigned b = xb[sv.x];
+          atomicAdd(&hcls[(sv.y & 0xFF) * FO_BINS + b], sv.y >> 8);
+          atomicAdd(&hcnt[b], 1u);
+        }
+        __syncthreads();
+        {  // presence bitmap
+          const unsigned bal = __ballot_sync(0xffffffffu, hcnt[tid] != 0);
+          if (lane == 0) present[wid] = bal;
+        }
+        __syncthreads();
+        // --- thread 0: scan the present bins in ascending order = the sorted distinct values ---
+        if (tid == 0) {
+          const float* bv = P.binval + (size_t)f * FO_BINS;
+          int first_bin = -1, last_bin = -1;
+          for (int wv = 0; wv < FO_BINS / 32; ++wv) if (present[wv]) { first_bin = wv * 32 + __ffs(present[wv]) - 1; break; }
+          for (int wv = FO_BINS / 32 - 1; wv >= 0; --wv) if (present[wv]) { last_bin = wv * 32 + 31 - __clz(present[wv]); break; }
+          if (bv[last_bin] <= bv[first_bin] + FEATURE_THRESHOLD) {
+            // constant in this node
+            const int t = features[fj]; features[fj] = features[n_total_constants]; features[n_total_constants] = t;
+            n_found += 1;
+            n_total_constants += 1;
+          } else {
+            f_i -= 1;
+            { const int t = features[f_i]; features[f_i] = features[fj]; features[fj] = t; }
+            unsigned long long sl[FO_MAXC];
+            for (int c = 0; c < C; ++c) sl[c] = 0;
+            int p = start;            // number of samples consumed + start
+            int prev_bin = -1;
+            for (int wv = 0; wv < FO_BINS / 32; ++wv) {
+              unsigned m = present[wv];
+              while (m) {
+                const int b = wv * 32 + __ffs(m) - 1;
+                m &= m - 1;
+                if (prev_bin >= 0 && bv[b] > bv[prev_bin] + FEATURE_THRESHOLD) {
+                  // candidate split between prev_bin (p_prev = p - 1) and b (position p)
+                  const int n_left = p - start, n_right = end - p;
+                  if (n_left >= P.min_samples_leaf && n_right >= P.min_samples_leaf) {
+                    double wl = 0.0;
+                    for (int c = 0; c < C; ++c) wl += (double)sl[c];
+                    const double wr = w_node - wl;
+                    if (!(wl < P.min_weight_leaf || wr < P.min_weight_leaf)) {
+                      double il, ir;
+                      fo_children_impurity(sl, rec.sums, C, wl, wr, &il, &ir);
+                      const double proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
+                      if (proxy > best_proxy) {
+                        best_proxy = proxy;
+                        best_feature = f; best_pos = p; best_bin = prev_bin;
+                        best_thr = (double)bv[prev_bin] / 2.0 + (double)bv[b] / 2.0;
+                        best_mgl = n_left > n_right;
+                        best_il = il; best_ir = ir;
+                        for (int c = 0; c < C; ++c) best_sl[c] = sl[c];
+                      }
+                    }
+                  }
+                }
+                for (int c = 0; c < C; ++c) sl[c] += hcls[c * FO_BINS + b];
+                p += (int)hcnt[b];
+                prev_bin = b;
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // restore / record the constant-feature invariants (end of node_split_best)
+      if (tid == 0) {
+        for (int i = 0; i < n_known; ++i) features[i] = constant_features[i];
+        for (int i = 0; i < n_found; ++i) constant_features[n_known + i] = features[n_known + i];
+        s_ctrl[2] = best_pos; s_ctrl[3] = best_feature; s_ctrl[4] = best_bin; s_ctrl[5] = n_total_constants;
+        s_ctrl[6] = best_mgl;
+        s_dbl[0] = best_thr; s_dbl[1] = best_il; s_dbl[2] = best_ir;
+        if (best_pos < end) {
+          double wl = 0.0;
+          for (int c = 0; c < C; ++c) wl += (double)best_sl[c];
+          const double wr = w_node - wl;
+          // impurity_improvement (SK/tree/_criterion.pyx:163-190)
+          const double a = __dmul_rn(__ddiv_rn(wr, w_node), best_ir);
+          const double b = __dmul_rn(__ddiv_rn(wl, w_node), best_il);
+          s_dbl[3] = __dmul_rn(__ddiv_rn(w_node, w_samples), __dsub_rn(__dsub_rn(impurity, a), b));
+        } else {
+          s_dbl[3] = 0.0;
+        }
+      }
+      __syncthreads();
+      best_pos = s_ctrl[2]; best_feature = s_ctrl[3]; best_bin = s_ctrl[4]; n_total_constants = s_ctrl[5];
+      best_mgl = s_ctrl[6];
+      best_thr = s_dbl[0]; best_il = s_dbl[1]; best_ir = s_dbl[2]; best_improvement = s_dbl[3];
+      is_leaf = is_leaf || best_pos >= end || (best_improvement + FO_EPSILON < P.min_impurity_decrease);
+
+      if (best_pos < end) {
+        // --- partition_samples_final: stable partition (keeps sample indices ascending) ---
+        const uint8_t* xb = P.xbin + (size_t)best_feature * n;
+        __shared__ int loff, roff;
+        if (tid == 0) { loff = start; roff = best_pos; }
+        __syncthreads();
+        for (int i0 = start; i0 < end; i0 += FO_THREADS) {
+          const int i = i0 + tid;
+          uint2 sv = make_uint2(0, 0);
+          int isl = 0, isr = 0;
+          if (i < end) { sv = samp[i]; isl = xb[sv.x] <= (unsigned)best_bin; isr = !isl; }
+          const unsigned bl = __ballot_sync(0xffffffffu, isl), br = __ballot_sync(0xffffffffu, isr);
+          if (lane == 0) { wsum[wid][0] = __popc(bl); wsum[wid][1] = __popc(br); }
+          __syncthreads();
+          int lo = 0, ro = 0, lt = 0, rt = 0;
+          for (int k = 0; k < FO_THREADS / 32; ++k) {
+            if (k < wid) { lo += wsum[k][0]; ro += wsum[k][1]; }
+            lt += wsum[k][0]; rt += wsum[k][1];
+          }
+          const int lb = loff, rb = roff;
+          if (isl) tmp[lb + lo + __popc(bl & ((1u << lane) - 1))] = sv;
+          if (isr) tmp[rb + ro + __popc(br & ((1u << lane) - 1))] = sv;
+          __syncthreads();
+          if (tid == 0) { loff = lb + lt; roff = rb + rt; }
+          __syncthreads();
+        }
+        for (int i = start + tid; i < end; i += FO_THREADS) samp[i] = tmp[i];
+        __syncthreads();
+      }
+    }
+
+    // ------------------------------- _add_node + node_value --------------------------------
+    const int node_id = node_count;
+    if (node_id >= P.node_cap) { status = 1; break; }
+    if (tid == 0) {
+      if (rec.parent >= 0) {
+        if (rec.is_left) P.o_left[nb + rec.parent] = node_id; else P.o_right[nb + rec.parent] = node_id;
+      }
+      P.o_imp[nb + node_id] = impurity;
+      P.o_nsamp[nb + node_id] = n_node;
+      P.o_wn[nb + node_id] = w_node;
+      if (is_leaf) {
+        P.o_left[nb + node_id] = -1; P.o_right[nb + node_id] = -1;
+        P.o_feature[nb + node_id] = -2; P.o_thr[nb + node_id] = -2.0; P.o_mgl[nb + node_id] = 0;
+      } else {
+        P.o_feature[nb + node_id] = best_feature; P.o_thr[nb + node_id] = best_thr;
+        P.o_mgl[nb + node_id] = (uint8_t)best_mgl;
+      }
+      for (int c = 0; c < C; ++c)
+        P.o_val[(nb + node_id) * C + c] = __ddiv_rn((double)rec.sums[c], w_node);   // class fractions
+    }
+    node_count += 1;
+    if (!is_leaf) {
+      if (sp + 2 > P.stack_cap) { status = 2; break; }
+      if (tid == 0) {
+        FoRecord r;
+        r.depth = depth + 1; r.parent = node_id; r.n_const = n_total_constants;
+        // right child first, then left (popped first)
+        r.start = best_pos; r.end = end; r.is_left = 0; r.impurity = best_ir;
+        for (int c = 0; c < FO_MAXC; ++c) r.sums[c] = c < C ? rec.sums[c] - best_sl[c] : 0;
+        stack[sp] = r;
+        r.start = start; r.end = best_pos; r.is_left = 1; r.impurity = best_il;
+        for (int c = 0; c < FO_MAXC; ++c) r.sums[c] = c < C ? best_sl[c] : 0;
+        stack[sp + 1] = r;
+      }
+      sp += 2;
+    }
+    if (depth > max_depth_seen) max_depth_seen = depth;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    P.o_count[slot] = node_count;
+    P.o_maxdepth[slot] = max_depth_seen;
+    P.o_status[slot] = status;
+  }
+}
+
+// ------------------------------------ binning ---------------------------------------------
+// column f of X -> contiguous buffer
+__global__ void fo_extract_col(const float* __restrict__ X, int64_t n, int ldx, int f, float* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = X[i * ldx + f];
+}
+// mark the first element of each run of equal values in a sorted column
+__global__ void fo_mark_unique(const float* __restrict__ sorted, int64_t n, int* __restrict__ n_unique,
+                               float* __restrict__ vals /*[256]*/) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0 || sorted[i] != sorted[i - 1]) {
+    int k = atomicAdd(n_unique, 1);
+    if (k < FO_BINS) vals[k] = sorted[i];    // unordered; sorted afterwards on the host (<= 256 values)
+  }
+}
+__global__ void fo_bin_col(const float* __restrict__ col, int64_t n, const float* __restrict__ vals, int nv,
+                           uint8_t* __restrict__ out) {
+  __shared__ float sv[FO_BINS];
+  if (threadIdx.x < FO_BINS) sv[threadIdx.x] = threadIdx.x < nv ? vals[threadIdx.x] : INFINITY;
+  __syncthreads();
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = col[i];
+  int lo = 0, hi = nv - 1;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (sv[mid] < x) lo = mid + 1; else hi = mid; }
+  out[i] = (uint8_t)lo;
+}
+
+}  // namespace skd
+
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/sort.h>
+
+namespace skd {
+
+void forest_free(Ctx* c) {
+  ForestData& f = c->forest;
+  if (f.xbin) cudaFree(f.xbin);
+  if (f.binval) cudaFree(f.binval);
+  f = ForestData();
+}
+
+// Bin codes of the staged X (feature-major uint8) + the distinct values per feature.
+int forest_prepare(Ctx* c) {
+  ForestData& fd = c->forest;
+  if (fd.valid) return 0;
+  forest_free(c);
+  const int64_t n = c->n;
+  const int d = (int)c->d, ldx = (int)c->ldx;
+  SKD_CUDA(c, cudaMalloc((void**)&fd.xbin, (size_t)d * n));
+  SKD_CUDA(c, cudaMalloc((void**)&fd.binval, (size_t)d * FO_BINS * sizeof(float)));
+  float *col, *srt, *dvals; int* dn;
+  Scratch sx(c);
+  SKD_CUDA(c, sx.alloc(&col, (size_t)n));
+  SKD_CUDA(c, sx.alloc(&srt, (size_t)n));
+  SKD_CUDA(c, sx.alloc(&dvals, (size_t)FO_BINS));
+  SKD_CUDA(c, sx.alloc(&dn, 1));
+  const unsigned g = (unsigned)((n + 255) / 256);
+  std::vector<float> hv(FO_BINS);
+  for (int f = 0; f < d; ++f) {
+    fo_extract_col<<<g, 256, 0, c->stream>>>(c->X, n, ldx, f, col);
+    SKD_CUDA(c, cudaMemcpyAsync(srt, col, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
+    thrust::sort(thrust::cuda::par.on(c->stream), thrust::device_pointer_cast(srt), thrust::device_pointer_cast(srt + n));
+    SKD_CUDA(c, cudaMemsetAsync(dn, 0, 4, c->stream));
+    fo_mark_unique<<<g, 256, 0, c->stream>>>(srt, n, dn, dvals);
+    int nu = 0;
+    SKD_CUDA(c, cudaMemcpyAsync(&nu, dn, 4, cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(hv.data(), dvals, FO_BINS * 4, cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (nu > FO_BINS) {
+      char b[200];
+      snprintf(b, sizeof(b), "forest: feature %d has %d distinct values; the histogram splitter needs <= %d "
+               "(continuous features need the sort-based splitter, not built yet)", f, nu, FO_BINS);
+      return fail(c, b);
+    }
+    for (int i = 0; i < nu; ++i)
+      if (hv[i] != hv[i]) return fail(c, "forest: NaN feature values are not supported on the device path");
+    std::sort(hv.begin(), hv.begin() + nu);
+    for (int i = nu; i < FO_BINS; ++i) hv[i] = INFINITY;
+    SKD_CUDA(c, cudaMemcpyAsync(dvals, hv.data(), FO_BINS * 4, cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(fd.binval + (size_t)f * FO_BINS, hv.data(), FO_BINS * 4, cudaMemcpyHostToDevice, c->stream));
+    fo_bin_col<<<g, 256, 0, c->stream>>>(col, n, dvals, nu, fd.xbin + (size_t)f * n);
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->launches += 3;
+  }
+  SKD_CUDA(c, cudaGetLastError());
+  fd.valid = true;
+  return 0;
+}
+
+// Build `n_trees` trees.  counts: [n_trees][n] uint8 host array of bootstrap multiplicities,
+// rand_states: [n_trees] splitter seeds.  Results are delivered tree by tree through `sink`.
+int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_states, int n_classes,
+               int max_features, int max_depth, int min_samples_split, int min_samples_leaf,
+               double min_weight_leaf, double min_impurity_decrease, ForestSink sink, void* sink_arg) {
+  if (forest_prepare(c)) return 1;
+  if (n_classes < 1 || n_classes > FO_MAXC) return fail(c, "forest: device path supports up to 16 classes");
+  if (!c->ycls) return fail(c, "forest: stage labels first");
+  const int64_t n = c->n;
+  const int d = (int)c->d;
+  if ((size_t)2 * d * sizeof(int) > 40 * 1024) return fail(c, "forest: too many features for the shared-memory feature permutation");
+  // slots: concurrent trees per wave, bounded by memory (worst case 2*n nodes per tree)
+  const int64_t node_cap = 2 * n;
+  const size_t per_slot = (size_t)n * 16 + (size_t)node_cap * (4 * 3 + 1 + 8 * 3 + 8 * n_classes) + 4096 * sizeof(FoRecord);
+  size_t free_b = 0, total_b = 0;
+  SKD_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  int slots = 2 * c->sm_count;
+  if ((size_t)slots * per_slot > free_b / 2) slots = (int)(free_b / 2 / per_slot);
+  if (slots < 1) return fail(c, "forest: not enough device memory for one tree");
+  if (slots > n_trees) slots = n_trees;
+  const int stack_cap = 4096;
+  Scratch sx(c);
+  FoParams P;
+  memset(&P, 0, sizeof(P));
+  uint8_t* dcounts; uint32_t* drs;
+  SKD_CUDA(c, sx.alloc(&dcounts, (size_t)slots * n));
+  SKD_CUDA(c, sx.alloc(&drs, (size_t)slots));
+  SKD_CUDA(c, sx.alloc(&P.samp, (size_t)slots * n));
+  SKD_CUDA(c, sx.alloc(&P.samp_tmp, (size_t)slots * n));
+  SKD_CUDA(c, sx.alloc(&P.stack, (size_t)slots * stack_cap));
+  SKD_CUDA(c, sx.alloc(&P.o_left, (size_t)slots * node_cap));
+  SKD_CUDA(c, sx.alloc(&P.o_right, (size_t)slots * node_cap));
+  SKD_CUDA(c, sx.alloc(&P.o_feature, (size_t)slots * node_cap));
+  SKD_CUDA(c, sx.alloc(&P.o_nsamp, (size_t)slots * node_cap));
+  SKD_CUDA(c, sx.alloc(&P.o_mgl, (size_t)slots * node_cap));
+  SKD_CUDA(c, sx.alloc(&P.o_thr, (size_t)slots * node_cap));
+  SKD_CUDA(c, sx.alloc(&P.o_imp, (size_t)slots * node_cap));
+  SKD_CUDA(c, sx.alloc(&P.o_wn, (size_t)slots * node_cap));
+  SKD_CUDA(c, sx.alloc(&P.o_val, (size_t)slots * node_cap * n_classes));
+  SKD_CUDA(c, sx.alloc(&P.o_count, (size_t)slots));
+  SKD_CUDA(c, sx.alloc(&P.o_maxdepth, (size_t)slots));
+  SKD_CUDA(c, sx.alloc(&P.o_status, (size_t)slots));
+  P.xbin = c->forest.xbin; P.binval = c->forest.binval; P.ycls = c->ycls;
+  P.n = n; P.d = d; P.n_classes = n_classes;
+  P.max_features = max_features; P.max_depth = max_depth; P.min_samples_split = min_samples_split;
+  P.min_samples_leaf = min_samples_leaf; P.min_weight_leaf = min_weight_leaf;
+  P.min_impurity_decrease = min_impurity_decrease;
+  P.counts = dcounts; P.rand_state = drs; P.stack_cap = stack_cap; P.node_cap = node_cap;
+  const size_t smem = (size_t)2 * d * sizeof(int);
+  std::vector<int32_t> hcount(slots), hdepth(slots), hstatus(slots);
+  SkdTreeView view;
+  std::vector<int32_t> hl, hr, hf, hn; std::vector<uint8_t> hm; std::vector<double> ht, hi, hw, hv;
+  for (int t0 = 0; t0 < n_trees; t0 += slots) {
+    const int nt = std::min(slots, n_trees - t0);
+    SKD_CUDA(c, cudaMemcpyAsync(dcounts, counts + (size_t)t0 * n, (size_t)nt * n, cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(drs, rand_states + t0, (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
+    c->h2d += (int64_t)nt * n;
+    P.n_trees = nt;
+    forest_build_kernel<<<nt, FO_THREADS, smem, c->stream>>>(P);
+    c->launches += 1;
+    SKD_CUDA(c, cudaGetLastError());
+    SKD_CUDA(c, cudaMemcpyAsync(hcount.data(), P.o_count, nt * 4, cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(hdepth.data(), P.o_maxdepth, nt * 4, cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(hstatus.data(), P.o_status, nt * 4, cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < nt; ++s) {
+      if (hstatus[s] != 0) return fail(c, hstatus[s] == 1 ? "forest: node capacity exceeded" : "forest: builder stack capacity exceeded");
+      const int m = hcount[s];
+      hl.resize(m); hr.resize(m); hf.resize(m); hn.resize(m); hm.resize(m); ht.resize(m); hi.resize(m); hw.resize(m);
+      hv.resize((size_t)m * n_classes);
+      const size_t o = (size_t)s * node_cap;
+      SKD_CUDA(c, cudaMemcpyAsync(hl.data(), P.o_left + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(hr.data(), P.o_right + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(hf.data(), P.o_feature + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(hn.data(), P.o_nsamp + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(hm.data(), P.o_mgl + o, m, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(ht.data(), P.o_thr + o, m * 8, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(hi.data(), P.o_imp + o, m * 8, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(hw.data(), P.o_wn + o, m * 8, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(hv.data(), P.o_val + o * n_classes, (size_t)m * n_classes * 8, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+      c->d2h += (int64_t)m * (4 * 4 + 1 + 8 * 3 + 8 * n_classes);
+      view.node_count = m; view.max_depth = hdepth[s]; view.n_classes = n_classes;
+      view.left = hl.data(); view.right = hr.data(); view.feature = hf.data(); view.n_node_samples = hn.data();
+      view.missing_go_to_left = hm.data(); view.threshold = ht.data(); view.impurity = hi.data();
+      view.weighted_n_node_samples = hw.data(); view.value = hv.data();
+      sink(sink_arg, t0 + s, &view);
+    }
+  }
+  return 0;
+}
+
+}  // namespace skd

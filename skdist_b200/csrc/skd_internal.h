@@ -30,6 +30,22 @@ struct TcData {
   CUtensorMap map_xh, map_xl;
 };
 
+// binned copy of the staged X for the forest builder (forest.cu)
+struct ForestData {
+  uint8_t* xbin = nullptr;   // [d][n] bin code of every value, feature-major
+  float* binval = nullptr;   // [d][256] distinct values of each feature, ascending (+inf padded)
+  bool valid = false;
+};
+
+// host view of one finished tree (arrays of node_count entries; value is [node_count][n_classes])
+struct SkdTreeView {
+  int32_t node_count, max_depth, n_classes;
+  const int32_t *left, *right, *feature, *n_node_samples;
+  const uint8_t* missing_go_to_left;
+  const double *threshold, *impurity, *weighted_n_node_samples, *value;
+};
+typedef void (*ForestSink)(void* arg, int tree_index, const SkdTreeView* view);
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -45,6 +61,7 @@ struct Ctx {
   int32_t n_folds = 0;
   std::vector<int64_t> fold_count;  // rows per fold id
   TcData tc;
+  ForestData forest;
   // counters
   int64_t launches = 0, h2d = 0, d2h = 0;
   // optional per-evaluation timing (bench.py roofline): CUDA events on `stream` around every
@@ -149,6 +166,10 @@ int sgd_fit_batch(Ctx* c, int B, const int32_t* col_pos, int loss, double alpha,
                   int max_iter, double tol, int shuffle, uint32_t seed, int lr_type, double eta0,
                   double power_t, double optimal_init, int n_iter_no_change, float* coef_out,
                   double* intercept_out, int32_t* n_iter_out, double* t_out, int32_t* status_out);
+void forest_free(Ctx* c);
+int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_states, int n_classes,
+               int max_features, int max_depth, int min_samples_split, int min_samples_leaf,
+               double min_weight_leaf, double min_impurity_decrease, ForestSink sink, void* sink_arg);
 int predict_device(Ctx* c, const float* dX, int64_t m, int ldx, int d, int B, const float* dW, float* dout);
 int ridge_fit_batch(Ctx* c, int B, const double* alpha, const int32_t* hold, int fit_intercept,
                     float* coef_out, int32_t* status_out);

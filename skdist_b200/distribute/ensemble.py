@@ -1,0 +1,207 @@
+"""Distributed tree ensembles on B200s.
+
+Drop-in for /root/reference/skdist/distribute/ensemble.py (class name, constructor signature with
+``sc`` FIRST, fitted attributes).  The reference fans `_build_trees` (ensemble.py:68-109) out over
+Spark, one task per tree seed (ensemble.py:278-322).  Here every tree is built by one persistent
+CTA of `forest_build_kernel` (csrc/forest.cu); the host draws exactly the random numbers the
+reference draws (per-tree seeds ensemble.py:278, bootstrap indices ensemble.py:51-55, splitter seed
+SK/tree/_splitter.pyx:155) and wraps the returned node arrays into genuine scikit-learn
+`DecisionTreeClassifier` objects, so `estimators_`, `predict`, `predict_proba` behave as before and
+the tree structure is bit-identical under a fixed `random_state`.
+"""
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+from sklearn.ensemble import RandomForestClassifier
+from sklearn.tree import DecisionTreeClassifier
+from sklearn.tree._tree import NODE_DTYPE, Tree
+from sklearn.utils import check_random_state
+
+from .. import parallel
+from ..engine import get_engine
+from .base import _parse_partitions, _ScParamMixin
+from .validation import _check_estimator
+
+__all__ = ["DistRandomForestClassifier"]
+
+MAX_RAND_SEED = np.iinfo(np.int32).max     # ref ensemble.py:38
+RAND_R_MAX = 2147483647                    # SK/tree/_utils.pxd
+
+
+def _tree_inputs(state, n_samples, bootstrap):
+    """What `_build_trees` (ref ensemble.py:68-109) derives from one tree seed: the bootstrap
+    multiplicities used as sample_weight and the splitter's xorshift seed."""
+    if bootstrap:
+        indices = check_random_state(state).randint(0, n_samples, n_samples)      # ref :51-55
+        counts = np.bincount(indices, minlength=n_samples)
+        if counts.max() > 255:
+            raise NotImplementedError("a bootstrap multiplicity above 255 does not fit the device format")
+        counts = counts.astype(np.uint8)
+    else:
+        counts = np.ones(n_samples, np.uint8)
+    rand_r_state = check_random_state(state).randint(0, RAND_R_MAX)                 # SK/tree/_splitter.pyx:155
+    return counts, np.uint32(rand_r_state)
+
+
+def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, max_features_):
+    """A fitted DecisionTreeClassifier holding the device-built tree (same attributes as
+    SK/tree/_classes.py:_fit leaves behind)."""
+    m = arrays["left"].shape[0]
+    nodes = np.zeros(m, dtype=NODE_DTYPE)
+    nodes["left_child"] = arrays["left"]
+    nodes["right_child"] = arrays["right"]
+    nodes["feature"] = arrays["feature"]
+    nodes["threshold"] = arrays["threshold"]
+    nodes["impurity"] = arrays["impurity"]
+    nodes["n_node_samples"] = arrays["n_node_samples"]
+    nodes["weighted_n_node_samples"] = arrays["weighted_n_node_samples"]
+    nodes["missing_go_to_left"] = arrays["missing_go_to_left"]
+    t = Tree(n_features, np.array([n_classes], dtype=np.intp), 1)
+    t.__setstate__({"max_depth": int(arrays["max_depth"]), "node_count": m, "nodes": nodes,
+                    "values": np.ascontiguousarray(arrays["value"].reshape(m, 1, n_classes))})
+    est = DecisionTreeClassifier(**template_params)
+    est.set_params(random_state=int(state))
+    est.n_features_in_ = n_features
+    est.n_outputs_ = 1
+    est.classes_ = np.arange(n_classes, dtype=np.float64)
+    est.n_classes_ = n_classes
+    est.max_features_ = max_features_
+    est.tree_ = t
+    return est
+
+
+class DistRandomForestClassifier(_ScParamMixin, RandomForestClassifier):
+    """Same as sklearn `RandomForestClassifier` with every tree built on a B200.
+    Constructor mirrors ref ensemble.py:378-422 (``sc`` is the FIRST positional argument)."""
+
+    def __init__(self, sc=None, partitions="auto", n_estimators=100, criterion="gini", max_depth=None,
+                 min_samples_split=2, min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
+                 max_leaf_nodes=None, min_impurity_decrease=0.0, min_impurity_split=None, bootstrap=True,
+                 oob_score=False, n_jobs=None, random_state=None, verbose=0, warm_start=False,
+                 class_weight=None):
+        self.sc = sc
+        self.partitions = partitions
+        self.n_estimators = n_estimators
+        self.criterion = criterion
+        self.max_depth = max_depth
+        self.min_samples_split = min_samples_split
+        self.min_samples_leaf = min_samples_leaf
+        self.min_weight_fraction_leaf = min_weight_fraction_leaf
+        self.max_features = max_features
+        self.max_leaf_nodes = max_leaf_nodes
+        self.min_impurity_decrease = min_impurity_decrease
+        self.min_impurity_split = min_impurity_split
+        self.bootstrap = bootstrap
+        self.oob_score = oob_score
+        self.n_jobs = n_jobs
+        self.random_state = random_state
+        self.verbose = verbose
+        self.warm_start = warm_start
+        self.class_weight = class_weight
+        # attributes newer scikit-learn forests expect on the instance
+        self.ccp_alpha = 0.0
+        self.max_samples = None
+        self.monotonic_cst = None
+        self.estimator = DecisionTreeClassifier()
+        self.estimator_params = ("criterion", "max_depth", "min_samples_split", "min_samples_leaf",
+                                 "min_weight_fraction_leaf", "max_features", "max_leaf_nodes",
+                                 "min_impurity_decrease", "random_state", "ccp_alpha", "monotonic_cst")
+
+    @classmethod
+    def _get_param_names(cls):
+        return sorted(["sc", "partitions", "n_estimators", "criterion", "max_depth", "min_samples_split",
+                       "min_samples_leaf", "min_weight_fraction_leaf", "max_features", "max_leaf_nodes",
+                       "min_impurity_decrease", "min_impurity_split", "bootstrap", "oob_score", "n_jobs",
+                       "random_state", "verbose", "warm_start", "class_weight"])
+
+    def _resolved(self, n_features):
+        bad = []
+        if self.criterion != "gini":
+            bad.append("criterion=%r (only 'gini')" % self.criterion)
+        if self.max_leaf_nodes is not None:
+            bad.append("max_leaf_nodes (best-first builder)")
+        if self.class_weight is not None:
+            bad.append("class_weight")
+        if self.warm_start:
+            bad.append("warm_start")
+        if self.min_impurity_split is not None:
+            bad.append("min_impurity_split")
+        if bad:
+            raise NotImplementedError("forest configuration without a device path: " + ", ".join(bad))
+        mf = self.max_features
+        if mf in ("auto", "sqrt"):                       # 'auto' meant sqrt for classifiers in the reference's era
+            mf_i = max(1, int(np.sqrt(n_features)))
+        elif mf == "log2":
+            mf_i = max(1, int(np.log2(n_features)))
+        elif mf is None:
+            mf_i = n_features
+        elif isinstance(mf, (int, np.integer)):
+            mf_i = int(mf)
+        else:
+            mf_i = max(1, int(mf * n_features))
+        max_depth = np.iinfo(np.int32).max if self.max_depth is None else int(self.max_depth)
+        mss = self.min_samples_split
+        msl = self.min_samples_leaf
+        return mf_i, max_depth, mss, msl
+
+    def fit(self, X, y, sample_weight=None):
+        """Build the forest (ref ensemble.py:177-336)."""
+        if sample_weight is not None:
+            raise NotImplementedError("sample_weight is not supported on the device path")
+        _check_estimator(self, verbose=self.verbose)
+        X = np.ascontiguousarray(X, dtype=np.float32)                 # ref :200 (check_array dtype=float32)
+        y = np.asarray(y)
+        if y.ndim != 1:
+            raise NotImplementedError("multi-output forests have no device path")
+        n, d = X.shape
+        self.n_features_in_ = d
+        self.n_outputs_ = 1
+        self.classes_, y_enc = np.unique(y, return_inverse=True)       # ref :229 (_validate_y_class_weight)
+        self.n_classes_ = len(self.classes_)
+        mf_i, max_depth, mss, msl = self._resolved(d)
+        if not isinstance(mss, (int, np.integer)):
+            mss = max(2, int(np.ceil(mss * n)))
+        if not isinstance(msl, (int, np.integer)):
+            msl = max(1, int(np.ceil(msl * n)))
+        mss = max(int(mss), 2 * int(msl))
+        min_weight_leaf = self.min_weight_fraction_leaf * n
+        random_state = check_random_state(self.random_state)
+        states = list(random_state.randint(MAX_RAND_SEED, size=self.n_estimators))   # ref :278
+        _parse_partitions(self.partitions, self.n_estimators)
+
+        rank, world, _ = parallel.dist_info()
+        eng = get_engine()
+        eng.stage_x(X)
+        eng.stage_labels(y_enc.astype(np.int32))
+        eng.stage_folds(None, 0)
+        mine = parallel.shard_indices(self.n_estimators, rank, world)
+        my_states = [states[i] for i in mine]
+        with ThreadPoolExecutor(max_workers=16) as ex:
+            inputs = list(ex.map(lambda s: _tree_inputs(s, n, self.bootstrap), my_states))
+        counts = np.stack([c for c, _ in inputs]) if inputs else np.zeros((0, n), np.uint8)
+        rs = np.array([r for _, r in inputs], dtype=np.uint32)
+        arrays = eng.forest_fit(counts, rs, self.n_classes_, mf_i, max_depth, int(mss), int(msl),
+                                float(min_weight_leaf), float(self.min_impurity_decrease)) if len(mine) else []
+        tmpl = dict(criterion=self.criterion, max_depth=self.max_depth, min_samples_split=self.min_samples_split,
+                    min_samples_leaf=self.min_samples_leaf, min_weight_fraction_leaf=self.min_weight_fraction_leaf,
+                    max_features="sqrt" if self.max_features == "auto" else self.max_features,
+                    max_leaf_nodes=self.max_leaf_nodes, min_impurity_decrease=self.min_impurity_decrease)
+        local = [_make_sklearn_tree(tmpl, s, a, d, self.n_classes_, mf_i) for s, a in zip(my_states, arrays)]
+        if world > 1:
+            import torch.distributed as dist
+            gathered = [None] * world
+            dist.all_gather_object(gathered, local)
+            ests = [None] * self.n_estimators
+            for r in range(world):
+                for i, e in zip(parallel.shard_indices(self.n_estimators, r, world), gathered[r]):
+                    ests[i] = e
+        else:
+            ests = local
+        self.estimators_ = ests
+        self.estimator_ = DecisionTreeClassifier()
+        del self.sc                                                     # ref :335
+        return self
+
+    def _set_oob_score(self, X, y):
+        """The reference overrides this to a no-op (ref ensemble.py:338-340)."""
+        return

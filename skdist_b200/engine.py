@@ -187,6 +187,42 @@ class Engine:
                 "coef32": coef, "intercept": intercept, "n_iter": n_iter, "t": t, "status": status,
                 "gpu_seconds": secs.value}
 
+    def forest_fit(self, sample_counts, rand_states, n_classes, max_features, max_depth, min_samples_split,
+                   min_samples_leaf, min_weight_leaf, min_impurity_decrease):
+        """Build len(rand_states) classifier trees.  sample_counts [n_trees, n] uint8 (bootstrap
+        multiplicities = the reference's sample_weight), rand_states [n_trees] uint32 splitter seeds.
+        Returns a list of dicts with the sklearn Tree arrays of every tree."""
+        counts = np.ascontiguousarray(sample_counts, dtype=np.uint8)
+        rs = np.ascontiguousarray(rand_states, dtype=np.uint32)
+        T = rs.shape[0]
+        assert counts.shape == (T, self.n)
+        h = ctypes.c_void_p()
+        secs = ctypes.c_double(0.0)
+        check(self._lib.skd_forest_fit(self._h, T, ptr(counts), ptr(rs), int(n_classes), int(max_features),
+                                       int(max_depth), int(min_samples_split), int(min_samples_leaf),
+                                       float(min_weight_leaf), float(min_impurity_decrease),
+                                       ctypes.byref(h), ctypes.byref(secs)), self._h)
+        self.last_forest_seconds = secs.value
+        trees = []
+        try:
+            for t in range(T):
+                m, md = ctypes.c_int32(), ctypes.c_int32()
+                check(self._lib.skd_forest_tree_size(h, t, ctypes.byref(m), ctypes.byref(md)))
+                m = m.value
+                a = {"left": np.empty(m, np.int32), "right": np.empty(m, np.int32), "feature": np.empty(m, np.int32),
+                     "threshold": np.empty(m, np.float64), "impurity": np.empty(m, np.float64),
+                     "n_node_samples": np.empty(m, np.int32), "weighted_n_node_samples": np.empty(m, np.float64),
+                     "missing_go_to_left": np.empty(m, np.uint8), "value": np.empty((m, n_classes), np.float64)}
+                check(self._lib.skd_forest_tree_copy(h, t, ptr(a["left"]), ptr(a["right"]), ptr(a["feature"]),
+                                                     ptr(a["threshold"]), ptr(a["impurity"]), ptr(a["n_node_samples"]),
+                                                     ptr(a["weighted_n_node_samples"]), ptr(a["missing_go_to_left"]),
+                                                     ptr(a["value"])))
+                a["max_depth"] = md.value
+                trees.append(a)
+        finally:
+            self._lib.skd_forest_free(h)
+        return trees
+
     def ridge_fit_batch(self, alpha, col_fold, fit_intercept=True):
         alpha = np.ascontiguousarray(alpha, dtype=np.float64)
         B = alpha.shape[0]

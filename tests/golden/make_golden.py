@@ -100,13 +100,18 @@ def run_ridge_case(name, X, y, alphas, cv, ref_search):
         assert np.array_equal(ref["cv_results_"][k], ora["cv_results_"][k]), (name, k)
     d = X.shape[1]
     coef = np.zeros((len(cands), cv, d + 1), np.float32)
+    coef64 = np.zeros((len(cands), cv, d + 1))      # same fit in float64: the fp32 reference's own error bar
+    X64, y64 = X.astype(np.float64), y.astype(np.float64)
     for ci, p in enumerate(cands):
         for fi, (tr, te) in enumerate(KFold(cv).split(X)):
             m = Ridge(**p).fit(X[tr], y[tr])
             coef[ci, fi, :d] = m.coef_
             coef[ci, fi, d] = m.intercept_
+            m = Ridge(**p).fit(X64[tr], y64[tr])
+            coef64[ci, fi, :d] = m.coef_
+            coef64[ci, fi, d] = m.intercept_
     out = {k: ref["cv_results_"][k] for k in keys}
-    out.update(best_index=ref["best_index_"], coef=coef, alpha=np.asarray(alphas, float),
+    out.update(best_index=ref["best_index_"], coef=coef, coef64=coef64, alpha=np.asarray(alphas, float),
                refit_coef=np.r_[ref["best_estimator_"].coef_, ref["best_estimator_"].intercept_])
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
     print(name, "mean_test_score", ref["cv_results_"]["mean_test_score"])

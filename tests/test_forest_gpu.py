@@ -1,0 +1,59 @@
+"""DistRandomForestClassifier on the device vs scikit-learn's RandomForestClassifier, which the
+reference's `_build_trees` equals tree for tree (live check below)."""
+import numpy as np
+import pytest
+from sklearn.ensemble import RandomForestClassifier
+
+pytestmark = pytest.mark.gpu
+
+
+def lattice_data(n, d, seed, levels=256, n_classes=2):
+    rng = np.random.default_rng(seed)
+    Z = rng.standard_normal((n, d))
+    X = np.clip(np.floor((Z + 4.0) / 8.0 * levels), 0, levels - 1).astype(np.float32)
+    s = Z[:, 0] + 0.5 * Z[:, 1] * Z[:, 2] - 0.7 * Z[:, 3] + 0.8 * rng.standard_normal(n)
+    if n_classes == 2:
+        y = (s > 0).astype(np.int64)
+    else:
+        y = np.digitize(s, np.quantile(s, np.linspace(0, 1, n_classes + 1)[1:-1]))
+    return X, y
+
+
+def assert_same_forest(a, b):
+    assert len(a.estimators_) == len(b.estimators_)
+    for ta, tb in zip(a.estimators_, b.estimators_):
+        x, z = ta.tree_, tb.tree_
+        assert x.node_count == z.node_count and x.max_depth == z.max_depth
+        np.testing.assert_array_equal(x.children_left, z.children_left)
+        np.testing.assert_array_equal(x.children_right, z.children_right)
+        np.testing.assert_array_equal(x.feature, z.feature)
+        np.testing.assert_array_equal(x.threshold, z.threshold)
+        np.testing.assert_array_equal(x.n_node_samples, z.n_node_samples)
+        np.testing.assert_array_equal(x.weighted_n_node_samples, z.weighted_n_node_samples)
+        np.testing.assert_array_equal(x.impurity, z.impurity)
+        np.testing.assert_array_equal(x.value, z.value)
+
+
+@pytest.mark.parametrize("n,d,levels,k", [(3000, 16, 256, 2), (20000, 64, 256, 2), (5000, 10, 8, 4)])
+def test_forest_bit_identical_to_sklearn(n, d, levels, k):
+    from skdist.distribute.ensemble import DistRandomForestClassifier
+    X, y = lattice_data(n, d, seed=n % 13, levels=levels, n_classes=k)
+    ours = DistRandomForestClassifier(n_estimators=6, random_state=5).fit(X, y)
+    ref = RandomForestClassifier(n_estimators=6, random_state=5).fit(X, y)
+    assert_same_forest(ours, ref)
+    np.testing.assert_array_equal(ours.predict(X[:500]), ref.predict(X[:500]))
+    np.testing.assert_array_equal(ours.predict_proba(X[:200]), ref.predict_proba(X[:200]))
+
+
+def test_forest_hyperparameters_and_toy_case():
+    from skdist.distribute.ensemble import DistRandomForestClassifier
+    X, y = lattice_data(8000, 12, seed=3, levels=32)
+    kw = dict(n_estimators=4, random_state=1, max_depth=7, min_samples_leaf=3, min_samples_split=10,
+              max_features=5, bootstrap=False)
+    assert_same_forest(DistRandomForestClassifier(**kw).fit(X, y), RandomForestClassifier(**kw).fit(X, y))
+    # ref skdist/distribute/tests/test_ensemble.py:25-32
+    Xt = np.array([[0, 1, 0, 1], [0, 0, 0, 1], [1, 0, 1, 0]])
+    yt = np.array([0, 1, 0])
+    rfc = DistRandomForestClassifier(n_estimators=10, random_state=5).fit(Xt, yt)
+    assert np.allclose(rfc.predict(Xt), np.array([0, 1, 0]))
+    assert_same_forest(rfc, RandomForestClassifier(n_estimators=10, random_state=5).fit(Xt, yt))

@@ -1,0 +1,56 @@
+"""Host side of the forest path (no GPU): the random numbers drawn per tree and the wrapping of
+node arrays into scikit-learn trees; plus the live pin that the reference's own `_build_trees`
+yields scikit-learn's trees (so sklearn's RandomForestClassifier is a valid oracle)."""
+import numpy as np
+import pytest
+from sklearn.ensemble import RandomForestClassifier
+from sklearn.tree import DecisionTreeClassifier
+
+from oracle import refshim
+from skdist_b200.distribute.ensemble import MAX_RAND_SEED, _make_sklearn_tree, _tree_inputs
+
+
+def lattice(n, d, seed, levels=16):
+    rng = np.random.default_rng(seed)
+    X = rng.integers(0, levels, size=(n, d)).astype(np.float32)
+    y = ((X[:, 0] + X[:, 1] * 0.5 + rng.standard_normal(n) * 3) > levels * 0.75).astype(np.int64)
+    return X, y
+
+
+def test_tree_inputs_match_sklearn_sample_weights():
+    X, y = lattice(500, 5, 1)
+    rf = RandomForestClassifier(n_estimators=3, random_state=7).fit(X, y)
+    states = np.random.RandomState(7).randint(MAX_RAND_SEED, size=3)
+    for s, t in zip(states, rf.estimators_):
+        assert t.random_state == s
+        counts, rstate = _tree_inputs(s, 500, True)
+        # weighted_n_node_samples of the root = n; number of distinct rows = n_node_samples of the root
+        assert counts.sum() == 500 and (counts > 0).sum() == t.tree_.n_node_samples[0]
+
+
+def test_wrapping_roundtrip():
+    X, y = lattice(800, 6, 2)
+    rf = RandomForestClassifier(n_estimators=2, random_state=3).fit(X, y)
+    t = rf.estimators_[0].tree_
+    arrays = {"left": t.children_left.astype(np.int32), "right": t.children_right.astype(np.int32),
+              "feature": t.feature.astype(np.int32), "threshold": t.threshold.copy(), "impurity": t.impurity.copy(),
+              "n_node_samples": t.n_node_samples.astype(np.int32),
+              "weighted_n_node_samples": t.weighted_n_node_samples.copy(),
+              "missing_go_to_left": np.zeros(t.node_count, np.uint8), "value": t.value[:, 0, :].copy(),
+              "max_depth": t.max_depth}
+    est = _make_sklearn_tree({"max_features": "sqrt"}, 11, arrays, 6, 2, 2)
+    np.testing.assert_array_equal(est.predict_proba(X), rf.estimators_[0].predict_proba(X))
+    np.testing.assert_array_equal(est.apply(X), rf.estimators_[0].apply(X))
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not present")
+def test_reference_build_trees_equals_sklearn():
+    _, _, ref_ens = refshim.load()
+    X, y = lattice(1500, 8, 3)
+    states = np.random.RandomState(5).randint(MAX_RAND_SEED, size=3)
+    ref = RandomForestClassifier(n_estimators=3, random_state=5).fit(X, y)
+    for s, t in zip(states, ref.estimators_):
+        tr = ref_ens._build_trees(DecisionTreeClassifier(max_features="sqrt"), (), {}, X,
+                                  y.astype(np.float64)[:, None], None, s, 3, bootstrap=True)
+        np.testing.assert_array_equal(tr.tree_.threshold, t.tree_.threshold)
+        np.testing.assert_array_equal(tr.tree_.children_left, t.tree_.children_left)
