@@ -36,6 +36,18 @@ struct FoRecord {          // builder stack record (SK/tree/_tree.pyx StackRecor
   unsigned long long sums[FO_MAXC];
 };
 
+struct FoItem {            // one speculatively drawn feature + the simulation state right after its draw
+  int f, fj, nv, nd, fi, ulen;
+  uint32_t rs;
+};
+struct FoResult {          // best split of one feature in the current node
+  int is_const, pos, bin;
+  double proxy, thr, il, ir;
+  unsigned long long sl[FO_MAXC];
+};
+constexpr int FO_KB_MAX = 8;
+constexpr int FO_HIST_WORDS = 40 * FO_BINS;   // KB * (C + 1) * 256 <= this
+
 struct FoParams {
   const uint8_t* xbin;        // [d][n] bin codes, feature-major
   const float* binval;        // [d][256] distinct values ascending
@@ -101,15 +113,18 @@ forest_build_kernel(const FoParams P) {
   extern __shared__ int fo_sm[];
   int* features = fo_sm;                     // [d]
   int* constant_features = fo_sm + d;        // [d]
-  __shared__ unsigned int hist[FO_BINS * (FO_MAXC + 1)];   // [bin][C] class weights, then [bin] sample counts at offset C*256.. (layout below)
-  __shared__ unsigned int present[FO_BINS / 32];
+  __shared__ unsigned int hist[FO_HIST_WORDS];   // per batch item: [c][bin] class weights (c < C), then [bin] sample counts
+  __shared__ FoItem items[FO_KB_MAX];
+  __shared__ FoResult results[FO_KB_MAX];
+  __shared__ int s_sim_nd, s_sim_ulen;
+  __shared__ uint32_t s_sim_rs;
   __shared__ int wsum[FO_THREADS / 32][2];
   __shared__ int s_ctrl[8];
   __shared__ double s_dbl[4];
   __shared__ FoRecord rec;
   __shared__ unsigned long long best_sl[FO_MAXC];
-  unsigned int* hcls = hist;                 // hcls[c * 256 + bin]
-  unsigned int* hcnt = hist + FO_MAXC * FO_BINS;
+  int2* undo = reinterpret_cast<int2*>(fo_sm + 2 * d);      // [d + 16] swap log of the speculative draws
+  const int KB = min(FO_KB_MAX, FO_HIST_WORDS / ((C + 1) * FO_BINS));
 
   // ---- initialise the tree: samples with non-zero weight in ascending order (Splitter.init) ----
   __shared__ int base_s;
@@ -193,96 +208,177 @@ forest_build_kernel(const FoParams P) {
       int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0;
       n_total_constants = n_known;
       double best_proxy = -INFINITY;
+      // Features are drawn from one RNG stream and a draw depends on whether earlier draws of this
+      // node turned out constant, so the reference evaluates them one by one.  Here thread 0
+      // SPECULATES that none of the next <= KB evaluated features is constant, simulates the
+      // draws (logging every swap), all KB histograms are built in one pass over the node's
+      // samples, one warp per feature scans its histogram, and thread 0 then commits the results
+      // in draw order; the first feature found constant rolls the simulation back to that draw,
+      // takes the constant branch and the remaining speculative results are discarded.
       for (;;) {
-        // --- thread 0: draw the next feature to evaluate (or stop) ---
         if (tid == 0) {
-          int go = 0, fj = -1;
-          while (f_i > n_total_constants &&
-                 (n_visited < P.max_features || n_visited <= n_found + n_drawn)) {
-            n_visited += 1;
-            fj = fo_rand_int(n_drawn, f_i - n_found, &rstate);
+          int nbatch = 0;
+          int s_fi = f_i, s_nv = n_visited, s_nd = n_drawn;
+          uint32_t s_rs = rstate;
+          int ulen = 0;
+          while (nbatch < KB && s_fi > n_total_constants &&
+                 (s_nv < P.max_features || s_nv <= n_found + s_nd)) {
+            s_nv += 1;
+            int fj = fo_rand_int(s_nd, s_fi - n_found, &s_rs);
             if (fj < n_known) {   // a known constant: move it to the drawn-constants prefix
-              const int t = features[n_drawn]; features[n_drawn] = features[fj]; features[fj] = t;
-              n_drawn += 1;
+              const int t = features[s_nd]; features[s_nd] = features[fj]; features[fj] = t;
+              undo[ulen++] = make_int2(s_nd, fj);
+              s_nd += 1;
               continue;
             }
             fj += n_found;
-            go = 1;
-            break;
+            FoItem it;
+            it.f = features[fj]; it.fj = fj; it.rs = s_rs; it.nv = s_nv; it.nd = s_nd; it.fi = s_fi; it.ulen = ulen;
+            items[nbatch] = it;
+            s_fi -= 1;          // speculative: not constant
+            { const int t = features[s_fi]; features[s_fi] = features[fj]; features[fj] = t; }
+            undo[ulen++] = make_int2(s_fi, fj);
+            nbatch += 1;
           }
-          s_ctrl[0] = go; s_ctrl[1] = fj;
+          s_ctrl[0] = nbatch;
+          // keep the simulated end state for the no-rollback case
+          s_ctrl[1] = s_fi; s_ctrl[7] = s_nv; s_sim_nd = s_nd; s_sim_rs = s_rs; s_sim_ulen = ulen;
+          if (nbatch == 0) { f_i = s_fi; n_visited = s_nv; n_drawn = s_nd; rstate = s_rs; }
         }
         __syncthreads();
-        if (!s_ctrl[0]) break;
-        const int fj = s_ctrl[1];
-        const int f = features[fj];
-        // --- histogram of the node's samples over the feature's bins ---
-        for (int i = tid; i < FO_BINS * (FO_MAXC + 1); i += FO_THREADS) hist[i] = 0;
+        const int nbatch = s_ctrl[0];
+        if (nbatch == 0) break;
+        // --- histograms of all batch features in one pass over the node's samples ---
+        const int hstride = (C + 1) * FO_BINS;
+        for (int i = tid; i < nbatch * hstride; i += FO_THREADS) hist[i] = 0;
         __syncthreads();
-        const uint8_t* xb = P.xbin + (size_t)f * n;
         for (int i = start + tid; i < end; i += FO_THREADS) {
           const uint2 sv = samp[i];
-          const unsigned b = xb[sv.x];
-          atomicAdd(&hcls[(sv.y & 0xFF) * FO_BINS + b], sv.y >> 8);
-          atomicAdd(&hcnt[b], 1u);
+          const unsigned cls = sv.y & 0xFF, wgt = sv.y >> 8;
+          for (int k = 0; k < nbatch; ++k) {
+            const unsigned bb = P.xbin[(size_t)items[k].f * n + sv.x];
+            unsigned int* H = hist + k * hstride;
+            atomicAdd(&H[cls * FO_BINS + bb], wgt);
+            atomicAdd(&H[C * FO_BINS + bb], 1u);
+          }
         }
         __syncthreads();
-        {  // presence bitmap
-          const unsigned bal = __ballot_sync(0xffffffffu, hcnt[tid] != 0);
-          if (lane == 0) present[wid] = bal;
-        }
-        __syncthreads();
-        // --- thread 0: scan the present bins in ascending order = the sorted distinct values ---
-        if (tid == 0) {
-          const float* bv = P.binval + (size_t)f * FO_BINS;
-          int first_bin = -1, last_bin = -1;
-          for (int wv = 0; wv < FO_BINS / 32; ++wv) if (present[wv]) { first_bin = wv * 32 + __ffs(present[wv]) - 1; break; }
-          for (int wv = FO_BINS / 32 - 1; wv >= 0; --wv) if (present[wv]) { last_bin = wv * 32 + 31 - __clz(present[wv]); break; }
-          if (bv[last_bin] <= bv[first_bin] + FEATURE_THRESHOLD) {
-            // constant in this node
-            const int t = features[fj]; features[fj] = features[n_total_constants]; features[n_total_constants] = t;
-            n_found += 1;
-            n_total_constants += 1;
-          } else {
-            f_i -= 1;
-            { const int t = features[f_i]; features[f_i] = features[fj]; features[fj] = t; }
+        // --- one warp per feature: scan the 256 bins (8 per lane) in ascending order ---
+        for (int k = wid; k < nbatch; k += FO_THREADS / 32) {
+          const unsigned int* H = hist + k * hstride;
+          const float* bv = P.binval + (size_t)items[k].f * FO_BINS;
+          unsigned cntb[8];
+          unsigned ltot = 0, pmask = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { cntb[j] = H[C * FO_BINS + lane * 8 + j]; ltot += cntb[j]; if (cntb[j]) pmask |= 1u << j; }
+          // exclusive prefix of sample counts over lanes
+          unsigned pre = ltot;
+          for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+          pre -= ltot;
+          // class-weight prefixes
+          unsigned long long clspre[FO_MAXC];
+          for (int c = 0; c < C; ++c) {
+            unsigned long long t = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t += H[c * FO_BINS + lane * 8 + j];
+            unsigned long long incl = t;
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            clspre[c] = incl - t;
+          }
+          // first present bin of this lane, then "first present bin in any later lane"
+          const int myfirst = pmask ? lane * 8 + __ffs(pmask) - 1 : 1 << 20;
+          int nxt = 1 << 20;   // first present bin among lanes > lane
+          {
+            int v = myfirst;
+            // suffix minimum (exclusive)
+            int run = v;
+            for (int o = 1; o < 32; o <<= 1) { int u = __shfl_down_sync(0xffffffffu, run, o); if (lane + o < 32) run = min(run, u); }
+            int nx = __shfl_down_sync(0xffffffffu, run, 1);
+            nxt = lane < 31 ? nx : (1 << 20);
+          }
+          const int gfirst = __reduce_min_sync(0xffffffffu, myfirst);
+          const int mylast = pmask ? lane * 8 + 31 - __clz(pmask) : -1;
+          const int glast = __reduce_max_sync(0xffffffffu, mylast);
+          const bool is_const = bv[glast] <= bv[gfirst] + FEATURE_THRESHOLD;
+          // candidates of this lane in ascending bin order
+          double bproxy = -INFINITY, bil = 0.0, bir = 0.0;
+          int bpos = 1 << 30, bbin = -1, bnext = -1;
+          unsigned long long bsl[FO_MAXC];
+          for (int c = 0; c < C; ++c) bsl[c] = 0;
+          if (!is_const) {
+            unsigned run_cnt = pre;
             unsigned long long sl[FO_MAXC];
-            for (int c = 0; c < C; ++c) sl[c] = 0;
-            int p = start;            // number of samples consumed + start
-            int prev_bin = -1;
-            for (int wv = 0; wv < FO_BINS / 32; ++wv) {
-              unsigned m = present[wv];
-              while (m) {
-                const int b = wv * 32 + __ffs(m) - 1;
-                m &= m - 1;
-                if (prev_bin >= 0 && bv[b] > bv[prev_bin] + FEATURE_THRESHOLD) {
-                  // candidate split between prev_bin (p_prev = p - 1) and b (position p)
-                  const int n_left = p - start, n_right = end - p;
-                  if (n_left >= P.min_samples_leaf && n_right >= P.min_samples_leaf) {
-                    double wl = 0.0;
-                    for (int c = 0; c < C; ++c) wl += (double)sl[c];
-                    const double wr = w_node - wl;
-                    if (!(wl < P.min_weight_leaf || wr < P.min_weight_leaf)) {
-                      double il, ir;
-                      fo_children_impurity(sl, rec.sums, C, wl, wr, &il, &ir);
-                      const double proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
-                      if (proxy > best_proxy) {
-                        best_proxy = proxy;
-                        best_feature = f; best_pos = p; best_bin = prev_bin;
-                        best_thr = (double)bv[prev_bin] / 2.0 + (double)bv[b] / 2.0;
-                        best_mgl = n_left > n_right;
-                        best_il = il; best_ir = ir;
-                        for (int c = 0; c < C; ++c) best_sl[c] = sl[c];
-                      }
-                    }
-                  }
-                }
-                for (int c = 0; c < C; ++c) sl[c] += hcls[c * FO_BINS + b];
-                p += (int)hcnt[b];
-                prev_bin = b;
+            for (int c = 0; c < C; ++c) sl[c] = clspre[c];
+            for (int j = 0; j < 8; ++j) {
+              if (!cntb[j]) continue;
+              const int bb = lane * 8 + j;
+              run_cnt += cntb[j];
+              for (int c = 0; c < C; ++c) sl[c] += H[c * FO_BINS + bb];
+              // next present bin
+              const unsigned higher = pmask & ~((2u << j) - 1u);
+              const int nb2 = higher ? lane * 8 + __ffs(higher) - 1 : nxt;
+              if (nb2 >= (1 << 20)) continue;                              // last present bin
+              if (!(bv[nb2] > bv[bb] + FEATURE_THRESHOLD)) continue;       // values within 1e-7: same run
+              const int n_left = (int)run_cnt, n_right = n_node - n_left;
+              if (n_left < P.min_samples_leaf || n_right < P.min_samples_leaf) continue;
+              double wl = 0.0;
+              for (int c = 0; c < C; ++c) wl += (double)sl[c];
+              const double wr = w_node - wl;
+              if (wl < P.min_weight_leaf || wr < P.min_weight_leaf) continue;
+              double il, ir;
+              fo_children_impurity(sl, rec.sums, C, wl, wr, &il, &ir);
+              const double proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
+              if (proxy > bproxy) {
+                bproxy = proxy; bil = il; bir = ir; bpos = start + n_left; bbin = bb; bnext = nb2;
+                for (int c = 0; c < C; ++c) bsl[c] = sl[c];
               }
             }
           }
+          // warp arg-max; ties keep the smallest position (the sequential scan's strict '>')
+          double wp = bproxy; int wpos = bpos;
+          for (int o = 16; o > 0; o >>= 1) {
+            const double op = __shfl_xor_sync(0xffffffffu, wp, o);
+            const int opos = __shfl_xor_sync(0xffffffffu, wpos, o);
+            if (op > wp || (op == wp && opos < wpos)) { wp = op; wpos = opos; }
+          }
+          FoResult* R = &results[k];
+          if (lane == 0) { R->is_const = is_const; R->proxy = wp; R->pos = wpos; }
+          if (bpos == wpos && bproxy == wp && wp > -INFINITY) {   // unique lane: positions are unique per bin
+            R->bin = bbin; R->il = bil; R->ir = bir;
+            R->thr = (double)bv[bbin] / 2.0 + (double)bv[bnext] / 2.0;
+            for (int c = 0; c < C; ++c) R->sl[c] = bsl[c];
+          }
+        }
+        __syncthreads();
+        // --- thread 0: commit in draw order, roll back at the first constant feature ---
+        if (tid == 0) {
+          bool rolled = false;
+          for (int k = 0; k < nbatch; ++k) {
+            const FoResult& R = results[k];
+            if (!R.is_const) {
+              if (R.proxy > best_proxy) {
+                best_proxy = R.proxy;
+                best_feature = items[k].f; best_pos = R.pos; best_bin = R.bin; best_thr = R.thr;
+                best_mgl = (R.pos - start) > (end - R.pos);
+                best_il = R.il; best_ir = R.ir;
+                for (int c = 0; c < C; ++c) best_sl[c] = R.sl[c];
+              }
+              continue;
+            }
+            // undo every swap made after this item's draw, then take the constant branch
+            for (int u = s_sim_ulen - 1; u >= items[k].ulen; --u) {
+              const int2 sw = undo[u];
+              const int t = features[sw.x]; features[sw.x] = features[sw.y]; features[sw.y] = t;
+            }
+            rstate = items[k].rs; n_visited = items[k].nv; n_drawn = items[k].nd; f_i = items[k].fi;
+            { const int fj = items[k].fj;
+              const int t = features[fj]; features[fj] = features[n_total_constants]; features[n_total_constants] = t; }
+            n_found += 1;
+            n_total_constants += 1;
+            rolled = true;
+            break;
+          }
+          if (!rolled) { f_i = s_ctrl[1]; n_visited = s_ctrl[7]; n_drawn = s_sim_nd; rstate = s_sim_rs; }
         }
         __syncthreads();
       }
@@ -490,7 +586,7 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   if (!c->ycls) return fail(c, "forest: stage labels first");
   const int64_t n = c->n;
   const int d = (int)c->d;
-  if ((size_t)2 * d * sizeof(int) > 40 * 1024) return fail(c, "forest: too many features for the shared-memory feature permutation");
+  if ((size_t)4 * d * sizeof(int) > 6 * 1024) return fail(c, "forest: device path supports up to 384 features (shared-memory feature permutation)");
   // slots: concurrent trees per wave, bounded by memory (worst case 2*n nodes per tree)
   const int64_t node_cap = 2 * n;
   const size_t per_slot = (size_t)n * 16 + (size_t)node_cap * (4 * 3 + 1 + 8 * 3 + 8 * n_classes) + 4096 * sizeof(FoRecord);
@@ -528,7 +624,7 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   P.min_samples_leaf = min_samples_leaf; P.min_weight_leaf = min_weight_leaf;
   P.min_impurity_decrease = min_impurity_decrease;
   P.counts = dcounts; P.rand_state = drs; P.stack_cap = stack_cap; P.node_cap = node_cap;
-  const size_t smem = (size_t)2 * d * sizeof(int);
+  const size_t smem = (size_t)2 * d * sizeof(int) + (size_t)(d + 16) * sizeof(int2);
   std::vector<int32_t> hcount(slots), hdepth(slots), hstatus(slots);
   SkdTreeView view;
   std::vector<int32_t> hl, hr, hf, hn; std::vector<uint8_t> hm; std::vector<double> ht, hi, hw, hv;
