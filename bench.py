@@ -64,12 +64,21 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.t0 = self.t1 = None
+
+    # nvidia-smi takes driver locks while it starts up (hundreds of ms of stalled CUDA calls), so it
+    # is started before the warm-up; only samples taken between begin() and end() are reported.
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "250"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -77,7 +86,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -89,7 +98,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (self.t0 is None or t >= self.t0) and (self.t1 is None or t <= self.t1 + 0.25)]
+        if not rows:
+            rows = [r for _, r in self.rows[-1:]]
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for nm, v in zip(names, r[3:7]):
@@ -225,12 +237,13 @@ def main():
         correct, count = eng.linear_score_batch(res["coef"], f_cols, pos)
         return res, correct, count
 
-    for _ in range(a.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler.begin()
     eng.profile(1)
     c0 = eng.counters()
     # CUDA events on the stream the kernels are launched on (the library's own stream;
@@ -240,6 +253,7 @@ def main():
         res, correct, count = step()
     wall = eng.timer_stop()
     barrier()
+    sampler.end()
     prof = eng.profile(0)
     c1 = eng.counters()
     clocks = sampler.stop() if rank == 0 else None

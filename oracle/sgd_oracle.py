@@ -2,7 +2,8 @@
 (ref multiclass.py:109-152) runs per label column.  TEST INFRASTRUCTURE ONLY (slow: small cases).
 
 The algorithm lives in scikit-learn 1.9.0 (the reference's third-party dependency):
-  * driver        SK/linear_model/_stochastic_gradient.py:387-515 (fit_binary: y in {-1,+1},
+  * driver        SK/linear_model/_stochastic_gradient.py:387-515 (fit_binary: y in {-1,+1} for
+                  hinge, {0,1} for log_loss = CyHalfBinomialLoss,
                   seed = RandomState(random_state).randint(MAX_INT), intercept_decay = 1 dense)
   * inner loop    SK/linear_model/_sgd_fast.pyx.tp:274-640 (_plain_sgd32: float32 weights,
                   float64 scalars, "optimal" schedule eta = 1/(alpha*(optimal_init+t-1)),
@@ -13,6 +14,8 @@ The algorithm lives in scikit-learn 1.9.0 (the reference's third-party dependenc
                   applied to the evolving index array), SK/utils/_random.pxd:20-34 (xorshift32)
 tests/test_oracle.py checks fit_binary_sgd() equals sklearn's SGDClassifier bit for bit.
 """
+import math
+
 import numpy as np
 
 f32 = np.float32
@@ -38,16 +41,32 @@ def shuffle_inplace(ind, seed):
         ind[i], ind[j] = ind[j], ind[i]
 
 
+def _log1pexp(x):
+    """SK/_loss/_loss.pyx.tp:256-266."""
+    if x <= -37:
+        return math.exp(x)
+    if x <= -2:
+        return math.log1p(math.exp(x))
+    if x <= 18:
+        return math.log(1.0 + math.exp(x))
+    if x <= 33.3:
+        return x + math.exp(-x)
+    return x
+
+
 def _loss_grad(loss, y, p):
-    z = p * y
+    """(cy_loss, cy_gradient).  Hinge takes y in {-1,+1} (SK/linear_model/_sgd_fast.pyx.tp:131-146);
+    log_loss is CyHalfBinomialLoss on y in {0,1} (SK/_loss/_loss.pyx.tp:686-725,
+    SK/linear_model/_stochastic_gradient.py:350-361,450)."""
     if loss == "hinge":
+        z = p * y
         return (1.0 - z, -y) if z <= 1.0 else (0.0, 0.0)
-    # log_loss (class Log)
-    if z > 18.0:
-        return np.exp(-z), np.exp(-z) * -y
-    if z < -18.0:
-        return -z, -y
-    return np.log(1.0 + np.exp(-z)), -y / (np.exp(z) + 1.0)
+    y01 = 1.0 if y > 0 else 0.0
+    cur = _log1pexp(p) - y01 * p
+    if p > -37:
+        e = math.exp(-p)
+        return cur, ((1 - y01) - y01 * e) / (1 + e)
+    return cur, math.exp(p) - y01
 
 
 def fit_binary_sgd(X, y_pm1, loss="hinge", alpha=1e-4, fit_intercept=True, max_iter=1000, tol=1e-3,

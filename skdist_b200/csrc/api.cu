@@ -46,12 +46,14 @@ static bool want_tc(const Ctx* c) {
 }
 
 // Decide the evaluation path for a batch and allocate its evaluation buffers.
-static int alloc_eval_buffers(Ctx* c, Scratch& sx, LogregWork& w, int B) {
+static int alloc_eval_buffers(Ctx* c, Scratch& sx, LogregWork& w, int B, int slot_cap = 0) {
   const int64_t n = c->n, ldx = c->ldx;
   if (c->kernel_choice == 2 && !tc_supported(c))
     return fail(c, "tcgen05 path requested but the staged shape is unsupported (needs d <= 256)");
   w.use_tc = want_tc(c);
-  w.cap_sc = (int64_t)4 * c->sm_count * 64 + B + 64;
+  if (slot_cap < B) slot_cap = B;
+  w.slot_cap = slot_cap;
+  w.cap_sc = (int64_t)4 * c->sm_count * 64 + slot_cap + 64;
   w.nz = 1024;
   SKD_CUDA(c, sx.alloc(&w.lossp, (size_t)w.cap_sc));
   SKD_CUDA(c, sx.alloc(&w.gsump, (size_t)w.cap_sc));
@@ -59,7 +61,7 @@ static int alloc_eval_buffers(Ctx* c, Scratch& sx, LogregWork& w, int B) {
     if (tc_prepare(c)) return 1;
     w.ldw = c->tc.dpad;
     w.gscale = c->tc.gscale;
-    w.slots_pad_cap = (int)round_up(B, 128);
+    w.slots_pad_cap = (int)round_up(slot_cap, 128);
     size_t wbytes = (size_t)w.slots_pad_cap * c->tc.dpad * 2;
     SKD_CUDA(c, sx.alloc((uint8_t**)&w.Wh, wbytes));
     SKD_CUDA(c, sx.alloc((uint8_t**)&w.Wl, wbytes));
@@ -210,9 +212,11 @@ int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_fo
   c->tc.meta_valid = false;
   c->n_folds = 0;
   c->fold_count.clear();
+  c->h_fold.clear();
   if (!fold_id) return 0;  // cleared
   if (n != c->n || n_folds <= 0 || n_folds > 127) return fail(c, "skd_stage_folds: bad arguments");
   c->fold_count.assign(n_folds, 0);
+  c->h_fold.assign(fold_id, fold_id + n);
   for (int64_t i = 0; i < n; ++i) {
     int f = fold_id[i];
     if (f < 0 || f >= n_folds) return fail(c, "skd_stage_folds: fold id out of range");
@@ -281,6 +285,23 @@ int skd_get_counters(skd_ctx* ctx, int64_t* launches, int64_t* h2d, int64_t* d2h
   return 0;
 }
 
+// SKDIST_B200_TRACE=1: host wall-clock per phase of a call (stream synchronised at each mark), to stderr
+struct Trace {
+  Ctx* c; const char* call; bool on; std::chrono::steady_clock::time_point t;
+  Trace(Ctx* c_, const char* call_) : c(c_), call(call_) {
+    const char* e = getenv("SKDIST_B200_TRACE");
+    on = e && *e && *e != '0';
+    t = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(c->stream);
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[skd trace] %s %-10s %9.3f ms\n", call, what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t* col_fold,
                          const int32_t* col_pos, int32_t fit_intercept, double tol,
                          int32_t max_iter, float* coef_out, int32_t* n_iter_out,
@@ -313,11 +334,32 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
     mean_ntrain += (double)ntrain / B;
   }
 
+  Trace tr(c, "logreg_fit");
   Scratch sx(c);
   LogregWork w;
   w.B = B; w.dp = dp;
   w.vec_stride = (size_t)(5 + 2 * m) * dp + 2 * m;
-  if (alloc_eval_buffers(c, sx, w, B)) return 1;
+  // Fold-grouped slot layout for the tensor-core path: columns sorted by held-out fold, every fold
+  // segment padded to a multiple of 128 slots (one MMA group = one fold -> tile skipping).
+  std::vector<SlotMeta> hslots;
+  const bool grouped = want_tc(c) && tc_supported(c);
+  if (grouped) {
+    std::vector<int> order(B);
+    for (int j = 0; j < B; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return col_fold[a] < col_fold[b]; });
+    for (int i = 0; i < B;) {
+      int f = col_fold[order[i]], i0 = i;
+      if (f > 127) return fail(c, "skd_logreg_fit_batch: fold id above 127");
+      for (; i < B && col_fold[order[i]] == f; ++i) {
+        SlotMeta sm; sm.col = order[i]; sm.fold = f < 0 ? -1 : f; sm.pos = col_pos[order[i]]; sm.pad = 0;
+        hslots.push_back(sm);
+      }
+      (void)i0;
+      while (hslots.size() % 128) { SlotMeta sm; sm.col = -1; sm.fold = f < 0 ? -1 : f; sm.pos = -1; sm.pad = 0; hslots.push_back(sm); }
+    }
+  }
+  if (alloc_eval_buffers(c, sx, w, B, grouped ? (int)hslots.size() : B)) return 1;
+  w.grouped = grouped && w.use_tc;
   SKD_CUDA(c, sx.alloc(&w.sc, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.vec, (size_t)B * w.vec_stride));
   SKD_CUDA(c, sx.alloc(&w.l2, (size_t)B));
@@ -325,14 +367,16 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   SKD_CUDA(c, sx.alloc(&w.col_fold, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.col_pos, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.n_evals, (size_t)B));
-  SKD_CUDA(c, sx.alloc(&w.slot, (size_t)B));
+  SKD_CUDA(c, sx.alloc(&w.slot, (size_t)w.slot_cap));
   SKD_CUDA(c, sx.alloc(&w.n_act, 1));
+  SKD_CUDA(c, sx.alloc(&w.n_run, 1));
   float* dcoef; int32_t *dniter, *dstatus; double* dloss;
   SKD_CUDA(c, sx.alloc(&dcoef, (size_t)B * dp));
   SKD_CUDA(c, sx.alloc(&dniter, (size_t)B));
   SKD_CUDA(c, sx.alloc(&dstatus, (size_t)B));
   SKD_CUDA(c, sx.alloc(&dloss, (size_t)B));
 
+  tr.mark("alloc");
   cudaEvent_t e0, e1;
   SKD_CUDA(c, cudaEventCreate(&e0));
   SKD_CUDA(c, cudaEventCreate(&e1));
@@ -343,13 +387,20 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   SKD_CUDA(c, cudaMemcpyAsync(w.col_pos, col_pos, B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   c->h2d += (int64_t)B * 24;
 
+  if (w.grouped) {
+    int32_t ns = (int32_t)hslots.size();
+    SKD_CUDA(c, cudaMemcpyAsync(w.slot, hslots.data(), hslots.size() * sizeof(SlotMeta), cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(w.n_act, &ns, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  }
   if (lbfgs_dev_init(c, w, fit_intercept, tol, max_iter)) return 1;
-  int n_act = B;
+  tr.mark("init");
+  int n_act = w.grouped ? (int)hslots.size() : B;
+  int n_run = B;
   const long max_rounds = (long)max_iter * 52 + 16;
   long rounds = 0;
   std::vector<double> round_flops;
   size_t ev_used = 0;
-  while (n_act > 0) {
+  while (n_run > 0) {
     int nz_used = 0;
     if (c->prof) {
       if (c->prof_events.size() < ev_used + 2) {
@@ -367,13 +418,15 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
       ev_used += 2;
       // algorithmic work of this launch: 4 * n_train * d per active column; the active set is
       // only known on the device, so use the mean training fraction of the batch
-      round_flops.push_back(4.0 * (double)d * (double)n_act * mean_ntrain);
+      round_flops.push_back(4.0 * (double)d * (double)n_run * mean_ntrain);
     }
-    int n_next = 0;
-    if (lbfgs_dev_step(c, w, n_act, nz_used, fit_intercept, &n_next)) return 1;
+    int n_next = 0, r_next = 0;
+    if (lbfgs_dev_step(c, w, n_act, nz_used, fit_intercept, &n_next, &r_next)) return 1;
     n_act = n_next;
+    n_run = r_next;
     if (++rounds > max_rounds) return fail(c, "skd_logreg_fit_batch: round limit exceeded (internal error)");
   }
+  tr.mark("rounds");
   if (c->prof) {
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i + 1 < ev_used; i += 2) {
@@ -401,6 +454,7 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
+  tr.mark("finish");
   return 0;
 }
 
@@ -486,6 +540,7 @@ int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int
   if (B <= 0 || !coef || !col_fold || !col_pos || !correct_out || !count_out)
     return fail(c, "skd_linear_score_batch: bad arguments");
   SKD_CUDA(c, cudaSetDevice(c->device));
+  Trace tr(c, "score");
   Scratch sx(c);
   std::vector<SlotMeta> hs(B);
   for (int j = 0; j < B; ++j) {
@@ -527,8 +582,10 @@ int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int
     SKD_CUDA(c, cudaMemcpyAsync(w.n_act, &nb, sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
     c->h2d += (int64_t)hx.size() * 8;
+    tr.mark("setup");
     if (tc_export(c, w, B, dx, 1)) return 1;
     if (tc_score(c, w, B, dcorrect, dcount)) return 1;
+    tr.mark("kernel");
   } else {
     float* dW;
     if (pack_coef(c, sx, B, coef, &dW)) return 1;

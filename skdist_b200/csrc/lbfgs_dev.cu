@@ -117,11 +117,13 @@ __global__ void lb_init_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride,
     LbfgsScalars s;
     lbfgs_init(s, n, m, maxiter, maxls, pgtol, ftol);
     sc[col] = s;
-    SlotMeta sm;
-    sm.col = col; sm.fold = col_fold[col]; sm.pos = col_pos[col]; sm.pad = 0;
-    slot[col] = sm;
+    if (slot) {   // dense layout: slot i = column i (the grouped layout is uploaded by the host)
+      SlotMeta sm;
+      sm.col = col; sm.fold = col_fold[col]; sm.pos = col_pos[col]; sm.pad = 0;
+      slot[col] = sm;
+      if (col == 0) *n_act = B;
+    }
     n_evals[col] = 0;
-    if (col == 0) *n_act = B;
   }
 }
 
@@ -136,6 +138,7 @@ lb_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta*
   const int s = blockIdx.x;
   if (s >= n_act) return;
   const int col = slot[s].col;
+  if (col < 0) return;   // padding slot of the fold-grouped layout
   LbfgsScalars st = sc[col];
   const int n = st.n, m = st.m;
   LbfgsVectors v = col_vectors(vec + (size_t)col * vec_stride, n, m);
@@ -201,6 +204,67 @@ __global__ void lb_compact_kernel(const LbfgsScalars* sc, SlotMeta* slot, int n_
   }
 }
 
+// Fold-grouped compaction (single CTA).  Input: slots grouped by fold in 128-aligned segments
+// (padding entries col = -1).  Output, in place: the still-running columns of every fold, in
+// their old order, each fold segment padded again to a multiple of 128.
+__global__ void lb_compact_grouped_kernel(const LbfgsScalars* sc, SlotMeta* slot, int n_in,
+                                          int32_t* n_slots_out, int32_t* n_run_out) {
+  __shared__ int cnt[130];       // kept per fold key (key = fold + 1, fold in [-1, 127])
+  __shared__ int base[130];      // output base per fold key
+  __shared__ int before[130];    // kept in earlier fold keys
+  __shared__ int wsum[32];
+  __shared__ int run_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < 130; i += blockDim.x) cnt[i] = 0;
+  if (tid == 0) run_s = 0;
+  __syncthreads();
+  for (int i = tid; i < n_in; i += blockDim.x) {
+    const SlotMeta sm = slot[i];
+    if (sm.col >= 0 && sc[sm.col].status == LB_RUNNING) atomicAdd(&cnt[sm.fold + 1], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int b = 0, k = 0;
+    for (int f = 0; f < 130; ++f) { base[f] = b; before[f] = k; b += (cnt[f] + 127) / 128 * 128; k += cnt[f]; }
+    *n_slots_out = b;
+    *n_run_out = k;
+  }
+  __syncthreads();
+  // ordered scatter: global rank of a kept entry minus the kept entries of earlier folds
+  for (int start = 0; start < n_in; start += blockDim.x) {
+    const int i = start + tid;
+    SlotMeta sm;
+    int keep = 0;
+    if (i < n_in) { sm = slot[i]; keep = (sm.col >= 0 && sc[sm.col].status == LB_RUNNING) ? 1 : 0; }
+    int x = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+      int w = (lane < (int)(blockDim.x >> 5)) ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const int rank = run_s + x - keep + (wid > 0 ? wsum[wid - 1] : 0);
+    const int total = wsum[(blockDim.x >> 5) - 1];
+    __syncthreads();
+    if (keep) slot[base[sm.fold + 1] + rank - before[sm.fold + 1]] = sm;
+    if (tid == 0) run_s += total;
+    __syncthreads();
+  }
+  // padding
+  for (int f = 0; f < 130; ++f) {
+    const int lo = base[f] + cnt[f], hi = base[f] + (cnt[f] + 127) / 128 * 128;
+    for (int i = lo + tid; i < hi; i += blockDim.x) {
+      SlotMeta sm; sm.col = -1; sm.fold = f - 1; sm.pos = -1; sm.pad = 0;
+      slot[i] = sm;
+    }
+  }
+}
+
 __global__ void lb_export_kernel(const LbfgsScalars* sc, const double* vec, size_t vec_stride,
                                  const SlotMeta* slot, const int32_t* n_act, int d, int ldx,
                                  int Bcap, float* Wact) {
@@ -233,12 +297,12 @@ int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max
   const int m = 10, maxls = 50;
   const double ftol = 64.0 * 2.220446049250313e-16;
   lb_init_kernel<<<w.B, 128, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.B, w.dp, m, max_iter,
-                                             maxls, tol, ftol, w.slot, w.col_fold, w.col_pos,
-                                             w.n_evals, w.n_act);
+                                             maxls, tol, ftol, w.grouped ? nullptr : w.slot, w.col_fold,
+                                             w.col_pos, w.n_evals, w.n_act);
   // initial iterate is w0 = 0 (SK/linear_model/_logistic.py:443): export zeros
   c->launches += 1;
   if (w.use_tc) {
-    if (tc_export(c, w, w.B, nullptr, fit_intercept)) return 1;
+    if (tc_export(c, w, w.grouped ? w.slot_cap : w.B, nullptr, fit_intercept)) return 1;
   } else {
     SKD_CUDA(c, cudaMemsetAsync(w.Wact, 0, ((size_t)w.B * c->ldx + w.B) * sizeof(float), c->stream));
   }
@@ -247,12 +311,13 @@ int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max
 }
 
 int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_intercept,
-                   int* n_act_out) {
+                   int* n_act_out, int* n_run_out) {
   const int d = (int)c->d, ldx = (int)c->ldx;
   lb_step_kernel<<<n_act_in, LB_THREADS, 0, c->stream>>>(
       w.sc, w.vec, w.vec_stride, w.slot, n_act_in, nz_used, d, w.ldw, fit_intercept, w.lossp,
       w.gsump, w.gradp, w.gscale, w.l2, w.inv_n, w.n_evals);
-  lb_compact_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, nullptr);
+  if (w.grouped) lb_compact_grouped_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, w.n_run);
+  else lb_compact_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, nullptr);
   c->launches += 2;
   if (w.use_tc) {
     if (tc_export(c, w, n_act_in, nullptr, fit_intercept)) return 1;
@@ -262,11 +327,13 @@ int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_int
     c->launches += 1;
   }
   SKD_CUDA(c, cudaGetLastError());
-  int32_t na = 0;
+  int32_t na = 0, nr = 0;
   SKD_CUDA(c, cudaMemcpyAsync(&na, w.n_act, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (w.grouped) SKD_CUDA(c, cudaMemcpyAsync(&nr, w.n_run, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->d2h += sizeof(int32_t);
+  c->d2h += 2 * sizeof(int32_t);
   *n_act_out = na;
+  *n_run_out = w.grouped ? nr : na;
   return 0;
 }
 

@@ -29,6 +29,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "skd_internal.h"
 
 namespace skd {
@@ -302,6 +304,14 @@ tc_export_kernel(const double* __restrict__ vec, size_t vec_stride, const SlotMe
   const int s = blockIdx.x;
   if (s >= *n_act) return;
   const SlotMeta sm = slot[s];
+  if (sm.col < 0) {   // padding slot of the fold-grouped layout: zero weights, keeps its segment's fold
+    for (int k = threadIdx.x; k < dpad; k += 128) {
+      Wh[(size_t)s * dpad + k] = __float2half_rn(0.f);
+      Wl[(size_t)s * dpad + k] = __float2half_rn(0.f);
+    }
+    if (threadIdx.x == 0) { TcSlotParam p; p.inv_t = 1.f; p.bias = 0.f; p.fold = sm.fold; p.pos = -1; sp[s] = p; }
+    return;
+  }
   const double* x = xin ? xin + (size_t)s * (d + 1) : vec + (size_t)sm.col * vec_stride;
   float m = 0.f;
   for (int k = threadIdx.x; k < d; k += 128) m = fmaxf(m, fabsf((float)x[k] / xscale[k]));
@@ -350,6 +360,9 @@ struct TcParams {
   int groups;
   int n_tiles;               // npad / 64
   int ldw;                   // leading dimension of gradp (== dpad)
+  const int32_t* tilelist;   // per-fold lists of tiles with training rows (nullptr: every tile)
+  const int32_t* tilecnt;
+  int n_lists, n_tiles_ld;
   int parts;                 // > 0: aligned split (CTA = (group, part), same row ranges for every group)
                              // 0  : balanced split (groups * n_tiles units cut into gridDim.x ranges)
 };
@@ -425,12 +438,21 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
 
   const long long units = (long long)prm.groups * prm.n_tiles;
   long long u_begin, u_end;
+  const int32_t* tlist = nullptr;   // aligned split + fold-grouped slots: this group's tile list
   if (prm.parts > 0) {
     // aligned: all groups stream the same rows at the same time -> X is fetched from HBM once
-    // and the other groups hit L2
+    // and the other groups hit L2.  A group whose 128 columns hold out the same fold only visits
+    // the tiles that contain training rows of that fold (its list); the others are skipped.
     const int gg = blockIdx.x / prm.parts, pp = blockIdx.x % prm.parts;
-    u_begin = (long long)gg * prm.n_tiles + (long long)pp * prm.n_tiles / prm.parts;
-    u_end = (long long)gg * prm.n_tiles + (long long)(pp + 1) * prm.n_tiles / prm.parts;
+    int cnt = prm.n_tiles;
+    if (prm.tilelist) {
+      const int f = prm.sp[gg * TC_BC].fold;
+      const int li = (f >= 0 && f < prm.n_lists - 1) ? f : prm.n_lists - 1;
+      tlist = prm.tilelist + (size_t)li * prm.n_tiles_ld;
+      cnt = prm.tilecnt[li];
+    }
+    u_begin = (long long)gg * prm.n_tiles + (long long)pp * cnt / prm.parts;
+    u_end = (long long)gg * prm.n_tiles + (long long)(pp + 1) * cnt / prm.parts;
   } else {
     u_begin = tc_unit_begin(blockIdx.x, units, gridDim.x);
     u_end = tc_unit_begin(blockIdx.x + 1, units, gridDim.x);
@@ -457,6 +479,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
         for (int c = 0; c < NCHUNK; ++c)
           tma_load_2d(s_wh + c * WH_CHUNK, &map_wh, c * 64, g * TC_BC, &bars->w_full);
         for (int t = t0; t < t1; ++t) {
+          const int tile = tlist ? tlist[t] : t;
 #pragma unroll
           for (int half = 0; half < 2; ++half, ++h) {
             const uint32_t sl = h % TC_NS, ph = (h / TC_NS) & 1;
@@ -465,7 +488,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             const CUtensorMap* mp = half == 0 ? &map_xh : &map_xl;
 #pragma unroll
             for (int c = 0; c < NCHUNK; ++c)
-              tma_load_2d(s_ring + sl * SLOT_BYTES + c * X_CHUNK, mp, c * 64, t * TC_R, &bars->full[sl]);
+              tma_load_2d(s_ring + sl * SLOT_BYTES + c * X_CHUNK, mp, c * 64, tile * TC_R, &bars->full[sl]);
           }
         }
       }
@@ -620,7 +643,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
       float ls_hi = 0.f, ls_lo = 0.f, gs_hi = 0.f, gs_lo = 0.f;
       unsigned long long n_ok = 0, n_all = 0;
       for (int i = 0; i < nt; ++i, ++tcount) {
-        const int t = t0 + i;
+        const int t = tlist ? tlist[t0 + i] : t0 + i;
         const uint32_t zb = tl + TM_Z0 + (tcount & 1) * 64;
         // row metadata of this warp's 32 rows: issue the loads before waiting for the MMA so
         // their latency is hidden behind the wait
@@ -816,6 +839,8 @@ void tc_free(Ctx* c) {
   if (t.Xl) cudaFree(t.Xl);
   if (t.rowmeta) cudaFree(t.rowmeta);
   if (t.yreal_pad) cudaFree(t.yreal_pad);
+  if (t.tilelist) cudaFree(t.tilelist);
+  if (t.tilecnt) cudaFree(t.tilecnt);
   if (t.xscale) cudaFree(t.xscale);
   if (t.gscale) cudaFree(t.gscale);
   t = TcData();
@@ -860,6 +885,27 @@ int tc_prepare(Ctx* c) {
     tc_rowmeta_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c->stream>>>(c->ycls, c->fold, n, npad,
                                                                             t.rowmeta);
     c->launches += 1;
+    {  // per-fold tile lists: list f = tiles holding at least one row NOT in fold f; last list = all
+      const int n_tiles = (int)(npad / TC_R);
+      const int nf = (c->fold && c->n_folds <= 32 && (int64_t)c->h_fold.size() == n) ? c->n_folds : 0;
+      std::vector<int32_t> hl((size_t)(nf + 1) * n_tiles), hc(nf + 1, 0);
+      for (int tt = 0; tt < n_tiles; ++tt) {
+        uint32_t mask = 0;
+        const int64_t r1 = std::min<int64_t>(n, (int64_t)(tt + 1) * TC_R);
+        if (nf) for (int64_t r = (int64_t)tt * TC_R; r < r1; ++r) mask |= 1u << c->h_fold[r];
+        for (int f = 0; f < nf; ++f)
+          if (mask & ~(1u << f)) hl[(size_t)f * n_tiles + hc[f]++] = tt;
+        hl[(size_t)nf * n_tiles + hc[nf]++] = tt;
+      }
+      if (t.tilelist) { cudaFree(t.tilelist); t.tilelist = nullptr; }
+      if (t.tilecnt) { cudaFree(t.tilecnt); t.tilecnt = nullptr; }
+      SKD_CUDA(c, cudaMalloc((void**)&t.tilelist, hl.size() * 4));
+      SKD_CUDA(c, cudaMalloc((void**)&t.tilecnt, hc.size() * 4));
+      SKD_CUDA(c, cudaMemcpyAsync(t.tilelist, hl.data(), hl.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(t.tilecnt, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+      t.n_lists = nf + 1;
+    }
     if (c->yreal) {
       if (!t.yreal_pad) SKD_CUDA(c, cudaMalloc((void**)&t.yreal_pad, (size_t)npad * sizeof(float)));
       SKD_CUDA(c, cudaMemsetAsync(t.yreal_pad, 0, (size_t)npad * sizeof(float), c->stream));
@@ -973,6 +1019,11 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   prm.n_tiles = n_tiles;
   prm.ldw = w.ldw;
   prm.parts = parts;
+  const bool lists = mode == TC_FIT && parts > 0 && w.grouped && t.tilelist;
+  prm.tilelist = lists ? t.tilelist : nullptr;
+  prm.tilecnt = lists ? t.tilecnt : nullptr;
+  prm.n_lists = t.n_lists;
+  prm.n_tiles_ld = n_tiles;
   const size_t smem = 1024 + (size_t)nchunk * (TC_BC * 128) + (size_t)TC_NS * nchunk * (TC_R * 128) +
                       sizeof(TcBarriers) + 64;
   if (mode == TC_R2 && !t.yreal_pad) return fail(c, "tc_r2: targets not staged");

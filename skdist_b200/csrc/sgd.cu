@@ -110,14 +110,25 @@ sgd_epoch_kernel(const float* __restrict__ X, int ldx, int d, const int32_t* __r
     acc = warp_sum(acc);
     const double p = (double)(float)(acc * wscale) + intercept;
     // loss / gradient
-    const double z = p * y;
     double cur_loss, dloss;
-    if (LOSS == SGD_HINGE) {
+    if (LOSS == SGD_HINGE) {       // Hinge on y in {-1,+1} (SK/linear_model/_sgd_fast.pyx.tp:131-146)
+      const double z = p * y;
       if (z <= 1.0) { cur_loss = 1.0 - z; dloss = -y; } else { cur_loss = 0.0; dloss = 0.0; }
-    } else {
-      if (z > 18.0) { const double ez = exp(-z); cur_loss = ez; dloss = ez * -y; }
-      else if (z < -18.0) { cur_loss = -z; dloss = -y; }
-      else { cur_loss = log(1.0 + exp(-z)); dloss = -y / (exp(z) + 1.0); }
+    } else {                       // CyHalfBinomialLoss on y in {0,1} (SK/_loss/_loss.pyx.tp:256-266,686-725)
+      const double y01 = y > 0.0 ? 1.0 : 0.0;
+      double l1p;
+      if (p <= -37.0) l1p = exp(p);
+      else if (p <= -2.0) l1p = log1p(exp(p));
+      else if (p <= 18.0) l1p = log(__dadd_rn(1.0, exp(p)));
+      else if (p <= 33.3) l1p = __dadd_rn(p, exp(-p));
+      else l1p = p;
+      cur_loss = __dsub_rn(l1p, __dmul_rn(y01, p));
+      if (p > -37.0) {
+        const double et = exp(-p);
+        dloss = __ddiv_rn(__dsub_rn(1.0 - y01, __dmul_rn(y01, et)), __dadd_rn(1.0, et));
+      } else {
+        dloss = __dsub_rn(exp(p), y01);
+      }
     }
     const float normf = (float)sqrt(sq_norm);
     objective_sum = __dadd_rn(objective_sum,

