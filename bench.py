@@ -304,8 +304,18 @@ def main():
                          "peak_source": pk["src"] + " bf16 dense (sustained)",
                          "kernel": "logistic loss+gradient evaluation (rank 0)",
                          "launches": prof["eval_launches"], "avg_launch_ms": prof["eval_ms"] / max(1, prof["eval_launches"]),
-                         "algorithmic_flops": "4 * n_train * d per active column per launch"},
+                         "algorithmic_flops": "4 * n_train * d per active column per launch",
+                         # fp32-grade accuracy costs 3 fp16 MMA passes per algorithmic FLOP
+                         "mma_passes": 3, "tensor_issue_frac": 3 * achieved / pk["bf16_sustained"]},
         }
+        # DRAM traffic of the dominant kernel comes from the committed ncu capture (bench.py never runs
+        # under a profiler); only reported for the workload it was captured on
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath) and (a.n, a.d, a.candidates, a.folds, a.kernel) == (1_000_000, 256, 512, 5, 0):
+            with open(tpath) as f:
+                tj = json.load(f)
+            line["roofline"]["traffic"] = tj["dram_bytes_per_launch"]
+            line["roofline"]["traffic_source"] = tj["source"]
         if world == 1 and a.cpu_sample > 0:
             cores = os.cpu_count() or 1
             v, dt, _ = cpu_fits_per_sec(X, y, fold, Cs, a.cpu_sample, n_jobs=1)

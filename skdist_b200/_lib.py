@@ -78,7 +78,8 @@ SYMBOLS = {
 
 
 def lib_path():
-    return _build.LIBPATH
+    # SKDIST_B200_LIBPATH: A/B experiments against another build of the same C-ABI
+    return os.environ.get("SKDIST_B200_LIBPATH") or _build.LIBPATH
 
 
 def load(build_if_missing=True):

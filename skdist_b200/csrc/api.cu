@@ -360,6 +360,11 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   }
   if (alloc_eval_buffers(c, sx, w, B, grouped ? (int)hslots.size() : B)) return 1;
   w.grouped = grouped && w.use_tc;
+  if (w.grouped) {
+    w.uni_pos = col_pos[0];
+    for (int j = 1; j < B; ++j)
+      if (col_pos[j] != col_pos[0]) { w.uni_pos = -1; break; }
+  }
   SKD_CUDA(c, sx.alloc(&w.sc, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.vec, (size_t)B * w.vec_stride));
   SKD_CUDA(c, sx.alloc(&w.l2, (size_t)B));
@@ -398,7 +403,9 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   int n_run = B;
   const long max_rounds = (long)max_iter * 52 + 16;
   long rounds = 0;
+  const long force_rounds = getenv("SKDIST_B200_FORCE_ROUNDS") ? atol(getenv("SKDIST_B200_FORCE_ROUNDS")) : 0;
   std::vector<double> round_flops;
+  std::vector<int> round_act, round_run;
   size_t ev_used = 0;
   while (n_run > 0) {
     int nz_used = 0;
@@ -419,8 +426,14 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
       // algorithmic work of this launch: 4 * n_train * d per active column; the active set is
       // only known on the device, so use the mean training fraction of the batch
       round_flops.push_back(4.0 * (double)d * (double)n_run * mean_ntrain);
+      round_act.push_back(n_act);
+      round_run.push_back(n_run);
     }
     int n_next = 0, r_next = 0;
+    if (force_rounds > 0) {   // timing experiments: repeat the evaluation of the initial point
+      if (++rounds >= force_rounds) break;
+      continue;
+    }
     if (lbfgs_dev_step(c, w, n_act, nz_used, fit_intercept, &n_next, &r_next)) return 1;
     n_act = n_next;
     n_run = r_next;
@@ -432,6 +445,9 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
     for (size_t i = 0; i + 1 < ev_used; i += 2) {
       float ms = 0.f;
       SKD_CUDA(c, cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+      if (tr.on && getenv("SKDIST_B200_TRACE")[0] == '2')
+        fprintf(stderr, "[skd trace] round %3d slots %5d running %5d eval %7.3f ms\n", (int)(i / 2), round_act[i / 2],
+                round_run[i / 2], ms);
       c->prof_eval_ms += ms;
       c->prof_eval_flops += round_flops[i / 2];
       c->prof_eval_launches += 1;

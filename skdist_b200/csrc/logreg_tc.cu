@@ -21,7 +21,7 @@
 // stationary in TMEM, gradient accumulators (128 x d fp32) stationary in TMEM, X streamed in
 // tiles of 64 rows through a ring of 5 half-tile (hi or lo) slots.
 //   warp 0      : TMA producer        warp 1 : MMA issuer (+ TMEM allocation)
-//   warps 2..9  : epilogue, two warps per TMEM lane quadrant (lane = slot), 32 rows of the tile each
+//   warps 2..17 : epilogue, four warps per TMEM lane quadrant (lane = slot), 16 rows of the tile each
 // TMEM columns : [0,256) grad accumulator | [256,384) W_lo (packed fp16 pairs) |
 //                [384,448) Z/G buffer 0 | [448,512) Z/G buffer 1
 #include <cuda.h>
@@ -38,7 +38,7 @@ namespace skd {
 constexpr int TC_BC = 128;       // slots per group
 constexpr int TC_R = 64;         // rows per tile
 constexpr int TC_NS = 5;         // ring slots (half tiles)
-constexpr int TC_EPI_WARPS = 8;     // two per TMEM lane quadrant
+constexpr int TC_EPI_WARPS = 16;    // four per TMEM lane quadrant
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
 constexpr uint32_t TM_GRAD = 0, TM_WLO = 256, TM_Z0 = 384;
@@ -172,6 +172,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3])
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {   // named barrier 1: the epilogue warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -284,6 +292,19 @@ __global__ void tc_rowmeta_kernel(const int32_t* __restrict__ ycls, const int8_t
   rowmeta[r] = m;
 }
 
+// rowsg[li][r] = -y * 2^14 for the rows list li trains on (li < n_lists - 1: every row outside
+// fold li; last list: every row), 0 for held-out and padding rows.  y = +1 iff class id == pos.
+__global__ void tc_rowsg_kernel(const int32_t* __restrict__ ycls, const int8_t* __restrict__ fold,
+                                int64_t n, int64_t npad, int n_lists, int pos, float* __restrict__ rowsg) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= npad) return;
+  const bool in = r < n;
+  const float s = in ? (ycls[r] == pos ? -GSCALE : GSCALE) : 0.f;
+  const int f = (in && fold) ? (int)(uint8_t)fold[r] : -1;
+  for (int li = 0; li < n_lists; ++li)
+    rowsg[(size_t)li * npad + r] = (li < n_lists - 1 && f == li) ? 0.f : s;
+}
+
 // Export of the active slots' iterates in tensor-core form (replaces lb_export_kernel):
 // w32 = (float)x (SK/_linear_loss.py:216), W' = w32 / xscale * t, t = 2^(13 - floor(log2 max|w32/xscale|)),
 // Wh/Wl [slots_pad x dpad] fp16, wmeta[slot] = {1/t, bias, fold, pos}
@@ -363,6 +384,9 @@ struct TcParams {
   const int32_t* tilelist;   // per-fold lists of tiles with training rows (nullptr: every tile)
   const int32_t* tilecnt;
   int n_lists, n_tiles_ld;
+  const float* rowsg;        // TC_FIT_UNI: [n_lists x npad] per-row -y * 2^14 (0 = not a training row of that list)
+  long long rowsg_ld;
+  int debug;                 // SKDIST_B200_TC_DEBUG (timing experiments only): 2 = no GEMM2, 3 = no MMAs, 4 = no epilogue work
   int parts;                 // > 0: aligned split (CTA = (group, part), same row ranges for every group)
                              // 0  : balanced split (groups * n_tiles units cut into gridDim.x ranges)
 };
@@ -398,12 +422,15 @@ __device__ __forceinline__ int tc_first_cta(int g, int n_tiles, long long units,
   return (int)c;
 }
 
-enum { TC_FIT = 0, TC_SCORE = 1, TC_R2 = 2 };
+// TC_FIT_UNI: fit where every slot of a group shares (held-out fold, positive class): the row's
+// sign/mask comes from a precomputed per-fold array instead of being decoded per element
+enum { TC_FIT = 0, TC_SCORE = 1, TC_R2 = 2, TC_FIT_UNI = 3 };
 
 template <int NCHUNK, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
                const __grid_constant__ CUtensorMap map_wh, const TcParams prm) {
+  constexpr bool IS_FIT = MODE == TC_FIT || MODE == TC_FIT_UNI;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // carve shared memory (1024-byte aligned for the 128B swizzle atoms)
@@ -525,12 +552,14 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             tc_fence_after();
             const uint64_t bb = bk_base + (uint64_t)((sl * SLOT_BYTES) >> 4);
             if (elect_one()) {
+              if (prm.debug != 3) {
 #pragma unroll
               for (int ks = 0; ks < KS1; ++ks) {
                 const uint32_t aoff = ((ks >> 2) * WH_CHUNK + (ks & 3) * 32) >> 4;
                 const uint32_t boff = ((ks >> 2) * X_CHUNK + (ks & 3) * 32) >> 4;
                 mma_ss(zcol, a_base + aoff, bb + boff, idesc1, ks > 0 ? 1u : 0u);
                 mma_ts(zcol, tmem + TM_WLO + ks * 8, bb + boff, idesc1, 1u);
+              }
               }
             }
             __syncwarp();
@@ -541,14 +570,16 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             tc_fence_after();
             const uint64_t bb = bk_base + (uint64_t)((sl * SLOT_BYTES) >> 4);
             if (elect_one()) {
+              if (prm.debug != 3) {
 #pragma unroll
               for (int ks = 0; ks < KS1; ++ks) {
                 const uint32_t aoff = ((ks >> 2) * WH_CHUNK + (ks & 3) * 32) >> 4;
                 const uint32_t boff = ((ks >> 2) * X_CHUNK + (ks & 3) * 32) >> 4;
                 mma_ss(zcol, a_base + aoff, bb + boff, idesc1, 1u);
               }
+              }
               tc_commit(&bars->z_full[tc & 1]);
-              if (MODE != TC_FIT) {  // no GEMM2: the ring slots are free once GEMM1 has read them
+              if (!IS_FIT) {  // no GEMM2: the ring slots are free once GEMM1 has read them
                 tc_commit(&bars->empty[hh % TC_NS]);
                 tc_commit(&bars->empty[(hh + 1) % TC_NS]);
               }
@@ -566,21 +597,25 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
           const uint64_t bh = bmn_base + (uint64_t)((sl_h * SLOT_BYTES) >> 4);
           const uint64_t bl = bmn_base + (uint64_t)((sl_l * SLOT_BYTES) >> 4);
           if (elect_one()) {
+            if (prm.debug < 2) {
 #pragma unroll
             for (int ks = 0; ks < TC_R / 16; ++ks) {
               mma_ts(tmem + TM_GRAD, gcol + ks * 16, bh + ks * 128, idesc2, (first_tile && ks == 0) ? 0u : 1u);
               mma_ts(tmem + TM_GRAD, gcol + ks * 16 + 8, bh + ks * 128, idesc2, 1u);
             }
+            }
             tc_commit(&bars->empty[sl_h]);
+            if (prm.debug < 2) {
 #pragma unroll
             for (int ks = 0; ks < TC_R / 16; ++ks)
               mma_ts(tmem + TM_GRAD, gcol + ks * 16, bl + ks * 128, idesc2, 1u);
+            }
             tc_commit(&bars->empty[sl_l]);
           }
           __syncwarp();
         };
 
-        if (MODE == TC_FIT) {
+        if (IS_FIT) {
           if (nt > 0) issue_g1(h, tcount);
           for (int i = 0; i < nt; ++i) {
             if (i + 1 < nt) issue_g1(h + 2 * (i + 1), tcount + i + 1);
@@ -603,12 +638,14 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
     }
   } else {
     // ================================ epilogue warps ========================================
-    // 8 warps: warps w and w+4 share TMEM lane quadrant q = w & 3 and split the tile's four
-    // 16-row chunks between them (hf = 0: chunks 0,1; hf = 1: chunks 2,3).
+    // 16 warps: warps with the same (warp & 3) share TMEM lane quadrant q and take one 16-row
+    // chunk of the tile each (qt = 0..3).  Four warps per scheduler hide the MUFU / TMEM latency;
+    // the per-element instruction count, not the tensor pipe, was the limiter with 8 warps.
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int hf = (warp - 2) >> 2;
+    const int qt = (warp - 2) >> 2;               // 16-row chunk of every tile
     const int lane_in_group = q * 32 + lane;      // slot within the group == TMEM lane
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    constexpr float INV_G = 1.f / GSCALE;
     uint32_t tcount = 0;
     int it_local = 0;
     for (int g = g_first; g <= g_last; ++g, ++it_local) {
@@ -621,11 +658,21 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
       TcSlotParam sp;
       sp.inv_t = 1.f; sp.bias = 0.f; sp.fold = -1; sp.pos = -1;
       if (valid) sp = prm.sp[slot];
+      // fit: work on z / 2^14 so that (row sign * 2^14) * z' = +-z and (row sign * 2^14) * sigma is
+      // the scaled gradient entry; all power-of-two factors, results identical to the unscaled form
+      const float zi = IS_FIT ? sp.inv_t * INV_G : sp.inv_t;
+      const float zb0 = IS_FIT ? sp.bias * INV_G : sp.bias;
+      const float* rsg = nullptr;
+      if (MODE == TC_FIT_UNI) {
+        const int f = prm.sp[g * TC_BC].fold;
+        const int li = (f >= 0 && f < prm.n_lists - 1) ? f : prm.n_lists - 1;
+        rsg = prm.rowsg + (size_t)li * prm.rowsg_ld;
+      }
       {  // W_lo row of this slot -> TMEM (packed fp16 pairs), 16 columns (32 values) at a time.
          // The previous item's MMAs are done with W_lo: its acc_done was waited for below.
         const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.Wl + (size_t)slot * (NCHUNK * 64));
 #pragma unroll 1
-        for (int c16 = hf * NCHUNK; c16 < (hf + 1) * NCHUNK; ++c16) {
+        for (int c16 = qt; c16 < NCHUNK * 2; c16 += 4) {
           uint32_t r[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -645,103 +692,107 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
       for (int i = 0; i < nt; ++i, ++tcount) {
         const int t = tlist ? tlist[t0 + i] : t0 + i;
         const uint32_t zb = tl + TM_Z0 + (tcount & 1) * 64;
-        // row metadata of this warp's 32 rows: issue the loads before waiting for the MMA so
-        // their latency is hidden behind the wait
-        uint32_t rm[32];
+        // per-row data of this warp's 16 rows: issue the loads before waiting for the MMA so their
+        // latency is hidden behind the wait
+        uint32_t rm[16];
         {
-          const uint4* rm4 = reinterpret_cast<const uint4*>(prm.rowmeta + (size_t)t * TC_R + hf * 32);
+          const uint4* rm4 = MODE == TC_FIT_UNI
+                                 ? reinterpret_cast<const uint4*>(rsg + (size_t)t * TC_R + qt * 16)
+                                 : reinterpret_cast<const uint4*>(prm.rowmeta + (size_t)t * TC_R + qt * 16);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             uint4 v = __ldg(rm4 + j);
             rm[4 * j] = v.x; rm[4 * j + 1] = v.y; rm[4 * j + 2] = v.z; rm[4 * j + 3] = v.w;
           }
         }
-        float yv[32];
+        float yv[16];
         if (MODE == TC_R2) {
-          const float4* y4 = reinterpret_cast<const float4*>(prm.yreal + (size_t)t * TC_R + hf * 32);
+          const float4* y4 = reinterpret_cast<const float4*>(prm.yreal + (size_t)t * TC_R + qt * 16);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             float4 v = __ldg(y4 + j);
             yv[4 * j] = v.x; yv[4 * j + 1] = v.y; yv[4 * j + 2] = v.z; yv[4 * j + 3] = v.w;
           }
         }
         mbar_wait(&bars->z_full[tcount & 1], (tcount >> 1) & 1, 300);
         tc_fence_after();
+        if (prm.debug == 4) { tc_fence_before(); mbar_arrive(&bars->g_full[tcount & 1]); continue; }
         float lt = 0.f, gt = 0.f;
         int ok_t = 0, all_t = 0;
+        uint32_t zr[16];
+        tmem_ld16(zb + qt * 16, zr);
+        tmem_wait_ld();
+        if (IS_FIT) {
+          float gv[16];
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int ch = hf * 2 + cc;
-          uint32_t zr[16];
-          tmem_ld16(zb + ch * 16, zr);
-          tmem_wait_ld();
-          if (MODE == TC_FIT) {
-            float gv[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t m = rm[cc * 16 + j];
-              const float z = fmaf(__uint_as_float(zr[j]), sp.inv_t, sp.bias);
+          for (int j = 0; j < 16; ++j) {
+            float sg;                       // -y * 2^14 for a training row, 0 otherwise
+            if (MODE == TC_FIT_UNI) {
+              sg = __uint_as_float(rm[j]);
+            } else {
+              const uint32_t m = rm[j];
               const int fr = (int)(m >> 24);
               const bool yb = (int)(m & 0x00FFFFFFu) == sp.pos;
               const bool train = (fr != 0xFF) && (fr != sp.fold);
-              const float u = yb ? -z : z;
-              const float e = ex2_approx(-fabsf(u) * 1.4426950408889634f);
-              const float s1 = 1.f + e;
-              const float loss = fmaxf(u, 0.f) + lg2_approx(s1) * 0.6931471805599453f;
-              const float r = rcp_approx(s1);
-              const float sig = (u >= 0.f) ? r : e * r;
-              const float gg = yb ? -sig : sig;
-              gv[j] = train ? gg : 0.f;
-              lt += train ? loss : 0.f;
-              gt += gv[j];
+              sg = train ? (yb ? -GSCALE : GSCALE) : 0.f;
             }
-            uint32_t out[16];
+            const float zp = fmaf(__uint_as_float(zr[j]), zi, zb0);
+            const float u = sg * zp;        // = -y * z
+            const float e = ex2_approx(-fabsf(u) * 1.4426950408889634f);
+            const float s1 = 1.f + e;
+            const float loss = fmaf(lg2_approx(s1), 0.6931471805599453f, fmaxf(u, 0.f));
+            const float r = rcp_approx(s1);
+            const float sig = (u >= 0.f) ? r : e * r;
+            gv[j] = sg * sig;               // 2^14 * dloss/dz
+            lt = fmaf(fabsf(sg), loss, lt); // 2^14 * loss
+            gt += gv[j];
+          }
+          uint32_t out[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float a = gv[2 * j] * GSCALE, b = gv[2 * j + 1] * GSCALE;
-              const uint32_t hi = pack_f16x2(a, b);
-              const float2 hf2 = unpack_f16x2(hi);
-              out[j] = hi;
-              out[8 + j] = pack_f16x2(a - hf2.x, b - hf2.y);
-            }
-            tmem_st16(zb + ch * 16, out);
-          } else if (MODE == TC_R2) {
+          for (int j = 0; j < 8; ++j) {
+            const float a = gv[2 * j], b = gv[2 * j + 1];
+            const uint32_t hi = pack_f16x2(a, b);
+            const float2 hf2 = unpack_f16x2(hi);
+            out[j] = hi;
+            out[8 + j] = pack_f16x2(a - hf2.x, b - hf2.y);
+          }
+          tmem_st16(zb + qt * 16, out);
+        } else if (MODE == TC_R2) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t m = rm[cc * 16 + j];
-              const float z = fmaf(__uint_as_float(zr[j]), sp.inv_t, sp.bias);
-              const int fr = (int)(m >> 24);
-              const bool in = (fr != 0xFF) && (sp.fold == -2 || (sp.fold >= 0 && fr == sp.fold) ||
-                                               (sp.fold <= -3 && fr != (-3 - sp.fold)));
-              const float r = yv[cc * 16 + j] - z;
-              lt += in ? r * r : 0.f;
-              all_t += in ? 1 : 0;
-            }
-          } else {
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t m = rm[j];
+            const float z = fmaf(__uint_as_float(zr[j]), zi, zb0);
+            const int fr = (int)(m >> 24);
+            const bool in = (fr != 0xFF) && (sp.fold == -2 || (sp.fold >= 0 && fr == sp.fold) ||
+                                             (sp.fold <= -3 && fr != (-3 - sp.fold)));
+            const float r = yv[j] - z;
+            lt += in ? r * r : 0.f;
+            all_t += in ? 1 : 0;
+          }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const uint32_t m = rm[cc * 16 + j];
-              const float z = fmaf(__uint_as_float(zr[j]), sp.inv_t, sp.bias);
-              const int fr = (int)(m >> 24);
-              const bool yb = (int)(m & 0x00FFFFFFu) == sp.pos;
-              // fold code: f >= 0 rows of fold f; -2 all rows; -3-f rows NOT in fold f
-              const bool in = (fr != 0xFF) && (sp.fold == -2 || (sp.fold >= 0 && fr == sp.fold) ||
-                                               (sp.fold <= -3 && fr != (-3 - sp.fold)));
-              ok_t += (in && ((z > 0.f) == yb)) ? 1 : 0;
-              all_t += in ? 1 : 0;
-            }
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t m = rm[j];
+            const float z = fmaf(__uint_as_float(zr[j]), zi, zb0);
+            const int fr = (int)(m >> 24);
+            const bool yb = (int)(m & 0x00FFFFFFu) == sp.pos;
+            // fold code: f >= 0 rows of fold f; -2 all rows; -3-f rows NOT in fold f
+            const bool in = (fr != 0xFF) && (sp.fold == -2 || (sp.fold >= 0 && fr == sp.fold) ||
+                                             (sp.fold <= -3 && fr != (-3 - sp.fold)));
+            ok_t += (in && ((z > 0.f) == yb)) ? 1 : 0;
+            all_t += in ? 1 : 0;
           }
         }
-        if (MODE == TC_FIT) tmem_wait_st();
+        if (IS_FIT) tmem_wait_st();
         tc_fence_before();
         mbar_arrive(&bars->g_full[tcount & 1]);
         {
           float sl = ls_hi + lt, bb = sl - ls_hi;
           ls_lo += (ls_hi - (sl - bb)) + (lt - bb);
           ls_hi = sl;
-          float sg = gs_hi + gt, cc = sg - gs_hi;
-          gs_lo += (gs_hi - (sg - cc)) + (gt - cc);
-          gs_hi = sg;
+          float sg2 = gs_hi + gt, cc = sg2 - gs_hi;
+          gs_lo += (gs_hi - (sg2 - cc)) + (gt - cc);
+          gs_hi = sg2;
         }
         n_ok += ok_t;
         n_all += all_t;
@@ -749,10 +800,21 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
       // end of item: all MMAs done -> flush
       mbar_wait(&bars->acc_done, it_local & 1, 310);
       tc_fence_after();
-      if (MODE == TC_FIT) {
+      if (IS_FIT || MODE == TC_R2) {
+        // the four warps of a quadrant hold partial sums of the same slots: exchange them through
+        // the (now idle) Z buffer and let warp qt = 0 add them in a fixed order (deterministic)
+        uint32_t v4[4] = {__float_as_uint(ls_hi), __float_as_uint(ls_lo), __float_as_uint(gs_hi),
+                          __float_as_uint(gs_lo)};
+        tmem_st4(tl + TM_Z0 + qt * 4, v4);
+        tmem_wait_st();
+        tc_fence_before();
+        epi_bar_sync();
+        tc_fence_after();
+      }
+      if (IS_FIT) {
         float* dst = prm.gradp + ((size_t)z_part * prm.n_act + slot) * prm.ldw;
 #pragma unroll 1
-        for (int c16 = hf * NCHUNK * 2; c16 < (hf + 1) * NCHUNK * 2; ++c16) {
+        for (int c16 = qt; c16 < NCHUNK * 4; c16 += 4) {
           uint32_t r[16];
           tmem_ld16(tl + TM_GRAD + c16 * 16, r);
           tmem_wait_ld();
@@ -763,16 +825,29 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
                   make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
           }
         }
-        if (valid && nt > 0) {   // the two half-warps of a slot add into the zeroed partial (a + b == b + a)
-          atomicAdd(prm.lossp + (size_t)z_part * prm.n_act + slot, (double)ls_hi + (double)ls_lo);
-          atomicAdd(prm.gsump + (size_t)z_part * prm.n_act + slot, (double)gs_hi + (double)gs_lo);
+      }
+      if ((IS_FIT || MODE == TC_R2) && qt == 0) {
+        uint32_t r[16];
+        tmem_ld16(tl + TM_Z0, r);
+        tmem_wait_ld();
+        double ls = 0.0, gs = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ls += (double)__uint_as_float(r[4 * k]) + (double)__uint_as_float(r[4 * k + 1]);
+          gs += (double)__uint_as_float(r[4 * k + 2]) + (double)__uint_as_float(r[4 * k + 3]);
         }
-      } else if (MODE == TC_R2) {
-        if (valid && n_all > 0) {
-          atomicAdd(prm.lossp + slot, (double)ls_hi + (double)ls_lo);   // sum of squared residuals
-          atomicAdd(prm.count + slot, n_all);
+        if (IS_FIT) {
+          if (valid && nt > 0) {   // partial (z_part, slot) has exactly one writer
+            prm.lossp[(size_t)z_part * prm.n_act + slot] = ls * (double)INV_G;
+            prm.gsump[(size_t)z_part * prm.n_act + slot] = gs * (double)INV_G;
+          }
+        } else if (valid && nt > 0) {
+          atomicAdd(prm.lossp + slot, ls);   // sum of squared residuals (parts add up)
         }
-      } else if (valid && n_all > 0) {
+      }
+      if (MODE == TC_R2) {
+        if (valid && n_all > 0) atomicAdd(prm.count + slot, n_all);
+      } else if (MODE == TC_SCORE && valid && n_all > 0) {
         atomicAdd(prm.correct + slot, n_ok);
         atomicAdd(prm.count + slot, n_all);
       }
@@ -841,6 +916,7 @@ void tc_free(Ctx* c) {
   if (t.yreal_pad) cudaFree(t.yreal_pad);
   if (t.tilelist) cudaFree(t.tilelist);
   if (t.tilecnt) cudaFree(t.tilecnt);
+  if (t.rowsg) cudaFree(t.rowsg);
   if (t.xscale) cudaFree(t.xscale);
   if (t.gscale) cudaFree(t.gscale);
   t = TcData();
@@ -905,6 +981,7 @@ int tc_prepare(Ctx* c) {
       SKD_CUDA(c, cudaMemcpyAsync(t.tilecnt, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice, c->stream));
       SKD_CUDA(c, cudaStreamSynchronize(c->stream));
       t.n_lists = nf + 1;
+      t.rowsg_valid = false;
     }
     if (c->yreal) {
       if (!t.yreal_pad) SKD_CUDA(c, cudaMalloc((void**)&t.yreal_pad, (size_t)npad * sizeof(float)));
@@ -1019,6 +1096,19 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   prm.n_tiles = n_tiles;
   prm.ldw = w.ldw;
   prm.parts = parts;
+  { const char* dbg = getenv("SKDIST_B200_TC_DEBUG"); prm.debug = dbg ? atoi(dbg) : 0; }
+  const bool uni = mode == TC_FIT && w.grouped && w.uni_pos >= 0 && c->ycls;
+  if (uni && (!t.rowsg_valid || t.rowsg_pos != w.uni_pos)) {
+    if (!t.rowsg) SKD_CUDA(c, cudaMalloc((void**)&t.rowsg, (size_t)t.n_lists * t.npad * sizeof(float)));
+    tc_rowsg_kernel<<<(unsigned)((t.npad + 255) / 256), 256, 0, c->stream>>>(c->ycls, c->fold, c->n, t.npad,
+                                                                          t.n_lists, w.uni_pos, t.rowsg);
+    c->launches += 1;
+    SKD_CUDA(c, cudaGetLastError());
+    t.rowsg_pos = w.uni_pos;
+    t.rowsg_valid = true;
+  }
+  prm.rowsg = uni ? t.rowsg : nullptr;
+  prm.rowsg_ld = t.npad;
   const bool lists = mode == TC_FIT && parts > 0 && w.grouped && t.tilelist;
   prm.tilelist = lists ? t.tilelist : nullptr;
   prm.tilecnt = lists ? t.tilecnt : nullptr;
@@ -1027,7 +1117,8 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   const size_t smem = 1024 + (size_t)nchunk * (TC_BC * 128) + (size_t)TC_NS * nchunk * (TC_R * 128) +
                       sizeof(TcBarriers) + 64;
   if (mode == TC_R2 && !t.yreal_pad) return fail(c, "tc_r2: targets not staged");
-  cudaError_t e = mode == TC_FIT ? tc_launch<TC_FIT>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm)
+  cudaError_t e = uni ? tc_launch<TC_FIT_UNI>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm)
+                  : mode == TC_FIT ? tc_launch<TC_FIT>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm)
                   : mode == TC_SCORE ? tc_launch<TC_SCORE>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm)
                                      : tc_launch<TC_R2>(nchunk, grid, smem, c->stream, t.map_xh, t.map_xl, map_wh, prm);
   c->launches += 1;

@@ -25,6 +25,9 @@ struct TcData {
   int32_t* tilelist = nullptr; // [(n_lists) x n_tiles] tiles that contain at least one TRAINING row of fold f
   int32_t* tilecnt = nullptr;  // [n_lists]; list index f for fold f, n_lists-1 = every tile (no held-out fold)
   int n_lists = 0;
+  float* rowsg = nullptr;      // [n_lists x npad] -y * 2^14 per row for positive class rowsg_pos; 0 = not a training row
+  int32_t rowsg_pos = -1;
+  bool rowsg_valid = false;
   float* xscale = nullptr;     // [dpad] power-of-two per-feature scale
   double* gscale = nullptr;    // [dpad] 1 / (xscale * 2^14): un-scales the gradient partials
   int dpad = 0;
@@ -162,6 +165,7 @@ struct LogregWork {
   bool grouped = false;
   int32_t slot_cap = 0;        // slots incl. padding at the start of the solve
   int32_t* n_run = nullptr;    // device scalar: columns still running
+  int32_t uni_pos = -1;        // >= 0: every column of the batch has this positive class (grouped layout only)
 };
 
 // forward (Z = X W^T, pointwise loss / gradient on training rows) + backward (G^T X)
