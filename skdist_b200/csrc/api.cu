@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
+#include <atomic>
+#include <chrono>
 
 #include "../../include/skdist_b200.h"
 #include "skd_internal.h"
@@ -128,12 +131,29 @@ int skd_ctx_create(int device, skd_ctx** out) {
   return 0;
 }
 
+// SKDIST_B200_TRACE=1: host wall-clock per phase of a call (stream synchronised at each mark), to stderr
+struct Trace {
+  Ctx* c; const char* call; bool on; std::chrono::steady_clock::time_point t;
+  Trace(Ctx* c_, const char* call_) : c(c_), call(call_) {
+    const char* e = getenv("SKDIST_B200_TRACE");
+    on = e && *e && *e != '0';
+    t = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(c->stream);
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[skd trace] %s %-10s %9.3f ms\n", call, what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+
 static void free_staged(Ctx& c) {
   if (c.X) cudaFree(c.X);
   if (c.ycls) cudaFree(c.ycls);
   if (c.yreal) cudaFree(c.yreal);
-  if (c.fold) cudaFree(c.fold);
-  c.X = nullptr; c.ycls = nullptr; c.yreal = nullptr; c.fold = nullptr;
+  if (c.fold_store) cudaFree(c.fold_store);
+  c.X = nullptr; c.ycls = nullptr; c.yreal = nullptr; c.fold = nullptr; c.fold_store = nullptr;
 }
 
 int skd_ctx_destroy(skd_ctx* ctx) {
@@ -141,6 +161,10 @@ int skd_ctx_destroy(skd_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   free_staged(ctx->c);
+  for (void* p : ctx->c.pin_bufs) cudaFreeHost(p);
+  ctx->c.pin_bufs.clear();
+  for (auto& b : ctx->c.pool_free) cudaFree(b.first);
+  ctx->c.pool_free.clear();
   tc_free(&ctx->c);
   forest_free(&ctx->c);
   cudaStreamDestroy(ctx->c.stream);
@@ -148,17 +172,100 @@ int skd_ctx_destroy(skd_ctx* ctx) {
   return 0;
 }
 
+// Host -> device copy of an [n x d] fp32 matrix (row pitch ldx_src) into dst (row pitch ldx).
+// Pinned sources go straight to the copy engine.  Pageable sources (plain numpy arrays) would be
+// bounced by the driver through one small internal buffer at a few GB/s; instead T host threads
+// each copy their own row blocks into pinned bounce buffers (double-buffered per thread) and
+// issue the DMA on their own stream, so memcpy and PCIe transfers of different blocks overlap.
+static int stage_rows_h2d(Ctx* c, float* dst, int64_t ldx, const float* src, int64_t n, int64_t d,
+                          int64_t ldx_src) {
+  cudaPointerAttributes attr;
+  bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const size_t total = (size_t)n * d * sizeof(float);
+  if (pinned || total < ((size_t)8 << 20)) {
+    SKD_CUDA(c, cudaMemcpy2DAsync(dst, ldx * sizeof(float), src, ldx_src * sizeof(float), d * sizeof(float), n,
+                                  cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  const int T = 8, NB = 2;
+  const size_t buf_bytes = (size_t)8 << 20;
+  if (c->pin_bufs.size() != (size_t)T * NB || c->pin_bytes != buf_bytes) {
+    for (void* p : c->pin_bufs) cudaFreeHost(p);
+    c->pin_bufs.clear();
+    for (int i = 0; i < T * NB; ++i) {
+      void* p = nullptr;
+      SKD_CUDA(c, cudaHostAlloc(&p, buf_bytes, cudaHostAllocDefault));
+      c->pin_bufs.push_back(p);
+    }
+    c->pin_bytes = buf_bytes;
+  }
+  const int64_t rows_per_blk = std::max<int64_t>(1, (int64_t)(buf_bytes / ((size_t)d * sizeof(float))));
+  const int64_t n_blk = (n + rows_per_blk - 1) / rows_per_blk;
+  std::atomic<int> err_code{0};
+  std::atomic<int64_t> next_blk{0};
+  auto worker = [&](int tid) {
+    if (cudaSetDevice(c->device) != cudaSuccess) { err_code = 1; return; }
+    cudaStream_t st;
+    cudaEvent_t ev[NB];
+    if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { err_code = 1; return; }
+    for (int b = 0; b < NB; ++b) cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+    int used = 0;
+    for (;;) {
+      const int64_t blk = next_blk.fetch_add(1);
+      if (blk >= n_blk || err_code) break;
+      const int b = used % NB;
+      if (used >= NB && cudaEventSynchronize(ev[b]) != cudaSuccess) { err_code = 2; break; }
+      float* pb = (float*)c->pin_bufs[(size_t)tid * NB + b];
+      const int64_t r0 = blk * rows_per_blk, r1 = std::min(n, r0 + rows_per_blk);
+      if (ldx_src == d) {
+        memcpy(pb, src + (size_t)r0 * ldx_src, (size_t)(r1 - r0) * d * sizeof(float));
+      } else {
+        for (int64_t r = r0; r < r1; ++r)
+          memcpy(pb + (size_t)(r - r0) * d, src + (size_t)r * ldx_src, (size_t)d * sizeof(float));
+      }
+      if (cudaMemcpy2DAsync(dst + (size_t)r0 * ldx, ldx * sizeof(float), pb, d * sizeof(float), d * sizeof(float),
+                            (size_t)(r1 - r0), cudaMemcpyHostToDevice, st) != cudaSuccess) { err_code = 3; break; }
+      cudaEventRecord(ev[b], st);
+      ++used;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) err_code = 4;
+    for (int b = 0; b < NB; ++b) cudaEventDestroy(ev[b]);
+    cudaStreamDestroy(st);
+  };
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));   // the memset of the padding (if any) is ordered before the copies
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; ++t) th.emplace_back(worker, t);
+  for (auto& t : th) t.join();
+  if (err_code) {
+    char b[128];
+    snprintf(b, sizeof(b), "skd_stage_x: threaded host-to-device staging failed (step %d): %s", (int)err_code,
+             cudaGetErrorString(cudaGetLastError()));
+    return fail(c, b);
+  }
+  return 0;
+}
+
 static int stage_x_common(Ctx* c, const float* src, int64_t n, int64_t d, int64_t ldx_src,
                           cudaMemcpyKind kind) {
   if (!src || n <= 0 || d <= 0 || ldx_src < d) return fail(c, "skd_stage_x: bad arguments");
   SKD_CUDA(c, cudaSetDevice(c->device));
-  if (c->X) { cudaFree(c->X); c->X = nullptr; }
+  Trace tr(c, "stage_x");
   int64_t ldx = round_up(d, 16);
-  SKD_CUDA(c, cudaMalloc((void**)&c->X, (size_t)n * ldx * sizeof(float)));
+  // keep the device buffer when the shape is unchanged (repeated fits on same-sized data)
+  if (c->X && !(c->n == n && c->ldx == ldx)) { cudaFree(c->X); c->X = nullptr; }
+  if (!c->X) SKD_CUDA(c, cudaMalloc((void**)&c->X, (size_t)n * ldx * sizeof(float)));
   if (ldx != d) SKD_CUDA(c, cudaMemsetAsync(c->X, 0, (size_t)n * ldx * sizeof(float), c->stream));
-  SKD_CUDA(c, cudaMemcpy2DAsync(c->X, ldx * sizeof(float), src, ldx_src * sizeof(float),
-                                d * sizeof(float), n, kind, c->stream));
-  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  tr.mark("alloc");
+  if (kind == cudaMemcpyHostToDevice) {
+    if (stage_rows_h2d(c, c->X, ldx, src, n, d, ldx_src)) return 1;
+  } else {
+    SKD_CUDA(c, cudaMemcpy2DAsync(c->X, ldx * sizeof(float), src, ldx_src * sizeof(float),
+                                  d * sizeof(float), n, kind, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  tr.mark("copy");
   c->n = n; c->d = d; c->ldx = ldx;
   c->tc.x_valid = false;
   c->forest.valid = false;
@@ -181,8 +288,8 @@ int skd_stage_labels(skd_ctx* ctx, const int32_t* y, int64_t n) {
   Ctx* c = &ctx->c;
   if (!y || n != c->n) return fail(c, "skd_stage_labels: n does not match the staged X");
   SKD_CUDA(c, cudaSetDevice(c->device));
-  if (c->ycls) { cudaFree(c->ycls); c->ycls = nullptr; }
-  SKD_CUDA(c, cudaMalloc((void**)&c->ycls, (size_t)n * sizeof(int32_t)));
+  if (c->ycls && c->ycls_cap < n) { cudaFree(c->ycls); c->ycls = nullptr; }
+  if (!c->ycls) { SKD_CUDA(c, cudaMalloc((void**)&c->ycls, (size_t)n * sizeof(int32_t))); c->ycls_cap = n; }
   SKD_CUDA(c, cudaMemcpyAsync(c->ycls, y, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->h2d += n * (int64_t)sizeof(int32_t);
@@ -195,8 +302,8 @@ int skd_stage_targets(skd_ctx* ctx, const float* y, int64_t n) {
   Ctx* c = &ctx->c;
   if (!y || n != c->n) return fail(c, "skd_stage_targets: n does not match the staged X");
   SKD_CUDA(c, cudaSetDevice(c->device));
-  if (c->yreal) { cudaFree(c->yreal); c->yreal = nullptr; }
-  SKD_CUDA(c, cudaMalloc((void**)&c->yreal, (size_t)n * sizeof(float)));
+  if (c->yreal && c->yreal_cap < n) { cudaFree(c->yreal); c->yreal = nullptr; }
+  if (!c->yreal) { SKD_CUDA(c, cudaMalloc((void**)&c->yreal, (size_t)n * sizeof(float))); c->yreal_cap = n; }
   SKD_CUDA(c, cudaMemcpyAsync(c->yreal, y, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->h2d += n * (int64_t)sizeof(float);
@@ -208,7 +315,7 @@ int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_fo
   if (!ctx) return fail(nullptr, "skd_stage_folds: ctx is NULL");
   Ctx* c = &ctx->c;
   SKD_CUDA(c, cudaSetDevice(c->device));
-  if (c->fold) { cudaFree(c->fold); c->fold = nullptr; }
+  c->fold = nullptr;
   c->tc.meta_valid = false;
   c->n_folds = 0;
   c->fold_count.clear();
@@ -222,7 +329,9 @@ int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_fo
     if (f < 0 || f >= n_folds) return fail(c, "skd_stage_folds: fold id out of range");
     c->fold_count[f] += 1;
   }
-  SKD_CUDA(c, cudaMalloc((void**)&c->fold, (size_t)n));
+  if (c->fold_store && c->fold_cap < n) { cudaFree(c->fold_store); c->fold_store = nullptr; }
+  if (!c->fold_store) { SKD_CUDA(c, cudaMalloc((void**)&c->fold_store, (size_t)n)); c->fold_cap = n; }
+  c->fold = c->fold_store;
   SKD_CUDA(c, cudaMemcpyAsync(c->fold, fold_id, (size_t)n, cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   c->n_folds = n_folds;
@@ -284,23 +393,6 @@ int skd_get_counters(skd_ctx* ctx, int64_t* launches, int64_t* h2d, int64_t* d2h
   if (d2h) *d2h = ctx->c.d2h;
   return 0;
 }
-
-// SKDIST_B200_TRACE=1: host wall-clock per phase of a call (stream synchronised at each mark), to stderr
-struct Trace {
-  Ctx* c; const char* call; bool on; std::chrono::steady_clock::time_point t;
-  Trace(Ctx* c_, const char* call_) : c(c_), call(call_) {
-    const char* e = getenv("SKDIST_B200_TRACE");
-    on = e && *e && *e != '0';
-    t = std::chrono::steady_clock::now();
-  }
-  void mark(const char* what) {
-    if (!on) return;
-    cudaStreamSynchronize(c->stream);
-    auto n = std::chrono::steady_clock::now();
-    fprintf(stderr, "[skd trace] %s %-10s %9.3f ms\n", call, what, std::chrono::duration<double, std::milli>(n - t).count());
-    t = n;
-  }
-};
 
 int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t* col_fold,
                          const int32_t* col_pos, int32_t fit_intercept, double tol,

@@ -930,14 +930,16 @@ int tc_prepare(Ctx* c) {
   const int dpad = (d + 63) / 64 * 64;
   const int64_t npad = (n + TC_R - 1) / TC_R * TC_R;
   if (!t.x_valid) {
-    tc_free(c);
-    t.dpad = dpad;
-    t.npad = npad;
-    SKD_CUDA(c, cudaMalloc((void**)&t.Xh, (size_t)npad * dpad * sizeof(__half)));
-    SKD_CUDA(c, cudaMalloc((void**)&t.Xl, (size_t)npad * dpad * sizeof(__half)));
-    SKD_CUDA(c, cudaMalloc((void**)&t.rowmeta, (size_t)npad * sizeof(uint32_t)));
-    SKD_CUDA(c, cudaMalloc((void**)&t.xscale, (size_t)dpad * sizeof(float)));
-    SKD_CUDA(c, cudaMalloc((void**)&t.gscale, (size_t)dpad * sizeof(double)));
+    if (t.Xh && (t.dpad != dpad || t.npad != npad)) tc_free(c);   // same shape restaged: keep the buffers
+    if (!t.Xh) {
+      t.dpad = dpad;
+      t.npad = npad;
+      SKD_CUDA(c, cudaMalloc((void**)&t.Xh, (size_t)npad * dpad * sizeof(__half)));
+      SKD_CUDA(c, cudaMalloc((void**)&t.Xl, (size_t)npad * dpad * sizeof(__half)));
+      SKD_CUDA(c, cudaMalloc((void**)&t.rowmeta, (size_t)npad * sizeof(uint32_t)));
+      SKD_CUDA(c, cudaMalloc((void**)&t.xscale, (size_t)dpad * sizeof(float)));
+      SKD_CUDA(c, cudaMalloc((void**)&t.gscale, (size_t)dpad * sizeof(double)));
+    }
     unsigned int* colmax;
     SKD_CUDA(c, cudaMalloc((void**)&colmax, (size_t)dpad * sizeof(unsigned int)));
     SKD_CUDA(c, cudaMemsetAsync(colmax, 0, (size_t)dpad * sizeof(unsigned int), c->stream));
@@ -980,6 +982,7 @@ int tc_prepare(Ctx* c) {
       SKD_CUDA(c, cudaMemcpyAsync(t.tilelist, hl.data(), hl.size() * 4, cudaMemcpyHostToDevice, c->stream));
       SKD_CUDA(c, cudaMemcpyAsync(t.tilecnt, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice, c->stream));
       SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (t.rowsg && t.n_lists != nf + 1) { cudaFree(t.rowsg); t.rowsg = nullptr; }
       t.n_lists = nf + 1;
       t.rowsg_valid = false;
     }

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "lbfgs_core.h"
@@ -63,12 +64,20 @@ struct Ctx {
   int64_t n = 0, d = 0, ldx = 0;
   int32_t* ycls = nullptr;  // [n]
   float* yreal = nullptr;   // [n]
-  int8_t* fold = nullptr;   // [n]
+  int8_t* fold = nullptr;   // [n]; nullptr = no folds staged (points into fold_store otherwise)
+  int8_t* fold_store = nullptr;
   std::vector<int8_t> h_fold;  // host copy of the fold ids (tile lists for fold-aware tile skipping)
   int32_t n_folds = 0;
   std::vector<int64_t> fold_count;  // rows per fold id
   TcData tc;
   ForestData forest;
+  int64_t ycls_cap = 0, yreal_cap = 0, fold_cap = 0;   // allocated rows of the staged vectors (reused when large enough)
+  // scratch pool: device blocks released by finished calls, reused by the next ones (Scratch below)
+  std::vector<std::pair<void*, size_t>> pool_free;
+  size_t pool_bytes = 0;
+  // pinned bounce buffers for staging pageable host arrays (api.cu: stage_rows_h2d)
+  std::vector<void*> pin_bufs;
+  size_t pin_bytes = 0;
   // counters
   int64_t launches = 0, h2d = 0, d2h = 0;
   // optional per-evaluation timing (bench.py roofline): CUDA events on `stream` around every
@@ -102,18 +111,52 @@ inline int fail(Ctx* c, const std::string& s) {
   } while (0)
 
 // Simple RAII device allocation tied to a stream-ordered free at scope exit.
+// Scratch device memory of one API call.  Blocks come from (and go back to) a per-context pool so
+// that repeated calls (search steps, refits, scoring passes) do not pay cudaMalloc / cudaFree each
+// time; every API call synchronises the stream before returning, so a pooled block is idle.
 struct Scratch {
   Ctx* ctx;
-  std::vector<void*> ptrs;
+  std::vector<std::pair<void*, size_t>> blocks;
   explicit Scratch(Ctx* c) : ctx(c) {}
   ~Scratch() {
-    for (void* p : ptrs) cudaFree(p);
+    for (auto& b : blocks) { ctx->pool_free.push_back(b); ctx->pool_bytes += b.second; }
+    // keep the pool bounded: drop the largest idle blocks beyond 6 GB
+    while (ctx->pool_bytes > ((size_t)6 << 30) && !ctx->pool_free.empty()) {
+      size_t bi = 0;
+      for (size_t i = 1; i < ctx->pool_free.size(); ++i)
+        if (ctx->pool_free[i].second > ctx->pool_free[bi].second) bi = i;
+      cudaFree(ctx->pool_free[bi].first);
+      ctx->pool_bytes -= ctx->pool_free[bi].second;
+      ctx->pool_free.erase(ctx->pool_free.begin() + bi);
+    }
   }
   template <class T>
   cudaError_t alloc(T** out, size_t count) {
+    const size_t need = (count * sizeof(T) + 256 + 511) / 512 * 512;
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < ctx->pool_free.size(); ++i) {
+      const size_t b = ctx->pool_free[i].second;
+      if (b >= need && b <= 2 * need + ((size_t)1 << 20) &&
+          (best == (size_t)-1 || b < ctx->pool_free[best].second))
+        best = i;
+    }
+    if (best != (size_t)-1) {
+      blocks.push_back(ctx->pool_free[best]);
+      ctx->pool_bytes -= ctx->pool_free[best].second;
+      *out = (T*)ctx->pool_free[best].first;
+      ctx->pool_free.erase(ctx->pool_free.begin() + best);
+      return cudaSuccess;
+    }
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, count * sizeof(T) + 256);
-    if (e == cudaSuccess) { ptrs.push_back(p); *out = (T*)p; }
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess && !ctx->pool_free.empty()) {   // out of memory: give the idle blocks back and retry
+      for (auto& b : ctx->pool_free) cudaFree(b.first);
+      ctx->pool_free.clear();
+      ctx->pool_bytes = 0;
+      cudaGetLastError();
+      e = cudaMalloc(&p, need);
+    }
+    if (e == cudaSuccess) { blocks.push_back({p, need}); *out = (T*)p; }
     return e;
   }
 };

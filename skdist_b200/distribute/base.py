@@ -72,3 +72,20 @@ class _ScParamMixin:
         finally:
             if missing:
                 del self.sc
+
+
+def _merged_params(estimator, candidate_params):
+    """Per-candidate parameter dicts (base params overridden by the candidate) without cloning the
+    estimator once per candidate; unknown names raise like ``set_params`` does."""
+    base = estimator.get_params(deep=False)
+    out = []
+    for p in candidate_params:
+        for k in p:
+            if k not in base:
+                raise ValueError("Invalid parameter %r for estimator %s. Valid parameters are: %r."
+                                 % (k, estimator, sorted(base)))
+        q = dict(base)
+        q.update(p)
+        out.append(q)
+    return out
+

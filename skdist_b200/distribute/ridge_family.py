@@ -9,7 +9,7 @@ from collections import defaultdict
 
 import numpy as np
 
-from .base import _clone
+from .base import _clone, _merged_params
 
 _RIDGE_SEARCHABLE = {"alpha", "fit_intercept"}
 
@@ -22,7 +22,7 @@ def _resolve(estimator, params):
 
 
 def _check_ridge(est):
-    p = est.get_params(deep=False)
+    p = est if isinstance(est, dict) else est.get_params(deep=False)
     bad = []
     if p.get("solver", "auto") not in ("auto", "cholesky"):
         bad.append("solver=%r (only 'auto'/'cholesky')" % p["solver"])
@@ -46,7 +46,7 @@ class _RidgeFamily:
                 raise NotImplementedError(
                     "searching Ridge over %s has no device path (searchable: %s)"
                     % (sorted(extra), sorted(_RIDGE_SEARCHABLE)))
-        self.cands = [_check_ridge(_resolve(estimator, p)) for p in candidate_params]
+        self.cands = [_check_ridge(q) for q in _merged_params(estimator, candidate_params)]
         if np.ndim(y) != 1:
             raise NotImplementedError("multi-target Ridge has no device path")
         self.y = np.asarray(y, dtype=np.float32)

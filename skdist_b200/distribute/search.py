@@ -36,7 +36,7 @@ from sklearn.utils.validation import indexable
 
 from .. import parallel
 from ..engine import get_engine
-from .base import _clone, _parse_partitions, _ScParamMixin
+from .base import _clone, _merged_params, _parse_partitions, _ScParamMixin
 from .utils import _check_multimetric_scoring, _num_samples
 from .validation import _check_estimator
 
@@ -88,7 +88,7 @@ def _resolve(estimator, params):
 def _check_logreg(est):
     """Raise unless `est` is a configuration the batched lbfgs kernel path reproduces
     (SK/linear_model/_logistic.py:1355-1593)."""
-    p = est.get_params(deep=False)
+    p = est if isinstance(est, dict) else est.get_params(deep=False)
     bad = []
     if p.get("solver", "lbfgs") != "lbfgs":
         bad.append("solver=%r (only 'lbfgs')" % p["solver"])
@@ -116,7 +116,7 @@ class _LogRegFamily:
 
     def __init__(self, estimator, candidate_params, X, y, scorers):
         self.estimator = estimator
-        self.cands = [_check_logreg(_resolve(estimator, p)) for p in candidate_params]
+        self.cands = [_check_logreg(q) for q in _merged_params(estimator, candidate_params)]
         for p in candidate_params:
             extra = set(p) - _LOGREG_SEARCHABLE
             if extra:

@@ -40,9 +40,13 @@ class Engine:
 
     # -- staging ----------------------------------------------------------------
     def stage_x(self, X):
-        X = np.ascontiguousarray(X, dtype=np.float32)
+        X = np.asarray(X)
+        ok = (X.ndim == 2 and X.dtype == np.float32 and X.shape[1] > 0 and X.strides[1] == 4
+              and X.strides[0] % 4 == 0 and X.strides[0] >= 4 * X.shape[1])
+        if not ok:      # row-strided fp32 views are staged in place; anything else is converted first
+            X = np.ascontiguousarray(X, dtype=np.float32)
         n, d = X.shape
-        check(self._lib.skd_stage_x(self._h, ptr(X), n, d, d), self._h)
+        check(self._lib.skd_stage_x(self._h, ptr(X), n, d, X.strides[0] // 4), self._h)
         self.n, self.d = n, d
 
     def stage_x_device(self, dev_ptr, n, d, ldx=None):

@@ -309,3 +309,20 @@ def test_ovr_sgd_log_loss_on_device(eng):
         assert rel(a, b) <= 3 * envelope
         assert abs(a.intercept_[0] - b.intercept_[0]) <= 1e-3 * max(1.0, abs(b.intercept_[0]))
     assert (ovr.predict(X) != ref.predict(X)).mean() <= 2e-3
+
+
+def test_stage_x_threaded_bounce_path(eng):
+    """Arrays above 8 MB in pageable memory go through the threaded pinned-bounce staging
+    (api.cu: stage_rows_h2d); a row-strided view is staged without a host-side copy.  One-hot
+    coefficient rows read single features back exactly."""
+    rng = np.random.default_rng(3)
+    big = rng.standard_normal((300001, 48)).astype(np.float32)     # 57.6 MB, odd row count
+    for X in (big, big[:, 3:43]):                                   # contiguous, row-strided view
+        eng.stage_x(X)
+        d = X.shape[1]
+        coef = np.zeros((3, d + 1), np.float32)
+        for j, k in enumerate((0, d // 2, d - 1)):
+            coef[j, k] = 1.0
+        out = eng.linear_decision(coef)
+        for j, k in enumerate((0, d // 2, d - 1)):
+            np.testing.assert_array_equal(out[:, j], X[:, k])
