@@ -139,11 +139,26 @@ int skd_linear_r2_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_
                         double* sse_out, int64_t* count_out);
 
 /* Streaming batched inference on NEW host rows: out[i*B + j] = Xnew[i,:].coef_j + intercept_j.
- * Rows are moved in <= 1 GiB chunks, double buffered (H2D of chunk i+1 overlaps the kernel and
- * D2H of chunk i).  gpu_seconds_out: device time of the whole call.
+ * Rows are moved in <= 256 MiB chunks; pageable sources go through a threaded pinned bounce so the
+ * copy engine, not a single host memcpy, sets the pace.  gpu_seconds_out: time of the whole call.
  * ref: replaces skdist/distribute/predict.py:160-179 (pandas_udf around model.predict). */
 int skd_predict_linear(skd_ctx* ctx, const float* Xnew, int64_t m, int64_t d, int64_t ld, int32_t B,
                        const float* coef, float* out, double* gpu_seconds_out);
+
+/* Class-probability inference of a fitted forest on NEW host rows (soft voting):
+ *   proba_out[i*C + c] = (1/n_trees) * sum_t value_t[leaf_t(x_i)][c]
+ * with the trees given as concatenated sklearn `Tree` arrays: node k of tree t lives at index
+ * tree_offset[t] + k of left/right/feature/threshold, its C class fractions at value[(..)*C].
+ * A row goes left iff (double)x[feature] <= threshold (SK/tree/_tree.pyx:960-986); the per-tree
+ * values are added in tree order in float64, i.e. exactly what
+ * RandomForestClassifier.predict_proba computes with n_jobs=1 (SK/ensemble/_forest.py:947-966).
+ * ref: replaces skdist/distribute/predict.py:160-179 for forest models (model.predict[_proba]). */
+int skd_forest_predict(skd_ctx* ctx, const float* Xnew, int64_t m, int64_t d, int64_t ld,
+                       int32_t n_trees, const int64_t* tree_offset, const int32_t* left,
+                       const int32_t* right, const int32_t* feature, const double* threshold,
+                       const double* value, int32_t n_classes, double* proba_out,
+                       double* gpu_seconds_out);
+
 
 /* Decision values out[i*B + j] = X[i,:].coef_j + intercept_j for the staged X (all rows).
  * ref: estimator.decision_function / predict inside scorers (utils.py:45-72) and

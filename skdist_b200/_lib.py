@@ -58,6 +58,8 @@ SYMBOLS = {
                                        _c.c_void_p]),
     "skd_predict_linear": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int64,
                                       _c.c_int32, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_double)]),
+    "skd_forest_predict": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int32]
+                           + [_c.c_void_p] * 6 + [_c.c_int32, _c.c_void_p, _c.POINTER(_c.c_double)]),
     "skd_linear_decision": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p]),
     "skd_set_kernel": (_c.c_int, [_c.c_void_p, _c.c_int32]),
     "skd_profile": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double),

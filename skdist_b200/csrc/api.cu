@@ -935,48 +935,90 @@ int skd_predict_linear(skd_ctx* ctx, const float* Xnew, int64_t m, int64_t d, in
   float* dW;
   SKD_CUDA(c, sx.alloc(&dW, hw.size()));
   SKD_CUDA(c, cudaMemcpyAsync(dW, hw.data(), hw.size() * 4, cudaMemcpyHostToDevice, c->stream));
-  // row chunks of <= 1 GiB, double buffered on two streams so H2D of chunk i+1 overlaps chunk i
-  int64_t rows_per_chunk = std::max<int64_t>(1, ((int64_t)1 << 30) / (ldx * 4));
+  // row chunks of <= 256 MiB: threaded pinned-bounce H2D (stage_rows_h2d), one pass of the kernel,
+  // D2H of the (small) result.  The copy engine is the bottleneck (4*d bytes in per row, 4*B out).
+  int64_t rows_per_chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / (ldx * 4));
   if (rows_per_chunk > m) rows_per_chunk = m;
-  float* dX[2]; float* dO[2];
-  cudaStream_t st[2]; cudaEvent_t ev[2];
-  for (int i = 0; i < 2; ++i) {
-    SKD_CUDA(c, sx.alloc(&dX[i], (size_t)rows_per_chunk * ldx));
-    SKD_CUDA(c, sx.alloc(&dO[i], (size_t)rows_per_chunk * B));
-    SKD_CUDA(c, cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
-    SKD_CUDA(c, cudaEventCreate(&ev[i]));
-    if (ldx != d) SKD_CUDA(c, cudaMemsetAsync(dX[i], 0, (size_t)rows_per_chunk * ldx * 4, c->stream));
-  }
+  float *dX, *dO;
+  SKD_CUDA(c, sx.alloc(&dX, (size_t)rows_per_chunk * ldx));
+  SKD_CUDA(c, sx.alloc(&dO, (size_t)rows_per_chunk * B));
+  if (ldx != d) SKD_CUDA(c, cudaMemsetAsync(dX, 0, (size_t)rows_per_chunk * ldx * 4, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
-  cudaEvent_t t0, t1;
-  SKD_CUDA(c, cudaEventCreate(&t0));
-  SKD_CUDA(c, cudaEventCreate(&t1));
-  SKD_CUDA(c, cudaEventRecord(t0, st[0]));
-  cudaStream_t keep = c->stream;
-  int rc = 0;
-  int k = 0;
-  for (int64_t r0 = 0; r0 < m && !rc; r0 += rows_per_chunk, k ^= 1) {
+  auto w0 = std::chrono::steady_clock::now();
+  for (int64_t r0 = 0; r0 < m; r0 += rows_per_chunk) {
     int64_t mr = std::min(rows_per_chunk, m - r0);
-    cudaError_t e = cudaMemcpy2DAsync(dX[k], ldx * 4, Xnew + r0 * ld, ld * 4, d * 4, mr, cudaMemcpyHostToDevice, st[k]);
-    if (e != cudaSuccess) { rc = fail(c, cudaGetErrorString(e)); break; }
-    c->stream = st[k];
-    rc = predict_device(c, dX[k], mr, (int)ldx, (int)d, B, dW, dO[k]);
-    c->stream = keep;
-    if (rc) break;
-    e = cudaMemcpyAsync(out + r0 * B, dO[k], (size_t)mr * B * 4, cudaMemcpyDeviceToHost, st[k]);
-    if (e != cudaSuccess) { rc = fail(c, cudaGetErrorString(e)); break; }
+    if (stage_rows_h2d(c, dX, ldx, Xnew + r0 * ld, mr, d, ld)) return 1;
+    if (predict_device(c, dX, mr, (int)ldx, (int)d, B, dW, dO)) return 1;
+    SKD_CUDA(c, cudaMemcpyAsync(out + r0 * B, dO, (size_t)mr * B * 4, cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
     c->h2d += mr * d * 4;
     c->d2h += mr * (int64_t)B * 4;
   }
-  for (int i = 0; i < 2; ++i) cudaStreamSynchronize(st[i]);
-  cudaEventRecord(t1, st[0]);
-  cudaEventSynchronize(t1);
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, t0, t1);
-  if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
-  for (int i = 0; i < 2; ++i) { cudaStreamDestroy(st[i]); cudaEventDestroy(ev[i]); }
-  cudaEventDestroy(t0); cudaEventDestroy(t1);
-  return rc;
+  if (gpu_seconds_out)
+    *gpu_seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+  return 0;
+}
+
+int skd_forest_predict(skd_ctx* ctx, const float* Xnew, int64_t m, int64_t d, int64_t ld,
+                       int32_t n_trees, const int64_t* tree_offset, const int32_t* left,
+                       const int32_t* right, const int32_t* feature, const double* threshold,
+                       const double* value, int32_t n_classes, double* proba_out,
+                       double* gpu_seconds_out) {
+  if (!ctx) return fail(nullptr, "skd_forest_predict: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!Xnew || m <= 0 || d <= 0 || ld < d || n_trees <= 0 || !tree_offset || !left || !right || !feature ||
+      !threshold || !value || n_classes <= 0 || !proba_out)
+    return fail(c, "skd_forest_predict: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  const int64_t total = tree_offset[n_trees];
+  if (tree_offset[0] != 0 || total <= 0) return fail(c, "skd_forest_predict: tree_offset must start at 0 and increase");
+  // validate the tree arrays once on the host: a malformed child or feature index must not become
+  // an out-of-bounds device read
+  std::vector<int32_t> hnode((size_t)total * 4);
+  for (int t = 0; t < n_trees; ++t) {
+    const int64_t b = tree_offset[t], e = tree_offset[t + 1];
+    if (e <= b) return fail(c, "skd_forest_predict: empty tree");
+    for (int64_t k = b; k < e; ++k) {
+      const int32_t l = left[k], r = right[k], f = feature[k];
+      if (l != -1 && (l <= 0 || l >= e - b || r <= 0 || r >= e - b || f < 0 || f >= d))
+        return fail(c, "skd_forest_predict: malformed tree arrays");
+      hnode[(size_t)k * 4] = l; hnode[(size_t)k * 4 + 1] = r; hnode[(size_t)k * 4 + 2] = l == -1 ? 0 : f;
+      hnode[(size_t)k * 4 + 3] = 0;
+    }
+  }
+  Scratch sx(c);
+  int64_t* d_off; int32_t* d_node; double *d_thr, *d_val;
+  SKD_CUDA(c, sx.alloc(&d_off, (size_t)n_trees + 1));
+  SKD_CUDA(c, sx.alloc(&d_node, (size_t)total * 4));
+  SKD_CUDA(c, sx.alloc(&d_thr, (size_t)total));
+  SKD_CUDA(c, sx.alloc(&d_val, (size_t)total * n_classes));
+  SKD_CUDA(c, cudaMemcpyAsync(d_off, tree_offset, ((size_t)n_trees + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(d_node, hnode.data(), hnode.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(d_thr, threshold, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+  SKD_CUDA(c, cudaMemcpyAsync(d_val, value, (size_t)total * n_classes * 8, cudaMemcpyHostToDevice, c->stream));
+  c->h2d += total * (int64_t)(16 + 8 + 8 * n_classes);
+  const int64_t ldx = round_up(d, 4);
+  int64_t rows_per_chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / (ldx * 4));
+  if (rows_per_chunk > m) rows_per_chunk = m;
+  float* dX; double* dO;
+  SKD_CUDA(c, sx.alloc(&dX, (size_t)rows_per_chunk * ldx));
+  SKD_CUDA(c, sx.alloc(&dO, (size_t)rows_per_chunk * n_classes));
+  if (ldx != d) SKD_CUDA(c, cudaMemsetAsync(dX, 0, (size_t)rows_per_chunk * ldx * 4, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  auto w0 = std::chrono::steady_clock::now();
+  for (int64_t r0 = 0; r0 < m; r0 += rows_per_chunk) {
+    const int64_t mr = std::min(rows_per_chunk, m - r0);
+    if (stage_rows_h2d(c, dX, ldx, Xnew + r0 * ld, mr, d, ld)) return 1;
+    if (forest_predict_device(c, dX, mr, (int)ldx, n_trees, d_off, d_node, d_thr, d_val, n_classes, dO)) return 1;
+    SKD_CUDA(c, cudaMemcpyAsync(proba_out + r0 * n_classes, dO, (size_t)mr * n_classes * 8, cudaMemcpyDeviceToHost,
+                                c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h2d += mr * d * 4;
+    c->d2h += mr * (int64_t)n_classes * 8;
+  }
+  if (gpu_seconds_out)
+    *gpu_seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
+  return 0;
 }
 
 int skd_linear_decision(skd_ctx* ctx, int32_t B, const float* coef, float* out) {

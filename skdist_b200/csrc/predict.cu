@@ -64,4 +64,71 @@ int predict_device(Ctx* c, const float* dX, int64_t m, int ldx, int d, int B, co
   return 0;
 }
 
+// ---- forest inference ----------------------------------------------------------------------
+// One thread per row walks every tree from its root (children_left == -1 marks a leaf) and adds
+// the leaf's class fractions in tree order (float64).  The walk is a chain of dependent loads of
+// 16-byte node records; rows are independent, so thousands of walks are in flight per SM and the
+// top levels of every tree stay in L2.
+struct __align__(16) FNode {
+  int32_t left, right, feature, pad;
+};
+
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+forest_predict_kernel(const float* __restrict__ X, int64_t m, int ldx, int n_trees,
+                      const int64_t* __restrict__ tree_offset, const FNode* __restrict__ node,
+                      const double* __restrict__ threshold, const double* __restrict__ value, int C,
+                      double* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  const float* x = X + r * ldx;
+  double acc[CMAX > 0 ? CMAX : 1];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) acc[c] = 0.0;
+  for (int t = 0; t < n_trees; ++t) {
+    const int64_t base = tree_offset[t];
+    int64_t k = base;
+    FNode nd = node[k];
+    while (nd.left != -1) {
+      const double v = (double)__ldg(x + nd.feature);
+      k = base + (v <= threshold[k] ? nd.left : nd.right);
+      nd = node[k];
+    }
+    const double* val = value + k * C;
+    if (CMAX > 0) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) acc[c] += val[c];
+    } else {
+      for (int c = 0; c < C; ++c) out[r * C + c] += val[c];   // many classes: accumulate in place (zeroed by the host)
+    }
+  }
+  if (CMAX > 0) {
+    const double inv = (double)n_trees;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) out[r * C + c] = acc[c] / inv;
+  } else {
+    for (int c = 0; c < C; ++c) out[r * C + c] /= (double)n_trees;
+  }
+}
+
+int forest_predict_device(Ctx* c, const float* dX, int64_t m, int ldx, int n_trees, const int64_t* d_off,
+                          const void* d_node, const double* d_thr, const double* d_val, int C, double* d_out) {
+  if (m <= 0) return 0;
+  const unsigned grid = (unsigned)((m + 255) / 256);
+  const FNode* nd = (const FNode*)d_node;
+  if (C <= 2) forest_predict_kernel<2><<<grid, 256, 0, c->stream>>>(dX, m, ldx, n_trees, d_off, nd, d_thr, d_val, C, d_out);
+  else if (C <= 8) forest_predict_kernel<8><<<grid, 256, 0, c->stream>>>(dX, m, ldx, n_trees, d_off, nd, d_thr, d_val, C, d_out);
+  else if (C <= 32) forest_predict_kernel<32><<<grid, 256, 0, c->stream>>>(dX, m, ldx, n_trees, d_off, nd, d_thr, d_val, C, d_out);
+  else {
+    cudaMemsetAsync(d_out, 0, (size_t)m * C * sizeof(double), c->stream);
+    forest_predict_kernel<0><<<grid, 256, 0, c->stream>>>(dX, m, ldx, n_trees, d_off, nd, d_thr, d_val, C, d_out);
+  }
+  c->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, std::string("forest predict launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 }  // namespace skd

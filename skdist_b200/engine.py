@@ -260,6 +260,26 @@ class Engine:
         self.last_predict_seconds = secs.value
         return out
 
+    def forest_predict(self, Xnew, tree_offset, left, right, feature, threshold, value):
+        """Soft-vote forest inference on NEW host rows: [m, C] float64 mean of the leaf values of
+        every tree (class fractions for classifiers, C = 1 for regressors)."""
+        Xnew = np.ascontiguousarray(Xnew, dtype=np.float32)
+        m, d = Xnew.shape
+        off = np.ascontiguousarray(tree_offset, dtype=np.int64)
+        left = np.ascontiguousarray(left, dtype=np.int32)
+        right = np.ascontiguousarray(right, dtype=np.int32)
+        feature = np.ascontiguousarray(feature, dtype=np.int32)
+        threshold = np.ascontiguousarray(threshold, dtype=np.float64)
+        value = np.ascontiguousarray(value, dtype=np.float64)
+        C = value.shape[1]
+        out = np.empty((m, C), dtype=np.float64)
+        secs = ctypes.c_double(0.0)
+        check(self._lib.skd_forest_predict(self._h, ptr(Xnew), m, d, d, len(off) - 1, ptr(off), ptr(left),
+                                           ptr(right), ptr(feature), ptr(threshold), ptr(value), C, ptr(out),
+                                           ctypes.byref(secs)), self._h)
+        self.last_predict_seconds = secs.value
+        return out
+
     def linear_decision(self, coef):
         coef = np.ascontiguousarray(coef, dtype=np.float32)
         B = coef.shape[0]

@@ -110,3 +110,29 @@ class FakeEngine:
 
     def linear_decision(self, coef):
         return (self.X @ coef[:, :self.d].T + coef[:, self.d][None, :]).astype(np.float32)
+
+    def predict_linear(self, Xnew, coef):
+        Xnew = np.asarray(Xnew, dtype=np.float32)
+        coef = np.asarray(coef, dtype=np.float32)
+        return (Xnew @ coef[:, :-1].T + coef[:, -1]).astype(np.float32)
+
+    def forest_predict(self, Xnew, tree_offset, left, right, feature, threshold, value):
+        """numpy walk of the concatenated tree arrays (test double of skd_forest_predict)."""
+        Xnew = np.asarray(Xnew, dtype=np.float32)
+        m = Xnew.shape[0]
+        out = np.zeros((m, value.shape[1]))
+        n_trees = len(tree_offset) - 1
+        for t in range(n_trees):
+            base = int(tree_offset[t])
+            node = np.zeros(m, dtype=np.int64)
+            active = np.ones(m, dtype=bool)
+            while True:
+                k = base + node
+                active = left[k] != -1
+                if not active.any():
+                    break
+                go_left = Xnew[np.arange(m), feature[k]].astype(np.float64) <= threshold[k]
+                nxt = np.where(go_left, left[k], right[k])
+                node = np.where(active, nxt, node)
+            out += value[base + node]
+        return out / n_trees

@@ -57,3 +57,25 @@ def test_forest_hyperparameters_and_toy_case():
     rfc = DistRandomForestClassifier(n_estimators=10, random_state=5).fit(Xt, yt)
     assert np.allclose(rfc.predict(Xt), np.array([0, 1, 0]))
     assert_same_forest(rfc, RandomForestClassifier(n_estimators=10, random_state=5).fit(Xt, yt))
+
+
+def test_forest_inference_kernel_matches_sklearn():
+    """skd_forest_predict (soft vote over the Tree arrays, float64 sums in tree order) equals
+    RandomForest*.predict_proba / predict bit for bit — for sklearn-built forests with continuous
+    features too (inference does not need the <= 256-level restriction of the builder)."""
+    from sklearn.ensemble import ExtraTreesClassifier, RandomForestClassifier, RandomForestRegressor
+    from skdist.distribute.predict import batch_predict, get_prediction_udf
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((20000, 12)).astype(np.float32)
+    y = (X[:, 0] + X[:, 1] * X[:, 2] + 0.3 * rng.standard_normal(20000) > 0).astype(int) + (X[:, 3] > 1)
+    Xt = rng.standard_normal((50001, 12)).astype(np.float32)
+    for model in (RandomForestClassifier(n_estimators=12, random_state=2).fit(X, y),
+                  ExtraTreesClassifier(n_estimators=6, max_depth=9, random_state=2).fit(X, y)):
+        np.testing.assert_array_equal(batch_predict(model, Xt, "predict_proba"), model.predict_proba(Xt))
+        np.testing.assert_array_equal(batch_predict(model, Xt, "predict"), model.predict(Xt))
+    reg = RandomForestRegressor(n_estimators=9, random_state=3).fit(X, X[:, 0] * 2 + X[:, 4])
+    np.testing.assert_allclose(batch_predict(reg, Xt), reg.predict(Xt), rtol=0, atol=1e-12)
+    import pandas as pd
+    udf = get_prediction_udf(model, method="predict_proba")
+    out = udf(*[pd.Series(Xt[:100, j]) for j in range(12)])
+    np.testing.assert_array_equal(np.vstack(out.values), model.predict_proba(Xt[:100]))

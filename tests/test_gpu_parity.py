@@ -326,3 +326,24 @@ def test_stage_x_threaded_bounce_path(eng):
         out = eng.linear_decision(coef)
         for j, k in enumerate((0, d // 2, d - 1)):
             np.testing.assert_array_equal(out[:, j], X[:, k])
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_batch_predict_linear_models(eng):
+    """skdist.distribute.predict on the device: labels equal scikit-learn's, probabilities within
+    fp32 rounding of the decision values."""
+    from sklearn.linear_model import SGDClassifier
+    from sklearn.multiclass import OneVsRestClassifier
+    from skdist.distribute.predict import batch_predict
+    from skdist_b200.datasets import make_multiclass
+    X, y = make_multiclass(30000, 24, 5, seed=9)
+    for model in (LogisticRegression(max_iter=300).fit(X, y), LogisticRegression().fit(X, y == 2),
+                  SGDClassifier(loss="log_loss", random_state=0).fit(X, y),
+                  OneVsRestClassifier(LogisticRegression()).fit(X, y)):
+        dec = np.asarray(model.decision_function(X), dtype=np.float64)
+        margin = np.abs(dec) if dec.ndim == 1 else np.sort(dec, axis=1)[:, -1] - np.sort(dec, axis=1)[:, -2]
+        clear = margin > 1e-4          # rows whose label does not hinge on the last fp32 bits of the dot product
+        pred = batch_predict(model, X, "predict")
+        np.testing.assert_array_equal(pred[clear], model.predict(X)[clear])
+        assert clear.mean() > 0.999
+        np.testing.assert_allclose(batch_predict(model, X, "predict_proba"), model.predict_proba(X), rtol=0, atol=2e-5)
