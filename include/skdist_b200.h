@@ -114,10 +114,13 @@ int skd_sgd_fit_batch(skd_ctx* ctx, int32_t B, const int32_t* col_pos, int32_t l
                       int32_t n_iter_no_change, float* coef_out, double* intercept_out,
                       int32_t* n_iter_out, double* t_out, int32_t* status_out, double* gpu_seconds_out);
 
-/* Random-forest classifier trees, one persistent CTA per tree (depth-first, exact scikit-learn
+/* Forest classifier trees, one persistent CTA per tree (depth-first, exact scikit-learn
  * splitter semantics on <= 256 distinct values per feature).  sample_counts[t*n + i] is the
- * bootstrap multiplicity of row i in tree t (the reference's sample_weight, uint8), rand_states[t]
- * the splitter's xorshift seed; both are derived by the host exactly as the reference does.
+ * bootstrap multiplicity of row i in tree t (the reference's sample_weight, uint8; NULL = no
+ * bootstrap, every row once), rand_states[t] the splitter's xorshift seed; both are derived by the
+ * host exactly as the reference does.  splitter: 0 = best split of the drawn features
+ * (RandomForest, SK/tree/_splitter.pyx:262-504), 1 = one uniformly drawn threshold per drawn
+ * feature (ExtraTrees, node_split_random :507-736).
  * Trees come back through an opaque handle: sizes first, then caller-allocated arrays.
  * ref: replaces n_trees invocations of ensemble.py:68-109 (_build_trees -> tree.fit):
  * SK/tree/_tree.pyx:139-337, SK/tree/_splitter.pyx:262-504, SK/tree/_criterion.pyx:605-680. */
@@ -125,7 +128,7 @@ typedef struct skd_forest skd_forest;
 int skd_forest_fit(skd_ctx* ctx, int32_t n_trees, const uint8_t* sample_counts, const uint32_t* rand_states,
                    int32_t n_classes, int32_t max_features, int32_t max_depth, int32_t min_samples_split,
                    int32_t min_samples_leaf, double min_weight_leaf, double min_impurity_decrease,
-                   skd_forest** out, double* gpu_seconds_out);
+                   int32_t splitter, skd_forest** out, double* gpu_seconds_out);
 int skd_forest_tree_size(skd_forest* f, int32_t tree, int32_t* node_count, int32_t* max_depth);
 int skd_forest_tree_copy(skd_forest* f, int32_t tree, int32_t* left, int32_t* right, int32_t* feature,
                          double* threshold, double* impurity, int32_t* n_node_samples,

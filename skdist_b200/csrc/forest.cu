@@ -39,6 +39,7 @@ struct FoRecord {          // builder stack record (SK/tree/_tree.pyx StackRecor
 struct FoItem {            // one speculatively drawn feature + the simulation state right after its draw
   int f, fj, nv, nd, fi, ulen;
   uint32_t rs;
+  uint32_t rnd;            // random splitter: the rand_r value that rand_uniform turns into the threshold
 };
 struct FoResult {          // best split of one feature in the current node
   int is_const, pos, bin;
@@ -55,6 +56,7 @@ struct FoParams {
   int64_t n;
   int d, n_classes;
   int max_features, max_depth, min_samples_split, min_samples_leaf;
+  int random_split;           // 0: node_split_best (RandomForest), 1: node_split_random (ExtraTrees)
   double min_weight_leaf, min_impurity_decrease;
   // per tree (wave-local index = blockIdx.x)
   const uint8_t* counts;      // [trees_in_wave][n] bootstrap multiplicities (sample_weight)
@@ -238,6 +240,9 @@ forest_build_kernel(const FoParams P) {
             s_fi -= 1;          // speculative: not constant
             { const int t = features[s_fi]; features[s_fi] = features[fj]; features[fj] = t; }
             undo[ulen++] = make_int2(s_fi, fj);
+            // node_split_random draws the threshold of a non-constant feature from the same stream
+            // right after the feature (SK/tree/_splitter.pyx:633-637)
+            if (P.random_split) items[nbatch].rnd = fo_rand_r(&s_rs);
             nbatch += 1;
           }
           s_ctrl[0] = nbatch;
@@ -300,6 +305,56 @@ forest_build_kernel(const FoParams P) {
           const int mylast = pmask ? lane * 8 + 31 - __clz(pmask) : -1;
           const int glast = __reduce_max_sync(0xffffffffu, mylast);
           const bool is_const = bv[glast] <= bv[gfirst] + FEATURE_THRESHOLD;
+          if (P.random_split) {
+            // one candidate per feature: threshold = rand_uniform(min, max) (SK/tree/_utils.pyx:57-61),
+            // samples with (double)value <= threshold go left (DensePartitioner.partition_samples)
+            FoResult* R = &results[k];
+            double thr = 0.0;
+            unsigned nl_lane = 0;
+            unsigned long long sl[FO_MAXC];
+            for (int c = 0; c < C; ++c) sl[c] = 0;
+            int nin = 0;
+            if (!is_const) {
+              const double lo = (double)bv[gfirst], hi = (double)bv[glast];
+              thr = __dadd_rn(__ddiv_rn(__dmul_rn(__dsub_rn(hi, lo), (double)items[k].rnd), 2147483647.0), lo);
+              if (thr == hi) thr = lo;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int bb = lane * 8 + j;
+                if ((double)bv[bb] <= thr) {
+                  nin += 1;
+                  nl_lane += cntb[j];
+                  for (int c = 0; c < C; ++c) sl[c] += H[c * FO_BINS + bb];
+                }
+              }
+            }
+            const unsigned n_left_u = __reduce_add_sync(0xffffffffu, nl_lane);
+            const int cutbin = (int)__reduce_add_sync(0xffffffffu, (unsigned)nin) - 1;
+            for (int c = 0; c < C; ++c) {
+              unsigned long long v = sl[c];
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              sl[c] = v;
+            }
+            if (lane == 0) {
+              R->is_const = is_const; R->proxy = -INFINITY; R->pos = end; R->bin = cutbin; R->thr = thr;
+              if (!is_const) {
+                const int n_left = (int)n_left_u, n_right = n_node - n_left;
+                if (n_left >= P.min_samples_leaf && n_right >= P.min_samples_leaf) {
+                  double wl = 0.0;
+                  for (int c = 0; c < C; ++c) wl += (double)sl[c];
+                  const double wr = w_node - wl;
+                  if (!(wl < P.min_weight_leaf || wr < P.min_weight_leaf)) {
+                    double il, ir;
+                    fo_children_impurity(sl, rec.sums, C, wl, wr, &il, &ir);
+                    R->proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
+                    R->pos = start + n_left; R->il = il; R->ir = ir;
+                    for (int c = 0; c < C; ++c) R->sl[c] = sl[c];
+                  }
+                }
+              }
+            }
+            continue;
+          }
           // candidates of this lane in ascending bin order
           double bproxy = -INFINITY, bil = 0.0, bir = 0.0;
           int bpos = 1 << 30, bbin = -1, bnext = -1;
@@ -580,7 +635,8 @@ int forest_prepare(Ctx* c) {
 // rand_states: [n_trees] splitter seeds.  Results are delivered tree by tree through `sink`.
 int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_states, int n_classes,
                int max_features, int max_depth, int min_samples_split, int min_samples_leaf,
-               double min_weight_leaf, double min_impurity_decrease, ForestSink sink, void* sink_arg) {
+               double min_weight_leaf, double min_impurity_decrease, int random_split, ForestSink sink,
+               void* sink_arg) {
   if (forest_prepare(c)) return 1;
   if (n_classes < 1 || n_classes > FO_MAXC) return fail(c, "forest: device path supports up to 16 classes");
   if (!c->ycls) return fail(c, "forest: stage labels first");
@@ -623,6 +679,7 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   P.max_features = max_features; P.max_depth = max_depth; P.min_samples_split = min_samples_split;
   P.min_samples_leaf = min_samples_leaf; P.min_weight_leaf = min_weight_leaf;
   P.min_impurity_decrease = min_impurity_decrease;
+  P.random_split = random_split ? 1 : 0;
   P.counts = dcounts; P.rand_state = drs; P.stack_cap = stack_cap; P.node_cap = node_cap;
   const size_t smem = (size_t)2 * d * sizeof(int) + (size_t)(d + 16) * sizeof(int2);
   std::vector<int32_t> hcount(slots), hdepth(slots), hstatus(slots);
@@ -630,7 +687,11 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   std::vector<int32_t> hl, hr, hf, hn; std::vector<uint8_t> hm; std::vector<double> ht, hi, hw, hv;
   for (int t0 = 0; t0 < n_trees; t0 += slots) {
     const int nt = std::min(slots, n_trees - t0);
-    SKD_CUDA(c, cudaMemcpyAsync(dcounts, counts + (size_t)t0 * n, (size_t)nt * n, cudaMemcpyHostToDevice, c->stream));
+    if (counts) {
+      SKD_CUDA(c, cudaMemcpyAsync(dcounts, counts + (size_t)t0 * n, (size_t)nt * n, cudaMemcpyHostToDevice, c->stream));
+    } else {   // no bootstrap: every row once
+      SKD_CUDA(c, cudaMemsetAsync(dcounts, 1, (size_t)nt * n, c->stream));
+    }
     SKD_CUDA(c, cudaMemcpyAsync(drs, rand_states + t0, (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
     c->h2d += (int64_t)nt * n;
     P.n_trees = nt;

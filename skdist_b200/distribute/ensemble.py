@@ -12,8 +12,8 @@ the tree structure is bit-identical under a fixed `random_state`.
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
-from sklearn.ensemble import RandomForestClassifier
-from sklearn.tree import DecisionTreeClassifier
+from sklearn.ensemble import ExtraTreesClassifier, RandomForestClassifier
+from sklearn.tree import DecisionTreeClassifier, ExtraTreeClassifier
 from sklearn.tree._tree import NODE_DTYPE, Tree
 from sklearn.utils import check_random_state
 
@@ -22,7 +22,7 @@ from ..engine import get_engine
 from .base import _parse_partitions, _ScParamMixin
 from .validation import _check_estimator
 
-__all__ = ["DistRandomForestClassifier"]
+__all__ = ["DistRandomForestClassifier", "DistExtraTreesClassifier"]
 
 MAX_RAND_SEED = np.iinfo(np.int32).max     # ref ensemble.py:38
 RAND_R_MAX = 2147483647                    # SK/tree/_utils.pxd
@@ -43,9 +43,10 @@ def _tree_inputs(state, n_samples, bootstrap):
     return counts, np.uint32(rand_r_state)
 
 
-def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, max_features_):
-    """A fitted DecisionTreeClassifier holding the device-built tree (same attributes as
-    SK/tree/_classes.py:_fit leaves behind)."""
+def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, max_features_,
+                       tree_cls=DecisionTreeClassifier):
+    """A fitted DecisionTreeClassifier / ExtraTreeClassifier holding the device-built tree (same
+    attributes as SK/tree/_classes.py:_fit leaves behind)."""
     m = arrays["left"].shape[0]
     nodes = np.zeros(m, dtype=NODE_DTYPE)
     nodes["left_child"] = arrays["left"]
@@ -59,7 +60,7 @@ def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, ma
     t = Tree(n_features, np.array([n_classes], dtype=np.intp), 1)
     t.__setstate__({"max_depth": int(arrays["max_depth"]), "node_count": m, "nodes": nodes,
                     "values": np.ascontiguousarray(arrays["value"].reshape(m, 1, n_classes))})
-    est = DecisionTreeClassifier(**template_params)
+    est = tree_cls(**template_params)
     est.set_params(random_state=int(state))
     est.n_features_in_ = n_features
     est.n_outputs_ = 1
@@ -70,15 +71,17 @@ def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, ma
     return est
 
 
-class DistRandomForestClassifier(_ScParamMixin, RandomForestClassifier):
-    """Same as sklearn `RandomForestClassifier` with every tree built on a B200.
-    Constructor mirrors ref ensemble.py:378-422 (``sc`` is the FIRST positional argument)."""
+class _DistForestClassifier(_ScParamMixin):
+    """Shared fit of the forest classifiers (ref DistBaseForest.fit, ensemble.py:177-336).
+    Subclasses set `_splitter` (0 best / 1 random) and `_tree_cls`."""
 
-    def __init__(self, sc=None, partitions="auto", n_estimators=100, criterion="gini", max_depth=None,
-                 min_samples_split=2, min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
-                 max_leaf_nodes=None, min_impurity_decrease=0.0, min_impurity_split=None, bootstrap=True,
-                 oob_score=False, n_jobs=None, random_state=None, verbose=0, warm_start=False,
-                 class_weight=None):
+    _splitter = 0
+    _tree_cls = DecisionTreeClassifier
+
+    def _init_params(self, sc, partitions, n_estimators, criterion, max_depth, min_samples_split,
+                     min_samples_leaf, min_weight_fraction_leaf, max_features, max_leaf_nodes,
+                     min_impurity_decrease, min_impurity_split, bootstrap, oob_score, n_jobs, random_state,
+                     verbose, warm_start, class_weight):
         self.sc = sc
         self.partitions = partitions
         self.n_estimators = n_estimators
@@ -102,7 +105,7 @@ class DistRandomForestClassifier(_ScParamMixin, RandomForestClassifier):
         self.ccp_alpha = 0.0
         self.max_samples = None
         self.monotonic_cst = None
-        self.estimator = DecisionTreeClassifier()
+        self.estimator = self._tree_cls()
         self.estimator_params = ("criterion", "max_depth", "min_samples_split", "min_samples_leaf",
                                  "min_weight_fraction_leaf", "max_features", "max_leaf_nodes",
                                  "min_impurity_decrease", "random_state", "ccp_alpha", "monotonic_cst")
@@ -178,15 +181,19 @@ class DistRandomForestClassifier(_ScParamMixin, RandomForestClassifier):
         my_states = [states[i] for i in mine]
         with ThreadPoolExecutor(max_workers=16) as ex:
             inputs = list(ex.map(lambda s: _tree_inputs(s, n, self.bootstrap), my_states))
-        counts = np.stack([c for c, _ in inputs]) if inputs else np.zeros((0, n), np.uint8)
+        counts = None
+        if self.bootstrap:
+            counts = np.stack([c for c, _ in inputs]) if inputs else np.zeros((0, n), np.uint8)
         rs = np.array([r for _, r in inputs], dtype=np.uint32)
-        arrays = eng.forest_fit(counts, rs, self.n_classes_, mf_i, max_depth, int(mss), int(msl),
-                                float(min_weight_leaf), float(self.min_impurity_decrease)) if len(mine) else []
+        arrays = eng.forest_fit(counts if self.bootstrap else None, rs, self.n_classes_, mf_i, max_depth, int(mss),
+                                int(msl), float(min_weight_leaf), float(self.min_impurity_decrease),
+                                splitter=self._splitter) if len(mine) else []
         tmpl = dict(criterion=self.criterion, max_depth=self.max_depth, min_samples_split=self.min_samples_split,
                     min_samples_leaf=self.min_samples_leaf, min_weight_fraction_leaf=self.min_weight_fraction_leaf,
                     max_features="sqrt" if self.max_features == "auto" else self.max_features,
                     max_leaf_nodes=self.max_leaf_nodes, min_impurity_decrease=self.min_impurity_decrease)
-        local = [_make_sklearn_tree(tmpl, s, a, d, self.n_classes_, mf_i) for s, a in zip(my_states, arrays)]
+        local = [_make_sklearn_tree(tmpl, s, a, d, self.n_classes_, mf_i, self._tree_cls)
+                 for s, a in zip(my_states, arrays)]
         if world > 1:
             import torch.distributed as dist
             gathered = [None] * world
@@ -198,10 +205,47 @@ class DistRandomForestClassifier(_ScParamMixin, RandomForestClassifier):
         else:
             ests = local
         self.estimators_ = ests
-        self.estimator_ = DecisionTreeClassifier()
+        self.estimator_ = self._tree_cls()
         del self.sc                                                     # ref :335
         return self
 
     def _set_oob_score(self, X, y):
         """The reference overrides this to a no-op (ref ensemble.py:338-340)."""
         return
+
+
+class DistRandomForestClassifier(_DistForestClassifier, RandomForestClassifier):
+    """Same as sklearn `RandomForestClassifier` with every tree built on a B200.
+    Constructor mirrors ref ensemble.py:378-422 (``sc`` is the FIRST positional argument)."""
+
+    _splitter = 0
+    _tree_cls = DecisionTreeClassifier
+
+    def __init__(self, sc=None, partitions="auto", n_estimators=100, criterion="gini", max_depth=None,
+                 min_samples_split=2, min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
+                 max_leaf_nodes=None, min_impurity_decrease=0.0, min_impurity_split=None, bootstrap=True,
+                 oob_score=False, n_jobs=None, random_state=None, verbose=0, warm_start=False,
+                 class_weight=None):
+        self._init_params(sc, partitions, n_estimators, criterion, max_depth, min_samples_split, min_samples_leaf,
+                          min_weight_fraction_leaf, max_features, max_leaf_nodes, min_impurity_decrease,
+                          min_impurity_split, bootstrap, oob_score, n_jobs, random_state, verbose, warm_start,
+                          class_weight)
+
+
+class DistExtraTreesClassifier(_DistForestClassifier, ExtraTreesClassifier):
+    """Same as sklearn `ExtraTreesClassifier` with every tree built on a B200 (random splitter:
+    one uniformly drawn threshold per drawn feature, no bootstrap by default).
+    Constructor mirrors ref ensemble.py:437-478 (``sc`` is the FIRST positional argument)."""
+
+    _splitter = 1
+    _tree_cls = ExtraTreeClassifier
+
+    def __init__(self, sc=None, partitions="auto", n_estimators=100, criterion="gini", max_depth=None,
+                 min_samples_split=2, min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
+                 max_leaf_nodes=None, min_impurity_decrease=0.0, min_impurity_split=None, bootstrap=False,
+                 oob_score=False, n_jobs=None, random_state=None, verbose=0, warm_start=False,
+                 class_weight=None):
+        self._init_params(sc, partitions, n_estimators, criterion, max_depth, min_samples_split, min_samples_leaf,
+                          min_weight_fraction_leaf, max_features, max_leaf_nodes, min_impurity_decrease,
+                          min_impurity_split, bootstrap, oob_score, n_jobs, random_state, verbose, warm_start,
+                          class_weight)

@@ -191,19 +191,23 @@ class Engine:
                 "gpu_seconds": secs.value}
 
     def forest_fit(self, sample_counts, rand_states, n_classes, max_features, max_depth, min_samples_split,
-                   min_samples_leaf, min_weight_leaf, min_impurity_decrease):
+                   min_samples_leaf, min_weight_leaf, min_impurity_decrease, splitter=0):
         """Build len(rand_states) classifier trees.  sample_counts [n_trees, n] uint8 (bootstrap
-        multiplicities = the reference's sample_weight), rand_states [n_trees] uint32 splitter seeds.
+        multiplicities = the reference's sample_weight; None = every row once), rand_states [n_trees]
+        uint32 splitter seeds, splitter 0 = best (RandomForest) / 1 = random (ExtraTrees).
         Returns a list of dicts with the sklearn Tree arrays of every tree."""
-        counts = np.ascontiguousarray(sample_counts, dtype=np.uint8)
         rs = np.ascontiguousarray(rand_states, dtype=np.uint32)
         T = rs.shape[0]
-        assert counts.shape == (T, self.n)
+        counts = None
+        if sample_counts is not None:
+            counts = np.ascontiguousarray(sample_counts, dtype=np.uint8)
+            assert counts.shape == (T, self.n)
         h = ctypes.c_void_p()
         secs = ctypes.c_double(0.0)
-        check(self._lib.skd_forest_fit(self._h, T, ptr(counts), ptr(rs), int(n_classes), int(max_features),
+        check(self._lib.skd_forest_fit(self._h, T, ptr(counts) if counts is not None else None, ptr(rs),
+                                       int(n_classes), int(max_features),
                                        int(max_depth), int(min_samples_split), int(min_samples_leaf),
-                                       float(min_weight_leaf), float(min_impurity_decrease),
+                                       float(min_weight_leaf), float(min_impurity_decrease), int(splitter),
                                        ctypes.byref(h), ctypes.byref(secs)), self._h)
         self.last_forest_seconds = secs.value
         trees = []

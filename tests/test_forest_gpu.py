@@ -79,3 +79,23 @@ def test_forest_inference_kernel_matches_sklearn():
     udf = get_prediction_udf(model, method="predict_proba")
     out = udf(*[pd.Series(Xt[:100, j]) for j in range(12)])
     np.testing.assert_array_equal(np.vstack(out.values), model.predict_proba(Xt[:100]))
+
+
+@pytest.mark.parametrize("n,d,levels,k", [(3000, 16, 256, 2), (20000, 40, 256, 3), (5000, 10, 8, 4)])
+def test_extra_trees_bit_identical_to_sklearn(n, d, levels, k):
+    """Random splitter (SK/tree/_splitter.pyx:507-736): thresholds are drawn from the same xorshift
+    stream as the features, so topology, thresholds and values must all equal scikit-learn's."""
+    from sklearn.ensemble import ExtraTreesClassifier
+    from skdist.distribute.ensemble import DistExtraTreesClassifier
+    X, y = lattice_data(n, d, seed=n % 11, levels=levels, n_classes=k)
+    ours = DistExtraTreesClassifier(n_estimators=5, random_state=7).fit(X, y)
+    ref = ExtraTreesClassifier(n_estimators=5, random_state=7).fit(X, y)
+    assert_same_forest(ours, ref)
+    np.testing.assert_array_equal(ours.predict_proba(X[:300]), ref.predict_proba(X[:300]))
+    kw = dict(n_estimators=3, random_state=2, max_depth=9, min_samples_leaf=4, max_features=3, bootstrap=True)
+    assert_same_forest(DistExtraTreesClassifier(**kw).fit(X, y), ExtraTreesClassifier(**kw).fit(X, y))
+    # ref skdist/distribute/tests/test_ensemble.py (ExtraTrees toy case)
+    Xt = np.array([[0, 1, 0, 1], [0, 0, 0, 1], [1, 0, 1, 0]])
+    yt = np.array([0, 1, 0])
+    etc = DistExtraTreesClassifier(n_estimators=10, random_state=5).fit(Xt, yt)
+    assert_same_forest(etc, ExtraTreesClassifier(n_estimators=10, random_state=5).fit(Xt, yt))
