@@ -59,6 +59,9 @@ int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_fo
 /* Batched binary L2 logistic regression (lbfgs), B independent columns sharing X.
  * Column j: positives = rows with y_class == col_pos[j]; training rows = rows whose fold id
  * != col_fold[j] (col_fold[j] < 0: all rows); l2 strength = 1 / (C[j] * n_train_j).
+ * col_neg (may be NULL): col_neg[j] >= 0 restricts column j to the rows of class col_pos[j] or
+ * col_neg[j] -- the one-vs-one pair fit of multiclass.py:155-173 (_fit_ovo_binary) without the
+ * X[cond] copy; col_neg[j] < 0 keeps every other class as negatives (one-vs-rest).
  * Outputs: coef_out[j*(d+1) + k] (k<d weights, k==d intercept, 0 if !fit_intercept),
  * n_iter_out[j] = min(nit, max_iter), status_out[j] (1,2 converged; 3 max_iter; 4 abnormal
  * line search; 5 non-finite), loss_out[j] final objective, n_evals_out[j] number of
@@ -68,8 +71,8 @@ int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_fo
  * penalty="l2"): SK/linear_model/_logistic.py:219-717, SK/linear_model/_linear_loss.py:291-379,
  * scipy L-BFGS-B with maxiter=max_iter, maxls=50, gtol=tol, ftol=64*eps. */
 int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t* col_fold,
-                         const int32_t* col_pos, int32_t fit_intercept, double tol,
-                         int32_t max_iter, float* coef_out, int32_t* n_iter_out,
+                         const int32_t* col_pos, const int32_t* col_neg, int32_t fit_intercept,
+                         double tol, int32_t max_iter, float* coef_out, int32_t* n_iter_out,
                          int32_t* status_out, double* loss_out, int32_t* n_evals_out,
                          double* gpu_seconds_out);
 

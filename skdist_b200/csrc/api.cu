@@ -292,6 +292,7 @@ int skd_stage_labels(skd_ctx* ctx, const int32_t* y, int64_t n) {
   if (!c->ycls) { SKD_CUDA(c, cudaMalloc((void**)&c->ycls, (size_t)n * sizeof(int32_t))); c->ycls_cap = n; }
   SKD_CUDA(c, cudaMemcpyAsync(c->ycls, y, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->h_ycls.assign(y, y + n);
   c->h2d += n * (int64_t)sizeof(int32_t);
   c->tc.meta_valid = false;
   return 0;
@@ -395,7 +396,7 @@ int skd_get_counters(skd_ctx* ctx, int64_t* launches, int64_t* h2d, int64_t* d2h
 }
 
 int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t* col_fold,
-                         const int32_t* col_pos, int32_t fit_intercept, double tol,
+                         const int32_t* col_pos, const int32_t* col_neg, int32_t fit_intercept, double tol,
                          int32_t max_iter, float* coef_out, int32_t* n_iter_out,
                          int32_t* status_out, double* loss_out, int32_t* n_evals_out,
                          double* gpu_seconds_out) {
@@ -411,6 +412,8 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
 
   // host-side per-column constants
   std::vector<double> l2(B), inv_n(B);
+  std::vector<int64_t> pair_counts;
+  int max_cls = -1;
   double mean_ntrain = 0.0;
   for (int j = 0; j < B; ++j) {
     int f = col_fold[j];
@@ -418,6 +421,24 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
     if (f >= 0) {
       if (!c->fold || f >= c->n_folds) return fail(c, "skd_logreg_fit_batch: col_fold refers to an unstaged fold");
       ntrain = n - c->fold_count[f];
+    }
+    if (col_neg && col_neg[j] >= 0) {   // pair column: only rows of class col_pos[j] or col_neg[j] train
+      if ((int64_t)c->h_ycls.size() != n) return fail(c, "skd_logreg_fit_batch: labels not staged");
+      if (col_neg[j] == col_pos[j]) return fail(c, "skd_logreg_fit_batch: col_neg equals col_pos");
+      if (pair_counts.empty()) {         // rows per (class, fold) once per call
+        for (int64_t i = 0; i < n; ++i) if (c->h_ycls[i] > max_cls) max_cls = c->h_ycls[i];
+        pair_counts.assign((size_t)(max_cls + 1) * (c->n_folds + 1), 0);
+        for (int64_t i = 0; i < n; ++i) {
+          const int fi = c->h_fold.empty() ? 0 : (int)c->h_fold[i];
+          if (c->h_ycls[i] >= 0) pair_counts[(size_t)c->h_ycls[i] * (c->n_folds + 1) + (c->h_fold.empty() ? 0 : fi)] += 1;
+        }
+      }
+      ntrain = 0;
+      for (int cls : {col_pos[j], col_neg[j]}) {
+        if (cls < 0 || cls > max_cls) continue;
+        for (int ff = 0; ff < (c->h_fold.empty() ? 1 : c->n_folds); ++ff)
+          if (ff != f) ntrain += pair_counts[(size_t)cls * (c->n_folds + 1) + ff];
+      }
     }
     if (ntrain <= 0) return fail(c, "skd_logreg_fit_batch: empty training set");
     if (!(C[j] > 0.0)) return fail(c, "skd_logreg_fit_batch: C must be positive");
@@ -443,7 +464,8 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
       int f = col_fold[order[i]], i0 = i;
       if (f > 127) return fail(c, "skd_logreg_fit_batch: fold id above 127");
       for (; i < B && col_fold[order[i]] == f; ++i) {
-        SlotMeta sm; sm.col = order[i]; sm.fold = f < 0 ? -1 : f; sm.pos = col_pos[order[i]]; sm.pad = 0;
+        SlotMeta sm; sm.col = order[i]; sm.fold = f < 0 ? -1 : f; sm.pos = col_pos[order[i]];
+        sm.pad = (col_neg && col_neg[order[i]] >= 0) ? col_neg[order[i]] + 1 : 0;
         hslots.push_back(sm);
       }
       (void)i0;
@@ -456,6 +478,9 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
     w.uni_pos = col_pos[0];
     for (int j = 1; j < B; ++j)
       if (col_pos[j] != col_pos[0]) { w.uni_pos = -1; break; }
+    if (col_neg)
+      for (int j = 0; j < B; ++j)
+        if (col_neg[j] >= 0) { w.uni_pos = -1; break; }   // pair masks are per column: general epilogue
   }
   SKD_CUDA(c, sx.alloc(&w.sc, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.vec, (size_t)B * w.vec_stride));
@@ -463,6 +488,12 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   SKD_CUDA(c, sx.alloc(&w.inv_n, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.col_fold, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.col_pos, (size_t)B));
+  std::vector<int32_t> hneg1;
+  if (col_neg) {
+    hneg1.resize(B);
+    for (int j = 0; j < B; ++j) hneg1[j] = col_neg[j] >= 0 ? col_neg[j] + 1 : 0;
+    SKD_CUDA(c, sx.alloc(&w.col_neg1, (size_t)B));
+  }
   SKD_CUDA(c, sx.alloc(&w.n_evals, (size_t)B));
   SKD_CUDA(c, sx.alloc(&w.slot, (size_t)w.slot_cap));
   SKD_CUDA(c, sx.alloc(&w.n_act, 1));
@@ -482,6 +513,7 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   SKD_CUDA(c, cudaMemcpyAsync(w.inv_n, inv_n.data(), B * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaMemcpyAsync(w.col_fold, col_fold, B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaMemcpyAsync(w.col_pos, col_pos, B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  if (col_neg) SKD_CUDA(c, cudaMemcpyAsync(w.col_neg1, hneg1.data(), B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   c->h2d += (int64_t)B * 24;
 
   if (w.grouped) {

@@ -108,7 +108,7 @@ lb_gather_kernel(int n_act, int nz_used, int d, int ldx, int fit_intercept,
 __global__ void lb_init_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, int B, int n,
                                int m, int maxiter, int maxls, double pgtol, double ftol,
                                SlotMeta* slot, const int32_t* col_fold, const int32_t* col_pos,
-                               int32_t* n_evals, int32_t* n_act) {
+                               const int32_t* col_neg1, int32_t* n_evals, int32_t* n_act) {
   int col = blockIdx.x;
   if (col >= B) return;
   double* base = vec + (size_t)col * vec_stride;
@@ -119,7 +119,7 @@ __global__ void lb_init_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride,
     sc[col] = s;
     if (slot) {   // dense layout: slot i = column i (the grouped layout is uploaded by the host)
       SlotMeta sm;
-      sm.col = col; sm.fold = col_fold[col]; sm.pos = col_pos[col]; sm.pad = 0;
+      sm.col = col; sm.fold = col_fold[col]; sm.pos = col_pos[col]; sm.pad = col_neg1 ? col_neg1[col] : 0;
       slot[col] = sm;
       if (col == 0) *n_act = B;
     }
@@ -298,7 +298,7 @@ int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max
   const double ftol = 64.0 * 2.220446049250313e-16;
   lb_init_kernel<<<w.B, 128, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.B, w.dp, m, max_iter,
                                              maxls, tol, ftol, w.grouped ? nullptr : w.slot, w.col_fold,
-                                             w.col_pos, w.n_evals, w.n_act);
+                                             w.col_pos, w.col_neg1, w.n_evals, w.n_act);
   // initial iterate is w0 = 0 (SK/linear_model/_logistic.py:443): export zeros
   c->launches += 1;
   if (w.use_tc) {

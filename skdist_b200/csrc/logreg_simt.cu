@@ -66,15 +66,15 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
   if (row_end > n) row_end = n;
 
   // per-thread slot metadata for its 4 slots
-  int sfold[4], spos[4];
+  int sfold[4], spos[4], sneg1[4];
   float sb[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     int s = s0 + tx * 4 + j;
-    sfold[j] = -100; spos[j] = -100; sb[j] = 0.f;
+    sfold[j] = -100; spos[j] = -100; sneg1[j] = 0; sb[j] = 0.f;
     if (s < n_act) {
       sb[j] = bias[s];
-      if (MODE != MODE_DECISION) { sfold[j] = slot[s].fold; spos[j] = slot[s].pos; }
+      if (MODE != MODE_DECISION) { sfold[j] = slot[s].fold; spos[j] = slot[s].pos; sneg1[j] = slot[s].pad; }
     }
   }
   double acc_loss[4] = {0, 0, 0, 0}, acc_g[4] = {0, 0, 0, 0};
@@ -132,7 +132,8 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
         float raw = acc[i][j] + sb[j];
         gout[j] = 0.f;
         if (MODE == MODE_FIT) {
-          bool train = rvalid && (fd != sfold[j] || sfold[j] < 0) && sfold[j] != -100;
+          bool train = rvalid && (fd != sfold[j] || sfold[j] < 0) && sfold[j] != -100 &&
+                       (sneg1[j] == 0 || yc == spos[j] || yc == sneg1[j] - 1);   // one-vs-one: only the pair's rows
           if (train) {
             double y = (yc == spos[j]) ? 1.0 : 0.0;
             double l, g;

@@ -313,6 +313,8 @@ struct TcSlotParam {
   float bias;
   int32_t fold;
   int32_t pos;
+  int32_t neg1;   // SlotMeta::pad (0 = one-vs-rest, k + 1 = pair with class k)
+  int32_t pad;
 };
 
 __global__ void __launch_bounds__(128)
@@ -330,7 +332,7 @@ tc_export_kernel(const double* __restrict__ vec, size_t vec_stride, const SlotMe
       Wh[(size_t)s * dpad + k] = __float2half_rn(0.f);
       Wl[(size_t)s * dpad + k] = __float2half_rn(0.f);
     }
-    if (threadIdx.x == 0) { TcSlotParam p; p.inv_t = 1.f; p.bias = 0.f; p.fold = sm.fold; p.pos = -1; sp[s] = p; }
+    if (threadIdx.x == 0) { TcSlotParam p; p.inv_t = 1.f; p.bias = 0.f; p.fold = sm.fold; p.pos = -1; p.neg1 = 0; p.pad = 0; sp[s] = p; }
     return;
   }
   const double* x = xin ? xin + (size_t)s * (d + 1) : vec + (size_t)sm.col * vec_stride;
@@ -360,6 +362,8 @@ tc_export_kernel(const double* __restrict__ vec, size_t vec_stride, const SlotMe
     p.bias = fit_intercept ? (float)x[d] : 0.f;
     p.fold = sm.fold;
     p.pos = sm.pos;
+    p.neg1 = sm.pad;
+    p.pad = 0;
     sp[s] = p;
   }
 }
@@ -656,7 +660,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
       const int slot = g * TC_BC + lane_in_group;
       const bool valid = slot < prm.n_act;
       TcSlotParam sp;
-      sp.inv_t = 1.f; sp.bias = 0.f; sp.fold = -1; sp.pos = -1;
+      sp.inv_t = 1.f; sp.bias = 0.f; sp.fold = -1; sp.pos = -1; sp.neg1 = 0; sp.pad = 0;
       if (valid) sp = prm.sp[slot];
       // fit: work on z / 2^14 so that (row sign * 2^14) * z' = +-z and (row sign * 2^14) * sigma is
       // the scaled gradient entry; all power-of-two factors, results identical to the unscaled form
@@ -732,8 +736,9 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             } else {
               const uint32_t m = rm[j];
               const int fr = (int)(m >> 24);
-              const bool yb = (int)(m & 0x00FFFFFFu) == sp.pos;
-              const bool train = (fr != 0xFF) && (fr != sp.fold);
+              const int cls = (int)(m & 0x00FFFFFFu);
+              const bool yb = cls == sp.pos;
+              const bool train = (fr != 0xFF) && (fr != sp.fold) && (sp.neg1 == 0 || yb || cls == sp.neg1 - 1);
               sg = train ? (yb ? -GSCALE : GSCALE) : 0.f;
             }
             const float zp = fmaf(__uint_as_float(zr[j]), zi, zb0);

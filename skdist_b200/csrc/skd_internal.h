@@ -66,6 +66,7 @@ struct Ctx {
   float* yreal = nullptr;   // [n]
   int8_t* fold = nullptr;   // [n]; nullptr = no folds staged (points into fold_store otherwise)
   int8_t* fold_store = nullptr;
+  std::vector<int32_t> h_ycls; // host copy of the class ids (training-set sizes of one-vs-one pair columns)
   std::vector<int8_t> h_fold;  // host copy of the fold ids (tile lists for fold-aware tile skipping)
   int32_t n_folds = 0;
   std::vector<int64_t> fold_count;  // rows per fold id
@@ -168,7 +169,8 @@ struct SlotMeta {
   int32_t col;     // column id in the caller's batch
   int32_t fold;    // held-out fold id (-1: none)
   int32_t pos;     // positive class id
-  int32_t pad;
+  int32_t pad;     // neg1: 0 = every other class is a negative (one-vs-rest); k + 1 = only rows of class
+                   // `pos` or class k take part (one-vs-one pair)
 };
 
 // Workspace of one skd_logreg_fit_batch call (device pointers).
@@ -186,6 +188,7 @@ struct LogregWork {
   double* inv_n = nullptr;     // [B] 1 / n_train
   int32_t* col_fold = nullptr; // [B]
   int32_t* col_pos = nullptr;  // [B]
+  int32_t* col_neg1 = nullptr; // [B] or nullptr (see SlotMeta::pad)
   int32_t* n_evals = nullptr;  // [B]
   // per slot (active batch)
   SlotMeta* slot = nullptr;    // [B]

@@ -11,13 +11,17 @@ carry an integer class id, column k treats `class id == k` as positive.
   LogisticRegression(solver="lbfgs")     Engine.logreg_fit_batch (same kernels as the search path)
   SGDClassifier(loss="hinge"|"log_loss") Engine.sgd_fit_batch (exact-order column-batched SGD)
   anything else                          NotImplementedError (no CPU fallback by design)
+
+`DistOneVsOneClassifier` (ref multiclass.py:365-475) fits the K(K-1)/2 class pairs the same way:
+pair (i, j) is a column whose training rows are masked to classes i and j on the device
+(`col_neg`), replacing the reference's per-pair `X[cond]` copy (`_fit_ovo_binary`, :155-173).
 """
 import warnings
 
 import numpy as np
 from sklearn.base import BaseEstimator
 from sklearn.linear_model import LogisticRegression, SGDClassifier
-from sklearn.multiclass import OneVsRestClassifier
+from sklearn.multiclass import OneVsOneClassifier, OneVsRestClassifier
 from sklearn.preprocessing import LabelBinarizer, normalize
 from sklearn.utils.validation import check_is_fitted
 
@@ -26,7 +30,7 @@ from ..engine import get_engine
 from .base import _clone, _parse_partitions, _ScParamMixin
 from .validation import _check_estimator
 
-__all__ = ["DistOneVsRestClassifier"]
+__all__ = ["DistOneVsRestClassifier", "DistOneVsOneClassifier"]
 
 
 class _ConstantPredictor(BaseEstimator):
@@ -160,3 +164,62 @@ class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
         if self.norm:
             return normalize(probs, norm=self.norm)
         return probs
+
+
+class DistOneVsOneClassifier(_ScParamMixin, OneVsOneClassifier):
+    """One-vs-one with all class pairs fitted as one batched GPU solve.
+    Constructor mirrors ref multiclass.py:382-386 (``sc`` is the 2nd positional argument)."""
+
+    def __init__(self, estimator, sc=None, partitions="auto", verbose=False, n_jobs=None):
+        self.estimator = estimator
+        self.sc = sc
+        self.partitions = partitions
+        self.verbose = verbose
+        self.n_jobs = n_jobs
+
+    def fit(self, X, y, **fit_params):
+        """Fit the K(K-1)/2 pair estimators (ref multiclass.py:388-475)."""
+        if fit_params:
+            raise NotImplementedError("fit_params are not supported on the device path")
+        _check_estimator(self, verbose=self.verbose)
+        X_arr = np.asarray(X)
+        y_arr = np.asarray(y)
+        if y_arr.ndim != 1:
+            raise ValueError("OneVsOneClassifier needs 1-d class labels")
+        self.classes_ = np.unique(y_arr)                                 # ref :404
+        if len(self.classes_) == 1:
+            raise ValueError("OneVsOneClassifier can not be fit when only one class is present.")  # ref :405-408
+        K = len(self.classes_)
+        n, d = X_arr.shape
+        pairs = [(i, j) for i in range(K) for j in range(i + 1, K)]      # ref :410-415 (same order)
+        _parse_partitions(self.partitions, len(pairs))
+        base = self.estimator
+        if type(base) is not LogisticRegression:
+            raise NotImplementedError(
+                "%s has no one-vs-one device path; supported base estimator: LogisticRegression(solver='lbfgs')."
+                "  (No CPU fallback by design.)" % type(base).__name__)
+        from .search import _check_logreg
+        p = _check_logreg(_clone(base))
+        ycls = np.searchsorted(self.classes_, y_arr).astype(np.int32)
+        rank, world, _ = parallel.dist_info()
+        eng = get_engine()
+        eng.stage_x(X_arr)
+        eng.stage_labels(ycls)
+        eng.stage_folds(None, 0)
+        mine = parallel.shard_indices(len(pairs), rank, world)
+        neg = np.array([pairs[k][0] for k in mine], dtype=np.int32)      # y_binary: class i -> 0, class j -> 1 (ref :159-161)
+        pos = np.array([pairs[k][1] for k in mine], dtype=np.int32)
+        res = eng.logreg_fit_batch(np.full(len(mine), p["C"]), np.full(len(mine), -1, np.int32), pos,
+                                   fit_intercept=p["fit_intercept"], tol=p["tol"], max_iter=p["max_iter"],
+                                   col_neg=neg)
+        packed = np.concatenate([res["coef"], res["n_iter"][:, None].astype(np.float32)], axis=1)
+        full = parallel.all_gather_columns(packed, len(pairs), rank, world)
+        self.estimators_ = tuple(
+            _binary_estimator(base, full[k][:d + 1], d, X_arr.dtype, n_iter_=np.array([int(full[k][-1])], dtype=np.int32))
+            for k in range(len(pairs)))
+        self.pairwise_indices_ = None                                    # ref :441 (non-pairwise estimators)
+        self.n_features_in_ = d
+        del self.sc                                                      # ref :472
+        if hasattr(self.estimator, "sc"):
+            del self.estimator.sc
+        return self

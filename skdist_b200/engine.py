@@ -95,12 +95,17 @@ class Engine:
         return ms.value * 1e-3
 
     # -- solvers ------------------------------------------------------------------
-    def logreg_fit_batch(self, C, col_fold, col_pos, fit_intercept=True, tol=1e-4, max_iter=100):
+    def logreg_fit_batch(self, C, col_fold, col_pos, fit_intercept=True, tol=1e-4, max_iter=100, col_neg=None):
+        """B binary lbfgs fits sharing the staged X.  col_neg[j] >= 0 restricts column j to the rows
+        of class col_pos[j] / col_neg[j] (one-vs-one pair); None or < 0 = one-vs-rest."""
         C = np.ascontiguousarray(C, dtype=np.float64)
         B = C.shape[0]
         col_fold = np.ascontiguousarray(col_fold, dtype=np.int32)
         col_pos = np.ascontiguousarray(col_pos, dtype=np.int32)
         assert col_fold.shape == (B,) and col_pos.shape == (B,)
+        if col_neg is not None:
+            col_neg = np.ascontiguousarray(col_neg, dtype=np.int32)
+            assert col_neg.shape == (B,)
         coef = np.empty((B, self.d + 1), dtype=np.float32)
         n_iter = np.empty(B, dtype=np.int32)
         status = np.empty(B, dtype=np.int32)
@@ -108,8 +113,8 @@ class Engine:
         n_evals = np.empty(B, dtype=np.int32)
         secs = ctypes.c_double(0.0)
         check(self._lib.skd_logreg_fit_batch(
-            self._h, B, ptr(C), ptr(col_fold), ptr(col_pos), int(bool(fit_intercept)), float(tol),
-            int(max_iter), ptr(coef), ptr(n_iter), ptr(status), ptr(loss), ptr(n_evals),
+            self._h, B, ptr(C), ptr(col_fold), ptr(col_pos), ptr(col_neg) if col_neg is not None else None,
+            int(bool(fit_intercept)), float(tol), int(max_iter), ptr(coef), ptr(n_iter), ptr(status), ptr(loss), ptr(n_evals),
             ctypes.byref(secs)), self._h)
         return {"coef": coef, "n_iter": n_iter, "status": status, "loss": loss,
                 "n_evals": n_evals, "gpu_seconds": secs.value}

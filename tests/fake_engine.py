@@ -34,13 +34,15 @@ class FakeEngine:
     def _train_mask(self, f):
         return np.ones(self.n, bool) if f < 0 else self.fold != f
 
-    def logreg_fit_batch(self, C, col_fold, col_pos, fit_intercept=True, tol=1e-4, max_iter=100):
+    def logreg_fit_batch(self, C, col_fold, col_pos, fit_intercept=True, tol=1e-4, max_iter=100, col_neg=None):
         B = len(C)
         self.calls.append(("fit", B))
         coef = np.zeros((B, self.d + 1), np.float32)
         n_iter = np.zeros(B, np.int32)
         for j in range(B):
             m = self._train_mask(int(col_fold[j]))
+            if col_neg is not None and col_neg[j] >= 0:
+                m = m & ((self.y == col_pos[j]) | (self.y == col_neg[j]))
             y01 = (self.y[m] == col_pos[j]).astype(np.float32)
             w, b, it = lo.fit_binary_lbfgs(self.X[m], y01, C=float(C[j]), tol=tol, max_iter=max_iter,
                                            fit_intercept=fit_intercept)

@@ -347,3 +347,19 @@ def test_batch_predict_linear_models(eng):
         np.testing.assert_array_equal(pred[clear], model.predict(X)[clear])
         assert clear.mean() > 0.999
         np.testing.assert_allclose(batch_predict(model, X, "predict_proba"), model.predict_proba(X), rtol=0, atol=2e-5)
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_ovo_logreg_on_device(eng):
+    """One-vs-one: every class pair is a column whose rows are masked to the pair on the device."""
+    from sklearn.multiclass import OneVsOneClassifier
+    from skdist.distribute.multiclass import DistOneVsOneClassifier
+    from skdist_b200.datasets import make_multiclass
+    X, y = make_multiclass(6000, 20, 5, seed=21)
+    ovo = DistOneVsOneClassifier(LogisticRegression(C=0.05), None).fit(X, y)
+    ref = OneVsOneClassifier(LogisticRegression(C=0.05)).fit(X, y)
+    assert len(ovo.estimators_) == 10
+    for a, b in zip(ovo.estimators_, ref.estimators_):
+        assert abs(int(a.n_iter_[0]) - int(b.n_iter_[0])) <= 2
+        np.testing.assert_allclose(a.coef_, b.coef_, rtol=0, atol=4e-3 * np.abs(b.coef_).max())
+    assert np.mean(ovo.predict(X) == ref.predict(X)) > 0.999

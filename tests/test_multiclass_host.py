@@ -75,3 +75,22 @@ def test_reference_ovr_equals_sklearn():
     s = OneVsRestClassifier(SGDClassifier(random_state=0)).fit(X, y)
     for a, b in zip(r.estimators_, s.estimators_):
         np.testing.assert_array_equal(a.coef_, b.coef_)
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_ovo_logreg_matches_sklearn(fake_engine):
+    """DistOneVsOneClassifier host logic (pair order, label mapping, voting) on the test-double engine."""
+    from sklearn.multiclass import OneVsOneClassifier
+    from skdist.distribute.multiclass import DistOneVsOneClassifier
+    X, y = make_multiclass(400, 6, 4, seed=8)
+    labels = np.array(["d", "a", "c", "b"])[y]
+    ovo = DistOneVsOneClassifier(LogisticRegression(), None).fit(X, labels)
+    ref = OneVsOneClassifier(LogisticRegression()).fit(X, labels)
+    assert len(ovo.estimators_) == 6 and not hasattr(ovo, "sc")
+    for a, b in zip(ovo.estimators_, ref.estimators_):
+        np.testing.assert_allclose(a.coef_, b.coef_, rtol=0, atol=1e-6)
+        np.testing.assert_allclose(a.intercept_, b.intercept_, rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(ovo.predict(X), ref.predict(X))
+    np.testing.assert_allclose(ovo.decision_function(X), ref.decision_function(X), atol=1e-5)
+    with pytest.raises(ValueError):
+        DistOneVsOneClassifier(LogisticRegression()).fit(X, np.zeros(len(X)))
