@@ -38,9 +38,9 @@ from .. import parallel
 from ..engine import get_engine
 from .base import _clone, _merged_params, _parse_partitions, _ScParamMixin
 from .utils import _check_multimetric_scoring, _num_samples
-from .validation import _check_estimator
+from .validation import _check_estimator, _check_n_iter, _validate_models
 
-__all__ = ["DistGridSearchCV", "DistRandomizedSearchCV"]
+__all__ = ["DistGridSearchCV", "DistRandomizedSearchCV", "DistMultiModelSearch"]
 
 
 # ----------------------------------------------------------------------------------------
@@ -413,3 +413,129 @@ class DistRandomizedSearchCV(DistBaseSearchCV, RandomizedSearchCV):
     def _get_param_iterator(self):
         """ref search.py:710-714"""
         return ParameterSampler(self.param_distributions, self.n_iter, random_state=self.random_state)
+
+
+# ----------------------------------------------------------------------------------------
+# multi-model randomized search (ref search.py:60-177, 717-908)
+# ----------------------------------------------------------------------------------------
+def _raw_sampler(models, n, random_state=None):
+    """`n` sampled parameter sets per model, every model sampled with the same random_state
+    (ref search.py:60-90)."""
+    param_sets = []
+    for index, (_, _, dist) in enumerate(models):
+        sampler = list(ParameterSampler(dist, n_iter=_check_n_iter(n, dist), random_state=random_state))
+        for sample_index, params in enumerate(sampler):
+            param_sets.append({"model_index": index, "params_index": sample_index, "param_set": params})
+    return param_sets
+
+
+class DistMultiModelSearch(_ScParamMixin, BaseEstimator):
+    """Randomized search over several (name, estimator, param_set) models at once; the
+    (model, sampled params, fold) fits of every model run as columns of that model's batched
+    device solve.  Constructor and fitted attributes mirror ref search.py:717-908."""
+
+    def __init__(self, models, sc=None, partitions="auto", n=5, cv=5, scoring=None, random_state=None,
+                 verbose=0, refit=True, n_jobs=None, pre_dispatch="2*n_jobs"):
+        self.models = models
+        self.sc = sc
+        self.partitions = partitions
+        self.n = n
+        self.cv = cv
+        self.scoring = scoring
+        self.random_state = random_state
+        self.verbose = verbose
+        self.refit = refit
+        self.n_jobs = n_jobs
+        self.pre_dispatch = pre_dispatch
+
+    def fit(self, X, y=None, groups=None, **fit_params):
+        """ref search.py:800-866"""
+        if fit_params:
+            raise NotImplementedError("fit_params are not supported on the device path")
+        _check_estimator(self, verbose=self.verbose)
+        models = _validate_models(self.models, self)
+        cv = check_cv(self.cv, y, classifier=is_classifier(models[0][1]))
+        X, y, groups = indexable(X, y, groups)
+        X_arr, y_arr = np.asarray(X), np.asarray(y)
+        n_samples, n_features = X_arr.shape
+        cv_splitted = list(cv.split(X, y, groups))
+        n_splits = len(cv_splitted)
+        fold = _fold_ids(cv_splitted, n_samples)
+        param_sets = _raw_sampler(models, self.n, random_state=self.random_state)
+        _parse_partitions(self.partitions, len(param_sets) * n_splits)
+
+        rank, world, _ = parallel.dist_info()
+        eng = get_engine()
+        scores = np.zeros(len(param_sets))
+        families = {}
+        for index, (_, estimator, _) in enumerate(models):
+            rows = [i for i, ps in enumerate(param_sets) if ps["model_index"] == index]
+            cands = [param_sets[i]["param_set"] for i in rows]
+            scorers, _ = _check_multimetric_scoring(estimator, scoring=self.scoring)
+            family = _pick_family(estimator, cands, X_arr, y_arr, scorers)
+            families[index] = family
+            family.stage(eng, X_arr, fold, n_splits)
+            n_cols = len(cands) * n_splits
+            my_cols = parallel.shard_indices(n_cols, rank, world)
+            loc = family.run_columns(eng, my_cols, n_splits, False)
+            test = parallel.all_gather_columns(loc["test_score"], n_cols, rank, world)
+            # plain mean over folds (ref search.py:166-176: groupby(...).agg({"score": "mean"}))
+            scores[rows] = np.asarray(test, dtype=np.float64).reshape(len(cands), n_splits).mean(axis=1)
+        if self.verbose:
+            for index, (name, _, _) in enumerate(models):
+                best = max(scores[i] for i, ps in enumerate(param_sets) if ps["model_index"] == index)
+                print("model %d (%s): best score %.6f" % (index, name, best))
+
+        best_index = int(np.argmax(scores))                              # ref :838
+        self.best_model_index_ = param_sets[best_index]["model_index"]
+        self.best_model_name_ = models[self.best_model_index_][0]
+        self.best_params_ = param_sets[best_index]["param_set"]
+        self.best_score_ = scores[best_index]
+        self.worst_score_ = scores[best_index]                           # sic (ref :843)
+        self.cv_results_ = {                                             # ref :844-859
+            "model_index": [ps["model_index"] for ps in param_sets],
+            "model_name": [models[ps["model_index"]][0] for ps in param_sets],
+            "params": [ps["param_set"] for ps in param_sets],
+            "rank_test_score": list(np.asarray(rankdata(-scores), dtype=np.int32)),
+            "mean_test_score": list(scores),
+        }
+        if self.refit:                                                   # ref :861-864
+            family = families[self.best_model_index_]
+            family.stage(eng, X_arr, fold, n_splits)
+            self.best_estimator_ = family.refit(eng, self.best_params_, X_arr.dtype, n_features)
+        del self.sc
+        return self
+
+    def _check_is_fitted(self):
+        """ref search.py:868-880"""
+        from sklearn.exceptions import NotFittedError
+        if not self.refit:
+            raise NotFittedError(
+                "This %s instance was initialized with refit=False. The method is available only after "
+                "refitting on the best parameters. You can refit an estimator manually using the "
+                "``best_params_`` attribute" % (type(self).__name__))
+        from sklearn.utils.validation import check_is_fitted
+        check_is_fitted(self, "best_estimator_")
+
+    def _delegate(self, name, X):
+        self._check_is_fitted()
+        if not hasattr(self.best_estimator_, name):
+            raise AttributeError("%s has no %s" % (type(self.best_estimator_).__name__, name))
+        return getattr(self.best_estimator_, name)(X)
+
+    def predict(self, X):
+        return self._delegate("predict", X)
+
+    def predict_proba(self, X):
+        return self._delegate("predict_proba", X)
+
+    def predict_log_proba(self, X):
+        return self._delegate("predict_log_proba", X)
+
+    def decision_function(self, X):
+        return self._delegate("decision_function", X)
+
+    @property
+    def classes_(self):
+        self._check_is_fitted()
+        return self.best_estimator_.classes_
