@@ -56,6 +56,13 @@ int skd_stage_targets(skd_ctx* ctx, const float* y, int64_t n);
  * X[train]/X[test] copies.  ref: search.py:378-383 (fit_sets), utils.py:171-209 (_safe_split). */
 int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_folds);
 
+/* Per-column feature masks for the NEXT skd_logreg_fit_batch call (one-shot): mask[j*d + k] = 1
+ * if feature k takes part in column j's fit, 0 if it is left out (its weight stays exactly 0, which
+ * equals fitting on X with those columns dropped).  B must equal the batch size of that call;
+ * mask = NULL clears.  ref: replaces the `_drop_col(X, index)` copies of eliminate.py:22-38
+ * (_fit_and_score_one) -- one feature set x fold per column. */
+int skd_stage_column_masks(skd_ctx* ctx, int32_t B, const uint8_t* mask);
+
 /* Batched binary L2 logistic regression (lbfgs), B independent columns sharing X.
  * Column j: positives = rows with y_class == col_pos[j]; training rows = rows whose fold id
  * != col_fold[j] (col_fold[j] < 0: all rows); l2 strength = 1 / (C[j] * n_train_j).

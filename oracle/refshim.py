@@ -20,10 +20,7 @@ def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "skdist", "distribute"))
 
 
-def load():
-    """Return the reference's (search, multiclass, ensemble) modules."""
-    if not available():
-        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+def _patch():
     import numpy as np
     import sklearn.utils.metaestimators as _m
     from sklearn.utils.metaestimators import available_if
@@ -38,10 +35,16 @@ def load():
     if "sklearn.ensemble.forest" not in sys.modules:
         import sklearn.ensemble._forest as _f
         sys.modules["sklearn.ensemble.forest"] = _f
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
-    # our own drop-in alias package is also called ``skdist``: make sure the
-    # reference's copy is the one imported here, under a private name.
+
+
+def _import_reference(names):
+    """Import reference modules by dotted name ('skdist.distribute.search', ...).  Our own drop-in
+    alias package is also called ``skdist``: the reference's copy is imported under that name only
+    for the duration of the call and the previous ``sys.modules`` entries are restored afterwards."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    _patch()
+    import importlib
     import importlib.util
     saved = {k: v for k, v in sys.modules.items() if k == "skdist" or k.startswith("skdist.")}
     for k in saved:
@@ -53,13 +56,21 @@ def load():
         pkg = importlib.util.module_from_spec(spec)
         sys.modules["skdist"] = pkg
         spec.loader.exec_module(pkg)
-        import importlib
-        search = importlib.import_module("skdist.distribute.search")
-        multiclass = importlib.import_module("skdist.distribute.multiclass")
-        ensemble = importlib.import_module("skdist.distribute.ensemble")
+        mods = [importlib.import_module(n) for n in names]
     finally:
         ref_mods = {k: v for k, v in sys.modules.items() if k == "skdist" or k.startswith("skdist.")}
         for k in ref_mods:
             del sys.modules[k]
         sys.modules.update(saved)
-    return search, multiclass, ensemble
+    return mods
+
+
+def load():
+    """Return the reference's (search, multiclass, ensemble) modules."""
+    return tuple(_import_reference(["skdist.distribute.search", "skdist.distribute.multiclass",
+                                    "skdist.distribute.ensemble"]))
+
+
+def load_module(name):
+    """Return one more reference module, e.g. 'skdist.distribute.eliminate'."""
+    return _import_reference([name])[0]

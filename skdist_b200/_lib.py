@@ -35,6 +35,7 @@ SYMBOLS = {
     "skd_stage_labels": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64]),
     "skd_stage_targets": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64]),
     "skd_stage_folds": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32]),
+    "skd_stage_column_masks": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p]),
     "skd_logreg_fit_batch": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_int32, _c.c_double, _c.c_int32, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_double)]),

@@ -340,6 +340,18 @@ int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_fo
   return 0;
 }
 
+int skd_stage_column_masks(skd_ctx* ctx, int32_t B, const uint8_t* mask) {
+  if (!ctx) return fail(nullptr, "skd_stage_column_masks: ctx is NULL");
+  Ctx* c = &ctx->c;
+  c->fmask_cols = 0;
+  c->h_fmask.clear();
+  if (!mask || B <= 0) return 0;   // cleared
+  if (!c->X) return fail(c, "skd_stage_column_masks: stage X first");
+  c->h_fmask.assign(mask, mask + (size_t)B * c->d);
+  c->fmask_cols = B;
+  return 0;
+}
+
 int skd_set_kernel(skd_ctx* ctx, int32_t which) {
   if (!ctx) return -1;
   int prev = ctx->c.kernel_choice;
@@ -495,6 +507,14 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
     SKD_CUDA(c, sx.alloc(&w.col_neg1, (size_t)B));
   }
   SKD_CUDA(c, sx.alloc(&w.n_evals, (size_t)B));
+  const bool use_fmask = c->fmask_cols > 0;
+  if (use_fmask) {
+    if (c->fmask_cols != B || (int64_t)c->h_fmask.size() != (int64_t)B * d) {
+      c->fmask_cols = 0; c->h_fmask.clear();
+      return fail(c, "skd_logreg_fit_batch: staged column masks do not match this batch (B x d)");
+    }
+    SKD_CUDA(c, sx.alloc(&w.fmask, (size_t)B * d));
+  }
   SKD_CUDA(c, sx.alloc(&w.slot, (size_t)w.slot_cap));
   SKD_CUDA(c, sx.alloc(&w.n_act, 1));
   SKD_CUDA(c, sx.alloc(&w.n_run, 1));
@@ -514,6 +534,12 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   SKD_CUDA(c, cudaMemcpyAsync(w.col_fold, col_fold, B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   SKD_CUDA(c, cudaMemcpyAsync(w.col_pos, col_pos, B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   if (col_neg) SKD_CUDA(c, cudaMemcpyAsync(w.col_neg1, hneg1.data(), B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  if (use_fmask) {
+    SKD_CUDA(c, cudaMemcpyAsync(w.fmask, c->h_fmask.data(), (size_t)B * d, cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h2d += (int64_t)B * d;
+    c->fmask_cols = 0; c->h_fmask.clear();   // one-shot: consumed by this call
+  }
   c->h2d += (int64_t)B * 24;
 
   if (w.grouped) {

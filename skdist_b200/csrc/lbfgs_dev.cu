@@ -68,7 +68,8 @@ __device__ __forceinline__ double gather_fg(const CtaPar& P, int s, int n_act, i
                                             const double* __restrict__ gsump,
                                             const float* __restrict__ gradp,
                                             const double* __restrict__ gscale, double l2,
-                                            double inv_n, const double* x, double* g) {
+                                            double inv_n, const double* x, double* g,
+                                            const uint8_t* __restrict__ fmask = nullptr) {
   double lsum = 0.0, gsum = 0.0;
   for (int z = 0; z < nz_used; ++z) {
     lsum += lossp[(size_t)z * n_act + s];
@@ -80,7 +81,9 @@ __device__ __forceinline__ double gather_fg(const CtaPar& P, int s, int n_act, i
     for (int z = 0; z < nz_used; ++z) acc += (double)gradp[((size_t)z * n_act + s) * ldx + k];
     double xk = x[k];
     if (gscale) acc *= gscale[k];
-    g[k] = acc * inv_n + l2 * xk;
+    // a feature masked out of this column (DistFeatureEliminator) keeps weight 0: with a zero
+    // gradient entry every L-BFGS direction is 0 there, i.e. the fit on the remaining columns of X
+    g[k] = (fmask && !fmask[k]) ? 0.0 : acc * inv_n + l2 * xk;
     wsq += xk * xk;
   }
   if (threadIdx.x == 0) g[d] = fit_intercept ? gsum * inv_n : 0.0;
@@ -133,7 +136,7 @@ lb_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta*
                const double* __restrict__ gsump, const float* __restrict__ gradp,
                const double* __restrict__ gscale,
                const double* __restrict__ l2v, const double* __restrict__ inv_nv,
-               int32_t* n_evals) {
+               int32_t* n_evals, const uint8_t* __restrict__ fmask) {
   __shared__ double red[8];
   const int s = blockIdx.x;
   if (s >= n_act) return;
@@ -145,7 +148,7 @@ lb_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta*
   CtaPar P{red};
   const double l2 = l2v[col], inv_n = inv_nv[col];
   double f = gather_fg(P, s, n_act, nz_used, d, ldx, fit_intercept, lossp, gsump, gradp, gscale, l2,
-                       inv_n, v.x, v.g);
+                       inv_n, v.x, v.g, fmask ? fmask + (size_t)col * d : nullptr);
   __syncthreads();
   lbfgs_advance(P, st, v, f);
   __syncthreads();
@@ -315,7 +318,7 @@ int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_int
   const int d = (int)c->d, ldx = (int)c->ldx;
   lb_step_kernel<<<n_act_in, LB_THREADS, 0, c->stream>>>(
       w.sc, w.vec, w.vec_stride, w.slot, n_act_in, nz_used, d, w.ldw, fit_intercept, w.lossp,
-      w.gsump, w.gradp, w.gscale, w.l2, w.inv_n, w.n_evals);
+      w.gsump, w.gradp, w.gscale, w.l2, w.inv_n, w.n_evals, w.fmask);
   if (w.grouped) lb_compact_grouped_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, w.n_run);
   else lb_compact_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, nullptr);
   c->launches += 2;

@@ -73,6 +73,9 @@ struct Ctx {
   TcData tc;
   ForestData forest;
   int64_t ycls_cap = 0, yreal_cap = 0, fold_cap = 0;   // allocated rows of the staged vectors (reused when large enough)
+  // per-column feature masks staged for the next skd_logreg_fit_batch (skd_stage_column_masks)
+  std::vector<uint8_t> h_fmask;
+  int32_t fmask_cols = 0;
   // scratch pool: device blocks released by finished calls, reused by the next ones (Scratch below)
   std::vector<std::pair<void*, size_t>> pool_free;
   size_t pool_bytes = 0;
@@ -189,6 +192,7 @@ struct LogregWork {
   int32_t* col_fold = nullptr; // [B]
   int32_t* col_pos = nullptr;  // [B]
   int32_t* col_neg1 = nullptr; // [B] or nullptr (see SlotMeta::pad)
+  uint8_t* fmask = nullptr;    // [B x d] or nullptr: 1 = feature takes part in the column's fit
   int32_t* n_evals = nullptr;  // [B]
   // per slot (active batch)
   SlotMeta* slot = nullptr;    // [B]

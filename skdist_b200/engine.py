@@ -95,6 +95,15 @@ class Engine:
         return ms.value * 1e-3
 
     # -- solvers ------------------------------------------------------------------
+    def stage_column_masks(self, mask):
+        """[B, d] 0/1 feature masks consumed by the next logreg_fit_batch (None clears)."""
+        if mask is None:
+            check(self._lib.skd_stage_column_masks(self._h, 0, None), self._h)
+            return
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        assert m.ndim == 2 and m.shape[1] == self.d
+        check(self._lib.skd_stage_column_masks(self._h, m.shape[0], ptr(m)), self._h)
+
     def logreg_fit_batch(self, C, col_fold, col_pos, fit_intercept=True, tol=1e-4, max_iter=100, col_neg=None):
         """B binary lbfgs fits sharing the staged X.  col_neg[j] >= 0 restricts column j to the rows
         of class col_pos[j] / col_neg[j] (one-vs-one pair); None or < 0 = one-vs-rest."""

@@ -34,8 +34,13 @@ class FakeEngine:
     def _train_mask(self, f):
         return np.ones(self.n, bool) if f < 0 else self.fold != f
 
+    def stage_column_masks(self, mask):
+        self._fmask = None if mask is None else np.asarray(mask, dtype=bool)
+
     def logreg_fit_batch(self, C, col_fold, col_pos, fit_intercept=True, tol=1e-4, max_iter=100, col_neg=None):
         B = len(C)
+        fmask = getattr(self, "_fmask", None)
+        self._fmask = None
         self.calls.append(("fit", B))
         coef = np.zeros((B, self.d + 1), np.float32)
         n_iter = np.zeros(B, np.int32)
@@ -44,9 +49,10 @@ class FakeEngine:
             if col_neg is not None and col_neg[j] >= 0:
                 m = m & ((self.y == col_pos[j]) | (self.y == col_neg[j]))
             y01 = (self.y[m] == col_pos[j]).astype(np.float32)
-            w, b, it = lo.fit_binary_lbfgs(self.X[m], y01, C=float(C[j]), tol=tol, max_iter=max_iter,
+            keep = np.arange(self.d) if fmask is None else np.flatnonzero(fmask[j])
+            w, b, it = lo.fit_binary_lbfgs(self.X[m][:, keep], y01, C=float(C[j]), tol=tol, max_iter=max_iter,
                                            fit_intercept=fit_intercept)
-            coef[j, :self.d] = w
+            coef[j, keep] = w
             coef[j, self.d] = b
             n_iter[j] = it
         return {"coef": coef, "n_iter": n_iter, "status": np.ones(B, np.int32),

@@ -363,3 +363,31 @@ def test_ovo_logreg_on_device(eng):
         assert abs(int(a.n_iter_[0]) - int(b.n_iter_[0])) <= 2
         np.testing.assert_allclose(a.coef_, b.coef_, rtol=0, atol=4e-3 * np.abs(b.coef_).max())
     assert np.mean(ovo.predict(X) == ref.predict(X)) > 0.999
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_feature_eliminator_on_device(eng):
+    """(feature set, fold) columns with per-column feature masks: the masked fit must equal
+    scikit-learn's fit on X with those columns dropped (well-conditioned problem: both converge)."""
+    from sklearn.model_selection import StratifiedKFold
+    from skdist.distribute.eliminate import DistFeatureEliminator
+    X, y = make_g1_classification(6000, 12, seed=31)
+    rng = np.random.default_rng(1)
+    X = np.hstack([X, rng.standard_normal((6000, 6)).astype(np.float32)])
+    d = X.shape[1]
+    fe = DistFeatureEliminator(LogisticRegression(C=0.05), None, step=3, cv=3, min_features_to_select=6).fit(X, y)
+    ranks = np.argsort(LogisticRegression(C=0.05).fit(X, y).coef_[0].astype(np.float64) ** 2)[: d - 6]
+    sets, k = [np.array([], int)], 0
+    while k < d - 6:
+        k += 3
+        sets.append(ranks[:k])
+    exp = []
+    for rm in sets:
+        keep = np.setdiff1d(np.arange(d), rm)
+        exp.append(np.mean([LogisticRegression(C=0.05).fit(X[tr][:, keep], y[tr]).score(X[te][:, keep], y[te])
+                            for tr, te in StratifiedKFold(3).split(X, y)]))
+    np.testing.assert_allclose(fe.scores_, exp, rtol=0, atol=FLIPS / 2000.0)
+    keep = np.asarray(fe.best_features_)
+    ref = LogisticRegression(C=0.05).fit(X[:, keep], y)
+    np.testing.assert_allclose(fe.best_estimator_.coef_, ref.coef_, rtol=0, atol=4e-3 * np.abs(ref.coef_).max())
+    assert np.mean(fe.predict(X) == ref.predict(X[:, keep])) > 0.999
