@@ -50,7 +50,8 @@ class FakeEngine:
                 m = m & ((self.y == col_pos[j]) | (self.y == col_neg[j]))
             y01 = (self.y[m] == col_pos[j]).astype(np.float32)
             keep = np.arange(self.d) if fmask is None else np.flatnonzero(fmask[j])
-            w, b, it = lo.fit_binary_lbfgs(self.X[m][:, keep], y01, C=float(C[j]), tol=tol, max_iter=max_iter,
+            Xm = self.X[m] if fmask is None else np.ascontiguousarray(self.X[m][:, keep])
+            w, b, it = lo.fit_binary_lbfgs(Xm, y01, C=float(C[j]), tol=tol, max_iter=max_iter,
                                            fit_intercept=fit_intercept)
             coef[j, keep] = w
             coef[j, self.d] = b
