@@ -15,6 +15,10 @@
 // -- so hinge-loss fits are bit-identical to scikit-learn.  No tensor cores: the work per sample
 // is two length-d vector operations per column, bound by the FP64 pipe and L2 latency.
 #include <math.h>
+#include <stdio.h>
+
+#include <chrono>
+#include <stdlib.h>
 
 #include "skd_internal.h"
 
@@ -183,6 +187,200 @@ sgd_epoch_kernel(const float* __restrict__ X, int ldx, int d, const int32_t* __r
   }
 }
 
+// Hinge loss, speculative blocks.  With hinge loss a sample whose margin y*p exceeds 1 changes
+// nothing but the lazy scale (wscale, sq_norm) and the objective sum -- scalars.  The warp therefore
+// computes the dot products of the next T = 16 samples against the CURRENT weights at once
+// (independent FMAs, all loads in flight together), reduces them with a butterfly, and then walks
+// the 16 samples in order doing only the scalar recurrence; the first margin violator (or a
+// reset_wscale) applies its weight update exactly as the sequential kernel does and the block
+// restarts behind it.  Every value is computed by the same operations in the same order as in
+// sgd_epoch_kernel, so the result stays bit-identical to scikit-learn; only the waiting changes.
+template <int DPL>
+__global__ void __launch_bounds__(128)
+sgd_epoch_spec_kernel(const float* __restrict__ X, int ldx, int d, const int32_t* __restrict__ ycls,
+                      const int32_t* __restrict__ order, const double* __restrict__ eta,
+                      const float* __restrict__ cfac, int64_t n, const int32_t* __restrict__ active,
+                      int n_active, const int32_t* __restrict__ col_pos, float* __restrict__ W, int ldw,
+                      SgdState* __restrict__ state, double alpha, int fit_intercept, double tol,
+                      int n_iter_no_change) {
+  constexpr int T = 16;                                                        // samples per block
+  constexpr int S = (64 / DPL) < 2 ? 2 : ((64 / DPL) > 8 ? 8 : (64 / DPL));   // samples per load batch
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int a = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (a >= n_active) return;
+  const int col = active[a];
+  const int pos = col_pos[col];
+  SgdState st = state[col];
+  float w[DPL];
+#pragma unroll
+  for (int j = 0; j < DPL; ++j) {
+    const int k = lane + 32 * j;
+    w[j] = k < d ? W[(size_t)col * ldw + k] : 0.f;
+  }
+  double wscale = st.wscale, sq_norm = st.sq_norm, intercept = st.intercept;
+  double objective_sum = 0.0;
+
+  int64_t i0 = 0;
+  while (i0 < n) {
+    const int Te = (int)((n - i0) < T ? (n - i0) : T);
+    // lane t < Te owns the metadata of sample i0 + t
+    int row_l = 0;
+    double y_l = 0.0, e_l = 0.0;
+    float c_l = 0.f;
+    if (lane < Te) {
+      row_l = order[i0 + lane];
+      e_l = eta[i0 + lane];
+      c_l = cfac[i0 + lane];
+      y_l = (ycls[row_l] == pos) ? 1.0 : -1.0;
+    }
+    // dot products of all block samples with the current weights
+    double part[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) part[t] = 0.0;
+    float xb[2][S][DPL];
+#pragma unroll
+    for (int s2 = 0; s2 < S; ++s2) {
+      const int r = __shfl_sync(FULL, row_l, s2);
+#pragma unroll
+      for (int j = 0; j < DPL; ++j) {
+        const int k = lane + 32 * j;
+        xb[0][s2][j] = k < ldx ? __ldg(X + (size_t)r * ldx + k) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < T / S; ++b) {
+      if (b + 1 < T / S) {
+#pragma unroll
+        for (int s2 = 0; s2 < S; ++s2) {
+          const int r = __shfl_sync(FULL, row_l, (b + 1) * S + s2);
+#pragma unroll
+          for (int j = 0; j < DPL; ++j) {
+            const int k = lane + 32 * j;
+            xb[(b + 1) & 1][s2][j] = k < ldx ? __ldg(X + (size_t)r * ldx + k) : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int s2 = 0; s2 < S; ++s2)
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) part[b * S + s2] += (double)__fmul_rn(w[j], xb[b & 1][s2][j]);
+    }
+    // butterfly reduce-scatter: afterwards lane L holds the full sum of sample L >> 1
+#pragma unroll
+    for (int half = T / 2, m = 16; half >= 1; half >>= 1, m >>= 1) {
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int q = 0; q < half; ++q) {
+        const double send = up ? part[q] : part[q + half];
+        const double keep = up ? part[q + half] : part[q];
+        part[q] = keep + __shfl_xor_sync(FULL, send, m);
+      }
+    }
+    const double mysum = part[0] + __shfl_xor_sync(FULL, part[0], 1);
+
+    // ---- ordered walk over the block, restructured so that only what is inherently serial is serial:
+    //  A. the lazy-scale recurrences wscale *= c_t, sq_norm *= c_t^2 (two chains of 16 dependent
+    //     multiplies, evaluated redundantly by every lane; lane t keeps the values BEFORE sample t);
+    //  B. lane t evaluates sample t: prediction, margin, loss and objective term;
+    //  C. the first event (margin violator or reset_wscale) is found with one ballot;
+    //  D. the objective terms of samples 0..event are added in order;
+    //  E. the event's weight update is applied exactly as in the sequential kernel.
+    float c_all[T];
+#pragma unroll
+    for (int q = 0; q < T; ++q) c_all[q] = __shfl_sync(FULL, c_l, q);
+    double my_ws = wscale, my_sq = sq_norm;        // state before this lane's sample
+    double my_ws_after = wscale, my_sq_after = sq_norm;
+    {
+      double ws = wscale, sq = sq_norm;
+#pragma unroll
+      for (int q = 0; q < T; ++q) {
+        if (lane == q) { my_ws = ws; my_sq = sq; }
+        ws *= (double)c_all[q];
+        sq *= (double)__fmul_rn(c_all[q], c_all[q]);
+        if (lane == q) { my_ws_after = ws; my_sq_after = sq; }
+      }
+    }
+    const double acc_l = __shfl_sync(FULL, mysum, (2 * lane) & 31);   // lane t < 16: dot of sample t
+    const double p_l = (double)(float)(acc_l * my_ws) + intercept;
+    const double z_l = p_l * y_l;
+    const bool viol_l = lane < Te && z_l <= 1.0;
+    const bool reset_l = lane < Te && my_ws_after < 1e-6;
+    const double loss_l = viol_l ? 1.0 - z_l : 0.0;
+    const float normf_l = (float)sqrt(my_sq);
+    const double term_l = __dadd_rn(loss_l, __dmul_rn(alpha, __dmul_rn(0.5, (double)__fmul_rn(normf_l, normf_l))));
+    const unsigned evmask = __ballot_sync(FULL, viol_l || reset_l);
+    const int ev = evmask ? __ffs(evmask) - 1 : -1;        // first event sample, -1: none in this block
+    const int last = ev >= 0 ? ev : Te - 1;                // samples 0..last are consumed
+    {
+      double terms[T];
+#pragma unroll
+      for (int q = 0; q < T; ++q) terms[q] = __shfl_sync(FULL, term_l, q);
+#pragma unroll
+      for (int q = 0; q < T; ++q)
+        if (q <= last) objective_sum = __dadd_rn(objective_sum, terms[q]);
+    }
+    wscale = __shfl_sync(FULL, my_ws_after, last);
+    sq_norm = __shfl_sync(FULL, my_sq_after, last);
+    if (ev >= 0) {
+      const bool is_reset = (evmask >> ev) & 1u ? __shfl_sync(FULL, (int)reset_l, ev) != 0 : false;
+      const bool is_viol = __shfl_sync(FULL, (int)viol_l, ev) != 0;
+      if (is_reset) {                 // reset_wscale(): sscal by float(wscale)
+        const float wf = (float)wscale;
+#pragma unroll
+        for (int j2 = 0; j2 < DPL; ++j2) w[j2] = __fmul_rn(w[j2], wf);
+        wscale = 1.0;
+      }
+      if (is_viol) {
+        const double y = __shfl_sync(FULL, y_l, ev);
+        const double e = __shfl_sync(FULL, e_l, ev);
+        const double update = -e * (-y);
+        if (update != 0.0) {           // w.add(x, update)
+          const int r = __shfl_sync(FULL, row_l, ev);
+          const float cf = (float)update, wsf = (float)wscale;
+          const double qd = (double)__fdiv_rn(cf, wsf);
+          double acc2 = 0.0;
+#pragma unroll
+          for (int j2 = 0; j2 < DPL; ++j2) {
+            const int k = lane + 32 * j2;
+            const float xv = k < ldx ? __ldg(X + (size_t)r * ldx + k) : 0.f;
+            w[j2] = (float)fma((double)xv, qd, (double)w[j2]);
+            acc2 += (double)__fmul_rn(w[j2], w[j2]);
+          }
+          acc2 = warp_sum(acc2);
+          sq_norm = acc2 * (double)__fmul_rn(wsf, wsf);
+          if (fit_intercept) intercept += update;
+        }
+      }
+    }
+    const int t = last + 1;
+    i0 += t;
+  }
+  // end of epoch (SK/linear_model/_sgd_fast.pyx.tp:570-628)
+  bool finite = isfinite(intercept);
+#pragma unroll
+  for (int j = 0; j < DPL; ++j) finite = finite && isfinite(w[j]);
+  finite = __all_sync(FULL, finite);
+#pragma unroll
+  for (int j = 0; j < DPL; ++j) {
+    const int k = lane + 32 * j;
+    if (k < d) W[(size_t)col * ldw + k] = w[j];
+  }
+  if (lane == 0) {
+    st.wscale = wscale; st.sq_norm = sq_norm; st.intercept = intercept;
+    st.t += (double)n;
+    st.n_iter += 1;
+    if (!finite) { st.done = 1; st.status = 5; }
+    else {
+      const double obj = objective_sum / (double)n;
+      if (tol > -INFINITY && obj > st.best_objective - tol) st.no_improve += 1; else st.no_improve = 0;
+      if (obj < st.best_objective) st.best_objective = obj;
+      if (st.no_improve >= n_iter_no_change) { st.done = 1; st.status = 1; }
+    }
+    state[col] = st;
+  }
+}
+
 // w.reset_wscale() at the end of _plain_sgd, then export
 __global__ void sgd_finish_kernel(const float* __restrict__ W, int ldw, int d, const SgdState* __restrict__ state,
                                   int B, float* __restrict__ coef, double* __restrict__ intercept,
@@ -214,10 +412,16 @@ static cudaError_t launch_epoch(int dpl, int grid, cudaStream_t st, const float*
                                 const float* cfac, int64_t n, const int32_t* active, int n_active,
                                 const int32_t* col_pos, float* W, int ldw, SgdState* state, double alpha,
                                 int fit_intercept, double tol, int nnc) {
+  // SKDIST_B200_SGD_SPEC=0 falls back to the one-sample-at-a-time kernel (A/B timing)
+  static const bool spec = !(getenv("SKDIST_B200_SGD_SPEC") && getenv("SKDIST_B200_SGD_SPEC")[0] == '0');
 #define SGD_CASE(D)                                                                                       \
   case D:                                                                                                 \
-    sgd_epoch_kernel<D, LOSS><<<grid, 128, 0, st>>>(X, ldx, d, ycls, order, eta, cfac, n, active, n_active, \
-                                                    col_pos, W, ldw, state, alpha, fit_intercept, tol, nnc); \
+    if (LOSS == SGD_HINGE && spec)                                                                        \
+      sgd_epoch_spec_kernel<D><<<grid, 128, 0, st>>>(X, ldx, d, ycls, order, eta, cfac, n, active, n_active, \
+                                                     col_pos, W, ldw, state, alpha, fit_intercept, tol, nnc); \
+    else                                                                                                  \
+      sgd_epoch_kernel<D, LOSS><<<grid, 128, 0, st>>>(X, ldx, d, ycls, order, eta, cfac, n, active, n_active, \
+                                                      col_pos, W, ldw, state, alpha, fit_intercept, tol, nnc); \
     break;
   switch (dpl) {
     SGD_CASE(1) SGD_CASE(2) SGD_CASE(4) SGD_CASE(8) SGD_CASE(16) SGD_CASE(32)
@@ -262,7 +466,10 @@ int sgd_fit_batch(Ctx* c, int B, const int32_t* col_pos, int loss, double alpha,
   for (int j = 0; j < B; ++j) hact[j] = j;
   for (int64_t i = 0; i < n; ++i) hord[i] = (int32_t)i;
   int n_active = B;
+  const char* trace_env = getenv("SKDIST_B200_TRACE");
+  const bool trace = trace_env && trace_env[0] == '2';
   for (int epoch = 0; epoch < max_iter && n_active > 0; ++epoch) {
+    auto tw0 = std::chrono::steady_clock::now();
     if (shuffle) {   // Fisher-Yates with the SAME seed every epoch, applied to the evolving order
       uint32_t s = seed;
       for (int64_t i = 0; i < n - 1; ++i) {
@@ -273,6 +480,7 @@ int sgd_fit_batch(Ctx* c, int B, const int32_t* col_pos, int loss, double alpha,
     if (shuffle || epoch == 0)
       SKD_CUDA(c, cudaMemcpyAsync(order, hord.data(), (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
     SKD_CUDA(c, cudaMemcpyAsync(active, hact.data(), (size_t)n_active * 4, cudaMemcpyHostToDevice, c->stream));
+    auto tw1 = std::chrono::steady_clock::now();
     const double t0 = 1.0 + (double)epoch * (double)n;
     sgd_schedule_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, t0, alpha, optimal_init, lr_type, eta0,
                                                                            power_t, eta, cfac);
@@ -286,6 +494,12 @@ int sgd_fit_batch(Ctx* c, int B, const int32_t* col_pos, int loss, double alpha,
     SKD_CUDA(c, cudaMemcpyAsync(hs.data(), state, (size_t)B * sizeof(SgdState), cudaMemcpyDeviceToHost, c->stream));
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
     c->h2d += n * 4; c->d2h += (int64_t)B * sizeof(SgdState);
+    if (trace) {
+      auto tw2 = std::chrono::steady_clock::now();
+      fprintf(stderr, "[skd trace] sgd epoch %3d active %5d host shuffle %7.2f ms device %8.2f ms\n", epoch, n_active,
+              std::chrono::duration<double, std::milli>(tw1 - tw0).count(),
+              std::chrono::duration<double, std::milli>(tw2 - tw1).count());
+    }
     n_active = 0;
     for (int j = 0; j < B; ++j)
       if (!hs[j].done) hact[n_active++] = j;
