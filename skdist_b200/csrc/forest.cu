@@ -16,6 +16,7 @@
 // RNG consumption and therefore every later draw are bit-identical to scikit-learn's.
 // No tensor cores: the work is integer histogramming, bound by gather bandwidth / latency.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -47,6 +48,7 @@ struct FoResult {          // best split of one feature in the current node
   unsigned long long sl[FO_MAXC];
 };
 constexpr int FO_KB_MAX = 8;
+constexpr int FO_SSTK = 128;     // builder-stack entries kept in shared memory (deeper ones spill to global)
 constexpr int FO_HIST_WORDS = 40 * FO_BINS;   // KB * (C + 1) * 256 <= this
 
 struct FoParams {
@@ -87,18 +89,25 @@ __device__ __forceinline__ int fo_rand_int(int low, int high, uint32_t* seed) {
 }
 
 // Gini children impurity, float64 with scikit-learn's operation order (no FMA contraction)
+template <int CM>
 __device__ __forceinline__ void fo_children_impurity(const unsigned long long* sl, const unsigned long long* st,
                                                      int C, double wl, double wr, double* il, double* ir) {
   double sql = 0.0, sqr = 0.0;
-  for (int c = 0; c < C; ++c) {
-    const double a = (double)sl[c], b = (double)(st[c] - sl[c]);
-    sql = __dadd_rn(sql, __dmul_rn(a, a));
-    sqr = __dadd_rn(sqr, __dmul_rn(b, b));
+#pragma unroll
+  for (int c = 0; c < CM; ++c) {
+    if (c < C) {
+      const double a = (double)sl[c], b = (double)(st[c] - sl[c]);
+      sql = __dadd_rn(sql, __dmul_rn(a, a));
+      sqr = __dadd_rn(sqr, __dmul_rn(b, b));
+    }
   }
   *il = __dsub_rn(1.0, __ddiv_rn(sql, __dmul_rn(wl, wl)));
   *ir = __dsub_rn(1.0, __ddiv_rn(sqr, __dmul_rn(wr, wr)));
 }
 
+// CM: compile-time bound on the class count, so the per-class arrays of a thread live in registers
+#define FOR_C(c) _Pragma("unroll") for (int c = 0; c < CM; ++c) if (c < C)
+template <int CM>
 __global__ void __launch_bounds__(FO_THREADS)
 forest_build_kernel(const FoParams P) {
   const int slot = blockIdx.x;
@@ -126,6 +135,8 @@ forest_build_kernel(const FoParams P) {
   __shared__ FoRecord rec;
   __shared__ unsigned long long best_sl[FO_MAXC];
   int2* undo = reinterpret_cast<int2*>(fo_sm + 2 * d);      // [d + 16] swap log of the speculative draws
+  float* sbv = reinterpret_cast<float*>(undo + (d + 16));   // [FO_KB_MAX][256] distinct values of the batch features
+  FoRecord* sstack = reinterpret_cast<FoRecord*>(sbv + FO_KB_MAX * FO_BINS);   // [FO_SSTK] top of the DFS stack
   const int KB = min(FO_KB_MAX, FO_HIST_WORDS / ((C + 1) * FO_BINS));
 
   // ---- initialise the tree: samples with non-zero weight in ascending order (Splitter.init) ----
@@ -133,8 +144,9 @@ forest_build_kernel(const FoParams P) {
   if (tid == 0) base_s = 0;
   for (int i = tid; i < d; i += FO_THREADS) features[i] = i;
   __syncthreads();
-  unsigned long long my_sums[FO_MAXC];
-  for (int c = 0; c < FO_MAXC; ++c) my_sums[c] = 0;
+  unsigned long long my_sums[CM];
+#pragma unroll
+  for (int c = 0; c < CM; ++c) my_sums[c] = 0;
   for (int64_t i0 = 0; i0 < n; i0 += FO_THREADS) {
     const int64_t i = i0 + tid;
     unsigned int w = 0, yc = 0;
@@ -148,7 +160,7 @@ forest_build_kernel(const FoParams P) {
     const int b = base_s;
     if (keep) {
       samp[b + off + __popc(bal & ((1u << lane) - 1))] = make_uint2((unsigned)i, (w << 8) | yc);
-      for (int c = 0; c < C; ++c) if ((int)yc == c) my_sums[c] += w;
+      FOR_C(c) if ((int)yc == c) my_sums[c] += w;
     }
     __syncthreads();
     if (tid == 0) base_s = b + tot;
@@ -159,14 +171,14 @@ forest_build_kernel(const FoParams P) {
   __shared__ unsigned long long red[FO_MAXC];
   if (tid < FO_MAXC) red[tid] = 0;
   __syncthreads();
-  for (int c = 0; c < C; ++c) {
+  FOR_C(c) {
     unsigned long long v = my_sums[c];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) atomicAdd(&red[c], v);
   }
   __syncthreads();
   double w_samples = 0.0;
-  for (int c = 0; c < C; ++c) w_samples += (double)red[c];     // weighted_n_samples (integer valued)
+  FOR_C(c) w_samples += (double)red[c];     // weighted_n_samples (integer valued)
 
   uint32_t rstate = P.rand_state[slot];
   int sp = 0;           // stack pointer
@@ -176,7 +188,7 @@ forest_build_kernel(const FoParams P) {
     r.start = 0; r.end = n_nz; r.depth = 0; r.parent = -1; r.is_left = 0; r.n_const = 0;
     r.impurity = INFINITY;
     for (int c = 0; c < FO_MAXC; ++c) r.sums[c] = c < C ? red[c] : 0;
-    stack[0] = r;
+    sstack[0] = r;
   }
   sp = 1;
   bool first = true;
@@ -184,18 +196,18 @@ forest_build_kernel(const FoParams P) {
 
   while (sp > 0 && status == 0) {
     --sp;
-    if (tid == 0) rec = stack[sp];
+    if (tid == 0) rec = sp < FO_SSTK ? sstack[sp] : stack[sp];
     __syncthreads();
     const int start = rec.start, end = rec.end, depth = rec.depth;
     const int n_node = end - start;
     double w_node = 0.0;
-    for (int c = 0; c < C; ++c) w_node += (double)rec.sums[c];
+    FOR_C(c) w_node += (double)rec.sums[c];
     double impurity = rec.impurity;
     bool is_leaf = depth >= P.max_depth || n_node < P.min_samples_split || n_node < 2 * P.min_samples_leaf ||
                    w_node < 2.0 * P.min_weight_leaf;
     if (first) {   // root: node_impurity()  (SK/tree/_criterion.pyx:620-640)
       double sq = 0.0;
-      for (int c = 0; c < C; ++c) { const double a = (double)rec.sums[c]; sq = __dadd_rn(sq, __dmul_rn(a, a)); }
+      FOR_C(c) { const double a = (double)rec.sums[c]; sq = __dadd_rn(sq, __dmul_rn(a, a)); }
       impurity = __dsub_rn(1.0, __ddiv_rn(sq, __dmul_rn(w_node, w_node)));
       first = false;
     }
@@ -256,6 +268,10 @@ forest_build_kernel(const FoParams P) {
         // --- histograms of all batch features in one pass over the node's samples ---
         const int hstride = (C + 1) * FO_BINS;
         for (int i = tid; i < nbatch * hstride; i += FO_THREADS) hist[i] = 0;
+        // the distinct values of the batch features, staged once per batch: the scan below reads
+        // them inside dependent per-candidate loops, where global/L2 latency dominated small nodes
+        for (int i = tid; i < nbatch * FO_BINS; i += FO_THREADS)
+          sbv[i] = P.binval[(size_t)items[i / FO_BINS].f * FO_BINS + (i % FO_BINS)];
         __syncthreads();
         for (int i = start + tid; i < end; i += FO_THREADS) {
           const uint2 sv = samp[i];
@@ -271,7 +287,7 @@ forest_build_kernel(const FoParams P) {
         // --- one warp per feature: scan the 256 bins (8 per lane) in ascending order ---
         for (int k = wid; k < nbatch; k += FO_THREADS / 32) {
           const unsigned int* H = hist + k * hstride;
-          const float* bv = P.binval + (size_t)items[k].f * FO_BINS;
+          const float* bv = sbv + k * FO_BINS;
           unsigned cntb[8];
           unsigned ltot = 0, pmask = 0;
 #pragma unroll
@@ -281,8 +297,8 @@ forest_build_kernel(const FoParams P) {
           for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
           pre -= ltot;
           // class-weight prefixes
-          unsigned long long clspre[FO_MAXC];
-          for (int c = 0; c < C; ++c) {
+          unsigned long long clspre[CM];
+          FOR_C(c) {
             unsigned long long t = 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) t += H[c * FO_BINS + lane * 8 + j];
@@ -311,8 +327,8 @@ forest_build_kernel(const FoParams P) {
             FoResult* R = &results[k];
             double thr = 0.0;
             unsigned nl_lane = 0;
-            unsigned long long sl[FO_MAXC];
-            for (int c = 0; c < C; ++c) sl[c] = 0;
+            unsigned long long sl[CM];
+            FOR_C(c) sl[c] = 0;
             int nin = 0;
             if (!is_const) {
               const double lo = (double)bv[gfirst], hi = (double)bv[glast];
@@ -324,13 +340,13 @@ forest_build_kernel(const FoParams P) {
                 if ((double)bv[bb] <= thr) {
                   nin += 1;
                   nl_lane += cntb[j];
-                  for (int c = 0; c < C; ++c) sl[c] += H[c * FO_BINS + bb];
+                  FOR_C(c) sl[c] += H[c * FO_BINS + bb];
                 }
               }
             }
             const unsigned n_left_u = __reduce_add_sync(0xffffffffu, nl_lane);
             const int cutbin = (int)__reduce_add_sync(0xffffffffu, (unsigned)nin) - 1;
-            for (int c = 0; c < C; ++c) {
+            FOR_C(c) {
               unsigned long long v = sl[c];
               for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
               sl[c] = v;
@@ -341,14 +357,14 @@ forest_build_kernel(const FoParams P) {
                 const int n_left = (int)n_left_u, n_right = n_node - n_left;
                 if (n_left >= P.min_samples_leaf && n_right >= P.min_samples_leaf) {
                   double wl = 0.0;
-                  for (int c = 0; c < C; ++c) wl += (double)sl[c];
+                  FOR_C(c) wl += (double)sl[c];
                   const double wr = w_node - wl;
                   if (!(wl < P.min_weight_leaf || wr < P.min_weight_leaf)) {
                     double il, ir;
-                    fo_children_impurity(sl, rec.sums, C, wl, wr, &il, &ir);
+                    fo_children_impurity<CM>(sl, rec.sums, C, wl, wr, &il, &ir);
                     R->proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
                     R->pos = start + n_left; R->il = il; R->ir = ir;
-                    for (int c = 0; c < C; ++c) R->sl[c] = sl[c];
+                    FOR_C(c) R->sl[c] = sl[c];
                   }
                 }
               }
@@ -358,17 +374,17 @@ forest_build_kernel(const FoParams P) {
           // candidates of this lane in ascending bin order
           double bproxy = -INFINITY, bil = 0.0, bir = 0.0;
           int bpos = 1 << 30, bbin = -1, bnext = -1;
-          unsigned long long bsl[FO_MAXC];
-          for (int c = 0; c < C; ++c) bsl[c] = 0;
+          unsigned long long bsl[CM];
+          FOR_C(c) bsl[c] = 0;
           if (!is_const) {
             unsigned run_cnt = pre;
-            unsigned long long sl[FO_MAXC];
-            for (int c = 0; c < C; ++c) sl[c] = clspre[c];
+            unsigned long long sl[CM];
+            FOR_C(c) sl[c] = clspre[c];
             for (int j = 0; j < 8; ++j) {
               if (!cntb[j]) continue;
               const int bb = lane * 8 + j;
               run_cnt += cntb[j];
-              for (int c = 0; c < C; ++c) sl[c] += H[c * FO_BINS + bb];
+              FOR_C(c) sl[c] += H[c * FO_BINS + bb];
               // next present bin
               const unsigned higher = pmask & ~((2u << j) - 1u);
               const int nb2 = higher ? lane * 8 + __ffs(higher) - 1 : nxt;
@@ -377,15 +393,15 @@ forest_build_kernel(const FoParams P) {
               const int n_left = (int)run_cnt, n_right = n_node - n_left;
               if (n_left < P.min_samples_leaf || n_right < P.min_samples_leaf) continue;
               double wl = 0.0;
-              for (int c = 0; c < C; ++c) wl += (double)sl[c];
+              FOR_C(c) wl += (double)sl[c];
               const double wr = w_node - wl;
               if (wl < P.min_weight_leaf || wr < P.min_weight_leaf) continue;
               double il, ir;
-              fo_children_impurity(sl, rec.sums, C, wl, wr, &il, &ir);
+              fo_children_impurity<CM>(sl, rec.sums, C, wl, wr, &il, &ir);
               const double proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
               if (proxy > bproxy) {
                 bproxy = proxy; bil = il; bir = ir; bpos = start + n_left; bbin = bb; bnext = nb2;
-                for (int c = 0; c < C; ++c) bsl[c] = sl[c];
+                FOR_C(c) bsl[c] = sl[c];
               }
             }
           }
@@ -401,7 +417,7 @@ forest_build_kernel(const FoParams P) {
           if (bpos == wpos && bproxy == wp && wp > -INFINITY) {   // unique lane: positions are unique per bin
             R->bin = bbin; R->il = bil; R->ir = bir;
             R->thr = (double)bv[bbin] / 2.0 + (double)bv[bnext] / 2.0;
-            for (int c = 0; c < C; ++c) R->sl[c] = bsl[c];
+            FOR_C(c) R->sl[c] = bsl[c];
           }
         }
         __syncthreads();
@@ -416,7 +432,7 @@ forest_build_kernel(const FoParams P) {
                 best_feature = items[k].f; best_pos = R.pos; best_bin = R.bin; best_thr = R.thr;
                 best_mgl = (R.pos - start) > (end - R.pos);
                 best_il = R.il; best_ir = R.ir;
-                for (int c = 0; c < C; ++c) best_sl[c] = R.sl[c];
+                FOR_C(c) best_sl[c] = R.sl[c];
               }
               continue;
             }
@@ -439,14 +455,12 @@ forest_build_kernel(const FoParams P) {
       }
       // restore / record the constant-feature invariants (end of node_split_best)
       if (tid == 0) {
-        for (int i = 0; i < n_known; ++i) features[i] = constant_features[i];
-        for (int i = 0; i < n_found; ++i) constant_features[n_known + i] = features[n_known + i];
         s_ctrl[2] = best_pos; s_ctrl[3] = best_feature; s_ctrl[4] = best_bin; s_ctrl[5] = n_total_constants;
         s_ctrl[6] = best_mgl;
         s_dbl[0] = best_thr; s_dbl[1] = best_il; s_dbl[2] = best_ir;
         if (best_pos < end) {
           double wl = 0.0;
-          for (int c = 0; c < C; ++c) wl += (double)best_sl[c];
+          FOR_C(c) wl += (double)best_sl[c];
           const double wr = w_node - wl;
           // impurity_improvement (SK/tree/_criterion.pyx:163-190)
           const double a = __dmul_rn(__ddiv_rn(wr, w_node), best_ir);
@@ -458,6 +472,10 @@ forest_build_kernel(const FoParams P) {
       }
       __syncthreads();
       best_pos = s_ctrl[2]; best_feature = s_ctrl[3]; best_bin = s_ctrl[4]; n_total_constants = s_ctrl[5];
+      // restore / record the constant-feature prefix (memcpy pair at the end of node_split_best),
+      // spread over the block; the next reader of these arrays is behind later barriers
+      for (int i = tid; i < n_known; i += FO_THREADS) features[i] = constant_features[i];
+      for (int i = n_known + tid; i < n_total_constants; i += FO_THREADS) constant_features[i] = features[i];
       best_mgl = s_ctrl[6];
       best_thr = s_dbl[0]; best_il = s_dbl[1]; best_ir = s_dbl[2]; best_improvement = s_dbl[3];
       is_leaf = is_leaf || best_pos >= end || (best_improvement + FO_EPSILON < P.min_impurity_decrease);
@@ -510,7 +528,7 @@ forest_build_kernel(const FoParams P) {
         P.o_feature[nb + node_id] = best_feature; P.o_thr[nb + node_id] = best_thr;
         P.o_mgl[nb + node_id] = (uint8_t)best_mgl;
       }
-      for (int c = 0; c < C; ++c)
+      FOR_C(c)
         P.o_val[(nb + node_id) * C + c] = __ddiv_rn((double)rec.sums[c], w_node);   // class fractions
     }
     node_count += 1;
@@ -522,10 +540,10 @@ forest_build_kernel(const FoParams P) {
         // right child first, then left (popped first)
         r.start = best_pos; r.end = end; r.is_left = 0; r.impurity = best_ir;
         for (int c = 0; c < FO_MAXC; ++c) r.sums[c] = c < C ? rec.sums[c] - best_sl[c] : 0;
-        stack[sp] = r;
+        if (sp < FO_SSTK) sstack[sp] = r; else stack[sp] = r;
         r.start = start; r.end = best_pos; r.is_left = 1; r.impurity = best_il;
         for (int c = 0; c < FO_MAXC; ++c) r.sums[c] = c < C ? best_sl[c] : 0;
-        stack[sp + 1] = r;
+        if (sp + 1 < FO_SSTK) sstack[sp + 1] = r; else stack[sp + 1] = r;
       }
       sp += 2;
     }
@@ -538,6 +556,8 @@ forest_build_kernel(const FoParams P) {
     P.o_status[slot] = status;
   }
 }
+
+#undef FOR_C
 
 // ------------------------------------ binning ---------------------------------------------
 // column f of X -> contiguous buffer
@@ -644,7 +664,11 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   const int d = (int)c->d;
   if ((size_t)4 * d * sizeof(int) > 6 * 1024) return fail(c, "forest: device path supports up to 384 features (shared-memory feature permutation)");
   // slots: concurrent trees per wave, bounded by memory (worst case 2*n nodes per tree)
-  const int64_t node_cap = 2 * n;
+  int64_t node_cap = 2 * n;
+  if (const char* e = getenv("SKDIST_B200_FOREST_NODECAP")) {   // experiments: smaller output arrays per tree
+    const long long v = atoll(e);
+    if (v > 0 && v < node_cap) node_cap = v;
+  }
   const size_t per_slot = (size_t)n * 16 + (size_t)node_cap * (4 * 3 + 1 + 8 * 3 + 8 * n_classes) + 4096 * sizeof(FoRecord);
   size_t free_b = 0, total_b = 0;
   SKD_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
@@ -681,7 +705,12 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   P.min_impurity_decrease = min_impurity_decrease;
   P.random_split = random_split ? 1 : 0;
   P.counts = dcounts; P.rand_state = drs; P.stack_cap = stack_cap; P.node_cap = node_cap;
-  const size_t smem = (size_t)2 * d * sizeof(int) + (size_t)(d + 16) * sizeof(int2);
+  const size_t smem = (size_t)2 * d * sizeof(int) + (size_t)(d + 16) * sizeof(int2) +
+                      (size_t)FO_KB_MAX * FO_BINS * sizeof(float) + (size_t)FO_SSTK * sizeof(FoRecord);
+  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<FO_MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   std::vector<int32_t> hcount(slots), hdepth(slots), hstatus(slots);
   SkdTreeView view;
   std::vector<int32_t> hl, hr, hf, hn; std::vector<uint8_t> hm; std::vector<double> ht, hi, hw, hv;
@@ -695,7 +724,10 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
     SKD_CUDA(c, cudaMemcpyAsync(drs, rand_states + t0, (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
     c->h2d += (int64_t)nt * n;
     P.n_trees = nt;
-    forest_build_kernel<<<nt, FO_THREADS, smem, c->stream>>>(P);
+    if (n_classes <= 2) forest_build_kernel<2><<<nt, FO_THREADS, smem, c->stream>>>(P);
+    else if (n_classes <= 4) forest_build_kernel<4><<<nt, FO_THREADS, smem, c->stream>>>(P);
+    else if (n_classes <= 8) forest_build_kernel<8><<<nt, FO_THREADS, smem, c->stream>>>(P);
+    else forest_build_kernel<FO_MAXC><<<nt, FO_THREADS, smem, c->stream>>>(P);
     c->launches += 1;
     SKD_CUDA(c, cudaGetLastError());
     SKD_CUDA(c, cudaMemcpyAsync(hcount.data(), P.o_count, nt * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -9,6 +9,7 @@ SK/tree/_splitter.pyx:155) and wraps the returned node arrays into genuine sciki
 `DecisionTreeClassifier` objects, so `estimators_`, `predict`, `predict_proba` behave as before and
 the tree structure is bit-identical under a fixed `random_state`.
 """
+import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -179,21 +180,49 @@ class _DistForestClassifier(_ScParamMixin):
         eng.stage_folds(None, 0)
         mine = parallel.shard_indices(self.n_estimators, rank, world)
         my_states = [states[i] for i in mine]
-        with ThreadPoolExecutor(max_workers=16) as ex:
-            inputs = list(ex.map(lambda s: _tree_inputs(s, n, self.bootstrap), my_states))
-        counts = None
-        if self.bootstrap:
-            counts = np.stack([c for c, _ in inputs]) if inputs else np.zeros((0, n), np.uint8)
-        rs = np.array([r for _, r in inputs], dtype=np.uint32)
-        arrays = eng.forest_fit(counts if self.bootstrap else None, rs, self.n_classes_, mf_i, max_depth, int(mss),
-                                int(msl), float(min_weight_leaf), float(self.min_impurity_decrease),
-                                splitter=self._splitter) if len(mine) else []
         tmpl = dict(criterion=self.criterion, max_depth=self.max_depth, min_samples_split=self.min_samples_split,
                     min_samples_leaf=self.min_samples_leaf, min_weight_fraction_leaf=self.min_weight_fraction_leaf,
                     max_features="sqrt" if self.max_features == "auto" else self.max_features,
                     max_leaf_nodes=self.max_leaf_nodes, min_impurity_decrease=self.min_impurity_decrease)
-        local = [_make_sklearn_tree(tmpl, s, a, d, self.n_classes_, mf_i, self._tree_cls)
-                 for s, a in zip(my_states, arrays)]
+
+        # Trees go to the device in chunks (two resident tree builders per SM).  While chunk k is
+        # being built, the host draws the bootstrap samples of chunk k+1 and wraps the node arrays
+        # of chunk k-1 into scikit-learn trees (ctypes releases the GIL during the device call).
+        chunk = int(os.environ.get("SKDIST_B200_FOREST_CHUNK", "296"))
+        chunks = [my_states[i:i + chunk] for i in range(0, len(my_states), chunk)]
+
+        def prepare(sts):
+            with ThreadPoolExecutor(max_workers=16) as ex:
+                inputs = list(ex.map(lambda st: _tree_inputs(st, n, self.bootstrap), sts))
+            counts = np.stack([c for c, _ in inputs]) if self.bootstrap else None
+            return counts, np.array([r for _, r in inputs], dtype=np.uint32)
+
+        def build(counts, rs):
+            return eng.forest_fit(counts, rs, self.n_classes_, mf_i, max_depth, int(mss), int(msl),
+                                  float(min_weight_leaf), float(self.min_impurity_decrease), splitter=self._splitter)
+
+        def wrap(sts, arrays):
+            with ThreadPoolExecutor(max_workers=8) as ex:
+                return list(ex.map(lambda sa: _make_sklearn_tree(tmpl, sa[0], sa[1], d, self.n_classes_, mf_i,
+                                                                 self._tree_cls), zip(sts, arrays)))
+
+        local = []
+        self.device_seconds_ = 0.0
+        if chunks:
+            with ThreadPoolExecutor(max_workers=1) as dev, ThreadPoolExecutor(max_workers=1) as side:
+                nxt = side.submit(prepare, chunks[0])
+                pending = None                      # (states, arrays) of the previous chunk, not yet wrapped
+                for k, sts in enumerate(chunks):
+                    counts, rs = nxt.result()
+                    fut = dev.submit(build, counts, rs)
+                    if k + 1 < len(chunks):
+                        nxt = side.submit(prepare, chunks[k + 1])
+                    if pending is not None:
+                        local.extend(wrap(*pending))
+                    arrays = fut.result()
+                    self.device_seconds_ += getattr(eng, "last_forest_seconds", 0.0)
+                    pending = (sts, arrays)
+                local.extend(wrap(*pending))
         if world > 1:
             import torch.distributed as dist
             gathered = [None] * world
