@@ -75,6 +75,7 @@ struct FoParams {
   int32_t* o_count;           // [slots] node_count
   int32_t* o_maxdepth;        // [slots]
   int32_t* o_status;          // [slots] 0 ok, 1 node capacity, 2 stack capacity
+  long long* o_prof;          // [slots][16] cycles per builder phase (SKDIST_B200_FOREST_PROF=1), else nullptr
 };
 
 __device__ __forceinline__ uint32_t fo_rand_r(uint32_t* seed) {   // SK/utils/_random.pxd:20-34
@@ -106,6 +107,7 @@ __device__ __forceinline__ void fo_children_impurity(const unsigned long long* s
 }
 
 // CM: compile-time bound on the class count, so the per-class arrays of a thread live in registers
+#define FO_TICK(ph) do { if (P.o_prof && tid == 0) { const long long _t = clock64(); prof[ph] += _t - tlast; tlast = _t; } } while (0)
 #define FOR_C(c) _Pragma("unroll") for (int c = 0; c < CM; ++c) if (c < C)
 template <int CM>
 __global__ void __launch_bounds__(FO_THREADS)
@@ -132,7 +134,7 @@ forest_build_kernel(const FoParams P) {
   __shared__ int wsum[FO_THREADS / 32][2];
   __shared__ int s_ctrl[8];
   __shared__ double s_dbl[4];
-  __shared__ FoRecord rec;
+  __shared__ FoRecord rec_spill;
   __shared__ unsigned long long best_sl[FO_MAXC];
   int2* undo = reinterpret_cast<int2*>(fo_sm + 2 * d);      // [d + 16] swap log of the speculative draws
   float* sbv = reinterpret_cast<float*>(undo + (d + 16));   // [FO_KB_MAX][256] distinct values of the batch features
@@ -180,6 +182,8 @@ forest_build_kernel(const FoParams P) {
   double w_samples = 0.0;
   FOR_C(c) w_samples += (double)red[c];     // weighted_n_samples (integer valued)
 
+  long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tlast = clock64();
   uint32_t rstate = P.rand_state[slot];
   int sp = 0;           // stack pointer
   int node_count = 0, max_depth_seen = -1, status = 0;
@@ -196,8 +200,15 @@ forest_build_kernel(const FoParams P) {
 
   while (sp > 0 && status == 0) {
     --sp;
-    if (tid == 0) rec = sp < FO_SSTK ? sstack[sp] : stack[sp];
-    __syncthreads();
+    FO_TICK(10);
+    // the popped record is read in place when it lives in the shared-memory part of the stack (its
+    // slot is only overwritten by this node's own push, after the last read)
+    if (sp >= FO_SSTK) {
+      if (tid == 0) rec_spill = stack[sp];
+      __syncthreads();
+    }
+    const FoRecord& rec = sp < FO_SSTK ? sstack[sp] : rec_spill;
+    FO_TICK(0);
     const int start = rec.start, end = rec.end, depth = rec.depth;
     const int n_node = end - start;
     double w_node = 0.0;
@@ -229,6 +240,7 @@ forest_build_kernel(const FoParams P) {
       // samples, one warp per feature scans its histogram, and thread 0 then commits the results
       // in draw order; the first feature found constant rolls the simulation back to that draw,
       // takes the constant branch and the remaining speculative results are discarded.
+      const int hstride = (C + 1) * FO_BINS;
       for (;;) {
         if (tid == 0) {
           int nbatch = 0;
@@ -261,29 +273,49 @@ forest_build_kernel(const FoParams P) {
           // keep the simulated end state for the no-rollback case
           s_ctrl[1] = s_fi; s_ctrl[7] = s_nv; s_sim_nd = s_nd; s_sim_rs = s_rs; s_sim_ulen = ulen;
           if (nbatch == 0) { f_i = s_fi; n_visited = s_nv; n_drawn = s_nd; rstate = s_rs; }
+        } else if (tid >= 32) {
+          // meanwhile the other warps clear the histograms of a full batch
+          for (int i = tid - 32; i < KB * hstride; i += FO_THREADS - 32) hist[i] = 0;
         }
         __syncthreads();
+        FO_TICK(1);
         const int nbatch = s_ctrl[0];
         if (nbatch == 0) break;
         // --- histograms of all batch features in one pass over the node's samples ---
-        const int hstride = (C + 1) * FO_BINS;
-        for (int i = tid; i < nbatch * hstride; i += FO_THREADS) hist[i] = 0;
-        // the distinct values of the batch features, staged once per batch: the scan below reads
-        // them inside dependent per-candidate loops, where global/L2 latency dominated small nodes
-        for (int i = tid; i < nbatch * FO_BINS; i += FO_THREADS)
-          sbv[i] = P.binval[(size_t)items[i / FO_BINS].f * FO_BINS + (i % FO_BINS)];
-        __syncthreads();
-        for (int i = start + tid; i < end; i += FO_THREADS) {
-          const uint2 sv = samp[i];
-          const unsigned cls = sv.y & 0xFF, wgt = sv.y >> 8;
-          for (int k = 0; k < nbatch; ++k) {
-            const unsigned bb = P.xbin[(size_t)items[k].f * n + sv.x];
-            unsigned int* H = hist + k * hstride;
-            atomicAdd(&H[cls * FO_BINS + bb], wgt);
-            atomicAdd(&H[C * FO_BINS + bb], 1u);
+        // the distinct values of the batch features are staged in the same phase (their loads overlap
+        // the gathers below); the scan reads them inside dependent per-candidate loops
+        float stage[FO_KB_MAX];   // FO_KB_MAX * 256 values / 256 threads
+#pragma unroll
+        for (int q = 0; q < FO_KB_MAX; ++q)
+          stage[q] = q < nbatch ? __ldg(P.binval + (size_t)items[q].f * FO_BINS + tid) : 0.f;
+        FO_TICK(2);
+        {
+          // all gathers of a sample are issued before the first atomic: one memory round trip per
+          // sample instead of one per feature (the dependent load -> atomic chain serialised them)
+          const uint8_t* col[FO_KB_MAX];
+#pragma unroll
+          for (int k = 0; k < FO_KB_MAX; ++k) col[k] = P.xbin + (size_t)items[k < nbatch ? k : 0].f * n;
+          for (int i = start + tid; i < end; i += FO_THREADS) {
+            const uint2 sv = samp[i];
+            const unsigned cls = sv.y & 0xFF, wgt = sv.y >> 8;
+            unsigned bbs[FO_KB_MAX];
+#pragma unroll
+            for (int k = 0; k < FO_KB_MAX; ++k) bbs[k] = k < nbatch ? (unsigned)__ldg(col[k] + sv.x) : 0u;
+#pragma unroll
+            for (int k = 0; k < FO_KB_MAX; ++k) {
+              if (k < nbatch) {
+                unsigned int* H = hist + k * hstride;
+                atomicAdd(&H[cls * FO_BINS + bbs[k]], wgt);
+                atomicAdd(&H[C * FO_BINS + bbs[k]], 1u);
+              }
+            }
           }
+#pragma unroll
+          for (int q = 0; q < FO_KB_MAX; ++q)
+            if (q < nbatch) sbv[q * FO_BINS + tid] = stage[q];
         }
         __syncthreads();
+        FO_TICK(3);
         // --- one warp per feature: scan the 256 bins (8 per lane) in ascending order ---
         for (int k = wid; k < nbatch; k += FO_THREADS / 32) {
           const unsigned int* H = hist + k * hstride;
@@ -421,6 +453,7 @@ forest_build_kernel(const FoParams P) {
           }
         }
         __syncthreads();
+        FO_TICK(4);
         // --- thread 0: commit in draw order, roll back at the first constant feature ---
         if (tid == 0) {
           bool rolled = false;
@@ -452,6 +485,7 @@ forest_build_kernel(const FoParams P) {
           if (!rolled) { f_i = s_ctrl[1]; n_visited = s_ctrl[7]; n_drawn = s_sim_nd; rstate = s_sim_rs; }
         }
         __syncthreads();
+        FO_TICK(5);
       }
       // restore / record the constant-feature invariants (end of node_split_best)
       if (tid == 0) {
@@ -471,6 +505,7 @@ forest_build_kernel(const FoParams P) {
         }
       }
       __syncthreads();
+      FO_TICK(6);
       best_pos = s_ctrl[2]; best_feature = s_ctrl[3]; best_bin = s_ctrl[4]; n_total_constants = s_ctrl[5];
       // restore / record the constant-feature prefix (memcpy pair at the end of node_split_best),
       // spread over the block; the next reader of these arrays is behind later barriers
@@ -511,6 +546,7 @@ forest_build_kernel(const FoParams P) {
       }
     }
 
+    FO_TICK(7);
     // ------------------------------- _add_node + node_value --------------------------------
     const int node_id = node_count;
     if (node_id >= P.node_cap) { status = 1; break; }
@@ -548,16 +584,19 @@ forest_build_kernel(const FoParams P) {
       sp += 2;
     }
     if (depth > max_depth_seen) max_depth_seen = depth;
+    FO_TICK(8);
     __syncthreads();
   }
   if (tid == 0) {
     P.o_count[slot] = node_count;
     P.o_maxdepth[slot] = max_depth_seen;
     P.o_status[slot] = status;
+    if (P.o_prof) for (int i = 0; i < 12; ++i) P.o_prof[(size_t)slot * 16 + i] = prof[i];
   }
 }
 
 #undef FOR_C
+#undef FO_TICK
 
 // ------------------------------------ binning ---------------------------------------------
 // column f of X -> contiguous buffer
@@ -698,6 +737,10 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   SKD_CUDA(c, sx.alloc(&P.o_count, (size_t)slots));
   SKD_CUDA(c, sx.alloc(&P.o_maxdepth, (size_t)slots));
   SKD_CUDA(c, sx.alloc(&P.o_status, (size_t)slots));
+  const bool want_prof = getenv("SKDIST_B200_FOREST_PROF") != nullptr;
+  P.o_prof = nullptr;
+  long long* d_prof = nullptr;
+  if (want_prof) SKD_CUDA(c, sx.alloc(&d_prof, (size_t)slots * 16));
   P.xbin = c->forest.xbin; P.binval = c->forest.binval; P.ycls = c->ycls;
   P.n = n; P.d = d; P.n_classes = n_classes;
   P.max_features = max_features; P.max_depth = max_depth; P.min_samples_split = min_samples_split;
@@ -705,6 +748,7 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   P.min_impurity_decrease = min_impurity_decrease;
   P.random_split = random_split ? 1 : 0;
   P.counts = dcounts; P.rand_state = drs; P.stack_cap = stack_cap; P.node_cap = node_cap;
+  P.o_prof = d_prof;
   const size_t smem = (size_t)2 * d * sizeof(int) + (size_t)(d + 16) * sizeof(int2) +
                       (size_t)FO_KB_MAX * FO_BINS * sizeof(float) + (size_t)FO_SSTK * sizeof(FoRecord);
   SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -734,6 +778,13 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
     SKD_CUDA(c, cudaMemcpyAsync(hdepth.data(), P.o_maxdepth, nt * 4, cudaMemcpyDeviceToHost, c->stream));
     SKD_CUDA(c, cudaMemcpyAsync(hstatus.data(), P.o_status, nt * 4, cudaMemcpyDeviceToHost, c->stream));
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (want_prof) {
+      std::vector<long long> hp((size_t)nt * 16);
+      cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost);
+      static const char* nm[12] = {"pop", "speculate", "zero+stage", "histogram", "scan", "commit", "restore+improve", "partition", "add_node+push", "-", "loop barrier", "-"};
+      double tot = 0; for (int i = 0; i < 12; ++i) tot += (double)hp[i];
+      for (int i = 0; i < 12; ++i) if (hp[i]) fprintf(stderr, "[skd forest prof] tree 0 %-16s %12lld cycles %5.1f%%  (%.0f per node)\n", nm[i], hp[i], 100.0 * hp[i] / tot, (double)hp[i] / hcount[0]);
+    }
     for (int s = 0; s < nt; ++s) {
       if (hstatus[s] != 0) return fail(c, hstatus[s] == 1 ? "forest: node capacity exceeded" : "forest: builder stack capacity exceeded");
       const int m = hcount[s];
