@@ -1,0 +1,41 @@
+"""Run under torchrun with N >= 2 GPUs: every sharded entry point must give, on every rank, the
+result scikit-learn gives in one process (bit-identical where the single-GPU path is)."""
+import os, sys, warnings
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.simplefilter("ignore")
+import torch, torch.distributed as dist
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", rank=rank, world_size=world)
+from sklearn.ensemble import RandomForestClassifier
+from sklearn.linear_model import LogisticRegression, Ridge, SGDClassifier
+from sklearn.multiclass import OneVsOneClassifier, OneVsRestClassifier
+from skdist.distribute.ensemble import DistRandomForestClassifier
+from skdist.distribute.multiclass import DistOneVsOneClassifier, DistOneVsRestClassifier
+from skdist.distribute.search import DistGridSearchCV, DistRandomizedSearchCV
+from skdist_b200.datasets import make_g1_regression, make_multiclass
+X, y = make_multiclass(4000, 24, 5, seed=3)
+ovr = DistOneVsRestClassifier(SGDClassifier(random_state=0), None).fit(X, y)
+ref = OneVsRestClassifier(SGDClassifier(random_state=0)).fit(X, y)
+assert all(np.array_equal(a.coef_, b.coef_) for a, b in zip(ovr.estimators_, ref.estimators_)), "ovr sgd"
+ovo = DistOneVsOneClassifier(LogisticRegression(C=0.05), None).fit(X, y)
+refo = OneVsOneClassifier(LogisticRegression(C=0.05)).fit(X, y)
+assert np.mean(ovo.predict(X) == refo.predict(X)) > 0.999, "ovo"
+Xq = np.round(X * 16).astype(np.float32)
+rf = DistRandomForestClassifier(n_estimators=7, random_state=4).fit(Xq, y)
+rr = RandomForestClassifier(n_estimators=7, random_state=4).fit(Xq, y)
+assert all(np.array_equal(a.tree_.threshold, b.tree_.threshold) for a, b in zip(rf.estimators_, rr.estimators_)), "forest"
+np.testing.assert_array_equal(rf.predict_proba(Xq[:200]), rr.predict_proba(Xq[:200]))
+Xr, yr = make_g1_regression(5000, 16, seed=5)
+rs = DistRandomizedSearchCV(Ridge(), {"alpha": list(np.logspace(-2, 2, 30))}, None, n_iter=11, random_state=0, cv=3).fit(Xr, yr)
+from sklearn.model_selection import RandomizedSearchCV
+rref = RandomizedSearchCV(Ridge(), {"alpha": list(np.logspace(-2, 2, 30))}, n_iter=11, random_state=0, cv=3).fit(Xr, yr)
+np.testing.assert_allclose(rs.cv_results_["mean_test_score"], rref.cv_results_["mean_test_score"], atol=2e-4)
+assert rs.best_params_ == rref.best_params_, "ridge"
+gathered = [None] * world
+dist.all_gather_object(gathered, float(rs.cv_results_["mean_test_score"].sum()))
+assert len(set(gathered)) == 1, "ranks disagree"
+print("rank %d/%d: multi-GPU checks passed" % (rank, world))
+dist.destroy_process_group()
