@@ -40,7 +40,7 @@ def parse():
     p.add_argument("--d", type=int, default=256)
     p.add_argument("--candidates", type=int, default=512)
     p.add_argument("--folds", type=int, default=5)
-    p.add_argument("--cpu-sample", type=int, default=2, help="fits timed for cpu_baseline (0 = skip)")
+    p.add_argument("--cpu-sample", type=int, default=8, help="fits timed for cpu_baseline (0 = skip)")
     p.add_argument("--kernel", type=int, default=0, help="0 auto, 1 SIMT fp32, 2 tcgen05")
     return p.parse_args()
 
@@ -113,30 +113,44 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_fits_per_sec(X, y, fold, Cs, n_fits, n_jobs=1):
+def cpu_fits_per_sec(X, y, fold, Cs, n_fits, n_jobs=None):
     """The reference's sc=None branch (search.py:388-409): the same per-task function
-    (oracle.search_oracle.fit_and_score <- search.py:180-288) on the host cores, on a bounded
-    sample of (candidate, fold) tasks of the same workload."""
-    from joblib import Parallel, delayed
+    (oracle.search_oracle.fit_and_score <- search.py:180-288) fanned out with joblib over the host
+    cores, on a bounded sample of (candidate, fold) tasks of the same workload.  One wave of
+    n_jobs = min(n_fits, 32, cores) worker processes, each with cores // n_jobs BLAS threads (the
+    faster of the two ways to use the box: a single process with all BLAS threads is limited by one
+    sgemv stream).  Thread counts are set explicitly (torchrun exports OMP_NUM_THREADS=1).
+    Returns (fits/s, seconds, scores, n_jobs, inner_threads)."""
+    from joblib import Parallel, delayed, parallel_config
     from sklearn.linear_model import LogisticRegression
     from sklearn.metrics import check_scoring
+    from threadpoolctl import threadpool_limits
     from oracle.search_oracle import fit_and_score
     est = LogisticRegression()
     scorer = check_scoring(est)
     n_folds = int(fold.max()) + 1
+    cores = os.cpu_count() or 1
+    if n_jobs is None:
+        n_jobs = max(1, min(n_fits, 32, cores))
+    inner = max(1, cores // n_jobs)
     # stratified sample over the C grid, fold cycling
     idx = np.linspace(0, len(Cs) - 1, n_fits).round().astype(int)
     tasks = []
     for t, ci in enumerate(idx):
         f = t % n_folds
         tasks.append(({"C": float(Cs[ci])}, np.flatnonzero(fold != f), np.flatnonzero(fold == f)))
-    t0 = time.time()
     import warnings
+    t0 = time.time()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        out = Parallel(n_jobs=n_jobs)(delayed(fit_and_score)(est, X, y, scorer, tr, te, p) for p, tr, te in tasks)
+        if n_jobs == 1:
+            with threadpool_limits(limits=inner):
+                out = [fit_and_score(est, X, y, scorer, tr, te, p) for p, tr, te in tasks]
+        else:
+            with parallel_config(backend="loky", n_jobs=n_jobs, inner_max_num_threads=inner):
+                out = Parallel()(delayed(fit_and_score)(est, X, y, scorer, tr, te, p) for p, tr, te in tasks)
     dt = time.time() - t0
-    return len(tasks) / dt, dt, [o[0]["score"] for o in out]
+    return len(tasks) / dt, dt, [o[0]["score"] for o in out], n_jobs, inner
 
 
 def fold_ids(y, n_folds):
@@ -162,15 +176,17 @@ def run_reference(a):
     fold = fold_ids(y, a.folds)
     Cs = np.logspace(-4, 4, a.candidates)
     cores = os.cpu_count() or 1
-    per_step = max(1, a.cpu_sample)
+    # one wave of worker processes per step; fewer fits per step when many steps are requested so
+    # that the whole run stays within a few minutes
+    per_step = max(1, a.cpu_sample if a.steps <= 3 else (a.cpu_sample // 2 if a.steps <= 6 else a.cpu_sample // 4))
     vals = []
     for s in range(a.warmup + a.steps):
         # warm-up steps of a CPU arm only need to page the data in: one short fit
         if s < a.warmup:
-            cpu_fits_per_sec(X[: max(1000, a.n // 50)], y[: max(1000, a.n // 50)],
-                             fold[: max(1000, a.n // 50)], Cs, 1)
+            st = max(1, a.n // 20000)          # strided subsample: every fold stays populated
+            cpu_fits_per_sec(np.ascontiguousarray(X[::st]), y[::st], fold[::st], Cs, 1)
             continue
-        v, dt, _ = cpu_fits_per_sec(X, y, fold, Cs, per_step, n_jobs=1)
+        v, dt, _, nj, inner = cpu_fits_per_sec(X, y, fold, Cs, per_step)
         vals.append((v, dt))
     tot_fits = per_step * len(vals)
     tot_t = sum(dt for _, dt in vals)
@@ -181,8 +197,8 @@ def run_reference(a):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": workload_name(a), "inputs": "exceed L2"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d (candidate, fold) fits per step, C spread over the grid, BLAS threads=%d "
-                                   "(reference sc=None branch: joblib n_jobs=1 x threaded BLAS)" % (per_step, cores)},
+                         "sample": "%d (candidate, fold) fits per step, C spread over the grid, joblib n_jobs=%d x %d BLAS "
+                                   "threads (reference sc=None branch, search.py:388-409)" % (per_step, nj, inner)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -318,12 +334,12 @@ def main():
             line["roofline"]["traffic_source"] = tj["source"]
         if world == 1 and a.cpu_sample > 0:
             cores = os.cpu_count() or 1
-            v, dt, _ = cpu_fits_per_sec(X, y, fold, Cs, a.cpu_sample, n_jobs=1)
+            v, dt, _, nj, inner = cpu_fits_per_sec(X, y, fold, Cs, a.cpu_sample)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "%d (candidate, fold) fits of the same workload in %.1f s, C spread over the grid, "
-                          "joblib n_jobs=1 x %d BLAS threads (reference sc=None branch, search.py:388-409)"
-                          % (a.cpu_sample, dt, cores)}
+                          "joblib n_jobs=%d x %d BLAS threads (reference sc=None branch, search.py:388-409)"
+                          % (a.cpu_sample, dt, nj, inner)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
