@@ -56,7 +56,9 @@ static int alloc_eval_buffers(Ctx* c, Scratch& sx, LogregWork& w, int B, int slo
   w.use_tc = want_tc(c);
   if (slot_cap < B) slot_cap = B;
   w.slot_cap = slot_cap;
-  w.cap_sc = (int64_t)4 * c->sm_count * 64 + slot_cap + 64;
+  // partial sums per slot: row chunks of the SIMT grid, or the fixed chunk count of the tensor-core kernel
+  w.cap_sc = w.use_tc ? (int64_t)tc_partials_per_slot() * round_up(slot_cap, 128)
+                      : (int64_t)4 * c->sm_count * 64 + slot_cap + 64;
   w.nz = 1024;
   SKD_CUDA(c, sx.alloc(&w.lossp, (size_t)w.cap_sc));
   SKD_CUDA(c, sx.alloc(&w.gsump, (size_t)w.cap_sc));

@@ -38,6 +38,7 @@ namespace skd {
 constexpr int TC_BC = 128;       // slots per group
 constexpr int TC_R = 64;         // rows per tile
 constexpr int TC_NS = 5;         // ring slots (half tiles)
+constexpr int TC_NCH = 56;       // fixed row chunks per group: one partial sum per (chunk, slot)
 constexpr int TC_EPI_WARPS = 16;    // four per TMEM lane quadrant
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
@@ -391,8 +392,6 @@ struct TcParams {
   const float* rowsg;        // TC_FIT_UNI: [n_lists x npad] per-row -y * 2^14 (0 = not a training row of that list)
   long long rowsg_ld;
   int debug;                 // SKDIST_B200_TC_DEBUG (timing experiments only): 2 = no GEMM2, 3 = no MMAs, 4 = no epilogue work
-  int parts;                 // > 0: aligned split (CTA = (group, part), same row ranges for every group)
-                             // 0  : balanced split (groups * n_tiles units cut into gridDim.x ranges)
 };
 
 struct __align__(8) TcBarriers {
@@ -407,24 +406,6 @@ struct __align__(8) TcBarriers {
   uint32_t tmem_base;
   uint32_t pad;
 };
-
-// Work split: the (group, tile) pairs form one list of groups * n_tiles units, cut into
-// gridDim.x equal contiguous ranges, one per CTA, so every SM gets the same number of tiles.
-// A CTA's range touches one or two groups ("items"); the partial results of item (g, cta)
-// go to partial index z = cta - first_cta(g).
-struct TcRange {
-  long long u0, u1;
-};
-__device__ __forceinline__ long long tc_unit_begin(long long cta, long long units, long long grid) {
-  return cta * units / grid;
-}
-__device__ __forceinline__ int tc_first_cta(int g, int n_tiles, long long units, int grid) {
-  long long u = (long long)g * n_tiles;
-  long long c = u * grid / units;
-  while (c + 1 < grid && tc_unit_begin(c + 1, units, grid) <= u) ++c;
-  while (c > 0 && tc_unit_begin(c, units, grid) > u) --c;
-  return (int)c;
-}
 
 // TC_FIT_UNI: fit where every slot of a group shares (held-out fold, positive class): the row's
 // sign/mask comes from a precomputed per-fold array instead of being decoded per element
@@ -467,48 +448,53 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
 
-  const long long units = (long long)prm.groups * prm.n_tiles;
-  long long u_begin, u_end;
-  const int32_t* tlist = nullptr;   // aligned split + fold-grouped slots: this group's tile list
-  if (prm.parts > 0) {
-    // aligned: all groups stream the same rows at the same time -> X is fetched from HBM once
-    // and the other groups hit L2.  A group whose 128 columns hold out the same fold only visits
-    // the tiles that contain training rows of that fold (its list); the others are skipped.
-    const int gg = blockIdx.x / prm.parts, pp = blockIdx.x % prm.parts;
+  // Work split.  A group's tile list (all tiles, or the tiles with training rows of the group's
+  // fold) is cut into TC_NCH fixed chunks; a unit = (group, chunk); the groups * TC_NCH units are
+  // dealt to the CTAs in contiguous ranges.  A chunk is always accumulated by ONE CTA from a zeroed
+  // accumulator and written to partial slot `chunk`, so the partial sums -- and with them every
+  // fitted coefficient -- do not depend on the grid, on how many columns share the batch, or on how
+  // many GPUs the columns were dealt to.  (The host picks grid = groups * parts so that all groups
+  // stream the same rows at the same time and X comes from HBM about once.)
+  const long long units = (long long)prm.groups * TC_NCH;
+  const long long u_begin = (long long)blockIdx.x * units / gridDim.x;
+  const long long u_end = (long long)(blockIdx.x + 1) * units / gridDim.x;
+  struct TcItem { int g, z, t0, t1; const int32_t* tl; };
+  auto get_item = [&](long long u, TcItem& it) -> bool {
+    it.g = (int)(u / TC_NCH);
+    it.z = (int)(u % TC_NCH);
     int cnt = prm.n_tiles;
+    it.tl = nullptr;
     if (prm.tilelist) {
-      const int f = prm.sp[gg * TC_BC].fold;
+      const int f = prm.sp[it.g * TC_BC].fold;
       const int li = (f >= 0 && f < prm.n_lists - 1) ? f : prm.n_lists - 1;
-      tlist = prm.tilelist + (size_t)li * prm.n_tiles_ld;
+      it.tl = prm.tilelist + (size_t)li * prm.n_tiles_ld;
       cnt = prm.tilecnt[li];
     }
-    u_begin = (long long)gg * prm.n_tiles + (long long)pp * cnt / prm.parts;
-    u_end = (long long)gg * prm.n_tiles + (long long)(pp + 1) * cnt / prm.parts;
-  } else {
-    u_begin = tc_unit_begin(blockIdx.x, units, gridDim.x);
-    u_end = tc_unit_begin(blockIdx.x + 1, units, gridDim.x);
-  }
-  const int g_first = (int)(u_begin / prm.n_tiles);
-  const int g_last = u_end > u_begin ? (int)((u_end - 1) / prm.n_tiles) : g_first - 1;
-  // item (group g) of this CTA covers tiles [t0, t1)
-#define TC_ITEM_RANGE(g, t0, t1)                                                     \
-  const long long _gb = (long long)(g) * prm.n_tiles;                                \
-  const int t0 = (int)((u_begin > _gb ? u_begin : _gb) - _gb);                       \
-  const int t1 = (int)((u_end < _gb + prm.n_tiles ? u_end : _gb + prm.n_tiles) - _gb);
+    it.t0 = (int)((long long)cnt * it.z / TC_NCH);
+    it.t1 = (int)((long long)cnt * (it.z + 1) / TC_NCH);
+    return it.t1 > it.t0;       // empty chunks (fewer tiles than chunks) are skipped by every role alike
+  };
 
   if (warp == 0) {
     // ================================ TMA producer ==========================================
     if (lane == 0) {
       uint32_t h = 0;  // running half-tile counter (ring position), persists across items
-      int it_local = 0;
-      for (int g = g_first; g <= g_last; ++g, ++it_local) {
-        TC_ITEM_RANGE(g, t0, t1)
-        // W_hi of this group: wait until the previous item's MMAs are done with the buffer
-        if (it_local > 0) mbar_wait(&bars->acc_done, (it_local - 1) & 1, 100);
-        mbar_expect_tx(&bars->w_full, NCHUNK * WH_CHUNK);
+      int it_local = 0, g_prev = -1;
+      for (long long u = u_begin; u < u_end; ++u) {
+        TcItem it;
+        if (!get_item(u, it)) continue;
+        const int g = it.g, t0 = it.t0, t1 = it.t1;
+        const int32_t* tlist = it.tl;
+        if (g != g_prev) {
+          // W_hi of a new group: wait until the previous item's MMAs are done with the buffer
+          if (it_local > 0) mbar_wait(&bars->acc_done, (it_local - 1) & 1, 100);
+          mbar_expect_tx(&bars->w_full, NCHUNK * WH_CHUNK);
 #pragma unroll
-        for (int c = 0; c < NCHUNK; ++c)
-          tma_load_2d(s_wh + c * WH_CHUNK, &map_wh, c * 64, g * TC_BC, &bars->w_full);
+          for (int c = 0; c < NCHUNK; ++c)
+            tma_load_2d(s_wh + c * WH_CHUNK, &map_wh, c * 64, g * TC_BC, &bars->w_full);
+          g_prev = g;
+        }
+        ++it_local;
         for (int t = t0; t < t1; ++t) {
           const int tile = tlist ? tlist[t] : t;
 #pragma unroll
@@ -539,12 +525,17 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
       const uint64_t bmn_base = make_desc(smem_u32(s_ring), X_CHUNK, 1024);    // MN-major view
       uint32_t h = 0;       // half-tile counter, mirrors the producer
       uint32_t tcount = 0;  // tile counter (Z buffer = tcount & 1)
-      int it_local = 0;
-      for (int g = g_first; g <= g_last; ++g, ++it_local) {
-        TC_ITEM_RANGE(g, t0, t1)
-        const int nt = t1 - t0;
-        mbar_wait(&bars->w_full, it_local & 1, 200);
-        mbar_wait(&bars->wl_full, it_local & 1, 201);
+      int it_local = 0, w_loads = 0, g_prev = -1;
+      for (long long u = u_begin; u < u_end; ++u, ++it_local) {
+        TcItem it;
+        if (!get_item(u, it)) { --it_local; continue; }
+        const int nt = it.t1 - it.t0;
+        if (it.g != g_prev) {       // weights of a new group (W_hi by TMA, W_lo staged by the epilogue warps)
+          mbar_wait(&bars->w_full, w_loads & 1, 200);
+          mbar_wait(&bars->wl_full, w_loads & 1, 201);
+          ++w_loads;
+          g_prev = it.g;
+        }
         if (it_local > 0) mbar_wait(&bars->acc_free, (it_local - 1) & 1, 202);
         tc_fence_after();
 
@@ -651,12 +642,16 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
     const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
     constexpr float INV_G = 1.f / GSCALE;
     uint32_t tcount = 0;
-    int it_local = 0;
-    for (int g = g_first; g <= g_last; ++g, ++it_local) {
-      TC_ITEM_RANGE(g, t0, t1)
+    int it_local = 0, g_prev = -1;
+    for (long long u = u_begin; u < u_end; ++u, ++it_local) {
+      TcItem it;
+      if (!get_item(u, it)) { --it_local; continue; }
+      const int g = it.g, t0 = it.t0, t1 = it.t1;
+      const int32_t* tlist = it.tl;
       const int nt = t1 - t0;
-      const int z_part = prm.parts > 0 ? (int)blockIdx.x % prm.parts
-                                       : (int)blockIdx.x - tc_first_cta(g, prm.n_tiles, units, gridDim.x);
+      const int z_part = it.z;
+      const bool new_group = g != g_prev;
+      g_prev = g;
       const int slot = g * TC_BC + lane_in_group;
       const bool valid = slot < prm.n_act;
       TcSlotParam sp;
@@ -672,7 +667,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
         const int li = (f >= 0 && f < prm.n_lists - 1) ? f : prm.n_lists - 1;
         rsg = prm.rowsg + (size_t)li * prm.rowsg_ld;
       }
-      {  // W_lo row of this slot -> TMEM (packed fp16 pairs), 16 columns (32 values) at a time.
+      if (new_group) {  // W_lo row of this slot -> TMEM (packed fp16 pairs), 16 columns (32 values) at a time.
          // The previous item's MMAs are done with W_lo: its acc_done was waited for below.
         const uint32_t* src = reinterpret_cast<const uint32_t*>(prm.Wl + (size_t)slot * (NCHUNK * 64));
 #pragma unroll 1
@@ -860,7 +855,6 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
       mbar_arrive(&bars->acc_free);
     }
   }
-#undef TC_ITEM_RANGE
 
   // teardown
   tc_fence_before();
@@ -987,6 +981,8 @@ int tc_prepare(Ctx* c) {
       SKD_CUDA(c, cudaMemcpyAsync(t.tilelist, hl.data(), hl.size() * 4, cudaMemcpyHostToDevice, c->stream));
       SKD_CUDA(c, cudaMemcpyAsync(t.tilecnt, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice, c->stream));
       SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+      t.min_list_tiles = n_tiles;
+      for (int f = 0; f <= nf; ++f) t.min_list_tiles = std::min(t.min_list_tiles, (int)hc[f]);
       if (t.rowsg && t.n_lists != nf + 1) { cudaFree(t.rowsg); t.rowsg = nullptr; }
       t.n_lists = nf + 1;
       t.rowsg_valid = false;
@@ -1013,15 +1009,7 @@ int tc_export(Ctx* c, LogregWork& w, int n_act_upper, const double* xin, int fit
 }
 
 size_t tc_slot_param_bytes() { return sizeof(TcSlotParam); }
-
-// host mirror of the in-kernel work split
-static long long h_unit_begin(long long cta, long long units, long long grid) { return cta * units / grid; }
-static int h_cta_of_unit(long long u, long long units, int grid) {
-  long long c = u * grid / units;
-  while (c + 1 < grid && h_unit_begin(c + 1, units, grid) <= u) ++c;
-  while (c > 0 && h_unit_begin(c, units, grid) > u) --c;
-  return (int)c;
-}
+int tc_partials_per_slot() { return TC_NCH; }
 
 template <int MODE>
 static cudaError_t tc_launch(int nchunk, int grid, size_t smem, cudaStream_t st, const CUtensorMap& xh,
@@ -1054,38 +1042,25 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   const int nchunk = t.dpad / 64;
   const int groups = (n_act + TC_BC - 1) / TC_BC;
   const int n_tiles = (int)(t.npad / TC_R);
-  const long long units = (long long)groups * n_tiles;
+  // Grid: units = (group, chunk) pairs (see the kernel).  With few groups every group gets the same
+  // number of CTAs ("parts", at most one per chunk), so all groups stream the same rows at the same
+  // time and the other groups' reads hit L2; with many groups the units are simply dealt evenly.
+  const long long units = (long long)groups * TC_NCH;
   int grid = c->sm_count;
+  int parts = groups <= c->sm_count ? c->sm_count / groups : 0;
+  if (parts > TC_NCH) parts = TC_NCH;
+  if (parts > 0) grid = groups * parts;
   if ((long long)grid > units) grid = (int)units;
-  // Work split.  "aligned" (default when it keeps >= 90 % of the SMs busy): parts = SMs / groups
-  // CTAs per group, every group cut at the same rows.  Otherwise "balanced" contiguous ranges.
-  int parts = 0;
-  {
-    const char* env = getenv("SKDIST_B200_TC_SPLIT");
-    int p_al = groups <= c->sm_count ? c->sm_count / groups : 0;
-    if (p_al > n_tiles) p_al = n_tiles;
-    bool want_aligned = p_al > 0 && (double)(groups * p_al) >= 0.90 * c->sm_count;
-    if (env && !strcmp(env, "balanced")) want_aligned = false;
-    if (env && !strcmp(env, "aligned") && p_al > 0) want_aligned = true;
-    if (want_aligned) parts = p_al;
-  }
-  int nz = 1;
-  if (parts > 0) {
-    grid = groups * parts;
-    nz = parts;
-  } else {
-    // partial slots needed: the largest number of CTAs that share one group
-    for (int g = 0; g < groups; ++g) {
-      int c0 = h_cta_of_unit((long long)g * n_tiles, units, grid);
-      int c1 = h_cta_of_unit((long long)(g + 1) * n_tiles - 1, units, grid);
-      if (c1 - c0 + 1 > nz) nz = c1 - c0 + 1;
-    }
-  }
+  const int nz = TC_NCH;
   if (mode == TC_FIT) {
     if ((int64_t)nz * n_act > w.cap_sc) return fail(c, "tc_eval: partial buffer too small");
-    SKD_CUDA(c, cudaMemsetAsync(w.lossp, 0, (size_t)nz * n_act * sizeof(double), c->stream));
-    SKD_CUDA(c, cudaMemsetAsync(w.gsump, 0, (size_t)nz * n_act * sizeof(double), c->stream));
-    SKD_CUDA(c, cudaMemsetAsync(w.gradp, 0, (size_t)nz * n_act * w.ldw * sizeof(float), c->stream));
+    // every (chunk, slot) partial has exactly one writer; only chunks without tiles (fewer tiles
+    // than chunks in some list) are never written and must read as zero
+    if (t.min_list_tiles < TC_NCH) {
+      SKD_CUDA(c, cudaMemsetAsync(w.lossp, 0, (size_t)nz * n_act * sizeof(double), c->stream));
+      SKD_CUDA(c, cudaMemsetAsync(w.gsump, 0, (size_t)nz * n_act * sizeof(double), c->stream));
+      SKD_CUDA(c, cudaMemsetAsync(w.gradp, 0, (size_t)nz * n_act * w.ldw * sizeof(float), c->stream));
+    }
   }
   CUtensorMap map_wh;
   if (make_map(c, &map_wh, w.Wh, (uint64_t)w.slots_pad_cap, (uint64_t)t.dpad, TC_BC)) return 1;
@@ -1103,7 +1078,6 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   prm.groups = groups;
   prm.n_tiles = n_tiles;
   prm.ldw = w.ldw;
-  prm.parts = parts;
   { const char* dbg = getenv("SKDIST_B200_TC_DEBUG"); prm.debug = dbg ? atoi(dbg) : 0; }
   const bool uni = mode == TC_FIT && w.grouped && w.uni_pos >= 0 && c->ycls;
   if (uni && (!t.rowsg_valid || t.rowsg_pos != w.uni_pos)) {
@@ -1117,7 +1091,7 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   }
   prm.rowsg = uni ? t.rowsg : nullptr;
   prm.rowsg_ld = t.npad;
-  const bool lists = mode == TC_FIT && parts > 0 && w.grouped && t.tilelist;
+  const bool lists = mode == TC_FIT && w.grouped && t.tilelist;
   prm.tilelist = lists ? t.tilelist : nullptr;
   prm.tilecnt = lists ? t.tilecnt : nullptr;
   prm.n_lists = t.n_lists;

@@ -26,6 +26,7 @@ struct TcData {
   int32_t* tilelist = nullptr; // [(n_lists) x n_tiles] tiles that contain at least one TRAINING row of fold f
   int32_t* tilecnt = nullptr;  // [n_lists]; list index f for fold f, n_lists-1 = every tile (no held-out fold)
   int n_lists = 0;
+  int min_list_tiles = 0;      // shortest tile list (chunks without tiles need zeroed partials)
   float* rowsg = nullptr;      // [n_lists x npad] -y * 2^14 per row for positive class rowsg_pos; 0 = not a training row
   int32_t rowsg_pos = -1;
   bool rowsg_valid = false;
@@ -249,6 +250,7 @@ int tc_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used);
 int tc_score(Ctx* c, LogregWork& w, int n_act, int64_t* dcorrect, int64_t* dcount);
 int tc_r2(Ctx* c, LogregWork& w, int n_act, double* dsse, int64_t* dcount);
 size_t tc_slot_param_bytes();
+int tc_partials_per_slot();
 
 // device L-BFGS (lbfgs_dev.cu)
 int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max_iter);

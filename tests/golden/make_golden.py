@@ -66,7 +66,7 @@ def run_case(name, X, y, grid, cv, ref_search):
     rng = np.random.default_rng(12345)
     noise_flips = np.zeros((len(cands), n_splits), np.int64)
     noise_coef = np.zeros((len(cands), n_splits))
-    for variant in range(4):
+    for variant in range(12):       # 1 thread, default threads, then 10 row permutations
         for ci, p in enumerate(cands):
             for fi, (tr, te) in enumerate(splits):
                 trv = tr if variant < 2 else tr[rng.permutation(len(tr))]

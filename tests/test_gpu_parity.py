@@ -391,3 +391,33 @@ def test_feature_eliminator_on_device(eng):
     ref = LogisticRegression(C=0.05).fit(X[:, keep], y)
     np.testing.assert_allclose(fe.best_estimator_.coef_, ref.coef_, rtol=0, atol=4e-3 * np.abs(ref.coef_).max())
     assert np.mean(fe.predict(X) == ref.predict(X[:, keep])) > 0.999
+
+
+def test_tc_column_result_independent_of_batch():
+    """tcgen05 path: partial sums are formed over fixed row chunks, so a (C, fold) column gets the
+    same bits whether it is fitted alone, in a small batch or among hundreds of columns (and hence
+    on however many GPUs the columns are dealt to)."""
+    from skdist_b200.engine import Engine
+    e = Engine(0)
+    try:
+        e.set_kernel(2)
+        X, y = make_g1_classification(30000, 48, seed=41)
+        from sklearn.model_selection import StratifiedKFold
+        fold = np.zeros(len(y), np.int8)
+        for k, (_, te) in enumerate(StratifiedKFold(4).split(X, y)):
+            fold[te] = k
+        e.stage_x(X); e.stage_labels(y.astype(np.int32)); e.stage_folds(fold, 4)
+        Cs = np.repeat(np.logspace(-3, 2, 90), 4)
+        fs = np.tile(np.arange(4, dtype=np.int32), 90)
+        pos = np.ones(len(Cs), np.int32)
+        big = e.logreg_fit_batch(Cs, fs, pos)
+        pick = np.array([5, 17, 130, 131, 222, 359])
+        small = e.logreg_fit_batch(Cs[pick], fs[pick], pos[pick])
+        np.testing.assert_array_equal(small["coef"], big["coef"][pick])
+        np.testing.assert_array_equal(small["n_iter"], big["n_iter"][pick])
+        one = e.logreg_fit_batch(Cs[[222]], fs[[222]], pos[[222]])
+        np.testing.assert_array_equal(one["coef"][0], big["coef"][222])
+        again = e.logreg_fit_batch(Cs, fs, pos)
+        np.testing.assert_array_equal(again["coef"], big["coef"])            # run-to-run deterministic
+    finally:
+        e.close()
