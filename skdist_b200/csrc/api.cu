@@ -920,12 +920,12 @@ static void forest_sink(void* arg, int t, const SkdTreeView* v) {
 int skd_forest_fit(skd_ctx* ctx, int32_t n_trees, const uint8_t* sample_counts, const uint32_t* rand_states,
                    int32_t n_classes, int32_t max_features, int32_t max_depth, int32_t min_samples_split,
                    int32_t min_samples_leaf, double min_weight_leaf, double min_impurity_decrease,
-                   int32_t splitter, skd_forest** out, double* gpu_seconds_out) {
+                   int32_t splitter, const double* y_regression, skd_forest** out, double* gpu_seconds_out) {
   if (!ctx) return fail(nullptr, "skd_forest_fit: ctx is NULL");
   Ctx* c = &ctx->c;
   if (!out) return fail(c, "skd_forest_fit: out is NULL");
   *out = nullptr;
-  if (!c->X || !c->ycls) return fail(c, "skd_forest_fit: stage X and labels first");
+  if (!c->X || (!y_regression && !c->ycls)) return fail(c, "skd_forest_fit: stage X and labels first");
   if (n_trees <= 0 || !rand_states || max_features < 1 || min_samples_split < 2 || min_samples_leaf < 1 ||
       splitter < 0 || splitter > 1)
     return fail(c, "skd_forest_fit: bad arguments");
@@ -937,7 +937,7 @@ int skd_forest_fit(skd_ctx* ctx, int32_t n_trees, const uint8_t* sample_counts, 
   SKD_CUDA(c, cudaEventCreate(&e1));
   SKD_CUDA(c, cudaEventRecord(e0, c->stream));
   int rc = forest_fit(c, n_trees, sample_counts, rand_states, n_classes, max_features, max_depth, min_samples_split,
-                      min_samples_leaf, min_weight_leaf, min_impurity_decrease, splitter, forest_sink, f);
+                      min_samples_leaf, min_weight_leaf, min_impurity_decrease, splitter, y_regression, forest_sink, f);
   float ms = 0.f;
   if (!rc) {
     cudaEventRecord(e1, c->stream);

@@ -54,7 +54,8 @@ constexpr int FO_HIST_WORDS = 40 * FO_BINS;   // KB * (C + 1) * 256 <= this
 struct FoParams {
   const uint8_t* xbin;        // [d][n] bin codes, feature-major
   const float* binval;        // [d][256] distinct values ascending
-  const int32_t* ycls;        // [n]
+  const int32_t* ycls;        // [n] class ids (classification)
+  const double* yreal;        // [n] float64 targets (regression: MSE criterion), else nullptr
   int64_t n;
   int d, n_classes;
   int max_features, max_depth, min_samples_split, min_samples_leaf;
@@ -106,16 +107,42 @@ __device__ __forceinline__ void fo_children_impurity(const unsigned long long* s
   *ir = __dsub_rn(1.0, __ddiv_rn(sqr, __dmul_rn(wr, wr)));
 }
 
-// CM: compile-time bound on the class count, so the per-class arrays of a thread live in registers
+// Node statistics are kept as 64-bit patterns so that the classification path (integer class
+// weights) and the regression path (float64 {sum w, sum w*y, sum w*y*y}, MSE criterion
+// SK/tree/_criterion.pyx:922-1017) share the stack records, the split records and the scan.
+template <bool REG>
+__device__ __forceinline__ unsigned long long st_add(unsigned long long a, unsigned long long b) {
+  if constexpr (REG) return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) + __longlong_as_double((long long)b));
+  else return a + b;
+}
+template <bool REG>
+__device__ __forceinline__ unsigned long long st_sub(unsigned long long a, unsigned long long b) {
+  if constexpr (REG) return (unsigned long long)__double_as_longlong(__longlong_as_double((long long)a) - __longlong_as_double((long long)b));
+  else return a - b;
+}
+__device__ __forceinline__ double st_d(unsigned long long a) { return __longlong_as_double((long long)a); }
+__device__ __forceinline__ unsigned long long d_st(double a) { return (unsigned long long)__double_as_longlong(a); }
+
+// MSE children impurity from the statistics of the left child and of the node
+__device__ __forceinline__ void fo_children_mse(const unsigned long long* sl, const unsigned long long* st,
+                                                double wl, double wr, double* il, double* ir) {
+  const double sum_l = st_d(sl[1]), sq_l = st_d(sl[2]);
+  const double sum_r = __dsub_rn(st_d(st[1]), sum_l), sq_r = __dsub_rn(st_d(st[2]), sq_l);
+  const double ml = __ddiv_rn(sum_l, wl), mr = __ddiv_rn(sum_r, wr);
+  *il = __dsub_rn(__ddiv_rn(sq_l, wl), __dmul_rn(ml, ml));
+  *ir = __dsub_rn(__ddiv_rn(sq_r, wr), __dmul_rn(mr, mr));
+}
+
+// CM: compile-time bound on the class count (3 statistics when REG), so the per-class arrays of a thread live in registers
 #define FO_TICK(ph) do { if (P.o_prof && tid == 0) { const long long _t = clock64(); prof[ph] += _t - tlast; tlast = _t; } } while (0)
 #define FOR_C(c) _Pragma("unroll") for (int c = 0; c < CM; ++c) if (c < C)
-template <int CM>
+template <int CM, bool REG>
 __global__ void __launch_bounds__(FO_THREADS)
 forest_build_kernel(const FoParams P) {
   const int slot = blockIdx.x;
   if (slot >= P.n_trees) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int C = P.n_classes, d = P.d;
+  const int C = REG ? 3 : P.n_classes, d = P.d;   // REG: the three statistics take the place of the classes
   const int64_t n = P.n;
   uint2* samp = P.samp + (size_t)slot * n;
   uint2* tmp = P.samp_tmp + (size_t)slot * n;
@@ -139,7 +166,10 @@ forest_build_kernel(const FoParams P) {
   int2* undo = reinterpret_cast<int2*>(fo_sm + 2 * d);      // [d + 16] swap log of the speculative draws
   float* sbv = reinterpret_cast<float*>(undo + (d + 16));   // [FO_KB_MAX][256] distinct values of the batch features
   FoRecord* sstack = reinterpret_cast<FoRecord*>(sbv + FO_KB_MAX * FO_BINS);   // [FO_SSTK] top of the DFS stack
-  const int KB = min(FO_KB_MAX, FO_HIST_WORDS / ((C + 1) * FO_BINS));
+  // histogram words per feature: classification [C][256] u32 weights + [256] counts; regression
+  // [3][256] float64 statistics + [256] counts
+  const int hstride = REG ? (3 * 2 + 1) * FO_BINS : (C + 1) * FO_BINS;
+  const int KB = min(FO_KB_MAX, FO_HIST_WORDS / hstride);
 
   // ---- initialise the tree: samples with non-zero weight in ascending order (Splitter.init) ----
   __shared__ int base_s;
@@ -152,7 +182,7 @@ forest_build_kernel(const FoParams P) {
   for (int64_t i0 = 0; i0 < n; i0 += FO_THREADS) {
     const int64_t i = i0 + tid;
     unsigned int w = 0, yc = 0;
-    if (i < n) { w = cnt[i]; yc = (unsigned)P.ycls[i]; }
+    if (i < n) { w = cnt[i]; if (!REG) yc = (unsigned)P.ycls[i]; }
     const int keep = w != 0;
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) wsum[wid][0] = __popc(bal);
@@ -162,7 +192,14 @@ forest_build_kernel(const FoParams P) {
     const int b = base_s;
     if (keep) {
       samp[b + off + __popc(bal & ((1u << lane) - 1))] = make_uint2((unsigned)i, (w << 8) | yc);
-      FOR_C(c) if ((int)yc == c) my_sums[c] += w;
+      if constexpr (REG) {   // RegressionCriterion.init (SK/tree/_criterion.pyx:  w_y = w*y; sum += w_y; sq += w_y*y)
+        const double yv = P.yreal[i], wy = __dmul_rn((double)w, yv);
+        my_sums[0] = d_st(st_d(my_sums[0]) + (double)w);
+        my_sums[1] = d_st(st_d(my_sums[1]) + wy);
+        my_sums[2] = d_st(st_d(my_sums[2]) + __dmul_rn(wy, yv));
+      } else {
+        FOR_C(c) if ((int)yc == c) my_sums[c] += w;
+      }
     }
     __syncthreads();
     if (tid == 0) base_s = b + tot;
@@ -175,12 +212,16 @@ forest_build_kernel(const FoParams P) {
   __syncthreads();
   FOR_C(c) {
     unsigned long long v = my_sums[c];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) atomicAdd(&red[c], v);
+    for (int o = 16; o > 0; o >>= 1) v = st_add<REG>(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) {
+      if constexpr (REG) atomicAdd(reinterpret_cast<double*>(&red[c]), st_d(v));   // 0 bit pattern == 0.0
+      else atomicAdd(&red[c], v);
+    }
   }
   __syncthreads();
   double w_samples = 0.0;
-  FOR_C(c) w_samples += (double)red[c];     // weighted_n_samples (integer valued)
+  if constexpr (REG) w_samples = st_d(red[0]);
+  else { FOR_C(c) w_samples += (double)red[c]; }    // weighted_n_samples (integer valued)
 
   long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tlast = clock64();
@@ -212,14 +253,20 @@ forest_build_kernel(const FoParams P) {
     const int start = rec.start, end = rec.end, depth = rec.depth;
     const int n_node = end - start;
     double w_node = 0.0;
-    FOR_C(c) w_node += (double)rec.sums[c];
+    if constexpr (REG) w_node = st_d(rec.sums[0]);
+    else { FOR_C(c) w_node += (double)rec.sums[c]; }
     double impurity = rec.impurity;
     bool is_leaf = depth >= P.max_depth || n_node < P.min_samples_split || n_node < 2 * P.min_samples_leaf ||
                    w_node < 2.0 * P.min_weight_leaf;
     if (first) {   // root: node_impurity()  (SK/tree/_criterion.pyx:620-640)
-      double sq = 0.0;
-      FOR_C(c) { const double a = (double)rec.sums[c]; sq = __dadd_rn(sq, __dmul_rn(a, a)); }
-      impurity = __dsub_rn(1.0, __ddiv_rn(sq, __dmul_rn(w_node, w_node)));
+      if constexpr (REG) {   // MSE.node_impurity
+        const double mean = __ddiv_rn(st_d(rec.sums[1]), w_node);
+        impurity = __dsub_rn(__ddiv_rn(st_d(rec.sums[2]), w_node), __dmul_rn(mean, mean));
+      } else {
+        double sq = 0.0;
+        FOR_C(c) { const double a = (double)rec.sums[c]; sq = __dadd_rn(sq, __dmul_rn(a, a)); }
+        impurity = __dsub_rn(1.0, __ddiv_rn(sq, __dmul_rn(w_node, w_node)));
+      }
       first = false;
     }
     is_leaf = is_leaf || impurity <= FO_EPSILON;
@@ -240,7 +287,6 @@ forest_build_kernel(const FoParams P) {
       // samples, one warp per feature scans its histogram, and thread 0 then commits the results
       // in draw order; the first feature found constant rolls the simulation back to that draw,
       // takes the constant branch and the remaining speculative results are discarded.
-      const int hstride = (C + 1) * FO_BINS;
       for (;;) {
         if (tid == 0) {
           int nbatch = 0;
@@ -298,15 +344,26 @@ forest_build_kernel(const FoParams P) {
           for (int i = start + tid; i < end; i += FO_THREADS) {
             const uint2 sv = samp[i];
             const unsigned cls = sv.y & 0xFF, wgt = sv.y >> 8;
+            double yv = 0.0;
+            if constexpr (REG) yv = __ldg(P.yreal + sv.x);
             unsigned bbs[FO_KB_MAX];
 #pragma unroll
             for (int k = 0; k < FO_KB_MAX; ++k) bbs[k] = k < nbatch ? (unsigned)__ldg(col[k] + sv.x) : 0u;
+            const double wy = __dmul_rn((double)wgt, yv), wyy = __dmul_rn(wy, yv);
 #pragma unroll
             for (int k = 0; k < FO_KB_MAX; ++k) {
               if (k < nbatch) {
                 unsigned int* H = hist + k * hstride;
-                atomicAdd(&H[cls * FO_BINS + bbs[k]], wgt);
-                atomicAdd(&H[C * FO_BINS + bbs[k]], 1u);
+                if constexpr (REG) {
+                  double* Hd = reinterpret_cast<double*>(H);
+                  atomicAdd(&Hd[0 * FO_BINS + bbs[k]], (double)wgt);
+                  atomicAdd(&Hd[1 * FO_BINS + bbs[k]], wy);
+                  atomicAdd(&Hd[2 * FO_BINS + bbs[k]], wyy);
+                  atomicAdd(&H[6 * FO_BINS + bbs[k]], 1u);
+                } else {
+                  atomicAdd(&H[cls * FO_BINS + bbs[k]], wgt);
+                  atomicAdd(&H[C * FO_BINS + bbs[k]], 1u);
+                }
               }
             }
           }
@@ -320,10 +377,16 @@ forest_build_kernel(const FoParams P) {
         for (int k = wid; k < nbatch; k += FO_THREADS / 32) {
           const unsigned int* H = hist + k * hstride;
           const float* bv = sbv + k * FO_BINS;
+          const int cnt_off = REG ? 6 * FO_BINS : C * FO_BINS;
+          // statistic c of bin bb as a 64-bit pattern (class weight, or float64 sum for regression)
+          auto hbin = [&](int c, int bb) -> unsigned long long {
+            if constexpr (REG) return d_st(reinterpret_cast<const double*>(H)[c * FO_BINS + bb]);
+            else return (unsigned long long)H[c * FO_BINS + bb];
+          };
           unsigned cntb[8];
           unsigned ltot = 0, pmask = 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { cntb[j] = H[C * FO_BINS + lane * 8 + j]; ltot += cntb[j]; if (cntb[j]) pmask |= 1u << j; }
+          for (int j = 0; j < 8; ++j) { cntb[j] = H[cnt_off + lane * 8 + j]; ltot += cntb[j]; if (cntb[j]) pmask |= 1u << j; }
           // exclusive prefix of sample counts over lanes
           unsigned pre = ltot;
           for (int o = 1; o < 32; o <<= 1) { unsigned v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
@@ -333,10 +396,14 @@ forest_build_kernel(const FoParams P) {
           FOR_C(c) {
             unsigned long long t = 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) t += H[c * FO_BINS + lane * 8 + j];
+            for (int j = 0; j < 8; ++j) t = st_add<REG>(t, hbin(c, lane * 8 + j));
             unsigned long long incl = t;
-            for (int o = 1; o < 32; o <<= 1) { unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            clspre[c] = incl - t;
+            for (int o = 1; o < 32; o <<= 1) {
+              unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl = st_add<REG>(v, incl);
+            }
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, 1);   // exclusive prefix
+            clspre[c] = lane > 0 ? up : 0ull;
           }
           // first present bin of this lane, then "first present bin in any later lane"
           const int myfirst = pmask ? lane * 8 + __ffs(pmask) - 1 : 1 << 20;
@@ -372,16 +439,20 @@ forest_build_kernel(const FoParams P) {
                 if ((double)bv[bb] <= thr) {
                   nin += 1;
                   nl_lane += cntb[j];
-                  FOR_C(c) sl[c] += H[c * FO_BINS + bb];
+                  FOR_C(c) sl[c] = st_add<REG>(sl[c], hbin(c, bb));
                 }
               }
             }
             const unsigned n_left_u = __reduce_add_sync(0xffffffffu, nl_lane);
             const int cutbin = (int)__reduce_add_sync(0xffffffffu, (unsigned)nin) - 1;
             FOR_C(c) {
+              // lanes hold consecutive bin ranges: an ordered inclusive scan, read from the last lane
               unsigned long long v = sl[c];
-              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-              sl[c] = v;
+              for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v = st_add<REG>(u, v);
+              }
+              sl[c] = __shfl_sync(0xffffffffu, v, 31);
             }
             if (lane == 0) {
               R->is_const = is_const; R->proxy = -INFINITY; R->pos = end; R->bin = cutbin; R->thr = thr;
@@ -389,12 +460,19 @@ forest_build_kernel(const FoParams P) {
                 const int n_left = (int)n_left_u, n_right = n_node - n_left;
                 if (n_left >= P.min_samples_leaf && n_right >= P.min_samples_leaf) {
                   double wl = 0.0;
-                  FOR_C(c) wl += (double)sl[c];
+                  if constexpr (REG) wl = st_d(sl[0]);
+                  else { FOR_C(c) wl += (double)sl[c]; }
                   const double wr = w_node - wl;
                   if (!(wl < P.min_weight_leaf || wr < P.min_weight_leaf)) {
                     double il, ir;
-                    fo_children_impurity<CM>(sl, rec.sums, C, wl, wr, &il, &ir);
-                    R->proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
+                    if constexpr (REG) {
+                      fo_children_mse(sl, rec.sums, wl, wr, &il, &ir);
+                      const double sum_l = st_d(sl[1]), sum_r = __dsub_rn(st_d(rec.sums[1]), sum_l);
+                      R->proxy = __dadd_rn(__ddiv_rn(__dmul_rn(sum_l, sum_l), wl), __ddiv_rn(__dmul_rn(sum_r, sum_r), wr));
+                    } else {
+                      fo_children_impurity<CM>(sl, rec.sums, C, wl, wr, &il, &ir);
+                      R->proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
+                    }
                     R->pos = start + n_left; R->il = il; R->ir = ir;
                     FOR_C(c) R->sl[c] = sl[c];
                   }
@@ -416,7 +494,7 @@ forest_build_kernel(const FoParams P) {
               if (!cntb[j]) continue;
               const int bb = lane * 8 + j;
               run_cnt += cntb[j];
-              FOR_C(c) sl[c] += H[c * FO_BINS + bb];
+              FOR_C(c) sl[c] = st_add<REG>(sl[c], hbin(c, bb));
               // next present bin
               const unsigned higher = pmask & ~((2u << j) - 1u);
               const int nb2 = higher ? lane * 8 + __ffs(higher) - 1 : nxt;
@@ -425,12 +503,19 @@ forest_build_kernel(const FoParams P) {
               const int n_left = (int)run_cnt, n_right = n_node - n_left;
               if (n_left < P.min_samples_leaf || n_right < P.min_samples_leaf) continue;
               double wl = 0.0;
-              FOR_C(c) wl += (double)sl[c];
+              if constexpr (REG) wl = st_d(sl[0]);
+              else { FOR_C(c) wl += (double)sl[c]; }
               const double wr = w_node - wl;
               if (wl < P.min_weight_leaf || wr < P.min_weight_leaf) continue;
-              double il, ir;
-              fo_children_impurity<CM>(sl, rec.sums, C, wl, wr, &il, &ir);
-              const double proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
+              double il, ir, proxy;
+              if constexpr (REG) {     // MSE.proxy_impurity_improvement: sum_l^2 / w_l + sum_r^2 / w_r
+                fo_children_mse(sl, rec.sums, wl, wr, &il, &ir);
+                const double sum_l = st_d(sl[1]), sum_r = __dsub_rn(st_d(rec.sums[1]), sum_l);
+                proxy = __dadd_rn(__ddiv_rn(__dmul_rn(sum_l, sum_l), wl), __ddiv_rn(__dmul_rn(sum_r, sum_r), wr));
+              } else {
+                fo_children_impurity<CM>(sl, rec.sums, C, wl, wr, &il, &ir);
+                proxy = __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
+              }
               if (proxy > bproxy) {
                 bproxy = proxy; bil = il; bir = ir; bpos = start + n_left; bbin = bb; bnext = nb2;
                 FOR_C(c) bsl[c] = sl[c];
@@ -494,7 +579,8 @@ forest_build_kernel(const FoParams P) {
         s_dbl[0] = best_thr; s_dbl[1] = best_il; s_dbl[2] = best_ir;
         if (best_pos < end) {
           double wl = 0.0;
-          FOR_C(c) wl += (double)best_sl[c];
+          if constexpr (REG) wl = st_d(best_sl[0]);
+          else { FOR_C(c) wl += (double)best_sl[c]; }
           const double wr = w_node - wl;
           // impurity_improvement (SK/tree/_criterion.pyx:163-190)
           const double a = __dmul_rn(__ddiv_rn(wr, w_node), best_ir);
@@ -564,8 +650,12 @@ forest_build_kernel(const FoParams P) {
         P.o_feature[nb + node_id] = best_feature; P.o_thr[nb + node_id] = best_thr;
         P.o_mgl[nb + node_id] = (uint8_t)best_mgl;
       }
-      FOR_C(c)
-        P.o_val[(nb + node_id) * C + c] = __ddiv_rn((double)rec.sums[c], w_node);   // class fractions
+      if constexpr (REG) {
+        P.o_val[nb + node_id] = __ddiv_rn(st_d(rec.sums[1]), w_node);               // node mean (MSE.node_value)
+      } else {
+        FOR_C(c)
+          P.o_val[(nb + node_id) * C + c] = __ddiv_rn((double)rec.sums[c], w_node);   // class fractions
+      }
     }
     node_count += 1;
     if (!is_leaf) {
@@ -575,7 +665,7 @@ forest_build_kernel(const FoParams P) {
         r.depth = depth + 1; r.parent = node_id; r.n_const = n_total_constants;
         // right child first, then left (popped first)
         r.start = best_pos; r.end = end; r.is_left = 0; r.impurity = best_ir;
-        for (int c = 0; c < FO_MAXC; ++c) r.sums[c] = c < C ? rec.sums[c] - best_sl[c] : 0;
+        for (int c = 0; c < FO_MAXC; ++c) r.sums[c] = c < C ? st_sub<REG>(rec.sums[c], best_sl[c]) : 0;
         if (sp < FO_SSTK) sstack[sp] = r; else stack[sp] = r;
         r.start = start; r.end = best_pos; r.is_left = 1; r.impurity = best_il;
         for (int c = 0; c < FO_MAXC; ++c) r.sums[c] = c < C ? best_sl[c] : 0;
@@ -694,11 +784,13 @@ int forest_prepare(Ctx* c) {
 // rand_states: [n_trees] splitter seeds.  Results are delivered tree by tree through `sink`.
 int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_states, int n_classes,
                int max_features, int max_depth, int min_samples_split, int min_samples_leaf,
-               double min_weight_leaf, double min_impurity_decrease, int random_split, ForestSink sink,
-               void* sink_arg) {
+               double min_weight_leaf, double min_impurity_decrease, int random_split, const double* h_yreal,
+               ForestSink sink, void* sink_arg) {
   if (forest_prepare(c)) return 1;
+  const bool reg = h_yreal != nullptr;       // regression trees (MSE) on float64 targets
+  if (reg) n_classes = 1;
   if (n_classes < 1 || n_classes > FO_MAXC) return fail(c, "forest: device path supports up to 16 classes");
-  if (!c->ycls) return fail(c, "forest: stage labels first");
+  if (!reg && !c->ycls) return fail(c, "forest: stage labels first");
   const int64_t n = c->n;
   const int d = (int)c->d;
   if ((size_t)4 * d * sizeof(int) > 6 * 1024) return fail(c, "forest: device path supports up to 384 features (shared-memory feature permutation)");
@@ -742,6 +834,13 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   long long* d_prof = nullptr;
   if (want_prof) SKD_CUDA(c, sx.alloc(&d_prof, (size_t)slots * 16));
   P.xbin = c->forest.xbin; P.binval = c->forest.binval; P.ycls = c->ycls;
+  if (reg) {
+    double* dy;
+    SKD_CUDA(c, sx.alloc(&dy, (size_t)n));
+    SKD_CUDA(c, cudaMemcpyAsync(dy, h_yreal, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->h2d += n * 8;
+    P.yreal = dy;
+  }
   P.n = n; P.d = d; P.n_classes = n_classes;
   P.max_features = max_features; P.max_depth = max_depth; P.min_samples_split = min_samples_split;
   P.min_samples_leaf = min_samples_leaf; P.min_weight_leaf = min_weight_leaf;
@@ -751,10 +850,11 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   P.o_prof = d_prof;
   const size_t smem = (size_t)2 * d * sizeof(int) + (size_t)(d + 16) * sizeof(int2) +
                       (size_t)FO_KB_MAX * FO_BINS * sizeof(float) + (size_t)FO_SSTK * sizeof(FoRecord);
-  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<FO_MAXC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<FO_MAXC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   std::vector<int32_t> hcount(slots), hdepth(slots), hstatus(slots);
   SkdTreeView view;
   std::vector<int32_t> hl, hr, hf, hn; std::vector<uint8_t> hm; std::vector<double> ht, hi, hw, hv;
@@ -768,10 +868,11 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
     SKD_CUDA(c, cudaMemcpyAsync(drs, rand_states + t0, (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
     c->h2d += (int64_t)nt * n;
     P.n_trees = nt;
-    if (n_classes <= 2) forest_build_kernel<2><<<nt, FO_THREADS, smem, c->stream>>>(P);
-    else if (n_classes <= 4) forest_build_kernel<4><<<nt, FO_THREADS, smem, c->stream>>>(P);
-    else if (n_classes <= 8) forest_build_kernel<8><<<nt, FO_THREADS, smem, c->stream>>>(P);
-    else forest_build_kernel<FO_MAXC><<<nt, FO_THREADS, smem, c->stream>>>(P);
+    if (reg) forest_build_kernel<4, true><<<nt, FO_THREADS, smem, c->stream>>>(P);
+    else if (n_classes <= 2) forest_build_kernel<2, false><<<nt, FO_THREADS, smem, c->stream>>>(P);
+    else if (n_classes <= 4) forest_build_kernel<4, false><<<nt, FO_THREADS, smem, c->stream>>>(P);
+    else if (n_classes <= 8) forest_build_kernel<8, false><<<nt, FO_THREADS, smem, c->stream>>>(P);
+    else forest_build_kernel<FO_MAXC, false><<<nt, FO_THREADS, smem, c->stream>>>(P);
     c->launches += 1;
     SKD_CUDA(c, cudaGetLastError());
     SKD_CUDA(c, cudaMemcpyAsync(hcount.data(), P.o_count, nt * 4, cudaMemcpyDeviceToHost, c->stream));

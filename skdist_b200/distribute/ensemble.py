@@ -13,8 +13,10 @@ import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
-from sklearn.ensemble import ExtraTreesClassifier, RandomForestClassifier
-from sklearn.tree import DecisionTreeClassifier, ExtraTreeClassifier
+from sklearn.ensemble import (ExtraTreesClassifier, ExtraTreesRegressor, RandomForestClassifier,
+                              RandomForestRegressor)
+from sklearn.tree import (DecisionTreeClassifier, DecisionTreeRegressor, ExtraTreeClassifier,
+                          ExtraTreeRegressor)
 from sklearn.tree._tree import NODE_DTYPE, Tree
 from sklearn.utils import check_random_state
 
@@ -23,7 +25,8 @@ from ..engine import get_engine
 from .base import _parse_partitions, _ScParamMixin
 from .validation import _check_estimator
 
-__all__ = ["DistRandomForestClassifier", "DistExtraTreesClassifier"]
+__all__ = ["DistRandomForestClassifier", "DistExtraTreesClassifier", "DistRandomForestRegressor",
+           "DistExtraTreesRegressor"]
 
 MAX_RAND_SEED = np.iinfo(np.int32).max     # ref ensemble.py:38
 RAND_R_MAX = 2147483647                    # SK/tree/_utils.pxd
@@ -65,8 +68,9 @@ def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, ma
     est.set_params(random_state=int(state))
     est.n_features_in_ = n_features
     est.n_outputs_ = 1
-    est.classes_ = np.arange(n_classes, dtype=np.float64)
-    est.n_classes_ = n_classes
+    if issubclass(tree_cls, DecisionTreeClassifier):
+        est.classes_ = np.arange(n_classes, dtype=np.float64)
+        est.n_classes_ = n_classes
     est.max_features_ = max_features_
     est.tree_ = t
     return est
@@ -78,6 +82,7 @@ class _DistForestClassifier(_ScParamMixin):
 
     _splitter = 0
     _tree_cls = DecisionTreeClassifier
+    _regression = False
 
     def _init_params(self, sc, partitions, n_estimators, criterion, max_depth, min_samples_split,
                      min_samples_leaf, min_weight_fraction_leaf, max_features, max_leaf_nodes,
@@ -120,7 +125,10 @@ class _DistForestClassifier(_ScParamMixin):
 
     def _resolved(self, n_features):
         bad = []
-        if self.criterion != "gini":
+        if self._regression:
+            if self.criterion not in ("mse", "squared_error"):   # "mse" is the reference era's name
+                bad.append("criterion=%r (only 'squared_error' / 'mse')" % self.criterion)
+        elif self.criterion != "gini":
             bad.append("criterion=%r (only 'gini')" % self.criterion)
         if self.max_leaf_nodes is not None:
             bad.append("max_leaf_nodes (best-first builder)")
@@ -133,7 +141,9 @@ class _DistForestClassifier(_ScParamMixin):
         if bad:
             raise NotImplementedError("forest configuration without a device path: " + ", ".join(bad))
         mf = self.max_features
-        if mf in ("auto", "sqrt"):                       # 'auto' meant sqrt for classifiers in the reference's era
+        if mf == "auto" and self._regression:            # 'auto' meant all features for regressors (ref era)
+            mf_i = n_features
+        elif mf in ("auto", "sqrt"):                     # ... and sqrt for classifiers
             mf_i = max(1, int(np.sqrt(n_features)))
         elif mf == "log2":
             mf_i = max(1, int(np.log2(n_features)))
@@ -160,8 +170,14 @@ class _DistForestClassifier(_ScParamMixin):
         n, d = X.shape
         self.n_features_in_ = d
         self.n_outputs_ = 1
-        self.classes_, y_enc = np.unique(y, return_inverse=True)       # ref :229 (_validate_y_class_weight)
-        self.n_classes_ = len(self.classes_)
+        if self._regression:
+            y_reg = np.ascontiguousarray(y, dtype=np.float64)          # SK/ensemble/_forest.py: y = DOUBLE
+            y_enc = np.zeros(len(y), np.int32)
+            self.n_classes_ = 1
+        else:
+            y_reg = None
+            self.classes_, y_enc = np.unique(y, return_inverse=True)   # ref :229 (_validate_y_class_weight)
+            self.n_classes_ = len(self.classes_)
         mf_i, max_depth, mss, msl = self._resolved(d)
         if not isinstance(mss, (int, np.integer)):
             mss = max(2, int(np.ceil(mss * n)))
@@ -180,9 +196,11 @@ class _DistForestClassifier(_ScParamMixin):
         eng.stage_folds(None, 0)
         mine = parallel.shard_indices(self.n_estimators, rank, world)
         my_states = [states[i] for i in mine]
-        tmpl = dict(criterion=self.criterion, max_depth=self.max_depth, min_samples_split=self.min_samples_split,
+        crit = "squared_error" if self._regression else self.criterion
+        tmpl = dict(criterion=crit, max_depth=self.max_depth, min_samples_split=self.min_samples_split,
                     min_samples_leaf=self.min_samples_leaf, min_weight_fraction_leaf=self.min_weight_fraction_leaf,
-                    max_features="sqrt" if self.max_features == "auto" else self.max_features,
+                    max_features=(1.0 if self._regression else "sqrt") if self.max_features == "auto"
+                    else self.max_features,
                     max_leaf_nodes=self.max_leaf_nodes, min_impurity_decrease=self.min_impurity_decrease)
 
         # Trees go to the device in chunks (two resident tree builders per SM).  While chunk k is
@@ -199,7 +217,8 @@ class _DistForestClassifier(_ScParamMixin):
 
         def build(counts, rs):
             return eng.forest_fit(counts, rs, self.n_classes_, mf_i, max_depth, int(mss), int(msl),
-                                  float(min_weight_leaf), float(self.min_impurity_decrease), splitter=self._splitter)
+                                  float(min_weight_leaf), float(self.min_impurity_decrease), splitter=self._splitter,
+                                  y_regression=y_reg)
 
         def wrap(sts, arrays):
             with ThreadPoolExecutor(max_workers=8) as ex:
@@ -278,3 +297,60 @@ class DistExtraTreesClassifier(_DistForestClassifier, ExtraTreesClassifier):
                           min_weight_fraction_leaf, max_features, max_leaf_nodes, min_impurity_decrease,
                           min_impurity_split, bootstrap, oob_score, n_jobs, random_state, verbose, warm_start,
                           class_weight)
+
+
+class _DistForestRegressor(_DistForestClassifier):
+    """Regression flavour of the shared fit: float64 targets, MSE criterion, no class bookkeeping
+    (ref DistForestRegressor, ensemble.py:481-517)."""
+
+    _regression = True
+    _tree_cls = DecisionTreeRegressor
+
+    def _init_reg(self, sc, partitions, n_estimators, criterion, max_depth, min_samples_split, min_samples_leaf,
+                  min_weight_fraction_leaf, max_features, max_leaf_nodes, min_impurity_decrease,
+                  min_impurity_split, bootstrap, oob_score, n_jobs, random_state, verbose, warm_start):
+        self._init_params(sc, partitions, n_estimators, criterion, max_depth, min_samples_split, min_samples_leaf,
+                          min_weight_fraction_leaf, max_features, max_leaf_nodes, min_impurity_decrease,
+                          min_impurity_split, bootstrap, oob_score, n_jobs, random_state, verbose, warm_start, None)
+        del self.class_weight
+
+    @classmethod
+    def _get_param_names(cls):
+        return sorted(["sc", "partitions", "n_estimators", "criterion", "max_depth", "min_samples_split",
+                       "min_samples_leaf", "min_weight_fraction_leaf", "max_features", "max_leaf_nodes",
+                       "min_impurity_decrease", "min_impurity_split", "bootstrap", "oob_score", "n_jobs",
+                       "random_state", "verbose", "warm_start"])
+
+    class_weight = None      # read by the shared validation; regressors have no such parameter
+
+
+class DistRandomForestRegressor(_DistForestRegressor, RandomForestRegressor):
+    """Same as sklearn `RandomForestRegressor` with every tree built on a B200.
+    Constructor mirrors ref ensemble.py:531-572 (``sc`` FIRST; criterion "mse" = squared error)."""
+
+    _splitter = 0
+    _tree_cls = DecisionTreeRegressor
+
+    def __init__(self, sc=None, partitions="auto", n_estimators=100, criterion="mse", max_depth=None,
+                 min_samples_split=2, min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
+                 max_leaf_nodes=None, min_impurity_decrease=0.0, min_impurity_split=None, bootstrap=True,
+                 oob_score=False, n_jobs=None, random_state=None, verbose=0, warm_start=False):
+        self._init_reg(sc, partitions, n_estimators, criterion, max_depth, min_samples_split, min_samples_leaf,
+                       min_weight_fraction_leaf, max_features, max_leaf_nodes, min_impurity_decrease,
+                       min_impurity_split, bootstrap, oob_score, n_jobs, random_state, verbose, warm_start)
+
+
+class DistExtraTreesRegressor(_DistForestRegressor, ExtraTreesRegressor):
+    """Same as sklearn `ExtraTreesRegressor` with every tree built on a B200.
+    Constructor mirrors ref ensemble.py:584-616."""
+
+    _splitter = 1
+    _tree_cls = ExtraTreeRegressor
+
+    def __init__(self, sc=None, partitions="auto", n_estimators=100, criterion="mse", max_depth=None,
+                 min_samples_split=2, min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_features="auto",
+                 max_leaf_nodes=None, min_impurity_decrease=0.0, min_impurity_split=None, bootstrap=False,
+                 oob_score=False, n_jobs=None, random_state=None, verbose=0, warm_start=False):
+        self._init_reg(sc, partitions, n_estimators, criterion, max_depth, min_samples_split, min_samples_leaf,
+                       min_weight_fraction_leaf, max_features, max_leaf_nodes, min_impurity_decrease,
+                       min_impurity_split, bootstrap, oob_score, n_jobs, random_state, verbose, warm_start)

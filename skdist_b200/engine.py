@@ -205,11 +205,17 @@ class Engine:
                 "gpu_seconds": secs.value}
 
     def forest_fit(self, sample_counts, rand_states, n_classes, max_features, max_depth, min_samples_split,
-                   min_samples_leaf, min_weight_leaf, min_impurity_decrease, splitter=0):
+                   min_samples_leaf, min_weight_leaf, min_impurity_decrease, splitter=0, y_regression=None):
         """Build len(rand_states) classifier trees.  sample_counts [n_trees, n] uint8 (bootstrap
         multiplicities = the reference's sample_weight; None = every row once), rand_states [n_trees]
         uint32 splitter seeds, splitter 0 = best (RandomForest) / 1 = random (ExtraTrees).
+        y_regression: float64 targets [n] -> regression trees (MSE), one value per node.
         Returns a list of dicts with the sklearn Tree arrays of every tree."""
+        yreg = None
+        if y_regression is not None:
+            yreg = np.ascontiguousarray(y_regression, dtype=np.float64)
+            assert yreg.shape == (self.n,)
+            n_classes = 1
         rs = np.ascontiguousarray(rand_states, dtype=np.uint32)
         T = rs.shape[0]
         counts = None
@@ -222,6 +228,7 @@ class Engine:
                                        int(n_classes), int(max_features),
                                        int(max_depth), int(min_samples_split), int(min_samples_leaf),
                                        float(min_weight_leaf), float(min_impurity_decrease), int(splitter),
+                                       ptr(yreg) if yreg is not None else None,
                                        ctypes.byref(h), ctypes.byref(secs)), self._h)
         self.last_forest_seconds = secs.value
         trees = []

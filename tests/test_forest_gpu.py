@@ -99,3 +99,44 @@ def test_extra_trees_bit_identical_to_sklearn(n, d, levels, k):
     yt = np.array([0, 1, 0])
     etc = DistExtraTreesClassifier(n_estimators=10, random_state=5).fit(Xt, yt)
     assert_same_forest(etc, ExtraTreesClassifier(n_estimators=10, random_state=5).fit(Xt, yt))
+
+
+@pytest.mark.parametrize("n,d,levels", [(4000, 12, 256), (20000, 24, 64)])
+def test_regression_forests_bit_identical_on_integer_targets(n, d, levels):
+    """MSE trees: with integer-valued targets every float64 sum is exact, so the device trees must
+    equal scikit-learn's bit for bit (structure, thresholds, impurities, node means)."""
+    from sklearn.ensemble import ExtraTreesRegressor, RandomForestRegressor
+    from skdist.distribute.ensemble import DistExtraTreesRegressor, DistRandomForestRegressor
+    X, _ = lattice_data(n, d, seed=5, levels=levels)
+    rng = np.random.default_rng(1)
+    y = np.rint(0.05 * X[:, 0] - 0.03 * X[:, 1] + 0.0004 * X[:, 2] * X[:, 3] + 3 * rng.standard_normal(n))
+    kw = dict(n_estimators=4, random_state=9, max_features=5, min_samples_leaf=2)
+    assert_same_forest(DistRandomForestRegressor(**kw).fit(X, y), RandomForestRegressor(**kw).fit(X, y))
+    assert_same_forest(DistExtraTreesRegressor(**kw).fit(X, y), ExtraTreesRegressor(**kw).fit(X, y))
+    ours = DistRandomForestRegressor(n_estimators=3, random_state=2, max_depth=8).fit(X, y)     # max_features="auto" = all
+    ref = RandomForestRegressor(n_estimators=3, random_state=2, max_depth=8).fit(X, y)
+    assert_same_forest(ours, ref)
+    np.testing.assert_array_equal(ours.predict(X[:300]), ref.predict(X[:300]))
+
+
+def test_regression_forest_real_targets_and_reference_toy_cases():
+    """Real-valued targets: sums are formed in a different order than scikit-learn's, so agreement
+    is to rounding (predictions), not bitwise.  Toy cases from the reference's own tests
+    (ref skdist/distribute/tests/test_ensemble.py:34-58)."""
+    from sklearn.ensemble import RandomForestRegressor
+    from skdist.distribute.ensemble import DistExtraTreesRegressor, DistRandomForestRegressor
+    X, _ = lattice_data(6000, 10, seed=8, levels=64)
+    rng = np.random.default_rng(3)
+    y = 0.05 * X[:, 0] - 0.03 * X[:, 1] + rng.standard_normal(6000)
+    kw = dict(n_estimators=5, random_state=4, max_depth=6, min_samples_leaf=20)
+    ours = DistRandomForestRegressor(**kw).fit(X, y)
+    ref = RandomForestRegressor(**kw).fit(X, y)
+    np.testing.assert_allclose(ours.predict(X), ref.predict(X), rtol=0, atol=1e-9)
+    Xt = np.array([[0, 1, 0, 1], [0, 0, 0, 1], [1, 0, 1, 0]])
+    yt = np.array([0.1, 0.2, 0.1])
+    rfr = DistRandomForestRegressor(n_estimators=10, random_state=5).fit(Xt, yt)
+    np.testing.assert_allclose(rfr.predict(Xt), RandomForestRegressor(n_estimators=10, random_state=5).fit(Xt, yt).predict(Xt),
+                               rtol=0, atol=1e-12)
+    assert np.allclose(rfr.predict(Xt), np.array([0.15, 0.18, 0.12]))     # the reference test's golden values
+    etr = DistExtraTreesRegressor(n_estimators=10, random_state=5).fit(Xt, yt)
+    assert np.allclose(etr.predict(Xt), np.array([0.1, 0.2, 0.1]))
