@@ -13,6 +13,11 @@ import numpy as np
 
 def dist_info():
     """(rank, world_size, local_rank); (0, 1, 0) when torch.distributed is not initialised."""
+    # torch is only needed when a process group exists; importing it costs seconds, so a plain
+    # single-process run (torch never imported by the caller) does not pay for it
+    import sys
+    if "torch" not in sys.modules:
+        return 0, 1, 0
     try:
         import torch.distributed as dist
     except Exception:  # pragma: no cover
