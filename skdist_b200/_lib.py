@@ -111,7 +111,10 @@ def load(build_if_missing=True):
 def check(rc, ctx=None):
     if rc != 0:
         msg = load().skd_last_error(ctx)
-        raise SkdError(msg.decode() if msg else "libskdist_b200 call failed (rc=%d)" % rc)
+        text = msg.decode() if msg else "libskdist_b200 call failed (rc=%d)" % rc
+        if text.startswith("Input X contains NaN"):     # what scikit-learn's check_array raises
+            raise ValueError(text)
+        raise SkdError(text)
 
 
 def ptr(a):

@@ -87,6 +87,18 @@ static int alloc_eval_buffers(Ctx* c, Scratch& sx, LogregWork& w, int B, int slo
   return 0;
 }
 
+// Non-finite scan of the staged matrix: scikit-learn's estimators reject NaN / infinity in X
+// (check_array -> "Input X contains NaN."), so the staging call does too -- at HBM speed, on the
+// copy that is already on the device.
+__global__ void finite_check_kernel(const float* __restrict__ X, int64_t total, int* __restrict__ flag) {
+  int bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = X[i];
+    bad |= !(fabsf(v) <= 3.402823466e38f);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 extern "C" {
 
 int skd_version(void) { return 100; }
@@ -268,6 +280,22 @@ static int stage_x_common(Ctx* c, const float* src, int64_t n, int64_t d, int64_
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   tr.mark("copy");
+  {
+    int* dflag;
+    Scratch sx(c);
+    SKD_CUDA(c, sx.alloc(&dflag, 1));
+    SKD_CUDA(c, cudaMemsetAsync(dflag, 0, sizeof(int), c->stream));
+    finite_check_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->X, n * ldx, dflag);
+    c->launches += 1;
+    int hflag = 0;
+    SKD_CUDA(c, cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (hflag) {
+      cudaFree(c->X); c->X = nullptr; c->n = 0;
+      return fail(c, "Input X contains NaN or infinity.");
+    }
+  }
+  tr.mark("check");
   c->n = n; c->d = d; c->ldx = ldx;
   c->tc.x_valid = false;
   c->forest.valid = false;

@@ -421,3 +421,16 @@ def test_tc_column_result_independent_of_batch():
         np.testing.assert_array_equal(again["coef"], big["coef"])            # run-to-run deterministic
     finally:
         e.close()
+
+
+def test_non_finite_input_is_rejected(eng):
+    """NaN / infinity in X raise ValueError at staging time, as scikit-learn's check_array does."""
+    from skdist.distribute.search import DistGridSearchCV
+    X, y = make_g1_classification(2000, 8, seed=1)
+    Xb = X.copy(); Xb[17, 3] = np.nan
+    with pytest.raises(ValueError):
+        DistGridSearchCV(LogisticRegression(), {"C": [1.0]}, None, cv=3).fit(Xb, y)
+    Xb = X.copy(); Xb[5, 0] = np.inf
+    with pytest.raises(ValueError):
+        eng.stage_x(Xb)
+    eng.stage_x(X)          # a clean matrix still stages afterwards
