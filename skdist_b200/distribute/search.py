@@ -272,14 +272,16 @@ class DistBaseSearchCV(_ScParamMixin):
         eng = get_engine()
         family.stage(eng, X_arr, fold, n_splits)
 
-        # task order: candidate-major, fold-minor (ref search.py:378-383); column j -> rank j % world
+        # task order: candidate-major, fold-minor (ref search.py:378-383), column = cand * n_splits + fold.
+        # Ranks are dealt blocks of 128 consecutive candidates of ONE fold (fold-major order).
         n_cols = n_candidates * n_splits
-        my_cols = parallel.shard_indices(n_cols, rank, world)
+        deal_order = (np.arange(n_candidates)[None, :] * n_splits + np.arange(n_splits)[:, None]).ravel()
+        my_cols = parallel.shard_blocks(n_cols, rank, world, deal_order)
         loc = family.run_columns(eng, my_cols, n_splits, bool(self.return_train_score))
         keys = ["test_score", "n_test", "fit_time", "score_time"]
         if self.return_train_score:
             keys.append("train_score")
-        res = {k: parallel.all_gather_columns(loc[k], n_cols, rank, world) for k in keys}
+        res = {k: parallel.all_gather_blocks(loc[k], n_cols, rank, world, deal_order) for k in keys}
 
         error_score = self.error_score
         bad = ~np.isfinite(res["test_score"])
@@ -476,9 +478,10 @@ class DistMultiModelSearch(_ScParamMixin, BaseEstimator):
             families[index] = family
             family.stage(eng, X_arr, fold, n_splits)
             n_cols = len(cands) * n_splits
-            my_cols = parallel.shard_indices(n_cols, rank, world)
+            deal_order = (np.arange(len(cands))[None, :] * n_splits + np.arange(n_splits)[:, None]).ravel()
+            my_cols = parallel.shard_blocks(n_cols, rank, world, deal_order)
             loc = family.run_columns(eng, my_cols, n_splits, False)
-            test = parallel.all_gather_columns(loc["test_score"], n_cols, rank, world)
+            test = parallel.all_gather_blocks(loc["test_score"], n_cols, rank, world, deal_order)
             # plain mean over folds (ref search.py:166-176: groupby(...).agg({"score": "mean"}))
             scores[rows] = np.asarray(test, dtype=np.float64).reshape(len(cands), n_splits).mean(axis=1)
         if self.verbose:

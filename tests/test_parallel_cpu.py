@@ -41,6 +41,12 @@ def _worker(rank, world, port, out_dir):
     idx = parallel.shard_indices(7, rank, world)
     full = parallel.all_gather_columns(np.stack([idx * 10.0, idx * 1.0], 1), 7, rank, world)
     assert np.array_equal(full[:, 0], np.arange(7) * 10.0)
+    # block-cyclic deal over a permuted order (what the search uses: fold-major blocks)
+    order = np.random.RandomState(0).permutation(301)
+    mine = parallel.shard_blocks(301, rank, world, order, block=64)
+    back = parallel.all_gather_blocks(mine.astype(np.float64) * 3.0, 301, rank, world, order, block=64)
+    assert np.array_equal(back, np.arange(301) * 3.0)
+    assert len(parallel.shard_blocks(5, rank, world)) in (2, 3)      # small problems still use every rank
     dist.destroy_process_group()
 
 
