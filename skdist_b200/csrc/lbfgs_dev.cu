@@ -78,7 +78,17 @@ __device__ __forceinline__ double gather_fg(const CtaPar& P, int s, int n_act, i
   double wsq = 0.0;
   for (int k = threadIdx.x; k < d; k += LB_THREADS) {
     double acc = 0.0;
-    for (int z = 0; z < nz_used; ++z) acc += (double)gradp[((size_t)z * n_act + s) * ldx + k];
+    // the partials are added in chunk order (the result must not depend on anything else); eight
+    // loads are put in flight at a time, the additions stay sequential
+    int z = 0;
+    for (; z + 8 <= nz_used; z += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = gradp[((size_t)(z + q) * n_act + s) * ldx + k];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc += (double)v[q];
+    }
+    for (; z < nz_used; ++z) acc += (double)gradp[((size_t)z * n_act + s) * ldx + k];
     double xk = x[k];
     if (gscale) acc *= gscale[k];
     // a feature masked out of this column (DistFeatureEliminator) keeps weight 0: with a zero
