@@ -38,7 +38,8 @@ namespace skd {
 constexpr int TC_BC = 128;       // slots per group
 constexpr int TC_R = 64;         // rows per tile
 constexpr int TC_NS = 5;         // ring slots (half tiles)
-constexpr int TC_NCH = 56;       // fixed row chunks per group: one partial sum per (chunk, slot)
+constexpr int TC_NCH = 147;      // fixed row chunks per group (one partial sum per (chunk, slot)); 147 = 3 * 7 * 7
+                                 // divides evenly over 7 / 21 / 49 CTAs per group (20, 7 or 3 groups per GPU)
 constexpr int TC_EPI_WARPS = 16;    // four per TMEM lane quadrant
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
