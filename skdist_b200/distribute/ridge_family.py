@@ -59,8 +59,9 @@ class _RidgeFamily:
         if not ok:
             raise NotImplementedError("only scoring=None / 'r2' is scored on the device for regressors")
 
-    def stage(self, eng, X, fold, n_splits):
-        eng.stage_x(X)
+    def stage(self, eng, X, fold, n_splits, x_staged=False):
+        if not x_staged:
+            eng.stage_x(X)
         eng.stage_targets(self.y)
         eng.stage_folds(fold, n_splits)
         self.fold = fold

@@ -141,8 +141,9 @@ class _LogRegFamily:
             raise NotImplementedError(
                 "only scoring=None / 'accuracy' is scored on the device for classifiers (got %r)" % (scorer,))
 
-    def stage(self, eng, X, fold, n_splits):
-        eng.stage_x(X)
+    def stage(self, eng, X, fold, n_splits, x_staged=False):
+        if not x_staged:
+            eng.stage_x(X)
         eng.stage_labels(self.y_class)
         eng.stage_folds(fold, n_splits)
 
@@ -264,13 +265,21 @@ class DistBaseSearchCV(_ScParamMixin):
             raise ValueError("X must be a 2-d array")
         y_arr = np.asarray(y)
         n_samples, n_features = X_arr.shape
-        cv_splitted = list(cv.split(X, y, groups))
-        fold = _fold_ids(cv_splitted, n_samples)
-        family = _pick_family(estimator, candidate_params, X_arr, y_arr, scorers)
+        # the host-to-device copy of X (the C-ABI call releases the GIL) runs while the host computes
+        # the cv splits and validates the candidates
+        eng = get_engine()
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            staged = pool.submit(eng.stage_x, X_arr)
+            try:
+                cv_splitted = list(cv.split(X, y, groups))
+                fold = _fold_ids(cv_splitted, n_samples)
+                family = _pick_family(estimator, candidate_params, X_arr, y_arr, scorers)
+            finally:
+                staged.result()
 
         rank, world, _ = parallel.dist_info()
-        eng = get_engine()
-        family.stage(eng, X_arr, fold, n_splits)
+        family.stage(eng, X_arr, fold, n_splits, x_staged=True)
 
         # task order: candidate-major, fold-minor (ref search.py:378-383), column = cand * n_splits + fold.
         # Ranks are dealt blocks of 128 consecutive candidates of ONE fold (fold-major order).
