@@ -50,14 +50,34 @@ class _RidgeFamily:
         if np.ndim(y) != 1:
             raise NotImplementedError("multi-target Ridge has no device path")
         self.y = np.asarray(y, dtype=np.float32)
-        scorer = scorers["score"]
-        ok = type(scorer).__name__ == "_PassthroughScorer"
-        if not ok:
-            f = getattr(scorer, "_score_func", None)
-            ok = getattr(f, "__name__", "") == "r2_score" and getattr(scorer, "_sign", 1) == 1 \
-                and not getattr(scorer, "_kwargs", {})
-        if not ok:
-            raise NotImplementedError("only scoring=None / 'r2' is scored on the device for regressors")
+        # scorers that are functions of the per-column (sum of squared residuals, row count):
+        # r2 (also estimator.score), neg_mean_squared_error, neg_root_mean_squared_error
+        self.metrics = {}
+        for name, scorer in scorers.items():
+            kind = None
+            if type(scorer).__name__ == "_PassthroughScorer":
+                kind = "r2"
+            else:
+                f = getattr(getattr(scorer, "_score_func", None), "__name__", "")
+                sign, kw = getattr(scorer, "_sign", 1), dict(getattr(scorer, "_kwargs", {}) or {})
+                if f == "r2_score" and sign == 1 and not kw:
+                    kind = "r2"
+                elif f == "mean_squared_error" and sign == -1 and not kw:
+                    kind = "neg_mse"
+                elif f == "root_mean_squared_error" and sign == -1 and not kw:
+                    kind = "neg_rmse"
+            if kind is None:
+                raise NotImplementedError(
+                    "scorer %r has no device path for regressors (supported: r2, neg_mean_squared_error, "
+                    "neg_root_mean_squared_error)" % (scorer,))
+            self.metrics[name] = kind
+
+    @staticmethod
+    def _metric(kind, sse, count, sst):
+        if kind == "r2":
+            return 1.0 - sse / sst
+        mse = sse / np.maximum(count, 1)
+        return -mse if kind == "neg_mse" else -np.sqrt(mse)
 
     def stage(self, eng, X, fold, n_splits, x_staged=False):
         if not x_staged:
@@ -77,12 +97,14 @@ class _RidgeFamily:
     def run_columns(self, eng, cols, n_splits, return_train_score):
         cols = np.asarray(cols, dtype=np.int64)
         out = {
-            "test_score": np.zeros(len(cols)), "n_test": np.zeros(len(cols), dtype=np.int64),
+            "n_test": np.zeros(len(cols), dtype=np.int64),
             "fit_time": np.zeros(len(cols)), "score_time": np.zeros(len(cols)),
             "n_iter": np.zeros(len(cols), dtype=np.int32), "status": np.zeros(len(cols), dtype=np.int32),
         }
-        if return_train_score:
-            out["train_score"] = np.zeros(len(cols))
+        for name in self.metrics:
+            out["test_%s" % name] = np.zeros(len(cols))
+            if return_train_score:
+                out["train_%s" % name] = np.zeros(len(cols))
         cand = cols // n_splits
         fold = (cols % n_splits).astype(np.int32)
         groups = defaultdict(list)
@@ -96,16 +118,18 @@ class _RidgeFamily:
             t1 = time.time()
             sse, count = eng.linear_r2_batch(res["coef"], fold[idx])
             t2 = time.time()
-            score = 1.0 - sse / self.sst_test[fold[idx]]
-            score[res["status"] != 1] = np.nan
-            out["test_score"][idx] = score
+            for name, kind in self.metrics.items():
+                score = self._metric(kind, sse, count, self.sst_test[fold[idx]])
+                score[res["status"] != 1] = np.nan
+                out["test_%s" % name][idx] = score
             out["n_test"][idx] = count
             out["fit_time"][idx] = (t1 - t0) / len(idx)
             out["score_time"][idx] = (t2 - t1) / len(idx)
             out["status"][idx] = res["status"]
             if return_train_score:
-                sse2, _ = eng.linear_r2_batch(res["coef"], (-3 - fold[idx]).astype(np.int32))
-                out["train_score"][idx] = 1.0 - sse2 / self.sst_train[fold[idx]]
+                sse2, n2 = eng.linear_r2_batch(res["coef"], (-3 - fold[idx]).astype(np.int32))
+                for name, kind in self.metrics.items():
+                    out["train_%s" % name][idx] = self._metric(kind, sse2, n2, self.sst_train[fold[idx]])
         return out
 
     def refit(self, eng, params, X_dtype, n_features):

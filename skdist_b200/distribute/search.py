@@ -109,6 +109,48 @@ def _check_logreg(est):
     return p
 
 
+def _classifier_metric(scorer):
+    """Name of the count-based metric a scikit-learn scorer computes, or None.  All of them are
+    functions of the per-column confusion counts the scoring kernels deliver."""
+    if type(scorer).__name__ == "_PassthroughScorer":       # estimator.score == accuracy (ref utils.py:75-143)
+        return "accuracy"
+    f = getattr(scorer, "_score_func", None)
+    name = getattr(f, "__name__", "")
+    kwargs = dict(getattr(scorer, "_kwargs", {}) or {})
+    if getattr(scorer, "_sign", 1) != 1:
+        return None
+    if kwargs.pop("average", "binary") != "binary" or kwargs.pop("pos_label", 1) != 1 or kwargs:
+        return None
+    return {"accuracy_score": "accuracy", "f1_score": "f1", "precision_score": "precision",
+            "recall_score": "recall", "balanced_accuracy_score": "balanced_accuracy"}.get(name)
+
+
+def _metric_from_counts(kind, correct, count, pred_pos, actual_pos):
+    """scikit-learn's formulas on confusion counts (SK/metrics/_classification.py: accuracy_score,
+    precision_recall_fscore_support with zero_division -> 0.0, balanced_accuracy_score)."""
+    correct = np.asarray(correct, dtype=np.float64)
+    count = np.asarray(count, dtype=np.float64)
+    if kind == "accuracy":
+        return correct / np.maximum(count, 1)
+    pred_pos = np.asarray(pred_pos, dtype=np.float64)
+    actual_pos = np.asarray(actual_pos, dtype=np.float64)
+    tp = (pred_pos + actual_pos + correct - count) / 2.0
+    fp, fn = pred_pos - tp, actual_pos - tp
+    tn = count - tp - fp - fn
+
+    def div(a, b):
+        return np.divide(a, b, out=np.zeros_like(a), where=b != 0)
+    if kind == "precision":
+        return div(tp, pred_pos)
+    if kind == "recall":
+        return div(tp, actual_pos)
+    if kind == "f1":
+        return div(2.0 * tp, actual_pos + pred_pos)
+    if kind == "balanced_accuracy":
+        return (div(tp, tp + fn) + div(tn, tn + fp)) / 2.0
+    raise ValueError(kind)
+
+
 class _LogRegFamily:
     """(candidate x fold) columns of binary L2 logistic regression."""
 
@@ -129,35 +171,50 @@ class _LogRegFamily:
                 "LogisticRegression device path is binary (got %d classes); wrap the estimator "
                 "in DistOneVsRestClassifier for multiclass" % len(self.classes_))
         self.y_class = np.searchsorted(self.classes_, y).astype(np.int32)
-        scorer = scorers["score"]
-        # scoring=None -> _PassthroughScorer -> estimator.score == accuracy (ref utils.py:75-143)
-        sname = type(scorer).__name__
-        ok = sname == "_PassthroughScorer"
-        if not ok:
-            f = getattr(scorer, "_score_func", None)
-            ok = getattr(f, "__name__", "") == "accuracy_score" and getattr(scorer, "_sign", 1) == 1 \
-                and not getattr(scorer, "_kwargs", {})
-        if not ok:
-            raise NotImplementedError(
-                "only scoring=None / 'accuracy' is scored on the device for classifiers (got %r)" % (scorer,))
+        # every scorer must be a count-based metric (accuracy / precision / recall / f1 / balanced
+        # accuracy on predict); scoring=None -> _PassthroughScorer -> estimator.score == accuracy
+        self.metrics = {}
+        for name, scorer in scorers.items():
+            kind = _classifier_metric(scorer)
+            if kind is None:
+                raise NotImplementedError(
+                    "scorer %r has no device path for classifiers (supported: accuracy, precision, recall, "
+                    "f1, balanced_accuracy with default arguments)" % (scorer,))
+            self.metrics[name] = kind
+        self.needs_pred_pos = any(k != "accuracy" for k in self.metrics.values())
 
     def stage(self, eng, X, fold, n_splits, x_staged=False):
         if not x_staged:
             eng.stage_x(X)
         eng.stage_labels(self.y_class)
         eng.stage_folds(fold, n_splits)
+        self.pos_in_fold = np.bincount(np.asarray(fold)[self.y_class == 1], minlength=n_splits).astype(np.int64)
+        self.total_pos = int((self.y_class == 1).sum())
+
+    def _scores(self, eng, coef, codes, pos, actual_pos):
+        """{scorer name: per-column value} on the rows selected by the scoring codes."""
+        correct, count = eng.linear_score_batch(coef, codes, pos)
+        pred_pos = None
+        if self.needs_pred_pos:
+            # a positive class id that matches no row makes "correct" count the predicted negatives
+            neg_correct, _ = eng.linear_score_batch(coef, codes, np.full(len(pos), -7, dtype=np.int32))
+            pred_pos = count - neg_correct
+        return {name: _metric_from_counts(kind, correct, count, pred_pos, actual_pos)
+                for name, kind in self.metrics.items()}, count
 
     def run_columns(self, eng, cols, n_splits, return_train_score):
         """Fit + score the given global column ids (col = cand * n_splits + fold).
         Returns dict of per-column arrays aligned with `cols`."""
         cols = np.asarray(cols, dtype=np.int64)
         out = {
-            "test_score": np.zeros(len(cols)), "n_test": np.zeros(len(cols), dtype=np.int64),
+            "n_test": np.zeros(len(cols), dtype=np.int64),
             "fit_time": np.zeros(len(cols)), "score_time": np.zeros(len(cols)),
             "n_iter": np.zeros(len(cols), dtype=np.int32), "status": np.zeros(len(cols), dtype=np.int32),
         }
-        if return_train_score:
-            out["train_score"] = np.zeros(len(cols))
+        for name in self.metrics:           # one array per scorer: "test_<name>" (+ "train_<name>")
+            out["test_%s" % name] = np.zeros(len(cols))
+            if return_train_score:
+                out["train_%s" % name] = np.zeros(len(cols))
         cand = cols // n_splits
         fold = (cols % n_splits).astype(np.int32)
         groups = defaultdict(list)
@@ -171,17 +228,20 @@ class _LogRegFamily:
             t0 = time.time()
             res = eng.logreg_fit_batch(C, fold[idx], pos, fit_intercept=fi, tol=tol, max_iter=mi)
             t1 = time.time()
-            correct, count = eng.linear_score_batch(res["coef"], fold[idx], pos)
+            vals, count = self._scores(eng, res["coef"], fold[idx], pos, self.pos_in_fold[fold[idx]])
             t2 = time.time()
-            out["test_score"][idx] = correct / np.maximum(count, 1)
+            for name, v in vals.items():
+                out["test_%s" % name][idx] = v
             out["n_test"][idx] = count
             out["fit_time"][idx] = (t1 - t0) / len(idx)
             out["score_time"][idx] = (t2 - t1) / len(idx)
             out["n_iter"][idx] = res["n_iter"]
             out["status"][idx] = res["status"]
             if return_train_score:
-                c2, n2 = eng.linear_score_batch(res["coef"], (-3 - fold[idx]).astype(np.int32), pos)
-                out["train_score"][idx] = c2 / np.maximum(n2, 1)
+                vals, _ = self._scores(eng, res["coef"], (-3 - fold[idx]).astype(np.int32), pos,
+                                       self.total_pos - self.pos_in_fold[fold[idx]])
+                for name, v in vals.items():
+                    out["train_%s" % name][idx] = v
         return out
 
     def refit(self, eng, params, X_dtype, n_features):
@@ -247,9 +307,16 @@ class DistBaseSearchCV(_ScParamMixin):
         estimator = self.estimator
         cv = check_cv(self.cv, y, classifier=is_classifier(estimator))
         scorers, self.multimetric_ = _check_multimetric_scoring(self.estimator, scoring=self.scoring)
-        if self.multimetric_:
-            raise NotImplementedError("multi-metric scoring is not supported on the device path")
-        refit_metric = "score"
+        if self.multimetric_:                                   # ref search.py:340-358
+            if self.refit is not False and (not isinstance(self.refit, str) or self.refit not in scorers):
+                raise ValueError(
+                    "For multi-metric scoring, the parameter refit must be set to a scorer key to refit an "
+                    "estimator with the best parameter setting on the whole data and make the best_* "
+                    "attributes available for that metric. If this is not needed, refit should be set to "
+                    "False explicitly. %r was passed." % self.refit)
+            refit_metric = self.refit
+        else:
+            refit_metric = "score"
 
         X, y, groups = indexable(X, y, groups)
         n_splits = cv.get_n_splits(X, y, groups)
@@ -287,19 +354,21 @@ class DistBaseSearchCV(_ScParamMixin):
         deal_order = (np.arange(n_candidates)[None, :] * n_splits + np.arange(n_splits)[:, None]).ravel()
         my_cols = parallel.shard_blocks(n_cols, rank, world, deal_order)
         loc = family.run_columns(eng, my_cols, n_splits, bool(self.return_train_score))
-        keys = ["test_score", "n_test", "fit_time", "score_time"]
+        metric_names = list(family.metrics)
+        keys = ["n_test", "fit_time", "score_time"] + ["test_%s" % m for m in metric_names]
         if self.return_train_score:
-            keys.append("train_score")
+            keys += ["train_%s" % m for m in metric_names]
         res = {k: parallel.all_gather_blocks(loc[k], n_cols, rank, world, deal_order) for k in keys}
 
         error_score = self.error_score
-        bad = ~np.isfinite(res["test_score"])
-        if np.any(bad):
-            # ref search.py:226-259 semantics for a failed fit
-            if isinstance(error_score, numbers.Number):
-                res["test_score"][bad] = error_score
-            else:
-                raise ValueError("a fit produced a non-finite score and error_score=%r" % (error_score,))
+        for m in metric_names:
+            bad = ~np.isfinite(res["test_%s" % m])
+            if np.any(bad):
+                # ref search.py:226-259 semantics for a failed fit
+                if isinstance(error_score, numbers.Number):
+                    res["test_%s" % m][bad] = error_score
+                else:
+                    raise ValueError("a fit produced a non-finite score and error_score=%r" % (error_score,))
 
         results = {}
 
@@ -329,15 +398,17 @@ class DistBaseSearchCV(_ScParamMixin):
 
         # ref search.py:510-519: weights = test-fold sizes when `iid` is truthy ("warn" default)
         test_sample_counts = np.array(res["n_test"][:n_splits], dtype=int)
-        _store("test_score", res["test_score"], splits=True, rank=True,
-               weights=test_sample_counts if self.iid else None)
-        if self.return_train_score:
-            _store("train_score", res["train_score"], splits=True)
+        for m in metric_names:                                  # ref search.py:512-533
+            _store("test_%s" % m, res["test_%s" % m], splits=True, rank=True,
+                   weights=test_sample_counts if self.iid else None)
+            if self.return_train_score:
+                _store("train_%s" % m, res["train_%s" % m], splits=True)
 
-        # ref search.py:538-541
-        self.best_index_ = results["rank_test_%s" % refit_metric].argmin()
-        self.best_params_ = candidate_params[self.best_index_]
-        self.best_score_ = results["mean_test_%s" % refit_metric][self.best_index_]
+        # ref search.py:535-541: best_* only when a refit metric is defined
+        if self.refit or not self.multimetric_:
+            self.best_index_ = results["rank_test_%s" % refit_metric].argmin()
+            self.best_params_ = candidate_params[self.best_index_]
+            self.best_score_ = results["mean_test_%s" % refit_metric][self.best_index_]
 
         if self.refit:
             # ref search.py:543-550 (one more full-data fit, here on the device)
@@ -347,7 +418,7 @@ class DistBaseSearchCV(_ScParamMixin):
             if self.preds:
                 self.preds_ = family.fold_proba(eng, self.best_params_, fold, n_splits)
 
-        self.scorer_ = scorers["score"]
+        self.scorer_ = scorers if self.multimetric_ else scorers["score"]   # ref search.py:563
         self.cv_results_ = results
         self.n_splits_ = n_splits
 

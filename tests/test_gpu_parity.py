@@ -434,3 +434,24 @@ def test_non_finite_input_is_rejected(eng):
     with pytest.raises(ValueError):
         eng.stage_x(Xb)
     eng.stage_x(X)          # a clean matrix still stages afterwards
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_multimetric_search_on_device(eng):
+    """f1 / precision / recall / balanced accuracy come from the confusion counts of two counting passes
+    (the second with a positive class id that matches no row); compared with scikit-learn on a
+    well-conditioned grid (all fits converge)."""
+    from sklearn.model_selection import GridSearchCV
+    from skdist.distribute.search import DistGridSearchCV
+    X, y = make_g1_classification(9000, 24, seed=19)
+    scoring = ["accuracy", "f1", "precision", "recall", "balanced_accuracy"]
+    grid = {"C": [1e-4, 1e-3, 1e-2]}
+    ours = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring=scoring, refit="f1",
+                            return_train_score=True).fit(X, y)
+    ref = GridSearchCV(LogisticRegression(), grid, cv=3, scoring=scoring, refit="f1", return_train_score=True).fit(X, y)
+    for m in scoring:
+        np.testing.assert_allclose(ours.cv_results_["mean_test_%s" % m], ref.cv_results_["mean_test_%s" % m],
+                                   rtol=0, atol=2e-3, err_msg=m)
+        np.testing.assert_allclose(ours.cv_results_["mean_train_%s" % m], ref.cv_results_["mean_train_%s" % m],
+                                   rtol=0, atol=2e-3, err_msg=m)
+    assert ours.best_params_ == ref.best_params_

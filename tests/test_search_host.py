@@ -151,3 +151,38 @@ def test_multi_model_search_against_reference_functions(fake_engine):
     assert ms.cv_results_["model_index"] == list(results["model_index"])
     np.testing.assert_allclose(ms.cv_results_["mean_test_score"], results["score"].values, atol=1e-12)
     assert ms.best_params_ == results.iloc[int(np.argmax(results["score"].values))]["param_set"]
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_multimetric_scoring_matches_sklearn(fake_engine):
+    """Multi-metric search (ref search.py:336-358, 512-541): every supported scorer is a function of the
+    per-column confusion counts (classifiers) or of (SSE, n) (regressors); cv_results_ must carry the same
+    keys and values scikit-learn's GridSearchCV produces."""
+    from sklearn.linear_model import Ridge
+    from sklearn.model_selection import GridSearchCV
+    from skdist_b200.datasets import make_g1_regression
+    X, y = make_g1_classification(600, 6, seed=5)
+    scoring = ["accuracy", "f1", "precision", "recall", "balanced_accuracy"]
+    grid = {"C": [0.001, 0.05, 1.0]}
+    ours = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring=scoring, refit="f1",
+                            return_train_score=True).fit(X, y)
+    ref = GridSearchCV(LogisticRegression(), grid, cv=3, scoring=scoring, refit="f1", return_train_score=True).fit(X, y)
+    for m in scoring:
+        for k in ["split0_test_%s" % m, "split2_test_%s" % m, "mean_test_%s" % m, "mean_train_%s" % m]:
+            np.testing.assert_allclose(ours.cv_results_[k], ref.cv_results_[k], rtol=0, atol=1e-12, err_msg=k)
+        np.testing.assert_array_equal(ours.cv_results_["rank_test_%s" % m], ref.cv_results_["rank_test_%s" % m])
+    assert ours.best_params_ == ref.best_params_ and ours.multimetric_ and set(ours.scorer_) == set(scoring)
+    assert ours.best_score_ == pytest.approx(ref.best_score_, abs=1e-12)
+    with pytest.raises(ValueError):      # multi-metric needs refit=<scorer name> or False
+        DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring=scoring).fit(X, y)
+    nr = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring=scoring, refit=False).fit(X, y)
+    assert not hasattr(nr, "best_index_")
+    with pytest.raises(NotImplementedError):
+        DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring="roc_auc").fit(X, y)
+    Xr, yr = make_g1_regression(500, 5, seed=2)
+    rs = ["r2", "neg_mean_squared_error", "neg_root_mean_squared_error"]
+    ours = DistGridSearchCV(Ridge(), {"alpha": [0.1, 10.0]}, None, cv=3, scoring=rs, refit="r2").fit(Xr, yr)
+    ref = GridSearchCV(Ridge(), {"alpha": [0.1, 10.0]}, cv=3, scoring=rs, refit="r2").fit(Xr, yr)
+    for m in rs:      # per split: the reference weights the mean by fold size (iid), scikit-learn 1.9 does not
+        for k in ("split0_test_%s" % m, "split1_test_%s" % m, "split2_test_%s" % m):
+            np.testing.assert_allclose(ours.cv_results_[k], ref.cv_results_[k], rtol=2e-5, atol=1e-6, err_msg=k)
