@@ -447,6 +447,11 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   if (!c->X || !c->ycls) return fail(c, "skd_logreg_fit_batch: stage X and labels first");
   if (B <= 0 || !C || !col_fold || !col_pos || !coef_out || !n_iter_out || !status_out)
     return fail(c, "skd_logreg_fit_batch: bad arguments");
+  // staged column masks are one-shot: whatever happens in this call, they do not outlive it
+  struct MaskGuard {
+    Ctx* c; std::vector<uint8_t> mask; int32_t cols;
+    explicit MaskGuard(Ctx* c_) : c(c_), cols(c_->fmask_cols) { mask.swap(c_->h_fmask); c_->fmask_cols = 0; }
+  } staged_masks(c);
   if (max_iter < 1) return fail(c, "skd_logreg_fit_batch: max_iter must be >= 1");
   SKD_CUDA(c, cudaSetDevice(c->device));
   const int64_t n = c->n, d = c->d, ldx = c->ldx;
@@ -537,12 +542,10 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
     SKD_CUDA(c, sx.alloc(&w.col_neg1, (size_t)B));
   }
   SKD_CUDA(c, sx.alloc(&w.n_evals, (size_t)B));
-  const bool use_fmask = c->fmask_cols > 0;
+  const bool use_fmask = staged_masks.cols > 0;
   if (use_fmask) {
-    if (c->fmask_cols != B || (int64_t)c->h_fmask.size() != (int64_t)B * d) {
-      c->fmask_cols = 0; c->h_fmask.clear();
+    if (staged_masks.cols != B || (int64_t)staged_masks.mask.size() != (int64_t)B * d)
       return fail(c, "skd_logreg_fit_batch: staged column masks do not match this batch (B x d)");
-    }
     SKD_CUDA(c, sx.alloc(&w.fmask, (size_t)B * d));
   }
   SKD_CUDA(c, sx.alloc(&w.slot, (size_t)w.slot_cap));
@@ -565,10 +568,9 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   SKD_CUDA(c, cudaMemcpyAsync(w.col_pos, col_pos, B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   if (col_neg) SKD_CUDA(c, cudaMemcpyAsync(w.col_neg1, hneg1.data(), B * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   if (use_fmask) {
-    SKD_CUDA(c, cudaMemcpyAsync(w.fmask, c->h_fmask.data(), (size_t)B * d, cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(w.fmask, staged_masks.mask.data(), (size_t)B * d, cudaMemcpyHostToDevice, c->stream));
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
     c->h2d += (int64_t)B * d;
-    c->fmask_cols = 0; c->h_fmask.clear();   // one-shot: consumed by this call
   }
   c->h2d += (int64_t)B * 24;
 
