@@ -18,7 +18,16 @@ Pinning status (see DESIGN.md "Oracle"):
   imported unmodified from /root/reference under a 3-line in-memory shim
   (``oracle/refshim.py``), by ``tests/golden/make_golden.py``; its outputs are
   committed as ``tests/golden/*.npz`` and re-checked by ``tests/test_oracle.py``.
+* Live pins that need /root/reference (skipped where it is absent): the multi-model search
+  against the reference's ``_raw_sampler`` / ``_fit_one_fold`` / ``_get_results``
+  (``tests/test_search_host.py``) and the feature eliminator against its ``_fit_and_score_one`` /
+  ``_drop_col`` (``tests/test_eliminate_host.py``).
+* The SGD (``sgd_oracle.py``), logistic (``logreg_oracle.py``) and ridge (``ridge_oracle.py``)
+  restatements are bit-identical to the installed scikit-learn estimators (``tests/test_oracle.py``,
+  ``tests/test_multiclass_host.py``); trees are checked against scikit-learn directly, which the
+  reference's ``_build_trees`` equals tree for tree (``tests/test_forest_host.py``).
 * The reference's own tests pin only toy predictions
-  (skdist/distribute/tests/test_search.py:37-56 etc.); those are reproduced in
-  ``tests/test_reference_cases.py``.
+  (skdist/distribute/tests/test_search.py:37-56, test_multiclass.py:23-38, test_ensemble.py:25-58);
+  those cases are reproduced in ``tests/test_search_host.py``, ``tests/test_multiclass_host.py``,
+  ``tests/test_forest_gpu.py`` (incl. the golden regressor predictions [0.15, 0.18, 0.12]).
 """
