@@ -74,6 +74,7 @@ static int alloc_eval_buffers(Ctx* c, Scratch& sx, LogregWork& w, int B, int slo
     SKD_CUDA(c, cudaMemsetAsync(w.Wh, 0, wbytes, c->stream));
     SKD_CUDA(c, cudaMemsetAsync(w.Wl, 0, wbytes, c->stream));
     SKD_CUDA(c, sx.alloc(&w.gradp, (size_t)w.cap_sc * w.ldw));
+    SKD_CUDA(c, sx.alloc(&w.gradr, (size_t)w.slots_pad_cap * w.ldw));
   } else {
     w.ldw = (int)ldx;
     w.gscale = nullptr;
@@ -589,38 +590,62 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
   std::vector<double> round_flops;
   std::vector<int> round_act, round_run;
   size_t ev_used = 0;
+  // Several optimiser rounds are enqueued per host round trip: the kernels read the live slot count
+  // on the device, the host's n_act is only an upper bound that sizes the grids and strides.  Each
+  // round records {slots, running} in `hist` so the profile below uses the true counts.
+  const int rounds_per_sync = 4;
+  int32_t* hist = nullptr;
+  const long hist_cap = max_rounds + rounds_per_sync + 4;
+  SKD_CUDA(c, sx.alloc(&hist, (size_t)2 * hist_cap));
+  std::vector<int> ev_round;              // round index of every profiled evaluation
   while (n_run > 0) {
-    int nz_used = 0;
-    if (c->prof) {
-      if (c->prof_events.size() < ev_used + 2) {
-        cudaEvent_t a, b;
-        SKD_CUDA(c, cudaEventCreate(&a));
-        SKD_CUDA(c, cudaEventCreate(&b));
-        c->prof_events.push_back(a);
-        c->prof_events.push_back(b);
+    for (int k = 0; k < rounds_per_sync; ++k) {
+      int nz_used = 0;
+      if (c->prof) {
+        if (c->prof_events.size() < ev_used + 2) {
+          cudaEvent_t a, b;
+          SKD_CUDA(c, cudaEventCreate(&a));
+          SKD_CUDA(c, cudaEventCreate(&b));
+          c->prof_events.push_back(a);
+          c->prof_events.push_back(b);
+        }
+        SKD_CUDA(c, cudaEventRecord(c->prof_events[ev_used], c->stream));
       }
-      SKD_CUDA(c, cudaEventRecord(c->prof_events[ev_used], c->stream));
+      if (eval_dispatch(c, w, n_act, &nz_used)) return 1;
+      if (c->prof) {
+        SKD_CUDA(c, cudaEventRecord(c->prof_events[ev_used + 1], c->stream));
+        ev_used += 2;
+        ev_round.push_back((int)rounds);
+      }
+      if (force_rounds > 0) {   // timing experiments: repeat the evaluation of the initial point
+        if (++rounds >= force_rounds) break;
+        continue;
+      }
+      if (lbfgs_dev_enqueue(c, w, n_act, nz_used, fit_intercept, hist + 2 * rounds)) return 1;
+      if (++rounds > max_rounds) return fail(c, "skd_logreg_fit_batch: round limit exceeded (internal error)");
     }
-    if (eval_dispatch(c, w, n_act, &nz_used)) return 1;
-    if (c->prof) {
-      SKD_CUDA(c, cudaEventRecord(c->prof_events[ev_used + 1], c->stream));
-      ev_used += 2;
-      // algorithmic work of this launch: 4 * n_train * d per active column; the active set is
-      // only known on the device, so use the mean training fraction of the batch
-      round_flops.push_back(4.0 * (double)d * (double)n_run * mean_ntrain);
-      round_act.push_back(n_act);
-      round_run.push_back(n_run);
-    }
+    if (force_rounds > 0) { if (rounds >= force_rounds) break; continue; }
     int n_next = 0, r_next = 0;
-    if (force_rounds > 0) {   // timing experiments: repeat the evaluation of the initial point
-      if (++rounds >= force_rounds) break;
-      continue;
-    }
-    if (lbfgs_dev_step(c, w, n_act, nz_used, fit_intercept, &n_next, &r_next)) return 1;
+    if (lbfgs_dev_readback(c, w, &n_next, &r_next)) return 1;
     n_act = n_next;
     n_run = r_next;
-    if (++rounds > max_rounds) return fail(c, "skd_logreg_fit_batch: round limit exceeded (internal error)");
   }
+  // true per-round counts (columns evaluated in round r = running after round r - 1)
+  std::vector<int32_t> hhist((size_t)2 * std::max<long>(rounds, 1), 0);
+  if (force_rounds == 0 && rounds > 0)
+    SKD_CUDA(c, cudaMemcpyAsync(hhist.data(), hist, (size_t)2 * rounds * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  long live_rounds = 0;
+  for (size_t e = 0; e < ev_round.size(); ++e) {
+    const int r = ev_round[e];
+    const int running = (force_rounds > 0 || r == 0) ? B : hhist[2 * (r - 1) + 1];
+    const int slots = (force_rounds > 0 || r == 0) ? (w.grouped ? (int)hslots.size() : B) : hhist[2 * (r - 1)];
+    round_flops.push_back(4.0 * (double)d * (double)running * mean_ntrain);
+    round_act.push_back(slots);
+    round_run.push_back(running);
+  }
+  for (long r = 0; r < rounds; ++r)
+    if (force_rounds > 0 || r == 0 || hhist[2 * (r - 1) + 1] > 0) ++live_rounds;
   tr.mark("rounds");
   if (c->prof) {
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -630,11 +655,12 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
       if (tr.on && getenv("SKDIST_B200_TRACE")[0] == '2')
         fprintf(stderr, "[skd trace] round %3d slots %5d running %5d eval %7.3f ms\n", (int)(i / 2), round_act[i / 2],
                 round_run[i / 2], ms);
+      if (round_run[i / 2] <= 0) continue;      // enqueued past convergence: the kernels returned at once
       c->prof_eval_ms += ms;
       c->prof_eval_flops += round_flops[i / 2];
       c->prof_eval_launches += 1;
     }
-    c->prof_rounds += rounds;
+    c->prof_rounds += live_rounds;
   }
   if (lbfgs_dev_finish(c, w, dcoef, dniter, dstatus, dloss)) return 1;
   SKD_CUDA(c, cudaMemcpyAsync(coef_out, dcoef, (size_t)B * dp * sizeof(float), cudaMemcpyDeviceToHost, c->stream));

@@ -44,6 +44,32 @@ struct CtaPar {
   }
 };
 
+// One WARP per column: no block barriers, reductions by shuffles.  The optimiser's vector
+// operations are a few hundred elements long; a 128-thread CTA spent most of its time in the two
+// barriers of every reduction.
+struct WarpPar {
+  __device__ __forceinline__ int tid() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int nthr() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+  __device__ __forceinline__ double block_sum(double v) const {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  }
+  __device__ __forceinline__ double dot(const double* a, const double* b, int n) const {
+    double acc = 0.0;
+    for (int i = threadIdx.x & 31; i < n; i += 32) acc += a[i] * b[i];
+    return block_sum(acc);
+  }
+  __device__ __forceinline__ double amax(const double* a, int n) const {
+    double m = 0.0;
+    for (int i = threadIdx.x & 31; i < n; i += 32) m = fmax(m, fabs(a[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    return m;
+  }
+};
+
 __device__ __forceinline__ LbfgsVectors col_vectors(double* base, int n, int m) {
   LbfgsVectors v;
   double* p = base;
@@ -62,25 +88,28 @@ __device__ __forceinline__ LbfgsVectors col_vectors(double* base, int n, int m) 
 
 // f, g of slot s from the evaluation partials, with the L2 term added in float64 exactly as
 // SK/linear_model/_linear_loss.py:349-361 does (penalty on the weights only).
-__device__ __forceinline__ double gather_fg(const CtaPar& P, int s, int n_act, int nz_used, int d,
+template <class Par>
+__device__ __forceinline__ double gather_fg(const Par& P, int s, int n_act, int nz_used, int d,
                                             int ldx, int fit_intercept,
                                             const double* __restrict__ lossp,
                                             const double* __restrict__ gsump,
                                             const float* __restrict__ gradp,
                                             const double* __restrict__ gscale, double l2,
                                             double inv_n, const double* x, double* g,
-                                            const uint8_t* __restrict__ fmask = nullptr) {
+                                            const uint8_t* __restrict__ fmask = nullptr,
+                                            const double* __restrict__ gradr = nullptr) {
   double lsum = 0.0, gsum = 0.0;
   for (int z = 0; z < nz_used; ++z) {
     lsum += lossp[(size_t)z * n_act + s];
     gsum += gsump[(size_t)z * n_act + s];
   }
   double wsq = 0.0;
-  for (int k = threadIdx.x; k < d; k += LB_THREADS) {
+  for (int k = P.tid(); k < d; k += P.nthr()) {
     double acc = 0.0;
     // the partials are added in chunk order (the result must not depend on anything else); eight
     // loads are put in flight at a time, the additions stay sequential
     int z = 0;
+    if (gradr) { acc = gradr[(size_t)s * ldx + k]; z = nz_used; }   // already reduced by lb_reduce_kernel
     for (; z + 8 <= nz_used; z += 8) {
       float v[8];
 #pragma unroll
@@ -96,9 +125,32 @@ __device__ __forceinline__ double gather_fg(const CtaPar& P, int s, int n_act, i
     g[k] = (fmask && !fmask[k]) ? 0.0 : acc * inv_n + l2 * xk;
     wsq += xk * xk;
   }
-  if (threadIdx.x == 0) g[d] = fit_intercept ? gsum * inv_n : 0.0;
+  if (P.tid() == 0) g[d] = fit_intercept ? gsum * inv_n : 0.0;
   wsq = P.block_sum(wsq);
   return lsum * inv_n + 0.5 * l2 * wsq;
+}
+
+// Sum of the per-chunk gradient partials of every (slot, feature) in chunk order, float64, one
+// thread per element: the whole device streams the partial array once (one column's optimiser CTA
+// alone cannot pull its 147 KB fast enough).  Same additions in the same order as gather_fg's loop.
+__global__ void __launch_bounds__(256)
+lb_reduce_kernel(const float* __restrict__ gradp, int nz, int n_act, int ldx, const int32_t* __restrict__ n_act_dev,
+                 double* __restrict__ gradr) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)min(n_act, (int)*n_act_dev) * ldx;
+  if (e >= total) return;
+  const size_t stride = (size_t)n_act * ldx;
+  double acc = 0.0;
+  int z = 0;
+  for (; z + 8 <= nz; z += 8) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = gradp[(size_t)(z + q) * stride + e];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc += (double)v[q];
+  }
+  for (; z < nz; ++z) acc += (double)gradp[(size_t)z * stride + e];
+  gradr[e] = acc;
 }
 
 // Diagnostic / test entry: objective and gradient of every slot at caller-supplied points.
@@ -140,29 +192,32 @@ __global__ void lb_init_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride,
   }
 }
 
+// one warp per slot, four slots per CTA
 __global__ void __launch_bounds__(LB_THREADS)
 lb_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta* slot, int n_act,
                int nz_used, int d, int ldx, int fit_intercept, const double* __restrict__ lossp,
                const double* __restrict__ gsump, const float* __restrict__ gradp,
                const double* __restrict__ gscale,
                const double* __restrict__ l2v, const double* __restrict__ inv_nv,
-               int32_t* n_evals, const uint8_t* __restrict__ fmask) {
-  __shared__ double red[8];
-  const int s = blockIdx.x;
-  if (s >= n_act) return;
+               int32_t* n_evals, const uint8_t* __restrict__ fmask, const int32_t* __restrict__ n_act_dev,
+               const double* __restrict__ gradr) {
+  const int s = blockIdx.x * (LB_THREADS / 32) + (threadIdx.x >> 5);
+  // n_act (host) may be a stale upper bound when several rounds are enqueued per host round trip:
+  // the partial sums are indexed with it, the live slot count is the device's
+  if (s >= n_act || s >= *n_act_dev) return;
   const int col = slot[s].col;
   if (col < 0) return;   // padding slot of the fold-grouped layout
   LbfgsScalars st = sc[col];
   const int n = st.n, m = st.m;
   LbfgsVectors v = col_vectors(vec + (size_t)col * vec_stride, n, m);
-  CtaPar P{red};
+  WarpPar P;
   const double l2 = l2v[col], inv_n = inv_nv[col];
   double f = gather_fg(P, s, n_act, nz_used, d, ldx, fit_intercept, lossp, gsump, gradp, gscale, l2,
-                       inv_n, v.x, v.g, fmask ? fmask + (size_t)col * d : nullptr);
-  __syncthreads();
+                       inv_n, v.x, v.g, fmask ? fmask + (size_t)col * d : nullptr, gradr);
+  __syncwarp();
   lbfgs_advance(P, st, v, f);
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  __syncwarp();
+  if (P.tid() == 0) {
     sc[col] = st;
     n_evals[col] += 1;
   }
@@ -175,6 +230,7 @@ __global__ void lb_compact_kernel(const LbfgsScalars* sc, SlotMeta* slot, int n_
   __shared__ int base_s;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) base_s = 0;
+  { const int live = *n_act_out; if (live < n_act_in) n_act_in = live; }   // host value may be a stale upper bound
   __syncthreads();
   for (int start = 0; start < n_act_in; start += blockDim.x) {
     int i = start + tid;
@@ -213,7 +269,7 @@ __global__ void lb_compact_kernel(const LbfgsScalars* sc, SlotMeta* slot, int n_
   }
   if (tid == 0) {
     *n_act_out = base_s;
-    if (n_act_host) *n_act_host = base_s;
+    if (n_act_host) { n_act_host[0] = base_s; n_act_host[1] = base_s; }   // per-round record
   }
 }
 
@@ -221,7 +277,7 @@ __global__ void lb_compact_kernel(const LbfgsScalars* sc, SlotMeta* slot, int n_
 // (padding entries col = -1).  Output, in place: the still-running columns of every fold, in
 // their old order, each fold segment padded again to a multiple of 128.
 __global__ void lb_compact_grouped_kernel(const LbfgsScalars* sc, SlotMeta* slot, int n_in,
-                                          int32_t* n_slots_out, int32_t* n_run_out) {
+                                          int32_t* n_slots_out, int32_t* n_run_out, int32_t* hist) {
   __shared__ int cnt[130];       // kept per fold key (key = fold + 1, fold in [-1, 127])
   __shared__ int base[130];      // output base per fold key
   __shared__ int before[130];    // kept in earlier fold keys
@@ -230,6 +286,7 @@ __global__ void lb_compact_grouped_kernel(const LbfgsScalars* sc, SlotMeta* slot
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i < 130; i += blockDim.x) cnt[i] = 0;
   if (tid == 0) run_s = 0;
+  { const int live = *n_slots_out; if (live < n_in) n_in = live; }         // host value may be a stale upper bound
   __syncthreads();
   for (int i = tid; i < n_in; i += blockDim.x) {
     const SlotMeta sm = slot[i];
@@ -241,6 +298,7 @@ __global__ void lb_compact_grouped_kernel(const LbfgsScalars* sc, SlotMeta* slot
     for (int f = 0; f < 130; ++f) { base[f] = b; before[f] = k; b += (cnt[f] + 127) / 128 * 128; k += cnt[f]; }
     *n_slots_out = b;
     *n_run_out = k;
+    if (hist) { hist[0] = b; hist[1] = k; }   // per-round record (read back once at the end)
   }
   __syncthreads();
   // ordered scatter: global rank of a kept entry minus the kept entries of earlier folds
@@ -323,14 +381,23 @@ int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max
   return 0;
 }
 
-int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_intercept,
-                   int* n_act_out, int* n_run_out) {
+// One optimiser round on the stream, no host synchronisation: advance every live column, rebuild the
+// slot list, export the new trial points.  n_act_in may be a stale upper bound of the live slot count
+// (the kernels read the device-side count); hist (may be null) receives {slots, running} of the round.
+int lbfgs_dev_enqueue(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_intercept, int32_t* hist) {
   const int d = (int)c->d, ldx = (int)c->ldx;
-  lb_step_kernel<<<n_act_in, LB_THREADS, 0, c->stream>>>(
+  if (w.gradr && nz_used > 8) {   // many partials per slot (tensor-core path): reduce them with the whole device first
+    const int64_t total = (int64_t)n_act_in * w.ldw;
+    lb_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(w.gradp, nz_used, n_act_in, w.ldw, w.n_act,
+                                                                          w.gradr);
+    c->launches += 1;
+  }
+  lb_step_kernel<<<(n_act_in + LB_THREADS / 32 - 1) / (LB_THREADS / 32), LB_THREADS, 0, c->stream>>>(
       w.sc, w.vec, w.vec_stride, w.slot, n_act_in, nz_used, d, w.ldw, fit_intercept, w.lossp,
-      w.gsump, w.gradp, w.gscale, w.l2, w.inv_n, w.n_evals, w.fmask);
-  if (w.grouped) lb_compact_grouped_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, w.n_run);
-  else lb_compact_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, nullptr);
+      w.gsump, w.gradp, w.gscale, w.l2, w.inv_n, w.n_evals, w.fmask, w.n_act,
+      (w.gradr && nz_used > 8) ? w.gradr : nullptr);
+  if (w.grouped) lb_compact_grouped_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, w.n_run, hist);
+  else lb_compact_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.slot, n_act_in, w.n_act, hist);
   c->launches += 2;
   if (w.use_tc) {
     if (tc_export(c, w, n_act_in, nullptr, fit_intercept)) return 1;
@@ -340,6 +407,11 @@ int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_int
     c->launches += 1;
   }
   SKD_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+// Host round trip: current slot count and number of running columns.
+int lbfgs_dev_readback(Ctx* c, LogregWork& w, int* n_act_out, int* n_run_out) {
   int32_t na = 0, nr = 0;
   SKD_CUDA(c, cudaMemcpyAsync(&na, w.n_act, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   if (w.grouped) SKD_CUDA(c, cudaMemcpyAsync(&nr, w.n_run, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -383,7 +383,8 @@ struct TcParams {
   float* gradp;              // [nz x n_act x ldw]  (fit)
   unsigned long long* correct;  // [n_act]          (score)
   unsigned long long* count;    // [n_act]          (score)
-  int n_act;
+  int n_act;                 // host value: stride of the partial arrays, upper bound of the live slots
+  const int32_t* n_act_dev;  // live slot count on the device (nullptr: n_act is exact)
   int groups;
   int n_tiles;               // npad / 64
   int ldw;                   // leading dimension of gradp (== dpad)
@@ -456,6 +457,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
   // fitted coefficient -- do not depend on the grid, on how many columns share the batch, or on how
   // many GPUs the columns were dealt to.  (The host picks grid = groups * parts so that all groups
   // stream the same rows at the same time and X comes from HBM about once.)
+  const int n_live = prm.n_act_dev ? min(prm.n_act, (int)*prm.n_act_dev) : prm.n_act;
   const long long units = (long long)prm.groups * TC_NCH;
   const long long u_begin = (long long)blockIdx.x * units / gridDim.x;
   const long long u_end = (long long)(blockIdx.x + 1) * units / gridDim.x;
@@ -463,6 +465,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
   auto get_item = [&](long long u, TcItem& it) -> bool {
     it.g = (int)(u / TC_NCH);
     it.z = (int)(u % TC_NCH);
+    if (it.g * TC_BC >= n_live) return false;   // group emptied since the host last looked
     int cnt = prm.n_tiles;
     it.tl = nullptr;
     if (prm.tilelist) {
@@ -654,7 +657,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
       const bool new_group = g != g_prev;
       g_prev = g;
       const int slot = g * TC_BC + lane_in_group;
-      const bool valid = slot < prm.n_act;
+      const bool valid = slot < n_live;
       TcSlotParam sp;
       sp.inv_t = 1.f; sp.bias = 0.f; sp.fold = -1; sp.pos = -1; sp.neg1 = 0; sp.pad = 0;
       if (valid) sp = prm.sp[slot];
@@ -1076,6 +1079,7 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   prm.correct = dcorrect;
   prm.count = dcount;
   prm.n_act = n_act;
+  prm.n_act_dev = (mode == TC_FIT) ? w.n_act : nullptr;
   prm.groups = groups;
   prm.n_tiles = n_tiles;
   prm.ldw = w.ldw;

@@ -202,6 +202,7 @@ struct LogregWork {
   double* lossp = nullptr;     // [cap_sc]        indexed z * n_act + slot
   double* gsump = nullptr;     // [cap_sc]
   float* gradp = nullptr;      // [cap_sc x ldx]
+  double* gradr = nullptr;     // [slots x ldw] partials reduced in chunk order (tensor-core path)
   int32_t* n_act = nullptr;    // device scalar
   // tensor-core path (logreg_tc.cu)
   bool use_tc = false;
@@ -254,8 +255,8 @@ int tc_partials_per_slot();
 
 // device L-BFGS (lbfgs_dev.cu)
 int lbfgs_dev_init(Ctx* c, LogregWork& w, int fit_intercept, double tol, int max_iter);
-int lbfgs_dev_step(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_intercept,
-                   int* n_act_out, int* n_run_out);  // advance + compact + export (synchronises)
+int lbfgs_dev_enqueue(Ctx* c, LogregWork& w, int n_act_in, int nz_used, int fit_intercept, int32_t* hist);
+int lbfgs_dev_readback(Ctx* c, LogregWork& w, int* n_act_out, int* n_run_out);  // advance + compact + export (synchronises)
 int lbfgs_dev_gather(Ctx* c, LogregWork& w, int n_act, int nz_used, int fit_intercept,
                      const double* dx, double* df, double* dg);
 int lbfgs_dev_finish(Ctx* c, LogregWork& w, float* dcoef, int32_t* dniter, int32_t* dstatus,
