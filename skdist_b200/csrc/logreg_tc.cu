@@ -125,37 +125,6 @@ __device__ __forceinline__ uint32_t elect_one() {
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
   return pred;
 }
-// Warp-uniform issue forms: every lane executes the statement with identical operands (so the
-// descriptor arithmetic stays in the uniform datapath) and only the elected lane issues.
-__device__ __forceinline__ void mma_ss_u(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo,
-                                         uint32_t bhi, uint32_t idesc, uint32_t accumulate,
-                                         uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
-      "setp.ne.b32 p, %6, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
-      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
-      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(leader)
-      : "memory");
-}
-__device__ __forceinline__ void mma_ts_u(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi,
-                                         uint32_t idesc, uint32_t accumulate, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
-      "setp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t"
-      "mov.b64 db, {%2, %3};\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate), "r"(leader)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_u(uint64_t* bar, uint32_t leader) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(
-          smem_u32(bar)),
-      "r"(leader)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, "
