@@ -72,6 +72,41 @@ def _fold_ids(cv_splitted, n_samples):
     return fold
 
 
+def _cv_fold_ids(cv, X, y, groups, n_samples):
+    """(fold id per row, n_splits) of a cross-validator.  The generic route materialises every
+    (train, test) index pair like the reference does (search.py:379) and converts them; the two
+    splitters `check_cv` produces for an integer `cv` -- unshuffled `StratifiedKFold` / `KFold` -- are
+    restated directly (no per-split index arrays, no sorts over the rows), fold for fold what
+    SK/model_selection/_split.py:774-841 (`_make_test_folds`) and :531-547 (`_iter_test_indices`) give."""
+    from sklearn.model_selection import KFold, StratifiedKFold
+    if type(cv) is KFold and not cv.shuffle and groups is None:
+        k = cv.n_splits
+        if k > n_samples:
+            return _fold_ids(list(cv.split(X, y, groups)), n_samples), k     # let scikit-learn raise its error
+        sizes = np.full(k, n_samples // k, dtype=np.int64)
+        sizes[: n_samples % k] += 1
+        return np.repeat(np.arange(k, dtype=np.int8), sizes), k
+    if type(cv) is StratifiedKFold and not cv.shuffle and groups is None and y is not None:
+        import pandas as pd
+        y1 = np.asarray(y)
+        k = cv.n_splits
+        if y1.ndim == 1 and y1.dtype.kind in "biu" and k <= 127:
+            y_encoded = pd.factorize(y1)[0]                   # classes numbered by order of appearance
+            counts = np.bincount(y_encoded)
+            if counts.min() >= k:                             # otherwise: scikit-learn's own warnings / errors
+                # y_order = sorted codes: class c occupies positions [start_c, start_c + counts[c]); fold i
+                # takes the positions congruent to i modulo k, class by class in original row order
+                starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
+                fold = np.empty(n_samples, dtype=np.int8)
+                for c in range(len(counts)):
+                    pos = np.arange(starts[c], starts[c] + counts[c])
+                    alloc = np.bincount(pos % k, minlength=k)
+                    fold[y_encoded == c] = np.repeat(np.arange(k, dtype=np.int8), alloc)
+                return fold, k
+    cv_splitted = list(cv.split(X, y, groups))
+    return _fold_ids(cv_splitted, n_samples), len(cv_splitted)
+
+
 # ----------------------------------------------------------------------------------------
 # estimator families with a device path
 # ----------------------------------------------------------------------------------------
@@ -339,8 +374,7 @@ class DistBaseSearchCV(_ScParamMixin):
         with ThreadPoolExecutor(max_workers=1) as pool:
             staged = pool.submit(eng.stage_x, X_arr)
             try:
-                cv_splitted = list(cv.split(X, y, groups))
-                fold = _fold_ids(cv_splitted, n_samples)
+                fold, _ = _cv_fold_ids(cv, X, y, groups, n_samples)
                 family = _pick_family(estimator, candidate_params, X_arr, y_arr, scorers)
             finally:
                 staged.result()
@@ -540,9 +574,7 @@ class DistMultiModelSearch(_ScParamMixin, BaseEstimator):
         X, y, groups = indexable(X, y, groups)
         X_arr, y_arr = np.asarray(X), np.asarray(y)
         n_samples, n_features = X_arr.shape
-        cv_splitted = list(cv.split(X, y, groups))
-        n_splits = len(cv_splitted)
-        fold = _fold_ids(cv_splitted, n_samples)
+        fold, n_splits = _cv_fold_ids(cv, X, y, groups, n_samples)
         param_sets = _raw_sampler(models, self.n, random_state=self.random_state)
         _parse_partitions(self.partitions, len(param_sets) * n_splits)
 

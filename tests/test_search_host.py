@@ -186,3 +186,28 @@ def test_multimetric_scoring_matches_sklearn(fake_engine):
     for m in rs:      # per split: the reference weights the mean by fold size (iid), scikit-learn 1.9 does not
         for k in ("split0_test_%s" % m, "split1_test_%s" % m, "split2_test_%s" % m):
             np.testing.assert_allclose(ours.cv_results_[k], ref.cv_results_[k], rtol=2e-5, atol=1e-6, err_msg=k)
+
+
+def test_fast_fold_ids_equal_sklearn_splitters():
+    """The direct restatement of unshuffled StratifiedKFold / KFold must give scikit-learn's folds."""
+    from sklearn.model_selection import GroupKFold, KFold, StratifiedKFold
+    from skdist_b200.distribute.search import _cv_fold_ids, _fold_ids
+    rng = np.random.RandomState(3)
+    for n, k, ymaker in [(1000, 5, lambda: rng.randint(0, 2, 1000)), (1003, 7, lambda: rng.randint(0, 4, 1003)),
+                         (50, 3, lambda: np.r_[np.zeros(40, int), np.ones(10, int)]),
+                         (997, 4, lambda: (rng.rand(997) < 0.03).astype(np.int64) * 5 - 2),
+                         (300, 3, lambda: rng.rand(300) < 0.5)]:
+        y = ymaker()
+        X = np.zeros((n, 1))
+        for cv in (StratifiedKFold(k), KFold(k)):
+            want = _fold_ids(list(cv.split(X, y)), n)
+            got, ks = _cv_fold_ids(cv, X, y, None, n)
+            assert ks == k and got.dtype == np.int8
+            np.testing.assert_array_equal(got, want)
+    # anything else goes through cv.split
+    y = rng.randint(0, 2, 60)
+    g = np.repeat(np.arange(12), 5)
+    got, ks = _cv_fold_ids(GroupKFold(3), np.zeros((60, 1)), y, g, 60)
+    np.testing.assert_array_equal(got, _fold_ids(list(GroupKFold(3).split(np.zeros((60, 1)), y, g)), 60))
+    got, _ = _cv_fold_ids(StratifiedKFold(3, shuffle=True, random_state=0), np.zeros((60, 1)), y, None, 60)
+    np.testing.assert_array_equal(got, _fold_ids(list(StratifiedKFold(3, shuffle=True, random_state=0).split(np.zeros((60, 1)), y)), 60))
