@@ -455,3 +455,25 @@ def test_multimetric_search_on_device(eng):
         np.testing.assert_allclose(ours.cv_results_["mean_train_%s" % m], ref.cv_results_["mean_train_%s" % m],
                                    rtol=0, atol=2e-3, err_msg=m)
     assert ours.best_params_ == ref.best_params_
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_reference_toy_cases_on_device(eng):
+    """The reference's own test inputs (skdist/distribute/tests/test_search.py:37-56,
+    test_multiclass.py:23-38): 300 rows x 3 features.  Far fewer 64-row tiles than row chunks per
+    group, so most chunks are empty -- the zeroed-partials path of the tensor-core kernel."""
+    from skdist.distribute.multiclass import DistOneVsOneClassifier, DistOneVsRestClassifier
+    from skdist.distribute.search import DistGridSearchCV, DistRandomizedSearchCV
+    X = np.array([[1, 1, 1], [0, 0, 0], [-1, -1, -1]] * 100)
+    y = np.array([0, 0, 1] * 100)
+    gs = DistGridSearchCV(LogisticRegression(), {"C": [0.1, 1.0]}, cv=3).fit(X, y)
+    assert np.allclose(gs.predict(X[:3]), np.array([0, 0, 1]))
+    rs = DistRandomizedSearchCV(LogisticRegression(), {"C": [0.1, 1.0]}, cv=3, n_iter=2).fit(X, y)
+    assert np.allclose(rs.predict(X[:3]), np.array([0, 0, 1]))
+    ref = LogisticRegression(C=gs.best_params_["C"]).fit(X, y)
+    np.testing.assert_allclose(gs.best_estimator_.coef_, ref.coef_, rtol=0, atol=2e-3 * np.abs(ref.coef_).max())
+    y3 = np.array([0, 1, 2] * 100)
+    ovr = DistOneVsRestClassifier(LogisticRegression()).fit(X, y3)
+    assert np.allclose(ovr.predict(X[:3]), np.array([0, 1, 2]))
+    ovo = DistOneVsOneClassifier(LogisticRegression()).fit(X, y3)
+    assert np.allclose(ovo.predict(X[:3]), np.array([0, 1, 2]))
