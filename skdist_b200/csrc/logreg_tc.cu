@@ -371,6 +371,7 @@ struct __align__(8) TcBarriers {
   uint64_t z_full[2];
   uint64_t g_full[2];
   uint64_t w_full;
+  uint64_t w_free;      // committed by the MMA warp when it leaves a group: W_hi may be overwritten
   uint64_t wl_full;
   uint64_t acc_done;
   uint64_t acc_free;
@@ -402,6 +403,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
     for (int i = 0; i < TC_NS; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->z_full[i], 1); mbar_init(&bars->g_full[i], TC_EPI_THREADS); }
     mbar_init(&bars->w_full, 1);
+    mbar_init(&bars->w_free, 1);
     mbar_init(&bars->wl_full, TC_EPI_THREADS);
     mbar_init(&bars->acc_done, 1);
     mbar_init(&bars->acc_free, TC_EPI_THREADS);
@@ -452,15 +454,18 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
     // ================================ TMA producer ==========================================
     if (lane == 0) {
       uint32_t h = 0;  // running half-tile counter (ring position), persists across items
-      int it_local = 0, g_prev = -1;
+      int it_local = 0, g_prev = -1, w_loads = 0;
       for (long long u = u_begin; u < u_end; ++u) {
         TcItem it;
         if (!get_item(u, it)) continue;
         const int g = it.g, t0 = it.t0, t1 = it.t1;
         const int32_t* tlist = it.tl;
         if (g != g_prev) {
-          // W_hi of a new group: wait until the previous item's MMAs are done with the buffer
-          if (it_local > 0) mbar_wait(&bars->acc_done, (it_local - 1) & 1, 100);
+          // W_hi of a new group: the MMA warp signals w_free once per group it leaves, after all its
+          // MMAs on that group (one phase per reload, so the parity wait cannot alias; acc_done
+          // completes one phase per ITEM and this thread may be several one-tile items ahead)
+          if (w_loads > 0) mbar_wait(&bars->w_free, (w_loads - 1) & 1, 100);
+          ++w_loads;
           mbar_expect_tx(&bars->w_full, NCHUNK * WH_CHUNK);
 #pragma unroll
           for (int c = 0; c < NCHUNK; ++c)
@@ -504,6 +509,10 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
         if (!get_item(u, it)) { --it_local; continue; }
         const int nt = it.t1 - it.t0;
         if (it.g != g_prev) {       // weights of a new group (W_hi by TMA, W_lo staged by the epilogue warps)
+          if (g_prev >= 0) {        // every MMA issued so far belongs to earlier groups: their completion frees W_hi
+            if (elect_one()) tc_commit(&bars->w_free);
+            __syncwarp();
+          }
           mbar_wait(&bars->w_full, w_loads & 1, 200);
           mbar_wait(&bars->wl_full, w_loads & 1, 201);
           ++w_loads;

@@ -477,3 +477,30 @@ def test_reference_toy_cases_on_device(eng):
     assert np.allclose(ovr.predict(X[:3]), np.array([0, 1, 2]))
     ovo = DistOneVsOneClassifier(LogisticRegression()).fit(X, y3)
     assert np.allclose(ovo.predict(X[:3]), np.array([0, 1, 2]))
+
+
+def test_tc_more_groups_than_sms():
+    """20 480 columns = 160 groups of 128 (more groups than SMs): the (group, chunk) units are simply
+    dealt over 148 CTAs.  Columns must still equal their small-batch results bit for bit."""
+    from skdist_b200.engine import Engine
+    e = Engine(0)
+    try:
+        e.set_kernel(2)
+        X, y = make_g1_classification(6000, 32, seed=77)
+        from sklearn.model_selection import StratifiedKFold
+        fold = np.zeros(len(y), np.int8)
+        for k, (_, te) in enumerate(StratifiedKFold(4).split(X, y)):
+            fold[te] = k
+        e.stage_x(X); e.stage_labels(y.astype(np.int32)); e.stage_folds(fold, 4)
+        Cs = np.repeat(np.logspace(-4, -1, 5120), 4)
+        fs = np.tile(np.arange(4, dtype=np.int32), 5120)
+        pos = np.ones(len(Cs), np.int32)
+        big = e.logreg_fit_batch(Cs, fs, pos)
+        assert (big["status"] > 0).all()
+        pick = np.array([0, 3, 777, 10001, 20479])
+        small = e.logreg_fit_batch(Cs[pick], fs[pick], pos[pick])
+        np.testing.assert_array_equal(small["coef"], big["coef"][pick])
+        ref = LogisticRegression(C=float(Cs[777])).fit(X[fold != fs[777]], y[fold != fs[777]])
+        np.testing.assert_allclose(big["coef"][777, :32], ref.coef_[0], rtol=0, atol=2e-3 * np.abs(ref.coef_).max())
+    finally:
+        e.close()
