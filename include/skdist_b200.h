@@ -99,6 +99,25 @@ int skd_logreg_loss_grad(skd_ctx* ctx, int32_t B, const double* w_in, const doub
 int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_t* col_fold,
                            const int32_t* col_pos, int64_t* correct_out, int64_t* count_out);
 
+/* B multinomial (n_classes > 2) L2 logistic regressions sharing the staged X and class ids
+ * 0..n_classes-1: candidate j minimises mean_i[logsumexp(W x_i + b) - (W x_i + b)_{y_i}] +
+ * 0.5 / (C[j] * n_train) * ||W||^2 over the rows whose fold id != col_fold[j] (col_fold[j] < 0: all
+ * rows) with L-BFGS-B from W = 0 (m = 10, maxls = 50, gtol = tol, ftol = 64 eps, like scikit-learn's
+ * call).  coef_out[(j * n_classes + k) * (d+1) + i]: i < d weights of class k, i == d its intercept.
+ * ref: replaces the estimator.fit of search.py:228-230 for a multiclass target
+ * (SK/linear_model/_logistic.py:523-547,584-598; SK/_loss/_loss.pyx.tp:1293-1327). */
+int skd_logreg_multinomial_fit_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const double* C,
+                                     const int32_t* col_fold, int32_t fit_intercept, double tol, int32_t max_iter,
+                                     float* coef_out, int32_t* n_iter_out, int32_t* status_out, double* loss_out,
+                                     int32_t* n_evals_out, double* gpu_seconds_out);
+
+/* Accuracy counts of B multiclass linear classifiers (coef laid out as above): prediction =
+ * first arg max_k (W x + b)_k compared with the staged class id, on the rows selected by the fold
+ * codes of skd_linear_score_batch.
+ * ref: replaces search.py:264 (_score -> ClassifierMixin.score -> accuracy_score). */
+int skd_multinomial_score_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const float* coef,
+                                const int32_t* col_fold, int64_t* correct_out, int64_t* count_out);
+
 /* Batched Ridge: B independent (alpha, fold) columns from one pass over the staged X and the
  * staged real targets.  Column j trains on rows whose fold id != col_fold[j] (col_fold[j] < 0: all
  * rows).  coef_out[j*(d+1)+k] (k<d weights, k==d intercept); status_out[j] 1 = ok, 4 = matrix not

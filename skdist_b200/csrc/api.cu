@@ -822,6 +822,59 @@ int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int
   return 0;
 }
 
+int skd_logreg_multinomial_fit_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const double* C,
+                                     const int32_t* col_fold, int32_t fit_intercept, double tol, int32_t max_iter,
+                                     float* coef_out, int32_t* n_iter_out, int32_t* status_out, double* loss_out,
+                                     int32_t* n_evals_out, double* gpu_seconds_out) {
+  if (!ctx) return fail(nullptr, "skd_logreg_multinomial_fit_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || !c->ycls) return fail(c, "skd_logreg_multinomial_fit_batch: stage X and labels first");
+  if (B <= 0 || n_classes < 2 || !C || !col_fold || !coef_out || !n_iter_out || !status_out)
+    return fail(c, "skd_logreg_multinomial_fit_batch: bad arguments");
+  if (max_iter < 1) return fail(c, "skd_logreg_multinomial_fit_batch: max_iter must be >= 1");
+  for (int j = 0; j < B; ++j) {
+    if (col_fold[j] >= 0 && (!c->fold || col_fold[j] >= c->n_folds))
+      return fail(c, "skd_logreg_multinomial_fit_batch: col_fold refers to an unstaged fold");
+    if (!(C[j] > 0.0)) return fail(c, "skd_logreg_multinomial_fit_batch: C must be positive");
+  }
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  Trace tr(c, "multinomial_fit");
+  cudaEvent_t e0, e1;
+  SKD_CUDA(c, cudaEventCreate(&e0));
+  SKD_CUDA(c, cudaEventCreate(&e1));
+  SKD_CUDA(c, cudaEventRecord(e0, c->stream));
+  const int rc = multi_fit(c, B, n_classes, C, col_fold, fit_intercept, tol, max_iter, coef_out, n_iter_out,
+                           status_out, loss_out, n_evals_out);
+  float ms = 0.f;
+  if (!rc) {
+    cudaEventRecord(e1, c->stream);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (gpu_seconds_out) *gpu_seconds_out = ms * 1e-3;
+  return rc;
+}
+
+int skd_multinomial_score_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const float* coef,
+                                const int32_t* col_fold, int64_t* correct_out, int64_t* count_out) {
+  if (!ctx) return fail(nullptr, "skd_multinomial_score_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || !c->ycls) return fail(c, "skd_multinomial_score_batch: stage X and labels first");
+  if (B <= 0 || n_classes < 2 || !coef || !col_fold || !correct_out || !count_out)
+    return fail(c, "skd_multinomial_score_batch: bad arguments");
+  for (int j = 0; j < B; ++j) {
+    const int f = col_fold[j] >= 0 ? col_fold[j] : (col_fold[j] <= -3 ? -3 - col_fold[j] : -1);
+    if (col_fold[j] == -1) return fail(c, "skd_multinomial_score_batch: col_fold -1 is not a scoring code");
+    if (f >= 0 && (!c->fold || f >= c->n_folds))
+      return fail(c, "skd_multinomial_score_batch: col_fold refers to an unstaged fold");
+  }
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  Trace tr(c, "multinomial_score");
+  return multi_score(c, B, n_classes, coef, col_fold, correct_out, count_out);
+}
+
 int skd_ridge_fit_batch(skd_ctx* ctx, int32_t B, const double* alpha, const int32_t* col_fold,
                         int32_t fit_intercept, float* coef_out, int32_t* status_out,
                         double* gpu_seconds_out) {

@@ -441,4 +441,129 @@ int lbfgs_dev_finish(Ctx* c, LogregWork& w, float* dcoef, int32_t* dniter, int32
   return 0;
 }
 
+// ---- multinomial problems: one CTA per active candidate, K * dp variables ------------------
+// f, g from the evaluation partials (SK/linear_model/_linear_loss.py:349-372, multiclass branch:
+// loss = sum(loss_i) / n + 0.5 * l2 * ||W||^2, grad[:, :d] = G^T X / n + l2 * W, grad[:, d] = sum_i G / n),
+// then one step of the optimiser state machine.
+__global__ void __launch_bounds__(LB_THREADS)
+mn_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta* cand, int n_act_in,
+               const int32_t* __restrict__ n_act_dev, int K, int d, int ldx, int nz, int fit_intercept,
+               const double* __restrict__ lossp, const double* __restrict__ gsump,
+               const float* __restrict__ gradp, const double* __restrict__ l2v,
+               const double* __restrict__ inv_nv, int32_t* n_evals) {
+  __shared__ double red[8];
+  const int a = blockIdx.x;
+  if (a >= n_act_in || a >= *n_act_dev) return;
+  const int col = cand[a].col;
+  LbfgsScalars st = sc[col];
+  const int n = st.n, m = st.m, dp = d + 1;
+  LbfgsVectors v = col_vectors(vec + (size_t)col * vec_stride, n, m);
+  CtaPar P{red};
+  const double l2 = l2v[col], inv_n = inv_nv[col];
+  const size_t n_slots = (size_t)n_act_in * K;
+  double lsum = 0.0;
+  for (int z = 0; z < nz; ++z) lsum += lossp[(size_t)z * n_act_in + a];
+  double wsq = 0.0;
+  for (int idx = threadIdx.x; idx < n; idx += LB_THREADS) {
+    const int k = idx / dp, j = idx - k * dp;
+    const size_t slot = (size_t)a * K + k;
+    double acc = 0.0;
+    if (j < d) {
+      for (int z = 0; z < nz; ++z) acc += (double)gradp[((size_t)z * n_slots + slot) * ldx + j];
+      const double xk = v.x[idx];
+      v.g[idx] = acc * inv_n + l2 * xk;
+      wsq += xk * xk;
+    } else {
+      for (int z = 0; z < nz; ++z) acc += gsump[(size_t)z * n_slots + slot];
+      v.g[idx] = fit_intercept ? acc * inv_n : 0.0;
+    }
+  }
+  wsq = P.block_sum(wsq);
+  const double f = lsum * inv_n + 0.5 * l2 * wsq;
+  __syncthreads();
+  lbfgs_advance(P, st, v, f);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sc[col] = st;
+    n_evals[col] += 1;
+  }
+}
+
+__global__ void mn_init_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, int B, int n, int m,
+                               int maxiter, int maxls, double pgtol, double ftol, SlotMeta* cand,
+                               const int32_t* col_fold, int32_t* n_evals, int32_t* n_act) {
+  const int col = blockIdx.x;
+  if (col >= B) return;
+  double* base = vec + (size_t)col * vec_stride;
+  for (size_t i = threadIdx.x; i < vec_stride; i += blockDim.x) base[i] = 0.0;
+  if (threadIdx.x == 0) {
+    LbfgsScalars s;
+    lbfgs_init(s, n, m, maxiter, maxls, pgtol, ftol);
+    sc[col] = s;
+    SlotMeta sm;
+    sm.col = col; sm.fold = col_fold[col]; sm.pos = 0; sm.pad = 0;
+    cand[col] = sm;
+    n_evals[col] = 0;
+    if (col == 0) *n_act = B;
+  }
+}
+
+// trial points of the active candidates as fp32 slot rows (SK/_linear_loss.py:216-217 casts the same way)
+__global__ void mn_export_kernel(const double* vec, size_t vec_stride, const SlotMeta* cand,
+                                 const int32_t* n_act, int K, int d, int ldx, size_t bias_off, float* W) {
+  const int a = blockIdx.x / K, k = blockIdx.x - a * K;
+  if (a >= *n_act) return;
+  const double* x = vec + (size_t)cand[a].col * vec_stride + (size_t)k * (d + 1);
+  const size_t slot = (size_t)a * K + k;
+  for (int j = threadIdx.x; j < ldx; j += blockDim.x) W[slot * ldx + j] = j < d ? (float)x[j] : 0.f;
+  if (threadIdx.x == 0) W[bias_off + slot] = (float)x[d];
+}
+
+__global__ void mn_finish_kernel(const LbfgsScalars* sc, const double* vec, size_t vec_stride, int B, int n,
+                                 float* coef, int32_t* niter, int32_t* status, double* loss) {
+  const int col = blockIdx.x;
+  if (col >= B) return;
+  const double* x = vec + (size_t)col * vec_stride;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) coef[(size_t)col * n + k] = (float)x[k];
+  if (threadIdx.x == 0) {
+    const LbfgsScalars& s = sc[col];
+    niter[col] = s.nit < s.maxiter ? s.nit : s.maxiter;
+    status[col] = s.status;
+    loss[col] = s.f;
+  }
+}
+
+int multi_lbfgs_init(Ctx* c, MultiWork& w, const int32_t* d_col_fold, double tol, int max_iter) {
+  const int m = 10, maxls = 50;
+  const double ftol = 64.0 * 2.220446049250313e-16;
+  mn_init_kernel<<<w.B, 128, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.B, w.K * w.dp, m, max_iter, maxls,
+                                             tol, ftol, w.cand, d_col_fold, w.n_evals, w.n_act);
+  c->launches += 1;
+  // w0 = 0 (SK/linear_model/_logistic.py:443)
+  SKD_CUDA(c, cudaMemsetAsync(w.W, 0, ((size_t)w.B * w.K * c->ldx + (size_t)w.B * w.K) * sizeof(float), c->stream));
+  SKD_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int multi_lbfgs_enqueue(Ctx* c, MultiWork& w, int n_act_in, int fit_intercept, int32_t* hist) {
+  const int d = (int)c->d, ldx = (int)c->ldx;
+  mn_step_kernel<<<n_act_in, LB_THREADS, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.cand, n_act_in, w.n_act,
+                                                         w.K, d, ldx, w.nz, fit_intercept, w.lossp, w.gsump,
+                                                         w.gradp, w.l2, w.inv_n, w.n_evals);
+  lb_compact_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.cand, n_act_in, w.n_act, hist);
+  mn_export_kernel<<<n_act_in * w.K, 128, 0, c->stream>>>(w.vec, w.vec_stride, w.cand, w.n_act, w.K, d, ldx,
+                                                          (size_t)w.B * w.K * ldx, w.W);
+  c->launches += 3;
+  SKD_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
+int multi_lbfgs_finish(Ctx* c, MultiWork& w, float* dcoef, int32_t* dniter, int32_t* dstatus, double* dloss) {
+  mn_finish_kernel<<<w.B, 128, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.B, w.K * w.dp, dcoef, dniter,
+                                               dstatus, dloss);
+  c->launches += 1;
+  SKD_CUDA(c, cudaGetLastError());
+  return 0;
+}
+
 }  // namespace skd

@@ -354,4 +354,30 @@ int simt_decision(Ctx* c, int B, const float* dW, float* dout) {
   return 0;
 }
 
+// Z = X W^T + b for an arbitrary slot matrix (multinomial path: K slots per candidate)
+int simt_raw_prediction(Ctx* c, int n_slots, const float* dW, const float* dbias, float* dout, int ldd) {
+  int nz;
+  int64_t rpc;
+  pick_chunks(c, c->n, n_slots, 4096, &nz, &rpc);
+  dim3 g((n_slots + TN - 1) / TN, nz);
+  fwd_kernel<MODE_DECISION><<<g, 256, 0, c->stream>>>(
+      c->X, c->n, (int)c->ldx, dW, dbias, nullptr, n_slots, c->ycls, c->fold, rpc, nullptr, 0,
+      nullptr, nullptr, nullptr, nullptr, dout, ldd, nullptr);
+  c->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, std::string("simt_raw_prediction launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+// gradp[z][slot][k] = sum over the rows of chunk z of G[i][slot] * X[i][k]; ldg must be a multiple of 64
+int simt_backward(Ctx* c, const float* G, int ldg, int n_slots, int nz, int64_t rpc, float* gradp) {
+  const int ldx = (int)c->ldx;
+  dim3 gb((ldx + 63) / 64, (n_slots + TN - 1) / TN, nz);
+  bwd_kernel<<<gb, 256, 0, c->stream>>>(c->X, c->n, ldx, G, ldg, n_slots, rpc, gradp);
+  c->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(c, std::string("simt_backward launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 }  // namespace skd

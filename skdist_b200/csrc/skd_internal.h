@@ -242,6 +242,40 @@ int forest_predict_device(Ctx* c, const float* dX, int64_t m, int ldx, int n_tre
 int ridge_fit_batch(Ctx* c, int B, const double* alpha, const int32_t* hold, int fit_intercept,
                     float* coef_out, int32_t* status_out);
 
+// ---- multinomial logistic regression (logreg_multi.cu / lbfgs_dev.cu) -------------------
+// One optimiser problem per candidate with K * (d + 1) variables, variable (k, j) at k * dp + j;
+// the evaluation sees K slots per active candidate (slot = a * K + k for active index a).
+struct MultiWork {
+  int32_t B = 0, K = 0, dp = 0;  // candidates of this solve, classes, d + 1
+  int32_t nz = 0;                // row chunks per evaluation (fixed by n alone)
+  int64_t rpc = 0;               // rows per chunk
+  int32_t ldg = 0;               // leading dimension of G
+  LbfgsScalars* sc = nullptr;    // [B]
+  double* vec = nullptr;         // [B x vec_stride]
+  size_t vec_stride = 0;
+  double* l2 = nullptr;          // [B]
+  double* inv_n = nullptr;       // [B]
+  int32_t* n_evals = nullptr;    // [B]
+  SlotMeta* cand = nullptr;      // [B] active candidates: col = candidate, fold = held-out fold (-1 none)
+  float* W = nullptr;            // [B*K x ldx] weights of the active slots, then bias [B*K]
+  float* G = nullptr;            // [n x ldg] raw predictions, overwritten by the pointwise gradients
+  double* lossp = nullptr;       // [nz x B]    indexed z * n_act + a
+  double* gsump = nullptr;       // [nz x B*K]  indexed z * n_slots + slot
+  float* gradp = nullptr;        // [nz x B*K x ldx]
+  int32_t* n_act = nullptr;      // device scalar: active candidates
+};
+int multi_lbfgs_init(Ctx* c, MultiWork& w, const int32_t* d_col_fold, double tol, int max_iter);
+int multi_lbfgs_enqueue(Ctx* c, MultiWork& w, int n_act_in, int fit_intercept, int32_t* hist);
+int multi_lbfgs_finish(Ctx* c, MultiWork& w, float* dcoef, int32_t* dniter, int32_t* dstatus, double* dloss);
+int multi_fit(Ctx* c, int B, int K, const double* C, const int32_t* col_fold, int fit_intercept, double tol,
+              int max_iter, float* coef_out, int32_t* n_iter_out, int32_t* status_out, double* loss_out,
+              int32_t* n_evals_out);
+int multi_score(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, int64_t* correct_out,
+                int64_t* count_out);
+// raw predictions / backward product of the fp32 CUDA-core path on arbitrary slot matrices (logreg_simt.cu)
+int simt_raw_prediction(Ctx* c, int n_slots, const float* dW, const float* dbias, float* dout, int ldd);
+int simt_backward(Ctx* c, const float* G, int ldg, int n_slots, int nz, int64_t rpc, float* gradp);
+
 // tensor-core evaluation (logreg_tc.cu)
 bool tc_supported(const Ctx* c);
 void tc_free(Ctx* c);

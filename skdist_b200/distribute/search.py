@@ -317,8 +317,116 @@ class _LogRegFamily:
         return np.vstack(preds)
 
 
+class _MultinomialFamily(_LogRegFamily):
+    """(candidate x fold) problems of multinomial L2 logistic regression: what LogisticRegression(lbfgs)
+    fits when the target has more than two classes (SK/linear_model/_logistic.py:523-547).  One
+    device optimiser problem per (candidate, fold) with n_classes x (d + 1) variables."""
+
+    name = "logreg_multinomial"
+
+    def __init__(self, estimator, candidate_params, X, y, scorers):
+        self.estimator = estimator
+        self.cands = [_check_logreg(q) for q in _merged_params(estimator, candidate_params)]
+        for p in candidate_params:
+            extra = set(p) - _LOGREG_SEARCHABLE
+            if extra:
+                raise NotImplementedError(
+                    "searching LogisticRegression over %s has no device path (searchable: %s)"
+                    % (sorted(extra), sorted(_LOGREG_SEARCHABLE)))
+        self.classes_ = np.unique(y)
+        self.n_classes = len(self.classes_)
+        self.y_class = np.searchsorted(self.classes_, y).astype(np.int32)
+        self.metrics = {}
+        for name, scorer in scorers.items():
+            if _classifier_metric(scorer) != "accuracy":
+                raise NotImplementedError(
+                    "scorer %r has no device path for a multiclass target (supported: accuracy)" % (scorer,))
+            self.metrics[name] = "accuracy"
+        self.needs_pred_pos = False
+
+    def stage(self, eng, X, fold, n_splits, x_staged=False):
+        if not x_staged:
+            eng.stage_x(X)
+        eng.stage_labels(self.y_class)
+        eng.stage_folds(fold, n_splits)
+
+    def run_columns(self, eng, cols, n_splits, return_train_score):
+        cols = np.asarray(cols, dtype=np.int64)
+        out = {
+            "n_test": np.zeros(len(cols), dtype=np.int64),
+            "fit_time": np.zeros(len(cols)), "score_time": np.zeros(len(cols)),
+            "n_iter": np.zeros(len(cols), dtype=np.int32), "status": np.zeros(len(cols), dtype=np.int32),
+        }
+        for name in self.metrics:
+            out["test_%s" % name] = np.zeros(len(cols))
+            if return_train_score:
+                out["train_%s" % name] = np.zeros(len(cols))
+        cand = cols // n_splits
+        fold = (cols % n_splits).astype(np.int32)
+        groups = defaultdict(list)
+        for i, c in enumerate(cand):
+            p = self.cands[c]
+            groups[(bool(p["fit_intercept"]), float(p["tol"]), int(p["max_iter"]))].append(i)
+        for (fi, tol, mi), idx in groups.items():
+            idx = np.asarray(idx)
+            C = np.array([self.cands[c]["C"] for c in cand[idx]], dtype=np.float64)
+            t0 = time.time()
+            res = eng.logreg_multinomial_fit_batch(C, fold[idx], self.n_classes, fit_intercept=fi, tol=tol,
+                                                   max_iter=mi)
+            t1 = time.time()
+            correct, count = eng.multinomial_score_batch(res["coef"], fold[idx])
+            t2 = time.time()
+            for name in self.metrics:
+                out["test_%s" % name][idx] = correct / np.maximum(count, 1)
+            out["n_test"][idx] = count
+            out["fit_time"][idx] = (t1 - t0) / len(idx)
+            out["score_time"][idx] = (t2 - t1) / len(idx)
+            out["n_iter"][idx] = res["n_iter"]
+            out["status"][idx] = res["status"]
+            if return_train_score:
+                correct, count = eng.multinomial_score_batch(res["coef"], (-3 - fold[idx]).astype(np.int32))
+                for name in self.metrics:
+                    out["train_%s" % name][idx] = correct / np.maximum(count, 1)
+        return out
+
+    def refit(self, eng, params, X_dtype, n_features):
+        p = _check_logreg(_resolve(self.estimator, params))
+        res = eng.logreg_multinomial_fit_batch(np.array([p["C"]]), np.array([-1], dtype=np.int32), self.n_classes,
+                                               fit_intercept=p["fit_intercept"], tol=p["tol"],
+                                               max_iter=p["max_iter"])
+        return self.make_estimator(params, res["coef"][0], res["n_iter"][0], X_dtype, n_features)
+
+    def make_estimator(self, params, coef_rows, n_iter, X_dtype, n_features):
+        """Fitted sklearn LogisticRegression with the multiclass attribute shapes
+        (SK/linear_model/_logistic.py:1561-1593): coef_ (K, d), intercept_ (K,), n_iter_ (1,)."""
+        est = _resolve(self.estimator, params)
+        dt = np.float64 if X_dtype == np.float64 else np.float32
+        est.coef_ = coef_rows[:, :n_features].astype(dt)
+        if est.fit_intercept:
+            est.intercept_ = coef_rows[:, n_features].astype(dt)
+        else:
+            est.intercept_ = np.zeros(self.n_classes, dtype=dt)
+        est.classes_ = self.classes_
+        est.n_iter_ = np.array([n_iter], dtype=np.int32)
+        est.n_features_in_ = n_features
+        return est
+
+    def fold_proba(self, eng, params, fold, n_splits):
+        from sklearn.utils.extmath import softmax
+        p = _check_logreg(_resolve(self.estimator, params))
+        f = np.arange(n_splits, dtype=np.int32)
+        res = eng.logreg_multinomial_fit_batch(np.full(n_splits, p["C"]), f, self.n_classes,
+                                               fit_intercept=p["fit_intercept"], tol=p["tol"],
+                                               max_iter=p["max_iter"])
+        K = self.n_classes
+        dec = eng.linear_decision(res["coef"].reshape(n_splits * K, -1))
+        return np.vstack([softmax(dec[fold == k, k * K:(k + 1) * K].astype(np.float64)) for k in range(n_splits)])
+
+
 def _pick_family(estimator, candidate_params, X, y, scorers):
     if type(estimator) is LogisticRegression:
+        if len(np.unique(y)) > 2:
+            return _MultinomialFamily(estimator, candidate_params, X, y, scorers)
         return _LogRegFamily(estimator, candidate_params, X, y, scorers)
     if type(estimator) is Ridge:
         from .ridge_family import _RidgeFamily
@@ -392,7 +500,11 @@ class DistBaseSearchCV(_ScParamMixin):
         keys = ["n_test", "fit_time", "score_time"] + ["test_%s" % m for m in metric_names]
         if self.return_train_score:
             keys += ["train_%s" % m for m in metric_names]
-        res = {k: parallel.all_gather_blocks(loc[k], n_cols, rank, world, deal_order) for k in keys}
+        # one collective for all per-column results (counts are exact in float64)
+        stacked = np.stack([np.asarray(loc[k], dtype=np.float64) for k in keys], axis=1)
+        gathered = parallel.all_gather_blocks(stacked, n_cols, rank, world, deal_order)
+        res = {k: gathered[:, i] for i, k in enumerate(keys)}
+        res["n_test"] = np.rint(res["n_test"]).astype(np.int64)
 
         error_score = self.error_score
         for m in metric_names:

@@ -153,6 +153,37 @@ class Engine:
                                                ptr(correct), ptr(count)), self._h)
         return correct, count
 
+    def logreg_multinomial_fit_batch(self, C, col_fold, n_classes, fit_intercept=True, tol=1e-4, max_iter=100):
+        """B multinomial lbfgs fits (class ids 0..n_classes-1 staged) sharing the staged X.
+        coef is [B, n_classes, d + 1] (weights, intercept last)."""
+        C = np.ascontiguousarray(C, dtype=np.float64)
+        B = C.shape[0]
+        col_fold = np.ascontiguousarray(col_fold, dtype=np.int32)
+        assert col_fold.shape == (B,)
+        K = int(n_classes)
+        coef = np.empty((B, K, self.d + 1), dtype=np.float32)
+        n_iter = np.empty(B, dtype=np.int32)
+        status = np.empty(B, dtype=np.int32)
+        loss = np.empty(B, dtype=np.float64)
+        n_evals = np.empty(B, dtype=np.int32)
+        secs = ctypes.c_double(0.0)
+        check(self._lib.skd_logreg_multinomial_fit_batch(
+            self._h, B, K, ptr(C), ptr(col_fold), int(bool(fit_intercept)), float(tol), int(max_iter), ptr(coef),
+            ptr(n_iter), ptr(status), ptr(loss), ptr(n_evals), ctypes.byref(secs)), self._h)
+        return {"coef": coef, "n_iter": n_iter, "status": status, "loss": loss,
+                "n_evals": n_evals, "gpu_seconds": secs.value}
+
+    def multinomial_score_batch(self, coef, col_fold):
+        coef = np.ascontiguousarray(coef, dtype=np.float32)
+        B, K = coef.shape[0], coef.shape[1]
+        assert coef.shape[2] == self.d + 1
+        col_fold = np.ascontiguousarray(col_fold, dtype=np.int32)
+        correct = np.empty(B, dtype=np.int64)
+        count = np.empty(B, dtype=np.int64)
+        check(self._lib.skd_multinomial_score_batch(self._h, B, K, ptr(coef), ptr(col_fold), ptr(correct),
+                                                    ptr(count)), self._h)
+        return correct, count
+
     def sgd_fit_batch(self, est, col_pos):
         """Fit one binary SGDClassifier per entry of col_pos (one-vs-rest label columns).
         `est` is the template SGDClassifier; host-side constants are derived exactly as

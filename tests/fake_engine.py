@@ -59,6 +59,32 @@ class FakeEngine:
         return {"coef": coef, "n_iter": n_iter, "status": np.ones(B, np.int32),
                 "loss": np.zeros(B), "n_evals": n_iter + 1, "gpu_seconds": 0.0}
 
+    def logreg_multinomial_fit_batch(self, C, col_fold, n_classes, fit_intercept=True, tol=1e-4, max_iter=100):
+        B = len(C)
+        self.calls.append(("fit_multinomial", B))
+        coef = np.zeros((B, n_classes, self.d + 1), np.float32)
+        n_iter = np.zeros(B, np.int32)
+        for j in range(B):
+            m = self._train_mask(int(col_fold[j]))
+            W, b, it = lo.fit_multinomial_lbfgs(self.X[m], self.y[m], n_classes, C=float(C[j]), tol=tol,
+                                                max_iter=max_iter, fit_intercept=fit_intercept)
+            coef[j, :, :self.d] = W
+            coef[j, :, self.d] = b
+            n_iter[j] = it
+        return {"coef": coef, "n_iter": n_iter, "status": np.ones(B, np.int32),
+                "loss": np.zeros(B), "n_evals": n_iter + 1, "gpu_seconds": 0.0}
+
+    def multinomial_score_batch(self, coef, col_fold):
+        B = coef.shape[0]
+        correct = np.zeros(B, np.int64)
+        count = np.zeros(B, np.int64)
+        for j in range(B):
+            m = self._rows(int(col_fold[j]))
+            z = self.X[m] @ coef[j, :, :self.d].T + coef[j, :, self.d]
+            correct[j] = np.sum(z.argmax(axis=1) == self.y[m])
+            count[j] = m.sum()
+        return correct, count
+
     def _rows(self, code):
         if code == -2:
             return np.ones(self.n, bool)

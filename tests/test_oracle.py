@@ -67,3 +67,25 @@ def test_oracle_task_equals_reference_task():
     b = search_oracle.search_cv(LogisticRegression(), cands, X, y, cv=3)
     np.testing.assert_array_equal(a["cv_results_"]["mean_test_score"], b["cv_results_"]["mean_test_score"])
     assert a["best_params_"] == b["best_params_"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_multinomial_restatement_is_sklearn(dtype):
+    """fit_multinomial_lbfgs vs LogisticRegression.fit on a multiclass target: bit-identical for
+    fp32 inputs (the device path's input type); fp64 differs only by numpy-vs-libm exp/log ulps."""
+    import warnings
+    from sklearn.linear_model import LogisticRegression
+    dg = load_digits()
+    X, y = (dg.data / 16).astype(dtype), dg.target
+    for C in (0.1, 10.0):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            est = LogisticRegression(C=C, max_iter=40).fit(X, y)
+        W, b, it = lo.fit_multinomial_lbfgs(X, y, 10, C=C, max_iter=40)
+        assert it == est.n_iter_[0]
+        if dtype == np.float32:
+            np.testing.assert_array_equal(W, est.coef_)
+            np.testing.assert_array_equal(b, est.intercept_)
+        else:
+            np.testing.assert_allclose(W, est.coef_, rtol=0, atol=1e-7)
+            np.testing.assert_allclose(b, est.intercept_, rtol=0, atol=1e-7)

@@ -211,3 +211,31 @@ def test_fast_fold_ids_equal_sklearn_splitters():
     np.testing.assert_array_equal(got, _fold_ids(list(GroupKFold(3).split(np.zeros((60, 1)), y, g)), 60))
     got, _ = _cv_fold_ids(StratifiedKFold(3, shuffle=True, random_state=0), np.zeros((60, 1)), y, None, 60)
     np.testing.assert_array_equal(got, _fold_ids(list(StratifiedKFold(3, shuffle=True, random_state=0).split(np.zeros((60, 1)), y)), 60))
+
+
+def test_config1_digits_multinomial_matches_oracle(fake_engine):
+    """BASELINE config 1: DistGridSearchCV(LogisticRegression) 4 params x 3 folds on sklearn digits
+    (10 classes -> multinomial lbfgs, SK/linear_model/_logistic.py:523-547).  The host logic on the
+    oracle-backed engine double must reproduce the reference's driver loop exactly (fp32 pixels:
+    the restated solve is bit-identical to scikit-learn's there)."""
+    from sklearn.datasets import load_digits
+    dg = load_digits()
+    X, y = (dg.data / 16).astype(np.float32), dg.target
+    grid = {"C": [0.01, 0.1, 1.0, 10.0]}
+    est = LogisticRegression(max_iter=30)
+    gs = DistGridSearchCV(est, grid, None, cv=3, return_train_score=True, preds=True).fit(X, y)
+    ora = search_oracle.search_cv(est, ParameterGrid(grid), X, y, cv=3, iid=True, return_train_score=True)
+    for k in ["split0_test_score", "split1_test_score", "split2_test_score", "mean_test_score",
+              "std_test_score", "rank_test_score", "mean_train_score"]:
+        np.testing.assert_array_equal(gs.cv_results_[k], ora["cv_results_"][k], err_msg=k)
+    assert gs.best_params_ == ora["best_params_"] and gs.best_index_ == ora["best_index_"]
+    be = gs.best_estimator_
+    assert be.coef_.shape == (10, 64) and be.intercept_.shape == (10,) and be.n_iter_.shape == (1,)
+    np.testing.assert_array_equal(be.coef_, ora["best_estimator_"].coef_)
+    np.testing.assert_array_equal(be.intercept_, ora["best_estimator_"].intercept_)
+    np.testing.assert_array_equal(gs.predict(X[:200]), ora["best_estimator_"].predict(X[:200]))
+    np.testing.assert_allclose(gs.predict_proba(X[:20]), ora["best_estimator_"].predict_proba(X[:20]), rtol=1e-4)
+    assert gs.get_preds().shape == (len(y), 10)
+    np.testing.assert_allclose(gs.get_preds().sum(1), 1.0, rtol=1e-6)
+    with pytest.raises(NotImplementedError):
+        DistGridSearchCV(est, grid, cv=3, scoring="f1_macro").fit(X, y)
