@@ -42,6 +42,10 @@ int skd_device_count(void);
 int skd_stage_x(skd_ctx* ctx, const float* X, int64_t n, int64_t d, int64_t ldx);
 /* Same, from a DEVICE pointer on ctx's device (e.g. the buffer an NCCL broadcast filled). */
 int skd_stage_x_device(skd_ctx* ctx, const float* dX, int64_t n, int64_t d, int64_t ldx);
+/* The staged matrix in HBM (device pointer owned by ctx, valid until the next staging call): the source
+ * of the NCCL broadcast that replicates X on the other ranks' GPUs over NVLink.
+ * ref: the sc.broadcast of search.py:414-421. */
+int skd_staged_x(skd_ctx* ctx, const float** dX, int64_t* n, int64_t* d, int64_t* ldx);
 
 /* Stage integer class ids (0..K-1), one per row.  Column j of a batch treats rows with
  * y_class == col_pos[j] as positive, the rest as negative.

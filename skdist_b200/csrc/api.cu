@@ -314,6 +314,17 @@ int skd_stage_x_device(skd_ctx* ctx, const float* dX, int64_t n, int64_t d, int6
   return stage_x_common(&ctx->c, dX, n, d, ldx, cudaMemcpyDeviceToDevice);
 }
 
+int skd_staged_x(skd_ctx* ctx, const float** dX, int64_t* n, int64_t* d, int64_t* ldx) {
+  if (!ctx) return fail(nullptr, "skd_staged_x: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X) return fail(c, "skd_staged_x: nothing staged");
+  if (dX) *dX = c->X;
+  if (n) *n = c->n;
+  if (d) *d = c->d;
+  if (ldx) *ldx = c->ldx;
+  return 0;
+}
+
 int skd_stage_labels(skd_ctx* ctx, const int32_t* y, int64_t n) {
   if (!ctx) return fail(nullptr, "skd_stage_labels: ctx is NULL");
   Ctx* c = &ctx->c;

@@ -480,7 +480,7 @@ class DistBaseSearchCV(_ScParamMixin):
         eng = get_engine()
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=1) as pool:
-            staged = pool.submit(eng.stage_x, X_arr)
+            staged = pool.submit(parallel.stage_x_replicated, eng, X_arr)
             try:
                 fold, _ = _cv_fold_ids(cv, X, y, groups, n_samples)
                 family = _pick_family(estimator, candidate_params, X_arr, y_arr, scorers)

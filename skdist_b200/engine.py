@@ -53,6 +53,14 @@ class Engine:
         check(self._lib.skd_stage_x_device(self._h, ctypes.c_void_p(int(dev_ptr)), n, d, ldx or d), self._h)
         self.n, self.d = n, d
 
+    def staged_x(self):
+        """(device pointer, n, d, ldx) of the staged matrix."""
+        p = ctypes.c_void_p()
+        n, d, ldx = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(self._lib.skd_staged_x(self._h, ctypes.byref(p), ctypes.byref(n), ctypes.byref(d),
+                                     ctypes.byref(ldx)), self._h)
+        return p.value, n.value, d.value, ldx.value
+
     def stage_labels(self, y_class):
         y = np.ascontiguousarray(y_class, dtype=np.int32)
         check(self._lib.skd_stage_labels(self._h, ptr(y), y.shape[0]), self._h)

@@ -124,3 +124,64 @@ def broadcast_array(arr, shape, dtype, src=0):
         t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), device=dev)
     dist.broadcast(t, src=src)
     return t.cpu().numpy()
+
+
+class _DeviceView:
+    """Zero-copy torch view of a raw device buffer (CUDA array interface)."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "strides": None, "version": 3}
+
+
+def stage_x_replicated(eng, X):
+    """Stage X in the HBM of every rank.  One process: a host-to-device copy.  Several ranks over
+    NCCL: rank 0 copies its host array to its GPU and the other ranks receive the staged matrix
+    over NVLink in ONE broadcast (the reference's sc.broadcast(X), search.py:414-421) -- N
+    concurrent host-to-device copies of the same matrix would share the host's memory bandwidth.
+    Every rank must call this with the same X (SPMD), as for the sharded fits themselves."""
+    rank, world, local = dist_info()
+    if world == 1:
+        return eng.stage_x(X)
+    import torch
+    import torch.distributed as dist
+    if dist.get_backend() != "nccl" or not hasattr(eng, "staged_x"):
+        return eng.stage_x(X)
+    # this may run on a worker thread (the search overlaps staging with the cv split): torch's
+    # current device is per thread, so name the rank's GPU explicitly
+    with torch.cuda.device(local):
+        return _stage_x_broadcast(eng, X, rank, torch.device("cuda", local))
+
+
+def _stage_x_broadcast(eng, X, rank, dev):
+    import torch
+    import torch.distributed as dist
+    X = np.asarray(X)
+    n, d = X.shape
+    # header: [status, ldx]; status != 0 -> rank 0 could not stage (e.g. NaN in X): everybody raises
+    head = torch.zeros(2, dtype=torch.int64, device=dev)
+    err = None
+    if rank == 0:
+        try:
+            eng.stage_x(X)
+            ptr, _, _, ldx = eng.staged_x()
+            head[1] = ldx
+        except Exception as e:      # noqa: BLE001 - re-raised below on every rank
+            err = e
+            head[0] = 1
+    dist.broadcast(head, src=0)
+    status, ldx = (int(v) for v in head.cpu().tolist())
+    if status:
+        if err is not None:
+            raise err
+        raise ValueError("rank 0 could not stage X (see its error)")
+    if rank == 0:
+        t = torch.as_tensor(_DeviceView(ptr, (n, ldx)), device=dev)
+        dist.broadcast(t, src=0)
+        torch.cuda.current_stream().synchronize()
+    else:
+        t = torch.empty((n, ldx), dtype=torch.float32, device=dev)
+        dist.broadcast(t, src=0)
+        torch.cuda.current_stream().synchronize()
+        eng.stage_x_device(t.data_ptr(), n, d, ldx)
+        del t

@@ -34,6 +34,22 @@ from sklearn.model_selection import RandomizedSearchCV
 rref = RandomizedSearchCV(Ridge(), {"alpha": list(np.logspace(-2, 2, 30))}, n_iter=11, random_state=0, cv=3).fit(Xr, yr)
 np.testing.assert_allclose(rs.cv_results_["mean_test_score"], rref.cv_results_["mean_test_score"], atol=2e-4)
 assert rs.best_params_ == rref.best_params_, "ridge"
+# multiclass target -> multinomial problems dealt over the ranks; X replicated by one NVLink broadcast
+from sklearn.datasets import load_digits
+from sklearn.model_selection import GridSearchCV
+dg = load_digits()
+Xd, yd = (dg.data / 16).astype(np.float32), dg.target
+gm = DistGridSearchCV(LogisticRegression(max_iter=300), {"C": [0.01, 0.1, 1.0, 10.0]}, None, cv=3).fit(Xd, yd)
+gk = GridSearchCV(LogisticRegression(max_iter=300), {"C": [0.01, 0.1, 1.0, 10.0]}, cv=3).fit(Xd, yd)
+np.testing.assert_allclose(gm.cv_results_["mean_test_score"], gk.cv_results_["mean_test_score"], atol=4.01 / len(yd))
+assert gk.cv_results_["mean_test_score"][gm.best_index_] >= gk.best_score_ - 4.01 / len(yd), "multinomial"
+# a matrix rank 0 cannot stage (NaN) must raise on every rank, not hang the broadcast
+Xbad = Xd.copy(); Xbad[3, 5] = np.nan
+try:
+    DistGridSearchCV(LogisticRegression(), {"C": [1.0]}, None, cv=3).fit(Xbad, yd)
+    raise SystemExit("NaN input was accepted")
+except ValueError:
+    pass
 gathered = [None] * world
 dist.all_gather_object(gathered, float(rs.cv_results_["mean_test_score"].sum()))
 assert len(set(gathered)) == 1, "ranks disagree"
