@@ -84,7 +84,7 @@ class DistFeatureEliminator(_ScParamMixin, ClassifierMixin, BaseEstimator):
         cv_splits = list(cv.split(X, y, groups))
         n_splits = len(cv_splits)
         fold = _fold_ids(cv_splits, n_samples)
-        eng.stage_x(X)
+        parallel.stage_x_replicated(eng, X)
         eng.stage_labels(ycls)
         eng.stage_folds(fold, n_splits)
         kw = dict(fit_intercept=p["fit_intercept"], tol=p["tol"], max_iter=p["max_iter"])

@@ -191,7 +191,7 @@ class _DistForestClassifier(_ScParamMixin):
 
         rank, world, _ = parallel.dist_info()
         eng = get_engine()
-        eng.stage_x(X)
+        parallel.stage_x_replicated(eng, X)
         eng.stage_labels(y_enc.astype(np.int32))
         eng.stage_folds(None, 0)
         mine = parallel.shard_indices(self.n_estimators, rank, world)

@@ -111,7 +111,7 @@ class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
 
         rank, world, _ = parallel.dist_info()
         eng = get_engine()
-        eng.stage_x(X_arr)
+        parallel.stage_x_replicated(eng, X_arr)
         eng.stage_labels(ycls)
         eng.stage_folds(None, 0)
         base = self.estimator
@@ -203,7 +203,7 @@ class DistOneVsOneClassifier(_ScParamMixin, OneVsOneClassifier):
         ycls = np.searchsorted(self.classes_, y_arr).astype(np.int32)
         rank, world, _ = parallel.dist_info()
         eng = get_engine()
-        eng.stage_x(X_arr)
+        parallel.stage_x_replicated(eng, X_arr)
         eng.stage_labels(ycls)
         eng.stage_folds(None, 0)
         mine = parallel.shard_indices(len(pairs), rank, world)

@@ -9,6 +9,7 @@ from collections import defaultdict
 
 import numpy as np
 
+from .. import parallel
 from .base import _clone, _merged_params
 
 _RIDGE_SEARCHABLE = {"alpha", "fit_intercept"}
@@ -81,7 +82,7 @@ class _RidgeFamily:
 
     def stage(self, eng, X, fold, n_splits, x_staged=False):
         if not x_staged:
-            eng.stage_x(X)
+            parallel.stage_x_replicated(eng, X)
         eng.stage_targets(self.y)
         eng.stage_folds(fold, n_splits)
         self.fold = fold

@@ -220,7 +220,7 @@ class _LogRegFamily:
 
     def stage(self, eng, X, fold, n_splits, x_staged=False):
         if not x_staged:
-            eng.stage_x(X)
+            parallel.stage_x_replicated(eng, X)
         eng.stage_labels(self.y_class)
         eng.stage_folds(fold, n_splits)
         self.pos_in_fold = np.bincount(np.asarray(fold)[self.y_class == 1], minlength=n_splits).astype(np.int64)
@@ -346,7 +346,7 @@ class _MultinomialFamily(_LogRegFamily):
 
     def stage(self, eng, X, fold, n_splits, x_staged=False):
         if not x_staged:
-            eng.stage_x(X)
+            parallel.stage_x_replicated(eng, X)
         eng.stage_labels(self.y_class)
         eng.stage_folds(fold, n_splits)
 
