@@ -122,6 +122,22 @@ int skd_logreg_multinomial_fit_batch(skd_ctx* ctx, int32_t B, int32_t n_classes,
 int skd_multinomial_score_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const float* coef,
                                 const int32_t* col_fold, int64_t* correct_out, int64_t* count_out);
 
+/* Confusion counts of the same classifiers on the same rows: confusion_out[(j * K + t) * K + p] = rows of
+ * true class t predicted as class p (K = n_classes).  Every count-based multiclass scorer (f1 / precision /
+ * recall with micro, macro or weighted averaging, balanced accuracy) is a function of this matrix.
+ * ref: replaces search.py:264 (_score -> scorer(estimator, X_test, y_test)) for those scorers
+ * (the reference's examples/search/hand_written_digits.py uses scoring="f1_weighted"). */
+int skd_multinomial_confusion_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const float* coef,
+                                    const int32_t* col_fold, int64_t* confusion_out);
+
+/* Area under the ROC curve of B linear binary classifiers on the rows selected by the fold codes of
+ * skd_linear_score_batch, as exact integer counts: u2_out[j] = 2 * U with U = #{(p, q): z_p > z_q} +
+ * 0.5 * #{z_p == z_q} over positive rows p (y_class == col_pos[j]) and negative rows q of the fp32 decision
+ * values z = x.w + b; auc = u2 / (2 * n_pos * n_neg) (== roc_auc_score(y, decision_function(X))).
+ * ref: replaces search.py:264 for scoring="roc_auc" (the reference's examples/search/basic_usage.py). */
+int skd_linear_auc_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_t* col_fold,
+                         const int32_t* col_pos, int64_t* u2_out, int64_t* n_pos_out, int64_t* n_neg_out);
+
 /* Batched Ridge: B independent (alpha, fold) columns from one pass over the staged X and the
  * staged real targets.  Column j trains on rows whose fold id != col_fold[j] (col_fold[j] < 0: all
  * rows).  coef_out[j*(d+1)+k] (k<d weights, k==d intercept); status_out[j] 1 = ok, 4 = matrix not

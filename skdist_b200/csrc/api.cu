@@ -868,22 +868,71 @@ int skd_logreg_multinomial_fit_batch(skd_ctx* ctx, int32_t B, int32_t n_classes,
   return rc;
 }
 
+static int multinomial_check(Ctx* c, const char* who, int32_t B, int32_t n_classes, const float* coef,
+                             const int32_t* col_fold) {
+  if (!c->X || !c->ycls) return fail(c, std::string(who) + ": stage X and labels first");
+  if (B <= 0 || n_classes < 2 || !coef || !col_fold) return fail(c, std::string(who) + ": bad arguments");
+  for (int j = 0; j < B; ++j) {
+    const int f = col_fold[j] >= 0 ? col_fold[j] : (col_fold[j] <= -3 ? -3 - col_fold[j] : -1);
+    if (col_fold[j] == -1) return fail(c, std::string(who) + ": col_fold -1 is not a scoring code");
+    if (f >= 0 && (!c->fold || f >= c->n_folds))
+      return fail(c, std::string(who) + ": col_fold refers to an unstaged fold");
+  }
+  return 0;
+}
+
+int skd_multinomial_confusion_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const float* coef,
+                                    const int32_t* col_fold, int64_t* confusion_out) {
+  if (!ctx) return fail(nullptr, "skd_multinomial_confusion_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (multinomial_check(c, "skd_multinomial_confusion_batch", B, n_classes, coef, col_fold)) return 1;
+  if (!confusion_out) return fail(c, "skd_multinomial_confusion_batch: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  Trace tr(c, "multinomial_confusion");
+  return multi_score(c, B, n_classes, coef, col_fold, confusion_out);
+}
+
 int skd_multinomial_score_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const float* coef,
                                 const int32_t* col_fold, int64_t* correct_out, int64_t* count_out) {
   if (!ctx) return fail(nullptr, "skd_multinomial_score_batch: ctx is NULL");
   Ctx* c = &ctx->c;
-  if (!c->X || !c->ycls) return fail(c, "skd_multinomial_score_batch: stage X and labels first");
-  if (B <= 0 || n_classes < 2 || !coef || !col_fold || !correct_out || !count_out)
-    return fail(c, "skd_multinomial_score_batch: bad arguments");
-  for (int j = 0; j < B; ++j) {
-    const int f = col_fold[j] >= 0 ? col_fold[j] : (col_fold[j] <= -3 ? -3 - col_fold[j] : -1);
-    if (col_fold[j] == -1) return fail(c, "skd_multinomial_score_batch: col_fold -1 is not a scoring code");
-    if (f >= 0 && (!c->fold || f >= c->n_folds))
-      return fail(c, "skd_multinomial_score_batch: col_fold refers to an unstaged fold");
-  }
+  if (multinomial_check(c, "skd_multinomial_score_batch", B, n_classes, coef, col_fold)) return 1;
+  if (!correct_out || !count_out) return fail(c, "skd_multinomial_score_batch: bad arguments");
   SKD_CUDA(c, cudaSetDevice(c->device));
   Trace tr(c, "multinomial_score");
-  return multi_score(c, B, n_classes, coef, col_fold, correct_out, count_out);
+  const size_t KK = (size_t)n_classes * n_classes;
+  std::vector<int64_t> conf((size_t)B * KK);
+  if (multi_score(c, B, n_classes, coef, col_fold, conf.data())) return 1;
+  for (int j = 0; j < B; ++j) {
+    int64_t tot = 0, diag = 0;
+    for (int a = 0; a < n_classes; ++a)
+      for (int b = 0; b < n_classes; ++b) {
+        const int64_t v = conf[(size_t)j * KK + (size_t)a * n_classes + b];
+        tot += v;
+        if (a == b) diag += v;
+      }
+    correct_out[j] = diag;
+    count_out[j] = tot;
+  }
+  return 0;
+}
+
+int skd_linear_auc_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_t* col_fold,
+                         const int32_t* col_pos, int64_t* u2_out, int64_t* n_pos_out, int64_t* n_neg_out) {
+  if (!ctx) return fail(nullptr, "skd_linear_auc_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || !c->ycls) return fail(c, "skd_linear_auc_batch: stage X and labels first");
+  if (B <= 0 || !coef || !col_fold || !col_pos || !u2_out || !n_pos_out || !n_neg_out)
+    return fail(c, "skd_linear_auc_batch: bad arguments");
+  for (int j = 0; j < B; ++j) {
+    const int f = col_fold[j] >= 0 ? col_fold[j] : (col_fold[j] <= -3 ? -3 - col_fold[j] : -1);
+    if (col_fold[j] == -1) return fail(c, "skd_linear_auc_batch: col_fold -1 is not a scoring code");
+    if (f >= 0 && (!c->fold || f >= c->n_folds))
+      return fail(c, "skd_linear_auc_batch: col_fold refers to an unstaged fold");
+  }
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  Trace tr(c, "auc");
+  return auc_batch(c, B, coef, col_fold, col_pos, u2_out, n_pos_out, n_neg_out);
 }
 
 int skd_ridge_fit_batch(skd_ctx* ctx, int32_t B, const double* alpha, const int32_t* col_fold,

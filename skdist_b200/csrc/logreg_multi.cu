@@ -90,43 +90,44 @@ mn_colsum_kernel(const float* __restrict__ G, int ldg, int64_t n, int64_t rpc, i
     gsump[(size_t)z * n_slots + s] = (part[0][tx] + part[1][tx]) + (part[2][tx] + part[3][tx]);
 }
 
-// accuracy counts of argmax_k z (first maximum, like numpy.argmax in LinearClassifierMixin.predict,
-// SK/linear_model/_base.py:351-374) on the rows selected by the candidate's fold code:
-// f >= 0 rows of fold f; -2 every row; -3-f rows NOT in fold f
+// confusion counts conf[b][true class][predicted class] of argmax_k z (first maximum, like
+// numpy.argmax in LinearClassifierMixin.predict, SK/linear_model/_base.py:351-374) on the rows
+// selected by the candidate's fold code: f >= 0 rows of fold f; -2 every row; -3-f rows NOT in fold f.
+// Every count-based multiclass metric (accuracy, precision / recall / f1 with any averaging,
+// balanced accuracy) is a function of this matrix.  SMEM = 1: the CTA counts in shared memory first.
+template <int SMEM>
 __global__ void __launch_bounds__(256)
-mn_argmax_count_kernel(const float* __restrict__ Z, int ldz, int64_t n, int64_t rpc, int K, int B,
-                       const int32_t* __restrict__ code, const int32_t* __restrict__ ycls,
-                       const int8_t* __restrict__ fold, unsigned long long* __restrict__ correct,
-                       unsigned long long* __restrict__ count) {
-  __shared__ unsigned long long red[2][8];
+mn_confusion_kernel(const float* __restrict__ Z, int ldz, int64_t n, int64_t rpc, int K, int B,
+                    const int32_t* __restrict__ code, const int32_t* __restrict__ ycls,
+                    const int8_t* __restrict__ fold, unsigned long long* __restrict__ conf) {
+  extern __shared__ unsigned int sconf[];
   const int b = blockIdx.x, z = blockIdx.y;
   const int cd = code[b];
+  const int KK = K * K;
+  if (SMEM) {
+    for (int i = threadIdx.x; i < KK; i += 256) sconf[i] = 0u;
+    __syncthreads();
+  }
+  unsigned long long* out = conf + (size_t)b * KK;
   const int64_t row_begin = (int64_t)z * rpc;
   int64_t row_end = row_begin + rpc;
   if (row_end > n) row_end = n;
-  unsigned long long nc = 0, nn = 0;
   for (int64_t r = row_begin + threadIdx.x; r < row_end; r += 256) {
     const int fd = fold ? (int)fold[r] : -1;
     const bool test = cd == -2 || (cd >= 0 && fd == cd) || (cd <= -3 && fd != (-3 - cd));
-    if (!test) continue;
+    const int y = ycls[r];
+    if (!test || y < 0 || y >= K) continue;
     const float* zr = Z + r * ldz + (size_t)b * K;
     int best = 0;
     float mx = zr[0];
     for (int k = 1; k < K; ++k) { const float v = zr[k]; if (v > mx) { mx = v; best = k; } }
-    nc += (best == ycls[r]) ? 1 : 0;
-    nn += 1;
+    if (SMEM) atomicAdd(&sconf[y * K + best], 1u);
+    else atomicAdd(&out[y * K + best], 1ull);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    nc += __shfl_xor_sync(0xffffffffu, nc, o);
-    nn += __shfl_xor_sync(0xffffffffu, nn, o);
-  }
-  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = nc; red[1][threadIdx.x >> 5] = nn; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long a = 0, t = 0;
-    for (int i = 0; i < 8; ++i) { a += red[0][i]; t += red[1][i]; }
-    if (t) { atomicAdd(&correct[b], a); atomicAdd(&count[b], t); }
+  if (SMEM) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < KK; i += 256)
+      if (sconf[i]) atomicAdd(&out[i], (unsigned long long)sconf[i]);
   }
 }
 
@@ -236,10 +237,10 @@ int multi_fit(Ctx* c, int B, int K, const double* C, const int32_t* col_fold, in
   return 0;
 }
 
-int multi_score(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, int64_t* correct_out,
-                int64_t* count_out) {
+int multi_score(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, int64_t* conf_out) {
   const int64_t n = c->n, d = c->d, ldx = c->ldx;
   const int dp = (int)d + 1;
+  const size_t KK = (size_t)K * K;
   int nz;
   int64_t rpc;
   multi_chunks(n, &nz, &rpc);
@@ -256,27 +257,28 @@ int multi_score(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold
     }
     float *dW, *Z;
     int32_t* dcode;
-    unsigned long long *dcorrect, *dcount;
+    unsigned long long* dconf;
     const int ldz = (int)slots;
     SKD_CUDA(c, sx.alloc(&dW, h.size()));
     SKD_CUDA(c, sx.alloc(&Z, (size_t)n * ldz));
     SKD_CUDA(c, sx.alloc(&dcode, (size_t)Bb));
-    SKD_CUDA(c, sx.alloc(&dcorrect, (size_t)Bb));
-    SKD_CUDA(c, sx.alloc(&dcount, (size_t)Bb));
+    SKD_CUDA(c, sx.alloc(&dconf, (size_t)Bb * KK));
     SKD_CUDA(c, cudaMemcpyAsync(dW, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     SKD_CUDA(c, cudaMemcpyAsync(dcode, col_fold + b0, Bb * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
-    SKD_CUDA(c, cudaMemsetAsync(dcorrect, 0, Bb * sizeof(unsigned long long), c->stream));
-    SKD_CUDA(c, cudaMemsetAsync(dcount, 0, Bb * sizeof(unsigned long long), c->stream));
+    SKD_CUDA(c, cudaMemsetAsync(dconf, 0, (size_t)Bb * KK * sizeof(unsigned long long), c->stream));
     c->h2d += (int64_t)h.size() * 4;
     if (simt_raw_prediction(c, (int)slots, dW, dW + slots * ldx, Z, ldz)) return 1;
-    mn_argmax_count_kernel<<<dim3(Bb, nz), 256, 0, c->stream>>>(Z, ldz, n, rpc, K, Bb, dcode, c->ycls, c->fold,
-                                                               dcorrect, dcount);
+    const size_t smem = KK * sizeof(unsigned int);
+    if (smem <= 48 * 1024)
+      mn_confusion_kernel<1><<<dim3(Bb, nz), 256, smem, c->stream>>>(Z, ldz, n, rpc, K, Bb, dcode, c->ycls, c->fold, dconf);
+    else
+      mn_confusion_kernel<0><<<dim3(Bb, nz), 256, 0, c->stream>>>(Z, ldz, n, rpc, K, Bb, dcode, c->ycls, c->fold, dconf);
     c->launches += 1;
     SKD_CUDA(c, cudaGetLastError());
-    SKD_CUDA(c, cudaMemcpyAsync(correct_out + b0, dcorrect, Bb * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    SKD_CUDA(c, cudaMemcpyAsync(count_out + b0, dcount, Bb * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(conf_out + (size_t)b0 * KK, dconf, (size_t)Bb * KK * sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, c->stream));
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));   // h is read by the async copy until here
-    c->d2h += (int64_t)Bb * 16;
+    c->d2h += (int64_t)Bb * KK * 8;
   }
   return 0;
 }

@@ -270,11 +270,15 @@ int multi_lbfgs_finish(Ctx* c, MultiWork& w, float* dcoef, int32_t* dniter, int3
 int multi_fit(Ctx* c, int B, int K, const double* C, const int32_t* col_fold, int fit_intercept, double tol,
               int max_iter, float* coef_out, int32_t* n_iter_out, int32_t* status_out, double* loss_out,
               int32_t* n_evals_out);
-int multi_score(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, int64_t* correct_out,
-                int64_t* count_out);
+int multi_score(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, int64_t* conf_out);
 // raw predictions / backward product of the fp32 CUDA-core path on arbitrary slot matrices (logreg_simt.cu)
 int simt_raw_prediction(Ctx* c, int n_slots, const float* dW, const float* dbias, float* dout, int ldd);
 int simt_backward(Ctx* c, const float* G, int ldg, int n_slots, int nz, int64_t rpc, float* gradp);
+
+// ROC-AUC counts of linear binary classifiers (auc.cu): 2U, n_pos, n_neg per column
+int auc_batch(Ctx* c, int B, const float* coef, const int32_t* col_fold, const int32_t* col_pos, int64_t* u2_out,
+              int64_t* n_pos_out, int64_t* n_neg_out);
+int simt_decision(Ctx* c, int B, const float* dW, float* dout);
 
 // tensor-core evaluation (logreg_tc.cu)
 bool tc_supported(const Ctx* c);

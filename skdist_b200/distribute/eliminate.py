@@ -13,7 +13,7 @@ columns (csrc/lbfgs_dev.cu gather_fg).  No column-dropped copies of X are made; 
 zero-padded coefficient rows on the full X.
 
 Base estimator with a device path: binary ``LogisticRegression(solver="lbfgs")`` with
-scoring=None / "accuracy".  Anything else raises NotImplementedError (no CPU fallback).
+scoring=None / "accuracy" / "roc_auc".  Anything else raises NotImplementedError (no CPU fallback).
 """
 import numpy as np
 from sklearn.base import BaseEstimator, ClassifierMixin, is_classifier
@@ -25,7 +25,7 @@ from sklearn.utils.validation import check_is_fitted
 from .. import parallel
 from ..engine import get_engine
 from .base import _clone, _parse_partitions, _ScParamMixin
-from .search import _check_logreg, _fold_ids
+from .search import _check_logreg, _count_metric, _fold_ids
 from .utils import _check_multimetric_scoring
 
 __all__ = ["DistFeatureEliminator"]
@@ -62,11 +62,9 @@ class DistFeatureEliminator(_ScParamMixin, ClassifierMixin, BaseEstimator):
                 "  (No CPU fallback by design.)" % type(self.estimator).__name__)
         p = _check_logreg(_clone(self.estimator))
         scorers, _ = _check_multimetric_scoring(self.estimator, scoring=self.scoring)
-        sname = type(scorers["score"]).__name__
-        if sname != "_PassthroughScorer":
-            f = getattr(scorers["score"], "_score_func", None)
-            if getattr(f, "__name__", "") != "accuracy_score":
-                raise NotImplementedError("only scoring=None / 'accuracy' is scored on the device")
+        metric = _count_metric(scorers["score"])
+        if metric is None or metric[0] not in ("accuracy", "roc_auc"):
+            raise NotImplementedError("scoring=None / 'accuracy' / 'roc_auc' are scored on the device")
         classes = np.unique(y)
         if len(classes) != 2:
             raise NotImplementedError("the device path is binary (got %d classes)" % len(classes))
@@ -114,8 +112,11 @@ class DistFeatureEliminator(_ScParamMixin, ClassifierMixin, BaseEstimator):
         if len(mine):
             eng.stage_column_masks(masks)
             res = eng.logreg_fit_batch(np.full(len(mine), p["C"]), f_cols, pos, **kw)
-            correct, count = eng.linear_score_batch(res["coef"], f_cols, pos)
-            loc = correct / np.maximum(count, 1)
+            if metric[0] == "roc_auc":       # the reference's examples/eliminate/basic_usage.py scorer
+                loc, _ = eng.linear_auc_batch(res["coef"], f_cols, pos)
+            else:
+                correct, count = eng.linear_score_batch(res["coef"], f_cols, pos)
+                loc = correct / np.maximum(count, 1)
         else:
             loc = np.zeros(0)
         scores = np.asarray(parallel.all_gather_columns(loc, n_cols, rank, world), dtype=np.float64)

@@ -144,20 +144,67 @@ def _check_logreg(est):
     return p
 
 
-def _classifier_metric(scorer):
-    """Name of the count-based metric a scikit-learn scorer computes, or None.  All of them are
-    functions of the per-column confusion counts the scoring kernels deliver."""
+_COUNT_METRICS = {"accuracy_score": "accuracy", "f1_score": "f1", "precision_score": "precision",
+                  "recall_score": "recall", "balanced_accuracy_score": "balanced_accuracy"}
+
+
+def _count_metric(scorer):
+    """(kind, average) of the count-based metric a scikit-learn scorer computes on predict(), or None.
+    average is None for accuracy / balanced accuracy, else "binary" / "micro" / "macro" / "weighted".
+    All of them are functions of the confusion counts the scoring kernels deliver."""
     if type(scorer).__name__ == "_PassthroughScorer":       # estimator.score == accuracy (ref utils.py:75-143)
-        return "accuracy"
+        return "accuracy", None
     f = getattr(scorer, "_score_func", None)
-    name = getattr(f, "__name__", "")
+    kind = _COUNT_METRICS.get(getattr(f, "__name__", ""))
     kwargs = dict(getattr(scorer, "_kwargs", {}) or {})
-    if getattr(scorer, "_sign", 1) != 1:
+    if getattr(f, "__name__", "") == "roc_auc_score" and not kwargs and getattr(scorer, "_sign", 1) == 1:
+        # scoring="roc_auc": roc_auc_score(y, decision_function(X)) -- exact pair counts on the device (csrc/auc.cu)
+        return "roc_auc", None
+    if kind is None or getattr(scorer, "_sign", 1) != 1:
         return None
-    if kwargs.pop("average", "binary") != "binary" or kwargs.pop("pos_label", 1) != 1 or kwargs:
+    if kind in ("accuracy", "balanced_accuracy"):
+        return None if kwargs else (kind, None)
+    average = kwargs.pop("average", "binary")
+    pos_label = kwargs.pop("pos_label", 1)      # the named averaged scorers ("f1_weighted", ...) carry pos_label=None
+    if kwargs or average not in ("binary", "micro", "macro", "weighted"):
         return None
-    return {"accuracy_score": "accuracy", "f1_score": "f1", "precision_score": "precision",
-            "recall_score": "recall", "balanced_accuracy_score": "balanced_accuracy"}.get(name)
+    if pos_label != 1 and not (average != "binary" and pos_label is None):
+        return None
+    return kind, average
+
+
+def _metric_from_confusion(kind, average, conf):
+    """scikit-learn's formulas on confusion matrices conf[..., true, predicted]
+    (SK/metrics/_classification.py: accuracy_score, balanced_accuracy_score,
+    precision_recall_fscore_support with zero_division -> 0.0; labels = classes present in y_true or
+    y_pred, as unique_labels gives them)."""
+    conf = np.asarray(conf, dtype=np.float64)
+    tp = np.diagonal(conf, axis1=-2, axis2=-1)
+    support = conf.sum(axis=-1)          # rows per true class
+    pred = conf.sum(axis=-2)             # rows per predicted class
+    total = support.sum(axis=-1)
+
+    def div(a, b):
+        return np.divide(a, b, out=np.zeros(np.broadcast(a, b).shape), where=b != 0)
+    if kind == "accuracy" or average == "micro":
+        return div(tp.sum(axis=-1), total)
+    if kind == "balanced_accuracy":      # mean recall over the classes that occur in y_true
+        has = support > 0
+        return div((div(tp, support) * has).sum(axis=-1), has.sum(axis=-1).astype(np.float64))
+    if kind == "precision":
+        per_class = div(tp, pred)
+    elif kind == "recall":
+        per_class = div(tp, support)
+    elif kind == "f1":
+        per_class = div(2.0 * tp, support + pred)
+    else:
+        raise ValueError(kind)
+    if average == "macro":
+        present = (support + pred) > 0
+        return div((per_class * present).sum(axis=-1), present.sum(axis=-1).astype(np.float64))
+    if average == "weighted":
+        return div((per_class * support).sum(axis=-1), total)
+    raise ValueError(average)
 
 
 def _metric_from_counts(kind, correct, count, pred_pos, actual_pos):
@@ -210,13 +257,14 @@ class _LogRegFamily:
         # accuracy on predict); scoring=None -> _PassthroughScorer -> estimator.score == accuracy
         self.metrics = {}
         for name, scorer in scorers.items():
-            kind = _classifier_metric(scorer)
-            if kind is None:
+            m = _count_metric(scorer)
+            if m is None:
                 raise NotImplementedError(
-                    "scorer %r has no device path for classifiers (supported: accuracy, precision, recall, "
-                    "f1, balanced_accuracy with default arguments)" % (scorer,))
-            self.metrics[name] = kind
-        self.needs_pred_pos = any(k != "accuracy" for k in self.metrics.values())
+                    "scorer %r has no device path for classifiers (supported: accuracy, balanced_accuracy, "
+                    "precision / recall / f1 with average binary, micro, macro or weighted)" % (scorer,))
+            # binary averaging keeps the plain name; averaged variants carry (kind, average)
+            self.metrics[name] = m[0] if m[1] in (None, "binary") else m
+        self.needs_pred_pos = any(k not in ("accuracy", "roc_auc") for k in self.metrics.values())
 
     def stage(self, eng, X, fold, n_splits, x_staged=False):
         if not x_staged:
@@ -234,8 +282,18 @@ class _LogRegFamily:
             # a positive class id that matches no row makes "correct" count the predicted negatives
             neg_correct, _ = eng.linear_score_batch(coef, codes, np.full(len(pos), -7, dtype=np.int32))
             pred_pos = count - neg_correct
-        return {name: _metric_from_counts(kind, correct, count, pred_pos, actual_pos)
-                for name, kind in self.metrics.items()}, count
+        out = {}
+        for name, kind in self.metrics.items():
+            if kind == "roc_auc":
+                out[name], _ = eng.linear_auc_batch(coef, codes, pos)
+            elif isinstance(kind, tuple):      # micro / macro / weighted: 2 x 2 confusion [true, predicted]
+                tp = (pred_pos + actual_pos + correct - count) / 2.0
+                fp, fn = pred_pos - tp, actual_pos - tp
+                conf = np.stack([np.stack([count - tp - fp - fn, fp], -1), np.stack([fn, tp], -1)], -2)
+                out[name] = _metric_from_confusion(kind[0], kind[1], conf)
+            else:
+                out[name] = _metric_from_counts(kind, correct, count, pred_pos, actual_pos)
+        return out, count
 
     def run_columns(self, eng, cols, n_splits, return_train_score):
         """Fit + score the given global column ids (col = cand * n_splits + fold).
@@ -338,10 +396,12 @@ class _MultinomialFamily(_LogRegFamily):
         self.y_class = np.searchsorted(self.classes_, y).astype(np.int32)
         self.metrics = {}
         for name, scorer in scorers.items():
-            if _classifier_metric(scorer) != "accuracy":
+            m = _count_metric(scorer)
+            if m is None or m[1] == "binary" or m[0] == "roc_auc":    # scikit-learn itself rejects these on a multiclass target
                 raise NotImplementedError(
-                    "scorer %r has no device path for a multiclass target (supported: accuracy)" % (scorer,))
-            self.metrics[name] = "accuracy"
+                    "scorer %r has no device path for a multiclass target (supported: accuracy, "
+                    "balanced_accuracy, precision / recall / f1 with average micro, macro or weighted)" % (scorer,))
+            self.metrics[name] = m
         self.needs_pred_pos = False
 
     def stage(self, eng, X, fold, n_splits, x_staged=False):
@@ -374,19 +434,19 @@ class _MultinomialFamily(_LogRegFamily):
             res = eng.logreg_multinomial_fit_batch(C, fold[idx], self.n_classes, fit_intercept=fi, tol=tol,
                                                    max_iter=mi)
             t1 = time.time()
-            correct, count = eng.multinomial_score_batch(res["coef"], fold[idx])
+            conf = eng.multinomial_confusion_batch(res["coef"], fold[idx])
             t2 = time.time()
-            for name in self.metrics:
-                out["test_%s" % name][idx] = correct / np.maximum(count, 1)
-            out["n_test"][idx] = count
+            for name, (kind, average) in self.metrics.items():
+                out["test_%s" % name][idx] = _metric_from_confusion(kind, average, conf)
+            out["n_test"][idx] = conf.sum(axis=(1, 2))
             out["fit_time"][idx] = (t1 - t0) / len(idx)
             out["score_time"][idx] = (t2 - t1) / len(idx)
             out["n_iter"][idx] = res["n_iter"]
             out["status"][idx] = res["status"]
             if return_train_score:
-                correct, count = eng.multinomial_score_batch(res["coef"], (-3 - fold[idx]).astype(np.int32))
-                for name in self.metrics:
-                    out["train_%s" % name][idx] = correct / np.maximum(count, 1)
+                conf = eng.multinomial_confusion_batch(res["coef"], (-3 - fold[idx]).astype(np.int32))
+                for name, (kind, average) in self.metrics.items():
+                    out["train_%s" % name][idx] = _metric_from_confusion(kind, average, conf)
         return out
 
     def refit(self, eng, params, X_dtype, n_features):

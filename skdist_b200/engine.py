@@ -192,6 +192,32 @@ class Engine:
                                                     ptr(count)), self._h)
         return correct, count
 
+    def multinomial_confusion_batch(self, coef, col_fold):
+        """[B, K, K] confusion counts (true class, predicted class) on the rows selected by the fold codes."""
+        coef = np.ascontiguousarray(coef, dtype=np.float32)
+        B, K = coef.shape[0], coef.shape[1]
+        assert coef.shape[2] == self.d + 1
+        col_fold = np.ascontiguousarray(col_fold, dtype=np.int32)
+        conf = np.empty((B, K, K), dtype=np.int64)
+        check(self._lib.skd_multinomial_confusion_batch(self._h, B, K, ptr(coef), ptr(col_fold), ptr(conf)), self._h)
+        return conf
+
+    def linear_auc_batch(self, coef, col_fold, col_pos):
+        """ROC-AUC of B linear binary classifiers on the rows selected by the fold codes (NaN where a
+        class is missing), from exact integer pair counts."""
+        coef = np.ascontiguousarray(coef, dtype=np.float32)
+        B = coef.shape[0]
+        assert coef.shape[1] == self.d + 1
+        col_fold = np.ascontiguousarray(col_fold, dtype=np.int32)
+        col_pos = np.ascontiguousarray(col_pos, dtype=np.int32)
+        u2 = np.empty(B, dtype=np.int64)
+        n_pos = np.empty(B, dtype=np.int64)
+        n_neg = np.empty(B, dtype=np.int64)
+        check(self._lib.skd_linear_auc_batch(self._h, B, ptr(coef), ptr(col_fold), ptr(col_pos), ptr(u2), ptr(n_pos),
+                                             ptr(n_neg)), self._h)
+        den = 2.0 * n_pos.astype(np.float64) * n_neg.astype(np.float64)
+        return np.divide(u2.astype(np.float64), den, out=np.full(B, np.nan), where=den > 0), n_pos + n_neg
+
     def sgd_fit_batch(self, est, col_pos):
         """Fit one binary SGDClassifier per entry of col_pos (one-vs-rest label columns).
         `est` is the template SGDClassifier; host-side constants are derived exactly as

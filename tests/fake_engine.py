@@ -85,6 +85,29 @@ class FakeEngine:
             count[j] = m.sum()
         return correct, count
 
+    def multinomial_confusion_batch(self, coef, col_fold):
+        B, K = coef.shape[0], coef.shape[1]
+        conf = np.zeros((B, K, K), np.int64)
+        for j in range(B):
+            m = self._rows(int(col_fold[j]))
+            z = self.X[m] @ coef[j, :, :self.d].T + coef[j, :, self.d]
+            np.add.at(conf[j], (self.y[m], z.argmax(axis=1)), 1)
+        return conf
+
+    def linear_auc_batch(self, coef, col_fold, col_pos):
+        from sklearn.metrics import roc_auc_score
+        B = coef.shape[0]
+        auc = np.full(B, np.nan)
+        count = np.zeros(B, np.int64)
+        for j in range(B):
+            m = self._rows(int(col_fold[j]))
+            z = self.X[m] @ coef[j, :self.d] + coef[j, self.d]
+            yb = self.y[m] == col_pos[j]
+            count[j] = m.sum()
+            if 0 < yb.sum() < len(yb):
+                auc[j] = roc_auc_score(yb, z)
+        return auc, count
+
     def _rows(self, code):
         if code == -2:
             return np.ones(self.n, bool)

@@ -76,3 +76,26 @@ def test_eliminator_restatement_and_errors(fake_engine):
     from sklearn.svm import LinearSVC
     with pytest.raises(NotImplementedError):
         DistFeatureEliminator(LinearSVC()).fit(X, y)
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_eliminator_roc_auc(fake_engine):
+    """scoring="roc_auc" as in the reference's examples/eliminate/basic_usage.py."""
+    from sklearn.metrics import roc_auc_score
+    from sklearn.model_selection import StratifiedKFold
+    X, y = _data()
+    fe = DistFeatureEliminator(LogisticRegression(), None, step=4, cv=3, min_features_to_select=4,
+                               scoring="roc_auc").fit(X, y)
+    d = X.shape[1]
+    ranks = np.argsort(LogisticRegression().fit(X, y).coef_[0].astype(np.float64) ** 2)[: d - 4]
+    sets, k = [np.array([], int)], 0
+    while k < d - 4:
+        k += 4
+        sets.append(ranks[:k])
+    exp = []
+    for rm in sets:
+        keep = np.setdiff1d(np.arange(d), rm)
+        exp.append(np.mean([roc_auc_score(y[te], LogisticRegression().fit(X[tr][:, keep], y[tr])
+                                          .decision_function(X[te][:, keep]))
+                            for tr, te in StratifiedKFold(3).split(X, y)]))
+    np.testing.assert_allclose(fe.scores_, exp, atol=1e-6)

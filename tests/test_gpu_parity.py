@@ -576,6 +576,13 @@ def test_multinomial_scores_are_exact_for_given_coefficients(eng):
         m = np.ones(len(y), bool) if cd == -2 else (fold == cd if cd >= 0 else fold != (-3 - cd))
         assert count[j] == m.sum()
         assert correct[j] == np.sum(dec[m, j * 10:(j + 1) * 10].argmax(1) == y[m])
+    # the confusion counts behind every averaged precision / recall / f1 scorer
+    conf = eng.multinomial_confusion_batch(coef, codes)
+    for j, cd in enumerate(codes):
+        m = np.ones(len(y), bool) if cd == -2 else (fold == cd if cd >= 0 else fold != (-3 - cd))
+        want = np.zeros((10, 10), np.int64)
+        np.add.at(want, (y[m], dec[m, j * 10:(j + 1) * 10].argmax(1)), 1)
+        np.testing.assert_array_equal(conf[j], want)
 
 
 def test_config1_digits_grid_search(eng):
@@ -599,6 +606,10 @@ def test_config1_digits_grid_search(eng):
     assert gs.best_estimator_.coef_.shape == (10, 64)
     assert np.mean(gs.predict(X) == sk.predict(X)) >= 0.998
     np.testing.assert_allclose(gs.predict_proba(X[:50]), sk.predict_proba(X[:50]), atol=3e-2)
+    # the scorer of the reference's examples/search/hand_written_digits.py
+    gf = DistGridSearchCV(est, grid, None, cv=3, scoring="f1_weighted").fit(X, y)
+    sf = GridSearchCV(est, grid, cv=3, scoring="f1_weighted").fit(X, y)
+    np.testing.assert_allclose(gf.cv_results_["mean_test_score"], sf.cv_results_["mean_test_score"], rtol=0, atol=3e-3)
     # the configuration as BASELINE states it (raw 0..16 pixels, float64): lbfgs stops on max_iter with
     # path-dependent iterates, so agreement is at the level of a few test rows per fold
     Xr = dg.data
@@ -609,3 +620,49 @@ def test_config1_digits_grid_search(eng):
     assert np.abs(gr.cv_results_["mean_test_score"] - pinned).max() <= 6.0 / 599
     assert gr.best_params_ == {"C": 0.01}
     assert gr.cv_results_["split0_test_score"].shape == (4,) and gr.n_splits_ == 3
+
+
+def test_roc_auc_counts_are_exact(eng):
+    """skd_linear_auc_batch vs roc_auc_score on the device's own decision values (integer pair counts,
+    ties included: every row is duplicated, so each decision value occurs at least twice)."""
+    from scipy.stats import rankdata
+    from sklearn.metrics import roc_auc_score
+    X0, y0 = make_g1_classification(3000, 12, seed=31)
+    X = np.concatenate([X0, X0[:1500]]).astype(np.float32)
+    y = np.concatenate([y0, 1 - y0[:1500]]).astype(np.int32)        # tied scores with opposite labels
+    fold = (np.arange(len(y)) % 4).astype(np.int8)
+    eng.stage_x(X); eng.stage_labels(y); eng.stage_folds(fold, 4)
+    rng = np.random.default_rng(7)
+    B = 20
+    coef = rng.standard_normal((B, 13)).astype(np.float32)
+    coef[3] = 0                                                     # all scores tied -> auc 0.5
+    codes = np.array([0, 1, 2, 3, -2, -3, -4, -5, -6, 0] * 2, np.int32)
+    pos = np.ones(B, np.int32)
+    pos[7] = 5                                                      # no positive row -> undefined
+    auc, count = eng.linear_auc_batch(coef, codes, pos)
+    dec = eng.linear_decision(coef)                                 # B > 16: the same fp32 kernel as the scorer
+    for j in range(B):
+        cd = codes[j]
+        m = np.ones(len(y), bool) if cd == -2 else (fold == cd if cd >= 0 else fold != (-3 - cd))
+        assert count[j] == m.sum()
+        yb = y[m] == pos[j]
+        if yb.sum() == 0:
+            assert np.isnan(auc[j])
+            continue
+        r = rankdata(dec[m, j].astype(np.float64))
+        u2 = 2.0 * (r[yb].sum() - yb.sum() * (yb.sum() + 1) / 2.0)
+        assert auc[j] == u2 / (2.0 * yb.sum() * (~yb).sum()), j
+        np.testing.assert_allclose(auc[j], roc_auc_score(yb, dec[m, j]), rtol=1e-12)
+    assert auc[3] == 0.5
+
+
+def test_roc_auc_grid_search(eng):
+    """scoring="roc_auc" through the public API (the reference's examples/search/basic_usage.py)."""
+    from sklearn.model_selection import GridSearchCV
+    from skdist.distribute.search import DistGridSearchCV
+    X, y = make_g1_classification(6000, 20, seed=33)
+    grid = {"C": [0.001, 0.1, 10.0]}
+    gs = DistGridSearchCV(LogisticRegression(), grid, None, cv=4, scoring="roc_auc").fit(X, y)
+    sk = GridSearchCV(LogisticRegression(), grid, cv=4, scoring="roc_auc").fit(X, y)
+    np.testing.assert_allclose(gs.cv_results_["mean_test_score"], sk.cv_results_["mean_test_score"], rtol=0, atol=2e-5)
+    assert gs.best_params_ == sk.best_params_

@@ -178,7 +178,7 @@ def test_multimetric_scoring_matches_sklearn(fake_engine):
     nr = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring=scoring, refit=False).fit(X, y)
     assert not hasattr(nr, "best_index_")
     with pytest.raises(NotImplementedError):
-        DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring="roc_auc").fit(X, y)
+        DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring="neg_log_loss").fit(X, y)
     Xr, yr = make_g1_regression(500, 5, seed=2)
     rs = ["r2", "neg_mean_squared_error", "neg_root_mean_squared_error"]
     ours = DistGridSearchCV(Ridge(), {"alpha": [0.1, 10.0]}, None, cv=3, scoring=rs, refit="r2").fit(Xr, yr)
@@ -238,4 +238,72 @@ def test_config1_digits_multinomial_matches_oracle(fake_engine):
     assert gs.get_preds().shape == (len(y), 10)
     np.testing.assert_allclose(gs.get_preds().sum(1), 1.0, rtol=1e-6)
     with pytest.raises(NotImplementedError):
-        DistGridSearchCV(est, grid, cv=3, scoring="f1_macro").fit(X, y)
+        DistGridSearchCV(est, grid, cv=3, scoring="neg_log_loss").fit(X, y)
+
+
+def test_confusion_metrics_are_sklearns():
+    """precision / recall / f1 (micro, macro, weighted), accuracy and balanced accuracy from a
+    confusion matrix, including classes missing from y_true, from y_pred or from both."""
+    import warnings
+    from sklearn import metrics as M
+    from skdist_b200.distribute.search import _metric_from_confusion
+    rng = np.random.default_rng(0)
+    K = 6
+    for trial in range(8):
+        yt = rng.integers(0, K - 1 - (trial % 2), 300)          # the last class(es) never occur in y_true
+        yp = rng.integers(0 if trial < 6 else 1, K - (trial % 3), 300)
+        conf = np.zeros((K, K), np.int64)
+        np.add.at(conf, (yt, yp), 1)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            assert _metric_from_confusion("accuracy", None, conf) == M.accuracy_score(yt, yp)
+            np.testing.assert_allclose(_metric_from_confusion("balanced_accuracy", None, conf),
+                                       M.balanced_accuracy_score(yt, yp), rtol=1e-15)
+            for avg in ("micro", "macro", "weighted"):
+                for kind, f in (("f1", M.f1_score), ("precision", M.precision_score), ("recall", M.recall_score)):
+                    np.testing.assert_allclose(_metric_from_confusion(kind, avg, conf), f(yt, yp, average=avg),
+                                               rtol=1e-14, err_msg="%s %s" % (kind, avg))
+
+
+def test_multiclass_f1_weighted_search_matches_oracle(fake_engine):
+    """The reference's examples/search/hand_written_digits.py scoring ("f1_weighted") plus a second
+    scorer, on 10-class digits."""
+    from sklearn.datasets import load_digits
+    dg = load_digits()
+    X, y = (dg.data / 16).astype(np.float32), dg.target
+    grid = {"C": [0.05, 5.0]}
+    est = LogisticRegression(max_iter=25)
+    scoring = {"f1w": "f1_weighted", "bal": "balanced_accuracy", "pm": "precision_macro"}
+    gs = DistGridSearchCV(est, grid, None, cv=3, scoring=scoring, refit="f1w", return_train_score=True).fit(X, y)
+    # equal-sized folds (599 rows each): the reference's test-size weighting == scikit-learn's plain mean
+    from sklearn.model_selection import GridSearchCV
+    sk = GridSearchCV(est, grid, cv=3, scoring=scoring, refit="f1w", return_train_score=True).fit(X, y)
+    for k in ["mean_test_f1w", "mean_test_bal", "mean_test_pm", "split1_test_f1w", "mean_train_pm", "rank_test_f1w"]:
+        np.testing.assert_allclose(gs.cv_results_[k], sk.cv_results_[k], rtol=1e-12, err_msg=k)
+    assert gs.best_params_ == sk.best_params_
+
+
+def test_binary_averaged_scorers_match_oracle(fake_engine):
+    X, y = make_g1_classification(1500, 8, seed=9)
+    grid = {"C": [0.1, 10.0]}
+    scoring = {"f1m": "f1_macro", "rw": "recall_weighted", "pmi": "precision_micro", "f1": "f1"}
+    gs = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring=scoring, refit="f1m").fit(X, y)
+    from sklearn.model_selection import GridSearchCV
+    sk = GridSearchCV(LogisticRegression(), grid, cv=3, scoring=scoring, refit="f1m").fit(X, y)
+    for k in ["mean_test_f1m", "mean_test_rw", "mean_test_pmi", "mean_test_f1"]:
+        np.testing.assert_allclose(gs.cv_results_[k], sk.cv_results_[k], rtol=1e-12, err_msg=k)
+
+
+def test_roc_auc_search_matches_sklearn(fake_engine):
+    """scoring="roc_auc" as in the reference's examples/search/basic_usage.py:89-100."""
+    from sklearn.model_selection import GridSearchCV
+    X, y = make_g1_classification(1500, 8, seed=11)
+    grid = {"C": [0.01, 1.0, 100.0]}
+    gs = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring="roc_auc", return_train_score=True).fit(X, y)
+    sk = GridSearchCV(LogisticRegression(), grid, cv=3, scoring="roc_auc", return_train_score=True).fit(X, y)
+    for k in ["mean_test_score", "split2_test_score", "mean_train_score", "rank_test_score"]:
+        np.testing.assert_allclose(gs.cv_results_[k], sk.cv_results_[k], rtol=1e-6, err_msg=k)
+    assert gs.best_params_ == sk.best_params_
+    both = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring={"auc": "roc_auc", "acc": "accuracy"},
+                            refit="auc").fit(X, y)
+    np.testing.assert_allclose(both.cv_results_["mean_test_auc"], sk.cv_results_["mean_test_score"], rtol=1e-6)
