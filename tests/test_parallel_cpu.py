@@ -34,6 +34,12 @@ def _worker(rank, world, port, out_dir):
     gs = DistGridSearchCV(LogisticRegression(), {"C": [0.01, 0.1, 1.0, 10.0, 100.0]}, cv=3).fit(X, y)
     eng = engine.get_engine()
     n_fit = sum(b for kind, b in eng.calls if kind == "fit")
+    # multiclass target: multinomial problems dealt over the ranks, confusion-count scorer
+    from skdist_b200.datasets import make_multiclass
+    Xm, ym = make_multiclass(600, 6, 4, seed=5)
+    gm = DistGridSearchCV(LogisticRegression(max_iter=40), {"C": [0.1, 1.0, 10.0]}, cv=3, scoring="f1_macro").fit(Xm, ym)
+    np.savez(os.path.join(out_dir, "multi%d.npz" % rank), mean=gm.cv_results_["mean_test_score"],
+             coef=gm.best_estimator_.coef_, n_fit=sum(b for kind, b in eng.calls if kind == "fit_multinomial"))
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), mean=gs.cv_results_["mean_test_score"],
              s0=gs.cv_results_["split0_test_score"], best=gs.best_index_, coef=gs.best_estimator_.coef_,
              n_fit=n_fit, shard=parallel.shard_indices(15, rank, world))
@@ -63,6 +69,16 @@ def test_two_rank_grid_search_matches_single_process(tmp_path):
     # each rank fitted only its own shard of the 15 columns (+ 1 refit)
     assert int(r0["n_fit"]) == 8 + 1 and int(r1["n_fit"]) == 7 + 1
     assert np.array_equal(r0["shard"], np.arange(0, 15, 2)) and np.array_equal(r1["shard"], np.arange(1, 15, 2))
+    m0, m1 = np.load(tmp_path / "multi0.npz"), np.load(tmp_path / "multi1.npz")
+    np.testing.assert_array_equal(m0["mean"], m1["mean"])
+    np.testing.assert_array_equal(m0["coef"], m1["coef"])
+    assert int(m0["n_fit"]) + int(m1["n_fit"]) == 9 + 2          # 9 (candidate, fold) problems + one refit per rank
+    from sklearn.model_selection import GridSearchCV
+    from skdist_b200.datasets import make_multiclass
+    Xm, ym = make_multiclass(600, 6, 4, seed=5)
+    from sklearn.linear_model import LogisticRegression as _LR
+    sk = GridSearchCV(_LR(max_iter=40), {"C": [0.1, 1.0, 10.0]}, cv=3, scoring="f1_macro").fit(Xm, ym)
+    np.testing.assert_allclose(m0["mean"], sk.cv_results_["mean_test_score"], rtol=1e-12)
     # single-process reference through the same host code
     from sklearn.linear_model import LogisticRegression
     from skdist.distribute.search import DistGridSearchCV
