@@ -138,6 +138,15 @@ int skd_multinomial_confusion_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, 
 int skd_linear_auc_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32_t* col_fold,
                          const int32_t* col_pos, int64_t* u2_out, int64_t* n_pos_out, int64_t* n_neg_out);
 
+/* Log loss of the predicted probabilities on the rows selected by the fold codes of
+ * skd_linear_score_batch: loss_sum_out[j] = sum_i -log(clip(p_i[y_i], eps, 1 - eps)), eps = float32 epsilon,
+ * p = softmax of the fp32 decision values; count_out[j] = rows.  n_classes == 1: B binary columns
+ * (coef [B][d+1], true class = y_class == col_pos[j], p = [1 - expit(z), expit(z)]); n_classes > 2: coef
+ * [B][n_classes][d+1], col_pos unused.  log_loss = loss_sum / count.
+ * ref: replaces search.py:264 for scoring="neg_log_loss" (log_loss(y_test, predict_proba(X_test))). */
+int skd_linear_logloss_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const float* coef, const int32_t* col_fold,
+                             const int32_t* col_pos, double* loss_sum_out, int64_t* count_out);
+
 /* Batched Ridge: B independent (alpha, fold) columns from one pass over the staged X and the
  * staged real targets.  Column j trains on rows whose fold id != col_fold[j] (col_fold[j] < 0: all
  * rows).  coef_out[j*(d+1)+k] (k<d weights, k==d intercept); status_out[j] 1 = ok, 4 = matrix not

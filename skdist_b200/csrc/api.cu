@@ -935,6 +935,19 @@ int skd_linear_auc_batch(skd_ctx* ctx, int32_t B, const float* coef, const int32
   return auc_batch(c, B, coef, col_fold, col_pos, u2_out, n_pos_out, n_neg_out);
 }
 
+int skd_linear_logloss_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const float* coef, const int32_t* col_fold,
+                             const int32_t* col_pos, double* loss_sum_out, int64_t* count_out) {
+  if (!ctx) return fail(nullptr, "skd_linear_logloss_batch: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (n_classes == 2) return fail(c, "skd_linear_logloss_batch: n_classes is 1 (binary columns) or > 2");
+  if (multinomial_check(c, "skd_linear_logloss_batch", B, n_classes == 1 ? 2 : n_classes, coef, col_fold)) return 1;
+  if (!loss_sum_out || !count_out || (n_classes == 1 && !col_pos))
+    return fail(c, "skd_linear_logloss_batch: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  Trace tr(c, "logloss");
+  return logloss_batch(c, B, n_classes, coef, col_fold, col_pos, loss_sum_out, count_out);
+}
+
 int skd_ridge_fit_batch(skd_ctx* ctx, int32_t B, const double* alpha, const int32_t* col_fold,
                         int32_t fit_intercept, float* coef_out, int32_t* status_out,
                         double* gpu_seconds_out) {

@@ -283,4 +283,118 @@ int multi_score(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold
   return 0;
 }
 
+// ---- log loss of the predicted probabilities (scoring="neg_log_loss") --------------------------------
+// log_loss(y_test, predict_proba(X_test)) of SK/metrics/_classification.py: probabilities = softmax of
+// the decision values (binary: [1 - expit(z), expit(z)], SK/linear_model/_logistic.py:1617-1625), clipped to
+// [eps, 1 - eps] with eps = float32 epsilon (predict_proba returns float32 for float32 X), summed as
+// -log p_true.  K == 1: binary columns, true class = (ycls == pos[b]).  Partials per (chunk, column) in
+// double, added in chunk order by the host.
+__global__ void __launch_bounds__(256)
+mn_logloss_kernel(const float* __restrict__ Z, int ldz, int64_t n, int64_t rpc, int K, int B,
+                  const int32_t* __restrict__ code, const int32_t* __restrict__ pos,
+                  const int32_t* __restrict__ ycls, const int8_t* __restrict__ fold,
+                  double* __restrict__ lossp, unsigned long long* __restrict__ count) {
+  __shared__ double red[8];
+  __shared__ unsigned long long redn[8];
+  const int b = blockIdx.x, z = blockIdx.y;
+  const int cd = code[b];
+  const double eps = 1.1920928955078125e-07;     // numpy.finfo(float32).eps
+  const int64_t row_begin = (int64_t)z * rpc;
+  int64_t row_end = row_begin + rpc;
+  if (row_end > n) row_end = n;
+  double acc = 0.0;
+  unsigned long long nn = 0;
+  for (int64_t r = row_begin + threadIdx.x; r < row_end; r += 256) {
+    const int fd = fold ? (int)fold[r] : -1;
+    const bool test = cd == -2 || (cd >= 0 && fd == cd) || (cd <= -3 && fd != (-3 - cd));
+    if (!test) continue;
+    const int y = ycls[r];
+    double p;
+    if (K == 1) {
+      // binary: p1 = expit(z) as float32, p0 = 1 - p1 in float32 (SK/linear_model/_base.py:438-440) --
+      // the cancellation in 1 - p1 is part of what the reference scores
+      const float p1 = (float)(1.0 / (1.0 + exp(-(double)Z[r * ldz + b])));
+      p = (double)((y == pos[b]) ? p1 : 1.0f - p1);
+    } else {
+      if (y < 0 || y >= K) continue;
+      const float* zr = Z + r * ldz + (size_t)b * K;
+      float mx = zr[0];
+      for (int k = 1; k < K; ++k) mx = fmaxf(mx, zr[k]);
+      double sum = 0.0;
+      for (int k = 0; k < K; ++k) sum += exp((double)zr[k] - (double)mx);
+      p = (double)(float)(exp((double)zr[y] - (double)mx) / sum);      // predict_proba is float32
+    }
+    p = fmin(fmax(p, eps), 1.0 - eps);
+    acc -= log(p);
+    nn += 1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    nn += __shfl_xor_sync(0xffffffffu, nn, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = acc; redn[threadIdx.x >> 5] = nn; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    lossp[(size_t)z * B + b] = ((red[0] + red[1]) + (red[2] + red[3])) + ((red[4] + red[5]) + (red[6] + red[7]));
+    unsigned long long t = 0;
+    for (int i = 0; i < 8; ++i) t += redn[i];
+    if (t) atomicAdd(&count[b], t);
+  }
+}
+
+// K == 1: coef [B][d+1] binary columns with col_pos; K >= 2: coef [B][K][d+1]
+int logloss_batch(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, const int32_t* col_pos,
+                  double* loss_sum_out, int64_t* count_out) {
+  const int64_t n = c->n, d = c->d, ldx = c->ldx;
+  const int dp = (int)d + 1;
+  int nz;
+  int64_t rpc;
+  multi_chunks(n, &nz, &rpc);
+  const int64_t per_pass = candidates_per_pass(c, K, 0);
+  for (int64_t b0 = 0; b0 < B; b0 += per_pass) {
+    const int Bb = (int)std::min<int64_t>(per_pass, B - b0);
+    const size_t slots = (size_t)Bb * K;
+    Scratch sx(c);
+    std::vector<float> h(slots * ldx + slots, 0.f);
+    for (size_t s = 0; s < slots; ++s) {
+      const float* src = coef + ((size_t)b0 * K + s) * dp;
+      memcpy(&h[s * ldx], src, d * sizeof(float));
+      h[slots * ldx + s] = src[d];
+    }
+    float *dW, *Z;
+    int32_t *dcode, *dpos = nullptr;
+    double* dloss;
+    unsigned long long* dcount;
+    const int ldz = (int)slots;
+    SKD_CUDA(c, sx.alloc(&dW, h.size()));
+    SKD_CUDA(c, sx.alloc(&Z, (size_t)n * ldz));
+    SKD_CUDA(c, sx.alloc(&dcode, (size_t)Bb));
+    SKD_CUDA(c, sx.alloc(&dpos, (size_t)Bb));
+    SKD_CUDA(c, sx.alloc(&dloss, (size_t)nz * Bb));
+    SKD_CUDA(c, sx.alloc(&dcount, (size_t)Bb));
+    SKD_CUDA(c, cudaMemcpyAsync(dW, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(dcode, col_fold + b0, Bb * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    if (col_pos) SKD_CUDA(c, cudaMemcpyAsync(dpos, col_pos + b0, Bb * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    SKD_CUDA(c, cudaMemsetAsync(dcount, 0, Bb * sizeof(unsigned long long), c->stream));
+    c->h2d += (int64_t)h.size() * 4;
+    if (simt_raw_prediction(c, (int)slots, dW, dW + slots * ldx, Z, ldz)) return 1;
+    mn_logloss_kernel<<<dim3(Bb, nz), 256, 0, c->stream>>>(Z, ldz, n, rpc, K, Bb, dcode, dpos, c->ycls, c->fold, dloss,
+                                                          dcount);
+    c->launches += 1;
+    SKD_CUDA(c, cudaGetLastError());
+    std::vector<double> hl((size_t)nz * Bb);
+    SKD_CUDA(c, cudaMemcpyAsync(hl.data(), dloss, hl.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaMemcpyAsync(count_out + b0, dcount, Bb * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->d2h += (int64_t)hl.size() * 8 + (int64_t)Bb * 8;
+    for (int j = 0; j < Bb; ++j) {
+      double sum = 0.0;
+      for (int z = 0; z < nz; ++z) sum += hl[(size_t)z * Bb + j];
+      loss_sum_out[b0 + j] = sum;
+    }
+  }
+  return 0;
+}
+
 }  // namespace skd

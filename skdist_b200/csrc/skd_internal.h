@@ -271,6 +271,8 @@ int multi_fit(Ctx* c, int B, int K, const double* C, const int32_t* col_fold, in
               int max_iter, float* coef_out, int32_t* n_iter_out, int32_t* status_out, double* loss_out,
               int32_t* n_evals_out);
 int multi_score(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, int64_t* conf_out);
+int logloss_batch(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, const int32_t* col_pos,
+                  double* loss_sum_out, int64_t* count_out);
 // raw predictions / backward product of the fp32 CUDA-core path on arbitrary slot matrices (logreg_simt.cu)
 int simt_raw_prediction(Ctx* c, int n_slots, const float* dW, const float* dbias, float* dout, int ldd);
 int simt_backward(Ctx* c, const float* G, int ldg, int n_slots, int nz, int64_t rpc, float* gradp);

@@ -157,6 +157,9 @@ def _count_metric(scorer):
     f = getattr(scorer, "_score_func", None)
     kind = _COUNT_METRICS.get(getattr(f, "__name__", ""))
     kwargs = dict(getattr(scorer, "_kwargs", {}) or {})
+    if getattr(f, "__name__", "") == "log_loss" and not kwargs and getattr(scorer, "_sign", 1) == -1:
+        # scoring="neg_log_loss": -log_loss(y, predict_proba(X)) -- summed on the device (csrc/logreg_multi.cu)
+        return "neg_log_loss", None
     if getattr(f, "__name__", "") == "roc_auc_score" and not kwargs and getattr(scorer, "_sign", 1) == 1:
         # scoring="roc_auc": roc_auc_score(y, decision_function(X)) -- exact pair counts on the device (csrc/auc.cu)
         return "roc_auc", None
@@ -261,10 +264,11 @@ class _LogRegFamily:
             if m is None:
                 raise NotImplementedError(
                     "scorer %r has no device path for classifiers (supported: accuracy, balanced_accuracy, "
-                    "precision / recall / f1 with average binary, micro, macro or weighted)" % (scorer,))
+                    "precision / recall / f1 with average binary, micro, macro or weighted, roc_auc, "
+                    "neg_log_loss)" % (scorer,))
             # binary averaging keeps the plain name; averaged variants carry (kind, average)
             self.metrics[name] = m[0] if m[1] in (None, "binary") else m
-        self.needs_pred_pos = any(k not in ("accuracy", "roc_auc") for k in self.metrics.values())
+        self.needs_pred_pos = any(k not in ("accuracy", "roc_auc", "neg_log_loss") for k in self.metrics.values())
 
     def stage(self, eng, X, fold, n_splits, x_staged=False):
         if not x_staged:
@@ -286,6 +290,8 @@ class _LogRegFamily:
         for name, kind in self.metrics.items():
             if kind == "roc_auc":
                 out[name], _ = eng.linear_auc_batch(coef, codes, pos)
+            elif kind == "neg_log_loss":
+                out[name] = -eng.linear_logloss_batch(coef, codes, pos)[0]
             elif isinstance(kind, tuple):      # micro / macro / weighted: 2 x 2 confusion [true, predicted]
                 tp = (pred_pos + actual_pos + correct - count) / 2.0
                 fp, fn = pred_pos - tp, actual_pos - tp
@@ -437,7 +443,7 @@ class _MultinomialFamily(_LogRegFamily):
             conf = eng.multinomial_confusion_batch(res["coef"], fold[idx])
             t2 = time.time()
             for name, (kind, average) in self.metrics.items():
-                out["test_%s" % name][idx] = _metric_from_confusion(kind, average, conf)
+                out["test_%s" % name][idx] = self._metric(eng, kind, average, conf, res["coef"], fold[idx])
             out["n_test"][idx] = conf.sum(axis=(1, 2))
             out["fit_time"][idx] = (t1 - t0) / len(idx)
             out["score_time"][idx] = (t2 - t1) / len(idx)
@@ -446,8 +452,15 @@ class _MultinomialFamily(_LogRegFamily):
             if return_train_score:
                 conf = eng.multinomial_confusion_batch(res["coef"], (-3 - fold[idx]).astype(np.int32))
                 for name, (kind, average) in self.metrics.items():
-                    out["train_%s" % name][idx] = _metric_from_confusion(kind, average, conf)
+                    out["train_%s" % name][idx] = self._metric(eng, kind, average, conf, res["coef"],
+                                                               (-3 - fold[idx]).astype(np.int32))
         return out
+
+    @staticmethod
+    def _metric(eng, kind, average, conf, coef, codes):
+        if kind == "neg_log_loss":
+            return -eng.linear_logloss_batch(coef, codes)[0]
+        return _metric_from_confusion(kind, average, conf)
 
     def refit(self, eng, params, X_dtype, n_features):
         p = _check_logreg(_resolve(self.estimator, params))

@@ -218,6 +218,22 @@ class Engine:
         den = 2.0 * n_pos.astype(np.float64) * n_neg.astype(np.float64)
         return np.divide(u2.astype(np.float64), den, out=np.full(B, np.nan), where=den > 0), n_pos + n_neg
 
+    def linear_logloss_batch(self, coef, col_fold, col_pos=None):
+        """Mean log loss of the predicted probabilities per column on the rows selected by the fold codes.
+        coef [B, d+1] with col_pos: binary columns; coef [B, K, d+1]: multiclass."""
+        coef = np.ascontiguousarray(coef, dtype=np.float32)
+        B = coef.shape[0]
+        K = 1 if coef.ndim == 2 else coef.shape[1]
+        assert coef.shape[-1] == self.d + 1
+        col_fold = np.ascontiguousarray(col_fold, dtype=np.int32)
+        if K == 1:
+            col_pos = np.ascontiguousarray(col_pos, dtype=np.int32)
+        loss = np.empty(B, dtype=np.float64)
+        count = np.empty(B, dtype=np.int64)
+        check(self._lib.skd_linear_logloss_batch(self._h, B, K, ptr(coef), ptr(col_fold),
+                                                 ptr(col_pos) if K == 1 else None, ptr(loss), ptr(count)), self._h)
+        return loss / np.maximum(count, 1), count
+
     def sgd_fit_batch(self, est, col_pos):
         """Fit one binary SGDClassifier per entry of col_pos (one-vs-rest label columns).
         `est` is the template SGDClassifier; host-side constants are derived exactly as

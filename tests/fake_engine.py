@@ -108,6 +108,29 @@ class FakeEngine:
                 auc[j] = roc_auc_score(yb, z)
         return auc, count
 
+    def linear_logloss_batch(self, coef, col_fold, col_pos=None):
+        from sklearn.metrics import log_loss
+        from sklearn.utils.extmath import softmax
+        B = coef.shape[0]
+        loss = np.zeros(B)
+        count = np.zeros(B, np.int64)
+        for j in range(B):
+            m = self._rows(int(col_fold[j]))
+            if coef.ndim == 2:
+                z = self.X[m] @ coef[j, :self.d] + coef[j, self.d]
+                from scipy.special import expit
+                p1 = expit(z)
+                proba = np.c_[1 - p1, p1]
+                yt = (self.y[m] == col_pos[j]).astype(int)
+                labels = [0, 1]
+            else:
+                proba = softmax(self.X[m] @ coef[j, :, :self.d].T + coef[j, :, self.d])
+                yt = self.y[m]
+                labels = list(range(coef.shape[1]))
+            loss[j] = log_loss(yt, proba, labels=labels)
+            count[j] = m.sum()
+        return loss, count
+
     def _rows(self, code):
         if code == -2:
             return np.ones(self.n, bool)

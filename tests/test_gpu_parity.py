@@ -666,3 +666,50 @@ def test_roc_auc_grid_search(eng):
     sk = GridSearchCV(LogisticRegression(), grid, cv=4, scoring="roc_auc").fit(X, y)
     np.testing.assert_allclose(gs.cv_results_["mean_test_score"], sk.cv_results_["mean_test_score"], rtol=0, atol=2e-5)
     assert gs.best_params_ == sk.best_params_
+
+
+def test_log_loss_sums_match_sklearn(eng):
+    """skd_linear_logloss_batch vs log_loss(y, predict_proba) rebuilt from the device's own fp32 decision
+    values with scikit-learn's float32 formulas (binary: expit, multiclass: softmax)."""
+    from scipy.special import expit
+    from sklearn.metrics import log_loss
+    from sklearn.utils.extmath import softmax
+    X, y = _digits32()
+    fold = _fold_ids(y, 3)
+    eng.stage_x(X); eng.stage_labels(y); eng.stage_folds(fold, 3)
+    rng = np.random.default_rng(9)
+    codes = np.array([0, 1, 2, -2, -3, -5], np.int32)
+    # multiclass, including saturated rows (large weights -> probabilities clipped at eps / 1 - eps)
+    coef = (rng.standard_normal((6, 10, 65)) * np.array([0.1, 0.3, 1, 3, 10, 0.5])[:, None, None]).astype(np.float32)
+    loss, count = eng.linear_logloss_batch(coef, codes)
+    dec = eng.linear_decision(coef.reshape(60, 65))
+    for j, cd in enumerate(codes):
+        m = np.ones(len(y), bool) if cd == -2 else (fold == cd if cd >= 0 else fold != (-3 - cd))
+        assert count[j] == m.sum()
+        want = log_loss(y[m], softmax(dec[m, j * 10:(j + 1) * 10].copy()), labels=list(range(10)))
+        np.testing.assert_allclose(loss[j], want, rtol=2e-6)
+    # binary columns (one-vs-rest of digit 3 / digit 8)
+    B = 18
+    cb = (rng.standard_normal((B, 65)) * np.linspace(0.05, 8, B)[:, None]).astype(np.float32)
+    cdb = np.resize(codes, B)
+    posb = np.where(np.arange(B) % 2 == 0, 3, 8).astype(np.int32)
+    lb, nb = eng.linear_logloss_batch(cb, cdb, posb)
+    db = eng.linear_decision(cb)
+    for j in range(B):
+        cd = cdb[j]
+        m = np.ones(len(y), bool) if cd == -2 else (fold == cd if cd >= 0 else fold != (-3 - cd))
+        p1 = expit(db[m, j])
+        want = log_loss((y[m] == posb[j]).astype(int), np.c_[1 - p1, p1], labels=[0, 1])
+        np.testing.assert_allclose(lb[j], want, rtol=2e-6)
+        assert nb[j] == m.sum()
+
+
+def test_neg_log_loss_grid_search(eng):
+    from sklearn.model_selection import GridSearchCV
+    from skdist.distribute.search import DistGridSearchCV
+    X, y = make_g1_classification(6000, 20, seed=35)
+    grid = {"C": [0.001, 0.1, 10.0]}
+    gs = DistGridSearchCV(LogisticRegression(), grid, None, cv=4, scoring="neg_log_loss").fit(X, y)
+    sk = GridSearchCV(LogisticRegression(), grid, cv=4, scoring="neg_log_loss").fit(X, y)
+    np.testing.assert_allclose(gs.cv_results_["mean_test_score"], sk.cv_results_["mean_test_score"], rtol=2e-5)
+    assert gs.best_params_ == sk.best_params_

@@ -178,7 +178,7 @@ def test_multimetric_scoring_matches_sklearn(fake_engine):
     nr = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring=scoring, refit=False).fit(X, y)
     assert not hasattr(nr, "best_index_")
     with pytest.raises(NotImplementedError):
-        DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring="neg_log_loss").fit(X, y)
+        DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring="average_precision").fit(X, y)
     Xr, yr = make_g1_regression(500, 5, seed=2)
     rs = ["r2", "neg_mean_squared_error", "neg_root_mean_squared_error"]
     ours = DistGridSearchCV(Ridge(), {"alpha": [0.1, 10.0]}, None, cv=3, scoring=rs, refit="r2").fit(Xr, yr)
@@ -238,7 +238,7 @@ def test_config1_digits_multinomial_matches_oracle(fake_engine):
     assert gs.get_preds().shape == (len(y), 10)
     np.testing.assert_allclose(gs.get_preds().sum(1), 1.0, rtol=1e-6)
     with pytest.raises(NotImplementedError):
-        DistGridSearchCV(est, grid, cv=3, scoring="neg_log_loss").fit(X, y)
+        DistGridSearchCV(est, grid, cv=3, scoring="roc_auc_ovr").fit(X, y)
 
 
 def test_confusion_metrics_are_sklearns():
@@ -307,3 +307,20 @@ def test_roc_auc_search_matches_sklearn(fake_engine):
     both = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring={"auc": "roc_auc", "acc": "accuracy"},
                             refit="auc").fit(X, y)
     np.testing.assert_allclose(both.cv_results_["mean_test_auc"], sk.cv_results_["mean_test_score"], rtol=1e-6)
+
+
+def test_neg_log_loss_search_matches_sklearn(fake_engine):
+    from sklearn.datasets import load_digits
+    from sklearn.model_selection import GridSearchCV
+    X, y = make_g1_classification(1200, 6, seed=12)
+    grid = {"C": [0.01, 1.0]}
+    gs = DistGridSearchCV(LogisticRegression(), grid, None, cv=3, scoring="neg_log_loss").fit(X, y)
+    sk = GridSearchCV(LogisticRegression(), grid, cv=3, scoring="neg_log_loss").fit(X, y)
+    np.testing.assert_allclose(gs.cv_results_["mean_test_score"], sk.cv_results_["mean_test_score"], rtol=1e-6)
+    dg = load_digits()
+    Xd, yd = (dg.data / 16).astype(np.float32), dg.target
+    est = LogisticRegression(max_iter=20)
+    gm = DistGridSearchCV(est, grid, None, cv=3, scoring={"nll": "neg_log_loss", "acc": "accuracy"}, refit="nll").fit(Xd, yd)
+    sm = GridSearchCV(est, grid, cv=3, scoring={"nll": "neg_log_loss", "acc": "accuracy"}, refit="nll").fit(Xd, yd)
+    np.testing.assert_allclose(gm.cv_results_["mean_test_nll"], sm.cv_results_["mean_test_nll"], rtol=1e-6)
+    np.testing.assert_array_equal(gm.cv_results_["mean_test_acc"], sm.cv_results_["mean_test_acc"])
