@@ -108,6 +108,8 @@ int skd_linear_score_batch(skd_ctx* ctx, int32_t B, const float* coef, const int
  * 0.5 / (C[j] * n_train) * ||W||^2 over the rows whose fold id != col_fold[j] (col_fold[j] < 0: all
  * rows) with L-BFGS-B from W = 0 (m = 10, maxls = 50, gtol = tol, ftol = 64 eps, like scikit-learn's
  * call).  coef_out[(j * n_classes + k) * (d+1) + i]: i < d weights of class k, i == d its intercept.
+ * Column masks staged with skd_stage_column_masks apply to the candidates (a masked feature keeps weight 0 in
+ * every class row) and are consumed by this call.
  * ref: replaces the estimator.fit of search.py:228-230 for a multiclass target
  * (SK/linear_model/_logistic.py:523-547,584-598; SK/_loss/_loss.pyx.tp:1293-1327). */
 int skd_logreg_multinomial_fit_batch(skd_ctx* ctx, int32_t B, int32_t n_classes, const double* C,

@@ -848,14 +848,21 @@ int skd_logreg_multinomial_fit_batch(skd_ctx* ctx, int32_t B, int32_t n_classes,
       return fail(c, "skd_logreg_multinomial_fit_batch: col_fold refers to an unstaged fold");
     if (!(C[j] > 0.0)) return fail(c, "skd_logreg_multinomial_fit_batch: C must be positive");
   }
+  // staged column masks are one-shot: whatever happens in this call, they do not outlive it
+  std::vector<uint8_t> masks;
+  masks.swap(c->h_fmask);
+  const int32_t mask_cols = c->fmask_cols;
+  c->fmask_cols = 0;
+  if (mask_cols > 0 && (mask_cols != B || (int64_t)masks.size() != (int64_t)B * c->d))
+    return fail(c, "skd_logreg_multinomial_fit_batch: staged column masks do not match the batch");
   SKD_CUDA(c, cudaSetDevice(c->device));
   Trace tr(c, "multinomial_fit");
   cudaEvent_t e0, e1;
   SKD_CUDA(c, cudaEventCreate(&e0));
   SKD_CUDA(c, cudaEventCreate(&e1));
   SKD_CUDA(c, cudaEventRecord(e0, c->stream));
-  const int rc = multi_fit(c, B, n_classes, C, col_fold, fit_intercept, tol, max_iter, coef_out, n_iter_out,
-                           status_out, loss_out, n_evals_out);
+  const int rc = multi_fit(c, B, n_classes, C, col_fold, fit_intercept, tol, max_iter, mask_cols > 0 ? masks.data() : nullptr,
+                           coef_out, n_iter_out, status_out, loss_out, n_evals_out);
   float ms = 0.f;
   if (!rc) {
     cudaEventRecord(e1, c->stream);

@@ -450,7 +450,7 @@ mn_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta*
                const int32_t* __restrict__ n_act_dev, int K, int d, int ldx, int nz, int fit_intercept,
                const double* __restrict__ lossp, const double* __restrict__ gsump,
                const float* __restrict__ gradp, const double* __restrict__ l2v,
-               const double* __restrict__ inv_nv, int32_t* n_evals) {
+               const double* __restrict__ inv_nv, int32_t* n_evals, const uint8_t* __restrict__ fmask) {
   __shared__ double red[8];
   const int a = blockIdx.x;
   if (a >= n_act_in || a >= *n_act_dev) return;
@@ -471,7 +471,8 @@ mn_step_kernel(LbfgsScalars* sc, double* vec, size_t vec_stride, const SlotMeta*
     if (j < d) {
       for (int z = 0; z < nz; ++z) acc += (double)gradp[((size_t)z * n_slots + slot) * ldx + j];
       const double xk = v.x[idx];
-      v.g[idx] = acc * inv_n + l2 * xk;
+      // a feature masked out of this candidate keeps weight 0 in every class row (zero gradient entry)
+      v.g[idx] = (fmask && !fmask[(size_t)col * d + j]) ? 0.0 : acc * inv_n + l2 * xk;
       wsq += xk * xk;
     } else {
       for (int z = 0; z < nz; ++z) acc += gsump[(size_t)z * n_slots + slot];
@@ -549,7 +550,7 @@ int multi_lbfgs_enqueue(Ctx* c, MultiWork& w, int n_act_in, int fit_intercept, i
   const int d = (int)c->d, ldx = (int)c->ldx;
   mn_step_kernel<<<n_act_in, LB_THREADS, 0, c->stream>>>(w.sc, w.vec, w.vec_stride, w.cand, n_act_in, w.n_act,
                                                          w.K, d, ldx, w.nz, fit_intercept, w.lossp, w.gsump,
-                                                         w.gradp, w.l2, w.inv_n, w.n_evals);
+                                                         w.gradp, w.l2, w.inv_n, w.n_evals, w.fmask);
   lb_compact_kernel<<<1, 1024, 0, c->stream>>>(w.sc, w.cand, n_act_in, w.n_act, hist);
   mn_export_kernel<<<n_act_in * w.K, 128, 0, c->stream>>>(w.vec, w.vec_stride, w.cand, w.n_act, w.K, d, ldx,
                                                           (size_t)w.B * w.K * ldx, w.W);

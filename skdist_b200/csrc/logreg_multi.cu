@@ -150,8 +150,8 @@ static int64_t candidates_per_pass(const Ctx* c, int K, int nz) {
 }
 
 int multi_fit(Ctx* c, int B, int K, const double* C, const int32_t* col_fold, int fit_intercept, double tol,
-              int max_iter, float* coef_out, int32_t* n_iter_out, int32_t* status_out, double* loss_out,
-              int32_t* n_evals_out) {
+              int max_iter, const uint8_t* fmask, float* coef_out, int32_t* n_iter_out, int32_t* status_out,
+              double* loss_out, int32_t* n_evals_out) {
   const int64_t n = c->n, ldx = c->ldx;
   const int dp = (int)c->d + 1, m = 10;
   int nz;
@@ -192,6 +192,11 @@ int multi_fit(Ctx* c, int B, int K, const double* C, const int32_t* col_fold, in
     SKD_CUDA(c, cudaMemcpyAsync(w.inv_n, inv_n.data(), Bb * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     SKD_CUDA(c, cudaMemcpyAsync(d_fold, col_fold + b0, Bb * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     c->h2d += (int64_t)Bb * 20;
+    if (fmask) {     // per-candidate feature masks (DistFeatureEliminator): masked weights stay exactly 0
+      SKD_CUDA(c, sx.alloc(&w.fmask, (size_t)Bb * c->d));
+      SKD_CUDA(c, cudaMemcpyAsync(w.fmask, fmask + (size_t)b0 * c->d, (size_t)Bb * c->d, cudaMemcpyHostToDevice, c->stream));
+      c->h2d += (int64_t)Bb * c->d;
+    }
     if (multi_lbfgs_init(c, w, d_fold, tol, max_iter)) return 1;
 
     // several optimiser rounds per host round trip; the kernels read the live candidate count from

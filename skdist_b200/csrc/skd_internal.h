@@ -263,13 +263,14 @@ struct MultiWork {
   double* gsump = nullptr;       // [nz x B*K]  indexed z * n_slots + slot
   float* gradp = nullptr;        // [nz x B*K x ldx]
   int32_t* n_act = nullptr;      // device scalar: active candidates
+  uint8_t* fmask = nullptr;      // [B x d] or nullptr: 1 = feature takes part in the candidate's fit
 };
 int multi_lbfgs_init(Ctx* c, MultiWork& w, const int32_t* d_col_fold, double tol, int max_iter);
 int multi_lbfgs_enqueue(Ctx* c, MultiWork& w, int n_act_in, int fit_intercept, int32_t* hist);
 int multi_lbfgs_finish(Ctx* c, MultiWork& w, float* dcoef, int32_t* dniter, int32_t* dstatus, double* dloss);
 int multi_fit(Ctx* c, int B, int K, const double* C, const int32_t* col_fold, int fit_intercept, double tol,
-              int max_iter, float* coef_out, int32_t* n_iter_out, int32_t* status_out, double* loss_out,
-              int32_t* n_evals_out);
+              int max_iter, const uint8_t* fmask /*[B x d] or nullptr*/, float* coef_out, int32_t* n_iter_out,
+              int32_t* status_out, double* loss_out, int32_t* n_evals_out);
 int multi_score(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, int64_t* conf_out);
 int logloss_batch(Ctx* c, int B, int K, const float* coef, const int32_t* col_fold, const int32_t* col_pos,
                   double* loss_sum_out, int64_t* count_out);

@@ -12,7 +12,7 @@ so its weight stays exactly 0 and the L-BFGS iterates are those of the fit on th
 columns (csrc/lbfgs_dev.cu gather_fg).  No column-dropped copies of X are made; scoring uses the
 zero-padded coefficient rows on the full X.
 
-Base estimator with a device path: binary ``LogisticRegression(solver="lbfgs")`` with
+Base estimator with a device path: ``LogisticRegression(solver="lbfgs")`` (binary or multiclass target) with
 scoring=None / "accuracy" / "roc_auc".  Anything else raises NotImplementedError (no CPU fallback).
 """
 import numpy as np
@@ -66,8 +66,12 @@ class DistFeatureEliminator(_ScParamMixin, ClassifierMixin, BaseEstimator):
         if metric is None or metric[0] not in ("accuracy", "roc_auc"):
             raise NotImplementedError("scoring=None / 'accuracy' / 'roc_auc' are scored on the device")
         classes = np.unique(y)
-        if len(classes) != 2:
-            raise NotImplementedError("the device path is binary (got %d classes)" % len(classes))
+        n_classes = len(classes)
+        if n_classes < 2:
+            raise ValueError("the target has a single class")
+        multi = n_classes > 2          # LogisticRegression(lbfgs) is multinomial there (SK/linear_model/_logistic.py:523-547)
+        if multi and metric[0] == "roc_auc":
+            raise NotImplementedError("roc_auc on a multiclass target has no device path")
         cv = check_cv(self.cv, y, classifier=is_classifier(self.estimator))
         n_samples, n_features = X.shape
         min_features_to_select = n_features // 2 if self.min_features_to_select is None \
@@ -88,10 +92,16 @@ class DistFeatureEliminator(_ScParamMixin, ClassifierMixin, BaseEstimator):
         kw = dict(fit_intercept=p["fit_intercept"], tol=p["tol"], max_iter=p["max_iter"])
         one = np.ones(1, np.int32)
 
-        # initial fit on every feature -> ranking by squared coefficient (ref :131-149)
-        res0 = eng.logreg_fit_batch(np.array([p["C"]]), np.array([-1], np.int32), one, **kw)
-        coefs = res0["coef"][0, :n_features].astype(np.float64)
-        ranks = np.argsort(coefs ** 2)
+        def fit(C, folds):
+            if multi:
+                return eng.logreg_multinomial_fit_batch(C, folds, n_classes, **kw)
+            return eng.logreg_fit_batch(C, folds, np.ones(len(C), np.int32), **kw)
+
+        # initial fit on every feature -> ranking by squared coefficient, summed over the class rows of a
+        # multiclass model (ref :141-156)
+        res0 = fit(np.array([p["C"]]), np.array([-1], np.int32))
+        coefs = res0["coef"][0][..., :n_features].astype(np.float64)
+        ranks = np.argsort((coefs ** 2).sum(axis=0) if multi else coefs ** 2)
         ranks = np.ravel(ranks)[: (n_features - min_features_to_select)]
         this_step = 0
         features_to_remove = [np.array([], dtype=np.int64)]
@@ -111,8 +121,11 @@ class DistFeatureEliminator(_ScParamMixin, ClassifierMixin, BaseEstimator):
         pos = np.ones(len(mine), np.int32)
         if len(mine):
             eng.stage_column_masks(masks)
-            res = eng.logreg_fit_batch(np.full(len(mine), p["C"]), f_cols, pos, **kw)
-            if metric[0] == "roc_auc":       # the reference's examples/eliminate/basic_usage.py scorer
+            res = fit(np.full(len(mine), p["C"]), f_cols)
+            if multi:
+                correct, count = eng.multinomial_score_batch(res["coef"], f_cols)
+                loc = correct / np.maximum(count, 1)
+            elif metric[0] == "roc_auc":       # the reference's examples/eliminate/basic_usage.py scorer
                 loc, _ = eng.linear_auc_batch(res["coef"], f_cols, pos)
             else:
                 correct, count = eng.linear_score_batch(res["coef"], f_cols, pos)
@@ -132,13 +145,14 @@ class DistFeatureEliminator(_ScParamMixin, ClassifierMixin, BaseEstimator):
         m = np.zeros((1, n_features), np.uint8)
         m[0, np.asarray(self.best_features_, dtype=np.int64)] = 1
         eng.stage_column_masks(m)
-        resb = eng.logreg_fit_batch(np.array([p["C"]]), np.array([-1], np.int32), one, **kw)
+        resb = fit(np.array([p["C"]]), np.array([-1], np.int32))
         keep = np.asarray(self.best_features_, dtype=np.int64)
         est = _clone(self.estimator)
         dt = np.float64 if X.dtype == np.float64 else np.float32
-        est.coef_ = resb["coef"][0, :n_features][keep][None, :].astype(dt)
-        est.intercept_ = (resb["coef"][0, n_features:n_features + 1].astype(dt) if est.fit_intercept
-                          else np.zeros(1, dtype=dt))
+        rows = np.atleast_2d(resb["coef"][0])                 # (1, d+1) binary, (K, d+1) multiclass
+        est.coef_ = rows[:, :n_features][:, keep].astype(dt)
+        est.intercept_ = (rows[:, n_features].astype(dt) if est.fit_intercept
+                          else np.zeros(rows.shape[0], dtype=dt))
         est.classes_ = classes
         est.n_iter_ = np.array([int(resb["n_iter"][0])], dtype=np.int32)
         est.n_features_in_ = len(keep)

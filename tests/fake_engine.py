@@ -61,14 +61,18 @@ class FakeEngine:
 
     def logreg_multinomial_fit_batch(self, C, col_fold, n_classes, fit_intercept=True, tol=1e-4, max_iter=100):
         B = len(C)
+        fmask = getattr(self, "_fmask", None)
+        self._fmask = None
         self.calls.append(("fit_multinomial", B))
         coef = np.zeros((B, n_classes, self.d + 1), np.float32)
         n_iter = np.zeros(B, np.int32)
         for j in range(B):
             m = self._train_mask(int(col_fold[j]))
-            W, b, it = lo.fit_multinomial_lbfgs(self.X[m], self.y[m], n_classes, C=float(C[j]), tol=tol,
+            keep = np.arange(self.d) if fmask is None else np.flatnonzero(fmask[j])
+            Xm = self.X[m] if fmask is None else np.ascontiguousarray(self.X[m][:, keep])
+            W, b, it = lo.fit_multinomial_lbfgs(Xm, self.y[m], n_classes, C=float(C[j]), tol=tol,
                                                 max_iter=max_iter, fit_intercept=fit_intercept)
-            coef[j, :, :self.d] = W
+            coef[j][:, keep] = W
             coef[j, :, self.d] = b
             n_iter[j] = it
         return {"coef": coef, "n_iter": n_iter, "status": np.ones(B, np.int32),

@@ -99,3 +99,35 @@ def test_eliminator_roc_auc(fake_engine):
                                           .decision_function(X[te][:, keep]))
                             for tr, te in StratifiedKFold(3).split(X, y)]))
     np.testing.assert_allclose(fe.scores_, exp, atol=1e-6)
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_eliminator_multiclass(fake_engine):
+    """Multiclass target: multinomial fits, ranking by the squared coefficients summed over the class rows
+    (ref eliminate.py:153-154), written out with scikit-learn on the CPU."""
+    from sklearn.model_selection import StratifiedKFold
+    from skdist_b200.datasets import make_multiclass
+    X, y = make_multiclass(500, 8, 3, seed=4)
+    rng = np.random.default_rng(1)
+    X = np.hstack([X, rng.standard_normal((500, 3)).astype(np.float32)])
+    d = X.shape[1]
+    base = LogisticRegression(C=0.5, max_iter=60)
+    fe = DistFeatureEliminator(base, None, step=2, cv=3, min_features_to_select=5).fit(X, y)
+    coefs = LogisticRegression(C=0.5, max_iter=60).fit(X, y).coef_.astype(np.float64)
+    ranks = np.argsort((coefs ** 2).sum(axis=0))[: d - 5]
+    sets, k = [np.array([], int)], 0
+    while k < d - 5:
+        k += 2
+        sets.append(ranks[:k])
+    exp = []
+    for rm in sets:
+        keep = np.setdiff1d(np.arange(d), rm)
+        exp.append(np.mean([LogisticRegression(C=0.5, max_iter=60).fit(X[tr][:, keep], y[tr]).score(X[te][:, keep], y[te])
+                            for tr, te in StratifiedKFold(3).split(X, y)]))
+    np.testing.assert_allclose(fe.scores_, exp, atol=1e-12)
+    keep = np.setdiff1d(np.arange(d), sets[int(np.argmax(exp))])
+    assert list(fe.best_features_) == list(keep)
+    ref = LogisticRegression(C=0.5, max_iter=60).fit(X[:, keep], y)
+    assert fe.best_estimator_.coef_.shape == (3, len(keep))
+    np.testing.assert_array_equal(fe.best_estimator_.coef_, ref.coef_)
+    np.testing.assert_array_equal(fe.predict(X), ref.predict(X[:, keep]))

@@ -713,3 +713,30 @@ def test_neg_log_loss_grid_search(eng):
     sk = GridSearchCV(LogisticRegression(), grid, cv=4, scoring="neg_log_loss").fit(X, y)
     np.testing.assert_allclose(gs.cv_results_["mean_test_score"], sk.cv_results_["mean_test_score"], rtol=2e-5)
     assert gs.best_params_ == sk.best_params_
+
+
+def test_multinomial_feature_masks(eng):
+    """Per-candidate feature masks on the multinomial solver (multiclass DistFeatureEliminator): the masked
+    fit on the full X is the fit on the column-dropped X; masked weights are exactly 0."""
+    X, y = _digits32()
+    fold = _fold_ids(y, 3)
+    keep = np.flatnonzero(X.std(0) > 0)[::2]
+    mask = np.zeros((2, 64), np.uint8)
+    mask[:, keep] = 1
+    cf = np.array([1, -1], np.int32)
+    eng.stage_x(X); eng.stage_labels(y); eng.stage_folds(fold, 3)
+    eng.stage_column_masks(mask)
+    a = eng.logreg_multinomial_fit_batch(np.array([0.5, 0.5]), cf, 10, max_iter=300)
+    b_unmasked = eng.logreg_multinomial_fit_batch(np.array([0.5]), cf[:1], 10, max_iter=300)   # masks were consumed
+    assert np.abs(b_unmasked["coef"][0, :, :64][:, np.setdiff1d(np.arange(64), keep)]).max() > 0
+    dropped = np.setdiff1d(np.arange(64), keep)
+    assert np.all(a["coef"][:, :, dropped] == 0)
+    Xk = np.ascontiguousarray(X[:, keep])
+    eng.stage_x(Xk); eng.stage_labels(y); eng.stage_folds(fold, 3)
+    b = eng.logreg_multinomial_fit_batch(np.array([0.5, 0.5]), cf, 10, max_iter=300)
+    scale = np.abs(b["coef"]).max()
+    assert np.abs(a["coef"][:, :, keep] - b["coef"][:, :, :len(keep)]).max() <= 2e-2 * scale
+    assert np.abs(a["loss"] - b["loss"]).max() <= 1e-5 * np.abs(b["loss"]).max()
+    from skdist.distribute.eliminate import DistFeatureEliminator
+    fe = DistFeatureEliminator(LogisticRegression(max_iter=300), None, step=8, cv=3, min_features_to_select=40).fit(X, y)
+    assert fe.best_estimator_.coef_.shape == (10, fe.n_features_) and fe.score(X, y) > 0.95
