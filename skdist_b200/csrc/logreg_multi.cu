@@ -318,8 +318,10 @@ mn_logloss_kernel(const float* __restrict__ Z, int ldz, int64_t n, int64_t rpc, 
     if (K == 1) {
       // binary: p1 = expit(z) as float32, p0 = 1 - p1 in float32 (SK/linear_model/_base.py:438-440) --
       // the cancellation in 1 - p1 is part of what the reference scores
-      const float p1 = (float)(1.0 / (1.0 + exp(-(double)Z[r * ldz + b])));
-      p = (double)((y == pos[b]) ? p1 : 1.0f - p1);
+      // scipy's float32 expit is 1 / (1 + expf(-z)) in float arithmetic; each rounding is reproduced
+      const float e = (float)exp(-(double)Z[r * ldz + b]);
+      const float p1 = __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+      p = (double)((y == pos[b]) ? p1 : __fsub_rn(1.0f, p1));
     } else {
       if (y < 0 || y >= K) continue;
       const float* zr = Z + r * ldz + (size_t)b * K;
