@@ -1,3 +1,6 @@
+"""Batch invariance of the tensor-core fit: one (C, fold) column fitted alone and inside batches of
+1 / 32 / 148 / 160 groups of 128 columns must give bit-identical coefficients (more groups than SMs
+exercises the weight reload of a CTA that spans several groups)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -1,3 +1,5 @@
+"""Batch invariance of the tensor-core objective / gradient evaluation at a fixed point: a column's loss
+and gradient inside a 160-group batch vs alone, group by group (diagnostic for multi-group CTAs)."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

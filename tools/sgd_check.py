@@ -1,3 +1,5 @@
+"""Column-batched exact-order SGD vs scikit-learn's SGDClassifier: coefficients, intercepts, n_iter_
+and t_ must be bit-identical (hinge and log_loss, several shapes)."""
 import os, sys, warnings
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
