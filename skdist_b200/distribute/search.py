@@ -72,12 +72,47 @@ def _fold_ids(cv_splitted, n_samples):
     return fold
 
 
-def _cv_fold_ids(cv, X, y, groups, n_samples):
+class _TargetCodes:
+    """One hash pass over a 1-d integer / bool target: `codes` numbers the classes by order of first
+    appearance (what StratifiedKFold's `_make_test_folds` works on), `classes` are the sorted labels and
+    `y_class` the index of every row's label in them (what `np.unique` + `searchsorted` give, without
+    the sort over the rows)."""
+
+    def __init__(self, y):
+        import pandas as pd
+        self.y = y
+        self.codes, uniques = pd.factorize(y)
+        uniques = np.asarray(uniques, dtype=y.dtype)
+        order = np.argsort(uniques, kind="stable")
+        self.classes = uniques[order]
+        rank = np.empty(len(order), dtype=np.int32)
+        rank[order] = np.arange(len(order), dtype=np.int32)
+        self.y_class = rank[self.codes]
+
+
+def _encode_target(y):
+    """_TargetCodes for targets the fast path covers (1-d integer / bool arrays), else None."""
+    y1 = np.asarray(y) if y is not None else None
+    if y1 is None or y1.ndim != 1 or y1.dtype.kind not in "biu" or len(y1) == 0:
+        return None
+    return _TargetCodes(y1)
+
+
+def _classes_and_ids(y, enc=None):
+    """(sorted class labels, int32 class id per row)."""
+    if enc is not None and enc.y is y:
+        return enc.classes, enc.y_class
+    classes = np.unique(y)
+    return classes, np.searchsorted(classes, y).astype(np.int32)
+
+
+def _cv_fold_ids(cv, X, y, groups, n_samples, enc=None):
     """(fold id per row, n_splits) of a cross-validator.  The generic route materialises every
     (train, test) index pair like the reference does (search.py:379) and converts them; the two
     splitters `check_cv` produces for an integer `cv` -- unshuffled `StratifiedKFold` / `KFold` -- are
     restated directly (no per-split index arrays, no sorts over the rows), fold for fold what
-    SK/model_selection/_split.py:774-841 (`_make_test_folds`) and :531-547 (`_iter_test_indices`) give."""
+    SK/model_selection/_split.py:774-841 (`_make_test_folds`) and :531-547 (`_iter_test_indices`) give.
+    `enc` (a _TargetCodes of y) saves the hash pass when the caller already has it."""
     from sklearn.model_selection import KFold, StratifiedKFold
     if type(cv) is KFold and not cv.shuffle and groups is None:
         k = cv.n_splits
@@ -87,21 +122,23 @@ def _cv_fold_ids(cv, X, y, groups, n_samples):
         sizes[: n_samples % k] += 1
         return np.repeat(np.arange(k, dtype=np.int8), sizes), k
     if type(cv) is StratifiedKFold and not cv.shuffle and groups is None and y is not None:
-        import pandas as pd
-        y1 = np.asarray(y)
         k = cv.n_splits
-        if y1.ndim == 1 and y1.dtype.kind in "biu" and k <= 127:
-            y_encoded = pd.factorize(y1)[0]                   # classes numbered by order of appearance
+        if enc is None or enc.y is not y:
+            enc = _encode_target(y)
+        if enc is not None and k <= 127:
+            y_encoded = enc.codes                             # classes numbered by order of appearance
             counts = np.bincount(y_encoded)
             if counts.min() >= k:                             # otherwise: scikit-learn's own warnings / errors
                 # y_order = sorted codes: class c occupies positions [start_c, start_c + counts[c]); fold i
-                # takes the positions congruent to i modulo k, class by class in original row order
+                # takes the positions congruent to i modulo k, class by class in original row order:
+                # alloc[i] = #{p in [start, start + count): p mod k == i}, in closed form
                 starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
                 fold = np.empty(n_samples, dtype=np.int8)
+                folds = np.arange(k, dtype=np.int64)
                 for c in range(len(counts)):
-                    pos = np.arange(starts[c], starts[c] + counts[c])
-                    alloc = np.bincount(pos % k, minlength=k)
-                    fold[y_encoded == c] = np.repeat(np.arange(k, dtype=np.int8), alloc)
+                    s0, cnt = int(starts[c]), int(counts[c])
+                    alloc = (s0 + cnt - 1 - folds) // k - (s0 - 1 - folds) // k
+                    fold[np.flatnonzero(y_encoded == c)] = np.repeat(np.arange(k, dtype=np.int8), alloc)
                 return fold, k
     cv_splitted = list(cv.split(X, y, groups))
     return _fold_ids(cv_splitted, n_samples), len(cv_splitted)
@@ -241,7 +278,7 @@ class _LogRegFamily:
 
     name = "logreg"
 
-    def __init__(self, estimator, candidate_params, X, y, scorers):
+    def __init__(self, estimator, candidate_params, X, y, scorers, enc=None):
         self.estimator = estimator
         self.cands = [_check_logreg(q) for q in _merged_params(estimator, candidate_params)]
         for p in candidate_params:
@@ -250,12 +287,10 @@ class _LogRegFamily:
                 raise NotImplementedError(
                     "searching LogisticRegression over %s has no device path (searchable: %s)"
                     % (sorted(extra), sorted(_LOGREG_SEARCHABLE)))
-        self.classes_ = np.unique(y)
+        self.classes_, self.y_class = _classes_and_ids(y, enc)
         if len(self.classes_) != 2:
             raise NotImplementedError(
-                "LogisticRegression device path is binary (got %d classes); wrap the estimator "
-                "in DistOneVsRestClassifier for multiclass" % len(self.classes_))
-        self.y_class = np.searchsorted(self.classes_, y).astype(np.int32)
+                "this family is binary (got %d classes)" % len(self.classes_))
         # every scorer must be a count-based metric (accuracy / precision / recall / f1 / balanced
         # accuracy on predict); scoring=None -> _PassthroughScorer -> estimator.score == accuracy
         self.metrics = {}
@@ -275,8 +310,12 @@ class _LogRegFamily:
             parallel.stage_x_replicated(eng, X)
         eng.stage_labels(self.y_class)
         eng.stage_folds(fold, n_splits)
-        self.pos_in_fold = np.bincount(np.asarray(fold)[self.y_class == 1], minlength=n_splits).astype(np.int64)
-        self.total_pos = int((self.y_class == 1).sum())
+        if self.needs_pred_pos:     # positives per fold: only the precision / recall / f1 formulas use them
+            self.pos_in_fold = np.bincount(np.asarray(fold)[self.y_class == 1], minlength=n_splits).astype(np.int64)
+            self.total_pos = int(self.pos_in_fold.sum())
+        else:
+            self.pos_in_fold = np.zeros(n_splits, dtype=np.int64)
+            self.total_pos = 0
 
     def _scores(self, eng, coef, codes, pos, actual_pos):
         """{scorer name: per-column value} on the rows selected by the scoring codes."""
@@ -388,7 +427,7 @@ class _MultinomialFamily(_LogRegFamily):
 
     name = "logreg_multinomial"
 
-    def __init__(self, estimator, candidate_params, X, y, scorers):
+    def __init__(self, estimator, candidate_params, X, y, scorers, enc=None):
         self.estimator = estimator
         self.cands = [_check_logreg(q) for q in _merged_params(estimator, candidate_params)]
         for p in candidate_params:
@@ -397,9 +436,8 @@ class _MultinomialFamily(_LogRegFamily):
                 raise NotImplementedError(
                     "searching LogisticRegression over %s has no device path (searchable: %s)"
                     % (sorted(extra), sorted(_LOGREG_SEARCHABLE)))
-        self.classes_ = np.unique(y)
+        self.classes_, self.y_class = _classes_and_ids(y, enc)
         self.n_classes = len(self.classes_)
-        self.y_class = np.searchsorted(self.classes_, y).astype(np.int32)
         self.metrics = {}
         for name, scorer in scorers.items():
             m = _count_metric(scorer)
@@ -496,11 +534,12 @@ class _MultinomialFamily(_LogRegFamily):
         return np.vstack([softmax(dec[fold == k, k * K:(k + 1) * K].astype(np.float64)) for k in range(n_splits)])
 
 
-def _pick_family(estimator, candidate_params, X, y, scorers):
+def _pick_family(estimator, candidate_params, X, y, scorers, enc=None):
     if type(estimator) is LogisticRegression:
-        if len(np.unique(y)) > 2:
-            return _MultinomialFamily(estimator, candidate_params, X, y, scorers)
-        return _LogRegFamily(estimator, candidate_params, X, y, scorers)
+        n_classes = len(enc.classes) if enc is not None and enc.y is y else len(np.unique(y))
+        if n_classes > 2:
+            return _MultinomialFamily(estimator, candidate_params, X, y, scorers, enc)
+        return _LogRegFamily(estimator, candidate_params, X, y, scorers, enc)
     if type(estimator) is Ridge:
         from .ridge_family import _RidgeFamily
         return _RidgeFamily(estimator, candidate_params, X, y, scorers)
@@ -554,9 +593,11 @@ class DistBaseSearchCV(_ScParamMixin):
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=1) as pool:
             staged = pool.submit(parallel.stage_x_replicated, eng, X_arr)
+            time.sleep(0)       # hand the GIL to the worker so that the copy starts before the host work below
             try:
-                fold, _ = _cv_fold_ids(cv, X, y, groups, n_samples)
-                family = _pick_family(estimator, candidate_params, X_arr, y_arr, scorers)
+                enc = _encode_target(y_arr) if is_classifier(estimator) else None   # one hash pass over y for both
+                fold, _ = _cv_fold_ids(cv, X, y_arr, groups, n_samples, enc)
+                family = _pick_family(estimator, candidate_params, X_arr, y_arr, scorers, enc)
             finally:
                 staged.result()
 
