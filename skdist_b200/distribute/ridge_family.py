@@ -85,6 +85,12 @@ class _RidgeFamily:
             parallel.stage_x_replicated(eng, X)
         eng.stage_targets(self.y)
         eng.stage_folds(fold, n_splits)
+        if getattr(self, "fold", None) is not fold:
+            self.prepare(fold, n_splits)
+
+    def prepare(self, fold, n_splits):
+        """Total sums of squares of the test / train part of every fold (denominators of r2); host-only,
+        so the search runs it while X is still on its way to the device."""
         self.fold = fold
         y64 = self.y.astype(np.float64)
         self.sst_test = np.zeros(n_splits)

@@ -575,29 +575,32 @@ class DistBaseSearchCV(_ScParamMixin):
 
         X, y, groups = indexable(X, y, groups)
         n_splits = cv.get_n_splits(X, y, groups)
-        candidate_params = list(self._get_param_iterator())
-        n_candidates = len(candidate_params)
-        if self.verbose > 0:
-            print("Fitting {0} folds for each of {1} candidates, totalling {2} fits".format(
-                n_splits, n_candidates, n_candidates * n_splits))
-        _parse_partitions(self.partitions, n_candidates * n_splits)
 
         X_arr = np.asarray(X)
         if X_arr.ndim != 2:
             raise ValueError("X must be a 2-d array")
         y_arr = np.asarray(y)
         n_samples, n_features = X_arr.shape
-        # the host-to-device copy of X (the C-ABI call releases the GIL) runs while the host computes
-        # the cv splits and validates the candidates
+        # the host-to-device copy of X (the C-ABI call releases the GIL) runs while the host draws the
+        # candidates (ParameterSampler: one scipy rvs call per candidate), computes the cv splits and
+        # validates the candidates
         eng = get_engine()
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=1) as pool:
             staged = pool.submit(parallel.stage_x_replicated, eng, X_arr)
             time.sleep(0)       # hand the GIL to the worker so that the copy starts before the host work below
             try:
+                candidate_params = list(self._get_param_iterator())
+                n_candidates = len(candidate_params)
+                if self.verbose > 0:
+                    print("Fitting {0} folds for each of {1} candidates, totalling {2} fits".format(
+                        n_splits, n_candidates, n_candidates * n_splits))
+                _parse_partitions(self.partitions, n_candidates * n_splits)
                 enc = _encode_target(y_arr) if is_classifier(estimator) else None   # one hash pass over y for both
                 fold, _ = _cv_fold_ids(cv, X, y_arr, groups, n_samples, enc)
                 family = _pick_family(estimator, candidate_params, X_arr, y_arr, scorers, enc)
+                if hasattr(family, "prepare"):      # host-only statistics of the folds (no engine calls)
+                    family.prepare(fold, n_splits)
             finally:
                 staged.result()
 
