@@ -25,7 +25,8 @@ from sklearn.utils.validation import check_is_fitted
 from .. import parallel
 from ..engine import get_engine
 from .base import _clone, _parse_partitions, _ScParamMixin
-from .search import _check_logreg, _count_metric, _fold_ids
+from .folds import _fold_ids
+from .logreg_family import _check_logreg, _count_metric
 from .utils import _check_multimetric_scoring
 
 __all__ = ["DistFeatureEliminator"]

@@ -124,7 +124,7 @@ class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
             col_ids = np.flatnonzero(~const)
         mine = col_ids[parallel.shard_indices(len(col_ids), rank, world)]
         if type(base) is LogisticRegression:
-            from .search import _check_logreg
+            from .logreg_family import _check_logreg
             p = _check_logreg(_clone(base))
             res = eng.logreg_fit_batch(np.full(len(mine), p["C"]), np.full(len(mine), -1, np.int32),
                                        mine.astype(np.int32), fit_intercept=p["fit_intercept"],
@@ -198,7 +198,7 @@ class DistOneVsOneClassifier(_ScParamMixin, OneVsOneClassifier):
             raise NotImplementedError(
                 "%s has no one-vs-one device path; supported base estimator: LogisticRegression(solver='lbfgs')."
                 "  (No CPU fallback by design.)" % type(base).__name__)
-        from .search import _check_logreg
+        from .logreg_family import _check_logreg
         p = _check_logreg(_clone(base))
         ycls = np.searchsorted(self.classes_, y_arr).astype(np.int32)
         rank, world, _ = parallel.dist_info()

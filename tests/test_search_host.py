@@ -191,7 +191,7 @@ def test_multimetric_scoring_matches_sklearn(fake_engine):
 def test_fast_fold_ids_equal_sklearn_splitters():
     """The direct restatement of unshuffled StratifiedKFold / KFold must give scikit-learn's folds."""
     from sklearn.model_selection import GroupKFold, KFold, StratifiedKFold
-    from skdist_b200.distribute.search import _cv_fold_ids, _fold_ids
+    from skdist_b200.distribute.folds import _cv_fold_ids, _fold_ids
     rng = np.random.RandomState(3)
     for n, k, ymaker in [(1000, 5, lambda: rng.randint(0, 2, 1000)), (1003, 7, lambda: rng.randint(0, 4, 1003)),
                          (50, 3, lambda: np.r_[np.zeros(40, int), np.ones(10, int)]),
@@ -246,7 +246,7 @@ def test_confusion_metrics_are_sklearns():
     confusion matrix, including classes missing from y_true, from y_pred or from both."""
     import warnings
     from sklearn import metrics as M
-    from skdist_b200.distribute.search import _metric_from_confusion
+    from skdist_b200.distribute.logreg_family import _metric_from_confusion
     rng = np.random.default_rng(0)
     K = 6
     for trial in range(8):
