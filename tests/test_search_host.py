@@ -324,3 +324,31 @@ def test_neg_log_loss_search_matches_sklearn(fake_engine):
     sm = GridSearchCV(est, grid, cv=3, scoring={"nll": "neg_log_loss", "acc": "accuracy"}, refit="nll").fit(Xd, yd)
     np.testing.assert_allclose(gm.cv_results_["mean_test_nll"], sm.cv_results_["mean_test_nll"], rtol=1e-6)
     np.testing.assert_array_equal(gm.cv_results_["mean_test_acc"], sm.cv_results_["mean_test_acc"])
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_odd_inputs_match_sklearn(fake_engine):
+    """Inputs a drop-in user passes: string labels, bool labels, float labels, pandas containers,
+    Fortran-ordered / float64 X, a single candidate, two folds."""
+    import pandas as pd
+    from sklearn.model_selection import GridSearchCV
+    X, y = make_g1_classification(600, 6, seed=21)
+    grid = {"C": [0.1, 1.0]}
+
+    def check(Xi, yi, g=grid, cv=3, **kw):
+        gs = DistGridSearchCV(LogisticRegression(), g, None, cv=cv, **kw).fit(Xi, yi)
+        sk = GridSearchCV(LogisticRegression(), g, cv=cv, **kw).fit(np.asarray(Xi, dtype=np.float32), yi)
+        np.testing.assert_allclose(gs.cv_results_["mean_test_score"], sk.cv_results_["mean_test_score"], rtol=1e-12)
+        assert gs.best_params_ == sk.best_params_
+        np.testing.assert_array_equal(gs.predict(np.asarray(Xi)[:40]), sk.predict(np.asarray(Xi, dtype=np.float32)[:40]))
+        return gs
+
+    gs = check(X, np.where(y == 1, "spam", "ham"))
+    assert list(gs.classes_) == ["ham", "spam"]
+    check(X, y.astype(bool))
+    check(X, y.astype(np.float64))
+    check(pd.DataFrame(X), pd.Series(y))
+    check(np.asfortranarray(X), y)
+    check(X, y, g={"C": [0.5]}, cv=2)
+    ym = (np.arange(600) % 3 == 0).astype(int) + 2 * (np.arange(600) % 5 == 0)      # 4 classes, strings below
+    check(X, np.array(["a", "b", "c", "d"])[ym])
