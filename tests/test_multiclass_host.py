@@ -94,3 +94,22 @@ def test_ovo_logreg_matches_sklearn(fake_engine):
     np.testing.assert_allclose(ovo.decision_function(X), ref.decision_function(X), atol=1e-5)
     with pytest.raises(ValueError):
         DistOneVsOneClassifier(LogisticRegression()).fit(X, np.zeros(len(X)))
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_string_labels_and_pandas_inputs(fake_engine):
+    """String class labels and pandas containers through one-vs-rest and one-vs-one."""
+    import pandas as pd
+    from sklearn.multiclass import OneVsOneClassifier
+    from skdist.distribute.multiclass import DistOneVsOneClassifier
+    X, y = make_multiclass(700, 10, 4, seed=6)
+    names = np.array(["delta", "alpha", "charlie", "bravo"])[y]
+    ovr = DistOneVsRestClassifier(LogisticRegression(C=0.3), None).fit(pd.DataFrame(X), pd.Series(names))
+    ref = OneVsRestClassifier(LogisticRegression(C=0.3)).fit(X, names)
+    assert list(ovr.classes_) == list(ref.classes_) == ["alpha", "bravo", "charlie", "delta"]
+    for a, b in zip(ovr.estimators_, ref.estimators_):
+        np.testing.assert_array_equal(a.coef_, b.coef_)
+    np.testing.assert_array_equal(ovr.predict(X), ref.predict(X))
+    ovo = DistOneVsOneClassifier(LogisticRegression(C=0.3), None).fit(X, names)
+    refo = OneVsOneClassifier(LogisticRegression(C=0.3)).fit(X, names)
+    np.testing.assert_array_equal(ovo.predict(X), refo.predict(X))
