@@ -117,8 +117,69 @@ def run_ridge_case(name, X, y, alphas, cv, ref_search):
     print(name, "mean_test_score", ref["cv_results_"]["mean_test_score"])
 
 
+def run_multinomial_case(name, X, y, grid, cv, max_iter, ref_search):
+    """BASELINE config 1 shape: multiclass target -> multinomial lbfgs (SK/linear_model/_logistic.py:523-547).
+    Scores from the reference's unmodified `_fit_and_score`; per-(candidate, fold) coefficients from the same
+    scikit-learn fit, checked bit for bit against the oracle's restatement when X is float32."""
+    import warnings
+    from sklearn.model_selection import check_cv
+    from threadpoolctl import threadpool_limits
+    from oracle import logreg_oracle
+    warnings.simplefilter("ignore")
+    est = LogisticRegression(max_iter=max_iter)
+    cands = list(ParameterGrid(grid))
+    ref = search_oracle.search_cv(est, cands, X, y, cv=cv, iid=True, task_fn=reference_task(ref_search))
+    ora = search_oracle.search_cv(est, cands, X, y, cv=cv, iid=True)
+    n_splits = ref["n_splits_"]
+    keys = ["split%d_test_score" % i for i in range(n_splits)] + ["mean_test_score", "std_test_score",
+                                                                  "rank_test_score"]
+    for k in keys:
+        assert np.array_equal(ref["cv_results_"][k], ora["cv_results_"][k]), (name, k)
+    splits = list(check_cv(cv, y, classifier=True).split(X, y))
+    K, d = len(np.unique(y)), X.shape[1]
+    coef = np.zeros((len(cands), n_splits, K, d + 1), X.dtype)
+    n_iter = np.zeros((len(cands), n_splits), np.int32)
+    for ci, p in enumerate(cands):
+        for fi, (tr, te) in enumerate(splits):
+            m = LogisticRegression(max_iter=max_iter, **p).fit(X[tr], y[tr])
+            coef[ci, fi, :, :d] = m.coef_
+            coef[ci, fi, :, d] = m.intercept_
+            n_iter[ci, fi] = m.n_iter_[0]
+            if X.dtype == np.float32:
+                W, b, it = logreg_oracle.fit_multinomial_lbfgs(X[tr], y[tr], K, C=p["C"], max_iter=max_iter)
+                assert np.array_equal(W, m.coef_) and np.array_equal(b, m.intercept_) and it == m.n_iter_[0]
+    rng = np.random.default_rng(4321)
+    noise_flips = np.zeros((len(cands), n_splits), np.int64)
+    noise_coef = np.zeros((len(cands), n_splits))
+    for variant in range(8):        # 1 thread, default threads, then 6 row permutations
+        for ci, p in enumerate(cands):
+            for fi, (tr, te) in enumerate(splits):
+                trv = tr if variant < 2 else tr[rng.permutation(len(tr))]
+                with threadpool_limits(limits=1 if variant == 0 else None):
+                    m = LogisticRegression(max_iter=max_iter, **p).fit(X[trv], y[trv])
+                base_correct = int(round(ref["cv_results_"]["split%d_test_score" % fi][ci] * len(te)))
+                noise_flips[ci, fi] = max(noise_flips[ci, fi], abs(int((m.predict(X[te]) == y[te]).sum()) - base_correct))
+                w = np.c_[m.coef_, m.intercept_]
+                noise_coef[ci, fi] = max(noise_coef[ci, fi], np.abs(w - coef[ci, fi]).max() / np.abs(coef[ci, fi]).max())
+    out = {k: ref["cv_results_"][k] for k in keys}
+    out.update(noise_flips=noise_flips, noise_coef=noise_coef, best_index=ref["best_index_"], coef=coef, n_iter=n_iter,
+               C=np.array([p["C"] for p in cands]), max_iter=max_iter)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "mean_test_score", ref["cv_results_"]["mean_test_score"], "n_iter", n_iter.ravel())
+    print(name, "noise_flips", noise_flips.ravel(), "\n  noise_coef", np.round(noise_coef.ravel(), 5))
+
+
 def main():
     ref_search, _, _ = refshim.load()
+    if "--multinomial-only" in sys.argv:
+        dg = load_digits()
+        grid = {"C": [0.01, 0.1, 1.0, 10.0]}
+        # config 1 of BASELINE.json as stated (raw 0..16 pixels, float64, default max_iter) and on scaled
+        # float32 pixels with enough iterations to converge (the reproducible variant)
+        run_multinomial_case("search_logreg_digits10_raw", dg.data, dg.target, grid, 3, 100, ref_search)
+        run_multinomial_case("search_logreg_digits10_scaled", (dg.data / 16).astype(np.float32), dg.target, grid, 3,
+                             300, ref_search)
+        return
     if "--ridge-only" in sys.argv:
         from skdist_b200.datasets import make_g1_regression
         X, y = make_g1_regression(6000, 40, seed=5)

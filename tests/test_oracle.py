@@ -89,3 +89,31 @@ def test_multinomial_restatement_is_sklearn(dtype):
         else:
             np.testing.assert_allclose(W, est.coef_, rtol=0, atol=1e-7)
             np.testing.assert_allclose(b, est.intercept_, rtol=0, atol=1e-7)
+
+
+@pytest.mark.parametrize("name", ["search_logreg_digits10_scaled", "search_logreg_digits10_raw"])
+@pytest.mark.filterwarnings("ignore")
+def test_multinomial_oracle_matches_golden(name):
+    """BASELINE config 1 (10-class digits, 4 C x 3 folds): the fixtures hold the scores of the reference's
+    unmodified `_fit_and_score` (tests/golden/make_golden.py --multinomial-only).  The oracle's driver loop
+    reproduces them exactly; on fp32 inputs the restated multinomial solve reproduces the stored
+    coefficients bit for bit."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    dg = load_digits()
+    X = (dg.data / 16).astype(np.float32) if name.endswith("scaled") else dg.data
+    y = dg.target
+    est = LogisticRegression(max_iter=int(g["max_iter"]))
+    cands = [{"C": float(c)} for c in g["C"]]
+    ora = search_oracle.search_cv(est, cands, X, y, cv=3, iid=True)
+    for k in ("split0_test_score", "split1_test_score", "split2_test_score", "mean_test_score", "rank_test_score"):
+        np.testing.assert_array_equal(ora["cv_results_"][k], g[k], err_msg=k)
+    assert ora["best_index_"] == int(g["best_index"])
+    if name.endswith("scaled"):
+        from sklearn.model_selection import StratifiedKFold
+        splits = list(StratifiedKFold(3).split(X, y))
+        for ci, fi in ((0, 0), (2, 1), (3, 2)):
+            tr = splits[fi][0]
+            W, b, it = lo.fit_multinomial_lbfgs(X[tr], y[tr], 10, C=float(g["C"][ci]), max_iter=int(g["max_iter"]))
+            np.testing.assert_array_equal(W, g["coef"][ci, fi, :, :64])
+            np.testing.assert_array_equal(b, g["coef"][ci, fi, :, 64])
+            assert it == g["n_iter"][ci, fi]
