@@ -18,6 +18,10 @@ Pinning status (see DESIGN.md "Oracle"):
   imported unmodified from /root/reference under a 3-line in-memory shim
   (``oracle/refshim.py``), by ``tests/golden/make_golden.py``; its outputs are
   committed as ``tests/golden/*.npz`` and re-checked by ``tests/test_oracle.py``.
+* BASELINE config 1 (10-class digits, multinomial lbfgs) is pinned the same way:
+  ``tests/golden/search_logreg_digits10_{raw,scaled}.npz`` hold the scores of the reference's
+  unmodified ``_fit_and_score`` plus its own run-to-run envelope; ``logreg_oracle.fit_multinomial_lbfgs``
+  reproduces the stored fp32 coefficients bit for bit (``tests/test_oracle.py``).
 * Live pins that need /root/reference (skipped where it is absent): the multi-model search
   against the reference's ``_raw_sampler`` / ``_fit_one_fold`` / ``_get_results``
   (``tests/test_search_host.py``) and the feature eliminator against its ``_fit_and_score_one`` /
