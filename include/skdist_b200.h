@@ -174,6 +174,16 @@ int skd_sgd_fit_batch(skd_ctx* ctx, int32_t B, const int32_t* col_pos, int32_t l
                       int32_t n_iter_no_change, float* coef_out, double* intercept_out,
                       int32_t* n_iter_out, double* t_out, int32_t* status_out, double* gpu_seconds_out);
 
+/* Host-only helper (no CUDA, no context): bootstrap multiplicities and splitter seeds of n_trees trees
+ * from their integer seeds, spread over host threads (n_threads <= 0: all cores, at most 64).
+ * counts_out[t * n + i] = how often row i is drawn by RandomState(seeds[t]).randint(0, n, n) (needed only
+ * when bootstrap != 0); rand_r_out[t] = RandomState(seeds[t]).randint(0, 2^31 - 1).  Bit-identical to numpy's
+ * legacy generator.  Returns 0, 1 if a multiplicity exceeds 255 (device format), 2 on bad arguments.
+ * ref: replaces the per-task `_generate_sample_indices` + `bincount` of ensemble.py:51-55, 97-99 and the seed draw
+ * of SK/tree/_splitter.pyx:155. */
+int skd_bootstrap_counts(int32_t n_trees, const uint32_t* seeds, int64_t n, int32_t bootstrap,
+                         uint8_t* counts_out, uint32_t* rand_r_out, int32_t n_threads);
+
 /* Forest classifier trees, one persistent CTA per tree (depth-first, exact scikit-learn
  * splitter semantics on <= 256 distinct values per feature).  sample_counts[t*n + i] is the
  * bootstrap multiplicity of row i in tree t (the reference's sample_weight, uint8; NULL = no

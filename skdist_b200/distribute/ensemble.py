@@ -21,6 +21,7 @@ from sklearn.tree._tree import NODE_DTYPE, Tree
 from sklearn.utils import check_random_state
 
 from .. import parallel
+from ..bootstrap import bootstrap_counts
 from ..engine import get_engine
 from .base import _parse_partitions, _ScParamMixin
 from .validation import _check_estimator
@@ -209,11 +210,12 @@ class _DistForestClassifier(_ScParamMixin):
         chunk = int(os.environ.get("SKDIST_B200_FOREST_CHUNK", "296"))
         chunks = [my_states[i:i + chunk] for i in range(0, len(my_states), chunk)]
 
+        host_threads = max(1, min(64, (os.cpu_count() or 8) // max(world, 1)))
+
         def prepare(sts):
-            with ThreadPoolExecutor(max_workers=16) as ex:
-                inputs = list(ex.map(lambda st: _tree_inputs(st, n, self.bootstrap), sts))
-            counts = np.stack([c for c, _ in inputs]) if self.bootstrap else None
-            return counts, np.array([r for _, r in inputs], dtype=np.uint32)
+            # bootstrap multiplicities + splitter seeds of a chunk: the library's host threads restate
+            # numpy's legacy generator bit for bit (csrc/bootstrap.cu; `_tree_inputs` is the numpy form)
+            return bootstrap_counts(sts, n, bootstrap=self.bootstrap, n_threads=host_threads)
 
         def build(counts, rs):
             return eng.forest_fit(counts, rs, self.n_classes_, mf_i, max_depth, int(mss), int(msl),

@@ -54,3 +54,21 @@ def test_reference_build_trees_equals_sklearn():
                                   y.astype(np.float64)[:, None], None, s, 3, bootstrap=True)
         np.testing.assert_array_equal(tr.tree_.threshold, t.tree_.threshold)
         np.testing.assert_array_equal(tr.tree_.children_left, t.tree_.children_left)
+
+
+def test_native_bootstrap_counts_equal_numpy():
+    """csrc/bootstrap.cu (host threads, no GPU) vs the numpy form of the reference's per-tree draw
+    (ref ensemble.py:51-55; `_tree_inputs`): bit-identical counts and splitter seeds, edge sizes included."""
+    from skdist_b200.bootstrap import bootstrap_counts
+    from skdist_b200.distribute.ensemble import _tree_inputs
+    rng = np.random.RandomState(3)
+    for n in (1, 2, 5, 255, 4097, 65536, 65537, 300_000):
+        seeds = list(rng.randint(np.iinfo(np.int32).max, size=5)) + [0, 1, 2 ** 31 - 2]
+        counts, rand_r = bootstrap_counts(seeds, n, n_threads=3)
+        for i, s in enumerate(seeds):
+            cw, rw = _tree_inputs(s, n, True)
+            np.testing.assert_array_equal(counts[i], cw)
+            assert rand_r[i] == rw
+        c0, r0 = bootstrap_counts(seeds, n, bootstrap=False)
+        assert c0 is None
+        np.testing.assert_array_equal(r0, rand_r)
