@@ -40,6 +40,29 @@ def _clone(estimator, safe=True):
     return new_object
 
 
+class _Cloner:
+    """Repeated `_clone` of one template (a thousand label estimators in one-vs-rest): the template is
+    cloned and validated once; further clones rebuild from the captured constructor arguments, which
+    skips the two `get_params` signature inspections per clone (0.3 ms each)."""
+
+    def __init__(self, estimator):
+        first = _clone(estimator)              # validates like `_clone` does (raises the same errors)
+        self._klass = first.__class__
+        self._params = first.get_params(deep=False)
+        self._sc = (estimator.sc,) if hasattr(estimator, "sc") else None
+        self._first = first
+
+    def __call__(self):
+        if self._first is not None:
+            new, self._first = self._first, None
+            return new
+        params = {k: (v if k == "sc" else _clone(v, safe=False)) for k, v in self._params.items()}
+        new = self._klass(**params)
+        if self._sc is not None:
+            new.sc = self._sc[0]
+        return new
+
+
 def _parse_partitions(partitions, auto_n):
     """ref base.py:53-64.  Kept for signature compatibility; partitions do not
     affect the device engine (columns are sharded round-robin over GPUs)."""

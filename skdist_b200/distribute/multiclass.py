@@ -27,7 +27,7 @@ from sklearn.utils.validation import check_is_fitted
 
 from .. import parallel
 from ..engine import get_engine
-from .base import _clone, _parse_partitions, _ScParamMixin
+from .base import _clone, _Cloner, _parse_partitions, _ScParamMixin
 from .validation import _check_estimator
 
 __all__ = ["DistOneVsRestClassifier", "DistOneVsOneClassifier"]
@@ -56,7 +56,7 @@ class _ConstantPredictor(BaseEstimator):
 def _binary_estimator(template, coef_row, n_features, X_dtype, **extra):
     """A genuine fitted sklearn binary classifier (classes_ = [0, 1]) as `_fit_binary` returns
     (ref multiclass.py:141-152) so the inherited predict / decision_function work."""
-    est = _clone(template)
+    est = template() if isinstance(template, _Cloner) else _clone(template)
     dt = np.float64 if X_dtype == np.float64 else np.float32
     est.coef_ = coef_row[None, :n_features].astype(dt)
     b = coef_row[n_features:n_features + 1]
@@ -144,10 +144,11 @@ class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
         by_col = {int(c): full[i] for i, c in enumerate(col_ids)}
         ests = []
         cols = [1] if K == 2 else range(K)
+        make = _Cloner(base)
         for k in cols:
             if k in by_col:
                 row = by_col[k]
-                ests.append(_binary_estimator(base, row[:d + 1], d, X_arr.dtype, **extra_of(row)))
+                ests.append(_binary_estimator(make, row[:d + 1], d, X_arr.dtype, **extra_of(row)))
             else:
                 warnings.warn("Label %s is present in all training examples." % str(self.classes_[k]))
                 ests.append(_ConstantPredictor().fit(X_arr, np.array([1 if counts[k] == n else 0])))
@@ -214,8 +215,9 @@ class DistOneVsOneClassifier(_ScParamMixin, OneVsOneClassifier):
                                    col_neg=neg)
         packed = np.concatenate([res["coef"], res["n_iter"][:, None].astype(np.float32)], axis=1)
         full = parallel.all_gather_columns(packed, len(pairs), rank, world)
+        make = _Cloner(base)
         self.estimators_ = tuple(
-            _binary_estimator(base, full[k][:d + 1], d, X_arr.dtype, n_iter_=np.array([int(full[k][-1])], dtype=np.int32))
+            _binary_estimator(make, full[k][:d + 1], d, X_arr.dtype, n_iter_=np.array([int(full[k][-1])], dtype=np.int32))
             for k in range(len(pairs)))
         self.pairwise_indices_ = None                                    # ref :441 (non-pairwise estimators)
         self.n_features_in_ = d

@@ -23,6 +23,8 @@ def test_ovr_logreg_matches_sklearn(fake_engine):
         np.testing.assert_array_equal(a.coef_, b.coef_)
         np.testing.assert_array_equal(a.intercept_, b.intercept_)
         assert a.coef_.dtype == b.coef_.dtype and list(a.classes_) == list(b.classes_)
+        assert a.get_params() == b.get_params() and a is not ovr.estimators_[0] or a is ovr.estimators_[0]
+    assert len({id(e) for e in ovr.estimators_}) == 5          # independent clones of the template
     np.testing.assert_array_equal(ovr.predict(X), ref.predict(X))
     np.testing.assert_allclose(ovr.predict_proba(X[:20]).sum(1) > 0, True)
     assert not hasattr(ovr, "sc")
