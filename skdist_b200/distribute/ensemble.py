@@ -223,7 +223,7 @@ class _DistForestClassifier(_ScParamMixin):
                                   y_regression=y_reg)
 
         def wrap(sts, arrays):
-            with ThreadPoolExecutor(max_workers=8) as ex:
+            with ThreadPoolExecutor(max_workers=min(32, max(8, host_threads))) as ex:   # strided field copies release the GIL
                 return list(ex.map(lambda sa: _make_sklearn_tree(tmpl, sa[0], sa[1], d, self.n_classes_, mf_i,
                                                                  self._tree_cls), zip(sts, arrays)))
 
