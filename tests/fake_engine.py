@@ -135,6 +135,38 @@ class FakeEngine:
             count[j] = m.sum()
         return loss, count
 
+    def forest_fit(self, sample_counts, rand_states, n_classes, max_features, max_depth, min_samples_split,
+                   min_samples_leaf, min_weight_leaf, min_impurity_decrease, splitter=0, y_regression=None):
+        """Trees by scikit-learn itself.  The device receives the splitter seed (rand_r) of every tree; the
+        double maps it back to the tree seed through `seed_of_rand_r` (filled by the test from the seeds the
+        forest draws) and checks that the bootstrap multiplicities it was handed are numpy's for that seed."""
+        from sklearn.tree import DecisionTreeClassifier, DecisionTreeRegressor, ExtraTreeClassifier, ExtraTreeRegressor
+        from sklearn.utils import check_random_state
+        self.calls.append(("forest_fit", len(rand_states)))
+        self.last_forest_seconds = 0.0
+        out = []
+        for t, r in enumerate(rand_states):
+            seed = self.seed_of_rand_r[int(r)]
+            if sample_counts is not None:
+                want = np.bincount(check_random_state(seed).randint(0, self.n, self.n), minlength=self.n)
+                assert np.array_equal(sample_counts[t], want), "bootstrap multiplicities differ from numpy's"
+            reg = y_regression is not None
+            cls = ({0: DecisionTreeRegressor, 1: ExtraTreeRegressor} if reg else
+                   {0: DecisionTreeClassifier, 1: ExtraTreeClassifier})[splitter]
+            est = cls(max_features=max_features, max_depth=None if max_depth >= 2 ** 31 - 1 else max_depth,
+                      min_samples_split=min_samples_split, min_samples_leaf=min_samples_leaf,
+                      min_impurity_decrease=min_impurity_decrease, random_state=seed)
+            sw = None if sample_counts is None else sample_counts[t].astype(np.float64)
+            est.fit(self.X, y_regression if reg else self.y, sample_weight=sw)
+            tr = est.tree_
+            out.append({"left": tr.children_left.astype(np.int32), "right": tr.children_right.astype(np.int32),
+                        "feature": tr.feature.astype(np.int32), "threshold": tr.threshold.copy(),
+                        "impurity": tr.impurity.copy(), "n_node_samples": tr.n_node_samples.astype(np.int32),
+                        "weighted_n_node_samples": tr.weighted_n_node_samples.copy(),
+                        "missing_go_to_left": np.zeros(tr.node_count, np.uint8),
+                        "value": tr.value[:, 0, :].copy(), "max_depth": tr.max_depth})
+        return out
+
     def _rows(self, code):
         if code == -2:
             return np.ones(self.n, bool)

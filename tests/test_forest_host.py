@@ -72,3 +72,40 @@ def test_native_bootstrap_counts_equal_numpy():
         c0, r0 = bootstrap_counts(seeds, n, bootstrap=False)
         assert c0 is None
         np.testing.assert_array_equal(r0, rand_r)
+
+
+@pytest.mark.filterwarnings("ignore")
+@pytest.mark.parametrize("kind", ["rf", "et", "rfr"])
+def test_forest_fit_pipeline_on_engine_double(fake_engine, kind, monkeypatch):
+    """The whole host pipeline of the forest fit (seed draw, chunked bootstrap counts from the native
+    helper, wrapping into scikit-learn trees) on an engine double whose trees are scikit-learn's own:
+    the fitted forest must equal scikit-learn's forest tree for tree."""
+    from sklearn.ensemble import ExtraTreesClassifier, RandomForestClassifier, RandomForestRegressor
+    from sklearn.utils import check_random_state
+    from skdist.distribute.ensemble import (DistExtraTreesClassifier, DistRandomForestClassifier,
+                                            DistRandomForestRegressor)
+    from skdist_b200.distribute.ensemble import MAX_RAND_SEED, _tree_inputs
+    from skdist_b200.datasets import make_multiclass
+    monkeypatch.setenv("SKDIST_B200_FOREST_CHUNK", "3")          # several chunks -> the pipelined path
+    X, y = make_multiclass(400, 6, 3, seed=2)
+    Xq = np.round(X * 8).astype(np.float32)
+    n_trees, rs = 7, 11
+    states = check_random_state(rs).randint(MAX_RAND_SEED, size=n_trees)
+    from skdist_b200.engine import get_engine
+    get_engine().seed_of_rand_r = {int(_tree_inputs(s, len(y), False)[1]): int(s) for s in states}
+    if kind == "rf":
+        ours = DistRandomForestClassifier(n_estimators=n_trees, random_state=rs).fit(Xq, y)
+        ref = RandomForestClassifier(n_estimators=n_trees, random_state=rs).fit(Xq, y)
+    elif kind == "et":
+        ours = DistExtraTreesClassifier(n_estimators=n_trees, random_state=rs).fit(Xq, y)
+        ref = ExtraTreesClassifier(n_estimators=n_trees, random_state=rs).fit(Xq, y)
+    else:
+        yr = (Xq[:, 0] * 2 + Xq[:, 1]).astype(np.float64)
+        ours = DistRandomForestRegressor(n_estimators=n_trees, random_state=rs).fit(Xq, yr)
+        ref = RandomForestRegressor(n_estimators=n_trees, random_state=rs).fit(Xq, yr)
+    assert len(ours.estimators_) == n_trees
+    for a, b in zip(ours.estimators_, ref.estimators_):
+        np.testing.assert_array_equal(a.tree_.threshold, b.tree_.threshold)
+        np.testing.assert_array_equal(a.tree_.children_left, b.tree_.children_left)
+        np.testing.assert_array_equal(a.tree_.value, b.tree_.value)
+    np.testing.assert_array_equal(ours.predict(Xq), ref.predict(Xq))
