@@ -40,7 +40,7 @@ def parse():
     p.add_argument("--d", type=int, default=256)
     p.add_argument("--candidates", type=int, default=512)
     p.add_argument("--folds", type=int, default=5)
-    p.add_argument("--cpu-sample", type=int, default=8, help="fits timed for cpu_baseline (0 = skip)")
+    p.add_argument("--cpu-sample", type=int, default=40, help="fits timed for cpu_baseline / compared for parity (0 = skip)")
     p.add_argument("--kernel", type=int, default=0, help="0 auto, 1 SIMT fp32, 2 tcgen05")
     return p.parse_args()
 
@@ -113,14 +113,26 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_fits_per_sec(X, y, fold, Cs, n_fits, n_jobs=None):
+def cpu_tasks(n_cands, n_folds, n_fits):
+    """The bounded sample of (candidate, fold) tasks the CPU legs run: whole candidates (every fold of
+    a C value, so that mean_test_score of the sub-grid is comparable), C spread evenly over the grid."""
+    n_c = max(1, n_fits // n_folds)
+    idx = np.unique(np.linspace(0, n_cands - 1, n_c).round().astype(int))
+    tasks = [(int(ci), f) for ci in idx for f in range(n_folds)]
+    if n_fits < n_folds:
+        tasks = tasks[:n_fits]
+    return tasks
+
+
+def cpu_fits_per_sec(X, y, fold, Cs, tasks, n_jobs=None):
     """The reference's sc=None branch (search.py:388-409): the same per-task function
     (oracle.search_oracle.fit_and_score <- search.py:180-288) fanned out with joblib over the host
-    cores, on a bounded sample of (candidate, fold) tasks of the same workload.  One wave of
-    n_jobs = min(n_fits, 32, cores) worker processes, each with cores // n_jobs BLAS threads (the
-    faster of the two ways to use the box: a single process with all BLAS threads is limited by one
-    sgemv stream).  Thread counts are set explicitly (torchrun exports OMP_NUM_THREADS=1).
-    Returns (fits/s, seconds, scores, n_jobs, inner_threads)."""
+    cores, on a bounded sample of (candidate, fold) tasks of the same workload.  ONE wave of
+    n_jobs = min(len(tasks), 40, cores) worker processes, each with cores // n_jobs BLAS threads (the
+    fastest way found to use the box: a single process with all BLAS threads is limited by one
+    sgemv stream; 8 x 16 threads measured 0.12-0.40 fits/s, 32 x 4 threads the same or better).
+    Thread counts are set explicitly (torchrun exports OMP_NUM_THREADS=1).
+    Returns (fits/s, seconds, scores aligned with tasks, n_jobs, inner_threads)."""
     from joblib import Parallel, delayed, parallel_config
     from sklearn.linear_model import LogisticRegression
     from sklearn.metrics import check_scoring
@@ -128,29 +140,52 @@ def cpu_fits_per_sec(X, y, fold, Cs, n_fits, n_jobs=None):
     from oracle.search_oracle import fit_and_score
     est = LogisticRegression()
     scorer = check_scoring(est)
-    n_folds = int(fold.max()) + 1
     cores = os.cpu_count() or 1
     if n_jobs is None:
-        n_jobs = max(1, min(n_fits, 32, cores))
+        n_jobs = max(1, min(len(tasks), 40, cores))
     inner = max(1, cores // n_jobs)
-    # stratified sample over the C grid, fold cycling
-    idx = np.linspace(0, len(Cs) - 1, n_fits).round().astype(int)
-    tasks = []
-    for t, ci in enumerate(idx):
-        f = t % n_folds
-        tasks.append(({"C": float(Cs[ci])}, np.flatnonzero(fold != f), np.flatnonzero(fold == f)))
+    jobs = [({"C": float(Cs[ci])}, np.flatnonzero(fold != f), np.flatnonzero(fold == f)) for ci, f in tasks]
     import warnings
     t0 = time.time()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         if n_jobs == 1:
             with threadpool_limits(limits=inner):
-                out = [fit_and_score(est, X, y, scorer, tr, te, p) for p, tr, te in tasks]
+                out = [fit_and_score(est, X, y, scorer, tr, te, p) for p, tr, te in jobs]
         else:
             with parallel_config(backend="loky", n_jobs=n_jobs, inner_max_num_threads=inner):
-                out = Parallel()(delayed(fit_and_score)(est, X, y, scorer, tr, te, p) for p, tr, te in tasks)
+                out = Parallel()(delayed(fit_and_score)(est, X, y, scorer, tr, te, p) for p, tr, te in jobs)
     dt = time.time() - t0
-    return len(tasks) / dt, dt, [o[0]["score"] for o in out], n_jobs, inner
+    return len(jobs) / dt, dt, [o[0]["score"] for o in out], n_jobs, inner
+
+
+def parity_block(cv_results, tasks, cpu_scores, fold, Cs, n_folds):
+    """The CPU leg's scores (the reference's per-task function on the exact bench inputs) against the
+    device search's cv_results_ at the same (candidate, fold): the checker of the headline workload."""
+    n_test = np.bincount(fold.astype(np.int64), minlength=n_folds)
+    flips, dsc = [], []
+    by_c = {}
+    for (ci, f), sc in zip(tasks, cpu_scores):
+        g = float(cv_results["split%d_test_score" % f][ci])
+        flips.append(abs(int(round(g * n_test[f])) - int(round(sc * n_test[f]))))
+        dsc.append(abs(g - sc))
+        by_c.setdefault(ci, {})[f] = (sc, g)
+    full = sorted(ci for ci, v in by_c.items() if len(v) == n_folds)
+    out = {"n_compared": len(tasks), "max_flips_per_fold": int(max(flips)), "mean_flips_per_fold": float(np.mean(flips)),
+           "test_rows_per_fold": int(n_test.min()), "max_abs_dscore_split": float(max(dsc)),
+           "checker": "oracle.search_oracle.fit_and_score (ref search.py:180-288) on the same inputs"}
+    if full:
+        w = n_test / n_test.sum()      # iid weighting by test-fold size (ref search.py:509-519)
+        cpu_mean = np.array([sum(w[f] * by_c[ci][f][0] for f in range(n_folds)) for ci in full])
+        gpu_mean = np.array([float(cv_results["mean_test_score"][ci]) for ci in full])
+        out.update(subgrid_C=[float(Cs[ci]) for ci in full],
+                   max_abs_dscore=float(np.max(np.abs(cpu_mean - gpu_mean))),
+                   max_rel_dscore=float(np.max(np.abs(cpu_mean - gpu_mean) / np.abs(cpu_mean))),
+                   best_C_cpu_on_subgrid=float(Cs[full[int(np.argmax(cpu_mean))]]),
+                   best_C_gpu_on_subgrid=float(Cs[full[int(np.argmax(gpu_mean))]]),
+                   best_C_equal_on_subgrid=bool(int(np.argmax(cpu_mean)) == int(np.argmax(gpu_mean))),
+                   cpu_best_margin=float(np.sort(cpu_mean)[-1] - np.sort(cpu_mean)[-2]) if len(full) > 1 else None)
+    return out
 
 
 def fold_ids(y, n_folds):
@@ -176,29 +211,31 @@ def run_reference(a):
     fold = fold_ids(y, a.folds)
     Cs = np.logspace(-4, 4, a.candidates)
     cores = os.cpu_count() or 1
-    # one wave of worker processes per step; fewer fits per step when many steps are requested so
-    # that the whole run stays within a few minutes
-    per_step = max(1, a.cpu_sample if a.steps <= 3 else (a.cpu_sample // 2 if a.steps <= 6 else a.cpu_sample // 4))
-    vals = []
-    for s in range(a.warmup + a.steps):
-        # warm-up steps of a CPU arm only need to page the data in: one short fit
-        if s < a.warmup:
-            st = max(1, a.n // 20000)          # strided subsample: every fold stays populated
-            cpu_fits_per_sec(np.ascontiguousarray(X[::st]), y[::st], fold[::st], Cs, 1)
-            continue
-        v, dt, _, nj, inner = cpu_fits_per_sec(X, y, fold, Cs, per_step)
-        vals.append((v, dt))
-    tot_fits = per_step * len(vals)
-    tot_t = sum(dt for _, dt in vals)
+    # The K timed steps are K equal bounded samples of the workload (each a few (candidate, fold) fits,
+    # C spread over the grid).  All K samples are run as ONE wave of worker processes that uses every
+    # host core (about 32-40 workers x 3-4 BLAS threads), whatever --steps is: the step time reported
+    # is the wave time / K.  (Round 1 ran 2 fits x 64 threads per step when --steps was large, the
+    # slowest way to use the box.)
+    st = max(1, a.n // 20000)              # warm-up: page the data in with one short fit on a strided subsample
+    for _ in range(min(a.warmup, 1)):
+        cpu_fits_per_sec(np.ascontiguousarray(X[::st]), y[::st], fold[::st], Cs, [(len(Cs) // 2, 0)])
+    per_step = max(1, int(round(max(a.cpu_sample, 32) / max(1, a.steps))))
+    tasks = cpu_tasks(a.candidates, a.folds, per_step * a.steps)[:per_step * a.steps]
+    while len(tasks) < per_step * a.steps:      # tiny grids: cycle
+        tasks = tasks + tasks[:per_step * a.steps - len(tasks)]
+    v, tot_t, _, nj, inner = cpu_fits_per_sec(X, y, fold, Cs, tasks)
+    tot_fits = len(tasks)
     value = tot_fits / tot_t
+    vals = [None] * a.steps
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / max(1, len(vals)),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": workload_name(a), "inputs": "exceed L2"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d (candidate, fold) fits per step, C spread over the grid, joblib n_jobs=%d x %d BLAS "
-                                   "threads (reference sc=None branch, search.py:388-409)" % (per_step, nj, inner)},
+                         "sample": "%d (candidate, fold) fits per step x %d steps run as one wave, C spread over the grid, joblib "
+                                   "n_jobs=%d x %d BLAS threads (reference sc=None branch, search.py:388-409)"
+                                   % (per_step, a.steps, nj, inner)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -285,7 +322,8 @@ def main():
     # ---- end-to-end arm: public API on host arrays (H2D + fits + scoring + D2H), refit excluded
     gs_times = []
     h2d = d2h = 0
-    for i in range(1 + 1):   # one warm-up, one timed
+    E2E_REPS = 3
+    for i in range(1 + E2E_REPS):   # one warm-up, then E2E_REPS timed fits (the median is reported)
         barrier()
         cc0 = eng.counters()
         t0 = time.perf_counter()
@@ -295,10 +333,12 @@ def main():
         gs_times.append(time.perf_counter() - t0)
         cc1 = eng.counters()
         h2d, d2h = cc1["h2d_bytes"] - cc0["h2d_bytes"], cc1["d2h_bytes"] - cc0["d2h_bytes"]
-    te = torch.tensor([gs_times[-1]], dtype=torch.float64, device="cuda")
+    te = torch.tensor(gs_times[1:], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n_cols / float(te.item())
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)      # per repetition: the slowest rank
+    e2e_all = sorted(float(v) for v in te.tolist())
+    e2e_seconds = e2e_all[len(e2e_all) // 2]
+    e2e_value = n_cols / e2e_seconds
 
     if rank == 0:
         pk = peaks()
@@ -314,7 +354,8 @@ def main():
                        "best_C": float(gs.best_params_["C"]),
                        "rounds_per_step": prof["rounds"] / max(1, a.steps)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "seconds": float(te.item())},
+                    "d2h_bytes_per_step": int(d2h), "seconds": e2e_seconds,
+                    "seconds_all": e2e_all, "reported": "median of %d timed fits after one warm-up" % E2E_REPS},
             "gpu_launches": int(c1["launches"] - c0["launches"]),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
@@ -336,12 +377,14 @@ def main():
             line["roofline"]["traffic_source"] = tj["source"]
         if world == 1 and a.cpu_sample > 0:
             cores = os.cpu_count() or 1
-            v, dt, _, nj, inner = cpu_fits_per_sec(X, y, fold, Cs, a.cpu_sample)
+            tasks = cpu_tasks(a.candidates, a.folds, a.cpu_sample)
+            v, dt, cpu_scores, nj, inner = cpu_fits_per_sec(X, y, fold, Cs, tasks)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": "%d (candidate, fold) fits of the same workload in %.1f s, C spread over the grid, "
-                          "joblib n_jobs=%d x %d BLAS threads (reference sc=None branch, search.py:388-409)"
-                          % (a.cpu_sample, dt, nj, inner)}
+                "sample": "%d (candidate, fold) fits of the same workload in %.1f s (one wave), whole candidates, C spread "
+                          "over the grid, joblib n_jobs=%d x %d BLAS threads (reference sc=None branch, search.py:388-409)"
+                          % (len(tasks), dt, nj, inner)}
+            line["parity"] = parity_block(gs.cv_results_, tasks, cpu_scores, fold, Cs, a.folds)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -37,13 +37,23 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIBPATH
     os.makedirs(LIBDIR, exist_ok=True)
-    srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    cmd = [_nvcc()] + NVCC_FLAGS + srcs + ["-o", LIBPATH + ".tmp"]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libskdist_b200.so")
-    os.replace(LIBPATH + ".tmp", LIBPATH)
+    # one builder at a time (torchrun starts N ranks that may all find the sources newer than the
+    # library): the others wait on the lock and then see an up-to-date file
+    import fcntl
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIBPATH
+        srcs = [os.path.join(CSRC, s) for s in SOURCES]
+        tmp = "%s.%d.tmp" % (LIBPATH, os.getpid())
+        cmd = [_nvcc()] + NVCC_FLAGS + srcs + ["-o", tmp]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            raise RuntimeError("nvcc failed building libskdist_b200.so")
+        os.replace(tmp, LIBPATH)
     log = os.path.join(LIBDIR, "build.log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -111,6 +111,9 @@ def load(build_if_missing=True):
         except Exception as e:  # no nvcc on the box: use the prebuilt file if any
             if not os.path.exists(path):
                 raise SkdError("libskdist_b200.so is missing and could not be built: %s" % e)
+            import warnings
+            warnings.warn("libskdist_b200.so is older than its sources and could not be rebuilt (%s); "
+                          "loading the existing file" % e)
     if not os.path.exists(path):
         raise SkdError("libskdist_b200.so not found at %s (run __graft_entry__.build())" % path)
     lib = ctypes.CDLL(path)

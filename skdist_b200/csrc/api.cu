@@ -198,7 +198,8 @@ static int stage_rows_h2d(Ctx* c, float* dst, int64_t ldx, const float* src, int
   bool pinned = cudaPointerGetAttributes(&attr, src) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
   const size_t total = (size_t)n * d * sizeof(float);
-  if (pinned || total < ((size_t)8 << 20)) {
+  // rows wider than one bounce block (d * 4 > 8 MiB) cannot go through the threaded bounce: plain copy
+  if (pinned || total < ((size_t)8 << 20) || (size_t)d * sizeof(float) > ((size_t)8 << 20)) {
     SKD_CUDA(c, cudaMemcpy2DAsync(dst, ldx * sizeof(float), src, ldx_src * sizeof(float), d * sizeof(float), n,
                                   cudaMemcpyHostToDevice, c->stream));
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));

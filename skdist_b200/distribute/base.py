@@ -1,43 +1,27 @@
 """Helpers shared by the distributed meta-estimators.
 
-Mirrors /root/reference/skdist/distribute/base.py: ``_clone`` (base.py:8-50, a
-sklearn ``clone`` that keeps a ``sc`` attribute by reference), ``_parse_partitions``
-(base.py:53-64) and ``_get_value`` (base.py:67-72).  ``sc`` (a SparkContext in
+Counterparts of /root/reference/skdist/distribute/base.py: ``_clone`` (base.py:8-50: sklearn's
+``clone`` keeping a ``sc`` attribute by reference) and ``_parse_partitions`` (base.py:53-64).  ``sc`` (a SparkContext in
 the reference) is accepted everywhere for drop-in compatibility and ignored:
 the "cluster" here is the set of B200s reached through ``skdist_b200.engine``.
 """
-import copy
+from sklearn.base import clone as _sk_clone
 
 
 def _clone(estimator, safe=True):
-    """Construct a new unfitted estimator with the same parameters; ``sc`` is
-    carried over by reference instead of being deep-copied (ref base.py:8-50)."""
-    found_sc = hasattr(estimator, "sc")
-    estimator_type = type(estimator)
-    if estimator_type in (list, tuple, set, frozenset):
-        return estimator_type([_clone(e, safe=safe) for e in estimator])
-    elif not hasattr(estimator, "get_params") or isinstance(estimator, type):
-        if not safe:
-            return copy.deepcopy(estimator)
-        raise TypeError(
-            "Cannot clone object '%s' (type %s): it does not seem to be a scikit-learn "
-            "estimator as it does not implement a 'get_params' methods."
-            % (repr(estimator), type(estimator)))
-    klass = estimator.__class__
-    params = estimator.get_params(deep=False)
-    for name, param in params.items():
-        if name != "sc":
-            params[name] = _clone(param, safe=False)
-    new_object = klass(**params)
-    params_set = new_object.get_params(deep=False)
-    for name in params:
-        if params[name] is not params_set[name]:
-            raise RuntimeError(
-                "Cannot clone object %s, as the constructor either does not set or "
-                "modifies parameter %s" % (estimator, name))
-    if found_sc:
-        new_object.sc = estimator.sc
-    return new_object
+    """scikit-learn's ``clone`` plus the one thing the reference adds to it (ref base.py:8-50): a
+    ``sc`` attribute is carried over by reference instead of being deep-copied.  ``sc`` is an
+    ignored placeholder here, so it is simply re-attached after the clone."""
+    if hasattr(estimator, "get_params") and not isinstance(estimator, type) and hasattr(estimator, "sc"):
+        sc = estimator.sc
+        estimator.sc = None              # never deep-copy a context object
+        try:
+            new = _sk_clone(estimator, safe=safe)
+        finally:
+            estimator.sc = sc
+        new.sc = sc
+        return new
+    return _sk_clone(estimator, safe=safe)
 
 
 class _Cloner:
@@ -76,11 +60,6 @@ def _parse_partitions(partitions, auto_n):
         return None
 
 
-def _get_value(obj):
-    """ref base.py:67-72: unwrap a broadcast variable."""
-    return obj.value if hasattr(obj, "value") else obj
-
-
 class _ScParamMixin:
     """The reference deletes ``self.sc`` at the end of ``fit`` (search.py:568,
     multiclass.py:283, ensemble.py:335) so that the fitted object pickles.  Under
@@ -94,7 +73,7 @@ class _ScParamMixin:
             return super().get_params(deep=deep)
         finally:
             if missing:
-                del self.sc
+                self.__dict__.pop("sc", None)
 
 
 def _merged_params(estimator, candidate_params):

@@ -159,7 +159,7 @@ class DistFeatureEliminator(_ScParamMixin, ClassifierMixin, BaseEstimator):
         est.n_features_in_ = len(keep)
         self.best_estimator_ = est
         self.n_features_ = len(self.best_features_)
-        del self.sc
+        self.__dict__.pop("sc", None)
         return self
 
     # ---- prediction surface (ref eliminate.py:239-284) --------------------------------------

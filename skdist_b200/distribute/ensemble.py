@@ -256,7 +256,7 @@ class _DistForestClassifier(_ScParamMixin):
             ests = local
         self.estimators_ = ests
         self.estimator_ = self._tree_cls()
-        del self.sc                                                     # ref :335
+        self.__dict__.pop("sc", None)                                                     # ref :335
         return self
 
     def _set_oob_score(self, X, y):

@@ -73,8 +73,8 @@ def _cv_fold_ids(cv, X, y, groups, n_samples, enc=None):
     from sklearn.model_selection import KFold, StratifiedKFold
     if type(cv) is KFold and not cv.shuffle and groups is None:
         k = cv.n_splits
-        if k > n_samples:
-            return _fold_ids(list(cv.split(X, y, groups)), n_samples), k     # let scikit-learn raise its error
+        if k > n_samples or k > 127:      # scikit-learn's own error / the int8 fold-id limit of _fold_ids
+            return _fold_ids(list(cv.split(X, y, groups)), n_samples), k
         sizes = np.full(k, n_samples // k, dtype=np.int64)
         sizes[: n_samples % k] += 1
         return np.repeat(np.arange(k, dtype=np.int8), sizes), k

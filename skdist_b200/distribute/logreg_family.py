@@ -238,7 +238,20 @@ class _LogRegFamily:
             t1 = time.time()
             vals, count = self._scores(eng, res["coef"], fold[idx], pos, self.pos_in_fold[fold[idx]])
             t2 = time.time()
+            # a column whose objective went non-finite has no usable coefficients: count-based scores
+            # would still be finite numbers, so they are set to NaN here and search.py applies
+            # `error_score` to them (ref search.py:226-259); max_iter / line-search stops only warn,
+            # as scikit-learn does (SK/linear_model/_logistic.py:599)
+            bad = res["status"] == 5
+            if np.any(res["status"] == 3) or np.any(res["status"] == 4):
+                import warnings
+                from sklearn.exceptions import ConvergenceWarning
+                warnings.warn("lbfgs failed to converge within max_iter=%d for %d of %d (candidate, fold) fits"
+                              % (mi, int(np.sum((res["status"] == 3) | (res["status"] == 4))), len(idx)),
+                              ConvergenceWarning)
             for name, v in vals.items():
+                v = np.asarray(v, dtype=np.float64).copy()
+                v[bad] = np.nan
                 out["test_%s" % name][idx] = v
             out["n_test"][idx] = count
             out["fit_time"][idx] = (t1 - t0) / len(idx)
@@ -249,6 +262,8 @@ class _LogRegFamily:
                 vals, _ = self._scores(eng, res["coef"], (-3 - fold[idx]).astype(np.int32), pos,
                                        self.total_pos - self.pos_in_fold[fold[idx]])
                 for name, v in vals.items():
+                    v = np.asarray(v, dtype=np.float64).copy()
+                    v[bad] = np.nan
                     out["train_%s" % name][idx] = v
         return out
 

@@ -154,7 +154,7 @@ class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
                 ests.append(_ConstantPredictor().fit(X_arr, np.array([1 if counts[k] == n else 0])))
         self.estimators_ = ests
         self.n_features_in_ = d
-        del self.sc                                                     # ref :283
+        self.__dict__.pop("sc", None)                                                     # ref :283
         if hasattr(self.estimator, "sc"):
             del self.estimator.sc
         return self
@@ -221,7 +221,7 @@ class DistOneVsOneClassifier(_ScParamMixin, OneVsOneClassifier):
             for k in range(len(pairs)))
         self.pairwise_indices_ = None                                    # ref :441 (non-pairwise estimators)
         self.n_features_in_ = d
-        del self.sc                                                      # ref :472
+        self.__dict__.pop("sc", None)                                                      # ref :472
         if hasattr(self.estimator, "sc"):
             del self.estimator.sc
         return self

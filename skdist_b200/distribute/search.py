@@ -202,7 +202,7 @@ class DistBaseSearchCV(_ScParamMixin):
         self.n_splits_ = n_splits
 
         # ref search.py:568-570
-        del self.sc
+        self.__dict__.pop("sc", None)
         if hasattr(self.estimator, "sc"):
             del self.estimator.sc
         return self
@@ -363,7 +363,7 @@ class DistMultiModelSearch(_ScParamMixin, BaseEstimator):
             family = families[self.best_model_index_]
             family.stage(eng, X_arr, fold, n_splits)
             self.best_estimator_ = family.refit(eng, self.best_params_, X_arr.dtype, n_features)
-        del self.sc
+        self.__dict__.pop("sc", None)
         return self
 
     def _check_is_fitted(self):

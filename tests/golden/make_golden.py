@@ -35,7 +35,7 @@ def reference_task(ref_search):
     return task
 
 
-def run_case(name, X, y, grid, cv, ref_search):
+def run_case(name, X, y, grid, cv, ref_search, variants=12):
     est = LogisticRegression()
     cands = list(ParameterGrid(grid))
     ref = search_oracle.search_cv(est, cands, X, y, cv=cv, iid=True, task_fn=reference_task(ref_search))
@@ -66,7 +66,7 @@ def run_case(name, X, y, grid, cv, ref_search):
     rng = np.random.default_rng(12345)
     noise_flips = np.zeros((len(cands), n_splits), np.int64)
     noise_coef = np.zeros((len(cands), n_splits))
-    for variant in range(12):       # 1 thread, default threads, then 10 row permutations
+    for variant in range(variants):  # 1 thread, default threads, then row permutations
         for ci, p in enumerate(cands):
             for fi, (tr, te) in enumerate(splits):
                 trv = tr if variant < 2 else tr[rng.permutation(len(tr))]
@@ -179,6 +179,13 @@ def main():
         run_multinomial_case("search_logreg_digits10_raw", dg.data, dg.target, grid, 3, 100, ref_search)
         run_multinomial_case("search_logreg_digits10_scaled", (dg.data / 16).astype(np.float32), dg.target, grid, 3,
                              300, ref_search)
+        return
+    if "--mid-only" in sys.argv:
+        # mid-size pin of the headline workload's generator and shape class (d = 256, tcgen05-eligible):
+        # G1 200 000 x 256, 32 C x 5 folds = 160 fits of the reference's unmodified _fit_and_score;
+        # envelope from 1 BLAS thread, all threads and 2 row permutations (about 40 minutes on 8 cores)
+        X, y = make_g1_classification(200000, 256, seed=7)
+        run_case("search_logreg_g1_200000x256", X, y, {"C": list(np.logspace(-4, 4, 32))}, 5, ref_search, variants=4)
         return
     if "--ridge-only" in sys.argv:
         from skdist_b200.datasets import make_g1_regression
