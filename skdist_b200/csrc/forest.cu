@@ -21,6 +21,7 @@
 
 #include <algorithm>
 
+#include "forest_common.h"
 #include "skd_internal.h"
 
 namespace skd {
@@ -717,6 +718,20 @@ __global__ void fo_bin_col(const float* __restrict__ col, int64_t n, const float
   out[i] = (uint8_t)lo;
 }
 
+// feature-major codes -> row-major [n][dp] (padding columns 0)
+__global__ void fo_rowmajor_kernel(const uint8_t* __restrict__ xbin, int64_t n, int d, int dp, uint8_t* __restrict__ xrow) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (row, 4 features)
+  const int q = dp >> 2;
+  if (idx >= n * q) return;
+  const int64_t r = idx / q;
+  const int f0 = (int)(idx - r * q) * 4;
+  unsigned v = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (f0 + k < d) v |= (unsigned)xbin[(size_t)(f0 + k) * n + r] << (8 * k);
+  reinterpret_cast<unsigned*>(xrow)[idx] = v;
+}
+
 }  // namespace skd
 
 #include <thrust/device_ptr.h>
@@ -729,6 +744,7 @@ void forest_free(Ctx* c) {
   ForestData& f = c->forest;
   if (f.xbin) cudaFree(f.xbin);
   if (f.binval) cudaFree(f.binval);
+  if (f.xrow) cudaFree(f.xrow);
   f = ForestData();
 }
 
@@ -749,6 +765,7 @@ int forest_prepare(Ctx* c) {
   SKD_CUDA(c, sx.alloc(&dn, 1));
   const unsigned g = (unsigned)((n + 255) / 256);
   std::vector<float> hv(FO_BINS);
+  bool well_separated = true;
   for (int f = 0; f < d; ++f) {
     fo_extract_col<<<g, 256, 0, c->stream>>>(c->X, n, ldx, f, col);
     SKD_CUDA(c, cudaMemcpyAsync(srt, col, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->stream));
@@ -768,6 +785,8 @@ int forest_prepare(Ctx* c) {
     for (int i = 0; i < nu; ++i)
       if (hv[i] != hv[i]) return fail(c, "forest: NaN feature values are not supported on the device path");
     std::sort(hv.begin(), hv.begin() + nu);
+    for (int i = 0; i + 1 < nu; ++i)      // the splitter's float32 tie test (SK/tree/_partitioner.pyx:210-214)
+      if (!(hv[i + 1] > hv[i] + FEATURE_THRESHOLD)) well_separated = false;
     for (int i = nu; i < FO_BINS; ++i) hv[i] = INFINITY;
     SKD_CUDA(c, cudaMemcpyAsync(dvals, hv.data(), FO_BINS * 4, cudaMemcpyHostToDevice, c->stream));
     SKD_CUDA(c, cudaMemcpyAsync(fd.binval + (size_t)f * FO_BINS, hv.data(), FO_BINS * 4, cudaMemcpyHostToDevice, c->stream));
@@ -775,13 +794,26 @@ int forest_prepare(Ctx* c) {
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
     c->launches += 3;
   }
+  fd.dp = (d + 15) / 16 * 16;
+  SKD_CUDA(c, cudaMalloc((void**)&fd.xrow, (size_t)n * fd.dp));
+  {
+    const int64_t total = n * (fd.dp / 4);
+    fo_rowmajor_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(fd.xbin, n, d, fd.dp, fd.xrow);
+    c->launches += 1;
+  }
+  fd.well_separated = well_separated;
   SKD_CUDA(c, cudaGetLastError());
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   fd.valid = true;
   return 0;
 }
 
 // Build `n_trees` trees.  counts: [n_trees][n] uint8 host array of bootstrap multiplicities,
 // rand_states: [n_trees] splitter seeds.  Results are delivered tree by tree through `sink`.
+// Two builders: forest_fast.cu (classification, best splitter, <= 4 classes: seven trees per SM)
+// and the general kernel above (two per SM).  Trees are built in rounds of `slots` concurrent
+// trees; the node arrays of a slot hold `node_cap` nodes, sized from the free device memory; a tree
+// that outgrows them (status 1) is rebuilt in a later round with the worst-case capacity 2n - 1.
 int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_states, int n_classes,
                int max_features, int max_depth, int min_samples_split, int min_samples_leaf,
                double min_weight_leaf, double min_impurity_decrease, int random_split, const double* h_yreal,
@@ -794,121 +826,166 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   const int64_t n = c->n;
   const int d = (int)c->d;
   if ((size_t)4 * d * sizeof(int) > 6 * 1024) return fail(c, "forest: device path supports up to 384 features (shared-memory feature permutation)");
-  // slots: concurrent trees per wave, bounded by memory (worst case 2*n nodes per tree)
-  int64_t node_cap = 2 * n;
-  if (const char* e = getenv("SKDIST_B200_FOREST_NODECAP")) {   // experiments: smaller output arrays per tree
+  const bool fast = forest_fast_supported(c, n_classes, reg, random_split);
+  const int stack_cap = 4096;
+  const size_t rec_bytes = fast ? forest_fast_record_bytes(n_classes) : sizeof(FoRecord);
+  const size_t node_bytes = (size_t)(4 * 4 + 1 + 8 * 3 + 8 * n_classes);
+  const size_t slot_fixed = (size_t)n * 17 + (size_t)stack_cap * rec_bytes + 64;   // two sample buffers + counts + stack
+  const int64_t node_cap_max = std::max<int64_t>(2 * n, 16);
+  int64_t node_cap = node_cap_max;
+  if (const char* e = getenv("SKDIST_B200_FOREST_NODECAP")) {   // experiments / tests: smaller output arrays per tree
     const long long v = atoll(e);
     if (v > 0 && v < node_cap) node_cap = v;
   }
-  const size_t per_slot = (size_t)n * 16 + (size_t)node_cap * (4 * 3 + 1 + 8 * 3 + 8 * n_classes) + 4096 * sizeof(FoRecord);
-  size_t free_b = 0, total_b = 0;
-  SKD_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-  int slots = 2 * c->sm_count;
-  if ((size_t)slots * per_slot > free_b / 2) slots = (int)(free_b / 2 / per_slot);
-  if (slots < 1) return fail(c, "forest: not enough device memory for one tree");
-  if (slots > n_trees) slots = n_trees;
-  const int stack_cap = 4096;
-  Scratch sx(c);
-  FoParams P;
-  memset(&P, 0, sizeof(P));
-  uint8_t* dcounts; uint32_t* drs;
-  SKD_CUDA(c, sx.alloc(&dcounts, (size_t)slots * n));
-  SKD_CUDA(c, sx.alloc(&drs, (size_t)slots));
-  SKD_CUDA(c, sx.alloc(&P.samp, (size_t)slots * n));
-  SKD_CUDA(c, sx.alloc(&P.samp_tmp, (size_t)slots * n));
-  SKD_CUDA(c, sx.alloc(&P.stack, (size_t)slots * stack_cap));
-  SKD_CUDA(c, sx.alloc(&P.o_left, (size_t)slots * node_cap));
-  SKD_CUDA(c, sx.alloc(&P.o_right, (size_t)slots * node_cap));
-  SKD_CUDA(c, sx.alloc(&P.o_feature, (size_t)slots * node_cap));
-  SKD_CUDA(c, sx.alloc(&P.o_nsamp, (size_t)slots * node_cap));
-  SKD_CUDA(c, sx.alloc(&P.o_mgl, (size_t)slots * node_cap));
-  SKD_CUDA(c, sx.alloc(&P.o_thr, (size_t)slots * node_cap));
-  SKD_CUDA(c, sx.alloc(&P.o_imp, (size_t)slots * node_cap));
-  SKD_CUDA(c, sx.alloc(&P.o_wn, (size_t)slots * node_cap));
-  SKD_CUDA(c, sx.alloc(&P.o_val, (size_t)slots * node_cap * n_classes));
-  SKD_CUDA(c, sx.alloc(&P.o_count, (size_t)slots));
-  SKD_CUDA(c, sx.alloc(&P.o_maxdepth, (size_t)slots));
-  SKD_CUDA(c, sx.alloc(&P.o_status, (size_t)slots));
-  const bool want_prof = getenv("SKDIST_B200_FOREST_PROF") != nullptr;
-  P.o_prof = nullptr;
-  long long* d_prof = nullptr;
-  if (want_prof) SKD_CUDA(c, sx.alloc(&d_prof, (size_t)slots * 16));
-  P.xbin = c->forest.xbin; P.binval = c->forest.binval; P.ycls = c->ycls;
+  const bool want_prof = !fast && getenv("SKDIST_B200_FOREST_PROF") != nullptr;
+  double* dy = nullptr;
+  Scratch sy(c);
   if (reg) {
-    double* dy;
-    SKD_CUDA(c, sx.alloc(&dy, (size_t)n));
+    SKD_CUDA(c, sy.alloc(&dy, (size_t)n));
     SKD_CUDA(c, cudaMemcpyAsync(dy, h_yreal, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     c->h2d += n * 8;
-    P.yreal = dy;
   }
-  P.n = n; P.d = d; P.n_classes = n_classes;
-  P.max_features = max_features; P.max_depth = max_depth; P.min_samples_split = min_samples_split;
-  P.min_samples_leaf = min_samples_leaf; P.min_weight_leaf = min_weight_leaf;
-  P.min_impurity_decrease = min_impurity_decrease;
-  P.random_split = random_split ? 1 : 0;
-  P.counts = dcounts; P.rand_state = drs; P.stack_cap = stack_cap; P.node_cap = node_cap;
-  P.o_prof = d_prof;
-  const size_t smem = (size_t)2 * d * sizeof(int) + (size_t)(d + 16) * sizeof(int2) +
-                      (size_t)FO_KB_MAX * FO_BINS * sizeof(float) + (size_t)FO_SSTK * sizeof(FoRecord);
-  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<FO_MAXC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  std::vector<int32_t> hcount(slots), hdepth(slots), hstatus(slots);
-  SkdTreeView view;
+  const size_t smem_general = (size_t)2 * d * sizeof(int) + (size_t)(d + 16) * sizeof(int2) +
+                              (size_t)FO_KB_MAX * FO_BINS * sizeof(float) + (size_t)FO_SSTK * sizeof(FoRecord);
+  if (!fast) {
+    SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_general));
+    SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_general));
+    SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_general));
+    SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<FO_MAXC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_general));
+    SKD_CUDA(c, cudaFuncSetAttribute(forest_build_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_general));
+  }
+  std::vector<int> pending(n_trees);
+  for (int t = 0; t < n_trees; ++t) pending[t] = t;
   std::vector<int32_t> hl, hr, hf, hn; std::vector<uint8_t> hm; std::vector<double> ht, hi, hw, hv;
-  for (int t0 = 0; t0 < n_trees; t0 += slots) {
-    const int nt = std::min(slots, n_trees - t0);
-    if (counts) {
-      SKD_CUDA(c, cudaMemcpyAsync(dcounts, counts + (size_t)t0 * n, (size_t)nt * n, cudaMemcpyHostToDevice, c->stream));
-    } else {   // no bootstrap: every row once
-      SKD_CUDA(c, cudaMemsetAsync(dcounts, 1, (size_t)nt * n, c->stream));
+  for (int round = 0; !pending.empty(); ++round) {
+    // slots: concurrent trees of this round, bounded by the resident builders and by memory
+    size_t free_b = 0, total_b = 0;
+    SKD_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+    free_b += c->pool_bytes;                       // idle pooled blocks are reusable
+    int slots = (fast ? forest_fast_slots_per_sm() : 2) * c->sm_count;
+    if (slots > (int)pending.size()) slots = (int)pending.size();
+    const size_t budget = (size_t)((double)free_b * 0.85);
+    if (round == 0 && fast && node_cap == node_cap_max) {
+      // the node arrays get what the fixed per-tree buffers leave; real trees are far below 2n nodes
+      if ((size_t)slots * slot_fixed < budget) {
+        const int64_t cap = (int64_t)((budget - (size_t)slots * slot_fixed) / ((size_t)slots * node_bytes));
+        node_cap = std::max<int64_t>(4096, std::min<int64_t>(node_cap_max, cap));
+      }
     }
-    SKD_CUDA(c, cudaMemcpyAsync(drs, rand_states + t0, (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
-    c->h2d += (int64_t)nt * n;
-    P.n_trees = nt;
-    if (reg) forest_build_kernel<4, true><<<nt, FO_THREADS, smem, c->stream>>>(P);
-    else if (n_classes <= 2) forest_build_kernel<2, false><<<nt, FO_THREADS, smem, c->stream>>>(P);
-    else if (n_classes <= 4) forest_build_kernel<4, false><<<nt, FO_THREADS, smem, c->stream>>>(P);
-    else if (n_classes <= 8) forest_build_kernel<8, false><<<nt, FO_THREADS, smem, c->stream>>>(P);
-    else forest_build_kernel<FO_MAXC, false><<<nt, FO_THREADS, smem, c->stream>>>(P);
-    c->launches += 1;
-    SKD_CUDA(c, cudaGetLastError());
-    SKD_CUDA(c, cudaMemcpyAsync(hcount.data(), P.o_count, nt * 4, cudaMemcpyDeviceToHost, c->stream));
-    SKD_CUDA(c, cudaMemcpyAsync(hdepth.data(), P.o_maxdepth, nt * 4, cudaMemcpyDeviceToHost, c->stream));
-    SKD_CUDA(c, cudaMemcpyAsync(hstatus.data(), P.o_status, nt * 4, cudaMemcpyDeviceToHost, c->stream));
-    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (want_prof) {
-      std::vector<long long> hp((size_t)nt * 16);
-      cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost);
-      static const char* nm[12] = {"pop", "speculate", "zero+stage", "histogram", "scan", "commit", "restore+improve", "partition", "add_node+push", "-", "loop barrier", "-"};
-      double tot = 0; for (int i = 0; i < 12; ++i) tot += (double)hp[i];
-      for (int i = 0; i < 12; ++i) if (hp[i]) fprintf(stderr, "[skd forest prof] tree 0 %-16s %12lld cycles %5.1f%%  (%.0f per node)\n", nm[i], hp[i], 100.0 * hp[i] / tot, (double)hp[i] / hcount[0]);
-    }
-    for (int s = 0; s < nt; ++s) {
-      if (hstatus[s] != 0) return fail(c, hstatus[s] == 1 ? "forest: node capacity exceeded" : "forest: builder stack capacity exceeded");
-      const int m = hcount[s];
-      hl.resize(m); hr.resize(m); hf.resize(m); hn.resize(m); hm.resize(m); ht.resize(m); hi.resize(m); hw.resize(m);
-      hv.resize((size_t)m * n_classes);
-      const size_t o = (size_t)s * node_cap;
-      SKD_CUDA(c, cudaMemcpyAsync(hl.data(), P.o_left + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
-      SKD_CUDA(c, cudaMemcpyAsync(hr.data(), P.o_right + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
-      SKD_CUDA(c, cudaMemcpyAsync(hf.data(), P.o_feature + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
-      SKD_CUDA(c, cudaMemcpyAsync(hn.data(), P.o_nsamp + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
-      SKD_CUDA(c, cudaMemcpyAsync(hm.data(), P.o_mgl + o, m, cudaMemcpyDeviceToHost, c->stream));
-      SKD_CUDA(c, cudaMemcpyAsync(ht.data(), P.o_thr + o, m * 8, cudaMemcpyDeviceToHost, c->stream));
-      SKD_CUDA(c, cudaMemcpyAsync(hi.data(), P.o_imp + o, m * 8, cudaMemcpyDeviceToHost, c->stream));
-      SKD_CUDA(c, cudaMemcpyAsync(hw.data(), P.o_wn + o, m * 8, cudaMemcpyDeviceToHost, c->stream));
-      SKD_CUDA(c, cudaMemcpyAsync(hv.data(), P.o_val + o * n_classes, (size_t)m * n_classes * 8, cudaMemcpyDeviceToHost, c->stream));
+    const size_t per_slot = slot_fixed + (size_t)node_cap * node_bytes;
+    if ((size_t)slots * per_slot > budget) slots = (int)(budget / per_slot);
+    if (slots < 1) return fail(c, "forest: not enough device memory for one tree");
+    Scratch sx(c);
+    FoParams P;
+    memset(&P, 0, sizeof(P));
+    uint8_t* dcounts; uint32_t* drs; void* dstack;
+    SKD_CUDA(c, sx.alloc(&dcounts, (size_t)slots * n));
+    SKD_CUDA(c, sx.alloc(&drs, (size_t)slots));
+    SKD_CUDA(c, sx.alloc(&P.samp, (size_t)slots * n));
+    SKD_CUDA(c, sx.alloc(&P.samp_tmp, (size_t)slots * n));
+    SKD_CUDA(c, sx.alloc((uint8_t**)&dstack, (size_t)slots * stack_cap * rec_bytes));
+    SKD_CUDA(c, sx.alloc(&P.o_left, (size_t)slots * node_cap));
+    SKD_CUDA(c, sx.alloc(&P.o_right, (size_t)slots * node_cap));
+    SKD_CUDA(c, sx.alloc(&P.o_feature, (size_t)slots * node_cap));
+    SKD_CUDA(c, sx.alloc(&P.o_nsamp, (size_t)slots * node_cap));
+    SKD_CUDA(c, sx.alloc(&P.o_mgl, (size_t)slots * node_cap));
+    SKD_CUDA(c, sx.alloc(&P.o_thr, (size_t)slots * node_cap));
+    SKD_CUDA(c, sx.alloc(&P.o_imp, (size_t)slots * node_cap));
+    SKD_CUDA(c, sx.alloc(&P.o_wn, (size_t)slots * node_cap));
+    SKD_CUDA(c, sx.alloc(&P.o_val, (size_t)slots * node_cap * n_classes));
+    SKD_CUDA(c, sx.alloc(&P.o_count, (size_t)slots));
+    SKD_CUDA(c, sx.alloc(&P.o_maxdepth, (size_t)slots));
+    SKD_CUDA(c, sx.alloc(&P.o_status, (size_t)slots));
+    long long* d_prof = nullptr;
+    if (want_prof) SKD_CUDA(c, sx.alloc(&d_prof, (size_t)slots * 16));
+    P.stack = (FoRecord*)dstack;
+    P.xbin = c->forest.xbin; P.binval = c->forest.binval; P.ycls = c->ycls; P.yreal = dy;
+    P.n = n; P.d = d; P.n_classes = n_classes;
+    P.max_features = max_features; P.max_depth = max_depth; P.min_samples_split = min_samples_split;
+    P.min_samples_leaf = min_samples_leaf; P.min_weight_leaf = min_weight_leaf;
+    P.min_impurity_decrease = min_impurity_decrease;
+    P.random_split = random_split ? 1 : 0;
+    P.counts = dcounts; P.rand_state = drs; P.stack_cap = stack_cap; P.node_cap = node_cap;
+    P.o_prof = d_prof;
+    FfParams F;
+    memset(&F, 0, sizeof(F));
+    F.xrow = c->forest.xrow; F.ycls = c->ycls; F.n = n; F.d = d; F.dp = c->forest.dp; F.n_classes = n_classes;
+    F.max_features = max_features; F.max_depth = max_depth; F.min_samples_split = min_samples_split;
+    F.min_samples_leaf = min_samples_leaf; F.min_weight_leaf = min_weight_leaf;
+    F.min_impurity_decrease = min_impurity_decrease;
+    F.counts = dcounts; F.rand_state = drs; F.samp = P.samp; F.samp_tmp = P.samp_tmp; F.stack = dstack;
+    F.stack_cap = stack_cap; F.node_cap = node_cap;
+    F.o_left = P.o_left; F.o_right = P.o_right; F.o_feature = P.o_feature; F.o_nsamp = P.o_nsamp; F.o_mgl = P.o_mgl;
+    F.o_thr = P.o_thr; F.o_imp = P.o_imp; F.o_wn = P.o_wn; F.o_val = P.o_val;
+    F.o_count = P.o_count; F.o_maxdepth = P.o_maxdepth; F.o_status = P.o_status;
+    std::vector<int32_t> hcount(slots), hdepth(slots), hstatus(slots);
+    std::vector<uint32_t> hrs(slots);
+    std::vector<int> failed;
+    SkdTreeView view;
+    for (size_t p0 = 0; p0 < pending.size(); p0 += slots) {
+      const int nt = (int)std::min<size_t>(slots, pending.size() - p0);
+      const bool contiguous = pending[p0 + nt - 1] - pending[p0] == nt - 1;
+      if (!counts) {   // no bootstrap: every row once
+        SKD_CUDA(c, cudaMemsetAsync(dcounts, 1, (size_t)nt * n, c->stream));
+      } else if (contiguous) {
+        SKD_CUDA(c, cudaMemcpyAsync(dcounts, counts + (size_t)pending[p0] * n, (size_t)nt * n, cudaMemcpyHostToDevice, c->stream));
+      } else {
+        for (int s = 0; s < nt; ++s)
+          SKD_CUDA(c, cudaMemcpyAsync(dcounts + (size_t)s * n, counts + (size_t)pending[p0 + s] * n, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+      }
+      for (int s = 0; s < nt; ++s) hrs[s] = rand_states[pending[p0 + s]];
+      SKD_CUDA(c, cudaMemcpyAsync(drs, hrs.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
+      c->h2d += (int64_t)nt * n;
+      P.n_trees = nt;
+      if (fast) {
+        if (forest_fast_launch(c, F, nt)) return 1;
+      } else {
+        if (reg) forest_build_kernel<4, true><<<nt, FO_THREADS, smem_general, c->stream>>>(P);
+        else if (n_classes <= 2) forest_build_kernel<2, false><<<nt, FO_THREADS, smem_general, c->stream>>>(P);
+        else if (n_classes <= 4) forest_build_kernel<4, false><<<nt, FO_THREADS, smem_general, c->stream>>>(P);
+        else if (n_classes <= 8) forest_build_kernel<8, false><<<nt, FO_THREADS, smem_general, c->stream>>>(P);
+        else forest_build_kernel<FO_MAXC, false><<<nt, FO_THREADS, smem_general, c->stream>>>(P);
+        c->launches += 1;
+      }
+      SKD_CUDA(c, cudaGetLastError());
+      SKD_CUDA(c, cudaMemcpyAsync(hcount.data(), P.o_count, nt * 4, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(hdepth.data(), P.o_maxdepth, nt * 4, cudaMemcpyDeviceToHost, c->stream));
+      SKD_CUDA(c, cudaMemcpyAsync(hstatus.data(), P.o_status, nt * 4, cudaMemcpyDeviceToHost, c->stream));
       SKD_CUDA(c, cudaStreamSynchronize(c->stream));
-      c->d2h += (int64_t)m * (4 * 4 + 1 + 8 * 3 + 8 * n_classes);
-      view.node_count = m; view.max_depth = hdepth[s]; view.n_classes = n_classes;
-      view.left = hl.data(); view.right = hr.data(); view.feature = hf.data(); view.n_node_samples = hn.data();
-      view.missing_go_to_left = hm.data(); view.threshold = ht.data(); view.impurity = hi.data();
-      view.weighted_n_node_samples = hw.data(); view.value = hv.data();
-      sink(sink_arg, t0 + s, &view);
+      if (want_prof) {
+        std::vector<long long> hp((size_t)nt * 16);
+        cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost);
+        static const char* nm[12] = {"pop", "speculate", "zero+stage", "histogram", "scan", "commit", "restore+improve", "partition", "add_node+push", "-", "loop barrier", "-"};
+        double tot = 0; for (int i = 0; i < 12; ++i) tot += (double)hp[i];
+        for (int i = 0; i < 12; ++i) if (hp[i]) fprintf(stderr, "[skd forest prof] tree 0 %-16s %12lld cycles %5.1f%%  (%.0f per node)\n", nm[i], hp[i], 100.0 * hp[i] / tot, (double)hp[i] / hcount[0]);
+      }
+      for (int s = 0; s < nt; ++s) {
+        if (hstatus[s] == 1 && node_cap < node_cap_max) { failed.push_back(pending[p0 + s]); continue; }
+        if (hstatus[s] != 0) return fail(c, hstatus[s] == 1 ? "forest: node capacity exceeded" : "forest: builder stack capacity exceeded");
+        const int m = hcount[s];
+        hl.resize(m); hr.resize(m); hf.resize(m); hn.resize(m); hm.resize(m); ht.resize(m); hi.resize(m); hw.resize(m);
+        hv.resize((size_t)m * n_classes);
+        const size_t o = (size_t)s * node_cap;
+        SKD_CUDA(c, cudaMemcpyAsync(hl.data(), P.o_left + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
+        SKD_CUDA(c, cudaMemcpyAsync(hr.data(), P.o_right + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
+        SKD_CUDA(c, cudaMemcpyAsync(hf.data(), P.o_feature + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
+        SKD_CUDA(c, cudaMemcpyAsync(hn.data(), P.o_nsamp + o, m * 4, cudaMemcpyDeviceToHost, c->stream));
+        SKD_CUDA(c, cudaMemcpyAsync(hm.data(), P.o_mgl + o, m, cudaMemcpyDeviceToHost, c->stream));
+        SKD_CUDA(c, cudaMemcpyAsync(ht.data(), P.o_thr + o, m * 8, cudaMemcpyDeviceToHost, c->stream));
+        SKD_CUDA(c, cudaMemcpyAsync(hi.data(), P.o_imp + o, m * 8, cudaMemcpyDeviceToHost, c->stream));
+        SKD_CUDA(c, cudaMemcpyAsync(hw.data(), P.o_wn + o, m * 8, cudaMemcpyDeviceToHost, c->stream));
+        SKD_CUDA(c, cudaMemcpyAsync(hv.data(), P.o_val + o * n_classes, (size_t)m * n_classes * 8, cudaMemcpyDeviceToHost, c->stream));
+        SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->d2h += (int64_t)m * (4 * 4 + 1 + 8 * 3 + 8 * n_classes);
+        view.node_count = m; view.max_depth = hdepth[s]; view.n_classes = n_classes;
+        view.left = hl.data(); view.right = hr.data(); view.feature = hf.data(); view.n_node_samples = hn.data();
+        view.missing_go_to_left = hm.data(); view.threshold = ht.data(); view.impurity = hi.data();
+        view.weighted_n_node_samples = hw.data(); view.value = hv.data();
+        sink(sink_arg, pending[p0 + s], &view);
+      }
     }
+    pending.swap(failed);
+    node_cap = node_cap_max;      // trees that outgrew their arrays: worst-case capacity, fewer at a time
   }
   return 0;
 }

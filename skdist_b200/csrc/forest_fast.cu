@@ -1,0 +1,775 @@
+// forest_fast.cu -- the throughput build of the exact depth-first tree builder (classification,
+// best splitter): every tree of a forest resident at once, seven 128-thread builders per SM.
+//
+// Same contract as forest.cu (which stays the general kernel: regression, random splitter, many
+// classes): the host draws what the reference's per-tree task `_build_trees` draws
+// (ref ensemble.py:68-109), the kernel replays
+//   SK/tree/_tree.pyx:139-337      DepthFirstTreeBuilder.build
+//   SK/tree/_splitter.pyx:262-504  node_split_best (one xorshift stream per tree, Fisher-Yates
+//                                  feature draws, constant-feature bookkeeping, strict '>')
+//   SK/tree/_criterion.pyx:605-680 Gini in float64, scikit-learn's operation order
+// and the trees are bit-identical to scikit-learn's.
+//
+// Why a second kernel.  A config-4 tree (2M x 64, 1.26M distinct rows) has 372k nodes; 110k of its
+// 184k internal nodes hold <= 32 samples and 58k more hold <= 256; the 1000 nodes above 4096
+// samples carry half of all sample visits but none of the time.  The RNG stream makes the nodes of
+// one tree strictly sequential, so throughput = (trees in flight) / (latency per node):
+//   * 7 builders per SM (128 threads, <= 72 registers, 28 KB shared memory): all 1024 trees of the
+//     headline forest run concurrently (the general kernel holds 2 per SM);
+//   * a subtree of <= S samples (S = 256 at d = 64) is STAGED: the bin codes of its rows (row-major
+//     copy of the binned matrix, 64 B per row) are copied to shared memory once, and the whole
+//     subtree -- 9 nodes in 10 -- is then built without touching global memory except for the node
+//     records it emits;
+//   * staged nodes of <= 32 samples skip the 256-bin histogram: one warp ranks the node's samples of
+//     a feature against each other (shuffle all-pairs count: left class weights and sample count of
+//     every candidate threshold in one packed integer add per pair);
+//   * larger staged nodes build packed 16-bit histograms (sum of <= 256 weights of <= 255 fits);
+//   * nodes above S samples gather from the row-major codes (all drawn features of a sample sit in
+//     the same 64 bytes) into 32-bit shared-memory histograms and ping-pong between two sample
+//     buffers instead of copying the partition back.
+// Requirements checked by the host (else forest.cu runs): n_classes <= 4, d <= 255, every feature's
+// distinct values more than 1e-7 apart (then "constant" == one present bin and every pair of
+// adjacent present bins is a candidate, SK/tree/_partitioner.pyx:210-214), n * 255 < 2^32.
+// No tensor cores: integer histogramming and float64 Gini arithmetic.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "forest_common.h"
+#include "skd_internal.h"
+
+namespace skd {
+
+constexpr int FF_THREADS = 128;
+constexpr int FF_WARPS = FF_THREADS / 32;
+constexpr int FF_KB = 8;          // speculative feature draws per batch (unstaged nodes, small staged nodes)
+constexpr int FF_KBM = 4;         // ... for staged histogram nodes: one feature per warp
+constexpr int FF_SSTK = 64;       // builder-stack entries kept in shared memory
+constexpr int FF_SMALL = 32;      // staged nodes up to this size take the ranking path
+constexpr double FF_EPSILON = 2.220446049250313e-16;
+
+template <int CM>
+struct __align__(8) FfRec {       // builder stack record (SK/tree/_tree.pyx StackRecord) + the node's class sums
+  int32_t start, end, depth, parent;
+  int32_t flags;                  // n_const [0,16) | is_left bit 16 | sample buffer bit 17
+  uint32_t sums[CM];
+  int32_t pad_;
+  double impurity;
+};
+struct FfItem {                   // one speculatively drawn feature + the simulation state right after its draw
+  int f, fj, nv, nd, fi, ulen;
+  uint32_t rs;
+  int pad_;
+};
+template <int CM>
+struct __align__(8) FfResult {    // best split of one feature in the current node
+  double proxy;
+  int n_left;
+  int code;                       // bin_a | bin_b << 8 | is_const << 16
+  uint32_t sl[CM];
+};
+
+// packed accumulators of the ranking path: class weights in 13-bit fields (32 samples x 255 < 2^13),
+// the sample count above them
+template <int CM> struct FfAcc { typedef unsigned long long T; static constexpr int CNT = 13 * CM; };
+template <> struct FfAcc<2> { typedef unsigned int T; static constexpr int CNT = 26; };
+
+__device__ __forceinline__ uint32_t ff_rand_r(uint32_t* seed) {   // SK/utils/_random.pxd:20-34
+  if (*seed == 0) *seed = 1;
+  *seed ^= (uint32_t)(*seed << 13);
+  *seed ^= (uint32_t)(*seed >> 17);
+  *seed ^= (uint32_t)(*seed << 5);
+  return *seed % ((uint32_t)2147483647 + 1);
+}
+__device__ __forceinline__ int ff_rand_int(int low, int high, uint32_t* seed) {
+  return low + (int)(ff_rand_r(seed) % (uint32_t)(high - low));
+}
+
+// proxy_impurity_improvement of the Gini criterion for left sums sl, node sums st
+// (SK/tree/_criterion.pyx:147-163, 650-680): -w_r * gini_r - w_l * gini_l, no FMA contraction
+template <int CM>
+__device__ __forceinline__ double ff_proxy(const uint32_t* sl, const uint32_t* st, int C, double wl, double wr,
+                                           double* il_out, double* ir_out) {
+  double sql = 0.0, sqr = 0.0;
+#pragma unroll
+  for (int c = 0; c < CM; ++c) {
+    if (c < C) {
+      const double a = (double)sl[c], b = (double)(st[c] - sl[c]);
+      sql = __dadd_rn(sql, __dmul_rn(a, a));
+      sqr = __dadd_rn(sqr, __dmul_rn(b, b));
+    }
+  }
+  const double il = __dsub_rn(1.0, __ddiv_rn(sql, __dmul_rn(wl, wl)));
+  const double ir = __dsub_rn(1.0, __ddiv_rn(sqr, __dmul_rn(wr, wr)));
+  if (il_out) { *il_out = il; *ir_out = ir; }
+  return __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
+}
+
+// One warp scans the 256 bins of one feature's histogram (8 bins per lane, ascending) and leaves the
+// feature's best split in *R.  HC(c, bin) = weight of class c in the bin, HN(bin) = samples in the bin.
+template <int CM, class HC, class HN>
+__device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_node, const uint32_t* st, double w_node,
+                                        int min_samples_leaf, double min_weight_leaf, FfResult<CM>* R) {
+  unsigned cntb[8];
+  unsigned ltot = 0, pmask = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { cntb[j] = hn(lane * 8 + j); ltot += cntb[j]; if (cntb[j]) pmask |= 1u << j; }
+  unsigned pre = ltot;   // exclusive prefix of the sample counts over lanes
+  for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
+  pre -= ltot;
+  uint32_t sl[CM];       // class weights left of this lane's first bin
+#pragma unroll
+  for (int c = 0; c < CM; ++c) {
+    sl[c] = 0;
+    if (c < C) {
+      uint32_t t = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += hc(c, lane * 8 + j);
+      uint32_t incl = t;
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+      sl[c] = incl - t;
+    }
+  }
+  // first present bin of the lanes above this one
+  const int myfirst = pmask ? lane * 8 + __ffs(pmask) - 1 : 1 << 20;
+  int run = myfirst;
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_down_sync(0xffffffffu, run, o); if (lane + o < 32) run = min(run, u); }
+  const int nx = __shfl_down_sync(0xffffffffu, run, 1);
+  const int nxt = lane < 31 ? nx : (1 << 20);
+  const int gfirst = __reduce_min_sync(0xffffffffu, myfirst);
+  const int mylast = pmask ? lane * 8 + 31 - __clz(pmask) : -1;
+  const int glast = __reduce_max_sync(0xffffffffu, mylast);
+  const bool is_const = glast <= gfirst;      // distinct values are > 1e-7 apart (host check): one bin == constant
+  double bproxy = -INFINITY;
+  int bnl = 1 << 30, bbin = 0, bnext = 0;
+  uint32_t bsl[CM];
+#pragma unroll
+  for (int c = 0; c < CM; ++c) bsl[c] = 0;
+  if (!is_const) {
+    unsigned run_cnt = pre;
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+      if (!cntb[j]) continue;
+      const int bb = lane * 8 + j;
+      run_cnt += cntb[j];
+#pragma unroll
+      for (int c = 0; c < CM; ++c) if (c < C) sl[c] += hc(c, bb);
+      const unsigned higher = pmask & ~((2u << j) - 1u);
+      const int nb2 = higher ? lane * 8 + __ffs(higher) - 1 : nxt;
+      if (nb2 >= (1 << 20)) continue;                             // last present bin: no boundary above it
+      const int n_left = (int)run_cnt, n_right = n_node - n_left;
+      if (n_left < min_samples_leaf || n_right < min_samples_leaf) continue;
+      double wl = 0.0;
+#pragma unroll
+      for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
+      const double wr = w_node - wl;
+      if (wl < min_weight_leaf || wr < min_weight_leaf) continue;
+      const double proxy = ff_proxy<CM>(sl, st, C, wl, wr, nullptr, nullptr);
+      if (proxy > bproxy) {
+        bproxy = proxy; bnl = n_left; bbin = bb; bnext = nb2;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) bsl[c] = sl[c];
+      }
+    }
+  }
+  // warp arg-max; ties keep the smallest position (the sequential scan's strict '>')
+  double wp = bproxy; int wnl = bnl;
+  for (int o = 16; o > 0; o >>= 1) {
+    const double op = __shfl_xor_sync(0xffffffffu, wp, o);
+    const int onl = __shfl_xor_sync(0xffffffffu, wnl, o);
+    if (op > wp || (op == wp && onl < wnl)) { wp = op; wnl = onl; }
+  }
+  if (lane == 0) { R->proxy = wp; R->n_left = wnl; R->code = is_const ? (1 << 16) : 0; }
+  __syncwarp();
+  if (bnl == wnl && bproxy == wp && wp > -INFINITY) {   // exactly one lane: positions are unique per bin
+    R->code = bbin | (bnext << 8);
+#pragma unroll
+    for (int c = 0; c < CM; ++c) R->sl[c] = bsl[c];
+  }
+}
+
+template <int CM>
+__global__ void __launch_bounds__(FF_THREADS, 7)
+forest_fast_kernel(const FfParams P) {
+  typedef typename FfAcc<CM>::T acc_t;
+  constexpr int CNT = FfAcc<CM>::CNT;
+  const int slot = blockIdx.x;
+  if (slot >= P.n_trees) return;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int C = P.n_classes, d = P.d, dp = P.dp;
+  const int64_t n = P.n;
+  uint2* sbuf[2] = {P.samp + (size_t)slot * n, P.samp_tmp + (size_t)slot * n};
+  FfRec<CM>* gstack = reinterpret_cast<FfRec<CM>*>(P.stack) + (size_t)slot * P.stack_cap;
+  const uint8_t* cnt = P.counts + (size_t)slot * n;
+  const int64_t nb = (int64_t)slot * P.node_cap;
+
+  // ---- shared memory ----
+  extern __shared__ __align__(16) unsigned char ff_sm[];
+  unsigned int* U = reinterpret_cast<unsigned int*>(ff_sm);                  // FF_UW words, see below
+  FfRec<CM>* sstack = reinterpret_cast<FfRec<CM>*>(U + FF_UW);               // [FF_SSTK]
+  FfItem* items = reinterpret_cast<FfItem*>(sstack + FF_SSTK);               // [FF_KB]
+  FfResult<CM>* results = reinterpret_cast<FfResult<CM>*>(items + FF_KB);    // [FF_KB]
+  double* s_dbl = reinterpret_cast<double*>(results + FF_KB);                // [4]
+  int* s_ctrl = reinterpret_cast<int*>(s_dbl + 4);                           // [16]
+  int* wsum = s_ctrl + 16;                                                   // [32]
+  uint32_t* best_sl = reinterpret_cast<uint32_t*>(wsum + 32);                // [4]
+  uint8_t* features = reinterpret_cast<uint8_t*>(best_sl + 4);               // [d]
+  uint8_t* constant_features = features + ((d + 3) & ~3);                    // [d]
+  uint8_t* undo = constant_features + ((d + 3) & ~3);                        // [2 * (d + 16)] swap log of the draws
+  // U, unstaged nodes: hist[k][c][256] class weights (c < C) then [256] sample counts, 32-bit
+  const int hstrideA = (C + 1) * 256;
+  const int KBA = min(FF_KB, FF_UW / hstrideA);
+  // U, staged subtree: rows[S][ws] bin codes | histB[FF_KBM][hbw] packed 16-bit | ord[S] u8 | wcls[S] u16
+  const int S = P.stage_rows, ws = P.stage_ws;
+  const int hcw = 256 * ((C + 1) >> 1);          // packed class-pair words per feature
+  const int hbw = hcw + 128;                     // + packed sample counts
+  const uint8_t* rowsB = reinterpret_cast<const uint8_t*>(U);
+  unsigned int* histB = U + S * ws;
+  uint8_t* ord = reinterpret_cast<uint8_t*>(histB + FF_KBM * hbw);
+  uint16_t* wcls = reinterpret_cast<uint16_t*>(ord + S);
+
+  // ---- initialise the tree: samples with non-zero weight in ascending order (Splitter.init) ----
+  for (int i = tid; i < d; i += FF_THREADS) features[i] = (uint8_t)i;
+  uint32_t my_sums[CM];
+#pragma unroll
+  for (int c = 0; c < CM; ++c) my_sums[c] = 0;
+  int base = 0;
+  for (int64_t i0 = 0; i0 < n; i0 += FF_THREADS * 4) {
+    unsigned w4[4], y4[4];
+    int keep4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = i0 + q * FF_THREADS + tid;
+      w4[q] = 0; y4[q] = 0;
+      if (i < n) { w4[q] = cnt[i]; y4[q] = (unsigned)P.ycls[i]; }
+      keep4[q] = w4[q] != 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, keep4[q]);
+      if (lane == 0) wsum[q * FF_WARPS + wid] = __popc(bal);
+      keep4[q] |= (int)(__popc(bal & ((1u << lane) - 1)) << 1);   // rank within the warp above bit 0
+    }
+    __syncthreads();
+    int tot = 0, off4[4];
+#pragma unroll
+    for (int k = 0; k < 4 * FF_WARPS; ++k) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (k == q * FF_WARPS + wid) off4[q] = tot;
+      tot += wsum[k];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (keep4[q] & 1) {
+        const int64_t i = i0 + q * FF_THREADS + tid;
+        sbuf[0][base + off4[q] + (keep4[q] >> 1)] = make_uint2((unsigned)i, (w4[q] << 8) | y4[q]);
+#pragma unroll
+        for (int c = 0; c < CM; ++c) if ((int)y4[q] == c) my_sums[c] += w4[q];
+      }
+    }
+    base += tot;
+    __syncthreads();
+  }
+  const int n_nz = base;
+  if (tid < 4) best_sl[tid] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < CM; ++c) {
+    if (c < C) {
+      uint32_t v = my_sums[c];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(&best_sl[c], v);
+    }
+  }
+  __syncthreads();
+  double w_samples = 0.0;          // weighted_n_samples (integer valued)
+#pragma unroll
+  for (int c = 0; c < CM; ++c) if (c < C) w_samples += (double)best_sl[c];
+
+  uint32_t rstate = P.rand_state[slot];
+  int sp = 0, node_count = 0, max_depth_seen = -1, status = 0;
+  int st_base = 0, st_end = -1;    // sample range of the staged subtree (empty)
+  if (tid == 0) {
+    FfRec<CM> r;
+    r.start = 0; r.end = n_nz; r.depth = 0; r.parent = -1; r.flags = 0; r.pad_ = 0;
+    r.impurity = INFINITY;
+#pragma unroll
+    for (int c = 0; c < CM; ++c) r.sums[c] = c < C ? best_sl[c] : 0;
+    sstack[0] = r;
+  }
+  sp = 1;
+  bool first = true;
+  __syncthreads();
+
+  while (sp > 0 && status == 0) {
+    --sp;
+    // the popped record is copied to registers: its stack slot is overwritten by this node's own push
+    FfRec<CM> rec = sp < FF_SSTK ? sstack[sp] : gstack[sp];
+    const int start = rec.start, end = rec.end, depth = rec.depth;
+    const int n_node = end - start;
+    const int cur = (rec.flags >> 17) & 1;
+    const int n_known = rec.flags & 0xFFFF;
+    double w_node = 0.0;
+#pragma unroll
+    for (int c = 0; c < CM; ++c) if (c < C) w_node += (double)rec.sums[c];
+    double impurity = rec.impurity;
+    bool is_leaf = depth >= P.max_depth || n_node < P.min_samples_split || n_node < 2 * P.min_samples_leaf ||
+                   w_node < 2.0 * P.min_weight_leaf;
+    if (first) {   // root: node_impurity()  (SK/tree/_criterion.pyx:620-640)
+      double sq = 0.0;
+#pragma unroll
+      for (int c = 0; c < CM; ++c) if (c < C) { const double a = (double)rec.sums[c]; sq = __dadd_rn(sq, __dmul_rn(a, a)); }
+      impurity = __dsub_rn(1.0, __ddiv_rn(sq, __dmul_rn(w_node, w_node)));
+      first = false;
+    }
+    is_leaf = is_leaf || impurity <= FF_EPSILON;
+
+    int best_feature = 0, best_nl = -1, best_code = 0, n_total_constants = n_known, best_mgl = 0;
+    double best_il = 0.0, best_ir = 0.0, best_improvement = 0.0;
+    bool staged = false;
+    if (!is_leaf) {
+      // ---------------------------- stage a small subtree ------------------------------------
+      staged = start >= st_base && end <= st_end;
+      if (!staged && n_node <= S) {
+        const uint2* src = sbuf[cur] + start;
+        const int cpr = dp >> 4;                       // 16-byte chunks per row
+        for (int q = tid; q < n_node * cpr; q += FF_THREADS) {
+          const int j = q / cpr, cc = q - j * cpr;
+          const uint2 sv = src[j];
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.xrow + (size_t)sv.x * dp) + cc);
+          unsigned int* dst = U + j * ws + cc * 4;
+          if (cc * 4 + 0 < ws) dst[0] = v.x;
+          if (cc * 4 + 1 < ws) dst[1] = v.y;
+          if (cc * 4 + 2 < ws) dst[2] = v.z;
+          if (cc * 4 + 3 < ws) dst[3] = v.w;
+          if (cc == 0) { ord[j] = (uint8_t)j; wcls[j] = (uint16_t)sv.y; }
+        }
+        st_base = start; st_end = end;
+        staged = true;
+        __syncthreads();
+      }
+      const int ls = start - st_base;                 // staged: the node is ord[ls, ls + n_node)
+      const bool small = staged && n_node <= FF_SMALL;
+      const int KB = staged ? (small ? FF_KB : FF_KBM) : KBA;
+
+      // ------------------------------- node_split_best -------------------------------------
+      int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0;
+      double best_proxy = -INFINITY;
+      // Features are drawn from one RNG stream and a draw depends on whether earlier draws of this
+      // node turned out constant, so the reference evaluates them one by one.  Thread 0 SPECULATES
+      // that none of the next <= KB evaluated features is constant, simulates the draws (logging
+      // every swap), the batch is evaluated in parallel, and thread 0 commits the results in draw
+      // order; the first constant feature rolls the simulation back to its draw.
+      for (;;) {
+        if (tid == 0) {
+          int nbatch = 0;
+          int s_fi = f_i, s_nv = n_visited, s_nd = n_drawn;
+          uint32_t s_rs = rstate;
+          int ulen = 0;
+          while (nbatch < KB && s_fi > n_total_constants &&
+                 (s_nv < P.max_features || s_nv <= n_found + s_nd)) {
+            s_nv += 1;
+            int fj = ff_rand_int(s_nd, s_fi - n_found, &s_rs);
+            if (fj < n_known) {   // a known constant: move it to the drawn-constants prefix
+              const uint8_t t = features[s_nd]; features[s_nd] = features[fj]; features[fj] = t;
+              undo[2 * ulen] = (uint8_t)s_nd; undo[2 * ulen + 1] = (uint8_t)fj; ++ulen;
+              s_nd += 1;
+              continue;
+            }
+            fj += n_found;
+            FfItem it;
+            it.f = features[fj]; it.fj = fj; it.rs = s_rs; it.nv = s_nv; it.nd = s_nd; it.fi = s_fi; it.ulen = ulen; it.pad_ = 0;
+            items[nbatch] = it;
+            s_fi -= 1;          // speculative: not constant
+            { const uint8_t t = features[s_fi]; features[s_fi] = features[fj]; features[fj] = t; }
+            undo[2 * ulen] = (uint8_t)s_fi; undo[2 * ulen + 1] = (uint8_t)fj; ++ulen;
+            nbatch += 1;
+          }
+          s_ctrl[0] = nbatch;
+          s_ctrl[1] = s_fi; s_ctrl[7] = s_nv; s_ctrl[8] = s_nd; s_ctrl[9] = (int)s_rs; s_ctrl[10] = ulen;
+          if (nbatch == 0) { f_i = s_fi; n_visited = s_nv; n_drawn = s_nd; rstate = s_rs; }
+        } else if (!staged && tid >= 32) {
+          for (int i = tid - 32; i < KBA * hstrideA; i += FF_THREADS - 32) U[i] = 0;   // meanwhile: clear the histograms
+        }
+        __syncthreads();
+        const int nbatch = s_ctrl[0];
+        if (nbatch == 0) break;
+
+        if (!staged) {
+          // ---- histograms of all batch features in one pass over the node's samples (global gathers:
+          // the drawn features of a sample share one 64-byte row of codes) ----
+          int fk[FF_KB];
+#pragma unroll
+          for (int k = 0; k < FF_KB; ++k) fk[k] = items[k < nbatch ? k : 0].f;
+          const uint2* src = sbuf[cur];
+          for (int i = start + tid; i < end; i += 2 * FF_THREADS) {
+            const int i2 = i + FF_THREADS;
+            const bool has2 = i2 < end;
+            const uint2 sa = src[i];
+            const uint2 sb = has2 ? src[i2] : sa;
+            const uint8_t* ra = P.xrow + (size_t)sa.x * dp;
+            const uint8_t* rb = P.xrow + (size_t)sb.x * dp;
+            unsigned ba[FF_KB], bb[FF_KB];
+#pragma unroll
+            for (int k = 0; k < FF_KB; ++k) {
+              ba[k] = k < nbatch ? (unsigned)__ldg(ra + fk[k]) : 0u;
+              bb[k] = k < nbatch ? (unsigned)__ldg(rb + fk[k]) : 0u;
+            }
+            const unsigned ca = sa.y & 0xFF, wa = sa.y >> 8, cb = sb.y & 0xFF, wb = sb.y >> 8;
+#pragma unroll
+            for (int k = 0; k < FF_KB; ++k) {
+              if (k < nbatch) {
+                unsigned int* H = U + k * hstrideA;
+                atomicAdd(&H[ca * 256 + ba[k]], wa);
+                atomicAdd(&H[C * 256 + ba[k]], 1u);
+                if (has2) {
+                  atomicAdd(&H[cb * 256 + bb[k]], wb);
+                  atomicAdd(&H[C * 256 + bb[k]], 1u);
+                }
+              }
+            }
+          }
+          __syncthreads();
+          for (int k = wid; k < nbatch; k += FF_WARPS) {
+            const unsigned int* H = U + k * hstrideA;
+            ff_scan<CM>([&](int c, int b) -> uint32_t { return H[c * 256 + b]; },
+                        [&](int b) -> unsigned { return H[C * 256 + b]; },
+                        lane, C, n_node, rec.sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[k]);
+          }
+        } else if (!small) {
+          // ---- staged histogram node: warp k builds and scans the packed histogram of item k ----
+          if (wid < nbatch) {
+            unsigned int* H = histB + wid * hbw;
+            for (int i = lane; i < hbw; i += 32) H[i] = 0;
+            __syncwarp();
+            const int f = items[wid].f;
+            for (int i = lane; i < n_node; i += 32) {
+              const int lid = ord[ls + i];
+              const unsigned b = rowsB[lid * (ws * 4) + f];
+              const unsigned wc = wcls[lid];
+              const unsigned cls = wc & 0xFF, w = wc >> 8;
+              atomicAdd(&H[(cls >> 1) * 256 + b], w << ((cls & 1) * 16));
+              atomicAdd(&H[hcw + (b >> 1)], 1u << ((b & 1) * 16));
+            }
+            __syncwarp();
+            ff_scan<CM>([&](int c, int b) -> uint32_t { return (H[(c >> 1) * 256 + b] >> ((c & 1) * 16)) & 0xFFFFu; },
+                        [&](int b) -> unsigned { return (H[hcw + (b >> 1)] >> ((b & 1) * 16)) & 0xFFFFu; },
+                        lane, C, n_node, rec.sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[wid]);
+          }
+        } else {
+          // ---- staged node of <= 32 samples: lane j holds sample j; every lane counts the samples
+          // (and their class weights) whose bin is <= its own: the left side of the candidate
+          // threshold just above its value ----
+          const bool have = lane < n_node;
+          const int lid = have ? ord[ls + lane] : 0;
+          const unsigned wc = have ? wcls[lid] : 0u;
+          const acc_t pw = have ? (((acc_t)(wc >> 8) << (13 * (wc & 0xFF))) | ((acc_t)1 << CNT)) : (acc_t)0;
+          for (int k = wid; k < nbatch; k += FF_WARPS) {
+            const int f = items[k].f;
+            const unsigned key = have ? (unsigned)rowsB[lid * (ws * 4) + f] : 0xFFFFu;
+            acc_t acc = 0;
+            unsigned nbn = 0xFFFFu;        // smallest bin above this lane's bin present in the node
+#pragma unroll 1
+            for (int j = 0; j < n_node; ++j) {
+              const unsigned bj = __shfl_sync(0xffffffffu, key, j);
+              const acc_t pj = __shfl_sync(0xffffffffu, pw, j);
+              if (bj <= key) acc += pj;
+              else nbn = min(nbn, bj);
+            }
+            const bool cand = have && nbn != 0xFFFFu;
+            const bool is_const = __ballot_sync(0xffffffffu, cand) == 0u;
+            double proxy = -INFINITY;
+            int n_left = 1 << 30;
+            uint32_t sl[CM];
+#pragma unroll
+            for (int c = 0; c < CM; ++c) sl[c] = (uint32_t)((acc >> (13 * c)) & 0x1FFFu);
+            if (cand) {
+              const int nl = (int)(acc >> CNT), nr = n_node - nl;
+              if (nl >= P.min_samples_leaf && nr >= P.min_samples_leaf) {
+                double wl = 0.0;
+#pragma unroll
+                for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
+                const double wr = w_node - wl;
+                if (!(wl < P.min_weight_leaf || wr < P.min_weight_leaf)) {
+                  proxy = ff_proxy<CM>(sl, rec.sums, C, wl, wr, nullptr, nullptr);
+                  n_left = nl;
+                }
+              }
+            }
+            double wp = proxy; int wnl = n_left;
+            for (int o = 16; o > 0; o >>= 1) {
+              const double op = __shfl_xor_sync(0xffffffffu, wp, o);
+              const int onl = __shfl_xor_sync(0xffffffffu, wnl, o);
+              if (op > wp || (op == wp && onl < wnl)) { wp = op; wnl = onl; }
+            }
+            FfResult<CM>* R = &results[k];
+            // lanes with the same bin hold the same candidate: the lowest of them writes it
+            const unsigned same = __ballot_sync(0xffffffffu, n_left == wnl && proxy == wp && wp > -INFINITY);
+            if (lane == 0) { R->proxy = wp; R->n_left = wnl; R->code = is_const ? (1 << 16) : 0; }
+            __syncwarp();
+            if (same && lane == __ffs(same) - 1) {
+              R->code = (int)(key | (nbn << 8));
+#pragma unroll
+              for (int c = 0; c < CM; ++c) R->sl[c] = sl[c];
+            }
+          }
+        }
+        __syncthreads();
+        // --- thread 0: commit in draw order, roll back at the first constant feature ---
+        if (tid == 0) {
+          bool rolled = false;
+          for (int k = 0; k < nbatch; ++k) {
+            const FfResult<CM>& R = results[k];
+            if (!(R.code & (1 << 16))) {
+              if (R.proxy > best_proxy) {
+                best_proxy = R.proxy;
+                best_feature = items[k].f; best_nl = R.n_left; best_code = R.code;
+#pragma unroll
+                for (int c = 0; c < CM; ++c) best_sl[c] = R.sl[c];
+              }
+              continue;
+            }
+            // undo every swap made after this item's draw, then take the constant branch
+            for (int u = s_ctrl[10] - 1; u >= items[k].ulen; --u) {
+              const int a = undo[2 * u], b = undo[2 * u + 1];
+              const uint8_t t = features[a]; features[a] = features[b]; features[b] = t;
+            }
+            rstate = items[k].rs; n_visited = items[k].nv; n_drawn = items[k].nd; f_i = items[k].fi;
+            { const int fj = items[k].fj;
+              const uint8_t t = features[fj]; features[fj] = features[n_total_constants]; features[n_total_constants] = t; }
+            n_found += 1;
+            n_total_constants += 1;
+            rolled = true;
+            break;
+          }
+          if (!rolled) { f_i = s_ctrl[1]; n_visited = s_ctrl[7]; n_drawn = s_ctrl[8]; rstate = (uint32_t)s_ctrl[9]; }
+        }
+        __syncthreads();
+      }
+      // end of node_split_best: children impurities, improvement, constant-feature invariants
+      if (tid == 0) {
+        s_ctrl[2] = best_nl; s_ctrl[3] = best_feature; s_ctrl[4] = best_code; s_ctrl[5] = n_total_constants;
+        if (best_nl > 0) {
+          double wl = 0.0;
+#pragma unroll
+          for (int c = 0; c < CM; ++c) if (c < C) wl += (double)best_sl[c];
+          const double wr = w_node - wl;
+          double il, ir;
+          ff_proxy<CM>(best_sl, rec.sums, C, wl, wr, &il, &ir);
+          // impurity_improvement (SK/tree/_criterion.pyx:163-190)
+          const double a = __dmul_rn(__ddiv_rn(wr, w_node), ir);
+          const double b = __dmul_rn(__ddiv_rn(wl, w_node), il);
+          s_dbl[0] = il; s_dbl[1] = ir;
+          s_dbl[2] = __dmul_rn(__ddiv_rn(w_node, w_samples), __dsub_rn(__dsub_rn(impurity, a), b));
+        } else {
+          s_dbl[0] = 0.0; s_dbl[1] = 0.0; s_dbl[2] = 0.0;
+        }
+      }
+      __syncthreads();
+      best_nl = s_ctrl[2]; best_feature = s_ctrl[3]; best_code = s_ctrl[4]; n_total_constants = s_ctrl[5];
+      best_il = s_dbl[0]; best_ir = s_dbl[1]; best_improvement = s_dbl[2];
+      // restore / record the constant-feature prefix (the memcpy pair at the end of node_split_best)
+      for (int i = tid; i < n_known; i += FF_THREADS) features[i] = constant_features[i];
+      for (int i = n_known + tid; i < n_total_constants; i += FF_THREADS) constant_features[i] = features[i];
+      is_leaf = best_nl <= 0 || (best_improvement + FF_EPSILON < P.min_impurity_decrease);
+      best_mgl = best_nl > (n_node - best_nl);
+
+      if (best_nl > 0) {
+        const unsigned best_bin = (unsigned)(best_code & 0xFF);
+        if (staged) {
+          // --- stable partition of the node's slice of ord[] ---
+          if (n_node <= 32) {
+            if (wid == 0) {
+              const bool have = lane < n_node;
+              const int lid = have ? ord[ls + lane] : 0;
+              const bool isl = have && rowsB[lid * (ws * 4) + best_feature] <= best_bin;
+              const unsigned bl = __ballot_sync(0xffffffffu, isl);
+              const unsigned br = __ballot_sync(0xffffffffu, have && !isl);
+              const unsigned lt = (1u << lane) - 1;
+              __syncwarp();
+              if (have) ord[ls + (isl ? __popc(bl & lt) : best_nl + __popc(br & lt))] = (uint8_t)lid;
+            }
+          } else {
+            // up to 256 entries: two per thread, order = (pass, warp, lane)
+            int lid2[2], isl2[2], rk2[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int i = q * FF_THREADS + tid;
+              const bool have = i < n_node;
+              lid2[q] = have ? ord[ls + i] : 0;
+              const bool isl = have && rowsB[lid2[q] * (ws * 4) + best_feature] <= best_bin;
+              const unsigned bl = __ballot_sync(0xffffffffu, isl);
+              const unsigned br = __ballot_sync(0xffffffffu, have && !isl);
+              const unsigned lt = (1u << lane) - 1;
+              isl2[q] = have ? (isl ? 1 : 0) : -1;
+              rk2[q] = isl ? __popc(bl & lt) : __popc(br & lt);
+              if (lane == 0) { wsum[(q * FF_WARPS + wid) * 2] = __popc(bl); wsum[(q * FF_WARPS + wid) * 2 + 1] = __popc(br); }
+            }
+            __syncthreads();
+            int lo = 0, ro = 0, off[2][2];
+#pragma unroll
+            for (int k = 0; k < 2 * FF_WARPS; ++k) {
+#pragma unroll
+              for (int q = 0; q < 2; ++q) if (k == q * FF_WARPS + wid) { off[q][0] = lo; off[q][1] = ro; }
+              lo += wsum[2 * k]; ro += wsum[2 * k + 1];
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              if (isl2[q] >= 0) ord[ls + (isl2[q] ? off[q][0] + rk2[q] : best_nl + off[q][1] + rk2[q])] = (uint8_t)lid2[q];
+          }
+        } else {
+          // --- partition_samples_final: stable partition into the other sample buffer ---
+          const uint2* src = sbuf[cur];
+          uint2* dst = sbuf[cur ^ 1];
+          int loff = start, roff = start + best_nl;
+          for (int i0 = start; i0 < end; i0 += 4 * FF_THREADS) {
+            uint2 sv4[4];
+            int isl4[4], rk4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = i0 + q * FF_THREADS + tid;
+              const bool have = i < end;
+              sv4[q] = have ? src[i] : make_uint2(0, 0);
+              const bool isl = have && __ldg(P.xrow + (size_t)sv4[q].x * dp + best_feature) <= best_bin;
+              const unsigned bl = __ballot_sync(0xffffffffu, isl);
+              const unsigned br = __ballot_sync(0xffffffffu, have && !isl);
+              const unsigned lt = (1u << lane) - 1;
+              isl4[q] = have ? (isl ? 1 : 0) : -1;
+              rk4[q] = isl ? __popc(bl & lt) : __popc(br & lt);
+              if (lane == 0) { wsum[(q * FF_WARPS + wid) * 2] = __popc(bl); wsum[(q * FF_WARPS + wid) * 2 + 1] = __popc(br); }
+            }
+            __syncthreads();
+            int lo = 0, ro = 0, off[4][2];
+#pragma unroll
+            for (int k = 0; k < 4 * FF_WARPS; ++k) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) if (k == q * FF_WARPS + wid) { off[q][0] = lo; off[q][1] = ro; }
+              lo += wsum[2 * k]; ro += wsum[2 * k + 1];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (isl4[q] >= 0) dst[isl4[q] ? loff + off[q][0] + rk4[q] : roff + off[q][1] + rk4[q]] = sv4[q];
+            loff += lo; roff += ro;
+            __syncthreads();
+          }
+        }
+      }
+    }
+
+    // ------------------------------- _add_node + node_value --------------------------------
+    const int node_id = node_count;
+    if (node_id >= P.node_cap) { status = 1; break; }
+    if (tid == 0) {
+      if (rec.parent >= 0) {
+        if (rec.flags & (1 << 16)) P.o_left[nb + rec.parent] = node_id; else P.o_right[nb + rec.parent] = node_id;
+      }
+      P.o_imp[nb + node_id] = impurity;
+      P.o_nsamp[nb + node_id] = n_node;
+      P.o_wn[nb + node_id] = w_node;
+      if (is_leaf) {
+        P.o_left[nb + node_id] = -1; P.o_right[nb + node_id] = -1;
+        P.o_feature[nb + node_id] = -2; P.o_thr[nb + node_id] = -2.0; P.o_mgl[nb + node_id] = 0;
+      } else {
+        P.o_feature[nb + node_id] = best_feature;
+        // the two bins around the threshold; ff_threshold_kernel turns them into v[a]/2 + v[b]/2
+        P.o_thr[nb + node_id] = __longlong_as_double((long long)(best_code & 0xFFFF));
+        P.o_mgl[nb + node_id] = (uint8_t)best_mgl;
+      }
+#pragma unroll
+      for (int c = 0; c < CM; ++c)
+        if (c < C) P.o_val[(nb + node_id) * C + c] = __ddiv_rn((double)rec.sums[c], w_node);   // class fractions
+    }
+    node_count += 1;
+    if (!is_leaf) {
+      if (sp + 2 > P.stack_cap) { status = 2; break; }
+      if (tid == 0) {
+        const int child_buf = staged ? cur : (cur ^ 1);
+        FfRec<CM> r;
+        r.depth = depth + 1; r.parent = node_id; r.pad_ = 0;
+        // right child first, then left (popped first)
+        r.start = start + best_nl; r.end = end; r.flags = n_total_constants | (child_buf << 17); r.impurity = best_ir;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) r.sums[c] = c < C ? rec.sums[c] - best_sl[c] : 0;
+        if (sp < FF_SSTK) sstack[sp] = r; else gstack[sp] = r;
+        r.start = start; r.end = start + best_nl; r.flags = n_total_constants | (1 << 16) | (child_buf << 17); r.impurity = best_il;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) r.sums[c] = c < C ? best_sl[c] : 0;
+        if (sp + 1 < FF_SSTK) sstack[sp + 1] = r; else gstack[sp + 1] = r;
+      }
+      sp += 2;
+    }
+    if (depth > max_depth_seen) max_depth_seen = depth;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    P.o_count[slot] = node_count;
+    P.o_maxdepth[slot] = max_depth_seen;
+    P.o_status[slot] = status;
+  }
+}
+
+// threshold of every internal node from the two bins the builder left in o_thr:
+// v[p-1]/2 + v[p] /2 in float64 (SK/tree/_splitter.pyx:459-461)
+__global__ void ff_threshold_kernel(const float* __restrict__ binval, const int32_t* __restrict__ o_feature,
+                                    double* __restrict__ o_thr, const int32_t* __restrict__ o_count, int64_t node_cap) {
+  const int slot = blockIdx.y;
+  const int m = o_count[slot];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    const int64_t o = (int64_t)slot * node_cap + i;
+    const int f = o_feature[o];
+    if (f < 0) continue;
+    const long long code = __double_as_longlong(o_thr[o]);
+    const int a = (int)(code & 0xFF), b = (int)((code >> 8) & 0xFF);
+    o_thr[o] = (double)binval[(size_t)f * 256 + a] / 2.0 + (double)binval[(size_t)f * 256 + b] / 2.0;
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+static size_t ff_smem_bytes(int CM, int d) {
+  const size_t rec = CM <= 2 ? sizeof(FfRec<2>) : sizeof(FfRec<4>);
+  const size_t res = CM <= 2 ? sizeof(FfResult<2>) : sizeof(FfResult<4>);
+  return (size_t)FF_UW * 4 + FF_SSTK * rec + FF_KB * sizeof(FfItem) + FF_KB * res + 4 * 8 + 16 * 4 + 32 * 4 + 4 * 4 +
+         2 * (size_t)((d + 3) & ~3) + 2 * (size_t)(d + 16) + 16;
+}
+
+// staged rows per subtree for (d, n_classes), 0 = the fast kernel cannot run this shape
+static int ff_stage_rows(int d, int n_classes, int* ws_out) {
+  const int ws = ((d + 3) / 4) | 1;                           // odd word stride: conflict-free column reads
+  const int hbw = 256 * ((n_classes + 1) / 2) + 128;
+  int S = (FF_UW - FF_KBM * hbw) * 4 / (ws * 4 + 3);
+  S = std::min(256, S / 32 * 32);
+  *ws_out = ws;
+  return S >= 64 ? S : 0;
+}
+
+bool forest_fast_supported(const Ctx* c, int n_classes, bool reg, int random_split) {
+  if (reg || random_split || n_classes > 4 || c->d > 255 || !c->forest.well_separated) return false;
+  if ((double)c->n * 255.0 >= 4294967296.0) return false;
+  if (const char* e = getenv("SKDIST_B200_FOREST_KERNEL")) if (!strcmp(e, "general")) return false;
+  int ws;
+  return ff_stage_rows((int)c->d, n_classes, &ws) > 0;
+}
+
+int forest_fast_slots_per_sm() { return 7; }
+size_t forest_fast_record_bytes(int n_classes) { return n_classes <= 2 ? sizeof(FfRec<2>) : sizeof(FfRec<4>); }
+
+int forest_fast_launch(Ctx* c, FfParams& P, int nt) {
+  int ws = 0;
+  P.stage_rows = ff_stage_rows(P.d, P.n_classes, &ws);
+  P.stage_ws = ws;
+  const int CM = P.n_classes <= 2 ? 2 : 4;
+  const size_t smem = ff_smem_bytes(CM, P.d);
+  P.n_trees = nt;
+  if (CM == 2) {
+    SKD_CUDA(c, cudaFuncSetAttribute(forest_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    forest_fast_kernel<2><<<nt, FF_THREADS, smem, c->stream>>>(P);
+  } else {
+    SKD_CUDA(c, cudaFuncSetAttribute(forest_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    forest_fast_kernel<4><<<nt, FF_THREADS, smem, c->stream>>>(P);
+  }
+  SKD_CUDA(c, cudaGetLastError());
+  dim3 g(64, nt);
+  ff_threshold_kernel<<<g, 256, 0, c->stream>>>(c->forest.binval, P.o_feature, P.o_thr, P.o_count, P.node_cap);
+  SKD_CUDA(c, cudaGetLastError());
+  c->launches += 2;
+  return 0;
+}
+
+}  // namespace skd

@@ -42,6 +42,9 @@ struct TcData {
 struct ForestData {
   uint8_t* xbin = nullptr;   // [d][n] bin code of every value, feature-major
   float* binval = nullptr;   // [d][256] distinct values of each feature, ascending (+inf padded)
+  uint8_t* xrow = nullptr;   // [n][dp] the same codes row-major, dp = d rounded up to 16 (forest_fast.cu)
+  int dp = 0;
+  bool well_separated = false;   // every feature's adjacent distinct values are more than 1e-7 apart
   bool valid = false;
 };
 

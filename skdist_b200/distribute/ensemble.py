@@ -207,7 +207,10 @@ class _DistForestClassifier(_ScParamMixin):
         # Trees go to the device in chunks (two resident tree builders per SM).  While chunk k is
         # being built, the host draws the bootstrap samples of chunk k+1 and wraps the node arrays
         # of chunk k-1 into scikit-learn trees (ctypes releases the GIL during the device call).
-        chunk = int(os.environ.get("SKDIST_B200_FOREST_CHUNK", "296"))
+        # (the throughput builder of csrc/forest_fast.cu keeps seven trees per SM resident, the general
+        # one two: a chunk is one full wave of the builder that will run)
+        fast = not self._regression and self._splitter == 0 and self.n_classes_ <= 4 and d <= 255
+        chunk = int(os.environ.get("SKDIST_B200_FOREST_CHUNK", "1036" if fast else "296"))
         chunks = [my_states[i:i + chunk] for i in range(0, len(my_states), chunk)]
 
         host_threads = max(1, min(64, (os.cpu_count() or 8) // max(world, 1)))

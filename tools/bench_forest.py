@@ -10,6 +10,7 @@ p.add_argument("--n", type=int, default=2_000_000)
 p.add_argument("--d", type=int, default=64)
 p.add_argument("--trees", type=int, default=64)
 p.add_argument("--cpu-sample", type=int, default=1)
+p.add_argument("--cpu-jobs", type=int, default=0, help="0 = one sklearn tree per sampled core (cpu-sample trees, n_jobs=cpu-sample)")
 a = p.parse_args()
 from sklearn.ensemble import RandomForestClassifier
 from skdist.distribute.ensemble import DistRandomForestClassifier
@@ -28,14 +29,16 @@ alg_bytes = 8.0 * (mf + 1) * float(np.sum(internal))
 line = {"workload": "DistRandomForestClassifier(n_estimators=%d, random_state=0) on lattice %dx%d fp32" % (a.trees, a.n, a.d),
         "trees_per_s_e2e": a.trees / dt, "seconds": dt, "device_seconds": rf.device_seconds_,
         "nodes_mean": float(nodes.mean()), "depth_max": int(max(e.tree_.max_depth for e in rf.estimators_)),
-        "algorithmic_bytes": alg_bytes, "algorithmic_GBps_device": alg_bytes / rf.device_seconds_ / 1e9}
+        "algorithmic_bytes": alg_bytes, "algorithmic_GBps_device": alg_bytes / rf.device_seconds_ / 1e9,
+        "kernel": os.environ.get("SKDIST_B200_FOREST_KERNEL", "auto")}
 if a.cpu_sample:
     t0 = time.time()
-    ref = RandomForestClassifier(n_estimators=a.cpu_sample, random_state=0, n_jobs=1).fit(X, y)
+    nj = a.cpu_jobs or a.cpu_sample
+    ref = RandomForestClassifier(n_estimators=a.cpu_sample, random_state=0, n_jobs=nj).fit(X, y)
     dtc = time.time() - t0
     same = all(np.array_equal(r.tree_.threshold, o.tree_.threshold) and np.array_equal(r.tree_.children_left, o.tree_.children_left)
                for r, o in zip(ref.estimators_, rf.estimators_))
-    line["cpu_baseline"] = {"value": a.cpu_sample / dtc, "unit": "trees/s", "cores": 1, "kind": "port",
-                            "sample": "%d tree(s) in %.1f s (one tree per core, as the reference's tasks)" % (a.cpu_sample, dtc),
+    line["cpu_baseline"] = {"value": a.cpu_sample / dtc, "unit": "trees/s", "cores": nj, "kind": "port", "host_cores": os.cpu_count(),
+                            "sample": "%d tree(s) in %.1f s, %d at a time (one tree per core, as the reference's tasks)" % (a.cpu_sample, dtc, nj),
                             "bit_identical_to_gpu": bool(same)}
 print(json.dumps(line))
