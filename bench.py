@@ -282,7 +282,8 @@ def main():
     n_cols = a.candidates * a.folds
     # same dealing as DistGridSearchCV: blocks of 128 consecutive candidates of one fold per rank
     deal_order = (np.arange(a.candidates)[None, :] * a.folds + np.arange(a.folds)[:, None]).ravel()
-    my = parallel.shard_blocks(n_cols, rank, world, deal_order)
+    col_cost = np.repeat(parallel.logreg_column_cost(Cs), a.folds) if world > 1 else None
+    my = parallel.shard_blocks(n_cols, rank, world, deal_order, cost=col_cost)
     C_cols = np.repeat(Cs, a.folds)[my]
     f_cols = np.tile(np.arange(a.folds, dtype=np.int32), a.candidates)[my]
     pos = np.ones(len(my), np.int32)
@@ -348,7 +349,7 @@ def main():
             "warmup": a.warmup, "ms_per_step": 1e3 * t_steps / a.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(a), "inputs": "exceed L2 (X is %.2f GB)" % (X.nbytes / 1e9),
-                       "parallelism": "blocks of 128 same-fold columns dealt over %d rank(s), X replicated" % world,
+                       "parallelism": "blocks of 128 same-fold columns dealt over %d rank(s) (longest first, by C), X replicated" % world,
                        "kernel": {0: "auto", 1: "simt-fp32", 2: "tcgen05"}[a.kernel],
                        "mean_test_score_best": float(np.max(gs.cv_results_["mean_test_score"])),
                        "best_C": float(gs.best_params_["C"]),

@@ -47,6 +47,16 @@ int skd_stage_x_device(skd_ctx* ctx, const float* dX, int64_t n, int64_t d, int6
  * ref: the sc.broadcast of search.py:414-421. */
 int skd_staged_x(skd_ctx* ctx, const float** dX, int64_t* n, int64_t* d, int64_t* ldx);
 
+/* Sliced staging when every rank holds X on the host (SPMD fit under torchrun): begin allocates the
+ * device buffer for n rows (n_alloc >= n rows of capacity, so that N equal slices fit) and returns it;
+ * rows copies this rank's slice [row0, row0 + n_rows) host -> device through its own PCIe link; the
+ * caller all-gathers the slices in place over NVLink (torch.distributed / NCCL); commit validates the
+ * matrix (NaN / infinity check as skd_stage_x) and makes it the staged X.
+ * ref: the sc.broadcast of search.py:414-421, with the host -> device copy divided over the GPUs. */
+int skd_stage_x_begin(skd_ctx* ctx, int64_t n, int64_t d, int64_t n_alloc, const float** dX, int64_t* ldx);
+int skd_stage_x_rows(skd_ctx* ctx, const float* X_rows, int64_t ld, int64_t row0, int64_t n_rows);
+int skd_stage_x_commit(skd_ctx* ctx);
+
 /* Stage integer class ids (0..K-1), one per row.  Column j of a batch treats rows with
  * y_class == col_pos[j] as positive, the rest as negative.
  * ref: y in the closure (search.py:416-421); LabelBinarizer columns (multiclass.py:289-317). */

@@ -263,16 +263,47 @@ static int stage_rows_h2d(Ctx* c, float* dst, int64_t ldx, const float* src, int
   return 0;
 }
 
+// device buffer of the staged matrix: kept when the row pitch is unchanged and it is large enough
+// (repeated fits on same-sized data); zeroed when the pitch pads the rows
+static int ensure_x_buffer(Ctx* c, int64_t n, int64_t d, int64_t n_alloc) {
+  const int64_t ldx = round_up(d, 16);
+  if (c->X && !(c->ldx == ldx && c->x_cap_rows >= n_alloc && c->x_cap_rows <= n_alloc + n_alloc / 8 + 64)) {
+    cudaFree(c->X); c->X = nullptr; c->n = 0; c->x_cap_rows = 0;
+  }
+  if (!c->X) {
+    SKD_CUDA(c, cudaMalloc((void**)&c->X, (size_t)n_alloc * ldx * sizeof(float)));
+    c->x_cap_rows = n_alloc;
+    c->ldx = ldx;
+  }
+  if (ldx != d) SKD_CUDA(c, cudaMemsetAsync(c->X, 0, (size_t)c->x_cap_rows * ldx * sizeof(float), c->stream));
+  (void)n;
+  return 0;
+}
+
+static int finite_check_staged(Ctx* c, int64_t n, int64_t ldx) {
+  int* dflag;
+  Scratch sx(c);
+  SKD_CUDA(c, sx.alloc(&dflag, 1));
+  SKD_CUDA(c, cudaMemsetAsync(dflag, 0, sizeof(int), c->stream));
+  finite_check_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->X, n * ldx, dflag);
+  c->launches += 1;
+  int hflag = 0;
+  SKD_CUDA(c, cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (hflag) {
+    cudaFree(c->X); c->X = nullptr; c->n = 0; c->x_cap_rows = 0;
+    return fail(c, "Input X contains NaN or infinity.");
+  }
+  return 0;
+}
+
 static int stage_x_common(Ctx* c, const float* src, int64_t n, int64_t d, int64_t ldx_src,
                           cudaMemcpyKind kind) {
   if (!src || n <= 0 || d <= 0 || ldx_src < d) return fail(c, "skd_stage_x: bad arguments");
   SKD_CUDA(c, cudaSetDevice(c->device));
   Trace tr(c, "stage_x");
   int64_t ldx = round_up(d, 16);
-  // keep the device buffer when the shape is unchanged (repeated fits on same-sized data)
-  if (c->X && !(c->n == n && c->ldx == ldx)) { cudaFree(c->X); c->X = nullptr; }
-  if (!c->X) SKD_CUDA(c, cudaMalloc((void**)&c->X, (size_t)n * ldx * sizeof(float)));
-  if (ldx != d) SKD_CUDA(c, cudaMemsetAsync(c->X, 0, (size_t)n * ldx * sizeof(float), c->stream));
+  if (ensure_x_buffer(c, n, d, n)) return 1;
   tr.mark("alloc");
   if (kind == cudaMemcpyHostToDevice) {
     if (stage_rows_h2d(c, c->X, ldx, src, n, d, ldx_src)) return 1;
@@ -282,21 +313,7 @@ static int stage_x_common(Ctx* c, const float* src, int64_t n, int64_t d, int64_
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   tr.mark("copy");
-  {
-    int* dflag;
-    Scratch sx(c);
-    SKD_CUDA(c, sx.alloc(&dflag, 1));
-    SKD_CUDA(c, cudaMemsetAsync(dflag, 0, sizeof(int), c->stream));
-    finite_check_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->X, n * ldx, dflag);
-    c->launches += 1;
-    int hflag = 0;
-    SKD_CUDA(c, cudaMemcpyAsync(&hflag, dflag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (hflag) {
-      cudaFree(c->X); c->X = nullptr; c->n = 0;
-      return fail(c, "Input X contains NaN or infinity.");
-    }
-  }
+  if (finite_check_staged(c, n, ldx)) return 1;
   tr.mark("check");
   c->n = n; c->d = d; c->ldx = ldx;
   c->tc.x_valid = false;
@@ -313,6 +330,50 @@ int skd_stage_x(skd_ctx* ctx, const float* X, int64_t n, int64_t d, int64_t ldx)
 int skd_stage_x_device(skd_ctx* ctx, const float* dX, int64_t n, int64_t d, int64_t ldx) {
   if (!ctx) return fail(nullptr, "skd_stage_x_device: ctx is NULL");
   return stage_x_common(&ctx->c, dX, n, d, ldx, cudaMemcpyDeviceToDevice);
+}
+
+// Sliced staging for several ranks that all hold X on the host: every rank copies its own row slice
+// (1/N of the matrix through its own PCIe link), the caller all-gathers the slices in place over
+// NVLink (the buffer holds n_alloc >= n rows so that the slices can be equal-sized), then commits.
+int skd_stage_x_begin(skd_ctx* ctx, int64_t n, int64_t d, int64_t n_alloc, const float** dX, int64_t* ldx_out) {
+  if (!ctx) return fail(nullptr, "skd_stage_x_begin: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (n <= 0 || d <= 0 || n_alloc < n) return fail(c, "skd_stage_x_begin: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  c->n = 0;                              // nothing is staged until the commit
+  if (ensure_x_buffer(c, n, d, n_alloc)) return 1;
+  SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->pend_n = n; c->pend_d = d;
+  if (dX) *dX = c->X;
+  if (ldx_out) *ldx_out = c->ldx;
+  return 0;
+}
+
+int skd_stage_x_rows(skd_ctx* ctx, const float* X_rows, int64_t ld, int64_t row0, int64_t n_rows) {
+  if (!ctx) return fail(nullptr, "skd_stage_x_rows: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || c->pend_n <= 0) return fail(c, "skd_stage_x_rows: call skd_stage_x_begin first");
+  if (n_rows == 0) return 0;
+  if (!X_rows || row0 < 0 || n_rows < 0 || row0 + n_rows > c->pend_n || ld < c->pend_d)
+    return fail(c, "skd_stage_x_rows: bad arguments");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  if (stage_rows_h2d(c, c->X + (size_t)row0 * c->ldx, c->ldx, X_rows, n_rows, c->pend_d, ld)) return 1;
+  c->h2d += n_rows * c->pend_d * (int64_t)sizeof(float);
+  return 0;
+}
+
+int skd_stage_x_commit(skd_ctx* ctx) {
+  if (!ctx) return fail(nullptr, "skd_stage_x_commit: ctx is NULL");
+  Ctx* c = &ctx->c;
+  if (!c->X || c->pend_n <= 0) return fail(c, "skd_stage_x_commit: call skd_stage_x_begin first");
+  SKD_CUDA(c, cudaSetDevice(c->device));
+  const int64_t n = c->pend_n, d = c->pend_d;
+  c->pend_n = 0;
+  if (finite_check_staged(c, n, c->ldx)) return 1;
+  c->n = n; c->d = d;
+  c->tc.x_valid = false;
+  c->forest.valid = false;
+  return 0;
 }
 
 int skd_staged_x(skd_ctx* ctx, const float** dX, int64_t* n, int64_t* d, int64_t* ldx) {

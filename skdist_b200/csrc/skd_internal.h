@@ -66,6 +66,8 @@ struct Ctx {
   // staged data
   float* X = nullptr;       // [n x ldx] fp32 row-major
   int64_t n = 0, d = 0, ldx = 0;
+  int64_t x_cap_rows = 0;   // allocated rows of X (>= n; the sliced staging pads to a multiple of the world size)
+  int64_t pend_n = 0, pend_d = 0;   // shape announced by skd_stage_x_begin, committed by skd_stage_x_commit
   int32_t* ycls = nullptr;  // [n]
   float* yreal = nullptr;   // [n]
   int8_t* fold = nullptr;   // [n]; nullptr = no folds staged (points into fold_store otherwise)

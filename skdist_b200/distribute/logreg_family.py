@@ -210,6 +210,11 @@ class _LogRegFamily:
                 out[name] = _metric_from_counts(kind, correct, count, pred_pos, actual_pos)
         return out, count
 
+    def column_cost(self, n_splits):
+        """Expected relative duration of every (candidate, fold) column, for the multi-GPU block deal."""
+        from ..parallel import logreg_column_cost
+        return np.repeat(logreg_column_cost([p["C"] for p in self.cands]), n_splits)
+
     def run_columns(self, eng, cols, n_splits, return_train_score):
         """Fit + score the given global column ids (col = cand * n_splits + fold).
         Returns dict of per-column arrays aligned with `cols`."""

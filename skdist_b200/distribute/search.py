@@ -127,7 +127,8 @@ class DistBaseSearchCV(_ScParamMixin):
         # Ranks are dealt blocks of 128 consecutive candidates of ONE fold (fold-major order).
         n_cols = n_candidates * n_splits
         deal_order = (np.arange(n_candidates)[None, :] * n_splits + np.arange(n_splits)[:, None]).ravel()
-        my_cols = parallel.shard_blocks(n_cols, rank, world, deal_order)
+        col_cost = family.column_cost(n_splits) if world > 1 and hasattr(family, "column_cost") else None
+        my_cols = parallel.shard_blocks(n_cols, rank, world, deal_order, cost=col_cost)
         loc = family.run_columns(eng, my_cols, n_splits, bool(self.return_train_score))
         metric_names = list(family.metrics)
         keys = ["n_test", "fit_time", "score_time"] + ["test_%s" % m for m in metric_names]
@@ -135,7 +136,7 @@ class DistBaseSearchCV(_ScParamMixin):
             keys += ["train_%s" % m for m in metric_names]
         # one collective for all per-column results (counts are exact in float64)
         stacked = np.stack([np.asarray(loc[k], dtype=np.float64) for k in keys], axis=1)
-        gathered = parallel.all_gather_blocks(stacked, n_cols, rank, world, deal_order)
+        gathered = parallel.all_gather_blocks(stacked, n_cols, rank, world, deal_order, cost=col_cost)
         res = {k: gathered[:, i] for i, k in enumerate(keys)}
         res["n_test"] = np.rint(res["n_test"]).astype(np.int64)
 

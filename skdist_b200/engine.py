@@ -53,6 +53,31 @@ class Engine:
         check(self._lib.skd_stage_x_device(self._h, ctypes.c_void_p(int(dev_ptr)), n, d, ldx or d), self._h)
         self.n, self.d = n, d
 
+    def stage_x_sliced(self, X, row0, row1, n_alloc, gather):
+        """Stage X when several ranks hold it: this rank copies rows [row0, row1) to its GPU,
+        `gather(dev_ptr, ldx)` completes the buffer in place (all-gather over NVLink), then the
+        matrix is validated and becomes the staged X."""
+        X = np.asarray(X)
+        ok = (X.ndim == 2 and X.dtype == np.float32 and X.shape[1] > 0 and X.strides[1] == 4
+              and X.strides[0] % 4 == 0 and X.strides[0] >= 4 * X.shape[1])
+        n, d = X.shape
+        sl = X[row0:row1]
+        if not ok:
+            sl = np.ascontiguousarray(sl, dtype=np.float32)
+        p, ldx = ctypes.c_void_p(), ctypes.c_int64()
+        check(self._lib.skd_stage_x_begin(self._h, n, d, int(n_alloc), ctypes.byref(p), ctypes.byref(ldx)), self._h)
+        err = None
+        try:
+            if row1 > row0:
+                check(self._lib.skd_stage_x_rows(self._h, ptr(sl), sl.strides[0] // 4, int(row0), int(row1 - row0)), self._h)
+        except Exception as e:      # noqa: BLE001 - the collective below must still be entered by every rank
+            err = e
+        gather(p.value, ldx.value)
+        if err is not None:
+            raise err
+        check(self._lib.skd_stage_x_commit(self._h), self._h)
+        self.n, self.d = n, d
+
     def staged_x(self):
         """(device pointer, n, d, ldx) of the staged matrix."""
         p = ctypes.c_void_p()

@@ -65,21 +65,59 @@ def _block_size(n_items, world, block):
     return max(1, min(int(block), n_items // max(1, world)))
 
 
-def shard_blocks(n_items, rank, world, order=None, block=128):
-    """Block-cyclic deal: the items, taken in `order` (default 0..n-1), are cut into blocks of
-    `block` (shrunk for small problems so that every rank gets work) and block b goes to rank
-    b % world.  The search passes a fold-major order, so a rank receives whole groups of 128
-    same-fold columns -- the unit the tensor-core kernel works on -- instead of a thin slice of every
-    fold that would have to be padded to 128 slots per fold."""
+def logreg_column_cost(C):
+    """Relative number of lock-step rounds a logistic column is expected to need: weakly regularised
+    fits (large C) run to max_iter, strongly regularised ones stop early.  Only the ordering and the
+    rough ratio matter (block dealing below); 1.0 = runs to the end."""
+    C = np.asarray(C, dtype=np.float64)
+    return np.clip(0.15 + 0.25 * (np.log10(np.maximum(C, 1e-300)) + 4.0), 0.15, 1.0)
+
+
+def _assign_blocks(block_cost, world):
+    """Rank of every block.  Without costs: block b -> rank b % world.  With costs: longest
+    processing time first -- blocks in descending cost (ties: lower index) to the rank with the
+    least load (ties: fewer blocks, lower rank), so the ranks that must take one block more than
+    the others get the blocks that finish early."""
+    nb = len(block_cost)
+    if world == 1:
+        return np.zeros(nb, dtype=np.int64)
+    if np.all(block_cost == block_cost[0]):
+        return np.arange(nb, dtype=np.int64) % world
+    out = np.empty(nb, dtype=np.int64)
+    load = np.zeros(world)
+    cnt = np.zeros(world, dtype=np.int64)
+    for bi in np.argsort(-block_cost, kind="stable"):
+        r = min(range(world), key=lambda q: (round(load[q], 9), cnt[q], q))
+        out[bi] = r
+        load[r] += block_cost[bi]
+        cnt[r] += 1
+    return out
+
+
+def shard_blocks(n_items, rank, world, order=None, block=128, cost=None):
+    """Block deal: the items, taken in `order` (default 0..n-1), are cut into blocks of `block`
+    (shrunk for small problems so that every rank gets work); block b goes to rank b % world, or,
+    when per-item costs are given (indexed by item id; a block costs as much as its most expensive
+    item because its columns advance in lock-step), to the rank `_assign_blocks` picks.  The search
+    passes a fold-major order, so a rank receives whole groups of 128 same-fold columns -- the unit
+    the tensor-core kernel works on -- instead of a thin slice of every fold that would have to be
+    padded to 128 slots per fold."""
     order = np.arange(n_items, dtype=np.int64) if order is None else np.asarray(order, dtype=np.int64)
     if world == 1:
         return order
     b = _block_size(n_items, world, block)
     pos = np.arange(n_items, dtype=np.int64)
-    return order[(pos // b) % world == rank]
+    blk = pos // b
+    if cost is None:
+        return order[blk % world == rank]
+    cost = np.asarray(cost, dtype=np.float64)
+    nb = int(blk[-1]) + 1 if n_items else 0
+    bcost = np.zeros(nb)
+    np.maximum.at(bcost, blk, cost[order])
+    return order[_assign_blocks(bcost, world)[blk] == rank]
 
 
-def all_gather_blocks(local, n_items, rank, world, order=None, block=128):
+def all_gather_blocks(local, n_items, rank, world, order=None, block=128, cost=None):
     """Inverse of shard_blocks for per-item result rows: the full [n_items, ...] array on every rank."""
     local = np.ascontiguousarray(local)
     if world == 1:
@@ -91,7 +129,7 @@ def all_gather_blocks(local, n_items, rank, world, order=None, block=128):
     import torch
     import torch.distributed as dist
 
-    idx = [shard_blocks(n_items, r, world, order, block) for r in range(world)]
+    idx = [shard_blocks(n_items, r, world, order, block, cost) for r in range(world)]
     per = max(len(i) for i in idx)
     tail = local.shape[1:]
     pad = np.zeros((per,) + tail, dtype=local.dtype)
@@ -150,7 +188,39 @@ def stage_x_replicated(eng, X):
     # this may run on a worker thread (the search overlaps staging with the cv split): torch's
     # current device is per thread, so name the rank's GPU explicitly
     with torch.cuda.device(local):
+        if hasattr(eng, "stage_x_sliced") and os.environ.get("SKDIST_B200_STAGE", "sliced") == "sliced":
+            return _stage_x_allgather(eng, X, rank, world, torch.device("cuda", local))
         return _stage_x_broadcast(eng, X, rank, torch.device("cuda", local))
+
+
+def _stage_x_allgather(eng, X, rank, world, dev):
+    """Every rank holds X on the host (SPMD): rank r copies rows [r * per, (r + 1) * per) to its GPU
+    through its own PCIe link (1/N of the bytes each, concurrently) and ONE in-place NCCL all-gather
+    over NVLink completes the matrix everywhere -- the reference's sc.broadcast(X) (search.py:414-421)
+    without the single host-to-device copy of the whole matrix in front of it."""
+    import torch
+    import torch.distributed as dist
+    n, d = np.asarray(X).shape
+    per = (n + world - 1) // world
+    row0, row1 = min(n, rank * per), min(n, (rank + 1) * per)
+
+    def gather(ptr, ldx):
+        full = torch.as_tensor(_DeviceView(ptr, (per * world, ldx)), device=dev)
+        dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per])
+        torch.cuda.current_stream().synchronize()
+
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    err = None
+    try:
+        eng.stage_x_sliced(X, row0, row1, per * world, gather)
+    except Exception as e:      # noqa: BLE001 - a NaN anywhere in X is seen by every rank's commit; other errors are agreed on below
+        err = e
+        status[0] = 1
+    dist.all_reduce(status, op=dist.ReduceOp.MAX)
+    if err is not None:
+        raise err
+    if int(status.item()):
+        raise ValueError("another rank could not stage X (see its error)")
 
 
 def _stage_x_broadcast(eng, X, rank, dev):
