@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libskdist_b200.so")
-SOURCES = ["api.cu", "logreg_simt.cu", "lbfgs_dev.cu", "logreg_multi.cu", "auc.cu", "logreg_tc.cu", "ridge.cu", "predict.cu", "sgd.cu", "forest.cu", "forest_fast.cu", "bootstrap.cu"]
+SOURCES = ["api.cu", "logreg_simt.cu", "lbfgs_dev.cu", "logreg_multi.cu", "auc.cu", "logreg_tc.cu", "ridge.cu", "predict.cu", "sgd.cu", "sgd_tc.cu", "forest.cu", "forest_fast.cu", "bootstrap.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC",

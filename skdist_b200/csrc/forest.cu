@@ -837,7 +837,7 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
     const long long v = atoll(e);
     if (v > 0 && v < node_cap) node_cap = v;
   }
-  const bool want_prof = !fast && getenv("SKDIST_B200_FOREST_PROF") != nullptr;
+  const bool want_prof = getenv("SKDIST_B200_FOREST_PROF") != nullptr;
   double* dy = nullptr;
   Scratch sy(c);
   if (reg) {
@@ -917,7 +917,7 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
     F.stack_cap = stack_cap; F.node_cap = node_cap;
     F.o_left = P.o_left; F.o_right = P.o_right; F.o_feature = P.o_feature; F.o_nsamp = P.o_nsamp; F.o_mgl = P.o_mgl;
     F.o_thr = P.o_thr; F.o_imp = P.o_imp; F.o_wn = P.o_wn; F.o_val = P.o_val;
-    F.o_count = P.o_count; F.o_maxdepth = P.o_maxdepth; F.o_status = P.o_status;
+    F.o_count = P.o_count; F.o_maxdepth = P.o_maxdepth; F.o_status = P.o_status; F.o_prof = d_prof;
     std::vector<int32_t> hcount(slots), hdepth(slots), hstatus(slots);
     std::vector<uint32_t> hrs(slots);
     std::vector<int> failed;
@@ -955,9 +955,14 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
       if (want_prof) {
         std::vector<long long> hp((size_t)nt * 16);
         cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost);
-        static const char* nm[12] = {"pop", "speculate", "zero+stage", "histogram", "scan", "commit", "restore+improve", "partition", "add_node+push", "-", "loop barrier", "-"};
-        double tot = 0; for (int i = 0; i < 12; ++i) tot += (double)hp[i];
-        for (int i = 0; i < 12; ++i) if (hp[i]) fprintf(stderr, "[skd forest prof] tree 0 %-16s %12lld cycles %5.1f%%  (%.0f per node)\n", nm[i], hp[i], 100.0 * hp[i] / tot, (double)hp[i] / hcount[0]);
+        static const char* nm_g[12] = {"pop", "speculate", "zero+stage", "histogram", "scan", "commit", "restore+improve", "partition", "add_node+push", "-", "loop barrier", "-"};
+        static const char* nm_f[12] = {"pop+header", "stage subtree", "draw", "gather hist", "scan (unstaged)", "hist+scan (staged)", "rank (<=32)", "commit", "finish split", "partition", "add_node+push", "-"};
+        const char** nm = fast ? nm_f : nm_g;
+        const int np = fast ? 11 : 12;
+        double tot = 0; for (int i = 0; i < np; ++i) tot += (double)hp[i];
+        for (int i = 0; i < np; ++i) if (hp[i]) fprintf(stderr, "[skd forest prof] tree 0 %-18s %12lld cycles %5.1f%%  (%.0f per node)\n", nm[i], hp[i], 100.0 * hp[i] / tot, (double)hp[i] / hcount[0]);
+        if (fast) fprintf(stderr, "[skd forest prof] tree 0 nodes: unstaged %lld, staged histogram %lld, staged rank %lld, leaves %lld; total %.3f Gcycles\n",
+                          hp[11], hp[12], hp[13], hp[14], tot * 1e-9);
       }
       for (int s = 0; s < nt; ++s) {
         if (hstatus[s] == 1 && node_cap < node_cap_max) { failed.push_back(pending[p0 + s]); continue; }

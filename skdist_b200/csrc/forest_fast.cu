@@ -40,10 +40,11 @@
 
 namespace skd {
 
-constexpr int FF_THREADS = 128;
+constexpr int FF_THREADS = 96;       // 7 builders x 96 threads per SM: up to 97 registers per thread, no spills
 constexpr int FF_WARPS = FF_THREADS / 32;
 constexpr int FF_KB = 8;          // speculative feature draws per batch (unstaged nodes, small staged nodes)
-constexpr int FF_KBM = 4;         // ... for staged histogram nodes: one feature per warp
+constexpr int FF_KBM = FF_WARPS;  // ... for staged histogram nodes: one feature per warp
+constexpr int FF_SMAX = 256;      // staged rows at most (local ids are bytes, packed 16-bit sums must hold 256 x 255)
 constexpr int FF_SSTK = 64;       // builder-stack entries kept in shared memory
 constexpr int FF_SMALL = 32;      // staged nodes up to this size take the ranking path
 constexpr double FF_EPSILON = 2.220446049250313e-16;
@@ -107,13 +108,13 @@ __device__ __forceinline__ double ff_proxy(const uint32_t* sl, const uint32_t* s
 
 // One warp scans the 256 bins of one feature's histogram (8 bins per lane, ascending) and leaves the
 // feature's best split in *R.  HC(c, bin) = weight of class c in the bin, HN(bin) = samples in the bin.
+// st = the node's class sums (shared memory).
 template <int CM, class HC, class HN>
 __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_node, const uint32_t* st, double w_node,
                                         int min_samples_leaf, double min_weight_leaf, FfResult<CM>* R) {
-  unsigned cntb[8];
   unsigned ltot = 0, pmask = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { cntb[j] = hn(lane * 8 + j); ltot += cntb[j]; if (cntb[j]) pmask |= 1u << j; }
+  for (int j = 0; j < 8; ++j) { const unsigned cj = hn(lane * 8 + j); ltot += cj; if (cj) pmask |= 1u << j; }
   unsigned pre = ltot;   // exclusive prefix of the sample counts over lanes
   for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
   pre -= ltot;
@@ -141,21 +142,21 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
   const int glast = __reduce_max_sync(0xffffffffu, mylast);
   const bool is_const = glast <= gfirst;      // distinct values are > 1e-7 apart (host check): one bin == constant
   double bproxy = -INFINITY;
-  int bnl = 1 << 30, bbin = 0, bnext = 0;
+  int bnl = 1 << 30, bcode = 0;
   uint32_t bsl[CM];
 #pragma unroll
   for (int c = 0; c < CM; ++c) bsl[c] = 0;
   if (!is_const) {
     unsigned run_cnt = pre;
-#pragma unroll 1
-    for (int j = 0; j < 8; ++j) {
-      if (!cntb[j]) continue;
+    unsigned pm = pmask;
+    while (pm) {                               // this lane's present bins in ascending order
+      const int j = __ffs(pm) - 1;
+      pm &= pm - 1;
       const int bb = lane * 8 + j;
-      run_cnt += cntb[j];
+      run_cnt += hn(bb);
 #pragma unroll
       for (int c = 0; c < CM; ++c) if (c < C) sl[c] += hc(c, bb);
-      const unsigned higher = pmask & ~((2u << j) - 1u);
-      const int nb2 = higher ? lane * 8 + __ffs(higher) - 1 : nxt;
+      const int nb2 = pm ? lane * 8 + __ffs(pm) - 1 : nxt;
       if (nb2 >= (1 << 20)) continue;                             // last present bin: no boundary above it
       const int n_left = (int)run_cnt, n_right = n_node - n_left;
       if (n_left < min_samples_leaf || n_right < min_samples_leaf) continue;
@@ -166,7 +167,7 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
       if (wl < min_weight_leaf || wr < min_weight_leaf) continue;
       const double proxy = ff_proxy<CM>(sl, st, C, wl, wr, nullptr, nullptr);
       if (proxy > bproxy) {
-        bproxy = proxy; bnl = n_left; bbin = bb; bnext = nb2;
+        bproxy = proxy; bnl = n_left; bcode = bb | (nb2 << 8);
 #pragma unroll
         for (int c = 0; c < CM; ++c) bsl[c] = sl[c];
       }
@@ -182,35 +183,36 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
   if (lane == 0) { R->proxy = wp; R->n_left = wnl; R->code = is_const ? (1 << 16) : 0; }
   __syncwarp();
   if (bnl == wnl && bproxy == wp && wp > -INFINITY) {   // exactly one lane: positions are unique per bin
-    R->code = bbin | (bnext << 8);
+    R->code = bcode;
 #pragma unroll
     for (int c = 0; c < CM; ++c) R->sl[c] = bsl[c];
   }
 }
 
+#define FF_TICK(ph) do { if (P.o_prof && tid == 0) { const long long _t = clock64(); s_prof[ph] += _t - tlast; tlast = _t; } } while (0)
+
 template <int CM>
-__global__ void __launch_bounds__(FF_THREADS, 7)
+// (minimum 6 blocks per SM lets ptxas use up to 112 registers; at <= 96 seven builders are resident)
+__global__ void __launch_bounds__(FF_THREADS, 6)
 forest_fast_kernel(const FfParams P) {
   typedef typename FfAcc<CM>::T acc_t;
   constexpr int CNT = FfAcc<CM>::CNT;
+  constexpr int MP = (FF_SMAX + FF_THREADS - 1) / FF_THREADS;   // passes of the staged partition
   const int slot = blockIdx.x;
   if (slot >= P.n_trees) return;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int C = P.n_classes, d = P.d, dp = P.dp;
   const int64_t n = P.n;
-  uint2* sbuf[2] = {P.samp + (size_t)slot * n, P.samp_tmp + (size_t)slot * n};
-  FfRec<CM>* gstack = reinterpret_cast<FfRec<CM>*>(P.stack) + (size_t)slot * P.stack_cap;
-  const uint8_t* cnt = P.counts + (size_t)slot * n;
-  const int64_t nb = (int64_t)slot * P.node_cap;
 
   // ---- shared memory ----
   extern __shared__ __align__(16) unsigned char ff_sm[];
   unsigned int* U = reinterpret_cast<unsigned int*>(ff_sm);                  // FF_UW words, see below
-  FfRec<CM>* sstack = reinterpret_cast<FfRec<CM>*>(U + FF_UW);               // [FF_SSTK]
-  FfItem* items = reinterpret_cast<FfItem*>(sstack + FF_SSTK);               // [FF_KB]
+  FfRec<CM>* sstack = reinterpret_cast<FfRec<CM>*>(U + FF_UW);               // [FF_SSTK + 1]; the last one: spill copy
+  FfItem* items = reinterpret_cast<FfItem*>(sstack + FF_SSTK + 1);           // [FF_KB]
   FfResult<CM>* results = reinterpret_cast<FfResult<CM>*>(items + FF_KB);    // [FF_KB]
   double* s_dbl = reinterpret_cast<double*>(results + FF_KB);                // [4]
-  int* s_ctrl = reinterpret_cast<int*>(s_dbl + 4);                           // [16]
+  long long* s_prof = reinterpret_cast<long long*>(s_dbl + 4);               // [16]
+  int* s_ctrl = reinterpret_cast<int*>(s_prof + 16);                         // [16]
   int* wsum = s_ctrl + 16;                                                   // [32]
   uint32_t* best_sl = reinterpret_cast<uint32_t*>(wsum + 32);                // [4]
   uint8_t* features = reinterpret_cast<uint8_t*>(best_sl + 4);               // [d]
@@ -220,62 +222,68 @@ forest_fast_kernel(const FfParams P) {
   const int hstrideA = (C + 1) * 256;
   const int KBA = min(FF_KB, FF_UW / hstrideA);
   // U, staged subtree: rows[S][ws] bin codes | histB[FF_KBM][hbw] packed 16-bit | ord[S] u8 | wcls[S] u16
-  const int S = P.stage_rows, ws = P.stage_ws;
+  const int S = P.stage_rows, ws4 = P.stage_ws * 4;
   const int hcw = 256 * ((C + 1) >> 1);          // packed class-pair words per feature
   const int hbw = hcw + 128;                     // + packed sample counts
   const uint8_t* rowsB = reinterpret_cast<const uint8_t*>(U);
-  unsigned int* histB = U + S * ws;
+  unsigned int* histB = U + S * P.stage_ws;
   uint8_t* ord = reinterpret_cast<uint8_t*>(histB + FF_KBM * hbw);
   uint16_t* wcls = reinterpret_cast<uint16_t*>(ord + S);
+  long long tlast = 0;
+  if (tid < 16) s_prof[tid] = 0;
 
   // ---- initialise the tree: samples with non-zero weight in ascending order (Splitter.init) ----
   for (int i = tid; i < d; i += FF_THREADS) features[i] = (uint8_t)i;
-  uint32_t my_sums[CM];
-#pragma unroll
-  for (int c = 0; c < CM; ++c) my_sums[c] = 0;
-  int base = 0;
-  for (int64_t i0 = 0; i0 < n; i0 += FF_THREADS * 4) {
-    unsigned w4[4], y4[4];
-    int keep4[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int64_t i = i0 + q * FF_THREADS + tid;
-      w4[q] = 0; y4[q] = 0;
-      if (i < n) { w4[q] = cnt[i]; y4[q] = (unsigned)P.ycls[i]; }
-      keep4[q] = w4[q] != 0;
-      const unsigned bal = __ballot_sync(0xffffffffu, keep4[q]);
-      if (lane == 0) wsum[q * FF_WARPS + wid] = __popc(bal);
-      keep4[q] |= (int)(__popc(bal & ((1u << lane) - 1)) << 1);   // rank within the warp above bit 0
-    }
-    __syncthreads();
-    int tot = 0, off4[4];
-#pragma unroll
-    for (int k = 0; k < 4 * FF_WARPS; ++k) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) if (k == q * FF_WARPS + wid) off4[q] = tot;
-      tot += wsum[k];
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (keep4[q] & 1) {
-        const int64_t i = i0 + q * FF_THREADS + tid;
-        sbuf[0][base + off4[q] + (keep4[q] >> 1)] = make_uint2((unsigned)i, (w4[q] << 8) | y4[q]);
-#pragma unroll
-        for (int c = 0; c < CM; ++c) if ((int)y4[q] == c) my_sums[c] += w4[q];
-      }
-    }
-    base += tot;
-    __syncthreads();
-  }
-  const int n_nz = base;
   if (tid < 4) best_sl[tid] = 0;
   __syncthreads();
+  int n_nz = 0;
+  {
+    const uint8_t* cnt = P.counts + (size_t)slot * n;
+    uint2* dst = P.samp + (size_t)slot * n;
+    uint32_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;      // class sums of this thread (CM <= 4)
+    int base = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += FF_THREADS * 4) {
+      unsigned w4[4], y4[4];
+      int rk4[4];
 #pragma unroll
-  for (int c = 0; c < CM; ++c) {
-    if (c < C) {
-      uint32_t v = my_sums[c];
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) atomicAdd(&best_sl[c], v);
+      for (int q = 0; q < 4; ++q) {
+        const int64_t i = i0 + q * FF_THREADS + tid;
+        w4[q] = 0; y4[q] = 0;
+        if (i < n) { w4[q] = cnt[i]; y4[q] = (unsigned)P.ycls[i]; }
+        const unsigned bal = __ballot_sync(0xffffffffu, w4[q] != 0);
+        if (lane == 0) wsum[q * FF_WARPS + wid] = __popc(bal);
+        rk4[q] = __popc(bal & ((1u << lane) - 1));
+      }
+      __syncthreads();
+      int tot = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int k = 0; k < FF_WARPS; ++k) {
+          if (k == wid) rk4[q] += tot;
+          tot += wsum[q * FF_WARPS + k];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (w4[q] != 0) {
+          const int64_t i = i0 + q * FF_THREADS + tid;
+          dst[base + rk4[q]] = make_uint2((unsigned)i, (w4[q] << 8) | y4[q]);
+          s0 += y4[q] == 0 ? w4[q] : 0; s1 += y4[q] == 1 ? w4[q] : 0;
+          if (CM > 2) { s2 += y4[q] == 2 ? w4[q] : 0; s3 += y4[q] == 3 ? w4[q] : 0; }
+        }
+      }
+      base += tot;
+      __syncthreads();
+    }
+    n_nz = base;
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      if (CM > 2) { s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o); }
+    }
+    if (lane == 0) {
+      atomicAdd(&best_sl[0], s0); atomicAdd(&best_sl[1], s1);
+      if (CM > 2) { atomicAdd(&best_sl[2], s2); atomicAdd(&best_sl[3], s3); }
     }
   }
   __syncthreads();
@@ -297,57 +305,65 @@ forest_fast_kernel(const FfParams P) {
   sp = 1;
   bool first = true;
   __syncthreads();
+  if (P.o_prof) tlast = clock64();
 
   while (sp > 0 && status == 0) {
     --sp;
-    // the popped record is copied to registers: its stack slot is overwritten by this node's own push
-    FfRec<CM> rec = sp < FF_SSTK ? sstack[sp] : gstack[sp];
-    const int start = rec.start, end = rec.end, depth = rec.depth;
+    // the popped record is read in place (its stack slot is only overwritten by this node's own push,
+    // after the last read); records beyond the shared part of the stack come back through the spill copy
+    if (sp >= FF_SSTK) {
+      if (tid == 0) sstack[FF_SSTK] = (reinterpret_cast<const FfRec<CM>*>(P.stack) + (size_t)slot * P.stack_cap)[sp];
+      __syncthreads();
+    }
+    const FfRec<CM>* rec = &sstack[sp < FF_SSTK ? sp : FF_SSTK];
+    const int start = rec->start, end = rec->end, depth = rec->depth;
     const int n_node = end - start;
-    const int cur = (rec.flags >> 17) & 1;
-    const int n_known = rec.flags & 0xFFFF;
+    const int n_known = rec->flags & 0xFFFF;
     double w_node = 0.0;
 #pragma unroll
-    for (int c = 0; c < CM; ++c) if (c < C) w_node += (double)rec.sums[c];
-    double impurity = rec.impurity;
+    for (int c = 0; c < CM; ++c) if (c < C) w_node += (double)rec->sums[c];
+    double impurity = rec->impurity;
     bool is_leaf = depth >= P.max_depth || n_node < P.min_samples_split || n_node < 2 * P.min_samples_leaf ||
                    w_node < 2.0 * P.min_weight_leaf;
     if (first) {   // root: node_impurity()  (SK/tree/_criterion.pyx:620-640)
       double sq = 0.0;
 #pragma unroll
-      for (int c = 0; c < CM; ++c) if (c < C) { const double a = (double)rec.sums[c]; sq = __dadd_rn(sq, __dmul_rn(a, a)); }
+      for (int c = 0; c < CM; ++c) if (c < C) { const double a = (double)rec->sums[c]; sq = __dadd_rn(sq, __dmul_rn(a, a)); }
       impurity = __dsub_rn(1.0, __ddiv_rn(sq, __dmul_rn(w_node, w_node)));
       first = false;
     }
     is_leaf = is_leaf || impurity <= FF_EPSILON;
+    FF_TICK(0);
 
-    int best_feature = 0, best_nl = -1, best_code = 0, n_total_constants = n_known, best_mgl = 0;
-    double best_il = 0.0, best_ir = 0.0, best_improvement = 0.0;
+    int best_feature = 0, best_nl = -1, best_code = 0, n_total_constants = n_known;
     bool staged = false;
     if (!is_leaf) {
+      const int cur = (rec->flags >> 17) & 1;
       // ---------------------------- stage a small subtree ------------------------------------
       staged = start >= st_base && end <= st_end;
       if (!staged && n_node <= S) {
-        const uint2* src = sbuf[cur] + start;
+        const uint2* src = (cur ? P.samp_tmp : P.samp) + (size_t)slot * n + start;
         const int cpr = dp >> 4;                       // 16-byte chunks per row
         for (int q = tid; q < n_node * cpr; q += FF_THREADS) {
           const int j = q / cpr, cc = q - j * cpr;
           const uint2 sv = src[j];
           const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.xrow + (size_t)sv.x * dp) + cc);
-          unsigned int* dst = U + j * ws + cc * 4;
-          if (cc * 4 + 0 < ws) dst[0] = v.x;
-          if (cc * 4 + 1 < ws) dst[1] = v.y;
-          if (cc * 4 + 2 < ws) dst[2] = v.z;
-          if (cc * 4 + 3 < ws) dst[3] = v.w;
+          unsigned int* dstw = U + j * P.stage_ws + cc * 4;
+          if (cc * 4 + 0 < P.stage_ws) dstw[0] = v.x;
+          if (cc * 4 + 1 < P.stage_ws) dstw[1] = v.y;
+          if (cc * 4 + 2 < P.stage_ws) dstw[2] = v.z;
+          if (cc * 4 + 3 < P.stage_ws) dstw[3] = v.w;
           if (cc == 0) { ord[j] = (uint8_t)j; wcls[j] = (uint16_t)sv.y; }
         }
         st_base = start; st_end = end;
         staged = true;
         __syncthreads();
+        FF_TICK(1);
       }
       const int ls = start - st_base;                 // staged: the node is ord[ls, ls + n_node)
       const bool small = staged && n_node <= FF_SMALL;
       const int KB = staged ? (small ? FF_KB : FF_KBM) : KBA;
+      if (P.o_prof && tid == 0) s_prof[staged ? (small ? 13 : 12) : 11] += 1;
 
       // ------------------------------- node_split_best -------------------------------------
       int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0;
@@ -374,9 +390,8 @@ forest_fast_kernel(const FfParams P) {
               continue;
             }
             fj += n_found;
-            FfItem it;
-            it.f = features[fj]; it.fj = fj; it.rs = s_rs; it.nv = s_nv; it.nd = s_nd; it.fi = s_fi; it.ulen = ulen; it.pad_ = 0;
-            items[nbatch] = it;
+            FfItem* it = &items[nbatch];
+            it->f = features[fj]; it->fj = fj; it->rs = s_rs; it->nv = s_nv; it->nd = s_nd; it->fi = s_fi; it->ulen = ulen;
             s_fi -= 1;          // speculative: not constant
             { const uint8_t t = features[s_fi]; features[s_fi] = features[fj]; features[fj] = t; }
             undo[2 * ulen] = (uint8_t)s_fi; undo[2 * ulen + 1] = (uint8_t)fj; ++ulen;
@@ -389,16 +404,14 @@ forest_fast_kernel(const FfParams P) {
           for (int i = tid - 32; i < KBA * hstrideA; i += FF_THREADS - 32) U[i] = 0;   // meanwhile: clear the histograms
         }
         __syncthreads();
+        FF_TICK(2);
         const int nbatch = s_ctrl[0];
         if (nbatch == 0) break;
 
         if (!staged) {
           // ---- histograms of all batch features in one pass over the node's samples (global gathers:
           // the drawn features of a sample share one 64-byte row of codes) ----
-          int fk[FF_KB];
-#pragma unroll
-          for (int k = 0; k < FF_KB; ++k) fk[k] = items[k < nbatch ? k : 0].f;
-          const uint2* src = sbuf[cur];
+          const uint2* src = (cur ? P.samp_tmp : P.samp) + (size_t)slot * n;
           for (int i = start + tid; i < end; i += 2 * FF_THREADS) {
             const int i2 = i + FF_THREADS;
             const bool has2 = i2 < end;
@@ -409,8 +422,9 @@ forest_fast_kernel(const FfParams P) {
             unsigned ba[FF_KB], bb[FF_KB];
 #pragma unroll
             for (int k = 0; k < FF_KB; ++k) {
-              ba[k] = k < nbatch ? (unsigned)__ldg(ra + fk[k]) : 0u;
-              bb[k] = k < nbatch ? (unsigned)__ldg(rb + fk[k]) : 0u;
+              const int fk = items[k < nbatch ? k : 0].f;
+              ba[k] = (unsigned)__ldg(ra + fk);
+              bb[k] = (unsigned)__ldg(rb + fk);
             }
             const unsigned ca = sa.y & 0xFF, wa = sa.y >> 8, cb = sb.y & 0xFF, wb = sb.y >> 8;
 #pragma unroll
@@ -427,11 +441,12 @@ forest_fast_kernel(const FfParams P) {
             }
           }
           __syncthreads();
+          FF_TICK(3);
           for (int k = wid; k < nbatch; k += FF_WARPS) {
             const unsigned int* H = U + k * hstrideA;
             ff_scan<CM>([&](int c, int b) -> uint32_t { return H[c * 256 + b]; },
                         [&](int b) -> unsigned { return H[C * 256 + b]; },
-                        lane, C, n_node, rec.sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[k]);
+                        lane, C, n_node, rec->sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[k]);
           }
         } else if (!small) {
           // ---- staged histogram node: warp k builds and scans the packed histogram of item k ----
@@ -442,7 +457,7 @@ forest_fast_kernel(const FfParams P) {
             const int f = items[wid].f;
             for (int i = lane; i < n_node; i += 32) {
               const int lid = ord[ls + i];
-              const unsigned b = rowsB[lid * (ws * 4) + f];
+              const unsigned b = rowsB[lid * ws4 + f];
               const unsigned wc = wcls[lid];
               const unsigned cls = wc & 0xFF, w = wc >> 8;
               atomicAdd(&H[(cls >> 1) * 256 + b], w << ((cls & 1) * 16));
@@ -451,7 +466,7 @@ forest_fast_kernel(const FfParams P) {
             __syncwarp();
             ff_scan<CM>([&](int c, int b) -> uint32_t { return (H[(c >> 1) * 256 + b] >> ((c & 1) * 16)) & 0xFFFFu; },
                         [&](int b) -> unsigned { return (H[hcw + (b >> 1)] >> ((b & 1) * 16)) & 0xFFFFu; },
-                        lane, C, n_node, rec.sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[wid]);
+                        lane, C, n_node, rec->sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[wid]);
           }
         } else {
           // ---- staged node of <= 32 samples: lane j holds sample j; every lane counts the samples
@@ -463,10 +478,10 @@ forest_fast_kernel(const FfParams P) {
           const acc_t pw = have ? (((acc_t)(wc >> 8) << (13 * (wc & 0xFF))) | ((acc_t)1 << CNT)) : (acc_t)0;
           for (int k = wid; k < nbatch; k += FF_WARPS) {
             const int f = items[k].f;
-            const unsigned key = have ? (unsigned)rowsB[lid * (ws * 4) + f] : 0xFFFFu;
+            const unsigned key = have ? (unsigned)rowsB[lid * ws4 + f] : 0xFFFFu;
             acc_t acc = 0;
             unsigned nbn = 0xFFFFu;        // smallest bin above this lane's bin present in the node
-#pragma unroll 1
+#pragma unroll 4
             for (int j = 0; j < n_node; ++j) {
               const unsigned bj = __shfl_sync(0xffffffffu, key, j);
               const acc_t pj = __shfl_sync(0xffffffffu, pw, j);
@@ -488,7 +503,7 @@ forest_fast_kernel(const FfParams P) {
                 for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
                 const double wr = w_node - wl;
                 if (!(wl < P.min_weight_leaf || wr < P.min_weight_leaf)) {
-                  proxy = ff_proxy<CM>(sl, rec.sums, C, wl, wr, nullptr, nullptr);
+                  proxy = ff_proxy<CM>(sl, rec->sums, C, wl, wr, nullptr, nullptr);
                   n_left = nl;
                 }
               }
@@ -512,6 +527,7 @@ forest_fast_kernel(const FfParams P) {
           }
         }
         __syncthreads();
+        FF_TICK(staged ? (small ? 6 : 5) : 4);
         // --- thread 0: commit in draw order, roll back at the first constant feature ---
         if (tid == 0) {
           bool rolled = false;
@@ -542,6 +558,7 @@ forest_fast_kernel(const FfParams P) {
           if (!rolled) { f_i = s_ctrl[1]; n_visited = s_ctrl[7]; n_drawn = s_ctrl[8]; rstate = (uint32_t)s_ctrl[9]; }
         }
         __syncthreads();
+        FF_TICK(7);
       }
       // end of node_split_best: children impurities, improvement, constant-feature invariants
       if (tid == 0) {
@@ -552,7 +569,7 @@ forest_fast_kernel(const FfParams P) {
           for (int c = 0; c < CM; ++c) if (c < C) wl += (double)best_sl[c];
           const double wr = w_node - wl;
           double il, ir;
-          ff_proxy<CM>(best_sl, rec.sums, C, wl, wr, &il, &ir);
+          ff_proxy<CM>(best_sl, rec->sums, C, wl, wr, &il, &ir);
           // impurity_improvement (SK/tree/_criterion.pyx:163-190)
           const double a = __dmul_rn(__ddiv_rn(wr, w_node), ir);
           const double b = __dmul_rn(__ddiv_rn(wl, w_node), il);
@@ -564,12 +581,11 @@ forest_fast_kernel(const FfParams P) {
       }
       __syncthreads();
       best_nl = s_ctrl[2]; best_feature = s_ctrl[3]; best_code = s_ctrl[4]; n_total_constants = s_ctrl[5];
-      best_il = s_dbl[0]; best_ir = s_dbl[1]; best_improvement = s_dbl[2];
       // restore / record the constant-feature prefix (the memcpy pair at the end of node_split_best)
       for (int i = tid; i < n_known; i += FF_THREADS) features[i] = constant_features[i];
       for (int i = n_known + tid; i < n_total_constants; i += FF_THREADS) constant_features[i] = features[i];
-      is_leaf = best_nl <= 0 || (best_improvement + FF_EPSILON < P.min_impurity_decrease);
-      best_mgl = best_nl > (n_node - best_nl);
+      is_leaf = best_nl <= 0 || (s_dbl[2] + FF_EPSILON < P.min_impurity_decrease);
+      FF_TICK(8);
 
       if (best_nl > 0) {
         const unsigned best_bin = (unsigned)(best_code & 0xFF);
@@ -579,7 +595,7 @@ forest_fast_kernel(const FfParams P) {
             if (wid == 0) {
               const bool have = lane < n_node;
               const int lid = have ? ord[ls + lane] : 0;
-              const bool isl = have && rowsB[lid * (ws * 4) + best_feature] <= best_bin;
+              const bool isl = have && rowsB[lid * ws4 + best_feature] <= best_bin;
               const unsigned bl = __ballot_sync(0xffffffffu, isl);
               const unsigned br = __ballot_sync(0xffffffffu, have && !isl);
               const unsigned lt = (1u << lane) - 1;
@@ -587,41 +603,44 @@ forest_fast_kernel(const FfParams P) {
               if (have) ord[ls + (isl ? __popc(bl & lt) : best_nl + __popc(br & lt))] = (uint8_t)lid;
             }
           } else {
-            // up to 256 entries: two per thread, order = (pass, warp, lane)
-            int lid2[2], isl2[2], rk2[2];
+            // up to S entries, MP per thread, order = (pass, warp, lane)
+            int lidp[MP], posp[MP];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < MP; ++q) {
               const int i = q * FF_THREADS + tid;
               const bool have = i < n_node;
-              lid2[q] = have ? ord[ls + i] : 0;
-              const bool isl = have && rowsB[lid2[q] * (ws * 4) + best_feature] <= best_bin;
+              lidp[q] = have ? ord[ls + i] : 0;
+              const bool isl = have && rowsB[lidp[q] * ws4 + best_feature] <= best_bin;
               const unsigned bl = __ballot_sync(0xffffffffu, isl);
               const unsigned br = __ballot_sync(0xffffffffu, have && !isl);
               const unsigned lt = (1u << lane) - 1;
-              isl2[q] = have ? (isl ? 1 : 0) : -1;
-              rk2[q] = isl ? __popc(bl & lt) : __popc(br & lt);
+              // rank within the warp; bit 30: goes right; -1: no element
+              posp[q] = have ? (isl ? __popc(bl & lt) : (__popc(br & lt) | (1 << 30))) : -1;
               if (lane == 0) { wsum[(q * FF_WARPS + wid) * 2] = __popc(bl); wsum[(q * FF_WARPS + wid) * 2 + 1] = __popc(br); }
             }
             __syncthreads();
-            int lo = 0, ro = 0, off[2][2];
+            int lo = 0, ro = 0;
 #pragma unroll
-            for (int k = 0; k < 2 * FF_WARPS; ++k) {
+            for (int q = 0; q < MP; ++q) {
 #pragma unroll
-              for (int q = 0; q < 2; ++q) if (k == q * FF_WARPS + wid) { off[q][0] = lo; off[q][1] = ro; }
-              lo += wsum[2 * k]; ro += wsum[2 * k + 1];
+              for (int k = 0; k < FF_WARPS; ++k) {
+                if (k == wid && posp[q] >= 0) posp[q] += (posp[q] & (1 << 30)) ? ro : lo;
+                lo += wsum[(q * FF_WARPS + k) * 2]; ro += wsum[(q * FF_WARPS + k) * 2 + 1];
+              }
             }
 #pragma unroll
-            for (int q = 0; q < 2; ++q)
-              if (isl2[q] >= 0) ord[ls + (isl2[q] ? off[q][0] + rk2[q] : best_nl + off[q][1] + rk2[q])] = (uint8_t)lid2[q];
+            for (int q = 0; q < MP; ++q)
+              if (posp[q] >= 0)
+                ord[ls + ((posp[q] & (1 << 30)) ? best_nl + (posp[q] & ~(1 << 30)) : posp[q])] = (uint8_t)lidp[q];
           }
         } else {
           // --- partition_samples_final: stable partition into the other sample buffer ---
-          const uint2* src = sbuf[cur];
-          uint2* dst = sbuf[cur ^ 1];
+          const uint2* src = (cur ? P.samp_tmp : P.samp) + (size_t)slot * n;
+          uint2* dst = (cur ? P.samp : P.samp_tmp) + (size_t)slot * n;
           int loff = start, roff = start + best_nl;
           for (int i0 = start; i0 < end; i0 += 4 * FF_THREADS) {
             uint2 sv4[4];
-            int isl4[4], rk4[4];
+            int pos4[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int i = i0 + q * FF_THREADS + tid;
@@ -631,34 +650,40 @@ forest_fast_kernel(const FfParams P) {
               const unsigned bl = __ballot_sync(0xffffffffu, isl);
               const unsigned br = __ballot_sync(0xffffffffu, have && !isl);
               const unsigned lt = (1u << lane) - 1;
-              isl4[q] = have ? (isl ? 1 : 0) : -1;
-              rk4[q] = isl ? __popc(bl & lt) : __popc(br & lt);
+              pos4[q] = have ? (isl ? __popc(bl & lt) : (__popc(br & lt) | (1 << 30))) : -1;
               if (lane == 0) { wsum[(q * FF_WARPS + wid) * 2] = __popc(bl); wsum[(q * FF_WARPS + wid) * 2 + 1] = __popc(br); }
             }
             __syncthreads();
-            int lo = 0, ro = 0, off[4][2];
+            int lo = 0, ro = 0;
 #pragma unroll
-            for (int k = 0; k < 4 * FF_WARPS; ++k) {
+            for (int q = 0; q < 4; ++q) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) if (k == q * FF_WARPS + wid) { off[q][0] = lo; off[q][1] = ro; }
-              lo += wsum[2 * k]; ro += wsum[2 * k + 1];
+              for (int k = 0; k < FF_WARPS; ++k) {
+                if (k == wid && pos4[q] >= 0) pos4[q] += (pos4[q] & (1 << 30)) ? ro : lo;
+                lo += wsum[(q * FF_WARPS + k) * 2]; ro += wsum[(q * FF_WARPS + k) * 2 + 1];
+              }
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              if (isl4[q] >= 0) dst[isl4[q] ? loff + off[q][0] + rk4[q] : roff + off[q][1] + rk4[q]] = sv4[q];
+              if (pos4[q] >= 0) dst[(pos4[q] & (1 << 30)) ? roff + (pos4[q] & ~(1 << 30)) : loff + pos4[q]] = sv4[q];
             loff += lo; roff += ro;
             __syncthreads();
           }
         }
       }
+      FF_TICK(9);
+    } else if (P.o_prof && tid == 0) {
+      s_prof[14] += 1;
     }
 
     // ------------------------------- _add_node + node_value --------------------------------
     const int node_id = node_count;
     if (node_id >= P.node_cap) { status = 1; break; }
     if (tid == 0) {
-      if (rec.parent >= 0) {
-        if (rec.flags & (1 << 16)) P.o_left[nb + rec.parent] = node_id; else P.o_right[nb + rec.parent] = node_id;
+      const int64_t nb = (int64_t)slot * P.node_cap;
+      const int flags = rec->flags;
+      if (rec->parent >= 0) {
+        if (flags & (1 << 16)) P.o_left[nb + rec->parent] = node_id; else P.o_right[nb + rec->parent] = node_id;
       }
       P.o_imp[nb + node_id] = impurity;
       P.o_nsamp[nb + node_id] = n_node;
@@ -670,40 +695,46 @@ forest_fast_kernel(const FfParams P) {
         P.o_feature[nb + node_id] = best_feature;
         // the two bins around the threshold; ff_threshold_kernel turns them into v[a]/2 + v[b]/2
         P.o_thr[nb + node_id] = __longlong_as_double((long long)(best_code & 0xFFFF));
-        P.o_mgl[nb + node_id] = (uint8_t)best_mgl;
+        P.o_mgl[nb + node_id] = (uint8_t)(best_nl > (n_node - best_nl));
       }
 #pragma unroll
       for (int c = 0; c < CM; ++c)
-        if (c < C) P.o_val[(nb + node_id) * C + c] = __ddiv_rn((double)rec.sums[c], w_node);   // class fractions
+        if (c < C) P.o_val[(nb + node_id) * C + c] = __ddiv_rn((double)rec->sums[c], w_node);   // class fractions
     }
     node_count += 1;
     if (!is_leaf) {
       if (sp + 2 > P.stack_cap) { status = 2; break; }
       if (tid == 0) {
-        const int child_buf = staged ? cur : (cur ^ 1);
-        FfRec<CM> r;
-        r.depth = depth + 1; r.parent = node_id; r.pad_ = 0;
+        FfRec<CM>* gstack = reinterpret_cast<FfRec<CM>*>(P.stack) + (size_t)slot * P.stack_cap;
+        const int child_buf = staged ? ((rec->flags >> 17) & 1) : (((rec->flags >> 17) & 1) ^ 1);
+        FfRec<CM> rr, rl;
+        rr.depth = depth + 1; rr.parent = node_id; rr.pad_ = 0;
         // right child first, then left (popped first)
-        r.start = start + best_nl; r.end = end; r.flags = n_total_constants | (child_buf << 17); r.impurity = best_ir;
+        rr.start = start + best_nl; rr.end = end; rr.flags = n_total_constants | (child_buf << 17); rr.impurity = s_dbl[1];
+        rl = rr;
+        rl.start = start; rl.end = start + best_nl; rl.flags = n_total_constants | (1 << 16) | (child_buf << 17); rl.impurity = s_dbl[0];
 #pragma unroll
-        for (int c = 0; c < CM; ++c) r.sums[c] = c < C ? rec.sums[c] - best_sl[c] : 0;
-        if (sp < FF_SSTK) sstack[sp] = r; else gstack[sp] = r;
-        r.start = start; r.end = start + best_nl; r.flags = n_total_constants | (1 << 16) | (child_buf << 17); r.impurity = best_il;
-#pragma unroll
-        for (int c = 0; c < CM; ++c) r.sums[c] = c < C ? best_sl[c] : 0;
-        if (sp + 1 < FF_SSTK) sstack[sp + 1] = r; else gstack[sp + 1] = r;
+        for (int c = 0; c < CM; ++c) {
+          rr.sums[c] = c < C ? rec->sums[c] - best_sl[c] : 0;
+          rl.sums[c] = c < C ? best_sl[c] : 0;
+        }
+        if (sp < FF_SSTK) sstack[sp] = rr; else gstack[sp] = rr;
+        if (sp + 1 < FF_SSTK) sstack[sp + 1] = rl; else gstack[sp + 1] = rl;
       }
       sp += 2;
     }
     if (depth > max_depth_seen) max_depth_seen = depth;
+    FF_TICK(10);
     __syncthreads();
   }
   if (tid == 0) {
     P.o_count[slot] = node_count;
     P.o_maxdepth[slot] = max_depth_seen;
     P.o_status[slot] = status;
+    if (P.o_prof) for (int i = 0; i < 16; ++i) P.o_prof[(size_t)slot * 16 + i] = s_prof[i];
   }
 }
+#undef FF_TICK
 
 // threshold of every internal node from the two bins the builder left in o_thr:
 // v[p-1]/2 + v[p] /2 in float64 (SK/tree/_splitter.pyx:459-461)
@@ -725,7 +756,7 @@ __global__ void ff_threshold_kernel(const float* __restrict__ binval, const int3
 static size_t ff_smem_bytes(int CM, int d) {
   const size_t rec = CM <= 2 ? sizeof(FfRec<2>) : sizeof(FfRec<4>);
   const size_t res = CM <= 2 ? sizeof(FfResult<2>) : sizeof(FfResult<4>);
-  return (size_t)FF_UW * 4 + FF_SSTK * rec + FF_KB * sizeof(FfItem) + FF_KB * res + 4 * 8 + 16 * 4 + 32 * 4 + 4 * 4 +
+  return (size_t)FF_UW * 4 + (FF_SSTK + 1) * rec + FF_KB * sizeof(FfItem) + FF_KB * res + 4 * 8 + 16 * 8 + 16 * 4 + 32 * 4 + 4 * 4 +
          2 * (size_t)((d + 3) & ~3) + 2 * (size_t)(d + 16) + 16;
 }
 
@@ -734,7 +765,7 @@ static int ff_stage_rows(int d, int n_classes, int* ws_out) {
   const int ws = ((d + 3) / 4) | 1;                           // odd word stride: conflict-free column reads
   const int hbw = 256 * ((n_classes + 1) / 2) + 128;
   int S = (FF_UW - FF_KBM * hbw) * 4 / (ws * 4 + 3);
-  S = std::min(256, S / 32 * 32);
+  S = std::min(FF_SMAX, S / 32 * 32);
   *ws_out = ws;
   return S >= 64 ? S : 0;
 }

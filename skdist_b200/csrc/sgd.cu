@@ -438,6 +438,9 @@ int sgd_fit_batch(Ctx* c, int B, const int32_t* col_pos, int loss, double alpha,
   const int64_t n = c->n;
   const int d = (int)c->d, ldx = (int)c->ldx;
   if (d > 1024) return fail(c, "sgd: device path supports d <= 1024");
+  if (sgd_tc_supported(c, loss, shuffle))     // hinge: blocked-exact on the tensor cores (sgd_tc.cu), same results
+    return sgd_fit_batch_tc(c, B, col_pos, alpha, fit_intercept, max_iter, tol, shuffle, seed, lr_type, eta0, power_t,
+                            optimal_init, n_iter_no_change, coef_out, intercept_out, n_iter_out, t_out, status_out);
   int dpl = 1;
   while (dpl * 32 < d) dpl *= 2;
   const int ldw = dpl * 32;

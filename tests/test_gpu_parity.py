@@ -281,6 +281,32 @@ def test_ovr_sgd_exact_order_on_device(eng):
     np.testing.assert_array_equal(ovr.predict(X), ref.predict(X))
 
 
+@pytest.mark.parametrize("n,d,k,alpha", [(9000, 40, 7, 1e-4), (5000, 100, 5, 1e-4), (6000, 24, 4, 100.0)])
+def test_ovr_sgd_tensor_core_path_bit_identical(eng, monkeypatch, n, d, k, alpha):
+    """The blocked-exact tensor-core path (csrc/sgd_tc.cu: fp16 tcgen05 products S = X_T W^T and
+    G = X_T X_T^T screen the margins of 2048-sample blocks, every sample that does not clear 1 by the
+    error bound gets the exact dot product) gives the same coefficients, intercepts, n_iter_ and t_
+    as scikit-learn bit for bit.  alpha = 100 makes the lazy scale fall below 1e-6 (at the first sample and
+    again near sample 31 624)
+    (reset_wscale: every column rescales its weights at the same sample); n is not a multiple of the
+    block so the last block is ragged."""
+    from sklearn.linear_model import SGDClassifier
+    from sklearn.multiclass import OneVsRestClassifier
+    from skdist.distribute.multiclass import DistOneVsRestClassifier
+    from skdist_b200.datasets import make_multiclass
+    import warnings
+    monkeypatch.setenv("SKDIST_B200_SGD_KERNEL", "tc")
+    X, y = make_multiclass(n, d, k, seed=n % 17)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ovr = DistOneVsRestClassifier(SGDClassifier(random_state=0, alpha=alpha), None).fit(X, y)
+        ref = OneVsRestClassifier(SGDClassifier(random_state=0, alpha=alpha)).fit(X, y)
+    for a, b in zip(ovr.estimators_, ref.estimators_):
+        assert a.n_iter_ == b.n_iter_ and a.t_ == b.t_
+        np.testing.assert_array_equal(a.coef_, b.coef_)
+        np.testing.assert_array_equal(a.intercept_, b.intercept_)
+
+
 def test_ovr_sgd_log_loss_on_device(eng):
     """log_loss SGD evaluates sklearn 1.9's CyHalfBinomialLoss formulas (y in {0,1}) in the same
     order, but exp/log/log1p come from CUDA's libdevice instead of glibc (both < 1 ulp, not
