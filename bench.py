@@ -4,6 +4,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path
+    python bench.py --config {3,4,5} ...                           # the other BASELINE.json configs (bench_configs.py)
 
 A "step" is one complete pass of the hot path: every (candidate, fold) column fitted with
 the batched L-BFGS solver and scored on its held-out rows.  `value` is measured with
@@ -36,13 +37,20 @@ def parse():
     p.add_argument("--steps", type=int, default=2)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--n", type=int, default=1_000_000)
-    p.add_argument("--d", type=int, default=256)
+    p.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                   help="BASELINE.json configs[k - 1]: 2 = the headline (default), 3 OvR-SGD, 4 forest, 5 Ridge search + predict "
+                        "(bench_configs.py)")
+    p.add_argument("--n", type=int, default=0, help="rows (0 = the config's size)")
+    p.add_argument("--d", type=int, default=0, help="features (0 = the config's size)")
     p.add_argument("--candidates", type=int, default=512)
     p.add_argument("--folds", type=int, default=5)
     p.add_argument("--cpu-sample", type=int, default=40, help="fits timed for cpu_baseline / compared for parity (0 = skip)")
     p.add_argument("--kernel", type=int, default=0, help="0 auto, 1 SIMT fp32, 2 tcgen05")
-    return p.parse_args()
+    a = p.parse_args()
+    if a.config == 2:
+        a.n = a.n or 1_000_000
+        a.d = a.d or 256
+    return a
 
 
 def peaks():
@@ -244,6 +252,11 @@ def run_reference(a):
 
 def main():
     a = parse()
+    if a.config != 2:
+        import bench_configs
+        if a.impl == "reference":
+            return bench_configs.run_reference(a)
+        return bench_configs.run(a, ClockSampler, peaks)
     if a.impl == "reference":
         return run_reference(a)
 
