@@ -213,6 +213,7 @@ struct TcParams {
   int n_lists, n_tiles_ld;
   const float* rowsg;        // TC_FIT_UNI: [n_lists x npad] per-row -y * 2^14 (0 = not a training row of that list)
   long long rowsg_ld;
+  int g_passes;              // MMA passes of the gradient product: 3 = G_hi X_hi + G_lo X_hi + G_hi X_lo, 2 = without G_lo X_hi
   int debug;                 // SKDIST_B200_TC_DEBUG (timing experiments only): 2 = no GEMM2, 3 = no MMAs, 4 = no epilogue work
 };
 
@@ -429,7 +430,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
 #pragma unroll
             for (int ks = 0; ks < TC_R / 16; ++ks) {
               mma_ts(tmem + TM_GRAD, gcol + ks * 16, bh + ks * 128, idesc2, (first_tile && ks == 0) ? 0u : 1u);
-              mma_ts(tmem + TM_GRAD, gcol + ks * 16 + 8, bh + ks * 128, idesc2, 1u);
+              if (prm.g_passes >= 3) mma_ts(tmem + TM_GRAD, gcol + ks * 16 + 8, bh + ks * 128, idesc2, 1u);
             }
             }
             tc_commit(&bars->empty[sl_h]);
@@ -912,6 +913,7 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   prm.n_tiles = n_tiles;
   prm.ldw = w.ldw;
   { const char* dbg = getenv("SKDIST_B200_TC_DEBUG"); prm.debug = dbg ? atoi(dbg) : 0; }
+  { const char* gp = getenv("SKDIST_B200_TC_GPASSES"); prm.g_passes = gp ? atoi(gp) : 3; }
   const bool uni = mode == TC_FIT && w.grouped && w.uni_pos >= 0 && c->ycls;
   if (uni && (!t.rowsg_valid || t.rowsg_pos != w.uni_pos)) {
     if (!t.rowsg) SKD_CUDA(c, cudaMalloc((void**)&t.rowsg, (size_t)t.n_lists * t.npad * sizeof(float)));

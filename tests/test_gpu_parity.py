@@ -46,6 +46,9 @@ def _case(name):
     if name == "search_logreg_digits3":
         dg = load_digits()
         return dg.data.astype(np.float32), (dg.target == 3).astype(np.int64), 3
+    if name == "search_logreg_g1_200000x256":      # mid-size pin of the headline generator / shape class
+        X, y = make_g1_classification(200000, 256, seed=7)
+        return X, y, 5
     X, y = make_g1_classification(20000, 64, seed=4)
     return X, y, 5
 
@@ -137,6 +140,58 @@ def test_fit_batch_vs_golden(eng, name):
     tol = (1 + 2 * nf.reshape(len(Cs), cv).sum(1).max()) / count[:cv].sum()
     assert mean.argmax() == int(g["best_index"]) or \
         g["mean_test_score"][mean.argmax()] >= g["mean_test_score"].max() - tol
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_fit_batch_vs_golden_midsize(eng, kernel):
+    """G1 200 000 x 256, 32 C x 5 folds (the headline workload's generator, feature count and fold
+    layout at 1/5 of its rows) against the scores of the reference's unmodified `_fit_and_score`
+    (tests/golden/make_golden.py --mid-only), on the fp32 CUDA-core kernels (1) and on the tcgen05
+    kernel (2) separately.  At this size the reference is far from reproducing itself on the
+    weakly regularised columns (fixture: up to 28 predictions per 40 000-row fold and 4 % in the
+    coefficients between 1 BLAS thread / all threads / permuted rows); the device path is held to
+    that envelope, and to exact predictions on the columns the reference does reproduce."""
+    name = "search_logreg_g1_200000x256"
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    X, y, cv = _case(name)
+    fold = _fold_ids(y, cv)
+    eng.stage_x(X); eng.stage_labels(y); eng.stage_folds(fold, cv)
+    Cs = g["C"]
+    C = np.repeat(Cs, cv)
+    cf = np.tile(np.arange(cv, dtype=np.int32), len(Cs))
+    eng.set_kernel(kernel)
+    try:
+        res = eng.logreg_fit_batch(C, cf, np.ones(len(C), np.int32))
+        correct, count = eng.linear_score_batch(res["coef"], cf, np.ones(len(C), np.int32))
+    finally:
+        eng.set_kernel(0)
+    gold_scores = np.stack([g["split%d_test_score" % i] for i in range(cv)], 1).ravel()
+    flips = np.abs(correct - np.rint(gold_scores * count))
+    nf = g["noise_flips"].ravel()
+    nc = g["noise_coef"].ravel()
+    gi = g["n_iter"].ravel()
+    print("kernel %d: flips max %d mean %.2f (reference envelope max %d mean %.2f); excess over envelope max %d"
+          % (kernel, flips.max(), flips.mean(), nf.max(), nf.mean(), np.max(flips - nf)))
+    assert np.all(flips <= 1 + 2 * nf), (flips, nf)
+    stable = (nf == 0) & (nc < 1e-4) & (gi < 100)
+    assert stable.sum() >= 20
+    assert np.all(flips[stable] == 0)
+    assert np.all(np.abs(res["n_iter"][stable] - gi[stable]) <= 1)
+    gc = g["coef"].reshape(len(C), -1)
+    rel = np.abs(res["coef"] - gc).max(1) / np.abs(gc).max(1)
+    assert np.all(rel[stable] <= 2e-4), rel[stable].max()
+    scores = (correct / count).reshape(len(Cs), cv)
+    mean = np.average(scores, axis=1, weights=count[:cv])
+    # mean_test_score: within the reference's own envelope everywhere, and to 1e-5 relative on the
+    # candidates whose five folds are all reproducible
+    env = (1 + 2 * nf.reshape(len(Cs), cv)).sum(1) / count[:cv].sum()
+    assert np.all(np.abs(mean - g["mean_test_score"]) <= env)
+    cand_stable = stable.reshape(len(Cs), cv).all(1)
+    assert cand_stable.sum() >= 4
+    np.testing.assert_allclose(mean[cand_stable], g["mean_test_score"][cand_stable], rtol=1e-5, atol=0)
+    # best_params_: the reference's own winner is separated from the runner-up by 2 predictions in
+    # 200 000, less than its own envelope: any candidate within the envelope of the best is a tie
+    assert g["mean_test_score"][mean.argmax()] >= g["mean_test_score"].max() - env[mean.argmax()]
 
 
 def test_dist_grid_search_end_to_end(eng):
