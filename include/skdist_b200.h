@@ -209,6 +209,9 @@ int skd_forest_fit(skd_ctx* ctx, int32_t n_trees, const uint8_t* sample_counts, 
                    int32_t n_classes, int32_t max_features, int32_t max_depth, int32_t min_samples_split,
                    int32_t min_samples_leaf, double min_weight_leaf, double min_impurity_decrease,
                    int32_t splitter, const double* y_regression, skd_forest** out, double* gpu_seconds_out);
+/* Device time (CUDA events) of the tree-builder kernels of the last skd_forest_fit on ctx, without the
+ * copies of bootstrap counts in and node arrays out: the numerator of the builder's HBM roofline. */
+int skd_forest_kernel_seconds(skd_ctx* ctx, double* seconds_out);
 int skd_forest_tree_size(skd_forest* f, int32_t tree, int32_t* node_count, int32_t* max_depth);
 int skd_forest_tree_copy(skd_forest* f, int32_t tree, int32_t* left, int32_t* right, int32_t* feature,
                          double* threshold, double* impurity, int32_t* n_node_samples,

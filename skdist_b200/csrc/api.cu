@@ -178,6 +178,7 @@ int skd_ctx_destroy(skd_ctx* ctx) {
   free_staged(ctx->c);
   for (void* p : ctx->c.pin_bufs) cudaFreeHost(p);
   ctx->c.pin_bufs.clear();
+  for (int b = 0; b < 2; ++b) if (ctx->c.pin_tree[b]) cudaFreeHost(ctx->c.pin_tree[b]);
   for (auto& b : ctx->c.pool_free) cudaFree(b.first);
   ctx->c.pool_free.clear();
   tc_free(&ctx->c);
@@ -1147,19 +1148,25 @@ int skd_sgd_fit_batch(skd_ctx* ctx, int32_t B, const int32_t* col_pos, int32_t l
 
 struct skd_forest {
   struct Tree {
-    int32_t max_depth = 0, n_classes = 0;
+    int32_t max_depth = 0, n_classes = 0, node_count = 0;
     std::vector<int32_t> left, right, feature, nsamp;
     std::vector<uint8_t> mgl;
     std::vector<double> thr, imp, wn, val;
+    std::vector<uint32_t> compact;     // 8 words per node (throughput builder); expanded by skd_forest_tree_copy
   };
   std::vector<Tree> trees;
+  std::vector<float> binval;           // [d][256] distinct feature values (thresholds of compact records)
 };
 
 static void forest_sink(void* arg, int t, const SkdTreeView* v) {
   skd_forest* f = (skd_forest*)arg;
   skd_forest::Tree& tr = f->trees[t];
   const int m = v->node_count;
-  tr.max_depth = v->max_depth; tr.n_classes = v->n_classes;
+  tr.max_depth = v->max_depth; tr.n_classes = v->n_classes; tr.node_count = m;
+  if (v->compact) {
+    tr.compact.assign(v->compact, v->compact + (size_t)m * 8);
+    return;
+  }
   tr.left.assign(v->left, v->left + m); tr.right.assign(v->right, v->right + m);
   tr.feature.assign(v->feature, v->feature + m); tr.nsamp.assign(v->n_node_samples, v->n_node_samples + m);
   tr.mgl.assign(v->missing_go_to_left, v->missing_go_to_left + m);
@@ -1189,6 +1196,7 @@ int skd_forest_fit(skd_ctx* ctx, int32_t n_trees, const uint8_t* sample_counts, 
   SKD_CUDA(c, cudaEventRecord(e0, c->stream));
   int rc = forest_fit(c, n_trees, sample_counts, rand_states, n_classes, max_features, max_depth, min_samples_split,
                       min_samples_leaf, min_weight_leaf, min_impurity_decrease, splitter, y_regression, forest_sink, f);
+  if (!rc) f->binval = c->forest.h_binval;
   float ms = 0.f;
   if (!rc) {
     cudaEventRecord(e1, c->stream);
@@ -1203,9 +1211,15 @@ int skd_forest_fit(skd_ctx* ctx, int32_t n_trees, const uint8_t* sample_counts, 
   return 0;
 }
 
+int skd_forest_kernel_seconds(skd_ctx* ctx, double* seconds_out) {
+  if (!ctx || !seconds_out) return fail(nullptr, "skd_forest_kernel_seconds: bad arguments");
+  *seconds_out = ctx->c.forest_kernel_ms * 1e-3;
+  return 0;
+}
+
 int skd_forest_tree_size(skd_forest* f, int32_t tree, int32_t* node_count, int32_t* max_depth) {
   if (!f || tree < 0 || tree >= (int)f->trees.size()) return fail(nullptr, "skd_forest_tree_size: bad arguments");
-  if (node_count) *node_count = (int32_t)f->trees[tree].left.size();
+  if (node_count) *node_count = f->trees[tree].node_count;
   if (max_depth) *max_depth = f->trees[tree].max_depth;
   return 0;
 }
@@ -1215,6 +1229,57 @@ int skd_forest_tree_copy(skd_forest* f, int32_t tree, int32_t* left, int32_t* ri
                          double* weighted_n_node_samples, uint8_t* missing_go_to_left, double* value) {
   if (!f || tree < 0 || tree >= (int)f->trees.size()) return fail(nullptr, "skd_forest_tree_copy: bad arguments");
   const skd_forest::Tree& t = f->trees[tree];
+  if (!t.compact.empty()) {
+    // Compact records of the throughput builder: {right child, feature | bin_a << 16 | bin_b << 24,
+    // n_node_samples, depth, class sums[4]}, nodes in depth-first order (left child = id + 1).  The
+    // float64 fields are formed here with the builder's (= scikit-learn's) operations:
+    //   weighted_n = sum_c (double)s_c;  value_c = s_c / weighted_n            (SK/tree/_criterion.pyx:483-486)
+    //   impurity   = 1 - (sum_c s_c^2) / (weighted_n * weighted_n)             (Gini, :650-680; what the parent's
+    //                children_impurity computed from the same integers)
+    //   threshold  = v[a] / 2 + v[b] / 2                                        (SK/tree/_splitter.pyx:459-461)
+    const size_t m = (size_t)t.node_count;
+    const int C = t.n_classes;
+    const uint32_t* r = t.compact.data();
+    const float* bv = f->binval.data();
+    for (size_t i = 0; i < m; ++i, r += 8) {
+      const int32_t rc = (int32_t)r[0];
+      const uint32_t code = r[1];
+      const bool leaf = (code & 0xFFFFu) == 0xFFFFu;
+      if (left) left[i] = leaf ? -1 : (int32_t)i + 1;
+      if (right) right[i] = leaf ? -1 : rc;
+      if (feature) feature[i] = leaf ? -2 : (int32_t)(code & 0xFFFFu);
+      if (threshold) {
+        if (leaf) threshold[i] = -2.0;
+        else {
+          const size_t fo = (size_t)(code & 0xFFFFu) * 256;
+          const volatile double ha = (double)bv[fo + ((code >> 16) & 0xFF)] / 2.0;
+          const volatile double hb = (double)bv[fo + ((code >> 24) & 0xFF)] / 2.0;
+          threshold[i] = ha + hb;
+        }
+      }
+      volatile double w = 0.0, sq = 0.0;
+      for (int c = 0; c < C; ++c) {
+        const double a = (double)r[4 + c];
+        w = w + a;
+        const volatile double aa = a * a;      // volatile: no contraction of the product into the sum
+        sq = sq + aa;
+      }
+      if (n_node_samples) n_node_samples[i] = (int32_t)r[2];
+      if (weighted_n_node_samples) weighted_n_node_samples[i] = w;
+      if (impurity) { const volatile double ww = w * w; const volatile double q = sq / ww; impurity[i] = 1.0 - q; }
+      if (value) for (int c = 0; c < C; ++c) value[i * C + c] = (double)r[4 + c] / w;
+      if (missing_go_to_left) missing_go_to_left[i] = 0;
+    }
+    if (missing_go_to_left) {      // n_left > n_right (SK/tree/_splitter.pyx: best_split.missing_go_to_left with no missing values)
+      r = t.compact.data();
+      for (size_t i = 0; i < m; ++i) {
+        const int32_t rc = (int32_t)r[i * 8];
+        if ((r[i * 8 + 1] & 0xFFFFu) != 0xFFFFu && rc > 0)
+          missing_go_to_left[i] = r[(i + 1) * 8 + 2] > r[(size_t)rc * 8 + 2] ? 1 : 0;
+      }
+    }
+    return 0;
+  }
   const size_t m = t.left.size();
   if (left) memcpy(left, t.left.data(), m * 4);
   if (right) memcpy(right, t.right.data(), m * 4);

@@ -788,6 +788,7 @@ int forest_prepare(Ctx* c) {
     for (int i = 0; i + 1 < nu; ++i)      // the splitter's float32 tie test (SK/tree/_partitioner.pyx:210-214)
       if (!(hv[i + 1] > hv[i] + FEATURE_THRESHOLD)) well_separated = false;
     for (int i = nu; i < FO_BINS; ++i) hv[i] = INFINITY;
+    fd.h_binval.insert(fd.h_binval.end(), hv.begin(), hv.end());
     SKD_CUDA(c, cudaMemcpyAsync(dvals, hv.data(), FO_BINS * 4, cudaMemcpyHostToDevice, c->stream));
     SKD_CUDA(c, cudaMemcpyAsync(fd.binval + (size_t)f * FO_BINS, hv.data(), FO_BINS * 4, cudaMemcpyHostToDevice, c->stream));
     fo_bin_col<<<g, 256, 0, c->stream>>>(col, n, dvals, nu, fd.xbin + (size_t)f * n);
@@ -829,7 +830,7 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   const bool fast = forest_fast_supported(c, n_classes, reg, random_split);
   const int stack_cap = 4096;
   const size_t rec_bytes = fast ? forest_fast_record_bytes(n_classes) : sizeof(FoRecord);
-  const size_t node_bytes = (size_t)(4 * 4 + 1 + 8 * 3 + 8 * n_classes);
+  const size_t node_bytes = fast ? 32 : (size_t)(4 * 4 + 1 + 8 * 3 + 8 * n_classes);   // fast builder: compact records
   const size_t slot_fixed = (size_t)n * 17 + (size_t)stack_cap * rec_bytes + 64;   // two sample buffers + counts + stack
   const int64_t node_cap_max = std::max<int64_t>(2 * n, 16);
   int64_t node_cap = node_cap_max;
@@ -856,6 +857,7 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
   }
   std::vector<int> pending(n_trees);
   for (int t = 0; t < n_trees; ++t) pending[t] = t;
+  c->forest_kernel_ms = 0.0;
   std::vector<int32_t> hl, hr, hf, hn; std::vector<uint8_t> hm; std::vector<double> ht, hi, hw, hv;
   for (int round = 0; !pending.empty(); ++round) {
     // slots: concurrent trees of this round, bounded by the resident builders and by memory
@@ -884,15 +886,20 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
     SKD_CUDA(c, sx.alloc(&P.samp, (size_t)slots * n));
     SKD_CUDA(c, sx.alloc(&P.samp_tmp, (size_t)slots * n));
     SKD_CUDA(c, sx.alloc((uint8_t**)&dstack, (size_t)slots * stack_cap * rec_bytes));
-    SKD_CUDA(c, sx.alloc(&P.o_left, (size_t)slots * node_cap));
-    SKD_CUDA(c, sx.alloc(&P.o_right, (size_t)slots * node_cap));
-    SKD_CUDA(c, sx.alloc(&P.o_feature, (size_t)slots * node_cap));
-    SKD_CUDA(c, sx.alloc(&P.o_nsamp, (size_t)slots * node_cap));
-    SKD_CUDA(c, sx.alloc(&P.o_mgl, (size_t)slots * node_cap));
-    SKD_CUDA(c, sx.alloc(&P.o_thr, (size_t)slots * node_cap));
-    SKD_CUDA(c, sx.alloc(&P.o_imp, (size_t)slots * node_cap));
-    SKD_CUDA(c, sx.alloc(&P.o_wn, (size_t)slots * node_cap));
-    SKD_CUDA(c, sx.alloc(&P.o_val, (size_t)slots * node_cap * n_classes));
+    uint32_t* d_nodes = nullptr;
+    if (fast) {
+      SKD_CUDA(c, sx.alloc(&d_nodes, (size_t)slots * node_cap * 8));
+    } else {
+      SKD_CUDA(c, sx.alloc(&P.o_left, (size_t)slots * node_cap));
+      SKD_CUDA(c, sx.alloc(&P.o_right, (size_t)slots * node_cap));
+      SKD_CUDA(c, sx.alloc(&P.o_feature, (size_t)slots * node_cap));
+      SKD_CUDA(c, sx.alloc(&P.o_nsamp, (size_t)slots * node_cap));
+      SKD_CUDA(c, sx.alloc(&P.o_mgl, (size_t)slots * node_cap));
+      SKD_CUDA(c, sx.alloc(&P.o_thr, (size_t)slots * node_cap));
+      SKD_CUDA(c, sx.alloc(&P.o_imp, (size_t)slots * node_cap));
+      SKD_CUDA(c, sx.alloc(&P.o_wn, (size_t)slots * node_cap));
+      SKD_CUDA(c, sx.alloc(&P.o_val, (size_t)slots * node_cap * n_classes));
+    }
     SKD_CUDA(c, sx.alloc(&P.o_count, (size_t)slots));
     SKD_CUDA(c, sx.alloc(&P.o_maxdepth, (size_t)slots));
     SKD_CUDA(c, sx.alloc(&P.o_status, (size_t)slots));
@@ -915,8 +922,7 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
     F.min_impurity_decrease = min_impurity_decrease;
     F.counts = dcounts; F.rand_state = drs; F.samp = P.samp; F.samp_tmp = P.samp_tmp; F.stack = dstack;
     F.stack_cap = stack_cap; F.node_cap = node_cap;
-    F.o_left = P.o_left; F.o_right = P.o_right; F.o_feature = P.o_feature; F.o_nsamp = P.o_nsamp; F.o_mgl = P.o_mgl;
-    F.o_thr = P.o_thr; F.o_imp = P.o_imp; F.o_wn = P.o_wn; F.o_val = P.o_val;
+    F.o_nodes = d_nodes;
     F.o_count = P.o_count; F.o_maxdepth = P.o_maxdepth; F.o_status = P.o_status; F.o_prof = d_prof;
     std::vector<int32_t> hcount(slots), hdepth(slots), hstatus(slots);
     std::vector<uint32_t> hrs(slots);
@@ -937,6 +943,10 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
       SKD_CUDA(c, cudaMemcpyAsync(drs, hrs.data(), (size_t)nt * 4, cudaMemcpyHostToDevice, c->stream));
       c->h2d += (int64_t)nt * n;
       P.n_trees = nt;
+      cudaEvent_t k0, k1;
+      SKD_CUDA(c, cudaEventCreate(&k0));
+      SKD_CUDA(c, cudaEventCreate(&k1));
+      SKD_CUDA(c, cudaEventRecord(k0, c->stream));
       if (fast) {
         if (forest_fast_launch(c, F, nt)) return 1;
       } else {
@@ -948,10 +958,12 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
         c->launches += 1;
       }
       SKD_CUDA(c, cudaGetLastError());
+      SKD_CUDA(c, cudaEventRecord(k1, c->stream));
       SKD_CUDA(c, cudaMemcpyAsync(hcount.data(), P.o_count, nt * 4, cudaMemcpyDeviceToHost, c->stream));
       SKD_CUDA(c, cudaMemcpyAsync(hdepth.data(), P.o_maxdepth, nt * 4, cudaMemcpyDeviceToHost, c->stream));
       SKD_CUDA(c, cudaMemcpyAsync(hstatus.data(), P.o_status, nt * 4, cudaMemcpyDeviceToHost, c->stream));
       SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+      { float kms = 0.f; cudaEventElapsedTime(&kms, k0, k1); c->forest_kernel_ms += kms; cudaEventDestroy(k0); cudaEventDestroy(k1); }
       if (want_prof) {
         std::vector<long long> hp((size_t)nt * 16);
         cudaMemcpy(hp.data(), d_prof, hp.size() * 8, cudaMemcpyDeviceToHost);
@@ -963,6 +975,44 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
         for (int i = 0; i < np; ++i) if (hp[i]) fprintf(stderr, "[skd forest prof] tree 0 %-18s %12lld cycles %5.1f%%  (%.0f per node)\n", nm[i], hp[i], 100.0 * hp[i] / tot, (double)hp[i] / hcount[0]);
         if (fast) fprintf(stderr, "[skd forest prof] tree 0 nodes: unstaged %lld, staged histogram %lld, staged rank %lld, leaves %lld; total %.3f Gcycles\n",
                           hp[11], hp[12], hp[13], hp[14], tot * 1e-9);
+      }
+      if (fast) {
+        // compact records: trees are copied through two pinned buffers (copy of tree s + 1 overlaps the
+        // consumer's work on tree s)
+        size_t max_m = 1;
+        for (int s = 0; s < nt; ++s) if (hstatus[s] == 0) max_m = std::max(max_m, (size_t)hcount[s]);
+        if (c->pin_tree_bytes < max_m * 32) {
+          for (int b = 0; b < 2; ++b) { if (c->pin_tree[b]) cudaFreeHost(c->pin_tree[b]); c->pin_tree[b] = nullptr; }
+          c->pin_tree_bytes = max_m * 32 + (max_m * 32) / 8;
+          for (int b = 0; b < 2; ++b) SKD_CUDA(c, cudaHostAlloc(&c->pin_tree[b], c->pin_tree_bytes, cudaHostAllocDefault));
+        }
+        cudaEvent_t evc[2];
+        for (int b = 0; b < 2; ++b) SKD_CUDA(c, cudaEventCreateWithFlags(&evc[b], cudaEventDisableTiming));
+        std::vector<int> ok;
+        for (int s = 0; s < nt; ++s) {
+          if (hstatus[s] == 1 && node_cap < node_cap_max) { failed.push_back(pending[p0 + s]); continue; }
+          if (hstatus[s] != 0) return fail(c, hstatus[s] == 1 ? "forest: node capacity exceeded" : "forest: builder stack capacity exceeded");
+          ok.push_back(s);
+        }
+        auto issue = [&](size_t k) {
+          const int s = ok[k];
+          cudaMemcpyAsync(c->pin_tree[k & 1], d_nodes + (size_t)s * node_cap * 8, (size_t)hcount[s] * 32, cudaMemcpyDeviceToHost, c->stream);
+          cudaEventRecord(evc[k & 1], c->stream);
+        };
+        if (!ok.empty()) issue(0);
+        for (size_t k = 0; k < ok.size(); ++k) {
+          SKD_CUDA(c, cudaEventSynchronize(evc[k & 1]));
+          if (k + 1 < ok.size()) issue(k + 1);
+          const int s = ok[k];
+          view.compact = (const uint32_t*)c->pin_tree[k & 1];
+          view.binval = c->forest.h_binval.data();
+          view.node_count = hcount[s]; view.max_depth = hdepth[s]; view.n_classes = n_classes;
+          sink(sink_arg, pending[p0 + s], &view);
+          c->d2h += (int64_t)hcount[s] * 32;
+        }
+        for (int b = 0; b < 2; ++b) cudaEventDestroy(evc[b]);
+        SKD_CUDA(c, cudaGetLastError());
+        continue;
       }
       for (int s = 0; s < nt; ++s) {
         if (hstatus[s] == 1 && node_cap < node_cap_max) { failed.push_back(pending[p0 + s]); continue; }

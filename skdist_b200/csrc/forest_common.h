@@ -28,8 +28,7 @@ struct FfParams {
   void* stack;                // [trees][stack_cap] builder-stack spill (records of forest_fast_record_bytes())
   int stack_cap;
   int64_t node_cap;
-  int32_t* o_left; int32_t* o_right; int32_t* o_feature; int32_t* o_nsamp; uint8_t* o_mgl;
-  double* o_thr; double* o_imp; double* o_wn; double* o_val;   // o_val [node_cap][n_classes]
+  uint32_t* o_nodes;          // [trees][node_cap][8] compact node records (see forest_fast.cu: _add_node)
   int32_t* o_count; int32_t* o_maxdepth; int32_t* o_status;    // [trees]; status 0 ok, 1 node capacity, 2 stack capacity
   long long* o_prof;          // [trees][16] cycles per builder phase / node counts (SKDIST_B200_FOREST_PROF=1), else nullptr
 };

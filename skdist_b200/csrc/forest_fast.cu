@@ -141,12 +141,49 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
   const int mylast = pmask ? lane * 8 + 31 - __clz(pmask) : -1;
   const int glast = __reduce_max_sync(0xffffffffu, mylast);
   const bool is_const = glast <= gfirst;      // distinct values are > 1e-7 apart (host check): one bin == constant
+  // Ranking the candidates takes two float64 divisions each in scikit-learn's expression.  They are
+  // ranked first by p = sq_l / w_l + sq_r / w_r in float32 (proxy = p - w_node in exact arithmetic;
+  // the float32 value is within 2^-20 * w_node of it), and the float64 expression is evaluated only
+  // for the candidates within 2^-19 * w_node of the best float32 value -- the others cannot win.
+  float pbest = -INFINITY;
+  if (!is_const) {
+    unsigned run_cnt = pre;
+    unsigned pm = pmask;
+    uint32_t s2[CM];
+#pragma unroll
+    for (int c = 0; c < CM; ++c) s2[c] = sl[c];
+    while (pm) {
+      const int j = __ffs(pm) - 1;
+      pm &= pm - 1;
+      const int bb = lane * 8 + j;
+      run_cnt += hn(bb);
+#pragma unroll
+      for (int c = 0; c < CM; ++c) if (c < C) s2[c] += hc(c, bb);
+      if (!pm && nxt >= (1 << 20)) continue;
+      const int n_left = (int)run_cnt, n_right = n_node - n_left;
+      if (n_left < min_samples_leaf || n_right < min_samples_leaf) continue;
+      float wl = 0.f, sql = 0.f, sqr = 0.f;
+#pragma unroll
+      for (int c = 0; c < CM; ++c) if (c < C) { const float a = (float)s2[c], b = (float)(st[c] - s2[c]); wl += a; sql = fmaf(a, a, sql); sqr = fmaf(b, b, sqr); }
+      const float wr = (float)w_node - wl;
+      if (min_weight_leaf > 0.0) {       // the validity tests are the exact ones: an invalid candidate must not set the bar
+        double wld = 0.0;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) if (c < C) wld += (double)s2[c];
+        if (wld < min_weight_leaf || w_node - wld < min_weight_leaf) continue;
+      }
+      pbest = fmaxf(pbest, __fdividef(sql, wl) + __fdividef(sqr, wr));
+    }
+  }
+  float pthr = pbest;
+  for (int o = 16; o > 0; o >>= 1) pthr = fmaxf(pthr, __shfl_xor_sync(0xffffffffu, pthr, o));
+  pthr -= (float)w_node * 1.9073486328125e-6f;      // 2^-19 * w_node
   double bproxy = -INFINITY;
   int bnl = 1 << 30, bcode = 0;
   uint32_t bsl[CM];
 #pragma unroll
   for (int c = 0; c < CM; ++c) bsl[c] = 0;
-  if (!is_const) {
+  if (!is_const && pbest >= pthr) {
     unsigned run_cnt = pre;
     unsigned pm = pmask;
     while (pm) {                               // this lane's present bins in ascending order
@@ -160,6 +197,13 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
       if (nb2 >= (1 << 20)) continue;                             // last present bin: no boundary above it
       const int n_left = (int)run_cnt, n_right = n_node - n_left;
       if (n_left < min_samples_leaf || n_right < min_samples_leaf) continue;
+      {
+        float wlf = 0.f, sqlf = 0.f, sqrf = 0.f;
+#pragma unroll
+        for (int c = 0; c < CM; ++c) if (c < C) { const float a = (float)sl[c], b = (float)(st[c] - sl[c]); wlf += a; sqlf = fmaf(a, a, sqlf); sqrf = fmaf(b, b, sqrf); }
+        const float wrf = (float)w_node - wlf;
+        if (!(__fdividef(sqlf, wlf) + __fdividef(sqrf, wrf) >= pthr)) continue;     // cannot be the best
+      }
       double wl = 0.0;
 #pragma unroll
       for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
@@ -192,8 +236,7 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
 #define FF_TICK(ph) do { if (P.o_prof && tid == 0) { const long long _t = clock64(); s_prof[ph] += _t - tlast; tlast = _t; } } while (0)
 
 template <int CM>
-// (minimum 6 blocks per SM lets ptxas use up to 112 registers; at <= 96 seven builders are resident)
-__global__ void __launch_bounds__(FF_THREADS, 6)
+__global__ void __launch_bounds__(FF_THREADS, 7)
 forest_fast_kernel(const FfParams P) {
   typedef typename FfAcc<CM>::T acc_t;
   constexpr int CNT = FfAcc<CM>::CNT;
@@ -213,8 +256,8 @@ forest_fast_kernel(const FfParams P) {
   double* s_dbl = reinterpret_cast<double*>(results + FF_KB);                // [4]
   long long* s_prof = reinterpret_cast<long long*>(s_dbl + 4);               // [16]
   int* s_ctrl = reinterpret_cast<int*>(s_prof + 16);                         // [16]
-  int* wsum = s_ctrl + 16;                                                   // [32]
-  uint32_t* best_sl = reinterpret_cast<uint32_t*>(wsum + 32);                // [4]
+  int* wsum = s_ctrl + 16;                                                   // [64]
+  uint32_t* best_sl = reinterpret_cast<uint32_t*>(wsum + 64);                // [4]
   uint8_t* features = reinterpret_cast<uint8_t*>(best_sl + 4);               // [d]
   uint8_t* constant_features = features + ((d + 3) & ~3);                    // [d]
   uint8_t* undo = constant_features + ((d + 3) & ~3);                        // [2 * (d + 16)] swap log of the draws
@@ -346,8 +389,8 @@ forest_fast_kernel(const FfParams P) {
         const int cpr = dp >> 4;                       // 16-byte chunks per row
         for (int q = tid; q < n_node * cpr; q += FF_THREADS) {
           const int j = q / cpr, cc = q - j * cpr;
-          const uint2 sv = src[j];
-          const uint4 v = __ldg(reinterpret_cast<const uint4*>(P.xrow + (size_t)sv.x * dp) + cc);
+          const uint2 sv = __ldcg(src + j);
+          const uint4 v = __ldcg(reinterpret_cast<const uint4*>(P.xrow + (size_t)sv.x * dp) + cc);   // L2 only: L1 is left to the spill slots
           unsigned int* dstw = U + j * P.stage_ws + cc * 4;
           if (cc * 4 + 0 < P.stage_ws) dstw[0] = v.x;
           if (cc * 4 + 1 < P.stage_ws) dstw[1] = v.y;
@@ -412,30 +455,30 @@ forest_fast_kernel(const FfParams P) {
           // ---- histograms of all batch features in one pass over the node's samples (global gathers:
           // the drawn features of a sample share one 64-byte row of codes) ----
           const uint2* src = (cur ? P.samp_tmp : P.samp) + (size_t)slot * n;
-          for (int i = start + tid; i < end; i += 2 * FF_THREADS) {
-            const int i2 = i + FF_THREADS;
-            const bool has2 = i2 < end;
-            const uint2 sa = src[i];
-            const uint2 sb = has2 ? src[i2] : sa;
-            const uint8_t* ra = P.xrow + (size_t)sa.x * dp;
-            const uint8_t* rb = P.xrow + (size_t)sb.x * dp;
-            unsigned ba[FF_KB], bb[FF_KB];
+          int fk[FF_KB];
 #pragma unroll
-            for (int k = 0; k < FF_KB; ++k) {
-              const int fk = items[k < nbatch ? k : 0].f;
-              ba[k] = (unsigned)__ldg(ra + fk);
-              bb[k] = (unsigned)__ldg(rb + fk);
+          for (int k = 0; k < FF_KB; ++k) fk[k] = items[k < nbatch ? k : 0].f;
+          for (int i0 = start; i0 < end; i0 += 4 * FF_THREADS) {
+            uint2 sv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int i = i0 + q * FF_THREADS + tid;
+              sv[q] = i < end ? __ldcg(src + i) : make_uint2(0xFFFFFFFFu, 0u);
             }
-            const unsigned ca = sa.y & 0xFF, wa = sa.y >> 8, cb = sb.y & 0xFF, wb = sb.y >> 8;
 #pragma unroll
-            for (int k = 0; k < FF_KB; ++k) {
-              if (k < nbatch) {
-                unsigned int* H = U + k * hstrideA;
-                atomicAdd(&H[ca * 256 + ba[k]], wa);
-                atomicAdd(&H[C * 256 + ba[k]], 1u);
-                if (has2) {
-                  atomicAdd(&H[cb * 256 + bb[k]], wb);
-                  atomicAdd(&H[C * 256 + bb[k]], 1u);
+            for (int q = 0; q < 4; ++q) {
+              if (sv[q].x == 0xFFFFFFFFu) continue;
+              const uint8_t* rq = P.xrow + (size_t)sv[q].x * dp;
+              unsigned bq[FF_KB];
+#pragma unroll
+              for (int k = 0; k < FF_KB; ++k) bq[k] = (unsigned)__ldcg(rq + fk[k]);
+              const unsigned cq = sv[q].y & 0xFF, wq = sv[q].y >> 8;
+#pragma unroll
+              for (int k = 0; k < FF_KB; ++k) {
+                if (k < nbatch) {
+                  unsigned int* H = U + k * hstrideA;
+                  atomicAdd(&H[cq * 256 + bq[k]], wq);
+                  atomicAdd(&H[C * 256 + bq[k]], 1u);
                 }
               }
             }
@@ -638,34 +681,42 @@ forest_fast_kernel(const FfParams P) {
           const uint2* src = (cur ? P.samp_tmp : P.samp) + (size_t)slot * n;
           uint2* dst = (cur ? P.samp : P.samp_tmp) + (size_t)slot * n;
           int loff = start, roff = start + best_nl;
-          for (int i0 = start; i0 < end; i0 += 4 * FF_THREADS) {
-            uint2 sv4[4];
-            int pos4[4];
+          constexpr int PQ = 8;                        // samples per thread and round
+          for (int i0 = start; i0 < end; i0 += PQ * FF_THREADS) {
+            uint2 svq[PQ];
+            int posq[PQ];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < PQ; ++q) {
               const int i = i0 + q * FF_THREADS + tid;
-              const bool have = i < end;
-              sv4[q] = have ? src[i] : make_uint2(0, 0);
-              const bool isl = have && __ldg(P.xrow + (size_t)sv4[q].x * dp + best_feature) <= best_bin;
+              svq[q] = i < end ? __ldcg(src + i) : make_uint2(0xFFFFFFFFu, 0u);
+            }
+            unsigned codeq[PQ];
+#pragma unroll
+            for (int q = 0; q < PQ; ++q)
+              codeq[q] = svq[q].x != 0xFFFFFFFFu ? (unsigned)__ldcg(P.xrow + (size_t)svq[q].x * dp + best_feature) : 0u;
+#pragma unroll
+            for (int q = 0; q < PQ; ++q) {
+              const bool have = svq[q].x != 0xFFFFFFFFu;
+              const bool isl = have && codeq[q] <= best_bin;
               const unsigned bl = __ballot_sync(0xffffffffu, isl);
               const unsigned br = __ballot_sync(0xffffffffu, have && !isl);
               const unsigned lt = (1u << lane) - 1;
-              pos4[q] = have ? (isl ? __popc(bl & lt) : (__popc(br & lt) | (1 << 30))) : -1;
+              posq[q] = have ? (isl ? __popc(bl & lt) : (__popc(br & lt) | (1 << 30))) : -1;
               if (lane == 0) { wsum[(q * FF_WARPS + wid) * 2] = __popc(bl); wsum[(q * FF_WARPS + wid) * 2 + 1] = __popc(br); }
             }
             __syncthreads();
             int lo = 0, ro = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < PQ; ++q) {
 #pragma unroll
               for (int k = 0; k < FF_WARPS; ++k) {
-                if (k == wid && pos4[q] >= 0) pos4[q] += (pos4[q] & (1 << 30)) ? ro : lo;
+                if (k == wid && posq[q] >= 0) posq[q] += (posq[q] & (1 << 30)) ? ro : lo;
                 lo += wsum[(q * FF_WARPS + k) * 2]; ro += wsum[(q * FF_WARPS + k) * 2 + 1];
               }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (pos4[q] >= 0) dst[(pos4[q] & (1 << 30)) ? roff + (pos4[q] & ~(1 << 30)) : loff + pos4[q]] = sv4[q];
+            for (int q = 0; q < PQ; ++q)
+              if (posq[q] >= 0) dst[(posq[q] & (1 << 30)) ? roff + (posq[q] & ~(1 << 30)) : loff + posq[q]] = svq[q];
             loff += lo; roff += ro;
             __syncthreads();
           }
@@ -680,26 +731,18 @@ forest_fast_kernel(const FfParams P) {
     const int node_id = node_count;
     if (node_id >= P.node_cap) { status = 1; break; }
     if (tid == 0) {
-      const int64_t nb = (int64_t)slot * P.node_cap;
-      const int flags = rec->flags;
-      if (rec->parent >= 0) {
-        if (flags & (1 << 16)) P.o_left[nb + rec->parent] = node_id; else P.o_right[nb + rec->parent] = node_id;
-      }
-      P.o_imp[nb + node_id] = impurity;
-      P.o_nsamp[nb + node_id] = n_node;
-      P.o_wn[nb + node_id] = w_node;
-      if (is_leaf) {
-        P.o_left[nb + node_id] = -1; P.o_right[nb + node_id] = -1;
-        P.o_feature[nb + node_id] = -2; P.o_thr[nb + node_id] = -2.0; P.o_mgl[nb + node_id] = 0;
-      } else {
-        P.o_feature[nb + node_id] = best_feature;
-        // the two bins around the threshold; ff_threshold_kernel turns them into v[a]/2 + v[b]/2
-        P.o_thr[nb + node_id] = __longlong_as_double((long long)(best_code & 0xFFFF));
-        P.o_mgl[nb + node_id] = (uint8_t)(best_nl > (n_node - best_nl));
-      }
-#pragma unroll
-      for (int c = 0; c < CM; ++c)
-        if (c < C) P.o_val[(nb + node_id) * C + c] = __ddiv_rn((double)rec->sums[c], w_node);   // class fractions
+      // compact node record (32 bytes = one sector): right child | feature + the two bins around the
+      // threshold | n_node_samples | depth | class sums.  Left child = id + 1 (depth-first order); the
+      // host derives threshold, impurity, weighted_n_node_samples, value and missing_go_to_left.
+      uint32_t* nodes = P.o_nodes + (size_t)slot * P.node_cap * 8;
+      if (rec->parent >= 0 && !(rec->flags & (1 << 16))) nodes[(size_t)rec->parent * 8] = (uint32_t)node_id;
+      const uint32_t code = is_leaf ? 0xFFFFu : ((uint32_t)best_feature | ((uint32_t)(best_code & 0xFFFF) << 16));
+      uint4 q0 = make_uint4(0xFFFFFFFFu, code, (uint32_t)n_node, (uint32_t)depth);
+      uint4 q1 = make_uint4(rec->sums[0], CM > 1 ? rec->sums[1] : 0u, 0u, 0u);
+      if (CM > 2) { q1.z = rec->sums[2]; q1.w = rec->sums[3]; }
+      uint4* dstn = reinterpret_cast<uint4*>(nodes + (size_t)node_id * 8);
+      dstn[0] = q0;
+      dstn[1] = q1;
     }
     node_count += 1;
     if (!is_leaf) {
@@ -736,27 +779,11 @@ forest_fast_kernel(const FfParams P) {
 }
 #undef FF_TICK
 
-// threshold of every internal node from the two bins the builder left in o_thr:
-// v[p-1]/2 + v[p] /2 in float64 (SK/tree/_splitter.pyx:459-461)
-__global__ void ff_threshold_kernel(const float* __restrict__ binval, const int32_t* __restrict__ o_feature,
-                                    double* __restrict__ o_thr, const int32_t* __restrict__ o_count, int64_t node_cap) {
-  const int slot = blockIdx.y;
-  const int m = o_count[slot];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-    const int64_t o = (int64_t)slot * node_cap + i;
-    const int f = o_feature[o];
-    if (f < 0) continue;
-    const long long code = __double_as_longlong(o_thr[o]);
-    const int a = (int)(code & 0xFF), b = (int)((code >> 8) & 0xFF);
-    o_thr[o] = (double)binval[(size_t)f * 256 + a] / 2.0 + (double)binval[(size_t)f * 256 + b] / 2.0;
-  }
-}
-
 // ---- host side -----------------------------------------------------------------------------
 static size_t ff_smem_bytes(int CM, int d) {
   const size_t rec = CM <= 2 ? sizeof(FfRec<2>) : sizeof(FfRec<4>);
   const size_t res = CM <= 2 ? sizeof(FfResult<2>) : sizeof(FfResult<4>);
-  return (size_t)FF_UW * 4 + (FF_SSTK + 1) * rec + FF_KB * sizeof(FfItem) + FF_KB * res + 4 * 8 + 16 * 8 + 16 * 4 + 32 * 4 + 4 * 4 +
+  return (size_t)FF_UW * 4 + (FF_SSTK + 1) * rec + FF_KB * sizeof(FfItem) + FF_KB * res + 4 * 8 + 16 * 8 + 16 * 4 + 64 * 4 + 4 * 4 +
          2 * (size_t)((d + 3) & ~3) + 2 * (size_t)(d + 16) + 16;
 }
 
@@ -790,16 +817,15 @@ int forest_fast_launch(Ctx* c, FfParams& P, int nt) {
   P.n_trees = nt;
   if (CM == 2) {
     SKD_CUDA(c, cudaFuncSetAttribute(forest_fast_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SKD_CUDA(c, cudaFuncSetAttribute(forest_fast_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     forest_fast_kernel<2><<<nt, FF_THREADS, smem, c->stream>>>(P);
   } else {
     SKD_CUDA(c, cudaFuncSetAttribute(forest_fast_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SKD_CUDA(c, cudaFuncSetAttribute(forest_fast_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     forest_fast_kernel<4><<<nt, FF_THREADS, smem, c->stream>>>(P);
   }
   SKD_CUDA(c, cudaGetLastError());
-  dim3 g(64, nt);
-  ff_threshold_kernel<<<g, 256, 0, c->stream>>>(c->forest.binval, P.o_feature, P.o_thr, P.o_count, P.node_cap);
-  SKD_CUDA(c, cudaGetLastError());
-  c->launches += 2;
+  c->launches += 1;
   return 0;
 }
 

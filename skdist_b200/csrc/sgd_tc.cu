@@ -182,12 +182,15 @@ __global__ void sgd_rownorm_kernel(const float* __restrict__ X, int64_t n, int l
 
 // Xp[i][k] = fp16(X[order[i]][k] * sx) for i < n, zero padding rows / columns
 __global__ void sgd_permute_kernel(const float* __restrict__ X, int ldx, int d, const int32_t* __restrict__ order,
-                                   int64_t n, int64_t npad, int dpad, float sx, __half* __restrict__ Xp) {
+                                   int64_t n, int64_t npad, int dpad, float sx, __half* __restrict__ Xp,
+                                   const int32_t* __restrict__ ycls, const float* __restrict__ xnorm,
+                                   int32_t* __restrict__ ycls_p, float* __restrict__ xnorm_p) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;    // one thread per 8 features
   const int per = dpad >> 3;
   if (idx >= npad * per) return;
   const int64_t i = idx / per;
   const int k0 = (int)(idx - i * per) * 8;
+  if (k0 == 0 && i < n) { const int r = order[i]; ycls_p[i] = ycls[r]; xnorm_p[i] = xnorm[r]; }   // sample metadata in walk order
   __align__(16) __half h[8];
   if (i < n) {
     const float* src = X + (size_t)order[i] * ldx + k0;
@@ -247,7 +250,8 @@ struct SgdScanParams {
   const float* X; int ldx, d, dpad;
   const int32_t* ycls; const int32_t* order; const double* eta; const float* cfac;
   const double* ws;          // [n + 1] lazy scale before sample i (identical for every running column)
-  const float* xnorm;        // [n] by original row
+  const int32_t* ycls_p;     // [n] class id of sample i of the epoch (walk order)
+  const float* xnorm_p;      // [n] |x| of sample i of the epoch (walk order)
   int64_t n; int row0, t_len;
   const int32_t* active; int n_active; const int32_t* col_pos;
   float* W; int ldw;
@@ -290,24 +294,32 @@ sgd_scan_kernel(const SgdScanParams P) {
   const float* Srow = P.S + (size_t)a * ST_T;
   unsigned long long n_screen = 0, n_exact = 0, n_viol = 0;
 
+  // per-sample inputs of the window [i0, i0 + 32): coalesced loads in walk order, requested one
+  // window ahead (the window normally advances by 32; after an event it is re-read)
+  struct Win { double e, ws; float c, nx, s; int yc; };
+  auto load_win = [&](int i0w) -> Win {
+    Win wv; wv.e = 0.0; wv.ws = 1.0; wv.c = 1.f; wv.nx = 0.f; wv.s = 0.f; wv.yc = -1;
+    if (i0w + lane < P.t_len) {
+      const int64_t gi = (int64_t)P.row0 + i0w + lane;
+      wv.e = P.eta[gi]; wv.ws = P.ws[gi]; wv.c = P.cfac[gi]; wv.nx = P.xnorm_p[gi]; wv.yc = P.ycls_p[gi];
+      wv.s = Srow[i0w + lane];
+    }
+    return wv;
+  };
   int i0 = 0;
+  Win nxt = load_win(0);
+  int nxt_i0 = 0;
   while (i0 < P.t_len) {
     const int Te = (P.t_len - i0) < T ? (P.t_len - i0) : T;
     // lane t < Te owns sample i0 + t of the block
-    const int64_t gi = (int64_t)P.row0 + i0 + lane;
-    int row_l = 0;
-    double y_l = 0.0, e_l = 0.0, ws_l = 1.0;
-    float c_l = 1.f, nx_l = 0.f, s_l = 0.f;
-    if (lane < Te) {
-      row_l = P.order[gi];
-      e_l = P.eta[gi];
-      c_l = P.cfac[gi];
-      ws_l = P.ws[gi];
-      y_l = (P.ycls[row_l] == pos) ? 1.0 : -1.0;
-      nx_l = P.xnorm[row_l];
-      s_l = Srow[i0 + lane] * inv_scale;
+    const Win cw = (nxt_i0 == i0) ? nxt : load_win(i0);
+    nxt_i0 = i0 + T;
+    nxt = load_win(nxt_i0);                       // in flight while this window is processed
+    const double y_l = (cw.yc == pos) ? 1.0 : -1.0, e_l = cw.e, ws_l = cw.ws;
+    const float c_l = cw.c, nx_l = cw.nx;
+    float s_l = cw.s * inv_scale;
+    if (lane < Te)
       for (int v = 0; v < nviol; ++v) s_l = fmaf(vq[v], P.G[(size_t)vj[v] * ST_T + i0 + lane], s_l);
-    }
     // A. the norm recurrence sq_norm *= c_t^2 in sample order (lane t keeps the value BEFORE sample t)
     double my_sq = sq_norm, my_sq_after = sq_norm;
     {
@@ -347,7 +359,7 @@ sgd_scan_kernel(const SgdScanParams P) {
     }
     // E. sample ev exactly as _plain_sgd32 does
     {
-      const int r = __shfl_sync(FULL, row_l, ev);
+      const int r = P.order[(int64_t)P.row0 + i0 + ev];
       const double y = __shfl_sync(FULL, y_l, ev);
       const double e = __shfl_sync(FULL, e_l, ev);
       const double wsb = __shfl_sync(FULL, ws_l, ev);
@@ -513,7 +525,7 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
   const int64_t npad = (n + ST_T - 1) / ST_T * ST_T;
   const int kpad = (B + ST_TILE - 1) / ST_TILE * ST_TILE;
   Scratch sx(c);
-  float* W; SgdStateTc* state; int32_t *order, *active, *dpos; double *eta, *dws; float *cfac, *xnorm;
+  float* W; SgdStateTc* state; int32_t *order, *active, *dpos, *ycls_p; double *eta, *dws; float *cfac, *xnorm, *xnorm_p;
   float* dcoef; double *dint, *dt; int32_t *dniter, *dstatus;
   __half *Xp, *Wp; float2* wmeta[2]; float *S, *G; unsigned int* absmax; int2* gtiles; unsigned long long* counters;
   SKD_CUDA(c, sx.alloc(&W, (size_t)B * ldw));
@@ -525,6 +537,8 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
   SKD_CUDA(c, sx.alloc(&dws, (size_t)n + 1));
   SKD_CUDA(c, sx.alloc(&cfac, (size_t)n));
   SKD_CUDA(c, sx.alloc(&xnorm, (size_t)n));
+  SKD_CUDA(c, sx.alloc(&xnorm_p, (size_t)n));
+  SKD_CUDA(c, sx.alloc(&ycls_p, (size_t)n));
   SKD_CUDA(c, sx.alloc(&dcoef, (size_t)B * d));
   SKD_CUDA(c, sx.alloc(&dint, (size_t)B));
   SKD_CUDA(c, sx.alloc(&dt, (size_t)B));
@@ -596,7 +610,8 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
     SKD_CUDA(c, cudaMemcpyAsync(hcfac.data(), cfac, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     if (shuffle || epoch == 0) {
       const int64_t total = npad * (dpad / 8);
-      sgd_permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->X, ldx, d, order, n, npad, dpad, sxs, Xp);
+      sgd_permute_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(c->X, ldx, d, order, n, npad, dpad, sxs, Xp, c->ycls, xnorm,
+                                                                               ycls_p, xnorm_p);
       c->launches += 1;
     }
     SKD_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -625,7 +640,7 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
       sgd_gemm_kernel<<<gp.n_s + gp.n_g, 192, gemm_smem, c->stream>>>(map_x, map_w, gp);
       SgdScanParams sp;
       sp.X = c->X; sp.ldx = ldx; sp.d = d; sp.dpad = dpad; sp.ycls = c->ycls; sp.order = order; sp.eta = eta; sp.cfac = cfac;
-      sp.ws = dws; sp.xnorm = xnorm; sp.n = n; sp.row0 = b * ST_T;
+      sp.ws = dws; sp.ycls_p = ycls_p; sp.xnorm_p = xnorm_p; sp.n = n; sp.row0 = b * ST_T;
       sp.t_len = (int)std::min<int64_t>(ST_T, n - (int64_t)b * ST_T);
       sp.active = active; sp.n_active = n_active; sp.col_pos = dpos; sp.W = W; sp.ldw = ldw; sp.state = state;
       sp.S = S; sp.G = G; sp.wmeta = wmeta[b & 1]; sp.Wp = Wp; sp.wmeta_out = wmeta[(b + 1) & 1];

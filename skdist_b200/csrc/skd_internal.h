@@ -45,11 +45,16 @@ struct ForestData {
   uint8_t* xrow = nullptr;   // [n][dp] the same codes row-major, dp = d rounded up to 16 (forest_fast.cu)
   int dp = 0;
   bool well_separated = false;   // every feature's adjacent distinct values are more than 1e-7 apart
+  std::vector<float> h_binval;   // host copy of binval (thresholds of compact node records are formed on the host)
   bool valid = false;
 };
 
-// host view of one finished tree (arrays of node_count entries; value is [node_count][n_classes])
+// host view of one finished tree (arrays of node_count entries; value is [node_count][n_classes]).
+// compact != nullptr: the tree comes as compact 32-byte node records (forest_fast.cu) and the arrays
+// are null; `binval` ([d][256] distinct feature values) lets the consumer form the thresholds.
 struct SkdTreeView {
+  const uint32_t* compact = nullptr;
+  const float* binval = nullptr;
   int32_t node_count, max_depth, n_classes;
   const int32_t *left, *right, *feature, *n_node_samples;
   const uint8_t* missing_go_to_left;
@@ -88,6 +93,9 @@ struct Ctx {
   // pinned bounce buffers for staging pageable host arrays (api.cu: stage_rows_h2d)
   std::vector<void*> pin_bufs;
   size_t pin_bytes = 0;
+  double forest_kernel_ms = 0.0;            // device time of the tree-builder kernels of the last forest_fit (events)
+  void* pin_tree[2] = {nullptr, nullptr};   // pinned double buffer for finished trees (forest.cu)
+  size_t pin_tree_bytes = 0;
   // counters
   int64_t launches = 0, h2d = 0, d2h = 0;
   // optional per-evaluation timing (bench.py roofline): CUDA events on `stream` around every

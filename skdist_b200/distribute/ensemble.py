@@ -232,6 +232,7 @@ class _DistForestClassifier(_ScParamMixin):
 
         local = []
         self.device_seconds_ = 0.0
+        self.kernel_seconds_ = 0.0
         if chunks:
             with ThreadPoolExecutor(max_workers=1) as dev, ThreadPoolExecutor(max_workers=1) as side:
                 nxt = side.submit(prepare, chunks[0])
@@ -245,6 +246,7 @@ class _DistForestClassifier(_ScParamMixin):
                         local.extend(wrap(*pending))
                     arrays = fut.result()
                     self.device_seconds_ += getattr(eng, "last_forest_seconds", 0.0)
+                    self.kernel_seconds_ = getattr(self, "kernel_seconds_", 0.0) + getattr(eng, "last_forest_kernel_seconds", 0.0)
                     pending = (sts, arrays)
                 local.extend(wrap(*pending))
         if world > 1:

@@ -337,22 +337,35 @@ class Engine:
                                        ptr(yreg) if yreg is not None else None,
                                        ctypes.byref(h), ctypes.byref(secs)), self._h)
         self.last_forest_seconds = secs.value
-        trees = []
+        ks = ctypes.c_double(0.0)
+        check(self._lib.skd_forest_kernel_seconds(self._h, ctypes.byref(ks)), self._h)
+        self.last_forest_kernel_seconds = ks.value
+        def fetch(t):
+            m, md = ctypes.c_int32(), ctypes.c_int32()
+            check(self._lib.skd_forest_tree_size(h, t, ctypes.byref(m), ctypes.byref(md)))
+            m = m.value
+            a = {"left": np.empty(m, np.int32), "right": np.empty(m, np.int32), "feature": np.empty(m, np.int32),
+                 "threshold": np.empty(m, np.float64), "impurity": np.empty(m, np.float64),
+                 "n_node_samples": np.empty(m, np.int32), "weighted_n_node_samples": np.empty(m, np.float64),
+                 "missing_go_to_left": np.empty(m, np.uint8), "value": np.empty((m, n_classes), np.float64)}
+            check(self._lib.skd_forest_tree_copy(h, t, ptr(a["left"]), ptr(a["right"]), ptr(a["feature"]),
+                                                 ptr(a["threshold"]), ptr(a["impurity"]), ptr(a["n_node_samples"]),
+                                                 ptr(a["weighted_n_node_samples"]), ptr(a["missing_go_to_left"]),
+                                                 ptr(a["value"])))
+            a["max_depth"] = md.value
+            return a
+
         try:
-            for t in range(T):
-                m, md = ctypes.c_int32(), ctypes.c_int32()
-                check(self._lib.skd_forest_tree_size(h, t, ctypes.byref(m), ctypes.byref(md)))
-                m = m.value
-                a = {"left": np.empty(m, np.int32), "right": np.empty(m, np.int32), "feature": np.empty(m, np.int32),
-                     "threshold": np.empty(m, np.float64), "impurity": np.empty(m, np.float64),
-                     "n_node_samples": np.empty(m, np.int32), "weighted_n_node_samples": np.empty(m, np.float64),
-                     "missing_go_to_left": np.empty(m, np.uint8), "value": np.empty((m, n_classes), np.float64)}
-                check(self._lib.skd_forest_tree_copy(h, t, ptr(a["left"]), ptr(a["right"]), ptr(a["feature"]),
-                                                     ptr(a["threshold"]), ptr(a["impurity"]), ptr(a["n_node_samples"]),
-                                                     ptr(a["weighted_n_node_samples"]), ptr(a["missing_go_to_left"]),
-                                                     ptr(a["value"])))
-                a["max_depth"] = md.value
-                trees.append(a)
+            # the copies (and, for the compact records of the throughput builder, the float64 fields formed
+            # from the integer class sums) run in the library without the GIL: one host thread per tree
+            import os
+            from concurrent.futures import ThreadPoolExecutor
+            nthr = max(1, min(32, T, (os.cpu_count() or 8) // 2))
+            if nthr > 1:
+                with ThreadPoolExecutor(max_workers=nthr) as ex:
+                    trees = list(ex.map(fetch, range(T)))
+            else:
+                trees = [fetch(t) for t in range(T)]
         finally:
             self._lib.skd_forest_free(h)
         return trees

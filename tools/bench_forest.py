@@ -29,7 +29,9 @@ alg_bytes = 8.0 * (mf + 1) * float(np.sum(internal))
 line = {"workload": "DistRandomForestClassifier(n_estimators=%d, random_state=0) on lattice %dx%d fp32" % (a.trees, a.n, a.d),
         "trees_per_s_e2e": a.trees / dt, "seconds": dt, "device_seconds": rf.device_seconds_,
         "nodes_mean": float(nodes.mean()), "depth_max": int(max(e.tree_.max_depth for e in rf.estimators_)),
+        "builder_kernel_seconds": rf.kernel_seconds_,
         "algorithmic_bytes": alg_bytes, "algorithmic_GBps_device": alg_bytes / rf.device_seconds_ / 1e9,
+        "algorithmic_GBps_builder_kernel": alg_bytes / max(rf.kernel_seconds_, 1e-9) / 1e9,
         "kernel": os.environ.get("SKDIST_B200_FOREST_KERNEL", "auto")}
 if a.cpu_sample:
     t0 = time.time()
