@@ -77,6 +77,16 @@ int skd_stage_folds(skd_ctx* ctx, const int8_t* fold_id, int64_t n, int32_t n_fo
  * (_fit_and_score_one) -- one feature set x fold per column. */
 int skd_stage_column_masks(skd_ctx* ctx, int32_t B, const uint8_t* mask);
 
+/* Row bit matrices for the NEXT skd_logreg_fit_batch call (one-shot; NULL / B = 0 clears): bit r of
+ * column j in `label_bits` = the binary label of row r in that column (instead of class id == col_pos[j]:
+ * multilabel targets), in `train_bits` = row r takes part in the column's fit (instead of every row: the
+ * reference's negative down-sampling).  Packed little-endian, `bytes_per_col` bytes per column (>= n / 8);
+ * either matrix may be NULL.  Not combinable with folds or pair columns.
+ * ref: the label columns of multiclass.py:288-297 (LabelBinarizer output of a multilabel y) and
+ * `_negatives_mask` (multiclass.py:76-106). */
+int skd_stage_row_bits(skd_ctx* ctx, int32_t B, const uint8_t* label_bits, const uint8_t* train_bits,
+                       int64_t bytes_per_col);
+
 /* Batched binary L2 logistic regression (lbfgs), B independent columns sharing X.
  * Column j: positives = rows with y_class == col_pos[j]; training rows = rows whose fold id
  * != col_fold[j] (col_fold[j] < 0: all rows); l2 strength = 1 / (C[j] * n_train_j).

@@ -40,6 +40,7 @@ SYMBOLS = {
     "skd_stage_targets": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64]),
     "skd_stage_folds": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int32]),
     "skd_stage_column_masks": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p]),
+    "skd_stage_row_bits": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_int64]),
     "skd_logreg_fit_batch": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_int32, _c.c_double, _c.c_int32, _c.c_void_p, _c.c_void_p,
                                         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_double)]),
@@ -135,6 +136,8 @@ def check(rc, ctx=None):
         text = msg.decode() if msg else "libskdist_b200 call failed (rc=%d)" % rc
         if text.startswith("Input X contains NaN"):     # what scikit-learn's check_array raises
             raise ValueError(text)
+        if text.startswith("forest: feature") or "device path supports" in text:   # input outside the device path's limits
+            raise NotImplementedError(text)
         raise SkdError(text)
 
 

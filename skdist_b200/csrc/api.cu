@@ -457,6 +457,34 @@ int skd_stage_column_masks(skd_ctx* ctx, int32_t B, const uint8_t* mask) {
   return 0;
 }
 
+int skd_stage_row_bits(skd_ctx* ctx, int32_t B, const uint8_t* label_bits, const uint8_t* train_bits,
+                       int64_t bytes_per_col) {
+  if (!ctx) return fail(nullptr, "skd_stage_row_bits: ctx is NULL");
+  Ctx* c = &ctx->c;
+  c->rb_cols = 0; c->rb_words = 0;
+  c->h_ybits.clear(); c->h_mbits.clear();
+  if (B <= 0 || (!label_bits && !train_bits)) return 0;   // cleared
+  if (!c->X) return fail(c, "skd_stage_row_bits: stage X first");
+  if (bytes_per_col * 8 < c->n) return fail(c, "skd_stage_row_bits: fewer bits per column than staged rows");
+  const int64_t words = (c->n + 63) / 64 * 2;              // whole 64-row tiles of the tensor-core path
+  const int64_t use = std::min<int64_t>(bytes_per_col, (c->n + 7) / 8);
+  auto pack = [&](const uint8_t* src, std::vector<uint32_t>& dst) {
+    dst.assign((size_t)B * words, 0u);
+    for (int j = 0; j < B; ++j) {
+      memcpy(dst.data() + (size_t)j * words, src + (size_t)j * bytes_per_col, (size_t)use);
+      if (c->n & 7) {   // bits beyond the last row must read as 0
+        uint8_t* last = reinterpret_cast<uint8_t*>(dst.data() + (size_t)j * words) + (c->n >> 3);
+        *last &= (uint8_t)((1u << (c->n & 7)) - 1u);
+      }
+    }
+  };
+  if (label_bits) pack(label_bits, c->h_ybits);
+  if (train_bits) pack(train_bits, c->h_mbits);
+  c->rb_cols = B;
+  c->rb_words = words;
+  return 0;
+}
+
 int skd_set_kernel(skd_ctx* ctx, int32_t which) {
   if (!ctx) return -1;
   int prev = ctx->c.kernel_choice;
@@ -527,6 +555,16 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
     Ctx* c; std::vector<uint8_t> mask; int32_t cols;
     explicit MaskGuard(Ctx* c_) : c(c_), cols(c_->fmask_cols) { mask.swap(c_->h_fmask); c_->fmask_cols = 0; }
   } staged_masks(c);
+  struct BitsGuard {     // staged row bit matrices are one-shot as well
+    std::vector<uint32_t> y, m; int32_t cols; int64_t words;
+    explicit BitsGuard(Ctx* c_) : cols(c_->rb_cols), words(c_->rb_words) { y.swap(c_->h_ybits); m.swap(c_->h_mbits); c_->rb_cols = 0; c_->rb_words = 0; }
+  } staged_bits(c);
+  if (staged_bits.cols > 0) {
+    if (staged_bits.cols != B) return fail(c, "skd_logreg_fit_batch: staged row bit matrices do not match this batch");
+    for (int j = 0; j < B; ++j)
+      if (col_fold[j] >= 0 || (col_neg && col_neg[j] >= 0))
+        return fail(c, "skd_logreg_fit_batch: row bit matrices cannot be combined with folds or pair columns");
+  }
   if (max_iter < 1) return fail(c, "skd_logreg_fit_batch: max_iter must be >= 1");
   SKD_CUDA(c, cudaSetDevice(c->device));
   const int64_t n = c->n, d = c->d, ldx = c->ldx;
@@ -561,6 +599,11 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
         for (int ff = 0; ff < (c->h_fold.empty() ? 1 : c->n_folds); ++ff)
           if (ff != f) ntrain += pair_counts[(size_t)cls * (c->n_folds + 1) + ff];
       }
+    }
+    if (staged_bits.cols > 0 && !staged_bits.m.empty()) {      // training rows of the column = set bits of its mask
+      ntrain = 0;
+      const uint32_t* mw = staged_bits.m.data() + (size_t)j * staged_bits.words;
+      for (int64_t q = 0; q < staged_bits.words; ++q) ntrain += __builtin_popcount(mw[q]);
     }
     if (ntrain <= 0) return fail(c, "skd_logreg_fit_batch: empty training set");
     if (!(C[j] > 0.0)) return fail(c, "skd_logreg_fit_batch: C must be positive");
@@ -622,6 +665,25 @@ int skd_logreg_fit_batch(skd_ctx* ctx, int32_t B, const double* C, const int32_t
     if (staged_masks.cols != B || (int64_t)staged_masks.mask.size() != (int64_t)B * d)
       return fail(c, "skd_logreg_fit_batch: staged column masks do not match this batch (B x d)");
     SKD_CUDA(c, sx.alloc(&w.fmask, (size_t)B * d));
+  }
+  if (staged_bits.cols > 0) {
+    w.rb_words = staged_bits.words;
+    if (!staged_bits.y.empty()) {
+      uint32_t* dy;
+      SKD_CUDA(c, sx.alloc(&dy, staged_bits.y.size()));
+      SKD_CUDA(c, cudaMemcpyAsync(dy, staged_bits.y.data(), staged_bits.y.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      w.ybits = dy;
+      c->h2d += (int64_t)staged_bits.y.size() * 4;
+    }
+    if (!staged_bits.m.empty()) {
+      uint32_t* dm;
+      SKD_CUDA(c, sx.alloc(&dm, staged_bits.m.size()));
+      SKD_CUDA(c, cudaMemcpyAsync(dm, staged_bits.m.data(), staged_bits.m.size() * 4, cudaMemcpyHostToDevice, c->stream));
+      w.mbits = dm;
+      c->h2d += (int64_t)staged_bits.m.size() * 4;
+    }
+    SKD_CUDA(c, cudaStreamSynchronize(c->stream));
+    w.uni_pos = -1;
   }
   SKD_CUDA(c, sx.alloc(&w.slot, (size_t)w.slot_cap));
   SKD_CUDA(c, sx.alloc(&w.n_act, 1));

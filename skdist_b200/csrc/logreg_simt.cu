@@ -52,7 +52,9 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
            const int32_t* __restrict__ ycls, const int8_t* __restrict__ fold,
            int64_t rows_per_chunk, float* __restrict__ G, int ldg, double* __restrict__ lossp,
            double* __restrict__ gsump, int64_t* __restrict__ correct, int64_t* __restrict__ count,
-           float* __restrict__ dec, int ldd, const float* __restrict__ yreal) {
+           float* __restrict__ dec, int ldd, const float* __restrict__ yreal,
+           const uint32_t* __restrict__ ybits = nullptr, const uint32_t* __restrict__ mbits = nullptr,
+           long long rb_words = 0) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   __shared__ double red[16][TN + 1];
@@ -66,15 +68,15 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
   if (row_end > n) row_end = n;
 
   // per-thread slot metadata for its 4 slots
-  int sfold[4], spos[4], sneg1[4];
+  int sfold[4], spos[4], sneg1[4], scol[4];
   float sb[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     int s = s0 + tx * 4 + j;
-    sfold[j] = -100; spos[j] = -100; sneg1[j] = 0; sb[j] = 0.f;
+    sfold[j] = -100; spos[j] = -100; sneg1[j] = 0; sb[j] = 0.f; scol[j] = 0;
     if (s < n_act) {
       sb[j] = bias[s];
-      if (MODE != MODE_DECISION) { sfold[j] = slot[s].fold; spos[j] = slot[s].pos; sneg1[j] = slot[s].pad; }
+      if (MODE != MODE_DECISION) { sfold[j] = slot[s].fold; spos[j] = slot[s].pos; sneg1[j] = slot[s].pad; scol[j] = slot[s].col; }
     }
   }
   double acc_loss[4] = {0, 0, 0, 0}, acc_g[4] = {0, 0, 0, 0};
@@ -134,8 +136,15 @@ fwd_kernel(const float* __restrict__ X, int64_t n, int ldx, const float* __restr
         if (MODE == MODE_FIT) {
           bool train = rvalid && (fd != sfold[j] || sfold[j] < 0) && sfold[j] != -100 &&
                        (sneg1[j] == 0 || yc == spos[j] || yc == sneg1[j] - 1);   // one-vs-one: only the pair's rows
+          bool ypos = yc == spos[j];
+          if (train && (ybits || mbits) && scol[j] >= 0) {    // staged row bit matrices (multilabel targets, sampled negatives)
+            const size_t wi = (size_t)scol[j] * rb_words + (size_t)(gr >> 5);
+            const unsigned sh = (unsigned)(gr & 31);
+            if (mbits) train = (mbits[wi] >> sh) & 1u;
+            if (ybits) ypos = (ybits[wi] >> sh) & 1u;
+          }
           if (train) {
-            double y = (yc == spos[j]) ? 1.0 : 0.0;
+            double y = ypos ? 1.0 : 0.0;
             double l, g;
             loss_grad_half_binomial(y, (double)raw, l, g);
             float lf = (float)l, gf = (float)g;   // sklearn stores both as float32
@@ -296,7 +305,8 @@ int simt_eval(Ctx* c, LogregWork& w, int n_act, int* nz_used) {
   dim3 gf((n_act + TN - 1) / TN, nz);
   fwd_kernel<MODE_FIT><<<gf, 256, 0, c->stream>>>(
       c->X, c->n, ldx, w.Wact, w.Wact + (size_t)w.B * ldx /*bias block*/, w.slot, n_act, c->ycls,
-      c->fold, rpc, w.G, w.ldg, w.lossp, w.gsump, nullptr, nullptr, nullptr, 0, nullptr);
+      c->fold, rpc, w.G, w.ldg, w.lossp, w.gsump, nullptr, nullptr, nullptr, 0, nullptr, w.ybits, w.mbits,
+      (long long)w.rb_words);
   dim3 gb((ldx + 63) / 64, (n_act + TN - 1) / TN, nz);
   bwd_kernel<<<gb, 256, 0, c->stream>>>(c->X, c->n, ldx, w.G, w.ldg, n_act, rpc, w.gradp);
   c->launches += 2;

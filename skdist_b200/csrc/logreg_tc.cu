@@ -136,7 +136,7 @@ struct TcSlotParam {
   int32_t fold;
   int32_t pos;
   int32_t neg1;   // SlotMeta::pad (0 = one-vs-rest, k + 1 = pair with class k)
-  int32_t pad;
+  int32_t col;    // column id of the slot in the caller's batch (-1: padding slot); indexes the row bit matrices
 };
 
 __global__ void __launch_bounds__(128)
@@ -154,7 +154,7 @@ tc_export_kernel(const double* __restrict__ vec, size_t vec_stride, const SlotMe
       Wh[(size_t)s * dpad + k] = __float2half_rn(0.f);
       Wl[(size_t)s * dpad + k] = __float2half_rn(0.f);
     }
-    if (threadIdx.x == 0) { TcSlotParam p; p.inv_t = 1.f; p.bias = 0.f; p.fold = sm.fold; p.pos = -1; p.neg1 = 0; p.pad = 0; sp[s] = p; }
+    if (threadIdx.x == 0) { TcSlotParam p; p.inv_t = 1.f; p.bias = 0.f; p.fold = sm.fold; p.pos = -1; p.neg1 = 0; p.col = -1; sp[s] = p; }
     return;
   }
   const double* x = xin ? xin + (size_t)s * (d + 1) : vec + (size_t)sm.col * vec_stride;
@@ -185,7 +185,7 @@ tc_export_kernel(const double* __restrict__ vec, size_t vec_stride, const SlotMe
     p.fold = sm.fold;
     p.pos = sm.pos;
     p.neg1 = sm.pad;
-    p.pad = 0;
+    p.col = sm.col;
     sp[s] = p;
   }
 }
@@ -213,6 +213,9 @@ struct TcParams {
   int n_lists, n_tiles_ld;
   const float* rowsg;        // TC_FIT_UNI: [n_lists x npad] per-row -y * 2^14 (0 = not a training row of that list)
   long long rowsg_ld;
+  const uint32_t* ybits;     // TC_FIT: per-column row label bits (nullptr: class id == pos), see LogregWork
+  const uint32_t* mbits;     // TC_FIT: per-column training-row bits (nullptr: every row of the training folds)
+  long long rb_words;
   int g_passes;              // MMA passes of the gradient product: 3 = G_hi X_hi + G_lo X_hi + G_hi X_lo, 2 = without G_lo X_hi
   int debug;                 // SKDIST_B200_TC_DEBUG (timing experiments only): 2 = no GEMM2, 3 = no MMAs, 4 = no epilogue work
 };
@@ -489,7 +492,7 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
       const int slot = g * TC_BC + lane_in_group;
       const bool valid = slot < n_live;
       TcSlotParam sp;
-      sp.inv_t = 1.f; sp.bias = 0.f; sp.fold = -1; sp.pos = -1; sp.neg1 = 0; sp.pad = 0;
+      sp.inv_t = 1.f; sp.bias = 0.f; sp.fold = -1; sp.pos = -1; sp.neg1 = 0; sp.col = -1;
       if (valid) sp = prm.sp[slot];
       // fit: work on z / 2^14 so that (row sign * 2^14) * z' = +-z and (row sign * 2^14) * sigma is
       // the scaled gradient entry; all power-of-two factors, results identical to the unscaled form
@@ -547,6 +550,13 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
             yv[4 * j] = v.x; yv[4 * j + 1] = v.y; yv[4 * j + 2] = v.z; yv[4 * j + 3] = v.w;
           }
         }
+        uint32_t yb16 = 0, mb16 = 0xFFFFu;
+        if (MODE == TC_FIT && (prm.ybits || prm.mbits) && sp.col >= 0) {
+          const size_t wi = (size_t)sp.col * prm.rb_words + (size_t)t * 2 + (qt >> 1);
+          const unsigned sh = (qt & 1) * 16;
+          if (prm.ybits) yb16 = (__ldg(prm.ybits + wi) >> sh) & 0xFFFFu;
+          if (prm.mbits) mb16 = (__ldg(prm.mbits + wi) >> sh) & 0xFFFFu;
+        }
         mbar_wait(&bars->z_full[tcount & 1], (tcount >> 1) & 1, 300);
         tc_fence_after();
         if (prm.debug == 4) { tc_fence_before(); mbar_arrive(&bars->g_full[tcount & 1]); continue; }
@@ -566,8 +576,12 @@ tc_eval_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant
               const uint32_t m = rm[j];
               const int fr = (int)(m >> 24);
               const int cls = (int)(m & 0x00FFFFFFu);
-              const bool yb = cls == sp.pos;
-              const bool train = (fr != 0xFF) && (fr != sp.fold) && (sp.neg1 == 0 || yb || cls == sp.neg1 - 1);
+              bool yb = cls == sp.pos;
+              bool train = (fr != 0xFF) && (fr != sp.fold) && (sp.neg1 == 0 || yb || cls == sp.neg1 - 1);
+              if (MODE == TC_FIT) {             // staged row bit matrices (multilabel targets, sampled negatives)
+                if (prm.ybits) yb = (yb16 >> j) & 1u;
+                if (prm.mbits) train = train && ((mb16 >> j) & 1u);
+              }
               sg = train ? (yb ? -GSCALE : GSCALE) : 0.f;
             }
             const float zp = fmaf(__uint_as_float(zr[j]), zi, zb0);
@@ -914,7 +928,10 @@ static int tc_run(Ctx* c, LogregWork& w, int n_act, int mode, int* nz_used, unsi
   prm.ldw = w.ldw;
   { const char* dbg = getenv("SKDIST_B200_TC_DEBUG"); prm.debug = dbg ? atoi(dbg) : 0; }
   { const char* gp = getenv("SKDIST_B200_TC_GPASSES"); prm.g_passes = gp ? atoi(gp) : 3; }
-  const bool uni = mode == TC_FIT && w.grouped && w.uni_pos >= 0 && c->ycls;
+  prm.ybits = mode == TC_FIT ? w.ybits : nullptr;
+  prm.mbits = mode == TC_FIT ? w.mbits : nullptr;
+  prm.rb_words = w.rb_words;
+  const bool uni = mode == TC_FIT && w.grouped && w.uni_pos >= 0 && c->ycls && !w.ybits && !w.mbits;
   if (uni && (!t.rowsg_valid || t.rowsg_pos != w.uni_pos)) {
     if (!t.rowsg) SKD_CUDA(c, cudaMalloc((void**)&t.rowsg, (size_t)t.n_lists * t.npad * sizeof(float)));
     tc_rowsg_kernel<<<(unsigned)((t.npad + 255) / 256), 256, 0, c->stream>>>(c->ycls, c->fold, c->n, t.npad,

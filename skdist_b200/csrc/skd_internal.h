@@ -87,6 +87,11 @@ struct Ctx {
   // per-column feature masks staged for the next skd_logreg_fit_batch (skd_stage_column_masks)
   std::vector<uint8_t> h_fmask;
   int32_t fmask_cols = 0;
+  // per-column row bit matrices staged for the next skd_logreg_fit_batch (skd_stage_row_bits):
+  // label of row r in column j / row r trains column j; packed little-endian, rb_words 32-bit words per column
+  std::vector<uint32_t> h_ybits, h_mbits;
+  int32_t rb_cols = 0;
+  int64_t rb_words = 0;
   // scratch pool: device blocks released by finished calls, reused by the next ones (Scratch below)
   std::vector<std::pair<void*, size_t>> pool_free;
   size_t pool_bytes = 0;
@@ -207,6 +212,9 @@ struct LogregWork {
   int32_t* col_pos = nullptr;  // [B]
   int32_t* col_neg1 = nullptr; // [B] or nullptr (see SlotMeta::pad)
   uint8_t* fmask = nullptr;    // [B x d] or nullptr: 1 = feature takes part in the column's fit
+  const uint32_t* ybits = nullptr;  // [B x rb_words] or nullptr: bit r of column j = its label of row r (instead of class id == pos)
+  const uint32_t* mbits = nullptr;  // [B x rb_words] or nullptr: bit r of column j = row r trains the column
+  int64_t rb_words = 0;
   int32_t* n_evals = nullptr;  // [B]
   // per slot (active batch)
   SlotMeta* slot = nullptr;    // [B]

@@ -77,6 +77,16 @@ def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, ma
     return est
 
 
+_LIMITS = """
+
+    Limits of the device path (checked when the trees are built; `NotImplementedError` otherwise, there
+    is no CPU fallback): every feature may take at most 256 distinct values (the exact splitter works on
+    per-feature value histograms: data on a lattice, counts, categorical codes, quantised measurements --
+    continuous float features need a sort-based splitter that is not built), at most 16 classes, at most
+    384 features, bootstrap multiplicities up to 255, no missing values, `criterion` gini / squared
+    error, no `class_weight`, `warm_start`, `max_leaf_nodes`, `sample_weight` or multi-output targets."""
+
+
 class _DistForestClassifier(_ScParamMixin):
     """Shared fit of the forest classifiers (ref DistBaseForest.fit, ensemble.py:177-336).
     Subclasses set `_splitter` (0 best / 1 random) and `_tree_cls`."""
@@ -270,8 +280,8 @@ class _DistForestClassifier(_ScParamMixin):
 
 
 class DistRandomForestClassifier(_DistForestClassifier, RandomForestClassifier):
-    """Same as sklearn `RandomForestClassifier` with every tree built on a B200.
-    Constructor mirrors ref ensemble.py:378-422 (``sc`` is the FIRST positional argument)."""
+    __doc__ = """Same as sklearn `RandomForestClassifier` with every tree built on a B200.
+    Constructor mirrors ref ensemble.py:378-422 (``sc`` is the FIRST positional argument).""" + _LIMITS
 
     _splitter = 0
     _tree_cls = DecisionTreeClassifier
@@ -288,9 +298,9 @@ class DistRandomForestClassifier(_DistForestClassifier, RandomForestClassifier):
 
 
 class DistExtraTreesClassifier(_DistForestClassifier, ExtraTreesClassifier):
-    """Same as sklearn `ExtraTreesClassifier` with every tree built on a B200 (random splitter:
+    __doc__ = """Same as sklearn `ExtraTreesClassifier` with every tree built on a B200 (random splitter:
     one uniformly drawn threshold per drawn feature, no bootstrap by default).
-    Constructor mirrors ref ensemble.py:437-478 (``sc`` is the FIRST positional argument)."""
+    Constructor mirrors ref ensemble.py:437-478 (``sc`` is the FIRST positional argument).""" + _LIMITS
 
     _splitter = 1
     _tree_cls = ExtraTreeClassifier
@@ -332,8 +342,8 @@ class _DistForestRegressor(_DistForestClassifier):
 
 
 class DistRandomForestRegressor(_DistForestRegressor, RandomForestRegressor):
-    """Same as sklearn `RandomForestRegressor` with every tree built on a B200.
-    Constructor mirrors ref ensemble.py:531-572 (``sc`` FIRST; criterion "mse" = squared error)."""
+    __doc__ = """Same as sklearn `RandomForestRegressor` with every tree built on a B200.
+    Constructor mirrors ref ensemble.py:531-572 (``sc`` FIRST; criterion "mse" = squared error).""" + _LIMITS
 
     _splitter = 0
     _tree_cls = DecisionTreeRegressor
@@ -348,8 +358,8 @@ class DistRandomForestRegressor(_DistForestRegressor, RandomForestRegressor):
 
 
 class DistExtraTreesRegressor(_DistForestRegressor, ExtraTreesRegressor):
-    """Same as sklearn `ExtraTreesRegressor` with every tree built on a B200.
-    Constructor mirrors ref ensemble.py:584-616."""
+    __doc__ = """Same as sklearn `ExtraTreesRegressor` with every tree built on a B200.
+    Constructor mirrors ref ensemble.py:584-616.""" + _LIMITS
 
     _splitter = 1
     _tree_cls = ExtraTreeRegressor

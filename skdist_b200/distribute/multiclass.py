@@ -12,6 +12,9 @@ carry an integer class id, column k treats `class id == k` as positive.
   SGDClassifier(loss="hinge"|"log_loss") Engine.sgd_fit_batch (exact-order column-batched SGD)
   anything else                          NotImplementedError (no CPU fallback by design)
 
+Multilabel targets and `max_negatives` give every column its own label vector / row set: bit
+matrices on the device (`skd_stage_row_bits`), LogisticRegression base.
+
 `DistOneVsOneClassifier` (ref multiclass.py:365-475) fits the K(K-1)/2 class pairs the same way:
 pair (i, j) is a column whose training rows are masked to classes i and j on the device
 (`col_neg`), replacing the reference's per-pair `X[cond]` copy (`_fit_ovo_binary`, :155-173).
@@ -70,6 +73,32 @@ def _binary_estimator(template, coef_row, n_features, X_dtype, **extra):
     return est
 
 
+def _negatives_rows(pos_mask, max_negatives, random_state, method):
+    """Training rows of one label column under the reference's negative down-sampling
+    (`_negatives_mask`, ref multiclass.py:76-106): every positive row plus the negatives that
+    `train_test_split(..., test_size=max_negatives, random_state=random_state)` puts in its test part.
+    Returns a boolean row mask (all True where the reference keeps every row).  The reference
+    additionally shuffles the kept rows, which does not change a full-batch lbfgs fit beyond the
+    summation order."""
+    from sklearn.model_selection import train_test_split
+    pos_mask = np.asarray(pos_mask, dtype=bool)
+    n_pos = int(pos_mask.sum())
+    n_neg = int(len(pos_mask) - n_pos)
+    if method == "ratio":
+        pass
+    elif method == "multiplier":
+        max_negatives = int(max_negatives * n_pos)
+    else:
+        raise ValueError("Unknown method. Options are 'ratio' or 'multiplier'.")
+    if isinstance(max_negatives, (int, np.integer)) and max_negatives >= n_neg:
+        return np.ones(len(pos_mask), bool)
+    frac = max_negatives if isinstance(max_negatives, float) else (max_negatives / float(n_neg))
+    _, neg_rows = train_test_split(np.flatnonzero(~pos_mask), test_size=frac, random_state=random_state)
+    mask = pos_mask.copy()
+    mask[neg_rows] = True
+    return mask
+
+
 class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
     """One-vs-the-rest with all label columns fitted as one batched GPU solve.
     Constructor mirrors ref multiclass.py:230-253 (``sc`` is the 2nd positional argument)."""
@@ -90,42 +119,78 @@ class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
         self.n_jobs = n_jobs
 
     def fit(self, X, y, **fit_params):
-        """Fit the K binary estimators (ref multiclass.py:255-335)."""
+        """Fit the K binary estimators (ref multiclass.py:255-335).
+
+        1-d class labels: column k = `class id == k` (the rows carry one integer id).  Multilabel
+        targets (indicator matrix, or sequences of labels -> `MultiLabelBinarizer` unless
+        `mlb_override`, ref :267-274) and `max_negatives` (ref `_negatives_mask`, :76-106) give every
+        column its own 0/1 label vector / training-row set: both go to the device as bit matrices
+        (`Engine.stage_row_bits`), no `X[rows]` copies.  `n_splits` only cuts X into broadcast pieces in
+        the reference (`_split_X`, :35-50) and has no effect here."""
         if fit_params:
             raise NotImplementedError("fit_params are not supported on the device path")
         _check_estimator(self, verbose=self.verbose)
-        if self.max_negatives is not None:
-            raise NotImplementedError("max_negatives down-sampling has no device path yet")
+        from collections.abc import Sequence
+        if (not self.mlb_override and not hasattr(y[0], "__array__") and isinstance(y[0], Sequence)
+                and not isinstance(y[0], str)):                          # ref :267-274
+            from sklearn.preprocessing import MultiLabelBinarizer
+            self.mlb = MultiLabelBinarizer()
+            y = self.mlb.fit_transform(y)
         X_arr = np.asarray(X)
         y_arr = np.asarray(y)
-        if y_arr.ndim != 1:
-            raise NotImplementedError("multilabel targets have no device path yet (1-d class labels only)")
         self.label_binarizer_ = LabelBinarizer(sparse_output=True)      # ref :279-281
         self.label_binarizer_.fit(y_arr)
         self.classes_ = self.label_binarizer_.classes_
         K = len(self.classes_)
         n, d = X_arr.shape
         _parse_partitions(self.partitions, K)
-        ycls = np.searchsorted(self.classes_, y_arr).astype(np.int32)
-        counts = np.bincount(ycls, minlength=K)
+        base = self.estimator
+        multilabel = y_arr.ndim == 2
+        use_bits = multilabel or self.max_negatives is not None
+        if use_bits and type(base) is not LogisticRegression:
+            raise NotImplementedError(
+                "multilabel targets / max_negatives need per-column row sets: device path for "
+                "LogisticRegression(solver='lbfgs') only (SGD walks one shared sample order)")
+        if multilabel:
+            Y = self.label_binarizer_.transform(y_arr).tocsc()          # ref :289-290
+            ycls = np.zeros(n, np.int32)
+            counts = np.asarray(Y.sum(axis=0)).ravel().astype(np.int64)
+            n_cols = Y.shape[1]
+        else:
+            ycls = np.searchsorted(self.classes_, y_arr).astype(np.int32)
+            counts = np.bincount(ycls, minlength=K)
+            n_cols = 1 if K == 2 else K
 
         rank, world, _ = parallel.dist_info()
         eng = get_engine()
         parallel.stage_x_replicated(eng, X_arr)
         eng.stage_labels(ycls)
         eng.stage_folds(None, 0)
-        base = self.estimator
         # constant columns (a label present in every / no row) -> _ConstantPredictor (ref :121-139)
-        const = (counts == 0) | (counts == n) if K > 2 else np.zeros(K, bool)
-        if K == 2:
+        if multilabel:
+            const = (counts == 0) | (counts == n)
+            col_ids = np.flatnonzero(~const)
+        elif K == 2:
             # LabelBinarizer gives ONE column for binary problems (positive = classes_[1])
+            const = np.zeros(K, bool)
             col_ids = np.array([1])
         else:
+            const = (counts == 0) | (counts == n)
             col_ids = np.flatnonzero(~const)
         mine = col_ids[parallel.shard_indices(len(col_ids), rank, world)]
         if type(base) is LogisticRegression:
             from .logreg_family import _check_logreg
             p = _check_logreg(_clone(base))
+            if use_bits and len(mine):
+                if multilabel:
+                    labels = np.ascontiguousarray(Y[:, mine].toarray().T.astype(bool))
+                else:
+                    labels = ycls[None, :] == mine[:, None].astype(np.int32)
+                train = None
+                if self.max_negatives is not None:
+                    train = np.stack([_negatives_rows(labels[i], self.max_negatives, self.random_state, self.method)
+                                      for i in range(len(mine))])
+                eng.stage_row_bits(labels if multilabel else None, train)
             res = eng.logreg_fit_batch(np.full(len(mine), p["C"]), np.full(len(mine), -1, np.int32),
                                        mine.astype(np.int32), fit_intercept=p["fit_intercept"],
                                        tol=p["tol"], max_iter=p["max_iter"])
@@ -143,7 +208,7 @@ class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
         full = parallel.all_gather_columns(packed, len(col_ids), rank, world)
         by_col = {int(c): full[i] for i, c in enumerate(col_ids)}
         ests = []
-        cols = [1] if K == 2 else range(K)
+        cols = [1] if (K == 2 and not multilabel) else range(n_cols)
         make = _Cloner(base)
         for k in cols:
             if k in by_col:

@@ -137,6 +137,28 @@ class Engine:
         assert m.ndim == 2 and m.shape[1] == self.d
         check(self._lib.skd_stage_column_masks(self._h, m.shape[0], ptr(m)), self._h)
 
+    def stage_row_bits(self, labels=None, train=None):
+        """[B, n] 0/1 matrices consumed by the next logreg_fit_batch: `labels[j, r]` = binary label of
+        row r in column j (multilabel targets), `train[j, r]` = row r takes part in column j's fit
+        (sampled negatives).  None clears."""
+        if labels is None and train is None:
+            check(self._lib.skd_stage_row_bits(self._h, 0, None, None, 0), self._h)
+            return
+        packed = []
+        B = None
+        for m in (labels, train):
+            if m is None:
+                packed.append(None)
+                continue
+            m = np.asarray(m)
+            assert m.ndim == 2 and m.shape[1] == self.n
+            B = m.shape[0] if B is None else B
+            assert m.shape[0] == B
+            packed.append(np.ascontiguousarray(np.packbits(m.astype(bool), axis=1, bitorder="little")))
+        bpc = next(p for p in packed if p is not None).shape[1]
+        check(self._lib.skd_stage_row_bits(self._h, B, ptr(packed[0]) if packed[0] is not None else None,
+                                           ptr(packed[1]) if packed[1] is not None else None, bpc), self._h)
+
     def logreg_fit_batch(self, C, col_fold, col_pos, fit_intercept=True, tol=1e-4, max_iter=100, col_neg=None):
         """B binary lbfgs fits sharing the staged X.  col_neg[j] >= 0 restricts column j to the rows
         of class col_pos[j] / col_neg[j] (one-vs-one pair); None or < 0 = one-vs-rest."""

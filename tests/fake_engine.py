@@ -37,10 +37,16 @@ class FakeEngine:
     def stage_column_masks(self, mask):
         self._fmask = None if mask is None else np.asarray(mask, dtype=bool)
 
+    def stage_row_bits(self, labels=None, train=None):
+        self._ybits = None if labels is None else np.asarray(labels, dtype=bool)
+        self._mbits = None if train is None else np.asarray(train, dtype=bool)
+
     def logreg_fit_batch(self, C, col_fold, col_pos, fit_intercept=True, tol=1e-4, max_iter=100, col_neg=None):
         B = len(C)
         fmask = getattr(self, "_fmask", None)
         self._fmask = None
+        ybits, mbits = getattr(self, "_ybits", None), getattr(self, "_mbits", None)
+        self._ybits = self._mbits = None
         self.calls.append(("fit", B))
         coef = np.zeros((B, self.d + 1), np.float32)
         n_iter = np.zeros(B, np.int32)
@@ -48,7 +54,9 @@ class FakeEngine:
             m = self._train_mask(int(col_fold[j]))
             if col_neg is not None and col_neg[j] >= 0:
                 m = m & ((self.y == col_pos[j]) | (self.y == col_neg[j]))
-            y01 = (self.y[m] == col_pos[j]).astype(np.float32)
+            if mbits is not None:
+                m = m & mbits[j]
+            y01 = (self.y[m] == col_pos[j]).astype(np.float32) if ybits is None else ybits[j][m].astype(np.float32)
             keep = np.arange(self.d) if fmask is None else np.flatnonzero(fmask[j])
             Xm = self.X[m] if fmask is None else np.ascontiguousarray(self.X[m][:, keep])
             w, b, it = lo.fit_binary_lbfgs(Xm, y01, C=float(C[j]), tol=tol, max_iter=max_iter,

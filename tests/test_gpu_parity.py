@@ -362,6 +362,40 @@ def test_ovr_sgd_tensor_core_path_bit_identical(eng, monkeypatch, n, d, k, alpha
         np.testing.assert_array_equal(a.intercept_, b.intercept_)
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_ovr_row_bit_matrices_on_device(eng, kernel):
+    """Per-column row sets on the device (skd_stage_row_bits): `max_negatives` down-sampling and
+    multilabel targets of DistOneVsRestClassifier(LogisticRegression) against scikit-learn fits on
+    the rows the reference's `_negatives_mask` keeps / on the indicator columns (well-conditioned
+    problems: converged fits, coefficients to 1e-3 of max|w|, identical predictions but near-ties)."""
+    from skdist.distribute.multiclass import DistOneVsRestClassifier
+    from skdist_b200.distribute.multiclass import _negatives_rows
+    from skdist_b200.datasets import make_multiclass
+    X, y = make_multiclass(6000, 48, 5, seed=31)
+    eng.set_kernel(kernel)
+    try:
+        ovr = DistOneVsRestClassifier(LogisticRegression(C=0.05), None, max_negatives=2.0, method="multiplier",
+                                      random_state=11).fit(X, y)
+        rng = np.random.default_rng(5)
+        Y = np.stack([(X[:, 0] + 0.3 * rng.standard_normal(len(X)) > 0.4), (X[:, 1] - X[:, 2] > 0.2),
+                      (rng.random(len(X)) < 0.2)], axis=1).astype(int)
+        ml = DistOneVsRestClassifier(LogisticRegression(C=0.05), None).fit(X, Y)
+    finally:
+        eng.set_kernel(0)
+    for k, est in enumerate(ovr.estimators_):
+        m = _negatives_rows(y == k, 2.0, 11, "multiplier")
+        assert m.sum() == 3 * (y == k).sum()
+        ref = LogisticRegression(C=0.05).fit(X[m], (y[m] == k).astype(int))
+        assert est.n_iter_[0] == ref.n_iter_[0] or abs(int(est.n_iter_[0]) - int(ref.n_iter_[0])) <= 1
+        np.testing.assert_allclose(est.coef_, ref.coef_, rtol=0, atol=1e-3 * np.abs(ref.coef_).max())
+        assert np.mean(est.predict(X) == ref.predict(X)) > 0.999
+    for k, est in enumerate(ml.estimators_):
+        ref = LogisticRegression(C=0.05).fit(X, Y[:, k])
+        np.testing.assert_allclose(est.coef_, ref.coef_, rtol=0, atol=1e-3 * np.abs(ref.coef_).max())
+        assert np.mean(est.predict(X) == ref.predict(X)) > 0.999
+    assert ml.predict(X[:10]).shape == (10, 3)
+
+
 def test_ovr_sgd_log_loss_on_device(eng):
     """log_loss SGD evaluates sklearn 1.9's CyHalfBinomialLoss formulas (y in {0,1}) in the same
     order, but exp/log/log1p come from CUDA's libdevice instead of glibc (both < 1 ulp, not

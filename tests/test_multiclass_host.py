@@ -115,3 +115,54 @@ def test_string_labels_and_pandas_inputs(fake_engine):
     ovo = DistOneVsOneClassifier(LogisticRegression(C=0.3), None).fit(X, names)
     refo = OneVsOneClassifier(LogisticRegression(C=0.3)).fit(X, names)
     np.testing.assert_array_equal(ovo.predict(X), refo.predict(X))
+
+
+def test_negatives_rows_match_reference():
+    """`max_negatives` down-sampling: the training rows of a label column equal the rows the
+    reference's `_negatives_mask` (ref multiclass.py:76-106) keeps, for every method / type of
+    `max_negatives` / random_state."""
+    if not refshim.available():
+        pytest.skip("reference tree not present")
+    from skdist_b200.distribute.multiclass import _negatives_rows
+    _, mc, _ = refshim.load()
+    rng = np.random.default_rng(0)
+    n = 5000
+    X = np.arange(n, dtype=np.float64)[:, None]
+    y = (rng.random(n) < 0.07).astype(int)
+    for mn, method in [(300, "ratio"), (0.2, "ratio"), (2, "multiplier"), (1.5, "multiplier"), (10 ** 6, "ratio")]:
+        for rs in (0, 7):
+            Xr, yr = mc._negatives_mask(X, y, max_negatives=mn, random_state=rs, method=method)
+            rows = np.sort(Xr[:, 0].astype(int))
+            np.testing.assert_array_equal(rows, np.flatnonzero(_negatives_rows(y == 1, mn, rs, method)))
+            assert yr.sum() == y.sum()
+
+
+def test_ovr_max_negatives_and_multilabel_host(fake_engine):
+    """Host logic of the per-column row sets: with the engine double doing each column's fit the way the
+    reference's `_fit_binary` does (lbfgs on the kept rows), DistOneVsRestClassifier equals a loop over
+    scikit-learn fits on `_negatives_rows` / on the columns of a multilabel indicator matrix."""
+    from skdist_b200.distribute.multiclass import _negatives_rows
+    X, y = make_multiclass(1500, 8, 4, seed=9)
+    ovr = DistOneVsRestClassifier(LogisticRegression(), None, max_negatives=200, random_state=3).fit(X, y)
+    for k, est in enumerate(ovr.estimators_):
+        m = _negatives_rows(y == k, 200, 3, "ratio")
+        ref = LogisticRegression().fit(X[m], (y[m] == k).astype(int))
+        np.testing.assert_allclose(est.coef_, ref.coef_, rtol=0, atol=2e-4 * np.abs(ref.coef_).max())
+        assert m.sum() == (y == k).sum() + 200
+    # multilabel: indicator matrix and sequences of labels (MultiLabelBinarizer, ref :267-274)
+    rng = np.random.default_rng(1)
+    Y = (rng.random((1500, 3)) < 0.3).astype(int)
+    Y[:, 0] |= (X[:, 0] > 0.5)
+    ml = DistOneVsRestClassifier(LogisticRegression(), None).fit(X, Y)
+    assert len(ml.estimators_) == 3 and ml.label_binarizer_.y_type_ == "multilabel-indicator"
+    for k, est in enumerate(ml.estimators_):
+        ref = LogisticRegression().fit(X, Y[:, k])
+        np.testing.assert_allclose(est.coef_, ref.coef_, rtol=0, atol=2e-4 * np.abs(ref.coef_).max())
+    np.testing.assert_array_equal(ml.predict(X[:50]).shape, (50, 3))
+    seqs = [tuple(np.flatnonzero(r)) for r in Y]
+    ml2 = DistOneVsRestClassifier(LogisticRegression(), None).fit(X, seqs)
+    assert hasattr(ml2, "mlb") and len(ml2.estimators_) == 3
+    for a, b in zip(ml.estimators_, ml2.estimators_):
+        np.testing.assert_array_equal(a.coef_, b.coef_)
+    with pytest.raises(NotImplementedError):
+        DistOneVsRestClassifier(SGDClassifier(), None, max_negatives=100).fit(X, y)
