@@ -99,3 +99,49 @@ def _cv_fold_ids(cv, X, y, groups, n_samples, enc=None):
                 return fold, k
     cv_splitted = list(cv.split(X, y, groups))
     return _fold_ids(cv_splitted, n_samples), len(cv_splitted)
+
+
+def _cv_fold_groups(cv, X, y, groups, n_samples, enc=None):
+    """Fold-id layouts for ANY cross-validator whose train sets are the complements of its test sets
+    (ShuffleSplit, StratifiedShuffleSplit, RepeatedKFold, RepeatedStratifiedKFold, LeavePOut,
+    PredefinedSplit, Group* ... as well as the partitions `_cv_fold_ids` handles directly).
+
+    Returns (layouts, n_splits): every layout is (fold id per row int8, n_folds, split indices) -- a
+    set of splits with pairwise disjoint test sets; split `split indices[k]` holds out the rows with
+    fold id k, rows in none of the layout's test sets carry the extra id `n_folds - 1` that no column
+    holds out.  A partition is one layout (no extra id); ShuffleSplit(n) is n layouts of one split.
+    The search re-stages the fold ids (n bytes) per layout; X stays staged.  Splitters whose train set
+    is not the complement of the test set (TimeSeriesSplit) have no device path."""
+    try:
+        fold, n_splits = _cv_fold_ids(cv, X, y, groups, n_samples, enc)
+        return [(fold, n_splits, list(range(n_splits)))], n_splits
+    except NotImplementedError:
+        pass
+    cv_splitted = list(cv.split(X, y, groups))
+    n_splits = len(cv_splitted)
+    layouts = []       # [used mask, fold ids, split indices]
+    for s, (train, test) in enumerate(cv_splitted):
+        train, test = np.asarray(train), np.asarray(test)
+        if len(train) + len(test) != n_samples or len(np.intersect1d(train, test, assume_unique=False)):
+            raise NotImplementedError(
+                "cv splits whose train set is not the complement of the test set (e.g. TimeSeriesSplit) "
+                "are not supported on the device path")
+        for lay in layouts:
+            if len(lay[2]) < 126 and not np.any(lay[0][test]):
+                break
+        else:
+            lay = [np.zeros(n_samples, bool), np.full(n_samples, -1, dtype=np.int8), []]
+            layouts.append(lay)
+        lay[1][test] = len(lay[2])
+        lay[0][test] = True
+        lay[2].append(s)
+    out = []
+    for used, fold, idx in layouts:
+        k = len(idx)
+        if np.all(used):
+            out.append((fold, k, idx))
+        else:
+            fold = fold.copy()
+            fold[~used] = k            # never held out
+            out.append((fold, k + 1, idx))
+    return out, n_splits

@@ -43,7 +43,7 @@ from .validation import _check_estimator, _check_n_iter, _validate_models
 __all__ = ["DistGridSearchCV", "DistRandomizedSearchCV", "DistMultiModelSearch"]
 
 
-from .folds import _cv_fold_ids, _encode_target
+from .folds import _cv_fold_groups, _cv_fold_ids, _encode_target
 from .logreg_family import _LogRegFamily, _MultinomialFamily
 
 
@@ -113,32 +113,46 @@ class DistBaseSearchCV(_ScParamMixin):
                         n_splits, n_candidates, n_candidates * n_splits))
                 _parse_partitions(self.partitions, n_candidates * n_splits)
                 enc = _encode_target(y_arr) if is_classifier(estimator) else None   # one hash pass over y for both
-                fold, _ = _cv_fold_ids(cv, X, y_arr, groups, n_samples, enc)
+                layouts, n_splits = _cv_fold_groups(cv, X, y_arr, groups, n_samples, enc)
+                fold = layouts[0][0]
                 family = _pick_family(estimator, candidate_params, X_arr, y_arr, scorers, enc)
                 if hasattr(family, "prepare"):      # host-only statistics of the folds (no engine calls)
-                    family.prepare(fold, n_splits)
+                    family.prepare(fold, layouts[0][1])
             finally:
                 staged.result()
 
         rank, world, _ = parallel.dist_info()
-        family.stage(eng, X_arr, fold, n_splits, x_staged=True)
-
-        # task order: candidate-major, fold-minor (ref search.py:378-383), column = cand * n_splits + fold.
-        # Ranks are dealt blocks of 128 consecutive candidates of ONE fold (fold-major order).
-        n_cols = n_candidates * n_splits
-        deal_order = (np.arange(n_candidates)[None, :] * n_splits + np.arange(n_splits)[:, None]).ravel()
-        col_cost = family.column_cost(n_splits) if world > 1 and hasattr(family, "column_cost") else None
-        my_cols = parallel.shard_blocks(n_cols, rank, world, deal_order, cost=col_cost)
-        loc = family.run_columns(eng, my_cols, n_splits, bool(self.return_train_score))
         metric_names = list(family.metrics)
         keys = ["n_test", "fit_time", "score_time"] + ["test_%s" % m for m in metric_names]
         if self.return_train_score:
             keys += ["train_%s" % m for m in metric_names]
-        # one collective for all per-column results (counts are exact in float64)
-        stacked = np.stack([np.asarray(loc[k], dtype=np.float64) for k in keys], axis=1)
-        gathered = parallel.all_gather_blocks(stacked, n_cols, rank, world, deal_order, cost=col_cost)
-        res = {k: gathered[:, i] for i, k in enumerate(keys)}
+        # task order: candidate-major, fold-minor (ref search.py:378-383), column = cand * n_splits + split.
+        # A cross-validator whose test sets overlap (ShuffleSplit, RepeatedKFold ...) comes as several
+        # fold-id layouts of disjoint test sets; the fold ids (n bytes) are re-staged per layout, X once.
+        n_cols = n_candidates * n_splits
+        full = np.zeros((n_cols, len(keys)))
+        for li, (fold_l, nf_l, idx_l) in enumerate(layouts):
+            if li > 0 and hasattr(family, "prepare"):
+                family.prepare(fold_l, nf_l)
+            family.stage(eng, X_arr, fold_l, nf_l, x_staged=True)
+            k_l = len(idx_l)
+            # local columns cand * nf_l + f, f < k_l (the extra fold id of a layout is never held out).
+            # Ranks are dealt blocks of 128 consecutive candidates of ONE fold (fold-major order).
+            cols_l = (np.arange(n_candidates)[None, :] * nf_l + np.arange(k_l)[:, None]).ravel()
+            col_cost = None
+            if world > 1 and hasattr(family, "column_cost"):
+                col_cost = family.column_cost(nf_l)[cols_l]
+            pick = parallel.shard_blocks(len(cols_l), rank, world, cost=col_cost)
+            loc = family.run_columns(eng, cols_l[pick], nf_l, bool(self.return_train_score))
+            # one collective per layout for all per-column results (counts are exact in float64)
+            stacked = np.stack([np.asarray(loc[k], dtype=np.float64) for k in keys], axis=1)
+            gathered = parallel.all_gather_blocks(stacked, len(cols_l), rank, world, cost=col_cost)
+            cand_l, f_l = cols_l // nf_l, cols_l % nf_l
+            full[cand_l * n_splits + np.asarray(idx_l)[f_l]] = gathered
+        res = {k: full[:, i] for i, k in enumerate(keys)}
         res["n_test"] = np.rint(res["n_test"]).astype(np.int64)
+        if len(layouts) > 1 and self.refit and self.preds:
+            raise NotImplementedError("preds=True needs a cross-validator whose test sets partition the rows")
 
         error_score = self.error_score
         for m in metric_names:

@@ -352,3 +352,35 @@ def test_odd_inputs_match_sklearn(fake_engine):
     check(X, y, g={"C": [0.5]}, cv=2)
     ym = (np.arange(600) % 3 == 0).astype(int) + 2 * (np.arange(600) % 5 == 0)      # 4 classes, strings below
     check(X, np.array(["a", "b", "c", "d"])[ym])
+
+
+@pytest.mark.parametrize("cvname", ["shuffle", "repeated", "predefined"])
+def test_cross_validators_with_overlapping_test_sets(fake_engine, cvname):
+    """Any splitter whose train sets are the complements of its test sets (ref search.py:334,379 take
+    whatever `check_cv` returns): the splits are grouped into fold-id layouts of disjoint test sets
+    (folds._cv_fold_groups); cv_results_ equal scikit-learn's GridSearchCV on the same splitter."""
+    from sklearn.model_selection import GridSearchCV, PredefinedSplit, RepeatedStratifiedKFold, ShuffleSplit
+    X, y = make_g1_classification(900, 8, seed=11)
+    if cvname == "shuffle":
+        cv = ShuffleSplit(n_splits=4, test_size=0.3, random_state=2)
+    elif cvname == "repeated":
+        cv = RepeatedStratifiedKFold(n_splits=3, n_repeats=2, random_state=5)
+    else:
+        tf = np.random.RandomState(0).randint(-1, 3, size=len(y))      # -1: always in the training set
+        cv = PredefinedSplit(tf)
+    grid = {"C": [0.01, 0.1, 1.0]}
+    gs = DistGridSearchCV(LogisticRegression(), grid, None, cv=cv).fit(X, y)
+    ref = GridSearchCV(LogisticRegression(), grid, cv=cv).fit(X, y)
+    n_splits = cv.get_n_splits(X, y)
+    assert gs.n_splits_ == n_splits
+    for i in range(n_splits):
+        np.testing.assert_allclose(gs.cv_results_["split%d_test_score" % i], ref.cv_results_["split%d_test_score" % i],
+                                   rtol=0, atol=1e-12)
+    assert gs.best_params_ == ref.best_params_
+
+
+def test_time_series_split_has_no_device_path(fake_engine):
+    from sklearn.model_selection import TimeSeriesSplit
+    X, y = make_g1_classification(300, 5, seed=1)
+    with pytest.raises(NotImplementedError):
+        DistGridSearchCV(LogisticRegression(), {"C": [1.0]}, None, cv=TimeSeriesSplit(3)).fit(X, y)
