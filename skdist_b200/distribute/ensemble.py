@@ -84,7 +84,7 @@ _LIMITS = """
     per-feature value histograms: data on a lattice, counts, categorical codes, quantised measurements --
     continuous float features need a sort-based splitter that is not built), at most 16 classes, at most
     384 features, bootstrap multiplicities up to 255, no missing values, `criterion` gini / squared
-    error, no `class_weight`, `warm_start`, `max_leaf_nodes`, `sample_weight` or multi-output targets."""
+    error, no `class_weight`, `max_leaf_nodes`, `sample_weight` or multi-output targets."""
 
 
 class _DistForestClassifier(_ScParamMixin):
@@ -145,8 +145,6 @@ class _DistForestClassifier(_ScParamMixin):
             bad.append("max_leaf_nodes (best-first builder)")
         if self.class_weight is not None:
             bad.append("class_weight")
-        if self.warm_start:
-            bad.append("warm_start")
         if self.min_impurity_split is not None:
             bad.append("min_impurity_split")
         if bad:
@@ -197,15 +195,28 @@ class _DistForestClassifier(_ScParamMixin):
         mss = max(int(mss), 2 * int(msl))
         min_weight_leaf = self.min_weight_fraction_leaf * n
         random_state = check_random_state(self.random_state)
-        states = list(random_state.randint(MAX_RAND_SEED, size=self.n_estimators))   # ref :278
-        _parse_partitions(self.partitions, self.n_estimators)
+        # warm start (ref :250-272): keep the fitted trees, draw past their seeds, grow only the new ones
+        kept = list(self.estimators_) if (self.warm_start and hasattr(self, "estimators_")) else []
+        n_more = self.n_estimators - len(kept)
+        if n_more < 0:
+            raise ValueError("n_estimators=%d must be larger or equal to len(estimators_)=%d when warm_start==True"
+                             % (self.n_estimators, len(kept)))
+        if n_more == 0:
+            import warnings
+            warnings.warn("Warm-start fitting without increasing n_estimators does not fit new trees.")
+            self.__dict__.pop("sc", None)
+            return self
+        if kept:
+            random_state.randint(MAX_RAND_SEED, size=len(kept))                   # ref :267-269
+        states = list(random_state.randint(MAX_RAND_SEED, size=n_more))         # ref :278
+        _parse_partitions(self.partitions, n_more)
 
         rank, world, _ = parallel.dist_info()
         eng = get_engine()
         parallel.stage_x_replicated(eng, X)
         eng.stage_labels(y_enc.astype(np.int32))
         eng.stage_folds(None, 0)
-        mine = parallel.shard_indices(self.n_estimators, rank, world)
+        mine = parallel.shard_indices(n_more, rank, world)
         my_states = [states[i] for i in mine]
         crit = "squared_error" if self._regression else self.criterion
         tmpl = dict(criterion=crit, max_depth=self.max_depth, min_samples_split=self.min_samples_split,
@@ -263,13 +274,13 @@ class _DistForestClassifier(_ScParamMixin):
             import torch.distributed as dist
             gathered = [None] * world
             dist.all_gather_object(gathered, local)
-            ests = [None] * self.n_estimators
+            ests = [None] * n_more
             for r in range(world):
-                for i, e in zip(parallel.shard_indices(self.n_estimators, r, world), gathered[r]):
+                for i, e in zip(parallel.shard_indices(n_more, r, world), gathered[r]):
                     ests[i] = e
         else:
             ests = local
-        self.estimators_ = ests
+        self.estimators_ = kept + ests
         self.estimator_ = self._tree_cls()
         self.__dict__.pop("sc", None)                                                     # ref :335
         return self

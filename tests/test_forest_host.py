@@ -109,3 +109,33 @@ def test_forest_fit_pipeline_on_engine_double(fake_engine, kind, monkeypatch):
         np.testing.assert_array_equal(a.tree_.children_left, b.tree_.children_left)
         np.testing.assert_array_equal(a.tree_.value, b.tree_.value)
     np.testing.assert_array_equal(ours.predict(Xq), ref.predict(Xq))
+
+
+def test_warm_start_adds_the_trees_a_cold_fit_would_have(fake_engine):
+    """ref ensemble.py:250-272: with warm_start the fitted trees are kept, the random state is drawn
+    past their seeds and only the additional trees are built -- the forest equals a cold fit with the
+    larger n_estimators (and scikit-learn's warm-started RandomForestClassifier)."""
+    from sklearn.ensemble import RandomForestClassifier
+    from skdist.distribute.ensemble import DistRandomForestClassifier
+    rng = np.random.default_rng(3)
+    X = rng.integers(0, 16, size=(400, 6)).astype(np.float32)
+    y = (X[:, 0] + X[:, 1] > 14).astype(int)
+    from sklearn.utils import check_random_state
+    from skdist.distribute.ensemble import MAX_RAND_SEED, _tree_inputs
+    from skdist_b200.engine import get_engine
+    states = check_random_state(9).randint(MAX_RAND_SEED, size=7)
+    get_engine().seed_of_rand_r = {int(_tree_inputs(s, len(y), False)[1]): int(s) for s in states}
+    warm = DistRandomForestClassifier(n_estimators=3, random_state=9, warm_start=True).fit(X, y)
+    warm.sc = None
+    warm.set_params(n_estimators=7)
+    warm.fit(X, y)
+    cold = DistRandomForestClassifier(n_estimators=7, random_state=9).fit(X, y)
+    ref = RandomForestClassifier(n_estimators=7, random_state=9).fit(X, y)
+    assert len(warm.estimators_) == 7
+    for a, b, c in zip(warm.estimators_, cold.estimators_, ref.estimators_):
+        np.testing.assert_array_equal(a.tree_.threshold, b.tree_.threshold)
+        np.testing.assert_array_equal(a.tree_.threshold, c.tree_.threshold)
+        np.testing.assert_array_equal(a.tree_.value, c.tree_.value)
+    with pytest.raises(ValueError):
+        warm.set_params(n_estimators=5)
+        warm.fit(X, y)
