@@ -226,6 +226,10 @@ int skd_forest_tree_size(skd_forest* f, int32_t tree, int32_t* node_count, int32
 int skd_forest_tree_copy(skd_forest* f, int32_t tree, int32_t* left, int32_t* right, int32_t* feature,
                          double* threshold, double* impurity, int32_t* n_node_samples,
                          double* weighted_n_node_samples, uint8_t* missing_go_to_left, double* value);
+/* One tree as scikit-learn `Node` records (64 bytes each: left, right, feature int64; threshold, impurity
+ * float64; n_node_samples int64; weighted_n_node_samples float64; missing_go_to_left uint8 + padding;
+ * SK/tree/_tree.pxd:15-25) plus value [node_count][n_classes]: the state `Tree.__setstate__` takes. */
+int skd_forest_tree_nodes(skd_forest* f, int32_t tree, void* nodes64, double* value);
 void skd_forest_free(skd_forest* f);
 
 /* Sum of squared residuals and row counts of B linear regressors on the rows selected by the

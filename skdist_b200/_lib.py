@@ -73,6 +73,7 @@ SYMBOLS = {
     "skd_forest_kernel_seconds": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_double)]),
     "skd_forest_tree_size": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_int32)]),
     "skd_forest_tree_copy": (_c.c_int, [_c.c_void_p, _c.c_int32] + [_c.c_void_p] * 9),
+    "skd_forest_tree_nodes": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p]),
     "skd_forest_free": (None, [_c.c_void_p]),
     "skd_linear_r2_batch": (_c.c_int, [_c.c_void_p, _c.c_int32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                        _c.c_void_p]),

@@ -1355,6 +1355,32 @@ int skd_forest_tree_copy(skd_forest* f, int32_t tree, int32_t* left, int32_t* ri
   return 0;
 }
 
+// The same tree as an array of 64-byte node records {left, right, feature: int64; threshold, impurity:
+// float64; n_node_samples: int64; weighted_n_node_samples: float64; missing_go_to_left: uint8 + 7 pad}
+// -- scikit-learn's `Node` struct (SK/tree/_tree.pxd:15-25), so that the caller can hand the buffer to
+// `Tree.__setstate__` without building it field by field.
+int skd_forest_tree_nodes(skd_forest* f, int32_t tree, void* nodes64, double* value) {
+  if (!f || tree < 0 || tree >= (int)f->trees.size() || !nodes64) return fail(nullptr, "skd_forest_tree_nodes: bad arguments");
+  const skd_forest::Tree& t = f->trees[tree];
+  const size_t m = (size_t)t.node_count;
+  struct Node64 { int64_t left, right, feature; double threshold, impurity; int64_t n_node_samples; double weighted; uint8_t mgl; uint8_t pad[7]; };
+  static_assert(sizeof(Node64) == 64, "node record must be 64 bytes");
+  Node64* out = (Node64*)nodes64;
+  std::vector<int32_t> l(m), r(m), ft(m), ns(m);
+  std::vector<uint8_t> mg(m);
+  std::vector<double> th(m), im(m), wn(m);
+  if (skd_forest_tree_copy(f, tree, l.data(), r.data(), ft.data(), th.data(), im.data(), ns.data(), wn.data(), mg.data(), value))
+    return 1;
+  for (size_t i = 0; i < m; ++i) {
+    Node64 nd;
+    nd.left = l[i]; nd.right = r[i]; nd.feature = ft[i]; nd.threshold = th[i]; nd.impurity = im[i];
+    nd.n_node_samples = ns[i]; nd.weighted = wn[i]; nd.mgl = mg[i];
+    memset(nd.pad, 0, sizeof(nd.pad));
+    out[i] = nd;
+  }
+  return 0;
+}
+
 void skd_forest_free(skd_forest* f) { delete f; }
 
 int skd_predict_linear(skd_ctx* ctx, const float* Xnew, int64_t m, int64_t d, int64_t ld, int32_t B,

@@ -527,7 +527,7 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
   Scratch sx(c);
   float* W; SgdStateTc* state; int32_t *order, *active, *dpos, *ycls_p; double *eta, *dws; float *cfac, *xnorm, *xnorm_p;
   float* dcoef; double *dint, *dt; int32_t *dniter, *dstatus;
-  __half *Xp, *Wp; float2* wmeta[2]; float *S, *G; unsigned int* absmax; int2* gtiles; unsigned long long* counters;
+  __half *Xp, *Wp; float2* wmeta[2]; float *S, *G[2]; unsigned int* absmax; int2* gtiles; unsigned long long* counters;
   SKD_CUDA(c, sx.alloc(&W, (size_t)B * ldw));
   SKD_CUDA(c, sx.alloc(&state, (size_t)B));
   SKD_CUDA(c, sx.alloc(&order, (size_t)n));
@@ -549,7 +549,8 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
   SKD_CUDA(c, sx.alloc(&wmeta[0], (size_t)kpad));
   SKD_CUDA(c, sx.alloc(&wmeta[1], (size_t)kpad));
   SKD_CUDA(c, sx.alloc(&S, (size_t)kpad * ST_T));
-  SKD_CUDA(c, sx.alloc(&G, (size_t)ST_T * ST_T));
+  SKD_CUDA(c, sx.alloc(&G[0], (size_t)ST_T * ST_T));
+  SKD_CUDA(c, sx.alloc(&G[1], (size_t)ST_T * ST_T));
   SKD_CUDA(c, sx.alloc(&absmax, 1));
   SKD_CUDA(c, sx.alloc(&counters, 4));
   const int tiles_t = ST_T / ST_TILE;
@@ -581,6 +582,18 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
   const size_t gemm_smem = 1024 + (size_t)ST_STAGES * 2 * ST_TILE * 128 + sizeof(SgdGemmBars) + 64;
   SKD_CUDA(c, cudaFuncSetAttribute(sgd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
 
+  cudaStream_t sB;
+  cudaEvent_t ev_perm, ev_g[2], ev_scan[2];
+  SKD_CUDA(c, cudaStreamCreateWithFlags(&sB, cudaStreamNonBlocking));
+  SKD_CUDA(c, cudaEventCreateWithFlags(&ev_perm, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    SKD_CUDA(c, cudaEventCreateWithFlags(&ev_g[i], cudaEventDisableTiming));
+    SKD_CUDA(c, cudaEventCreateWithFlags(&ev_scan[i], cudaEventDisableTiming));
+  }
+  struct StreamGuard {
+    cudaStream_t s; cudaEvent_t* e[5];
+    ~StreamGuard() { cudaStreamSynchronize(s); for (auto p : e) cudaEventDestroy(*p); cudaStreamDestroy(s); }
+  } guard{sB, {&ev_perm, &ev_g[0], &ev_g[1], &ev_scan[0], &ev_scan[1]}};
   std::vector<int32_t> hact(B), hord(n);
   std::vector<float> hcfac(n);
   std::vector<double> hws(n + 1);
@@ -633,23 +646,41 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
                    SGD_TC_CASE(16, SGD_EXPORT) SGD_TC_CASE(32, SGD_EXPORT) default: return fail(c, "sgd: bad dpl"); }
     c->launches += 2;
     const int n_blocks = (int)((n + ST_T - 1) / ST_T);
+    // The Gram product of a block does not depend on the weights: it runs one block ahead on a second
+    // stream (two G buffers), so only S = X_T W^T sits between two scans.
+    SKD_CUDA(c, cudaEventRecord(ev_perm, c->stream));          // Xp of this epoch is complete
+    SKD_CUDA(c, cudaStreamWaitEvent(sB, ev_perm, 0));
+    auto launch_g = [&](int b) {
+      SgdGemmParams gg;
+      gg.S = S; gg.G = G[b & 1]; gg.row0 = b * ST_T; gg.n_colgroups = 1; gg.n_s = 0;
+      gg.n_g = (int)hg.size(); gg.gtiles = gtiles; gg.kchunks = dpad / 64;
+      sgd_gemm_kernel<<<gg.n_g, 192, gemm_smem, sB>>>(map_x, map_w, gg);
+      cudaEventRecord(ev_g[b & 1], sB);
+    };
+    launch_g(0);
     for (int b = 0; b < n_blocks; ++b) {
+      if (b + 1 < n_blocks) {
+        if (b >= 1) SKD_CUDA(c, cudaStreamWaitEvent(sB, ev_scan[(b + 1) & 1], 0));   // scan(b - 1) is done with that buffer
+        launch_g(b + 1);
+      }
       SgdGemmParams gp;
-      gp.S = S; gp.G = G; gp.row0 = b * ST_T; gp.n_colgroups = kgroups; gp.n_s = tiles_t * kgroups;
-      gp.n_g = (int)hg.size(); gp.gtiles = gtiles; gp.kchunks = dpad / 64;
-      sgd_gemm_kernel<<<gp.n_s + gp.n_g, 192, gemm_smem, c->stream>>>(map_x, map_w, gp);
+      gp.S = S; gp.G = G[b & 1]; gp.row0 = b * ST_T; gp.n_colgroups = kgroups; gp.n_s = tiles_t * kgroups;
+      gp.n_g = 0; gp.gtiles = gtiles; gp.kchunks = dpad / 64;
+      sgd_gemm_kernel<<<gp.n_s, 192, gemm_smem, c->stream>>>(map_x, map_w, gp);
+      SKD_CUDA(c, cudaStreamWaitEvent(c->stream, ev_g[b & 1], 0));
       SgdScanParams sp;
       sp.X = c->X; sp.ldx = ldx; sp.d = d; sp.dpad = dpad; sp.ycls = c->ycls; sp.order = order; sp.eta = eta; sp.cfac = cfac;
       sp.ws = dws; sp.ycls_p = ycls_p; sp.xnorm_p = xnorm_p; sp.n = n; sp.row0 = b * ST_T;
       sp.t_len = (int)std::min<int64_t>(ST_T, n - (int64_t)b * ST_T);
       sp.active = active; sp.n_active = n_active; sp.col_pos = dpos; sp.W = W; sp.ldw = ldw; sp.state = state;
-      sp.S = S; sp.G = G; sp.wmeta = wmeta[b & 1]; sp.Wp = Wp; sp.wmeta_out = wmeta[(b + 1) & 1];
+      sp.S = S; sp.G = G[b & 1]; sp.wmeta = wmeta[b & 1]; sp.Wp = Wp; sp.wmeta_out = wmeta[(b + 1) & 1];
       sp.inv_sx = inv_sx; sp.inv_sx2 = inv_sx2; sp.alpha = alpha; sp.fit_intercept = fit_intercept;
       sp.last_block = b == n_blocks - 1; sp.tol = tol; sp.n_iter_no_change = n_iter_no_change; sp.counters = counters;
 #define SGD_SCAN(D) sgd_scan_kernel<D><<<(n_active + 3) / 4, 128, 0, c->stream>>>(sp)
       switch (dpl) { SGD_TC_CASE(1, SGD_SCAN) SGD_TC_CASE(2, SGD_SCAN) SGD_TC_CASE(4, SGD_SCAN) SGD_TC_CASE(8, SGD_SCAN)
                      SGD_TC_CASE(16, SGD_SCAN) SGD_TC_CASE(32, SGD_SCAN) default: return fail(c, "sgd: bad dpl"); }
-      c->launches += 2;
+      SKD_CUDA(c, cudaEventRecord(ev_scan[b & 1], c->stream));
+      c->launches += 3;
     }
     SKD_CUDA(c, cudaGetLastError());
     SKD_CUDA(c, cudaMemcpyAsync(hs.data(), state, (size_t)B * sizeof(SgdStateTc), cudaMemcpyDeviceToHost, c->stream));

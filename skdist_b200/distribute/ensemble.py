@@ -53,6 +53,11 @@ def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, ma
     """A fitted DecisionTreeClassifier / ExtraTreeClassifier holding the device-built tree (same
     attributes as SK/tree/_classes.py:_fit leaves behind)."""
     m = arrays["left"].shape[0]
+    if "nodes" in arrays:       # the library filled scikit-learn's node records directly
+        t = Tree(n_features, np.array([n_classes], dtype=np.intp), 1)
+        t.__setstate__({"max_depth": int(arrays["max_depth"]), "node_count": m, "nodes": arrays["nodes"],
+                        "values": np.ascontiguousarray(arrays["value"].reshape(m, 1, n_classes))})
+        return _finish_tree(t, template_params, state, n_features, n_classes, max_features_, tree_cls)
     nodes = np.zeros(m, dtype=NODE_DTYPE)
     nodes["left_child"] = arrays["left"]
     nodes["right_child"] = arrays["right"]
@@ -65,6 +70,10 @@ def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, ma
     t = Tree(n_features, np.array([n_classes], dtype=np.intp), 1)
     t.__setstate__({"max_depth": int(arrays["max_depth"]), "node_count": m, "nodes": nodes,
                     "values": np.ascontiguousarray(arrays["value"].reshape(m, 1, n_classes))})
+    return _finish_tree(t, template_params, state, n_features, n_classes, max_features_, tree_cls)
+
+
+def _finish_tree(t, template_params, state, n_features, n_classes, max_features_, tree_cls):
     est = tree_cls(**template_params)
     est.set_params(random_state=int(state))
     est.n_features_in_ = n_features

@@ -362,10 +362,20 @@ class Engine:
         ks = ctypes.c_double(0.0)
         check(self._lib.skd_forest_kernel_seconds(self._h, ctypes.byref(ks)), self._h)
         self.last_forest_kernel_seconds = ks.value
+        from sklearn.tree._tree import NODE_DTYPE
+        node_records = (NODE_DTYPE.itemsize == 64 and
+                        [NODE_DTYPE.fields[k][1] for k in NODE_DTYPE.names] == [0, 8, 16, 24, 32, 40, 48, 56])
+
         def fetch(t):
             m, md = ctypes.c_int32(), ctypes.c_int32()
             check(self._lib.skd_forest_tree_size(h, t, ctypes.byref(m), ctypes.byref(md)))
             m = m.value
+            if node_records:      # scikit-learn's node struct filled by the library: no per-field passes in Python
+                nodes = np.empty(m, dtype=NODE_DTYPE)
+                value = np.empty((m, n_classes), np.float64)
+                check(self._lib.skd_forest_tree_nodes(h, t, ptr(nodes), ptr(value)))
+                return {"nodes": nodes, "value": value, "max_depth": md.value, "left": nodes["left_child"],
+                        "n_node_samples": nodes["n_node_samples"]}
             a = {"left": np.empty(m, np.int32), "right": np.empty(m, np.int32), "feature": np.empty(m, np.int32),
                  "threshold": np.empty(m, np.float64), "impurity": np.empty(m, np.float64),
                  "n_node_samples": np.empty(m, np.int32), "weighted_n_node_samples": np.empty(m, np.float64),
