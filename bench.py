@@ -192,7 +192,13 @@ def parity_block(cv_results, tasks, cpu_scores, fold, Cs, n_folds):
                    best_C_cpu_on_subgrid=float(Cs[full[int(np.argmax(cpu_mean))]]),
                    best_C_gpu_on_subgrid=float(Cs[full[int(np.argmax(gpu_mean))]]),
                    best_C_equal_on_subgrid=bool(int(np.argmax(cpu_mean)) == int(np.argmax(gpu_mean))),
-                   cpu_best_margin=float(np.sort(cpu_mean)[-1] - np.sort(cpu_mean)[-2]) if len(full) > 1 else None)
+                   cpu_best_margin=float(np.sort(cpu_mean)[-1] - np.sort(cpu_mean)[-2]) if len(full) > 1 else None,
+                   # how much worse, by the CPU leg's own scores, the device's choice is than the CPU's: a value
+                   # below the CPU-vs-device differences above means the two picked from a tie
+                   cpu_score_of_device_choice_minus_cpu_best=float(cpu_mean[int(np.argmax(gpu_mean))] - cpu_mean.max()),
+                   best_C_tied=bool(cpu_mean.max() - cpu_mean[int(np.argmax(gpu_mean))]
+                                    <= max(2e-5, float(np.max(np.abs(cpu_mean - gpu_mean))))),
+                   cpu_mean_test_score=[float(v) for v in cpu_mean], device_mean_test_score=[float(v) for v in gpu_mean])
     return out
 
 
