@@ -1,5 +1,5 @@
 // forest_fast.cu -- the throughput build of the exact depth-first tree builder (classification,
-// best splitter): every tree of a forest resident at once, seven 128-thread builders per SM.
+// best splitter): every tree of a forest resident at once, seven 64-thread builders per SM.
 //
 // Same contract as forest.cu (which stays the general kernel: regression, random splitter, many
 // classes): the host draws what the reference's per-tree task `_build_trees` draws
@@ -14,7 +14,7 @@
 // 184k internal nodes hold <= 32 samples and 58k more hold <= 256; the 1000 nodes above 4096
 // samples carry half of all sample visits but none of the time.  The RNG stream makes the nodes of
 // one tree strictly sequential, so throughput = (trees in flight) / (latency per node):
-//   * 7 builders per SM (128 threads, <= 72 registers, 28 KB shared memory): all 1024 trees of the
+//   * 7 builders per SM (64 threads, up to 128 registers, 28 KB shared memory): all 1024 trees of the
 //     headline forest run concurrently (the general kernel holds 2 per SM);
 //   * a subtree of <= S samples (S = 256 at d = 64) is STAGED: the bin codes of its rows (row-major
 //     copy of the binned matrix, 64 B per row) are copied to shared memory once, and the whole
@@ -40,10 +40,14 @@
 
 namespace skd {
 
-constexpr int FF_THREADS = 96;       // 7 builders x 96 threads per SM: up to 97 registers per thread, no spills
+// 7 builders x 64 threads per SM.  The register file is split over the four SM sub-partitions (16384
+// registers each): 14 warps per SM are at most 4 per sub-partition, i.e. up to 128 registers per thread
+// without spilling (96-thread builders are limited to 80 for seven per SM and spilled; 6 per SM means
+// two waves for 1024 trees).
+constexpr int FF_THREADS = 64;
 constexpr int FF_WARPS = FF_THREADS / 32;
 constexpr int FF_KB = 8;          // speculative feature draws per batch (unstaged nodes, small staged nodes)
-constexpr int FF_KBM = FF_WARPS;  // ... for staged histogram nodes: one feature per warp
+constexpr int FF_KBM = 4;         // ... for staged histogram nodes (packed histograms of four features fit next to the rows)
 constexpr int FF_SMAX = 256;      // staged rows at most (local ids are bytes, packed 16-bit sums must hold 256 x 255)
 constexpr int FF_SSTK = 64;       // builder-stack entries kept in shared memory
 constexpr int FF_SMALL = 32;      // staged nodes up to this size take the ranking path
@@ -458,20 +462,21 @@ forest_fast_kernel(const FfParams P) {
           int fk[FF_KB];
 #pragma unroll
           for (int k = 0; k < FF_KB; ++k) fk[k] = items[k < nbatch ? k : 0].f;
-          for (int i0 = start; i0 < end; i0 += 4 * FF_THREADS) {
-            uint2 sv[4];
+          constexpr int GQ = 6;                        // samples per thread in flight
+          for (int i0 = start; i0 < end; i0 += GQ * FF_THREADS) {
+            uint2 sv[GQ];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < GQ; ++q) {
               const int i = i0 + q * FF_THREADS + tid;
               sv[q] = i < end ? __ldcg(src + i) : make_uint2(0xFFFFFFFFu, 0u);
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < GQ; ++q) {
               if (sv[q].x == 0xFFFFFFFFu) continue;
               const uint8_t* rq = P.xrow + (size_t)sv[q].x * dp;
               unsigned bq[FF_KB];
 #pragma unroll
-              for (int k = 0; k < FF_KB; ++k) bq[k] = (unsigned)__ldcg(rq + fk[k]);
+              for (int k = 0; k < FF_KB; ++k) bq[k] = (unsigned)__ldg(rq + fk[k]);      // the drawn features of a row share two sectors: L1 serves 7 of the 8 loads
               const unsigned cq = sv[q].y & 0xFF, wq = sv[q].y >> 8;
 #pragma unroll
               for (int k = 0; k < FF_KB; ++k) {
@@ -493,11 +498,11 @@ forest_fast_kernel(const FfParams P) {
           }
         } else if (!small) {
           // ---- staged histogram node: warp k builds and scans the packed histogram of item k ----
-          if (wid < nbatch) {
-            unsigned int* H = histB + wid * hbw;
+          for (int k = wid; k < nbatch; k += FF_WARPS) {
+            unsigned int* H = histB + k * hbw;
             for (int i = lane; i < hbw; i += 32) H[i] = 0;
             __syncwarp();
-            const int f = items[wid].f;
+            const int f = items[k].f;
             for (int i = lane; i < n_node; i += 32) {
               const int lid = ord[ls + i];
               const unsigned b = rowsB[lid * ws4 + f];
@@ -509,7 +514,7 @@ forest_fast_kernel(const FfParams P) {
             __syncwarp();
             ff_scan<CM>([&](int c, int b) -> uint32_t { return (H[(c >> 1) * 256 + b] >> ((c & 1) * 16)) & 0xFFFFu; },
                         [&](int b) -> unsigned { return (H[hcw + (b >> 1)] >> ((b & 1) * 16)) & 0xFFFFu; },
-                        lane, C, n_node, rec->sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[wid]);
+                        lane, C, n_node, rec->sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[k]);
           }
         } else {
           // ---- staged node of <= 32 samples: lane j holds sample j; every lane counts the samples

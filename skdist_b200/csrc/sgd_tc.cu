@@ -296,13 +296,16 @@ sgd_scan_kernel(const SgdScanParams P) {
 
   // per-sample inputs of the window [i0, i0 + 32): coalesced loads in walk order, requested one
   // window ahead (the window normally advances by 32; after an event it is re-read)
-  struct Win { double e, ws; float c, nx, s; int yc; };
+  struct Win { double e, ws; float c, nx, s, corr; int yc, nv; };
   auto load_win = [&](int i0w) -> Win {
-    Win wv; wv.e = 0.0; wv.ws = 1.0; wv.c = 1.f; wv.nx = 0.f; wv.s = 0.f; wv.yc = -1;
+    Win wv; wv.e = 0.0; wv.ws = 1.0; wv.c = 1.f; wv.nx = 0.f; wv.s = 0.f; wv.corr = 0.f; wv.yc = -1; wv.nv = nviol;
     if (i0w + lane < P.t_len) {
       const int64_t gi = (int64_t)P.row0 + i0w + lane;
       wv.e = P.eta[gi]; wv.ws = P.ws[gi]; wv.c = P.cfac[gi]; wv.nx = P.xnorm_p[gi]; wv.yc = P.ycls_p[gi];
       wv.s = Srow[i0w + lane];
+      // margin corrections of the updates logged so far (updates logged while this window is in
+      // flight are added when it is consumed)
+      for (int v = 0; v < nviol; ++v) wv.corr = fmaf(vq[v], P.G[(size_t)vj[v] * ST_T + i0w + lane], wv.corr);
     }
     return wv;
   };
@@ -317,9 +320,9 @@ sgd_scan_kernel(const SgdScanParams P) {
     nxt = load_win(nxt_i0);                       // in flight while this window is processed
     const double y_l = (cw.yc == pos) ? 1.0 : -1.0, e_l = cw.e, ws_l = cw.ws;
     const float c_l = cw.c, nx_l = cw.nx;
-    float s_l = cw.s * inv_scale;
+    float s_l = fmaf(cw.s, inv_scale, cw.corr);
     if (lane < Te)
-      for (int v = 0; v < nviol; ++v) s_l = fmaf(vq[v], P.G[(size_t)vj[v] * ST_T + i0 + lane], s_l);
+      for (int v = cw.nv; v < nviol; ++v) s_l = fmaf(vq[v], P.G[(size_t)vj[v] * ST_T + i0 + lane], s_l);
     // A. the norm recurrence sq_norm *= c_t^2 in sample order (lane t keeps the value BEFORE sample t)
     double my_sq = sq_norm, my_sq_after = sq_norm;
     {
@@ -583,7 +586,9 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
   SKD_CUDA(c, cudaFuncSetAttribute(sgd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
 
   cudaStream_t sB;
-  cudaEvent_t ev_perm, ev_g[2], ev_scan[2];
+  cudaEvent_t ev_perm, ev_g[2], ev_scan[2], ev_t[3];
+  double t_gemm = 0.0, t_scan = 0.0; int t_cnt = 0;
+  for (int i = 0; i < 3; ++i) SKD_CUDA(c, cudaEventCreate(&ev_t[i]));
   SKD_CUDA(c, cudaStreamCreateWithFlags(&sB, cudaStreamNonBlocking));
   SKD_CUDA(c, cudaEventCreateWithFlags(&ev_perm, cudaEventDisableTiming));
   for (int i = 0; i < 2; ++i) {
@@ -666,7 +671,10 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
       SgdGemmParams gp;
       gp.S = S; gp.G = G[b & 1]; gp.row0 = b * ST_T; gp.n_colgroups = kgroups; gp.n_s = tiles_t * kgroups;
       gp.n_g = 0; gp.gtiles = gtiles; gp.kchunks = dpad / 64;
+      const bool tb = trace && (epoch == 1 || epoch == 20) && b >= 8 && b < 24;    // kernel split of 16 blocks
+      if (tb) cudaEventRecord(ev_t[0], c->stream);
       sgd_gemm_kernel<<<gp.n_s, 192, gemm_smem, c->stream>>>(map_x, map_w, gp);
+      if (tb) cudaEventRecord(ev_t[1], c->stream);
       SKD_CUDA(c, cudaStreamWaitEvent(c->stream, ev_g[b & 1], 0));
       SgdScanParams sp;
       sp.X = c->X; sp.ldx = ldx; sp.d = d; sp.dpad = dpad; sp.ycls = c->ycls; sp.order = order; sp.eta = eta; sp.cfac = cfac;
@@ -680,6 +688,14 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
       switch (dpl) { SGD_TC_CASE(1, SGD_SCAN) SGD_TC_CASE(2, SGD_SCAN) SGD_TC_CASE(4, SGD_SCAN) SGD_TC_CASE(8, SGD_SCAN)
                      SGD_TC_CASE(16, SGD_SCAN) SGD_TC_CASE(32, SGD_SCAN) default: return fail(c, "sgd: bad dpl"); }
       SKD_CUDA(c, cudaEventRecord(ev_scan[b & 1], c->stream));
+      if (tb) {
+        cudaEventRecord(ev_t[2], c->stream);
+        cudaEventSynchronize(ev_t[2]);
+        float m1 = 0.f, m2 = 0.f;
+        cudaEventElapsedTime(&m1, ev_t[0], ev_t[1]);
+        cudaEventElapsedTime(&m2, ev_t[1], ev_t[2]);
+        t_gemm += m1; t_scan += m2; t_cnt += 1;
+      }
       c->launches += 3;
     }
     SKD_CUDA(c, cudaGetLastError());
@@ -691,6 +707,11 @@ int sgd_fit_batch_tc(Ctx* c, int B, const int32_t* col_pos, double alpha, int fi
       auto tw2 = std::chrono::steady_clock::now();
       fprintf(stderr, "[skd trace] sgd-tc epoch %3d active %5d  %8.2f ms\n", epoch, n_active,
               std::chrono::duration<double, std::milli>(tw2 - tw0).count());
+      if (t_cnt > 0) {
+        fprintf(stderr, "[skd trace] sgd-tc epoch %3d per block (16 blocks, synchronised): S product %.1f us, wait for G + scan %.1f us\n",
+                epoch, 1e3 * t_gemm / t_cnt, 1e3 * t_scan / t_cnt);
+        t_gemm = t_scan = 0.0; t_cnt = 0;
+      }
     }
     n_active = 0;
     for (int j = 0; j < B; ++j)
