@@ -116,9 +116,19 @@ __device__ __forceinline__ double ff_proxy(const uint32_t* sl, const uint32_t* s
 template <int CM, class HC, class HN>
 __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_node, const uint32_t* st, double w_node,
                                         int min_samples_leaf, double min_weight_leaf, FfResult<CM>* R) {
+  // the lane's eight bins are read once into registers (fully unrolled loops index them statically):
+  // the candidate loops below then run without shared-memory latency in their dependency chains
+  unsigned cn[8];
+  uint32_t cwt[CM][8];
   unsigned ltot = 0, pmask = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { const unsigned cj = hn(lane * 8 + j); ltot += cj; if (cj) pmask |= 1u << j; }
+  for (int j = 0; j < 8; ++j) {
+    cn[j] = hn(lane * 8 + j);
+#pragma unroll
+    for (int c = 0; c < CM; ++c) cwt[c][j] = c < C ? hc(c, lane * 8 + j) : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ltot += cn[j]; if (cn[j]) pmask |= 1u << j; }
   unsigned pre = ltot;   // exclusive prefix of the sample counts over lanes
   for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
   pre -= ltot;
@@ -129,7 +139,7 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
     if (c < C) {
       uint32_t t = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) t += hc(c, lane * 8 + j);
+      for (int j = 0; j < 8; ++j) t += cwt[c][j];
       uint32_t incl = t;
       for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
       sl[c] = incl - t;
@@ -149,26 +159,25 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
   // ranked first by p = sq_l / w_l + sq_r / w_r in float32 (proxy = p - w_node in exact arithmetic;
   // the float32 value is within 2^-20 * w_node of it), and the float64 expression is evaluated only
   // for the candidates within 2^-19 * w_node of the best float32 value -- the others cannot win.
+  float pj[8];           // float32 rank value of the candidate above bin j (-inf: no candidate)
   float pbest = -INFINITY;
-  if (!is_const) {
+  {
     unsigned run_cnt = pre;
-    unsigned pm = pmask;
     uint32_t s2[CM];
 #pragma unroll
     for (int c = 0; c < CM; ++c) s2[c] = sl[c];
-    while (pm) {
-      const int j = __ffs(pm) - 1;
-      pm &= pm - 1;
-      const int bb = lane * 8 + j;
-      run_cnt += hn(bb);
 #pragma unroll
-      for (int c = 0; c < CM; ++c) if (c < C) s2[c] += hc(c, bb);
-      if (!pm && nxt >= (1 << 20)) continue;
+    for (int j = 0; j < 8; ++j) {
+      pj[j] = -INFINITY;
+      run_cnt += cn[j];
+#pragma unroll
+      for (int c = 0; c < CM; ++c) s2[c] += cwt[c][j];
+      const bool last = !(pmask >> (j + 1)) && nxt >= (1 << 20);      // no present bin above: no boundary
       const int n_left = (int)run_cnt, n_right = n_node - n_left;
-      if (n_left < min_samples_leaf || n_right < min_samples_leaf) continue;
+      if (is_const || !cn[j] || last || n_left < min_samples_leaf || n_right < min_samples_leaf) continue;
       float wl = 0.f, sql = 0.f, sqr = 0.f;
 #pragma unroll
-      for (int c = 0; c < CM; ++c) if (c < C) { const float a = (float)s2[c], b = (float)(st[c] - s2[c]); wl += a; sql = fmaf(a, a, sql); sqr = fmaf(b, b, sqr); }
+      for (int c = 0; c < CM; ++c) if (c < C) { const float a = (float)s2[c], b2 = (float)(st[c] - s2[c]); wl += a; sql = fmaf(a, a, sql); sqr = fmaf(b2, b2, sqr); }
       const float wr = (float)w_node - wl;
       if (min_weight_leaf > 0.0) {       // the validity tests are the exact ones: an invalid candidate must not set the bar
         double wld = 0.0;
@@ -176,7 +185,8 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
         for (int c = 0; c < CM; ++c) if (c < C) wld += (double)s2[c];
         if (wld < min_weight_leaf || w_node - wld < min_weight_leaf) continue;
       }
-      pbest = fmaxf(pbest, __fdividef(sql, wl) + __fdividef(sqr, wr));
+      pj[j] = __fdividef(sql, wl) + __fdividef(sqr, wr);
+      pbest = fmaxf(pbest, pj[j]);
     }
   }
   float pthr = pbest;
@@ -187,35 +197,23 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
   uint32_t bsl[CM];
 #pragma unroll
   for (int c = 0; c < CM; ++c) bsl[c] = 0;
-  if (!is_const && pbest >= pthr) {
+  if (pbest >= pthr && pbest > -INFINITY) {
     unsigned run_cnt = pre;
-    unsigned pm = pmask;
-    while (pm) {                               // this lane's present bins in ascending order
-      const int j = __ffs(pm) - 1;
-      pm &= pm - 1;
-      const int bb = lane * 8 + j;
-      run_cnt += hn(bb);
 #pragma unroll
-      for (int c = 0; c < CM; ++c) if (c < C) sl[c] += hc(c, bb);
-      const int nb2 = pm ? lane * 8 + __ffs(pm) - 1 : nxt;
-      if (nb2 >= (1 << 20)) continue;                             // last present bin: no boundary above it
-      const int n_left = (int)run_cnt, n_right = n_node - n_left;
-      if (n_left < min_samples_leaf || n_right < min_samples_leaf) continue;
-      {
-        float wlf = 0.f, sqlf = 0.f, sqrf = 0.f;
+    for (int j = 0; j < 8; ++j) {               // this lane's bins in ascending order
+      run_cnt += cn[j];
 #pragma unroll
-        for (int c = 0; c < CM; ++c) if (c < C) { const float a = (float)sl[c], b = (float)(st[c] - sl[c]); wlf += a; sqlf = fmaf(a, a, sqlf); sqrf = fmaf(b, b, sqrf); }
-        const float wrf = (float)w_node - wlf;
-        if (!(__fdividef(sqlf, wlf) + __fdividef(sqrf, wrf) >= pthr)) continue;     // cannot be the best
-      }
+      for (int c = 0; c < CM; ++c) sl[c] += cwt[c][j];
+      if (!(pj[j] >= pthr)) continue;           // not a candidate, or cannot be the best
+      const unsigned higher = pmask >> (j + 1);
+      const int nb2 = higher ? lane * 8 + j + __ffs(higher) : nxt;
       double wl = 0.0;
 #pragma unroll
       for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
       const double wr = w_node - wl;
-      if (wl < min_weight_leaf || wr < min_weight_leaf) continue;
       const double proxy = ff_proxy<CM>(sl, st, C, wl, wr, nullptr, nullptr);
       if (proxy > bproxy) {
-        bproxy = proxy; bnl = n_left; bcode = bb | (nb2 << 8);
+        bproxy = proxy; bnl = (int)run_cnt; bcode = (lane * 8 + j) | (nb2 << 8);
 #pragma unroll
         for (int c = 0; c < CM; ++c) bsl[c] = sl[c];
       }
@@ -462,7 +460,7 @@ forest_fast_kernel(const FfParams P) {
           int fk[FF_KB];
 #pragma unroll
           for (int k = 0; k < FF_KB; ++k) fk[k] = items[k < nbatch ? k : 0].f;
-          constexpr int GQ = 6;                        // samples per thread in flight
+          constexpr int GQ = 4;                        // samples per thread in flight
           for (int i0 = start; i0 < end; i0 += GQ * FF_THREADS) {
             uint2 sv[GQ];
 #pragma unroll
@@ -470,20 +468,25 @@ forest_fast_kernel(const FfParams P) {
               const int i = i0 + q * FF_THREADS + tid;
               sv[q] = i < end ? __ldcg(src + i) : make_uint2(0xFFFFFFFFu, 0u);
             }
+            // every code of the round is requested before the first histogram update (a warp issues in
+            // order: an atomic that needs a loaded code would hold back the loads behind it)
+            unsigned bq[GQ][FF_KB];
+#pragma unroll
+            for (int q = 0; q < GQ; ++q) {
+              const uint8_t* rq = P.xrow + (size_t)(sv[q].x != 0xFFFFFFFFu ? sv[q].x : 0u) * dp;
+#pragma unroll
+              for (int k = 0; k < FF_KB; ++k) bq[q][k] = (unsigned)__ldg(rq + fk[k]);   // the drawn features of a row share two sectors
+            }
 #pragma unroll
             for (int q = 0; q < GQ; ++q) {
               if (sv[q].x == 0xFFFFFFFFu) continue;
-              const uint8_t* rq = P.xrow + (size_t)sv[q].x * dp;
-              unsigned bq[FF_KB];
-#pragma unroll
-              for (int k = 0; k < FF_KB; ++k) bq[k] = (unsigned)__ldg(rq + fk[k]);      // the drawn features of a row share two sectors: L1 serves 7 of the 8 loads
               const unsigned cq = sv[q].y & 0xFF, wq = sv[q].y >> 8;
 #pragma unroll
               for (int k = 0; k < FF_KB; ++k) {
                 if (k < nbatch) {
                   unsigned int* H = U + k * hstrideA;
-                  atomicAdd(&H[cq * 256 + bq[k]], wq);
-                  atomicAdd(&H[C * 256 + bq[k]], 1u);
+                  atomicAdd(&H[cq * 256 + bq[q][k]], wq);
+                  atomicAdd(&H[C * 256 + bq[q][k]], 1u);
                 }
               }
             }
@@ -503,13 +506,23 @@ forest_fast_kernel(const FfParams P) {
             for (int i = lane; i < hbw; i += 32) H[i] = 0;
             __syncwarp();
             const int f = items[k].f;
-            for (int i = lane; i < n_node; i += 32) {
-              const int lid = ord[ls + i];
-              const unsigned b = rowsB[lid * ws4 + f];
-              const unsigned wc = wcls[lid];
-              const unsigned cls = wc & 0xFF, w = wc >> 8;
-              atomicAdd(&H[(cls >> 1) * 256 + b], w << ((cls & 1) * 16));
-              atomicAdd(&H[hcw + (b >> 1)], 1u << ((b & 1) * 16));
+            for (int i0 = 0; i0 < n_node; i0 += 4 * 32) {        // four samples per lane and round, loads first
+              int lid4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { const int i = i0 + q * 32 + lane; lid4[q] = i < n_node ? (int)ord[ls + i] : -1; }
+              unsigned b4[4], wc4[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                b4[q] = lid4[q] >= 0 ? (unsigned)rowsB[lid4[q] * ws4 + f] : 0u;
+                wc4[q] = lid4[q] >= 0 ? (unsigned)wcls[lid4[q]] : 0u;
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (lid4[q] < 0) continue;
+                const unsigned cls = wc4[q] & 0xFF, w = wc4[q] >> 8;
+                atomicAdd(&H[(cls >> 1) * 256 + b4[q]], w << ((cls & 1) * 16));
+                atomicAdd(&H[hcw + (b4[q] >> 1)], 1u << ((b4[q] & 1) * 16));
+              }
             }
             __syncwarp();
             ff_scan<CM>([&](int c, int b) -> uint32_t { return (H[(c >> 1) * 256 + b] >> ((c & 1) * 16)) & 0xFFFFu; },

@@ -296,16 +296,22 @@ sgd_scan_kernel(const SgdScanParams P) {
 
   // per-sample inputs of the window [i0, i0 + 32): coalesced loads in walk order, requested one
   // window ahead (the window normally advances by 32; after an event it is re-read)
-  struct Win { double e, ws; float c, nx, s, corr; int yc, nv; };
+  // (only loads here: an instruction that consumes a loaded value would stall the warp for the memory
+  // latency and the window would no longer be fetched in the shadow of the previous one)
+  constexpr int PV = 4;              // Gram entries of the first PV logged updates travel with the window
+  struct Win { double e, ws; float c, nx, s, g[PV]; int yc, nv; };
   auto load_win = [&](int i0w) -> Win {
-    Win wv; wv.e = 0.0; wv.ws = 1.0; wv.c = 1.f; wv.nx = 0.f; wv.s = 0.f; wv.corr = 0.f; wv.yc = -1; wv.nv = nviol;
+    Win wv; wv.e = 0.0; wv.ws = 1.0; wv.c = 1.f; wv.nx = 0.f; wv.s = 0.f; wv.yc = -1;
+    wv.nv = nviol < PV ? nviol : PV;
+#pragma unroll
+    for (int v = 0; v < PV; ++v) wv.g[v] = 0.f;
     if (i0w + lane < P.t_len) {
       const int64_t gi = (int64_t)P.row0 + i0w + lane;
       wv.e = P.eta[gi]; wv.ws = P.ws[gi]; wv.c = P.cfac[gi]; wv.nx = P.xnorm_p[gi]; wv.yc = P.ycls_p[gi];
       wv.s = Srow[i0w + lane];
-      // margin corrections of the updates logged so far (updates logged while this window is in
-      // flight are added when it is consumed)
-      for (int v = 0; v < nviol; ++v) wv.corr = fmaf(vq[v], P.G[(size_t)vj[v] * ST_T + i0w + lane], wv.corr);
+#pragma unroll
+      for (int v = 0; v < PV; ++v)
+        if (v < nviol) wv.g[v] = P.G[(size_t)vj[v] * ST_T + i0w + lane];
     }
     return wv;
   };
@@ -320,8 +326,10 @@ sgd_scan_kernel(const SgdScanParams P) {
     nxt = load_win(nxt_i0);                       // in flight while this window is processed
     const double y_l = (cw.yc == pos) ? 1.0 : -1.0, e_l = cw.e, ws_l = cw.ws;
     const float c_l = cw.c, nx_l = cw.nx;
-    float s_l = fmaf(cw.s, inv_scale, cw.corr);
-    if (lane < Te)
+    float s_l = cw.s * inv_scale;
+#pragma unroll
+    for (int v = 0; v < PV; ++v) if (v < cw.nv) s_l = fmaf(vq[v], cw.g[v], s_l);
+    if (lane < Te)      // updates logged after the window was requested / beyond the first PV
       for (int v = cw.nv; v < nviol; ++v) s_l = fmaf(vq[v], P.G[(size_t)vj[v] * ST_T + i0 + lane], s_l);
     // A. the norm recurrence sq_norm *= c_t^2 in sample order (lane t keeps the value BEFORE sample t)
     double my_sq = sq_norm, my_sq_after = sq_norm;
