@@ -50,6 +50,20 @@ try:
     raise SystemExit("NaN input was accepted")
 except ValueError:
     pass
+# round 2: overlapping test sets (several fold-id layouts), multilabel one-vs-rest (row bit matrices), both
+# over ranks; X staged in slices + in-place all-gather
+from sklearn.model_selection import ShuffleSplit
+from skdist_b200.datasets import make_g1_classification
+Xc, yc = make_g1_classification(6000, 20, seed=8)
+cvs = ShuffleSplit(n_splits=3, test_size=0.25, random_state=1)
+gsh = DistGridSearchCV(LogisticRegression(), {"C": [0.01, 0.1]}, None, cv=cvs).fit(Xc, yc)
+gsk = GridSearchCV(LogisticRegression(), {"C": [0.01, 0.1]}, cv=cvs).fit(Xc, yc)
+np.testing.assert_allclose(gsh.cv_results_["mean_test_score"], gsk.cv_results_["mean_test_score"], atol=2.01 / 1500)
+Yml = np.stack([Xc[:, 0] > 0.3, Xc[:, 1] + Xc[:, 2] > 0.1, yc == 1], axis=1).astype(int)
+ml = DistOneVsRestClassifier(LogisticRegression(C=0.05), None).fit(Xc, Yml)
+for k, e in enumerate(ml.estimators_):
+    r = LogisticRegression(C=0.05).fit(Xc, Yml[:, k])
+    assert np.mean(e.predict(Xc) == r.predict(Xc)) > 0.998, "multilabel ovr"
 gathered = [None] * world
 dist.all_gather_object(gathered, float(rs.cv_results_["mean_test_score"].sum()))
 assert len(set(gathered)) == 1, "ranks disagree"
