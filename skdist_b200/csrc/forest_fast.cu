@@ -68,7 +68,9 @@ struct FfItem {                   // one speculatively drawn feature + the simul
 };
 template <int CM>
 struct __align__(8) FfResult {    // best split of one feature in the current node
-  double proxy;
+  double proxy;                   // scikit-learn's float64 proxy of the split -- valid only if `exact`
+  float ptil;                     // its float32 rank value sq_l / w_l + sq_r / w_r (-inf: no valid split)
+  int exact;
   int n_left;
   int code;                       // bin_a | bin_b << 8 | is_const << 16
   uint32_t sl[CM];
@@ -192,12 +194,20 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
   float pthr = pbest;
   for (int o = 16; o > 0; o >>= 1) pthr = fmaxf(pthr, __shfl_xor_sync(0xffffffffu, pthr, o));
   pthr -= (float)w_node * 1.9073486328125e-6f;      // 2^-19 * w_node
+  // how many candidates are within the bar?  Exactly one (the usual case): it is the feature's best
+  // split and no float64 evaluation is needed here (the commit step compares features the same way).
+  int nnear = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) nnear += (pbest > -INFINITY && pj[j] >= pthr) ? 1 : 0;
+  const int total_near = (int)__reduce_add_sync(0xffffffffu, (unsigned)nnear);
+  const bool single = total_near == 1;
   double bproxy = -INFINITY;
+  float bpt = -INFINITY;
   int bnl = 1 << 30, bcode = 0;
   uint32_t bsl[CM];
 #pragma unroll
   for (int c = 0; c < CM; ++c) bsl[c] = 0;
-  if (pbest >= pthr && pbest > -INFINITY) {
+  if (nnear > 0) {
     unsigned run_cnt = pre;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {               // this lane's bins in ascending order
@@ -207,29 +217,37 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
       if (!(pj[j] >= pthr)) continue;           // not a candidate, or cannot be the best
       const unsigned higher = pmask >> (j + 1);
       const int nb2 = higher ? lane * 8 + j + __ffs(higher) : nxt;
-      double wl = 0.0;
+      double proxy = 0.0;
+      if (!single) {
+        double wl = 0.0;
 #pragma unroll
-      for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
-      const double wr = w_node - wl;
-      const double proxy = ff_proxy<CM>(sl, st, C, wl, wr, nullptr, nullptr);
-      if (proxy > bproxy) {
-        bproxy = proxy; bnl = (int)run_cnt; bcode = (lane * 8 + j) | (nb2 << 8);
+        for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
+        proxy = ff_proxy<CM>(sl, st, C, wl, w_node - wl, nullptr, nullptr);
+      }
+      if (single || proxy > bproxy) {
+        bproxy = proxy; bpt = pj[j]; bnl = (int)run_cnt; bcode = (lane * 8 + j) | (nb2 << 8);
 #pragma unroll
         for (int c = 0; c < CM; ++c) bsl[c] = sl[c];
       }
     }
   }
-  // warp arg-max; ties keep the smallest position (the sequential scan's strict '>')
-  double wp = bproxy; int wnl = bnl;
-  for (int o = 16; o > 0; o >>= 1) {
-    const double op = __shfl_xor_sync(0xffffffffu, wp, o);
-    const int onl = __shfl_xor_sync(0xffffffffu, wnl, o);
-    if (op > wp || (op == wp && onl < wnl)) { wp = op; wnl = onl; }
+  if (total_near == 0) {
+    if (lane == 0) { R->proxy = -INFINITY; R->ptil = -INFINITY; R->exact = 1; R->n_left = 1 << 30; R->code = is_const ? (1 << 16) : 0; }
+    return;
   }
-  if (lane == 0) { R->proxy = wp; R->n_left = wnl; R->code = is_const ? (1 << 16) : 0; }
-  __syncwarp();
-  if (bnl == wnl && bproxy == wp && wp > -INFINITY) {   // exactly one lane: positions are unique per bin
-    R->code = bcode;
+  bool writer = single && nnear > 0;
+  if (!single) {
+    // warp arg-max; ties keep the smallest position (the sequential scan's strict '>')
+    double wp = bproxy; int wnl = bnl;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double op = __shfl_xor_sync(0xffffffffu, wp, o);
+      const int onl = __shfl_xor_sync(0xffffffffu, wnl, o);
+      if (op > wp || (op == wp && onl < wnl)) { wp = op; wnl = onl; }
+    }
+    writer = bnl == wnl && bproxy == wp && wp > -INFINITY;   // exactly one lane: positions are unique per bin
+  }
+  if (writer) {
+    R->proxy = bproxy; R->ptil = bpt; R->exact = single ? 0 : 1; R->n_left = bnl; R->code = bcode;
 #pragma unroll
     for (int c = 0; c < CM; ++c) R->sl[c] = bsl[c];
   }
@@ -413,6 +431,8 @@ forest_fast_kernel(const FfParams P) {
       // ------------------------------- node_split_best -------------------------------------
       int f_i = d, n_visited = 0, n_found = 0, n_drawn = 0;
       double best_proxy = -INFINITY;
+      float best_ptil = -INFINITY;
+      bool best_exact = false;
       // Features are drawn from one RNG stream and a draw depends on whether earlier draws of this
       // node turned out constant, so the reference evaluates them one by one.  Thread 0 SPECULATES
       // that none of the next <= KB evaluated features is constant, simulates the draws (logging
@@ -551,36 +571,61 @@ forest_fast_kernel(const FfParams P) {
             }
             const bool cand = have && nbn != 0xFFFFu;
             const bool is_const = __ballot_sync(0xffffffffu, cand) == 0u;
-            double proxy = -INFINITY;
-            int n_left = 1 << 30;
             uint32_t sl[CM];
 #pragma unroll
             for (int c = 0; c < CM; ++c) sl[c] = (uint32_t)((acc >> (13 * c)) & 0x1FFFu);
-            if (cand) {
-              const int nl = (int)(acc >> CNT), nr = n_node - nl;
-              if (nl >= P.min_samples_leaf && nr >= P.min_samples_leaf) {
+            // float32 rank value of this lane's candidate (see ff_scan): the float64 proxy is formed only
+            // when two different candidates are within the bar of each other
+            float pt = -INFINITY;
+            const int n_left = (int)(acc >> CNT);
+            if (cand && n_left >= P.min_samples_leaf && n_node - n_left >= P.min_samples_leaf) {
+              bool ok = true;
+              if (P.min_weight_leaf > 0.0) {
+                double wld = 0.0;
+#pragma unroll
+                for (int c = 0; c < CM; ++c) if (c < C) wld += (double)sl[c];
+                ok = !(wld < P.min_weight_leaf || w_node - wld < P.min_weight_leaf);
+              }
+              if (ok) {
+                float wl = 0.f, sql = 0.f, sqr = 0.f;
+#pragma unroll
+                for (int c = 0; c < CM; ++c) if (c < C) { const float a = (float)sl[c], b2 = (float)(rec->sums[c] - sl[c]); wl += a; sql = fmaf(a, a, sql); sqr = fmaf(b2, b2, sqr); }
+                pt = __fdividef(sql, wl) + __fdividef(sqr, (float)w_node - wl);
+              }
+            }
+            float pm = pt;
+            for (int o = 16; o > 0; o >>= 1) pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+            const bool near = pt > -INFINITY && pt >= pm - (float)w_node * 1.9073486328125e-6f;
+            const unsigned nm = __ballot_sync(0xffffffffu, near);
+            FfResult<CM>* R = &results[k];
+            if (nm == 0u) {
+              if (lane == 0) { R->proxy = -INFINITY; R->ptil = -INFINITY; R->exact = 1; R->n_left = 1 << 30; R->code = is_const ? (1 << 16) : 0; }
+              continue;
+            }
+            // lanes with the same bin hold the same candidate
+            const unsigned kmin = __reduce_min_sync(0xffffffffu, near ? key : 0xFFFFu);
+            const unsigned kmax = __reduce_max_sync(0xffffffffu, near ? key : 0u);
+            int wlane = __ffs(nm) - 1;
+            double proxy = 0.0;
+            if (kmin != kmax) {          // different candidates within the bar: scikit-learn's float64 expression decides
+              proxy = -INFINITY;
+              if (near) {
                 double wl = 0.0;
 #pragma unroll
                 for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
-                const double wr = w_node - wl;
-                if (!(wl < P.min_weight_leaf || wr < P.min_weight_leaf)) {
-                  proxy = ff_proxy<CM>(sl, rec->sums, C, wl, wr, nullptr, nullptr);
-                  n_left = nl;
-                }
+                proxy = ff_proxy<CM>(sl, rec->sums, C, wl, w_node - wl, nullptr, nullptr);
               }
+              double wp = proxy; int wnl = near ? n_left : (1 << 30);
+              for (int o = 16; o > 0; o >>= 1) {
+                const double op = __shfl_xor_sync(0xffffffffu, wp, o);
+                const int onl = __shfl_xor_sync(0xffffffffu, wnl, o);
+                if (op > wp || (op == wp && onl < wnl)) { wp = op; wnl = onl; }
+              }
+              const unsigned same = __ballot_sync(0xffffffffu, near && n_left == wnl && proxy == wp);
+              wlane = __ffs(same) - 1;
             }
-            double wp = proxy; int wnl = n_left;
-            for (int o = 16; o > 0; o >>= 1) {
-              const double op = __shfl_xor_sync(0xffffffffu, wp, o);
-              const int onl = __shfl_xor_sync(0xffffffffu, wnl, o);
-              if (op > wp || (op == wp && onl < wnl)) { wp = op; wnl = onl; }
-            }
-            FfResult<CM>* R = &results[k];
-            // lanes with the same bin hold the same candidate: the lowest of them writes it
-            const unsigned same = __ballot_sync(0xffffffffu, n_left == wnl && proxy == wp && wp > -INFINITY);
-            if (lane == 0) { R->proxy = wp; R->n_left = wnl; R->code = is_const ? (1 << 16) : 0; }
-            __syncwarp();
-            if (same && lane == __ffs(same) - 1) {
+            if (lane == wlane) {
+              R->proxy = proxy; R->ptil = pt; R->exact = kmin != kmax ? 1 : 0; R->n_left = n_left;
               R->code = (int)(key | (nbn << 8));
 #pragma unroll
               for (int c = 0; c < CM; ++c) R->sl[c] = sl[c];
@@ -595,11 +640,39 @@ forest_fast_kernel(const FfParams P) {
           for (int k = 0; k < nbatch; ++k) {
             const FfResult<CM>& R = results[k];
             if (!(R.code & (1 << 16))) {
-              if (R.proxy > best_proxy) {
-                best_proxy = R.proxy;
-                best_feature = items[k].f; best_nl = R.n_left; best_code = R.code;
+              // `proxy > best_proxy` of the reference, decided on the float32 rank values whenever they are
+              // more than the bar apart and on scikit-learn's float64 expression otherwise
+              if (R.ptil > -INFINITY) {
+                const float bar = (float)w_node * 1.9073486328125e-6f;
+                bool take;
+                if (best_nl <= 0 || R.ptil > best_ptil + bar) {          // first valid split / surely larger
+                  take = true; best_exact = R.exact != 0; best_proxy = R.proxy;
+                } else if (R.ptil < best_ptil - bar) {                   // surely not larger
+                  take = false;
+                } else {                                                 // within the bar: float64, strict '>'
+                  if (!best_exact) {
+                    double wl = 0.0;
 #pragma unroll
-                for (int c = 0; c < CM; ++c) best_sl[c] = R.sl[c];
+                    for (int c = 0; c < CM; ++c) if (c < C) wl += (double)best_sl[c];
+                    best_proxy = ff_proxy<CM>(best_sl, rec->sums, C, wl, w_node - wl, nullptr, nullptr);
+                    best_exact = true;
+                  }
+                  double rp = R.proxy;
+                  if (!R.exact) {
+                    double wl = 0.0;
+#pragma unroll
+                    for (int c = 0; c < CM; ++c) if (c < C) wl += (double)R.sl[c];
+                    rp = ff_proxy<CM>(R.sl, rec->sums, C, wl, w_node - wl, nullptr, nullptr);
+                  }
+                  take = rp > best_proxy;
+                  if (take) best_proxy = rp;
+                }
+                if (take) {
+                  best_ptil = R.ptil;
+                  best_feature = items[k].f; best_nl = R.n_left; best_code = R.code;
+#pragma unroll
+                  for (int c = 0; c < CM; ++c) best_sl[c] = R.sl[c];
+                }
               }
               continue;
             }
