@@ -92,64 +92,101 @@ __device__ __forceinline__ int ff_rand_int(int low, int high, uint32_t* seed) {
   return low + (int)(ff_rand_r(seed) % (uint32_t)(high - low));
 }
 
+// The builder is latency-bound on ONE warp's instruction stream per tree (ncu: 44 % of the stall
+// samples are instruction fetch when the kernel is unrolled to 130 KB), so everything below is written
+// for a small instruction footprint: one out-of-line copy of the float64 expressions and of the
+// histogram scan, rolled loops, shared-memory re-reads instead of unrolled register arrays.
+
 // proxy_impurity_improvement of the Gini criterion for left sums sl, node sums st
 // (SK/tree/_criterion.pyx:147-163, 650-680): -w_r * gini_r - w_l * gini_l, no FMA contraction
 template <int CM>
-__device__ __forceinline__ double ff_proxy(const uint32_t* sl, const uint32_t* st, int C, double wl, double wr,
-                                           double* il_out, double* ir_out) {
-  double sql = 0.0, sqr = 0.0;
+__device__ __noinline__ double ff_proxy(const uint32_t* sl, const uint32_t* st, int C, double w_node,
+                                        double* il_out, double* ir_out) {
+  double sql = 0.0, sqr = 0.0, wl = 0.0;
 #pragma unroll
   for (int c = 0; c < CM; ++c) {
     if (c < C) {
       const double a = (double)sl[c], b = (double)(st[c] - sl[c]);
+      wl += a;
       sql = __dadd_rn(sql, __dmul_rn(a, a));
       sqr = __dadd_rn(sqr, __dmul_rn(b, b));
     }
   }
+  const double wr = w_node - wl;
   const double il = __dsub_rn(1.0, __ddiv_rn(sql, __dmul_rn(wl, wl)));
   const double ir = __dsub_rn(1.0, __ddiv_rn(sqr, __dmul_rn(wr, wr)));
   if (il_out) { *il_out = il; *ir_out = ir; }
   return __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
 }
 
+// float32 rank value of a split: sq_l / w_l + sq_r / w_r (= proxy + w_node in exact arithmetic; the
+// float32 value is within 2^-20 * w_node of it).  Candidates, features and batches are compared on it;
+// scikit-learn's float64 expression is evaluated only for values within FF_BAR * w_node of each other.
+constexpr float FF_BAR = 1.9073486328125e-6f;      // 2^-19
+template <int CM>
+__device__ __forceinline__ float ff_rank(const uint32_t* sl, const uint32_t* st, int C, float w_node) {
+  float wl = 0.f, sql = 0.f, sqr = 0.f;
+#pragma unroll
+  for (int c = 0; c < CM; ++c) if (c < C) { const float a = (float)sl[c], b = (float)(st[c] - sl[c]); wl += a; sql = fmaf(a, a, sql); sqr = fmaf(b, b, sqr); }
+  return __fdividef(sql, wl) + __fdividef(sqr, w_node - wl);
+}
+template <int CM>
+__device__ __forceinline__ bool ff_weights_ok(const uint32_t* sl, int C, double w_node, double min_weight_leaf) {
+  if (!(min_weight_leaf > 0.0)) return true;
+  double wl = 0.0;
+#pragma unroll
+  for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
+  return !(wl < min_weight_leaf || w_node - wl < min_weight_leaf);
+}
+
 // One warp scans the 256 bins of one feature's histogram (8 bins per lane, ascending) and leaves the
-// feature's best split in *R.  HC(c, bin) = weight of class c in the bin, HN(bin) = samples in the bin.
-// st = the node's class sums (shared memory).
-template <int CM, class HC, class HN>
-__device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_node, const uint32_t* st, double w_node,
-                                        int min_samples_leaf, double min_weight_leaf, FfResult<CM>* R) {
-  // the lane's eight bins are read once into registers (fully unrolled loops index them statically):
-  // the candidate loops below then run without shared-memory latency in their dependency chains
-  unsigned cn[8];
-  uint32_t cwt[CM][8];
+// feature's best split in *R.  Two histogram layouts: packed = 0: H[c][256] class weights (32-bit) then
+// [256] sample counts; packed = 1: class pairs in 16-bit halves H[c / 2][256], then sample counts, two
+// bins per word, from word `hcw`.  st = the node's class sums (shared memory).
+template <int CM>
+__device__ __noinline__ void ff_scan(const unsigned int* H, int packed, int hcw, int lane, int C, int n_node,
+                                     const uint32_t* st, double w_node, int min_samples_leaf,
+                                     double min_weight_leaf, FfResult<CM>* R) {
+  auto hn = [&](int b) -> unsigned {
+    return packed ? (H[hcw + (b >> 1)] >> ((b & 1) * 16)) & 0xFFFFu : H[C * 256 + b];
+  };
+  auto hc = [&](int c, int b) -> uint32_t {
+    return packed ? (H[(c >> 1) * 256 + b] >> ((c & 1) * 16)) & 0xFFFFu : H[c * 256 + b];
+  };
   unsigned ltot = 0, pmask = 0;
+  uint32_t sl[CM];       // class weights of this lane's bins, then: left of this lane's first bin
 #pragma unroll
+  for (int c = 0; c < CM; ++c) sl[c] = 0;
+#pragma unroll 2
   for (int j = 0; j < 8; ++j) {
-    cn[j] = hn(lane * 8 + j);
+    const unsigned cj = hn(lane * 8 + j);
+    ltot += cj;
+    if (cj) pmask |= 1u << j;
 #pragma unroll
-    for (int c = 0; c < CM; ++c) cwt[c][j] = c < C ? hc(c, lane * 8 + j) : 0u;
+    for (int c = 0; c < CM; ++c) if (c < C) sl[c] += hc(c, lane * 8 + j);
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { ltot += cn[j]; if (cn[j]) pmask |= 1u << j; }
   unsigned pre = ltot;   // exclusive prefix of the sample counts over lanes
-  for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += v; }
-  pre -= ltot;
-  uint32_t sl[CM];       // class weights left of this lane's first bin
+#pragma unroll 1
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned v = __shfl_up_sync(0xffffffffu, pre, o);
+    if (lane >= o) pre += v;
 #pragma unroll
-  for (int c = 0; c < CM; ++c) {
-    sl[c] = 0;
-    if (c < C) {
-      uint32_t t = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) t += cwt[c][j];
-      uint32_t incl = t;
-      for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-      sl[c] = incl - t;
+    for (int c = 0; c < CM; ++c) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, sl[c], o);
+      if (lane >= o) sl[c] += u;
     }
+  }
+  pre -= ltot;
+#pragma unroll
+  for (int c = 0; c < CM; ++c) sl[c] = __shfl_up_sync(0xffffffffu, sl[c], 1);     // inclusive -> exclusive
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < CM; ++c) sl[c] = 0;
   }
   // first present bin of the lanes above this one
   const int myfirst = pmask ? lane * 8 + __ffs(pmask) - 1 : 1 << 20;
   int run = myfirst;
+#pragma unroll 1
   for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_down_sync(0xffffffffu, run, o); if (lane + o < 32) run = min(run, u); }
   const int nx = __shfl_down_sync(0xffffffffu, run, 1);
   const int nxt = lane < 31 ? nx : (1 << 20);
@@ -157,50 +194,64 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
   const int mylast = pmask ? lane * 8 + 31 - __clz(pmask) : -1;
   const int glast = __reduce_max_sync(0xffffffffu, mylast);
   const bool is_const = glast <= gfirst;      // distinct values are > 1e-7 apart (host check): one bin == constant
-  // Ranking the candidates takes two float64 divisions each in scikit-learn's expression.  They are
-  // ranked first by p = sq_l / w_l + sq_r / w_r in float32 (proxy = p - w_node in exact arithmetic;
-  // the float32 value is within 2^-20 * w_node of it), and the float64 expression is evaluated only
-  // for the candidates within 2^-19 * w_node of the best float32 value -- the others cannot win.
-  float pj[8];           // float32 rank value of the candidate above bin j (-inf: no candidate)
+  const float wnf = (float)w_node;
+  // pass 1: float32 rank value of every candidate of this lane; the best one and how many are near it
   float pbest = -INFINITY;
-  {
+  int jbest = 0;
+  if (!is_const) {
     unsigned run_cnt = pre;
     uint32_t s2[CM];
 #pragma unroll
     for (int c = 0; c < CM; ++c) s2[c] = sl[c];
+    unsigned pm = pmask;
+    while (pm) {                               // this lane's present bins in ascending order
+      const int j = __ffs(pm) - 1;
+      pm &= pm - 1;
+      run_cnt += hn(lane * 8 + j);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      pj[j] = -INFINITY;
-      run_cnt += cn[j];
-#pragma unroll
-      for (int c = 0; c < CM; ++c) s2[c] += cwt[c][j];
-      const bool last = !(pmask >> (j + 1)) && nxt >= (1 << 20);      // no present bin above: no boundary
-      const int n_left = (int)run_cnt, n_right = n_node - n_left;
-      if (is_const || !cn[j] || last || n_left < min_samples_leaf || n_right < min_samples_leaf) continue;
-      float wl = 0.f, sql = 0.f, sqr = 0.f;
-#pragma unroll
-      for (int c = 0; c < CM; ++c) if (c < C) { const float a = (float)s2[c], b2 = (float)(st[c] - s2[c]); wl += a; sql = fmaf(a, a, sql); sqr = fmaf(b2, b2, sqr); }
-      const float wr = (float)w_node - wl;
-      if (min_weight_leaf > 0.0) {       // the validity tests are the exact ones: an invalid candidate must not set the bar
-        double wld = 0.0;
-#pragma unroll
-        for (int c = 0; c < CM; ++c) if (c < C) wld += (double)s2[c];
-        if (wld < min_weight_leaf || w_node - wld < min_weight_leaf) continue;
-      }
-      pj[j] = __fdividef(sql, wl) + __fdividef(sqr, wr);
-      pbest = fmaxf(pbest, pj[j]);
+      for (int c = 0; c < CM; ++c) if (c < C) s2[c] += hc(c, lane * 8 + j);
+      if (!pm && nxt >= (1 << 20)) break;       // last present bin of the node: no boundary above it
+      const int n_left = (int)run_cnt;
+      if (n_left < min_samples_leaf || n_node - n_left < min_samples_leaf) continue;
+      if (!ff_weights_ok<CM>(s2, C, w_node, min_weight_leaf)) continue;   // exact test: an invalid candidate must not set the bar
+      const float pt = ff_rank<CM>(s2, st, C, wnf);
+      if (pt > pbest) { pbest = pt; jbest = j; }
     }
   }
-  float pthr = pbest;
-  for (int o = 16; o > 0; o >>= 1) pthr = fmaxf(pthr, __shfl_xor_sync(0xffffffffu, pthr, o));
-  pthr -= (float)w_node * 1.9073486328125e-6f;      // 2^-19 * w_node
-  // how many candidates are within the bar?  Exactly one (the usual case): it is the feature's best
-  // split and no float64 evaluation is needed here (the commit step compares features the same way).
+  float pmax = pbest;
+#pragma unroll 1
+  for (int o = 16; o > 0; o >>= 1) pmax = fmaxf(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+  if (!(pmax > -INFINITY)) {
+    if (lane == 0) { R->proxy = -INFINITY; R->ptil = -INFINITY; R->exact = 1; R->n_left = 1 << 30; R->code = is_const ? (1 << 16) : 0; }
+    return;
+  }
+  const float pthr = pmax - wnf * FF_BAR;
+  // Is the best candidate alone within the bar?  (lanes whose best is below the bar have no near
+  // candidate; a lane whose best is within it may have more: it counts them in a second walk)
   int nnear = 0;
+  if (pbest >= pthr) {
+    unsigned run_cnt = pre;
+    uint32_t s2[CM];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) nnear += (pbest > -INFINITY && pj[j] >= pthr) ? 1 : 0;
-  const int total_near = (int)__reduce_add_sync(0xffffffffu, (unsigned)nnear);
-  const bool single = total_near == 1;
+    for (int c = 0; c < CM; ++c) s2[c] = sl[c];
+    unsigned pm = pmask;
+    while (pm) {
+      const int j = __ffs(pm) - 1;
+      pm &= pm - 1;
+      run_cnt += hn(lane * 8 + j);
+#pragma unroll
+      for (int c = 0; c < CM; ++c) if (c < C) s2[c] += hc(c, lane * 8 + j);
+      if (!pm && nxt >= (1 << 20)) break;
+      const int n_left = (int)run_cnt;
+      if (n_left < min_samples_leaf || n_node - n_left < min_samples_leaf) continue;
+      if (!ff_weights_ok<CM>(s2, C, w_node, min_weight_leaf)) continue;
+      if (ff_rank<CM>(s2, st, C, wnf) >= pthr) nnear += 1;
+    }
+  }
+  const bool single = __reduce_add_sync(0xffffffffu, (unsigned)nnear) == 1u;
+  // pass 2 (lanes with a near candidate): the winner's position, bins and left sums; float64 proxies only
+  // when several candidates are within the bar (ties then go to the smallest position, as the
+  // sequential scan's strict '>' does)
   double bproxy = -INFINITY;
   float bpt = -INFINITY;
   int bnl = 1 << 30, bcode = 0;
@@ -209,36 +260,32 @@ __device__ __forceinline__ void ff_scan(HC hc, HN hn, int lane, int C, int n_nod
   for (int c = 0; c < CM; ++c) bsl[c] = 0;
   if (nnear > 0) {
     unsigned run_cnt = pre;
+    unsigned pm = pmask;
+    while (pm) {
+      const int j = __ffs(pm) - 1;
+      pm &= pm - 1;
+      run_cnt += hn(lane * 8 + j);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {               // this lane's bins in ascending order
-      run_cnt += cn[j];
-#pragma unroll
-      for (int c = 0; c < CM; ++c) sl[c] += cwt[c][j];
-      if (!(pj[j] >= pthr)) continue;           // not a candidate, or cannot be the best
-      const unsigned higher = pmask >> (j + 1);
-      const int nb2 = higher ? lane * 8 + j + __ffs(higher) : nxt;
-      double proxy = 0.0;
-      if (!single) {
-        double wl = 0.0;
-#pragma unroll
-        for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
-        proxy = ff_proxy<CM>(sl, st, C, wl, w_node - wl, nullptr, nullptr);
-      }
+      for (int c = 0; c < CM; ++c) if (c < C) sl[c] += hc(c, lane * 8 + j);
+      if (!pm && nxt >= (1 << 20)) break;
+      const int n_left = (int)run_cnt;
+      if (n_left < min_samples_leaf || n_node - n_left < min_samples_leaf) continue;
+      if (!ff_weights_ok<CM>(sl, C, w_node, min_weight_leaf)) continue;
+      const float pt = ff_rank<CM>(sl, st, C, wnf);
+      if (!(pt >= pthr)) continue;
+      const double proxy = single ? 0.0 : ff_proxy<CM>(sl, st, C, w_node, nullptr, nullptr);
       if (single || proxy > bproxy) {
-        bproxy = proxy; bpt = pj[j]; bnl = (int)run_cnt; bcode = (lane * 8 + j) | (nb2 << 8);
+        const int nb2 = pm ? lane * 8 + __ffs(pm) - 1 : nxt;
+        bproxy = proxy; bpt = pt; bnl = n_left; bcode = (lane * 8 + j) | (nb2 << 8);
 #pragma unroll
         for (int c = 0; c < CM; ++c) bsl[c] = sl[c];
       }
     }
   }
-  if (total_near == 0) {
-    if (lane == 0) { R->proxy = -INFINITY; R->ptil = -INFINITY; R->exact = 1; R->n_left = 1 << 30; R->code = is_const ? (1 << 16) : 0; }
-    return;
-  }
   bool writer = single && nnear > 0;
   if (!single) {
-    // warp arg-max; ties keep the smallest position (the sequential scan's strict '>')
     double wp = bproxy; int wnl = bnl;
+#pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
       const double op = __shfl_xor_sync(0xffffffffu, wp, o);
       const int onl = __shfl_xor_sync(0xffffffffu, wnl, o);
@@ -515,9 +562,7 @@ forest_fast_kernel(const FfParams P) {
           FF_TICK(3);
           for (int k = wid; k < nbatch; k += FF_WARPS) {
             const unsigned int* H = U + k * hstrideA;
-            ff_scan<CM>([&](int c, int b) -> uint32_t { return H[c * 256 + b]; },
-                        [&](int b) -> unsigned { return H[C * 256 + b]; },
-                        lane, C, n_node, rec->sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[k]);
+            ff_scan<CM>(H, 0, 0, lane, C, n_node, rec->sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[k]);
           }
         } else if (!small) {
           // ---- staged histogram node: warp k builds and scans the packed histogram of item k ----
@@ -545,9 +590,7 @@ forest_fast_kernel(const FfParams P) {
               }
             }
             __syncwarp();
-            ff_scan<CM>([&](int c, int b) -> uint32_t { return (H[(c >> 1) * 256 + b] >> ((c & 1) * 16)) & 0xFFFFu; },
-                        [&](int b) -> unsigned { return (H[hcw + (b >> 1)] >> ((b & 1) * 16)) & 0xFFFFu; },
-                        lane, C, n_node, rec->sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[k]);
+            ff_scan<CM>(H, 1, hcw, lane, C, n_node, rec->sums, w_node, P.min_samples_leaf, P.min_weight_leaf, &results[k]);
           }
         } else {
           // ---- staged node of <= 32 samples: lane j holds sample j; every lane counts the samples
@@ -562,7 +605,7 @@ forest_fast_kernel(const FfParams P) {
             const unsigned key = have ? (unsigned)rowsB[lid * ws4 + f] : 0xFFFFu;
             acc_t acc = 0;
             unsigned nbn = 0xFFFFu;        // smallest bin above this lane's bin present in the node
-#pragma unroll 4
+#pragma unroll 2
             for (int j = 0; j < n_node; ++j) {
               const unsigned bj = __shfl_sync(0xffffffffu, key, j);
               const acc_t pj = __shfl_sync(0xffffffffu, pw, j);
@@ -578,24 +621,13 @@ forest_fast_kernel(const FfParams P) {
             // when two different candidates are within the bar of each other
             float pt = -INFINITY;
             const int n_left = (int)(acc >> CNT);
-            if (cand && n_left >= P.min_samples_leaf && n_node - n_left >= P.min_samples_leaf) {
-              bool ok = true;
-              if (P.min_weight_leaf > 0.0) {
-                double wld = 0.0;
-#pragma unroll
-                for (int c = 0; c < CM; ++c) if (c < C) wld += (double)sl[c];
-                ok = !(wld < P.min_weight_leaf || w_node - wld < P.min_weight_leaf);
-              }
-              if (ok) {
-                float wl = 0.f, sql = 0.f, sqr = 0.f;
-#pragma unroll
-                for (int c = 0; c < CM; ++c) if (c < C) { const float a = (float)sl[c], b2 = (float)(rec->sums[c] - sl[c]); wl += a; sql = fmaf(a, a, sql); sqr = fmaf(b2, b2, sqr); }
-                pt = __fdividef(sql, wl) + __fdividef(sqr, (float)w_node - wl);
-              }
-            }
+            if (cand && n_left >= P.min_samples_leaf && n_node - n_left >= P.min_samples_leaf &&
+                ff_weights_ok<CM>(sl, C, w_node, P.min_weight_leaf))
+              pt = ff_rank<CM>(sl, rec->sums, C, (float)w_node);
             float pm = pt;
+#pragma unroll 1
             for (int o = 16; o > 0; o >>= 1) pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, o));
-            const bool near = pt > -INFINITY && pt >= pm - (float)w_node * 1.9073486328125e-6f;
+            const bool near = pt > -INFINITY && pt >= pm - (float)w_node * FF_BAR;
             const unsigned nm = __ballot_sync(0xffffffffu, near);
             FfResult<CM>* R = &results[k];
             if (nm == 0u) {
@@ -609,13 +641,9 @@ forest_fast_kernel(const FfParams P) {
             double proxy = 0.0;
             if (kmin != kmax) {          // different candidates within the bar: scikit-learn's float64 expression decides
               proxy = -INFINITY;
-              if (near) {
-                double wl = 0.0;
-#pragma unroll
-                for (int c = 0; c < CM; ++c) if (c < C) wl += (double)sl[c];
-                proxy = ff_proxy<CM>(sl, rec->sums, C, wl, w_node - wl, nullptr, nullptr);
-              }
+              if (near) proxy = ff_proxy<CM>(sl, rec->sums, C, w_node, nullptr, nullptr);
               double wp = proxy; int wnl = near ? n_left : (1 << 30);
+#pragma unroll 1
               for (int o = 16; o > 0; o >>= 1) {
                 const double op = __shfl_xor_sync(0xffffffffu, wp, o);
                 const int onl = __shfl_xor_sync(0xffffffffu, wnl, o);
@@ -643,27 +671,15 @@ forest_fast_kernel(const FfParams P) {
               // `proxy > best_proxy` of the reference, decided on the float32 rank values whenever they are
               // more than the bar apart and on scikit-learn's float64 expression otherwise
               if (R.ptil > -INFINITY) {
-                const float bar = (float)w_node * 1.9073486328125e-6f;
+                const float bar = (float)w_node * FF_BAR;
                 bool take;
                 if (best_nl <= 0 || R.ptil > best_ptil + bar) {          // first valid split / surely larger
                   take = true; best_exact = R.exact != 0; best_proxy = R.proxy;
                 } else if (R.ptil < best_ptil - bar) {                   // surely not larger
                   take = false;
                 } else {                                                 // within the bar: float64, strict '>'
-                  if (!best_exact) {
-                    double wl = 0.0;
-#pragma unroll
-                    for (int c = 0; c < CM; ++c) if (c < C) wl += (double)best_sl[c];
-                    best_proxy = ff_proxy<CM>(best_sl, rec->sums, C, wl, w_node - wl, nullptr, nullptr);
-                    best_exact = true;
-                  }
-                  double rp = R.proxy;
-                  if (!R.exact) {
-                    double wl = 0.0;
-#pragma unroll
-                    for (int c = 0; c < CM; ++c) if (c < C) wl += (double)R.sl[c];
-                    rp = ff_proxy<CM>(R.sl, rec->sums, C, wl, w_node - wl, nullptr, nullptr);
-                  }
+                  if (!best_exact) { best_proxy = ff_proxy<CM>(best_sl, rec->sums, C, w_node, nullptr, nullptr); best_exact = true; }
+                  const double rp = R.exact ? R.proxy : ff_proxy<CM>(R.sl, rec->sums, C, w_node, nullptr, nullptr);
                   take = rp > best_proxy;
                   if (take) best_proxy = rp;
                 }
@@ -703,7 +719,7 @@ forest_fast_kernel(const FfParams P) {
           for (int c = 0; c < CM; ++c) if (c < C) wl += (double)best_sl[c];
           const double wr = w_node - wl;
           double il, ir;
-          ff_proxy<CM>(best_sl, rec->sums, C, wl, wr, &il, &ir);
+          ff_proxy<CM>(best_sl, rec->sums, C, w_node, &il, &ir);
           // impurity_improvement (SK/tree/_criterion.pyx:163-190)
           const double a = __dmul_rn(__ddiv_rn(wr, w_node), ir);
           const double b = __dmul_rn(__ddiv_rn(wl, w_node), il);

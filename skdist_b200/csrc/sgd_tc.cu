@@ -332,17 +332,16 @@ sgd_scan_kernel(const SgdScanParams P) {
     if (lane < Te)      // updates logged after the window was requested / beyond the first PV
       for (int v = cw.nv; v < nviol; ++v) s_l = fmaf(vq[v], P.G[(size_t)vj[v] * ST_T + i0 + lane], s_l);
     // A. the norm recurrence sq_norm *= c_t^2 in sample order (lane t keeps the value BEFORE sample t)
-    double my_sq = sq_norm, my_sq_after = sq_norm;
-    {
-      double sq = sq_norm;
+    // (lane t multiplies the factors of the samples before it, in order: its own sequential chain; one
+    // broadcast and one predicated multiply per step instead of a shared chain with per-lane captures)
+    const double c2_l = (double)__fmul_rn(c_l, c_l);
+    double my_sq = sq_norm;
 #pragma unroll
-      for (int q = 0; q < T; ++q) {
-        const float cq = __shfl_sync(FULL, c_l, q);
-        if (lane == q) my_sq = sq;
-        sq *= (double)__fmul_rn(cq, cq);
-        if (lane == q) my_sq_after = sq;
-      }
+    for (int q = 0; q < T - 1; ++q) {
+      const double c2q = __shfl_sync(FULL, c2_l, q);
+      if (lane > q) my_sq *= c2q;
     }
+    const double my_sq_after = my_sq * c2_l;
     // B. screening: approximate margin against 1 + error bound
     const double pa = (double)(float)((double)s_l * ws_l) + intercept;
     const double za = pa * y_l;
@@ -357,10 +356,11 @@ sgd_scan_kernel(const SgdScanParams P) {
     const int ev = evmask ? __ffs(evmask) - 1 : -1;        // first sample that needs the exact path
     const int nfree = ev >= 0 ? ev : Te;                   // samples 0..nfree-1 are certain non-violators
     // D. their objective terms (loss 0) in order
+    // (cur_loss + l2 term with cur_loss = 0.0 is the l2 term itself: the terms are non-negative)
 #pragma unroll
     for (int q = 0; q < T; ++q) {
       const double tq = __shfl_sync(FULL, l2_l, q);
-      if (q < nfree) objective_sum = __dadd_rn(objective_sum, __dadd_rn(0.0, tq));
+      if (q < nfree) objective_sum = __dadd_rn(objective_sum, tq);
     }
     n_screen += nfree;
     if (ev < 0) {
