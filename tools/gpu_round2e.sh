@@ -1,0 +1,10 @@
+#!/bin/bash
+# Round-2 development check (e): compact forest builder + lighter SGD scan: tests, timings, one ncu capture.
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+echo "== forest tests"; timeout 600 python -m pytest tests/test_forest_gpu.py -x -q > gpurun_out/pytest_forest.log 2>&1; tail -2 gpurun_out/pytest_forest.log
+echo "== sgd tests"; timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "sgd" > gpurun_out/pytest_sgd.log 2>&1; tail -2 gpurun_out/pytest_sgd.log
+echo "== forest config 4 (phase profile)"; SKDIST_B200_FOREST_PROF=1 timeout 600 python tools/bench_forest.py --trees 1024 --cpu-sample 0 > gpurun_out/bench_forest_prof.log 2>&1; grep "forest prof" gpurun_out/bench_forest_prof.log | head -20; tail -1 gpurun_out/bench_forest_prof.log | cut -c1-700
+echo "== ovr sgd config 3"; SKDIST_B200_TRACE=2 timeout 900 python tools/bench_ovr.py --cpu-sample 0 > gpurun_out/bench_ovr.log 2>&1; grep "sgd-tc" gpurun_out/bench_ovr.log | sed -n '2,4p;22,23p;$p'; tail -1 gpurun_out/bench_ovr.log | cut -c1-400
+echo "== ncu forest (reduced problem: 200k rows, one wave)"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:forest_fast_kernel -c 1 -o gpurun_out/prof_forest_fast2 python tools/bench_forest.py --n 200000 --trees 1036 --cpu-sample 0 > gpurun_out/ncu_forest.log 2>&1; tail -1 gpurun_out/ncu_forest.log | cut -c1-200
