@@ -99,24 +99,33 @@ __device__ __forceinline__ int ff_rand_int(int low, int high, uint32_t* seed) {
 
 // proxy_impurity_improvement of the Gini criterion for left sums sl, node sums st
 // (SK/tree/_criterion.pyx:147-163, 650-680): -w_r * gini_r - w_l * gini_l, no FMA contraction
-template <int CM>
-__device__ __noinline__ double ff_proxy(const uint32_t* sl, const uint32_t* st, int C, double w_node,
-                                        double* il_out, double* ir_out) {
+// (all operands by value: a pointer to a caller's register array would force that array -- and every
+// update of it in the caller's loops -- into local memory)
+struct FfProxy { double proxy, il, ir; };
+__device__ __noinline__ FfProxy ff_proxy4(uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3,
+                                          uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, int C, double w_node) {
+  const uint32_t l[4] = {l0, l1, l2, l3}, t[4] = {t0, t1, t2, t3};
   double sql = 0.0, sqr = 0.0, wl = 0.0;
 #pragma unroll
-  for (int c = 0; c < CM; ++c) {
+  for (int c = 0; c < 4; ++c) {
     if (c < C) {
-      const double a = (double)sl[c], b = (double)(st[c] - sl[c]);
+      const double a = (double)l[c], b = (double)(t[c] - l[c]);
       wl += a;
       sql = __dadd_rn(sql, __dmul_rn(a, a));
       sqr = __dadd_rn(sqr, __dmul_rn(b, b));
     }
   }
   const double wr = w_node - wl;
-  const double il = __dsub_rn(1.0, __ddiv_rn(sql, __dmul_rn(wl, wl)));
-  const double ir = __dsub_rn(1.0, __ddiv_rn(sqr, __dmul_rn(wr, wr)));
-  if (il_out) { *il_out = il; *ir_out = ir; }
-  return __dsub_rn(__dmul_rn(-wr, ir), __dmul_rn(wl, il));
+  FfProxy r;
+  r.il = __dsub_rn(1.0, __ddiv_rn(sql, __dmul_rn(wl, wl)));
+  r.ir = __dsub_rn(1.0, __ddiv_rn(sqr, __dmul_rn(wr, wr)));
+  r.proxy = __dsub_rn(__dmul_rn(-wr, r.ir), __dmul_rn(wl, r.il));
+  return r;
+}
+template <int CM>
+__device__ __forceinline__ FfProxy ff_proxy(const uint32_t (&sl)[CM], const uint32_t* st, int C, double w_node) {
+  return ff_proxy4(sl[0], CM > 1 ? sl[1] : 0u, CM > 2 ? sl[2] : 0u, CM > 3 ? sl[3] : 0u,
+                   st[0], CM > 1 ? st[1] : 0u, CM > 2 ? st[2] : 0u, CM > 3 ? st[3] : 0u, C, w_node);
 }
 
 // float32 rank value of a split: sq_l / w_l + sq_r / w_r (= proxy + w_node in exact arithmetic; the
@@ -273,7 +282,7 @@ __device__ __noinline__ void ff_scan(const unsigned int* H, int packed, int hcw,
       if (!ff_weights_ok<CM>(sl, C, w_node, min_weight_leaf)) continue;
       const float pt = ff_rank<CM>(sl, st, C, wnf);
       if (!(pt >= pthr)) continue;
-      const double proxy = single ? 0.0 : ff_proxy<CM>(sl, st, C, w_node, nullptr, nullptr);
+      const double proxy = single ? 0.0 : ff_proxy<CM>(sl, st, C, w_node).proxy;
       if (single || proxy > bproxy) {
         const int nb2 = pm ? lane * 8 + __ffs(pm) - 1 : nxt;
         bproxy = proxy; bpt = pt; bnl = n_left; bcode = (lane * 8 + j) | (nb2 << 8);
@@ -641,7 +650,7 @@ forest_fast_kernel(const FfParams P) {
             double proxy = 0.0;
             if (kmin != kmax) {          // different candidates within the bar: scikit-learn's float64 expression decides
               proxy = -INFINITY;
-              if (near) proxy = ff_proxy<CM>(sl, rec->sums, C, w_node, nullptr, nullptr);
+              if (near) proxy = ff_proxy<CM>(sl, rec->sums, C, w_node).proxy;
               double wp = proxy; int wnl = near ? n_left : (1 << 30);
 #pragma unroll 1
               for (int o = 16; o > 0; o >>= 1) {
@@ -678,8 +687,20 @@ forest_fast_kernel(const FfParams P) {
                 } else if (R.ptil < best_ptil - bar) {                   // surely not larger
                   take = false;
                 } else {                                                 // within the bar: float64, strict '>'
-                  if (!best_exact) { best_proxy = ff_proxy<CM>(best_sl, rec->sums, C, w_node, nullptr, nullptr); best_exact = true; }
-                  const double rp = R.exact ? R.proxy : ff_proxy<CM>(R.sl, rec->sums, C, w_node, nullptr, nullptr);
+                  if (!best_exact) {
+                    uint32_t bs[CM];
+#pragma unroll
+                    for (int c = 0; c < CM; ++c) bs[c] = best_sl[c];
+                    best_proxy = ff_proxy<CM>(bs, rec->sums, C, w_node).proxy;
+                    best_exact = true;
+                  }
+                  double rp = R.proxy;
+                  if (!R.exact) {
+                    uint32_t rs2[CM];
+#pragma unroll
+                    for (int c = 0; c < CM; ++c) rs2[c] = R.sl[c];
+                    rp = ff_proxy<CM>(rs2, rec->sums, C, w_node).proxy;
+                  }
                   take = rp > best_proxy;
                   if (take) best_proxy = rp;
                 }
@@ -718,8 +739,11 @@ forest_fast_kernel(const FfParams P) {
 #pragma unroll
           for (int c = 0; c < CM; ++c) if (c < C) wl += (double)best_sl[c];
           const double wr = w_node - wl;
-          double il, ir;
-          ff_proxy<CM>(best_sl, rec->sums, C, w_node, &il, &ir);
+          uint32_t bs[CM];
+#pragma unroll
+          for (int c = 0; c < CM; ++c) bs[c] = best_sl[c];
+          const FfProxy pr = ff_proxy<CM>(bs, rec->sums, C, w_node);
+          const double il = pr.il, ir = pr.ir;
           // impurity_improvement (SK/tree/_criterion.pyx:163-190)
           const double a = __dmul_rn(__ddiv_rn(wr, w_node), ir);
           const double b = __dmul_rn(__ddiv_rn(wl, w_node), il);

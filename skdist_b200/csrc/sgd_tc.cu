@@ -322,19 +322,24 @@ sgd_scan_kernel(const SgdScanParams P) {
     const int Te = (P.t_len - i0) < T ? (P.t_len - i0) : T;
     // lane t < Te owns sample i0 + t of the block
     const Win cw = (nxt_i0 == i0) ? nxt : load_win(i0);
-    nxt_i0 = i0 + T;
-    nxt = load_win(nxt_i0);                       // in flight while this window is processed
-    const double y_l = (cw.yc == pos) ? 1.0 : -1.0, e_l = cw.e, ws_l = cw.ws;
-    const float c_l = cw.c, nx_l = cw.nx;
+    // Every loaded value of this window is consumed BEFORE the next window is requested: the consumer of a
+    // load waits on a scoreboard slot, and a slot re-armed by the new loads would make it wait for them
+    // too (ncu, first build: 22 % of the stall samples on the first use of the prefetched S value).
+    const double y_l = (cw.yc == pos) ? 1.0 : -1.0, e_l = cw.e + 0.0, ws_l = cw.ws + 0.0;
+    const float c_l = cw.c + 0.f, nx_l = cw.nx + 0.f;
     float s_l = cw.s * inv_scale;
 #pragma unroll
     for (int v = 0; v < PV; ++v) if (v < cw.nv) s_l = fmaf(vq[v], cw.g[v], s_l);
     if (lane < Te)      // updates logged after the window was requested / beyond the first PV
       for (int v = cw.nv; v < nviol; ++v) s_l = fmaf(vq[v], P.G[(size_t)vj[v] * ST_T + i0 + lane], s_l);
+    const double c2_l = (double)__fmul_rn(c_l, c_l);
+    asm volatile("" ::: "memory");
+    nxt_i0 = i0 + T;
+    nxt = load_win(nxt_i0);                       // in flight while this window is processed
+    asm volatile("" ::: "memory");
     // A. the norm recurrence sq_norm *= c_t^2 in sample order (lane t keeps the value BEFORE sample t)
     // (lane t multiplies the factors of the samples before it, in order: its own sequential chain; one
     // broadcast and one predicated multiply per step instead of a shared chain with per-lane captures)
-    const double c2_l = (double)__fmul_rn(c_l, c_l);
     double my_sq = sq_norm;
 #pragma unroll
     for (int q = 0; q < T - 1; ++q) {

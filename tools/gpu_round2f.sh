@@ -1,0 +1,8 @@
+#!/bin/bash
+# Round-2 development check (f)
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+echo "== forest tests"; timeout 600 python -m pytest tests/test_forest_gpu.py -x -q > gpurun_out/pytest_forest.log 2>&1; tail -2 gpurun_out/pytest_forest.log
+echo "== sgd tests"; timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "sgd" > gpurun_out/pytest_sgd.log 2>&1; tail -2 gpurun_out/pytest_sgd.log
+echo "== forest config 4 (phase profile)"; SKDIST_B200_FOREST_PROF=1 timeout 600 python tools/bench_forest.py --trees 1024 --cpu-sample 0 > gpurun_out/bench_forest_prof.log 2>&1; grep "forest prof" gpurun_out/bench_forest_prof.log | head -20; tail -1 gpurun_out/bench_forest_prof.log | cut -c1-700
+echo "== ovr sgd config 3"; SKDIST_B200_TRACE=2 timeout 900 python tools/bench_ovr.py --cpu-sample 0 > gpurun_out/bench_ovr.log 2>&1; grep "sgd-tc" gpurun_out/bench_ovr.log | sed -n '2,4p;22,23p;$p'; tail -1 gpurun_out/bench_ovr.log | cut -c1-400
