@@ -178,7 +178,7 @@ int skd_ctx_destroy(skd_ctx* ctx) {
   free_staged(ctx->c);
   for (void* p : ctx->c.pin_bufs) cudaFreeHost(p);
   ctx->c.pin_bufs.clear();
-  for (int b = 0; b < 2; ++b) if (ctx->c.pin_tree[b]) cudaFreeHost(ctx->c.pin_tree[b]);
+  for (void* pb : ctx->c.pin_tree) if (pb) cudaFreeHost(pb);
   for (auto& b : ctx->c.pool_free) cudaFree(b.first);
   ctx->c.pool_free.clear();
   tc_free(&ctx->c);

@@ -20,6 +20,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 
 #include "forest_common.h"
 #include "skd_internal.h"
@@ -977,40 +982,69 @@ int forest_fit(Ctx* c, int n_trees, const uint8_t* counts, const uint32_t* rand_
                           hp[11], hp[12], hp[13], hp[14], tot * 1e-9);
       }
       if (fast) {
-        // compact records: trees are copied through two pinned buffers (copy of tree s + 1 overlaps the
-        // consumer's work on tree s)
+        // compact records: trees come back through a ring of pinned buffers; the copies are issued by
+        // this thread, a few host threads wait for them and hand the trees to the consumer (which copies
+        // 12 MB per tree out of the pinned buffer: a single thread would be the bottleneck)
+        constexpr int NB = 8, NW = 4;
         size_t max_m = 1;
         for (int s = 0; s < nt; ++s) if (hstatus[s] == 0) max_m = std::max(max_m, (size_t)hcount[s]);
         if (c->pin_tree_bytes < max_m * 32) {
-          for (int b = 0; b < 2; ++b) { if (c->pin_tree[b]) cudaFreeHost(c->pin_tree[b]); c->pin_tree[b] = nullptr; }
+          for (void*& pb : c->pin_tree) { if (pb) cudaFreeHost(pb); pb = nullptr; }
           c->pin_tree_bytes = max_m * 32 + (max_m * 32) / 8;
-          for (int b = 0; b < 2; ++b) SKD_CUDA(c, cudaHostAlloc(&c->pin_tree[b], c->pin_tree_bytes, cudaHostAllocDefault));
+          for (void*& pb : c->pin_tree) SKD_CUDA(c, cudaHostAlloc(&pb, c->pin_tree_bytes, cudaHostAllocDefault));
         }
-        cudaEvent_t evc[2];
-        for (int b = 0; b < 2; ++b) SKD_CUDA(c, cudaEventCreateWithFlags(&evc[b], cudaEventDisableTiming));
         std::vector<int> ok;
         for (int s = 0; s < nt; ++s) {
           if (hstatus[s] == 1 && node_cap < node_cap_max) { failed.push_back(pending[p0 + s]); continue; }
           if (hstatus[s] != 0) return fail(c, hstatus[s] == 1 ? "forest: node capacity exceeded" : "forest: builder stack capacity exceeded");
           ok.push_back(s);
         }
-        auto issue = [&](size_t k) {
-          const int s = ok[k];
-          cudaMemcpyAsync(c->pin_tree[k & 1], d_nodes + (size_t)s * node_cap * 8, (size_t)hcount[s] * 32, cudaMemcpyDeviceToHost, c->stream);
-          cudaEventRecord(evc[k & 1], c->stream);
+        cudaEvent_t evc[NB];
+        for (int b = 0; b < NB; ++b) SKD_CUDA(c, cudaEventCreateWithFlags(&evc[b], cudaEventDisableTiming));
+        std::mutex mu;
+        std::condition_variable cv_job, cv_free;
+        std::deque<size_t> ready;
+        bool busy[NB] = {false}, finished = false;
+        std::atomic<int> cuda_err{0};
+        auto worker = [&]() {
+          cudaSetDevice(c->device);
+          for (;;) {
+            size_t k;
+            {
+              std::unique_lock<std::mutex> lk(mu);
+              cv_job.wait(lk, [&] { return !ready.empty() || finished; });
+              if (ready.empty()) return;
+              k = ready.front(); ready.pop_front();
+            }
+            const int b = (int)(k % NB), s = ok[k];
+            if (cudaEventSynchronize(evc[b]) != cudaSuccess) cuda_err = 1;
+            SkdTreeView v;
+            v.compact = (const uint32_t*)c->pin_tree[b];
+            v.binval = c->forest.h_binval.data();
+            v.node_count = hcount[s]; v.max_depth = hdepth[s]; v.n_classes = n_classes;
+            v.left = v.right = v.feature = v.n_node_samples = nullptr; v.missing_go_to_left = nullptr;
+            v.threshold = v.impurity = v.weighted_n_node_samples = v.value = nullptr;
+            sink(sink_arg, pending[p0 + s], &v);
+            { std::lock_guard<std::mutex> lk(mu); busy[b] = false; }
+            cv_free.notify_all();
+          }
         };
-        if (!ok.empty()) issue(0);
+        std::vector<std::thread> pool;
+        for (int w = 0; w < NW; ++w) pool.emplace_back(worker);
         for (size_t k = 0; k < ok.size(); ++k) {
-          SKD_CUDA(c, cudaEventSynchronize(evc[k & 1]));
-          if (k + 1 < ok.size()) issue(k + 1);
-          const int s = ok[k];
-          view.compact = (const uint32_t*)c->pin_tree[k & 1];
-          view.binval = c->forest.h_binval.data();
-          view.node_count = hcount[s]; view.max_depth = hdepth[s]; view.n_classes = n_classes;
-          sink(sink_arg, pending[p0 + s], &view);
+          const int b = (int)(k % NB), s = ok[k];
+          { std::unique_lock<std::mutex> lk(mu); cv_free.wait(lk, [&] { return !busy[b]; }); busy[b] = true; }
+          cudaMemcpyAsync(c->pin_tree[b], d_nodes + (size_t)s * node_cap * 8, (size_t)hcount[s] * 32, cudaMemcpyDeviceToHost, c->stream);
+          cudaEventRecord(evc[b], c->stream);
+          { std::lock_guard<std::mutex> lk(mu); ready.push_back(k); }
+          cv_job.notify_one();
           c->d2h += (int64_t)hcount[s] * 32;
         }
-        for (int b = 0; b < 2; ++b) cudaEventDestroy(evc[b]);
+        { std::lock_guard<std::mutex> lk(mu); finished = true; }
+        cv_job.notify_all();
+        for (auto& t : pool) t.join();
+        for (int b = 0; b < NB; ++b) cudaEventDestroy(evc[b]);
+        if (cuda_err) return fail(c, "forest: copying the trees back failed");
         SKD_CUDA(c, cudaGetLastError());
         continue;
       }

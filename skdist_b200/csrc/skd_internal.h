@@ -99,7 +99,7 @@ struct Ctx {
   std::vector<void*> pin_bufs;
   size_t pin_bytes = 0;
   double forest_kernel_ms = 0.0;            // device time of the tree-builder kernels of the last forest_fit (events)
-  void* pin_tree[2] = {nullptr, nullptr};   // pinned double buffer for finished trees (forest.cu)
+  void* pin_tree[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // pinned ring for finished trees (forest.cu)
   size_t pin_tree_bytes = 0;
   // counters
   int64_t launches = 0, h2d = 0, d2h = 0;
