@@ -204,9 +204,8 @@ __device__ __noinline__ void ff_scan(const unsigned int* H, int packed, int hcw,
   const int glast = __reduce_max_sync(0xffffffffu, mylast);
   const bool is_const = glast <= gfirst;      // distinct values are > 1e-7 apart (host check): one bin == constant
   const float wnf = (float)w_node;
-  // pass 1: float32 rank value of every candidate of this lane; the best one and how many are near it
-  float pbest = -INFINITY;
-  int jbest = 0;
+  // pass 1: float32 rank value of every candidate of this lane: its best and second best
+  float pbest = -INFINITY, psecond = -INFINITY;
   if (!is_const) {
     unsigned run_cnt = pre;
     uint32_t s2[CM];
@@ -224,7 +223,8 @@ __device__ __noinline__ void ff_scan(const unsigned int* H, int packed, int hcw,
       if (n_left < min_samples_leaf || n_node - n_left < min_samples_leaf) continue;
       if (!ff_weights_ok<CM>(s2, C, w_node, min_weight_leaf)) continue;   // exact test: an invalid candidate must not set the bar
       const float pt = ff_rank<CM>(s2, st, C, wnf);
-      if (pt > pbest) { pbest = pt; jbest = j; }
+      if (pt > pbest) { psecond = pbest; pbest = pt; }
+      else if (pt > psecond) psecond = pt;
     }
   }
   float pmax = pbest;
@@ -235,28 +235,9 @@ __device__ __noinline__ void ff_scan(const unsigned int* H, int packed, int hcw,
     return;
   }
   const float pthr = pmax - wnf * FF_BAR;
-  // Is the best candidate alone within the bar?  (lanes whose best is below the bar have no near
-  // candidate; a lane whose best is within it may have more: it counts them in a second walk)
-  int nnear = 0;
-  if (pbest >= pthr) {
-    unsigned run_cnt = pre;
-    uint32_t s2[CM];
-#pragma unroll
-    for (int c = 0; c < CM; ++c) s2[c] = sl[c];
-    unsigned pm = pmask;
-    while (pm) {
-      const int j = __ffs(pm) - 1;
-      pm &= pm - 1;
-      run_cnt += hn(lane * 8 + j);
-#pragma unroll
-      for (int c = 0; c < CM; ++c) if (c < C) s2[c] += hc(c, lane * 8 + j);
-      if (!pm && nxt >= (1 << 20)) break;
-      const int n_left = (int)run_cnt;
-      if (n_left < min_samples_leaf || n_node - n_left < min_samples_leaf) continue;
-      if (!ff_weights_ok<CM>(s2, C, w_node, min_weight_leaf)) continue;
-      if (ff_rank<CM>(s2, st, C, wnf) >= pthr) nnear += 1;
-    }
-  }
+  // Is the best candidate alone within the bar?  (a lane's best and second best tell "none", "one" or
+  // "several" of its candidates are near)
+  const int nnear = (pbest >= pthr ? 1 : 0) + (psecond >= pthr ? 1 : 0);
   const bool single = __reduce_add_sync(0xffffffffu, (unsigned)nnear) == 1u;
   // pass 2 (lanes with a near candidate): the winner's position, bins and left sums; float64 proxies only
   // when several candidates are within the bar (ties then go to the smallest position, as the
