@@ -281,6 +281,23 @@ static int ensure_x_buffer(Ctx* c, int64_t n, int64_t d, int64_t n_alloc) {
   return 0;
 }
 
+// Labels, targets and fold ids describe the rows of one staged X: a matrix with another row count makes them
+// stale (a later call must not read n rows out of a vector staged for fewer), so they are dropped with it.
+static void drop_stale_row_vectors(Ctx* c, int64_t n_new) {
+  if (c->vec_n == n_new) return;
+  if (c->ycls) { cudaFree(c->ycls); c->ycls = nullptr; c->ycls_cap = 0; }
+  if (c->yreal) { cudaFree(c->yreal); c->yreal = nullptr; c->yreal_cap = 0; }
+  if (c->fold_store) { cudaFree(c->fold_store); c->fold_store = nullptr; c->fold_cap = 0; }
+  c->fold = nullptr;
+  c->n_folds = 0;
+  c->fold_count.clear();
+  c->h_fold.clear();
+  c->h_ycls.clear();
+  c->rb_cols = 0;
+  c->tc.meta_valid = false;
+  c->vec_n = n_new;
+}
+
 static int finite_check_staged(Ctx* c, int64_t n, int64_t ldx) {
   int* dflag;
   Scratch sx(c);
@@ -316,6 +333,7 @@ static int stage_x_common(Ctx* c, const float* src, int64_t n, int64_t d, int64_
   tr.mark("copy");
   if (finite_check_staged(c, n, ldx)) return 1;
   tr.mark("check");
+  drop_stale_row_vectors(c, n);
   c->n = n; c->d = d; c->ldx = ldx;
   c->tc.x_valid = false;
   c->forest.valid = false;
@@ -371,6 +389,7 @@ int skd_stage_x_commit(skd_ctx* ctx) {
   const int64_t n = c->pend_n, d = c->pend_d;
   c->pend_n = 0;
   if (finite_check_staged(c, n, c->ldx)) return 1;
+  drop_stale_row_vectors(c, n);
   c->n = n; c->d = d;
   c->tc.x_valid = false;
   c->forest.valid = false;

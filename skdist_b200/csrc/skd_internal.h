@@ -84,6 +84,7 @@ struct Ctx {
   TcData tc;
   ForestData forest;
   int64_t ycls_cap = 0, yreal_cap = 0, fold_cap = 0;   // allocated rows of the staged vectors (reused when large enough)
+  int64_t vec_n = 0;        // row count the staged labels / targets / folds belong to (dropped when X changes it)
   // per-column feature masks staged for the next skd_logreg_fit_batch (skd_stage_column_masks)
   std::vector<uint8_t> h_fmask;
   int32_t fmask_cols = 0;

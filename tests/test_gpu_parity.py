@@ -312,6 +312,21 @@ def test_dist_randomized_search_ridge_end_to_end(eng):
     np.testing.assert_allclose(rs.predict(X[:100]), ora["best_estimator_"].predict(X[:100]), rtol=0, atol=1e-3)
 
 
+def test_row_vectors_do_not_outlive_their_matrix(eng):
+    """Targets staged for a small matrix must not be read (n rows out of a shorter vector) once a larger
+    matrix is staged: a Ridge search followed by a classification search on more rows."""
+    from sklearn.linear_model import Ridge
+    from skdist.distribute.search import DistGridSearchCV
+    from skdist_b200.datasets import make_g1_classification, make_g1_regression
+    Xr, yr = make_g1_regression(3000, 16, seed=3)
+    DistGridSearchCV(Ridge(), {"alpha": [0.1, 1.0]}, None, cv=3).fit(Xr, yr)
+    Xc, yc = make_g1_classification(7000, 16, seed=4)
+    gs = DistGridSearchCV(LogisticRegression(), {"C": [0.1, 1.0]}, None, cv=3).fit(Xc, yc)
+    assert np.isfinite(gs.cv_results_["mean_test_score"]).all()
+    with pytest.raises(Exception):          # and the stale targets are gone, not silently reused
+        eng.ridge_fit_batch(np.array([1.0]), np.array([-1], np.int32))
+
+
 def test_ovr_logreg_on_device(eng):
     from sklearn.multiclass import OneVsRestClassifier
     from skdist.distribute.multiclass import DistOneVsRestClassifier
