@@ -280,13 +280,16 @@ class _DistForestClassifier(_ScParamMixin):
                     pending = (sts, arrays)
                 local.extend(wrap(*pending))
         if world > 1:
-            import torch.distributed as dist
-            gathered = [None] * world
-            dist.all_gather_object(gathered, local)
-            ests = [None] * n_more
-            for r in range(world):
-                for i, e in zip(parallel.shard_indices(n_more, r, world), gathered[r]):
-                    ests[i] = e
+            # the trees of the other ranks arrive as raw node / value arrays in bounded pieces and are wrapped
+            # here (parallel.all_gather_trees: no pickle of the whole forest, optional rank-0-only collection)
+            def rebuild(i, depth, nodes, values):
+                t = Tree(d, np.array([self.n_classes_], dtype=np.intp), 1)
+                t.__setstate__({"max_depth": depth, "node_count": nodes.shape[0], "nodes": nodes,
+                                "values": np.ascontiguousarray(values.reshape(nodes.shape[0], 1, -1))})
+                return _finish_tree(t, tmpl, states[i], d, self.n_classes_, mf_i, self._tree_cls)
+            ests = parallel.all_gather_trees(local, n_more, rank, world, rebuild)
+            if any(e is None for e in ests):        # rank-0-only collection: this rank keeps the trees it built
+                ests = [e for e in ests if e is not None]
         else:
             ests = local
         self.estimators_ = kept + ests

@@ -145,6 +145,126 @@ def all_gather_blocks(local, n_items, rank, world, order=None, block=128, cost=N
     return full
 
 
+def _host_memory_available():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:  # pragma: no cover
+        return None
+
+
+def all_gather_trees(local, n_items, rank, world, rebuild, mode=None, piece_bytes=256 << 20):
+    """Fitted trees of a forest dealt by `shard_indices`, back on the ranks: streamed, never pickled as a whole.
+
+    The reference collects the trees on the Spark driver (ensemble.py:319: `.collect()`).  In the SPMD form
+    every rank ends with the complete forest -- but a config-4 forest (1024 trees of 372 k nodes) is 38 GB of
+    node records, and one `all_gather_object` of the local list held the list, its pickle, the byte tensor,
+    every other rank's bytes and the unpickled copies at once (~7x the forest per rank: enough to take a
+    host down).  Here a tree travels as its raw `nodes` / `values` arrays in pieces of about `piece_bytes`
+    per rank (one fixed-size all-gather per piece, sizes agreed on up front), and the receiving side rebuilds
+    the estimator with `rebuild(item_index, max_depth, nodes, values)`; peak temporary memory is
+    world x piece_bytes.
+
+    mode (default: env SKDIST_B200_FOREST_GATHER or "auto"): "all" = every rank gets every tree;
+    "rank0" = only rank 0 does (the reference's driver), the other ranks return their own trees and None for
+    the rest; "auto" = "all" unless world copies of the forest would not fit in the host memory that is
+    available (one node), then "rank0" with a warning.  Returns the list of n_items estimators."""
+    if world == 1:
+        return list(local)
+    import torch
+    import torch.distributed as dist
+
+    mode = mode or os.environ.get("SKDIST_B200_FOREST_GATHER", "auto")
+    if mode not in ("all", "rank0", "auto"):
+        raise ValueError("SKDIST_B200_FOREST_GATHER must be all, rank0 or auto")
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    idx = [shard_indices(n_items, r, world) for r in range(world)]
+    per = max(len(i) for i in idx)
+    # sizes of every tree of every rank: [node_count, nodes bytes, values bytes, max_depth]
+    meta = np.zeros((per, 4), dtype=np.int64)
+    states = []
+    for j, est in enumerate(local):
+        st = est.tree_.__getstate__()
+        nodes = np.ascontiguousarray(st["nodes"])
+        values = np.ascontiguousarray(st["values"])
+        states.append((nodes, values))
+        meta[j] = (st["node_count"], nodes.nbytes, values.nbytes, st["max_depth"])
+    mt = torch.from_numpy(meta).to(dev)
+    mall = [torch.empty_like(mt) for _ in range(world)]
+    dist.all_gather(mall, mt)
+    mall = [m.cpu().numpy() for m in mall]
+    total = int(sum(int(m[:, 1:3].sum()) for m in mall))
+    if mode == "auto":
+        avail = _host_memory_available()
+        # every rank of this node would hold the other ranks' trees on top of its own
+        need = sum(total - int(mall[r][:, 1:3].sum()) for r in range(world))
+        mode = "all"
+        if avail is not None and need > 0.6 * avail:
+            mode = "rank0"
+            if rank == 0:
+                import warnings
+                warnings.warn("forest of %.1f GB: %d copies do not fit in the %.1f GB of host memory available; "
+                              "only rank 0 collects every tree (SKDIST_B200_FOREST_GATHER=all overrides)"
+                              % (total / 1e9, world, avail / 1e9))
+        flag = torch.tensor([1 if mode == "rank0" else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)      # the ranks must agree (they sample free memory at different times)
+        mode = "rank0" if int(flag.item()) else "all"
+    node_dtype = states[0][0].dtype if states else None
+    val_shape = states[0][1].shape[1:] if states else None
+    # dtype / value shape of the records: same on every rank (taken from any rank that has a tree)
+    out = [None] * n_items
+    for j, est in enumerate(local):
+        out[idx[rank][j]] = est
+    keep = mode == "all" or rank == 0
+    j0 = 0
+    while j0 < per:
+        # trees j0 .. j1-1 of every rank in one piece: as many as fit in piece_bytes on the fullest rank
+        j1, size = j0, np.zeros(world, dtype=np.int64)
+        while j1 < per:
+            nxt = np.array([int(m[j1, 1] + m[j1, 2]) for m in mall], dtype=np.int64)
+            if j1 > j0 and (size + nxt).max() > piece_bytes:
+                break
+            size += nxt
+            j1 += 1
+        width = int(size.max())
+        buf = np.zeros(max(width, 1), dtype=np.uint8)
+        o = 0
+        for j in range(j0, min(j1, len(local))):
+            for a in states[j]:
+                b = a.view(np.uint8).reshape(-1)
+                buf[o:o + b.size] = b
+                o += b.size
+            states[j] = None                  # the local copy lives on in local[j].tree_
+        t = torch.from_numpy(buf).to(dev)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        if keep:
+            for r in range(world):
+                if r == rank:
+                    continue
+                got = outs[r].cpu().numpy()
+                o = 0
+                for j in range(j0, min(j1, len(idx[r]))):
+                    cnt, nb, vb, depth = (int(v) for v in mall[r][j])
+                    nd = _node_dtype(node_dtype)
+                    nodes = got[o:o + nb].view(nd).copy()
+                    o += nb
+                    values = got[o:o + vb].view(np.float64).copy()
+                    o += vb
+                    out[idx[r][j]] = rebuild(int(idx[r][j]), depth, nodes, values.reshape(cnt, -1))
+        del outs, t
+        j0 = j1
+    return out
+
+
+def _node_dtype(local_dtype):
+    if local_dtype is not None:
+        return local_dtype
+    from sklearn.tree._tree import NODE_DTYPE      # a rank without trees of its own
+    return NODE_DTYPE
+
+
 def broadcast_array(arr, shape, dtype, src=0):
     """Replicate a host array held by rank `src` on every rank (NCCL broadcast through
     device memory on GPUs).  Ranks other than src pass arr=None."""

@@ -53,6 +53,43 @@ def _worker(rank, world, port, out_dir):
     back = parallel.all_gather_blocks(mine.astype(np.float64) * 3.0, 301, rank, world, order, block=64)
     assert np.array_equal(back, np.arange(301) * 3.0)
     assert len(parallel.shard_blocks(5, rank, world)) in (2, 3)      # small problems still use every rank
+    # forests: the trees of the other rank arrive as raw node / value arrays in pieces (a tiny piece size
+    # forces several all-gathers), both collection modes; regressors have one "class"
+    from sklearn.ensemble import RandomForestClassifier, RandomForestRegressor
+    from sklearn.utils import check_random_state
+    from skdist.distribute.ensemble import DistRandomForestClassifier, DistRandomForestRegressor
+    from skdist_b200.distribute.ensemble import MAX_RAND_SEED, _tree_inputs
+    Xq = np.round(Xm * 8).astype(np.float32)
+    seeds = check_random_state(4).randint(MAX_RAND_SEED, size=7)
+    eng.seed_of_rand_r = {int(_tree_inputs(s_, len(ym), False)[1]): int(s_) for s_ in seeds}
+    real_gather = parallel.all_gather_trees
+    parallel.all_gather_trees = lambda *a, **k: real_gather(*a, piece_bytes=4096, **k)
+    try:
+        os.environ["SKDIST_B200_FOREST_GATHER"] = "all"
+        rf = DistRandomForestClassifier(n_estimators=7, random_state=4).fit(Xq, ym)
+        ref = RandomForestClassifier(n_estimators=7, random_state=4).fit(Xq, ym)
+        assert len(rf.estimators_) == 7
+        for a_, b_ in zip(rf.estimators_, ref.estimators_):
+            assert a_.random_state == b_.random_state
+            np.testing.assert_array_equal(a_.tree_.threshold, b_.tree_.threshold)
+            np.testing.assert_array_equal(a_.tree_.value, b_.tree_.value)
+            np.testing.assert_array_equal(a_.tree_.children_right, b_.tree_.children_right)
+        np.testing.assert_array_equal(rf.predict_proba(Xq), ref.predict_proba(Xq))
+        yr = (Xq[:, 0] * 2 + Xq[:, 1]).astype(np.float64)
+        rr = DistRandomForestRegressor(n_estimators=7, random_state=4).fit(Xq, yr)
+        rref = RandomForestRegressor(n_estimators=7, random_state=4).fit(Xq, yr)
+        np.testing.assert_allclose(rr.predict(Xq), rref.predict(Xq), rtol=1e-12)
+        os.environ["SKDIST_B200_FOREST_GATHER"] = "rank0"
+        r0 = DistRandomForestClassifier(n_estimators=7, random_state=4).fit(Xq, ym)
+        assert len(r0.estimators_) == (7 if rank == 0 else len(parallel.shard_indices(7, rank, world)))
+        if rank == 0:
+            np.testing.assert_array_equal(r0.predict_proba(Xq), ref.predict_proba(Xq))
+        os.environ.pop("SKDIST_B200_FOREST_GATHER")            # default "auto": a small forest is replicated
+        ra = DistRandomForestClassifier(n_estimators=7, random_state=4).fit(Xq, ym)
+        assert len(ra.estimators_) == 7
+    finally:
+        parallel.all_gather_trees = real_gather
+        os.environ.pop("SKDIST_B200_FOREST_GATHER", None)
     dist.destroy_process_group()
 
 
