@@ -73,6 +73,62 @@ def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, ma
     return _finish_tree(t, template_params, state, n_features, n_classes, max_features_, tree_cls)
 
 
+def _quantile_codes(X, max_bins):
+    """Opt-in histogram mode for continuous features (env SKDIST_B200_FOREST_MAX_BINS = 2 ... 256).
+
+    The exact splitter of the device path needs features with at most 256 distinct values.  Every feature
+    with more than `max_bins` distinct values is replaced by its equal-count bin code 0 .. B-1 (ties stay in
+    one bin), the forest is built on the codes -- exactly the trees scikit-learn builds on the coded matrix --
+    and `_remap_thresholds` then moves every threshold back to raw units (the midpoint between the largest
+    value of the left bin and the smallest of the right bin, scikit-learn's own rule for two adjacent values),
+    so the fitted trees route raw rows exactly as they route the coded ones.  This is the usual histogram
+    approximation (the candidate thresholds of such a feature are the B-1 bin boundaries, not every pair of
+    adjacent values): NOT bit-identical to the reference on such data, hence opt-in.
+
+    Returns (X with the coded columns, table [d x max_bins] float64 of raw thresholds after code c -- NaN
+    rows for untouched features) or (X, None) when no feature needs it."""
+    n, d = X.shape
+    table = None
+    out = X
+    for f in range(d):
+        srt = np.sort(X[:, f])
+        n_distinct = 1 + int(np.count_nonzero(srt[1:] != srt[:-1]))
+        if n_distinct <= max_bins:
+            continue
+        pos = (np.arange(1, max_bins, dtype=np.int64) * n) // max_bins
+        edges = np.unique(srt[pos])                                  # inclusive upper edges; the last bin is open
+        code = np.searchsorted(edges, X[:, f], side="left")
+        present, code = np.unique(code, return_inverse=True)         # dense codes (the top edge can be the maximum)
+        cnt = np.bincount(code, minlength=len(present))
+        end = np.cumsum(cnt)
+        hi = srt[end - 1].astype(np.float64)                         # codes are monotone in the value
+        lo = srt[end - cnt].astype(np.float64)
+        thr = hi[:-1] / 2.0 + lo[1:] / 2.0                           # SK/tree/_splitter.pyx: midpoint in float64 ...
+        thr = np.where(thr == lo[1:], hi[:-1], thr)                  # ... that falls back to the left value
+        if table is None:
+            table = np.full((d, max_bins), np.nan)
+            out = X.copy()
+        table[f, :len(thr)] = thr
+        out[:, f] = code.astype(np.float32)
+    return out, table
+
+
+def _remap_thresholds(arrays, table):
+    """Thresholds of the coded features (any cut between two codes a < b present in the node: the device
+    reports their midpoint, the random splitter a uniform draw in [a, b)) back to raw units: the boundary
+    after code floor(t), which lies in [a, b)."""
+    if "nodes" in arrays:
+        feat, thr = arrays["nodes"]["feature"], arrays["nodes"]["threshold"]
+    else:
+        feat, thr = arrays["feature"], arrays["threshold"]
+    coded = ~np.isnan(table[:, 0])
+    sel = np.flatnonzero((feat >= 0) & coded[np.maximum(feat, 0)])
+    if len(sel):
+        c = np.clip(np.floor(thr[sel]).astype(np.int64), 0, table.shape[1] - 1)
+        thr[sel] = table[feat[sel], c]
+    return arrays
+
+
 def _finish_tree(t, template_params, state, n_features, n_classes, max_features_, tree_cls):
     est = tree_cls(**template_params)
     est.set_params(random_state=int(state))
@@ -91,7 +147,10 @@ _LIMITS = """
     Limits of the device path (checked when the trees are built; `NotImplementedError` otherwise, there
     is no CPU fallback): every feature may take at most 256 distinct values (the exact splitter works on
     per-feature value histograms: data on a lattice, counts, categorical codes, quantised measurements --
-    continuous float features need a sort-based splitter that is not built), at most 16 classes, at most
+    continuous float features need a sort-based splitter that is not built; the opt-in histogram mode
+    `SKDIST_B200_FOREST_MAX_BINS=<2..256>` replaces such features by equal-count bin codes and maps the
+    thresholds back to raw units -- the trees scikit-learn builds on the coded matrix, not bit-identical to the
+    reference on the raw one), at most 16 classes, at most
     384 features, bootstrap multiplicities up to 255, no missing values, `criterion` gini / squared
     error, no `class_weight`, `max_leaf_nodes`, `sample_weight` or multi-output targets."""
 
@@ -222,9 +281,16 @@ class _DistForestClassifier(_ScParamMixin):
 
         rank, world, _ = parallel.dist_info()
         eng = get_engine()
-        parallel.stage_x_replicated(eng, X)
-        eng.stage_labels(y_enc.astype(np.int32))
-        eng.stage_folds(None, 0)
+        max_bins = int(os.environ.get("SKDIST_B200_FOREST_MAX_BINS", "0"))
+        if max_bins and not 2 <= max_bins <= 256:
+            raise ValueError("SKDIST_B200_FOREST_MAX_BINS must be between 2 and 256")
+        X_dev, bin_table = _quantile_codes(X, max_bins) if max_bins else (X, None)
+        try:
+            parallel.stage_x_replicated(eng, X_dev)
+            eng.stage_labels(y_enc.astype(np.int32))
+            eng.stage_folds(None, 0)
+        finally:
+            del X_dev
         mine = parallel.shard_indices(n_more, rank, world)
         my_states = [states[i] for i in mine]
         crit = "squared_error" if self._regression else self.criterion
@@ -251,14 +317,21 @@ class _DistForestClassifier(_ScParamMixin):
             return bootstrap_counts(sts, n, bootstrap=self.bootstrap, n_threads=host_threads)
 
         def build(counts, rs):
-            return eng.forest_fit(counts, rs, self.n_classes_, mf_i, max_depth, int(mss), int(msl),
-                                  float(min_weight_leaf), float(self.min_impurity_decrease), splitter=self._splitter,
-                                  y_regression=y_reg)
+            try:
+                return eng.forest_fit(counts, rs, self.n_classes_, mf_i, max_depth, int(mss), int(msl),
+                                      float(min_weight_leaf), float(self.min_impurity_decrease),
+                                      splitter=self._splitter, y_regression=y_reg)
+            except NotImplementedError as e:
+                if "distinct values" in str(e) and not max_bins:
+                    raise NotImplementedError(str(e) + "; SKDIST_B200_FOREST_MAX_BINS=256 selects the histogram "
+                                              "approximation (equal-count bins, see the class docstring)") from None
+                raise
 
         def wrap(sts, arrays):
             with ThreadPoolExecutor(max_workers=min(32, max(8, host_threads))) as ex:   # strided field copies release the GIL
-                return list(ex.map(lambda sa: _make_sklearn_tree(tmpl, sa[0], sa[1], d, self.n_classes_, mf_i,
-                                                                 self._tree_cls), zip(sts, arrays)))
+                return list(ex.map(lambda sa: _make_sklearn_tree(
+                    tmpl, sa[0], sa[1] if bin_table is None else _remap_thresholds(sa[1], bin_table), d,
+                    self.n_classes_, mf_i, self._tree_cls), zip(sts, arrays)))
 
         local = []
         self.device_seconds_ = 0.0

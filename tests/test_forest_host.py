@@ -139,3 +139,70 @@ def test_warm_start_adds_the_trees_a_cold_fit_would_have(fake_engine):
     with pytest.raises(ValueError):
         warm.set_params(n_estimators=5)
         warm.fit(X, y)
+
+
+@pytest.mark.parametrize("kind", ["rf", "et"])
+def test_histogram_mode_for_continuous_features(fake_engine, monkeypatch, kind):
+    """SKDIST_B200_FOREST_MAX_BINS: features with more distinct values than the bins are replaced by equal-count
+    bin codes; the fitted trees are scikit-learn's trees on the coded matrix with the thresholds moved back to
+    raw units, so they route raw rows exactly as the coded trees route coded rows -- training rows and new
+    rows alike (a new row's code is found with the same edges)."""
+    from sklearn.ensemble import ExtraTreesClassifier, RandomForestClassifier
+    from sklearn.utils import check_random_state
+    from skdist.distribute.ensemble import DistExtraTreesClassifier, DistRandomForestClassifier
+    from skdist_b200.distribute.ensemble import MAX_RAND_SEED, _quantile_codes, _tree_inputs
+    from skdist_b200.engine import get_engine
+    rng = np.random.default_rng(5)
+    n, d, bins = 900, 5, 16
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X[:, 3] = rng.integers(0, 6, n)                      # a low-cardinality feature stays as it is
+    X[::7, 1] = X[0, 1]                                  # heavy ties inside a continuous feature
+    y = ((X[:, 0] + 0.5 * X[:, 1] * X[:, 2] + 0.3 * X[:, 3]) > 0.4).astype(int)
+    Xc, table = _quantile_codes(X, bins)
+    assert np.isnan(table[3]).all() and not np.isnan(table[0, 0])
+    assert np.array_equal(Xc[:, 3], X[:, 3]) and Xc[:, 0].max() <= bins - 1
+    for f in (0, 1, 2, 4):                               # the raw thresholds reproduce the coding: x <= thr[c]  <=>  code <= c
+        nb = int(Xc[:, f].max())
+        for c in range(nb):
+            assert np.array_equal(X[:, f] <= table[f, c], Xc[:, f] <= c)
+    n_trees, rs = 5, 3
+    states = check_random_state(rs).randint(MAX_RAND_SEED, size=n_trees)
+    get_engine().seed_of_rand_r = {int(_tree_inputs(s, n, False)[1]): int(s) for s in states}
+    monkeypatch.setenv("SKDIST_B200_FOREST_MAX_BINS", str(bins))
+    if kind == "rf":
+        ours = DistRandomForestClassifier(n_estimators=n_trees, random_state=rs).fit(X, y)
+        ref = RandomForestClassifier(n_estimators=n_trees, random_state=rs).fit(Xc, y)
+    else:
+        ours = DistExtraTreesClassifier(n_estimators=n_trees, random_state=rs).fit(X, y)
+        ref = ExtraTreesClassifier(n_estimators=n_trees, random_state=rs).fit(Xc, y)
+    for a, b in zip(ours.estimators_, ref.estimators_):
+        np.testing.assert_array_equal(a.tree_.feature, b.tree_.feature)
+        np.testing.assert_array_equal(a.tree_.children_left, b.tree_.children_left)
+        np.testing.assert_array_equal(a.tree_.value, b.tree_.value)
+        on3 = a.tree_.feature == 3
+        np.testing.assert_array_equal(a.tree_.threshold[on3], b.tree_.threshold[on3])
+    np.testing.assert_array_equal(ours.predict_proba(X), ref.predict_proba(Xc))
+    # new rows: coded with the training edges (searchsorted on the raw thresholds), same routing
+    Xn = rng.standard_normal((300, d)).astype(np.float32)
+    Xn[:, 3] = rng.integers(0, 6, 300)
+    Xnc = Xn.copy()
+    for f in (0, 1, 2, 4):
+        thr = table[f][~np.isnan(table[f])]
+        Xnc[:, f] = np.searchsorted(thr, Xn[:, f].astype(np.float64), side="left")
+    np.testing.assert_array_equal(ours.predict_proba(Xn), ref.predict_proba(Xnc))
+    assert ours.score(X, y) > 0.9
+
+
+def test_remap_thresholds_on_node_records():
+    """The library hands back scikit-learn node records (one structured array): the remap writes through the
+    field views and leaves leaves / uncoded features alone."""
+    from sklearn.tree._tree import NODE_DTYPE
+    from skdist_b200.distribute.ensemble import _remap_thresholds
+    nodes = np.zeros(6, dtype=NODE_DTYPE)
+    nodes["feature"] = [0, 2, -2, 0, 1, -2]
+    nodes["threshold"] = [1.5, 3.0, -2.0, 0.25, 7.5, -2.0]
+    table = np.full((3, 8), np.nan)
+    table[0, :4] = [-0.7, -0.1, 0.4, 1.9]
+    table[2, :5] = [10.0, 20.0, 30.0, 40.0, 50.0]
+    out = _remap_thresholds({"nodes": nodes, "left": nodes["left_child"]}, table)
+    np.testing.assert_array_equal(out["nodes"]["threshold"], [-0.1, 40.0, -2.0, -0.7, 7.5, -2.0])
