@@ -130,3 +130,31 @@ def test_two_rank_grid_search_matches_single_process(tmp_path):
         engine.set_engine_factory(None)
     np.testing.assert_array_equal(gs.cv_results_["mean_test_score"], r0["mean"])
     np.testing.assert_array_equal(gs.best_estimator_.coef_, r0["coef"])
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_block_dealing_is_a_partition_and_balances_rounds(world):
+    """The headline search (512 C x 5 folds, fold-major order) dealt over `world` ranks: every column goes to
+    exactly one rank, every rank gets whole 128-column blocks of one fold, and with the longest-first deal a
+    rank that takes one block more than the others gets the blocks that stop early."""
+    from skdist_b200 import parallel
+    n_c, n_f = 512, 5
+    Cs = np.logspace(-4, 4, n_c)
+    cols = np.arange(n_c * n_f)
+    order = np.concatenate([cols[cols % n_f == f] for f in range(n_f)])     # fold-major: what the search passes
+    cost = np.repeat(parallel.logreg_column_cost(Cs), n_f)                   # column = candidate * n_f + fold
+    parts = [parallel.shard_blocks(len(cols), r, world, order, 128, cost) for r in range(world)]
+    assert np.array_equal(np.sort(np.concatenate(parts)), cols)
+    loads, blocks = [], []
+    for p in parts:
+        assert len(p) % 128 == 0
+        blk = p.reshape(-1, 128)
+        assert all(len(set(b % n_f)) == 1 for b in blk)                      # one fold per block
+        blocks.append(len(blk))
+        loads.append(sum(cost[b].max() for b in blk))                        # a block runs as long as its slowest column
+    assert max(blocks) - min(blocks) <= 1
+    plain = [parallel.shard_blocks(len(cols), r, world, order, 128) for r in range(world)]
+    plain_load = max(sum(cost[b].max() for b in p.reshape(-1, 128)) for p in plain)
+    assert max(loads) <= plain_load + 1e-12                                   # never worse than round-robin
+    if world == 8:              # 20 blocks over 8 ranks: the third block of a rank is one that stops early
+        assert plain_load == pytest.approx(3.0) and max(loads) < 2.7
