@@ -210,9 +210,7 @@ def all_gather_trees(local, n_items, rank, world, rebuild, mode=None, piece_byte
         flag = torch.tensor([1 if mode == "rank0" else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MAX)      # the ranks must agree (they sample free memory at different times)
         mode = "rank0" if int(flag.item()) else "all"
-    node_dtype = states[0][0].dtype if states else None
-    val_shape = states[0][1].shape[1:] if states else None
-    # dtype / value shape of the records: same on every rank (taken from any rank that has a tree)
+    node_dtype = states[0][0].dtype if states else None      # scikit-learn's NODE_DTYPE: the same on every rank
     out = [None] * n_items
     for j, est in enumerate(local):
         out[idx[rank][j]] = est
