@@ -237,6 +237,7 @@ def run(a, ClockSampler, peaks):
             est = DistOneVsRestClassifier(SGDClassifier(random_state=0), None).fit(X, y)
         elif a.config == 4:
             from skdist.distribute.ensemble import DistRandomForestClassifier
+            est = None          # a fitted config-4 forest is 38 GB of node records: release it before the next fit
             est = DistRandomForestClassifier(n_estimators=z["trees"], random_state=0).fit(X, y)
         else:
             from scipy.stats import loguniform
