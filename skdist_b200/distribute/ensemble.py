@@ -246,6 +246,7 @@ class _DistForestClassifier(_ScParamMixin):
             raise NotImplementedError("multi-output forests have no device path")
         n, d = X.shape
         self.n_features_in_ = d
+        self.n_features_ = d                                           # ref :210 (the attribute's pre-1.0 name)
         self.n_outputs_ = 1
         if self._regression:
             y_reg = np.ascontiguousarray(y, dtype=np.float64)          # SK/ensemble/_forest.py: y = DOUBLE
