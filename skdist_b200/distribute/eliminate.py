@@ -16,6 +16,7 @@ Base estimator with a device path: ``LogisticRegression(solver="lbfgs")`` (binar
 scoring=None / "accuracy" / "roc_auc".  Anything else raises NotImplementedError (no CPU fallback).
 """
 import numpy as np
+from sklearn.utils.metaestimators import available_if
 from sklearn.base import BaseEstimator, ClassifierMixin, is_classifier
 from sklearn.linear_model import LogisticRegression
 from sklearn.model_selection import check_cv
@@ -181,6 +182,11 @@ class DistFeatureEliminator(_ScParamMixin, ClassifierMixin, BaseEstimator):
 
     def decision_function(self, X):
         return self.best_estimator_.decision_function(self._apply_mask(X))
+
+    # ref eliminate.py:271-275: present only when the estimator has it (if_delegate_has_method)
+    @available_if(lambda self: hasattr(getattr(self, "best_estimator_", None), "transform"))
+    def transform(self, X):
+        return self.best_estimator_.transform(self._apply_mask(X))
 
     def score(self, X, y):
         return self.best_estimator_.score(self._apply_mask(X), y)

@@ -26,6 +26,7 @@ from collections import defaultdict
 from functools import partial
 
 import numpy as np
+from sklearn.utils.metaestimators import available_if
 from numpy.ma import MaskedArray
 from scipy.stats import rankdata
 from sklearn.base import BaseEstimator, is_classifier
@@ -409,6 +410,15 @@ class DistMultiModelSearch(_ScParamMixin, BaseEstimator):
 
     def decision_function(self, X):
         return self._delegate("decision_function", X)
+
+    # ref search.py:895-903: present only when the (best) estimator has them (if_delegate_has_method)
+    @available_if(lambda self: hasattr(getattr(self, "best_estimator_", None), "transform"))
+    def transform(self, X):
+        return self._delegate("transform", X)
+
+    @available_if(lambda self: hasattr(getattr(self, "best_estimator_", None), "inverse_transform"))
+    def inverse_transform(self, Xt):
+        return self._delegate("inverse_transform", Xt)
 
     @property
     def classes_(self):
