@@ -13,7 +13,7 @@ import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
-from sklearn.ensemble import (ExtraTreesClassifier, ExtraTreesRegressor, RandomForestClassifier,
+from sklearn.ensemble import (ExtraTreesClassifier, ExtraTreesRegressor, RandomForestClassifier, RandomTreesEmbedding,
                               RandomForestRegressor)
 from sklearn.tree import (DecisionTreeClassifier, DecisionTreeRegressor, ExtraTreeClassifier,
                           ExtraTreeRegressor)
@@ -27,7 +27,7 @@ from .base import _parse_partitions, _ScParamMixin
 from .validation import _check_estimator
 
 __all__ = ["DistRandomForestClassifier", "DistExtraTreesClassifier", "DistRandomForestRegressor",
-           "DistExtraTreesRegressor"]
+           "DistExtraTreesRegressor", "DistRandomTreesEmbedding"]
 
 MAX_RAND_SEED = np.iinfo(np.int32).max     # ref ensemble.py:38
 RAND_R_MAX = 2147483647                    # SK/tree/_utils.pxd
@@ -468,3 +468,56 @@ class DistExtraTreesRegressor(_DistForestRegressor, ExtraTreesRegressor):
         self._init_reg(sc, partitions, n_estimators, criterion, max_depth, min_samples_split, min_samples_leaf,
                        min_weight_fraction_leaf, max_features, max_leaf_nodes, min_impurity_decrease,
                        min_impurity_split, bootstrap, oob_score, n_jobs, random_state, verbose, warm_start)
+
+
+class DistRandomTreesEmbedding(_DistForestRegressor, RandomTreesEmbedding):
+    __doc__ = """Same as sklearn `RandomTreesEmbedding` with every tree built on a B200: totally random trees
+    (`ExtraTreeRegressor`, one drawn feature per node, uniformly drawn threshold) fitted on uniform random
+    targets, then the one-hot code of the leaf every row lands in.  Constructor and `fit` / `fit_transform` /
+    `transform` mirror ref ensemble.py:619-708 (``sc`` is the FIRST positional argument).  With one feature
+    drawn per node the split does not depend on the criterion, so the trees -- and the embedding -- are
+    scikit-learn's bit for bit.""" + _LIMITS
+
+    _splitter = 1
+    _tree_cls = ExtraTreeRegressor
+    criterion = "squared_error"        # ref :633 ("mse")
+    max_features = 1                   # ref :634
+
+    def __init__(self, sc=None, partitions="auto", n_estimators=100, max_depth=5, min_samples_split=2,
+                 min_samples_leaf=1, min_weight_fraction_leaf=0.0, max_leaf_nodes=None, min_impurity_decrease=0.0,
+                 min_impurity_split=None, sparse_output=True, n_jobs=None, random_state=None, verbose=0,
+                 warm_start=False):
+        self._init_reg(sc, partitions, n_estimators, "squared_error", max_depth, min_samples_split, min_samples_leaf,
+                       min_weight_fraction_leaf, 1, max_leaf_nodes, min_impurity_decrease, min_impurity_split,
+                       False, False, n_jobs, random_state, verbose, warm_start)
+        # class attributes in the reference, not constructor parameters
+        del self.criterion, self.max_features, self.bootstrap, self.oob_score
+        self.sparse_output = sparse_output
+
+    bootstrap = False
+    oob_score = False
+
+    @classmethod
+    def _get_param_names(cls):
+        return sorted(["sc", "partitions", "n_estimators", "max_depth", "min_samples_split", "min_samples_leaf",
+                       "min_weight_fraction_leaf", "max_leaf_nodes", "min_impurity_decrease", "min_impurity_split",
+                       "sparse_output", "n_jobs", "random_state", "verbose", "warm_start"])
+
+    def _set_oob_score(self, X, y):
+        raise NotImplementedError("OOB score not supported by tree embedding")      # ref :685-686
+
+    def fit(self, X, y=None, sample_weight=None):
+        self.fit_transform(X, y, sample_weight=sample_weight)                        # ref :688-691
+        return self
+
+    def fit_transform(self, X, y=None, sample_weight=None):
+        """ref :693-710: uniform random targets from `random_state`, the forest fit, one-hot of the leaves."""
+        from sklearn.preprocessing import OneHotEncoder
+        X = np.ascontiguousarray(X, dtype=np.float32)
+        rnd = check_random_state(self.random_state)
+        y = rnd.uniform(size=X.shape[0])
+        _DistForestClassifier.fit(self, X, y, sample_weight=sample_weight)
+        self.one_hot_encoder_ = OneHotEncoder(sparse_output=self.sparse_output)
+        out = self.one_hot_encoder_.fit_transform(self.apply(X))
+        self._n_features_out = out.shape[1]
+        return out

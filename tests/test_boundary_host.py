@@ -13,7 +13,7 @@ CLASSES = {
     "search": ["DistGridSearchCV", "DistRandomizedSearchCV", "DistMultiModelSearch"],
     "multiclass": ["DistOneVsRestClassifier", "DistOneVsOneClassifier"],
     "ensemble": ["DistRandomForestClassifier", "DistRandomForestRegressor", "DistExtraTreesClassifier",
-                 "DistExtraTreesRegressor"],
+                 "DistExtraTreesRegressor", "DistRandomTreesEmbedding"],
     "eliminate": ["DistFeatureEliminator"],
 }
 # The reference's one-vs-rest / one-vs-one constructors end in **kwargs, forwarded to scikit-learn's

@@ -206,3 +206,33 @@ def test_remap_thresholds_on_node_records():
     table[2, :5] = [10.0, 20.0, 30.0, 40.0, 50.0]
     out = _remap_thresholds({"nodes": nodes, "left": nodes["left_child"]}, table)
     np.testing.assert_array_equal(out["nodes"]["threshold"], [-0.1, 40.0, -2.0, -0.7, 7.5, -2.0])
+
+
+def test_random_trees_embedding_matches_sklearn_and_the_reference_test(fake_engine):
+    """DistRandomTreesEmbedding (ref ensemble.py:619-708): the reference's own test case
+    (skdist/distribute/tests/test_ensemble.py:61-66: shape (3, 30)) and scikit-learn's RandomTreesEmbedding with the
+    same random_state on a larger lattice, leaf for leaf."""
+    from sklearn.base import clone
+    from sklearn.ensemble import RandomTreesEmbedding
+    from sklearn.utils import check_random_state
+    from skdist.distribute.ensemble import DistRandomTreesEmbedding
+    from skdist_b200.engine import get_engine
+
+    def seeds(rs, n_trees, n):
+        st = check_random_state(rs).randint(MAX_RAND_SEED, size=n_trees)
+        get_engine().seed_of_rand_r = {int(_tree_inputs(s, n, False)[1]): int(s) for s in st}
+
+    X = np.array([[0, 1, 0, 1], [0, 0, 0, 1], [1, 0, 1, 0]])
+    seeds(5, 10, 3)
+    rte = DistRandomTreesEmbedding(n_estimators=10, random_state=5)
+    rte.fit(X, y=None)
+    assert rte.transform(X).shape == (3, 30)
+    Xl, _ = lattice(600, 7, 4)
+    seeds(11, 6, 600)
+    ours = DistRandomTreesEmbedding(None, "auto", 6, max_depth=4, random_state=11)
+    got = ours.fit_transform(Xl)
+    ref = RandomTreesEmbedding(n_estimators=6, max_depth=4, random_state=11)
+    want = ref.fit_transform(Xl)
+    assert got.shape == want.shape and (got != want).nnz == 0
+    assert (ours.transform(Xl[:50]) != ref.transform(Xl[:50])).nnz == 0
+    assert clone(ours).get_params()["max_depth"] == 4 and not hasattr(ours, "sc")

@@ -25,3 +25,17 @@ def test_histogram_mode_on_device(monkeypatch):
         np.testing.assert_array_equal(a.tree_.children_right, b.tree_.children_right)
         np.testing.assert_array_equal(a.tree_.value, b.tree_.value)
     np.testing.assert_array_equal(ours.predict_proba(X), ref.predict_proba(Xc))
+
+
+def test_random_trees_embedding_on_device():
+    """DistRandomTreesEmbedding: totally random regression trees (one drawn feature per node) on uniform random
+    targets -- the leaves every row lands in are scikit-learn's."""
+    from sklearn.ensemble import RandomTreesEmbedding
+    from skdist.distribute.ensemble import DistRandomTreesEmbedding
+    rng = np.random.default_rng(2)
+    X = rng.integers(0, 32, size=(5000, 10)).astype(np.float32)
+    ours = DistRandomTreesEmbedding(n_estimators=8, random_state=3)
+    got = ours.fit_transform(X)
+    ref = RandomTreesEmbedding(n_estimators=8, random_state=3)
+    want = ref.fit_transform(X)
+    assert got.shape == want.shape and (got != want).nnz == 0
