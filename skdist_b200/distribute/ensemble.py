@@ -27,7 +27,7 @@ from .base import _parse_partitions, _ScParamMixin
 from .validation import _check_estimator
 
 __all__ = ["DistRandomForestClassifier", "DistExtraTreesClassifier", "DistRandomForestRegressor",
-           "DistExtraTreesRegressor", "DistRandomTreesEmbedding"]
+           "DistExtraTreesRegressor", "DistRandomTreesEmbedding", "get_single_oof", "get_oof"]
 
 MAX_RAND_SEED = np.iinfo(np.int32).max     # ref ensemble.py:38
 RAND_R_MAX = 2147483647                    # SK/tree/_utils.pxd
@@ -71,6 +71,28 @@ def _make_sklearn_tree(template_params, state, arrays, n_features, n_classes, ma
     t.__setstate__({"max_depth": int(arrays["max_depth"]), "node_count": m, "nodes": nodes,
                     "values": np.ascontiguousarray(arrays["value"].reshape(m, 1, n_classes))})
     return _finish_tree(t, template_params, state, n_features, n_classes, max_features_, tree_cls)
+
+
+def _rows(X, idx):
+    return X.iloc[idx] if hasattr(X, "iloc") else X[idx]
+
+
+def get_single_oof(clf, X, y, train_index, test_index):
+    """Out-of-fold probabilities of one split (ref ensemble.py:112-127): fit on the train rows, `predict_proba`
+    on the test rows; `clf` is any classifier -- a Dist* forest fits on the device."""
+    clf.fit(_rows(X, train_index), y[train_index])
+    return test_index, clf.predict_proba(_rows(X, test_index))
+
+
+def get_oof(clf, X, y, n_splits=5):
+    """Out-of-fold probabilities over an unshuffled KFold, then a fit on everything (ref ensemble.py:130-151).
+    Returns (clf fitted on all rows, [n, n_classes] out-of-fold probabilities)."""
+    from sklearn.model_selection import KFold
+    oof = np.zeros((y.shape[0], len(np.unique(y))))
+    for train_index, test_index in KFold(n_splits=n_splits).split(X):
+        _, oof[test_index] = get_single_oof(clf, X, y, train_index, test_index)
+    clf.fit(X, y)
+    return clf, oof
 
 
 def _quantile_codes(X, max_bins):

@@ -236,3 +236,18 @@ def test_random_trees_embedding_matches_sklearn_and_the_reference_test(fake_engi
     assert got.shape == want.shape and (got != want).nnz == 0
     assert (ours.transform(Xl[:50]) != ref.transform(Xl[:50])).nnz == 0
     assert clone(ours).get_params()["max_depth"] == 4 and not hasattr(ours, "sc")
+
+
+def test_out_of_fold_helpers():
+    """get_oof / get_single_oof (ref ensemble.py:112-151) against the reference's own functions."""
+    from sklearn.linear_model import LogisticRegression
+    from skdist.distribute.ensemble import get_oof, get_single_oof
+    X, y = lattice(300, 4, 6)
+    clf, oof = get_oof(LogisticRegression(), X, y, n_splits=3)
+    assert oof.shape == (300, 2) and np.allclose(oof.sum(1), 1.0) and hasattr(clf, "coef_")
+    idx, p = get_single_oof(LogisticRegression(), X, y, np.arange(100, 300), np.arange(100))
+    np.testing.assert_allclose(p, oof[:100], rtol=1e-12)
+    if refshim.available():
+        ref = refshim.load_module("skdist.distribute.ensemble")
+        _, want = ref.get_oof(LogisticRegression(), X, y, n_splits=3)
+        np.testing.assert_array_equal(oof, want)
