@@ -233,7 +233,8 @@ class DistOneVsRestClassifier(_ScParamMixin, OneVsRestClassifier):
 
 
 class DistOneVsOneClassifier(_ScParamMixin, OneVsOneClassifier):
-    """One-vs-one with all class pairs fitted as one batched GPU solve.
+    """One-vs-one: LogisticRegression pairs as one batched GPU solve (row-masked columns), SGDClassifier pairs as
+    one exact-order device fit per pair on the pair's rows.
     Constructor mirrors ref multiclass.py:382-386 (``sc`` is the 2nd positional argument)."""
 
     def __init__(self, estimator, sc=None, partitions="auto", verbose=False, n_jobs=None):
@@ -260,10 +261,12 @@ class DistOneVsOneClassifier(_ScParamMixin, OneVsOneClassifier):
         pairs = [(i, j) for i in range(K) for j in range(i + 1, K)]      # ref :410-415 (same order)
         _parse_partitions(self.partitions, len(pairs))
         base = self.estimator
+        if type(base) is SGDClassifier:
+            return self._fit_sgd_pairs(X_arr, y_arr, pairs)
         if type(base) is not LogisticRegression:
             raise NotImplementedError(
-                "%s has no one-vs-one device path; supported base estimator: LogisticRegression(solver='lbfgs')."
-                "  (No CPU fallback by design.)" % type(base).__name__)
+                "%s has no one-vs-one device path; supported base estimators: LogisticRegression(solver='lbfgs'), "
+                "SGDClassifier.  (No CPU fallback by design.)" % type(base).__name__)
         from .logreg_family import _check_logreg
         p = _check_logreg(_clone(base))
         ycls = np.searchsorted(self.classes_, y_arr).astype(np.int32)
@@ -284,9 +287,43 @@ class DistOneVsOneClassifier(_ScParamMixin, OneVsOneClassifier):
         self.estimators_ = tuple(
             _binary_estimator(make, full[k][:d + 1], d, X_arr.dtype, n_iter_=np.array([int(full[k][-1])], dtype=np.int32))
             for k in range(len(pairs)))
+        return self._finish(d)
+
+    def _finish(self, d):
         self.pairwise_indices_ = None                                    # ref :441 (non-pairwise estimators)
         self.n_features_in_ = d
         self.__dict__.pop("sc", None)                                                      # ref :472
         if hasattr(self.estimator, "sc"):
             del self.estimator.sc
         return self
+
+    def _fit_sgd_pairs(self, X_arr, y_arr, pairs):
+        """SGD base estimator: `_fit_ovo_binary` (ref multiclass.py:155-173) trains pair (i, j) on the rows of the
+        two classes only, and SGD walks ITS OWN shuffled order of those rows -- so a pair is not a masked column of
+        the shared matrix (as it is for the full-batch lbfgs fit above) but one exact-order SGD fit on `X[cond]`:
+        the pair's rows are staged (the row gather the reference does too) and the one-vs-rest SGD engine fits
+        the single label column `y == classes_[j]`; pairs are dealt over the ranks."""
+        base = self.estimator
+        n, d = X_arr.shape
+        Xf = np.ascontiguousarray(X_arr, dtype=np.float32)
+        ycls = np.searchsorted(self.classes_, y_arr).astype(np.int32)
+        rank, world, _ = parallel.dist_info()
+        eng = get_engine()
+        mine = parallel.shard_indices(len(pairs), rank, world)
+        packed = np.zeros((len(mine), d + 3))
+        for r, k in enumerate(mine):
+            i, j = pairs[k]
+            cond = (ycls == i) | (ycls == j)
+            eng.stage_x(Xf[cond])                                        # this rank's pair only: no collective
+            eng.stage_labels((ycls[cond] == j).astype(np.int32))         # y_binary: class i -> 0, class j -> 1 (ref :159-161)
+            eng.stage_folds(None, 0)
+            res = eng.sgd_fit_batch(base, np.array([1], dtype=np.int32))
+            packed[r, :d + 1] = res["coef"][0]
+            packed[r, d + 1] = res["n_iter"][0]
+            packed[r, d + 2] = res["t"][0]
+        full = parallel.all_gather_columns(packed, len(pairs), rank, world)
+        make = _Cloner(base)
+        self.estimators_ = tuple(
+            _binary_estimator(make, full[k][:d + 1], d, X_arr.dtype, n_iter_=int(full[k][d + 1]), t_=float(full[k][d + 2]))
+            for k in range(len(pairs)))
+        return self._finish(d)

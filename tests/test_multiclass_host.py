@@ -166,3 +166,24 @@ def test_ovr_max_negatives_and_multilabel_host(fake_engine):
         np.testing.assert_array_equal(a.coef_, b.coef_)
     with pytest.raises(NotImplementedError):
         DistOneVsRestClassifier(SGDClassifier(), None, max_negatives=100).fit(X, y)
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_ovo_sgd_matches_sklearn(fake_engine):
+    """DistOneVsOneClassifier(SGDClassifier): one exact-order fit per class pair on the pair's rows (ref
+    `_fit_ovo_binary`, multiclass.py:155-173) -- the estimators scikit-learn's OneVsOneClassifier fits."""
+    from sklearn.linear_model import SGDClassifier
+    from sklearn.multiclass import OneVsOneClassifier
+    from skdist.distribute.multiclass import DistOneVsOneClassifier
+    from skdist_b200.datasets import make_multiclass
+    X, y = make_multiclass(1200, 9, 4, seed=6)
+    labels = np.array(["a", "b", "c", "d"])[y]                       # string labels: pairs are formed on class indices
+    ours = DistOneVsOneClassifier(SGDClassifier(random_state=0), None).fit(X, labels)
+    ref = OneVsOneClassifier(SGDClassifier(random_state=0)).fit(X, labels)
+    assert len(ours.estimators_) == 6
+    for a, b in zip(ours.estimators_, ref.estimators_):
+        np.testing.assert_array_equal(a.coef_, b.coef_)
+        np.testing.assert_array_equal(a.intercept_, b.intercept_)
+        assert a.n_iter_ == b.n_iter_ and a.t_ == b.t_
+    np.testing.assert_array_equal(ours.predict(X), ref.predict(X))
+    np.testing.assert_array_equal(ours.decision_function(X), ref.decision_function(X))

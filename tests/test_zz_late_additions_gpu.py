@@ -1,5 +1,6 @@
-"""Opt-in histogram mode of the forests on the device (runs last: it only adds a host transform in front of
-the device path the other forest tests cover)."""
+"""Device runs of the host-side additions made after the last GPU session of round 2 (histogram mode of the
+forests, DistRandomTreesEmbedding, one-vs-one with an SGD base): each only adds host logic in front of a device
+path the earlier test files cover, and each has a CPU test on the engine double.  Named to run last."""
 import numpy as np
 import pytest
 
@@ -39,3 +40,21 @@ def test_random_trees_embedding_on_device():
     ref = RandomTreesEmbedding(n_estimators=8, random_state=3)
     want = ref.fit_transform(X)
     assert got.shape == want.shape and (got != want).nnz == 0
+
+
+@pytest.mark.filterwarnings("ignore")
+def test_ovo_sgd_on_device():
+    """DistOneVsOneClassifier(SGDClassifier): one exact-order SGD fit per class pair on the pair's rows, through
+    the one-vs-rest SGD engine (warp-per-column kernel for the small pairs, tensor-core screening from 4096 rows)."""
+    from sklearn.linear_model import SGDClassifier
+    from sklearn.multiclass import OneVsOneClassifier
+    from skdist.distribute.multiclass import DistOneVsOneClassifier
+    from skdist_b200.datasets import make_multiclass
+    for n in (3000, 15000):
+        X, y = make_multiclass(n, 20, 3, seed=n % 13)
+        ours = DistOneVsOneClassifier(SGDClassifier(random_state=0), None).fit(X, y)
+        ref = OneVsOneClassifier(SGDClassifier(random_state=0)).fit(X, y)
+        for a, b in zip(ours.estimators_, ref.estimators_):
+            np.testing.assert_array_equal(a.coef_, b.coef_)
+            np.testing.assert_array_equal(a.intercept_, b.intercept_)
+            assert a.n_iter_ == b.n_iter_
